@@ -1,0 +1,247 @@
+/*
+ * pdune_b200.h -- C ABI of the B200-native batched putting-dune simulator.
+ *
+ * The reference (google/putting-dune) has no FFI: its boundary for this path
+ * is three synchronous Python protocols.  Every entry
+ * point below names the reference interface it replaces (paths relative to
+ * putting_dune/ in the reference).  Signatures use only plain pointers and
+ * sizes; "device pointer" means a CUDA global-memory address (the Python host
+ * passes torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).
+ *
+ * Conventions
+ *   - All calls return PD_OK (0) or a negative pd_status; pd_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - No call allocates device memory; the caller owns every buffer.  Calls
+ *     ending in _host take HOST pointers for the per-step inputs/outputs and
+ *     copy them inside the call through caller-provided device staging.
+ *   - Calls are asynchronous on `stream` unless documented otherwise; they are
+ *     re-entrant across states, not thread-safe on one state.
+ *   - Data-dependent failures that the reference raises per object
+ *     (AssertionError on negative rates, graphene.py:258) are reported per
+ *     env in pd_state.status (PD_ENV_* bits), never by aborting the batch.
+ *
+ * Random draws: Philox4x32-10, key = (seed lo, seed hi), counter =
+ *   (global env id, seq, slot, stream).  See DESIGN.md "Random streams"; the
+ *   same function in NumPy (oracle/pdune_oracle.py) lets identical draws be
+ *   injected into the unmodified reference.
+ */
+#ifndef PDUNE_B200_H_
+#define PDUNE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDUNE_B200_ABI_VERSION 1
+
+typedef enum pd_status {
+  PD_OK = 0,
+  PD_ERR_INVALID_ARGUMENT = -1,
+  PD_ERR_CUDA = -2,
+  PD_ERR_UNSUPPORTED = -3,
+  PD_ERR_NO_DEVICE = -4
+} pd_status;
+
+/* pd_state.status bits (per env). */
+#define PD_ENV_OK 0u
+#define PD_ENV_BAD_RATE 1u      /* rate < 0 or NaN (graphene.py:258 assert)   */
+#define PD_ENV_LOG_OVERFLOW 2u  /* more transitions than the event log holds */
+#define PD_ENV_NOT_RESET 4u     /* stepped before reset (simulator.py:224)    */
+
+/* Rate functions (the RateFunction / CanonicalRatePredictionFn seam,
+ * graphene.py:52-78). */
+typedef enum pd_rate_fn {
+  PD_RATE_SIMPLE = 0,   /* graphene.py:133-166 simple_canonical_rate_function */
+  PD_RATE_PRIOR = 1,    /* graphene.py:169-229 HumanPriorRatePredictor.predict */
+  PD_RATE_LEARNED = 2,  /* rate_learning/learn_rates.py:925-972 predict        */
+  PD_RATE_CONSTANT = 3  /* fixed rates: the seam the reference's own tests     */
+                        /* mock (simulator_test.py:139-168, graphene_test.py)  */
+} pd_rate_fn;
+
+/* Philox stream ids (counter word 3). */
+#define PD_STREAM_KMC 0u
+#define PD_STREAM_RESET 1u
+#define PD_STREAM_RENDER_A 2u
+#define PD_STREAM_RENDER_B 3u
+#define PD_STREAM_JITTER 4u
+#define PD_STREAM_GOAL 5u
+#define PD_STREAM_AGENT 6u
+
+/* Shared lattice (graphene.py:464-559): device pointers, env-independent. */
+typedef struct pd_lattice {
+  int32_t n_cols;        /* grid_columns (reference default 50)              */
+  int32_t n_sites;       /* 1881 for 50 columns                              */
+  const double* base_xy; /* [n_sites][2] (G*1.42 - mean), graphene.py:537-543 */
+  const int32_t* nbr;    /* [n_sites][4] 3-NN site ids + pad, geometry.py:93  */
+} pd_lattice;
+
+/* Per-env simulator state, struct of arrays, all device pointers of length
+ * n_envs (x the inner extent shown).  This is everything that
+ * PuttingDuneSimulator + PristineSingleDopedGraphene hold between calls
+ * (SURVEY.md appendix A.1). */
+typedef struct pd_state {
+  int64_t n_envs;
+  uint64_t seed;          /* Philox key                                        */
+  uint32_t env_offset;    /* global id of local env 0 (multi-GPU sharding)     */
+  uint32_t reserved_;
+  int32_t* si_idx;        /* lattice site of the Si dopant                     */
+  double* lattice;        /* [n][4] off_x, off_y, cos, sin (graphene.py:544-557)*/
+  double* fov;            /* [n][4] ll_x, ll_y, ur_x, ur_y (simulator.py:79-82) */
+  double* fov_scale;      /* [n]    FOV width (simulator.py:77)                */
+  double* image_params;   /* [n][9] imaging.py:42-54, dataclass order          */
+  uint32_t* episode;      /* resets seen (Philox seq of the RESET stream)      */
+  uint32_t* ctrl_count;   /* apply_control calls seen (seq of the KMC stream)  */
+  uint32_t* frame_count;  /* frames rendered (seq of the RENDER streams)       */
+  int64_t* sim_time_us;   /* cumulative simulated time                         */
+  int64_t* n_events;      /* cumulative rate evaluations (KMC iterations)      */
+  int64_t* n_transitions; /* cumulative Si hops                                */
+  uint8_t* status;        /* PD_ENV_* bits                                     */
+} pd_state;
+
+/* Learned rate model: eval-mode forward of get_mlp_fn
+ * (rate_learning/learn_rates.py:80-99). float32 device pointers, row-major
+ * [in][out] like the Haiku `w` leaves. */
+typedef struct pd_mlp {
+  int32_t context_dim;  /* D; only 2 is a valid drop-in          */
+  int32_t hidden1;
+  int32_t hidden2;
+  int32_t batchnorm;    /* 0/1                                                */
+  const float* bn_scale;   /* [D] batch_norm/scale                             */
+  const float* bn_offset;  /* [D] batch_norm/offset                            */
+  const float* bn_mean;    /* [D] batch_norm/~/mean_ema/average                */
+  const float* bn_var;     /* [D] batch_norm/~/var_ema/average                 */
+  const float* w0;         /* [D][H1]   mlp/~/linear_0/w                       */
+  const float* b0;         /* [H1]                                             */
+  const float* w1;         /* [H1][H2]  mlp/~/linear_1/w                       */
+  const float* b1;         /* [H2]                                             */
+  const float* w2;         /* [H2][4]   mlp/~/linear_2/w                       */
+  const float* b2;         /* [4]                                              */
+} pd_mlp;
+
+/* Rate-function selection passed to every stepping call. */
+typedef struct pd_rate_config {
+  int32_t rate_fn;         /* pd_rate_fn                                       */
+  int32_t reserved_;
+  const pd_mlp* mlp;       /* HOST pointer to the struct; PD_RATE_LEARNED only */
+  float constant_rates[3]; /* PD_RATE_CONSTANT only                            */
+  float reserved2_;
+} pd_rate_config;
+
+/* Optional per-call outputs of the stepping calls (any pointer may be NULL).
+ * The event log carries the observe_transition payload
+ * (microscope_utils.py:516-521): for env e, transition k < log_count[e] of
+ * this call happened log_elapsed_us[e][k] after its control was applied and
+ * moved the Si to site log_site[e][k] during control log_ctrl[e][k]. */
+typedef struct pd_step_out {
+  int64_t* elapsed_us;     /* [n] MicroscopeObservation.elapsed_time           */
+  int32_t* transitions;    /* [n] hops during this call                        */
+  int32_t* events;         /* [n] rate evaluations during this call            */
+  uint8_t* recentred;      /* [n] 1 if the FOV was re-centred (simulator.py:156)*/
+  double* si_xy;           /* [n][2] Si position after the call, material frame */
+  int32_t log_capacity;    /* K                                                */
+  int32_t reserved_;
+  int32_t* log_count;      /* [n]                                              */
+  int64_t* log_elapsed_us; /* [n][K]                                           */
+  int32_t* log_site;       /* [n][K]                                           */
+  int32_t* log_ctrl;       /* [n][K] index of the control within the call      */
+} pd_step_out;
+
+/* ---- library ---------------------------------------------------------- */
+int pd_abi_version(void);
+const char* pd_last_error(void);
+/* Number of SMs of the current device (grid sizing; 148 on B200). */
+int pd_device_sm_count(int* out_sm_count);
+
+/* ---- lattice: graphene.py:464-501 _generate_hexagonal_grid, :537-543,
+ *      geometry.py:93-111 nearest_neighbors3 (canonical order) ------------ */
+/* Host-only arithmetic: number of sites/rows for a column count. */
+int pd_lattice_size(int32_t n_cols, int32_t* out_n_sites, int32_t* out_n_rows);
+/* Builds base_xy [n_sites][2] and nbr [n_sites][4] on the device. */
+int pd_build_lattice(int32_t n_cols, double* base_xy, int32_t* nbr,
+                     void* stream);
+
+/* ---- reset: simulator.py:65-105 PuttingDuneSimulator.reset,
+ *      graphene.py:584-598 PristineSingleDopedGraphene.reset,
+ *      imaging.py:42-54 sample_image_parameters --------------------------- */
+/* mask: device uint8 [n] (NULL = all envs). */
+int pd_reset(const pd_lattice* lat, const pd_state* st, const uint8_t* mask,
+             void* stream);
+
+/* ---- RateFunction seam: graphene.py:238-276
+ *      PristineSingleSiGrRatePredictor.__call__ --------------------------- */
+/* beam_xy: device double [n][2] material frame.  rates_out: float [n][3];
+ * nbr_out: int32 [n][3] successor Si sites (either may be NULL). */
+int pd_rates(const pd_lattice* lat, const pd_state* st,
+             const pd_rate_config* rc, const double* beam_xy, float* rates_out,
+             int32_t* nbr_out, void* stream);
+
+/* ---- Material seam: graphene.py:646-694
+ *      PristineSingleDopedGraphene.apply_control -------------------------- */
+/* beam_xy: device double [n][2] MATERIAL frame; dwell_us: device int64 [n]
+ * or NULL to use dwell_us_scalar for every env. */
+int pd_apply_control(const pd_lattice* lat, const pd_state* st,
+                     const pd_rate_config* rc, const double* beam_xy,
+                     const int64_t* dwell_us, int64_t dwell_us_scalar,
+                     const pd_step_out* out, void* stream);
+
+/* ---- Simulator seam: simulator.py:107-182
+ *      PuttingDuneSimulator.step_and_image (return_image=False part) ------ */
+/* controls_xy: device double [n][n_controls][2] MICROSCOPE frame;
+ * dwell_us: device int64 [n][n_controls] or NULL (scalar). */
+int pd_step_and_image(const pd_lattice* lat, const pd_state* st,
+                      const pd_rate_config* rc, const double* controls_xy,
+                      const int64_t* dwell_us, int64_t dwell_us_scalar,
+                      int32_t n_controls, int64_t image_duration_us,
+                      const pd_step_out* out, void* stream);
+
+/* Same call with HOST buffers for the per-step inputs and outputs: copies
+ * controls (and dwell if non-NULL) host->device into the staging buffers,
+ * steps, copies elapsed_us / si_xy / fov back, and synchronises `stream`.
+ * h_* are host pointers (pinned for full speed), d_* device staging of the
+ * same extents.  This is the call a reference user's step() maps to. */
+int pd_step_and_image_host(const pd_lattice* lat, const pd_state* st,
+                           const pd_rate_config* rc, const double* h_controls_xy,
+                           const int64_t* h_dwell_us, int64_t dwell_us_scalar,
+                           int32_t n_controls, int64_t image_duration_us,
+                           double* d_controls_xy, int64_t* d_dwell_us,
+                           const pd_step_out* d_out, int64_t* h_elapsed_us,
+                           double* h_si_xy, double* h_fov, void* stream);
+
+/* ---- beam-action stream: n_steps consecutive step_and_image calls with one
+ *      control each, fused in one launch (state stays on chip between steps;
+ *      semantics identical to calling pd_step_and_image n_steps times).
+ *      controls_xy: device double [n_steps][n][2] MICROSCOPE frame.
+ *      Per-step outputs (any may be NULL): si_idx_out int32 [n_steps][n],
+ *      elapsed_us_out int64 [n_steps][n]. -------------------------------- */
+int pd_rollout(const pd_lattice* lat, const pd_state* st,
+               const pd_rate_config* rc, const double* controls_xy,
+               int64_t dwell_us_scalar, int32_t n_steps,
+               int64_t image_duration_us, int32_t* si_idx_out,
+               int64_t* elapsed_us_out, void* stream);
+
+/* ---- queries: graphene.py:600-644 get_atoms_in_bounds,
+ *      graphene.py:696-700 get_silicon_position --------------------------- */
+/* fov_override: device double [n][4] or NULL (use st->fov).  Outputs are
+ * padded to max_atoms per env, in lattice order: out_xy double
+ * [n][max_atoms][2] normalised to the box, out_z uint8 [n][max_atoms]
+ * (6 / 14), out_site int32 [n][max_atoms] (may be NULL), out_count int32 [n]
+ * (the true count even if it exceeds max_atoms). */
+int pd_get_atoms_in_bounds(const pd_lattice* lat, const pd_state* st,
+                           const double* fov_override, int32_t max_atoms,
+                           double* out_xy, uint8_t* out_z, int32_t* out_site,
+                           int32_t* out_count, void* stream);
+int pd_get_silicon_position(const pd_lattice* lat, const pd_state* st,
+                            double* out_xy, void* stream);
+/* All atom positions of a subset of envs (the `.grid` attribute,
+ * graphene.py:581): env_ids device int32 [m]; out_xy double [m][n_sites][2]. */
+int pd_get_grid(const pd_lattice* lat, const pd_state* st,
+                const int32_t* env_ids, int32_t m, double* out_xy,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDUNE_B200_H_ */

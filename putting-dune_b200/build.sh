@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+# Builds libpdune_b200.so (sm_100a) in-tree. Parity-critical translation units
+# (float64 geometry -> rate -> clock) are compiled with -fmad=false so that
+# every product and sum is rounded exactly like the reference's NumPy code.
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+src="$here/csrc"
+out="$here/lib"
+obj="$here/build"
+mkdir -p "$out" "$obj"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
+        -Xcompiler -fPIC -I"$here/../include" -I"$src" ${PD_NVCC_EXTRA:-})
+exact=(pd_lattice pd_reset pd_step pd_query)
+fast=(pd_api pd_mlp)
+[ -f "$src/pd_render.cu" ] && fast+=(pd_render)
+[ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
+pids=()
+for f in "${exact[@]}"; do
+  "$NVCC" "${COMMON[@]}" -fmad=false -c "$src/$f.cu" -o "$obj/$f.o" & pids+=($!)
+done
+for f in "${fast[@]}"; do
+  "$NVCC" "${COMMON[@]}" -c "$src/$f.cu" -o "$obj/$f.o" & pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+objs=()
+for f in "${exact[@]}" "${fast[@]}"; do objs+=("$obj/$f.o"); done
+"$NVCC" -shared -o "$out/libpdune_b200.so" "${objs[@]}" -lcudart
+echo "built $out/libpdune_b200.so"

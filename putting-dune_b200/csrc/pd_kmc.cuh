@@ -1,0 +1,253 @@
+// Device-side building blocks of one kinetic-Monte-Carlo control
+// (graphene.py:646-694 PristineSingleDopedGraphene.apply_control and the rate
+// functions it calls).  Included by pd_step.cu and pd_mlp.cu.
+//
+// Arithmetic contract: geometry -> rate in float64
+// with every operation individually rounded (translation units including
+// this header are compiled with -fmad=false and use explicit *_rn
+// intrinsics); rates cast to float32; total rate = sequential float32 sum;
+// waiting time in float64; integer-microsecond clock.
+#pragma once
+
+#include "pd_common.cuh"
+
+namespace pd {
+
+// ---------------------------------------------------------------------------
+// Lattice tables: either straight from global memory through L1 (small
+// batches: staging 45 KB per CTA would cost more than the step) or staged in
+// shared memory (large batches: random 16-byte gathers are ~3x cheaper from
+// shared memory than as 32 separate L1 wavefronts).
+// ---------------------------------------------------------------------------
+struct GlobalTables {
+  const double2* base;
+  const int4* nbr;
+  __device__ __forceinline__ double2 position(int k) const {
+    return __ldg(base + k);
+  }
+  __device__ __forceinline__ void neighbors(int k, int out[3]) const {
+    const int4 v = __ldg(nbr + k);
+    out[0] = v.x;
+    out[1] = v.y;
+    out[2] = v.z;
+  }
+};
+
+struct SharedTables {
+  const double2* base;   // shared memory
+  const ushort4* nbr;    // shared memory
+  __device__ __forceinline__ double2 position(int k) const { return base[k]; }
+  __device__ __forceinline__ void neighbors(int k, int out[3]) const {
+    const ushort4 v = nbr[k];
+    out[0] = v.x;
+    out[1] = v.y;
+    out[2] = v.z;
+  }
+};
+
+__device__ __forceinline__ size_t shared_tables_bytes(int n_sites) {
+  return static_cast<size_t>(n_sites) * (sizeof(double2) + sizeof(ushort4));
+}
+
+// Cooperative stage of the lattice tables into dynamic shared memory.
+__device__ __forceinline__ SharedTables stage_tables(const pd_lattice& lat,
+                                                     unsigned char* smem) {
+  double2* sbase = reinterpret_cast<double2*>(smem);
+  ushort4* snbr = reinterpret_cast<ushort4*>(sbase + lat.n_sites);
+  const double2* gbase = reinterpret_cast<const double2*>(lat.base_xy);
+  const int4* gnbr = reinterpret_cast<const int4*>(lat.nbr);
+  for (int k = threadIdx.x; k < lat.n_sites; k += blockDim.x) {
+    sbase[k] = __ldg(gbase + k);
+    const int4 v = __ldg(gnbr + k);
+    snbr[k] = make_ushort4(static_cast<unsigned short>(v.x),
+                           static_cast<unsigned short>(v.y),
+                           static_cast<unsigned short>(v.z), 0);
+  }
+  __syncthreads();
+  return SharedTables{sbase, snbr};
+}
+
+// ---------------------------------------------------------------------------
+// Rate functions -> float32[3]
+// ---------------------------------------------------------------------------
+// graphene.py:133-166 simple_canonical_rate_function.
+__device__ __forceinline__ void rates_simple(const double2 beam,
+                                             const double2 psi,
+                                             const double2 pn[3], float r[3]) {
+  const double bx = __dsub_rn(beam.x, psi.x);
+  const double by = __dsub_rn(beam.y, psi.y);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = __dsub_rn(pn[i].x, psi.x);
+    const double ny = __dsub_rn(pn[i].y, psi.y);
+    const double dx = __dsub_rn(bx, nx);
+    const double dy = __dsub_rn(by, ny);
+    // np.linalg.norm(axis=-1) == sqrt(dx*dx + dy*dy)
+    double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    d = __ddiv_rn(d, kBond);
+    const double a = __dmul_rn(d, 4.0);
+    const double den = __dadd_rn(__dmul_rn(a, a), 1.0);
+    r[i] = __double2float_rn(__ddiv_rn(1.0, den));
+  }
+}
+
+// graphene.py:191-229 HumanPriorRatePredictor.predict with the constants of
+// constants.py:26-28.  The reference rotates the mean (0.85, 0) by
+// rotate_coordinates(mean, -theta) with theta = atan2 of the neighbour, which
+// places the peak at 0.85*(cos theta, -sin theta) (mirror quirk, SURVEY
+// appendix B.1); cos/sin of atan2 are taken directly from the neighbour
+// vector here (identical value up to 1e-16 relative, far inside the float32
+// cast that follows).  With covariance 0.1*I,
+//   max_rate * pdf(x)/pdf(mu) = (ln 2 / 3) * exp(-0.5 * |x - mu|^2 / 0.1).
+__device__ __forceinline__ void rates_prior(const double2 beam,
+                                            const double2 psi,
+                                            const double2 pn[3], float r[3]) {
+  const double kMaxRate = 0.23104906018664842;  // np.log(2) / 3
+  const double x = __ddiv_rn(__dsub_rn(beam.x, psi.x), kBond);
+  const double y = __ddiv_rn(__dsub_rn(beam.y, psi.y), kBond);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = __dsub_rn(pn[i].x, psi.x);
+    const double ny = __dsub_rn(pn[i].y, psi.y);
+    const double inv =
+        __ddiv_rn(0.85, __dsqrt_rn(__dadd_rn(__dmul_rn(nx, nx),
+                                             __dmul_rn(ny, ny))));
+    const double dx = __dsub_rn(x, __dmul_rn(nx, inv));
+    const double dy = __dadd_rn(y, __dmul_rn(ny, inv));
+    const double maha =
+        __ddiv_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.1);
+    r[i] = __double2float_rn(__dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha))));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// One event of the direct-method loop (graphene.py:658-694).
+// Returns true if a transition was accepted; *slot is the successor index.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ long long seconds_to_us(double t) {
+  // dt.timedelta(seconds=t): whole seconds * 10^6 + fractional part * 10^6
+  // rounded half-to-even (CPython datetime delta_new).
+  const double whole = trunc(t);
+  const double frac = __dsub_rn(t, whole);
+  return static_cast<long long>(whole) * 1000000LL +
+         static_cast<long long>(rint(__dmul_rn(frac, 1e6)));
+}
+
+__device__ __forceinline__ bool kmc_event(const float r[3], double u_exp,
+                                          double u_choice, long long dwell_us,
+                                          long long* elapsed_us, int* slot,
+                                          bool* bad_rate) {
+  // assert (transition_rates >= 0).all()  (graphene.py:258)
+  *bad_rate = !(r[0] >= 0.f) || !(r[1] >= 0.f) || !(r[2] >= 0.f);
+  // Rates.total_rate: sequential float32 sum (graphene.py:47-49).
+  const float tot = __fadd_rn(__fadd_rn(r[0], r[1]), r[2]);
+  double t = kMaxTransitionSeconds;
+  if (tot > 0.f) {
+    // rng.exponential(scale=1.0 / total): float32 scale under NumPy 2.
+    const float scale = __fdiv_rn(1.0f, tot);
+    t = __dmul_rn(-log1p(-u_exp), static_cast<double>(scale));
+    t = fmin(t, kMaxTransitionSeconds);  // graphene.py:668
+  }
+  *elapsed_us += seconds_to_us(t);
+  if (*elapsed_us > dwell_us) return false;  // graphene.py:677
+  // rng.choice(3, p=rates/total): float32 p, float64 normalised CDF,
+  // searchsorted(side='right').
+  const double c0 = static_cast<double>(__fdiv_rn(r[0], tot));
+  const double c1 = __dadd_rn(c0, static_cast<double>(__fdiv_rn(r[1], tot)));
+  const double c2 = __dadd_rn(c1, static_cast<double>(__fdiv_rn(r[2], tot)));
+  *slot = (__ddiv_rn(c0, c2) <= u_choice) + (__ddiv_rn(c1, c2) <= u_choice);
+  return true;
+}
+
+// Frame transforms: microscope_utils.py:362-369 / :421-428.
+__device__ __forceinline__ double2 microscope_to_material(const Fov4& f,
+                                                          double px,
+                                                          double py) {
+  return make_double2(
+      __dadd_rn(__dmul_rn(px, __dsub_rn(f.urx, f.llx)), f.llx),
+      __dadd_rn(__dmul_rn(py, __dsub_rn(f.ury, f.lly)), f.lly));
+}
+
+// simulator.py:230-250 _silicon_outside_of_safe_area on the observed grid of
+// graphene.py:600-644 (inclusive bounds, normalised coordinates).
+__device__ __forceinline__ bool silicon_outside_safe_area(const Fov4& f,
+                                                          const double2 p) {
+  const bool in_view = (f.llx <= p.x) && (p.x <= f.urx) && (f.lly <= p.y) &&
+                       (p.y <= f.ury);
+  const double qx = __ddiv_rn(__dsub_rn(p.x, f.llx), __dsub_rn(f.urx, f.llx));
+  const double qy = __ddiv_rn(__dsub_rn(p.y, f.lly), __dsub_rn(f.ury, f.lly));
+  const bool near_edge = (qx < 0.25) || (qx > 0.75) || (qy < 0.25) ||
+                         (qy > 0.75);
+  return !in_view || near_edge;
+}
+
+// simulator.py:161-165: FOV = [P_si - s/2, P_si + s/2].
+__device__ __forceinline__ Fov4 centred_fov(const double2 p, double scale) {
+  const double h = __ddiv_rn(scale, 2.0);
+  return Fov4{__dsub_rn(p.x, h), __dsub_rn(p.y, h), __dadd_rn(p.x, h),
+              __dadd_rn(p.y, h)};
+}
+
+
+// ---------------------------------------------------------------------------
+// Arguments and per-env registers shared by the stepping kernels.
+// ---------------------------------------------------------------------------
+constexpr int kStepThreads = 128;
+
+struct RateArgs {
+  float constant_rates[3];
+};
+
+// Per-env registers carried through a call.
+struct EnvRegs {
+  int si;
+  double2 psi;
+  Lattice4 lat;
+  uint32_t env_id;
+  uint32_t ctrl_count;
+  int transitions;
+  int events;
+  int log_n;
+  uint8_t status;
+};
+
+struct LogSink {
+  int capacity;
+  int64_t* elapsed_us;
+  int32_t* site;
+  int32_t* ctrl;
+};
+
+struct StepArgs {
+  pd_lattice lat;
+  pd_state st;
+  RateArgs ra;
+  const double* controls_xy;  // [n][C][2] or [T][n][2] (rollout)
+  const int64_t* dwell_us;    // [n][C] or null
+  int64_t dwell_us_scalar;
+  int32_t n_controls;
+  int32_t n_steps;            // rollout only
+  int64_t image_duration_us;
+  int32_t material_frame;     // 1: apply_control (no observe phase)
+  pd_step_out out;
+  int32_t* si_idx_out;        // rollout [T][n]
+  int64_t* elapsed_us_out;    // rollout [T][n]
+};
+
+template <class Tables>
+__device__ __forceinline__ EnvRegs load_env(const Tables& tab,
+                                            const StepArgs& a, int64_t e) {
+  EnvRegs r;
+  r.si = a.st.si_idx[e];
+  r.lat = load_lattice4(a.st.lattice, e);
+  r.psi = site_position(tab.position(r.si), r.lat);
+  r.env_id = a.st.env_offset + static_cast<uint32_t>(e);
+  r.ctrl_count = a.st.ctrl_count[e];
+  r.transitions = 0;
+  r.events = 0;
+  r.log_n = 0;
+  r.status = a.st.status[e];
+  return r;
+}
+
+}  // namespace pd

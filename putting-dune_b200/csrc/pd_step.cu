@@ -1,0 +1,457 @@
+// K1: the event step.  One thread owns one environment for the duration of a
+// call: neighbour geometry -> rate function -> direct-method event loop with a
+// microsecond clock -> Si update -> FOV safe-area check / re-centre.
+//
+//   graphene.py:238-276   PristineSingleSiGrRatePredictor.__call__
+//   graphene.py:646-694   PristineSingleDopedGraphene.apply_control
+//   simulator.py:107-182  PuttingDuneSimulator.step_and_image
+//
+// Compiled with -fmad=false (see pd_kmc.cuh).
+#include <math.h>
+
+#include "pd_kmc.cuh"
+
+namespace pd {
+
+template <int RATE>
+__device__ __forceinline__ void eval_rates(const RateArgs& ra,
+                                           const double2 beam,
+                                           const double2 psi,
+                                           const double2 pn[3], float r[3]) {
+  if (RATE == PD_RATE_SIMPLE) {
+    rates_simple(beam, psi, pn, r);
+  } else if (RATE == PD_RATE_PRIOR) {
+    rates_prior(beam, psi, pn, r);
+  } else {
+    r[0] = ra.constant_rates[0];
+    r[1] = ra.constant_rates[1];
+    r[2] = ra.constant_rates[2];
+  }
+}
+
+// graphene.py:646-694 for one env.
+template <int RATE, class Tables>
+__device__ __forceinline__ void run_control(const Tables& tab,
+                                            const RateArgs& ra, uint64_t seed,
+                                            const double2 beam,
+                                            long long dwell_us, int ctrl_index,
+                                            int64_t env_local,
+                                            const LogSink& log, EnvRegs* e) {
+  long long elapsed = 0;
+  uint32_t it = 0;
+  while (elapsed < dwell_us) {  // graphene.py:658
+    int nb[3];
+    tab.neighbors(e->si, nb);
+    double2 pn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      pn[i] = site_position(tab.position(nb[i]), e->lat);
+    float r[3];
+    eval_rates<RATE>(ra, beam, e->psi, pn, r);
+    const uint4 w =
+        philox4x32_10(e->env_id, e->ctrl_count, it, PD_STREAM_KMC, seed);
+    int slot = 0;
+    bool bad = false;
+    const bool hit = kmc_event(r, u53(w.x, w.y), u53(w.z, w.w), dwell_us,
+                               &elapsed, &slot, &bad);
+    if (bad) e->status |= PD_ENV_BAD_RATE;
+    e->events += 1;
+    if (hit) {
+      e->si = nb[slot];
+      e->psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
+      e->transitions += 1;
+      if (log.capacity > 0) {
+        if (e->log_n < log.capacity) {
+          const int64_t o = env_local * log.capacity + e->log_n;
+          log.elapsed_us[o] = elapsed;
+          log.site[o] = e->si;
+          if (log.ctrl) log.ctrl[o] = ctrl_index;
+        } else {
+          e->status |= PD_ENV_LOG_OVERFLOW;
+        }
+        e->log_n += 1;
+      }
+    }
+    ++it;
+  }
+  e->ctrl_count += 1;
+}
+
+// One step_and_image (or apply_control) call for every env.
+template <int RATE, bool STAGE>
+__global__ void __launch_bounds__(kStepThreads)
+    k_step(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
+  if constexpr (STAGE) {
+    tab = stage_tables(a.lat, smem);
+  } else {
+    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
+    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
+  }
+  const LogSink log{a.out.log_count ? a.out.log_capacity : 0,
+                    a.out.log_elapsed_us, a.out.log_site, a.out.log_ctrl};
+  const int64_t n = a.st.n_envs;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    EnvRegs r = load_env(tab, a, e);
+    Fov4 fov = load_fov4(a.st.fov, e);
+    long long elapsed = 0;
+    for (int c = 0; c < a.n_controls; ++c) {
+      const double2 ctl = reinterpret_cast<const double2*>(
+          a.controls_xy)[e * a.n_controls + c];
+      const long long dwell =
+          a.dwell_us ? a.dwell_us[e * a.n_controls + c] : a.dwell_us_scalar;
+      // simulator.py:137 microscope frame -> material frame
+      const double2 beam = a.material_frame
+                               ? ctl
+                               : microscope_to_material(fov, ctl.x, ctl.y);
+      run_control<RATE>(tab, a.ra, a.st.seed, beam, dwell, c, e, log, &r);
+      elapsed += dwell;  // simulator.py:149
+    }
+    uint8_t recentred = 0;
+    if (!a.material_frame) {
+      elapsed += a.image_duration_us;  // simulator.py:152-153
+      if (silicon_outside_safe_area(fov, r.psi)) {  // simulator.py:156
+        fov = centred_fov(r.psi, a.st.fov_scale[e]);
+        store_fov4(a.st.fov, e, fov);
+        elapsed += a.image_duration_us;  // simulator.py:168-169
+        recentred = 1;
+      }
+      a.st.sim_time_us[e] += elapsed;
+    }
+    a.st.si_idx[e] = r.si;
+    a.st.ctrl_count[e] = r.ctrl_count;
+    a.st.n_events[e] += r.events;
+    a.st.n_transitions[e] += r.transitions;
+    a.st.status[e] = r.status;
+    if (a.out.elapsed_us) a.out.elapsed_us[e] = elapsed;
+    if (a.out.transitions) a.out.transitions[e] = r.transitions;
+    if (a.out.events) a.out.events[e] = r.events;
+    if (a.out.recentred) a.out.recentred[e] = recentred;
+    if (a.out.si_xy)
+      reinterpret_cast<double2*>(a.out.si_xy)[e] = r.psi;
+    if (a.out.log_count) a.out.log_count[e] = r.log_n;
+  }
+}
+
+// n_steps consecutive single-control step_and_image calls in one launch.
+template <int RATE, bool STAGE>
+__global__ void __launch_bounds__(kStepThreads)
+    k_rollout(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
+  if constexpr (STAGE) {
+    tab = stage_tables(a.lat, smem);
+  } else {
+    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
+    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
+  }
+  const LogSink log{0, nullptr, nullptr, nullptr};
+  const int64_t n = a.st.n_envs;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    EnvRegs r = load_env(tab, a, e);
+    Fov4 fov = load_fov4(a.st.fov, e);
+    const double scale = a.st.fov_scale[e];
+    long long total = 0;
+    bool fov_dirty = false;
+    // Software prefetch of the next control hides the HBM latency of the
+    // action stream behind the current step's arithmetic.
+    double2 next = reinterpret_cast<const double2*>(a.controls_xy)[e];
+    for (int t = 0; t < a.n_steps; ++t) {
+      const double2 ctl = next;
+      if (t + 1 < a.n_steps)
+        next = reinterpret_cast<const double2*>(
+            a.controls_xy)[static_cast<int64_t>(t + 1) * n + e];
+      const double2 beam = microscope_to_material(fov, ctl.x, ctl.y);
+      run_control<RATE>(tab, a.ra, a.st.seed, beam, a.dwell_us_scalar, 0, e,
+                        log, &r);
+      long long elapsed = a.dwell_us_scalar + a.image_duration_us;
+      if (silicon_outside_safe_area(fov, r.psi)) {
+        fov = centred_fov(r.psi, scale);
+        elapsed += a.image_duration_us;
+        fov_dirty = true;
+      }
+      total += elapsed;
+      if (a.si_idx_out) a.si_idx_out[static_cast<int64_t>(t) * n + e] = r.si;
+      if (a.elapsed_us_out)
+        a.elapsed_us_out[static_cast<int64_t>(t) * n + e] = elapsed;
+    }
+    if (fov_dirty) store_fov4(a.st.fov, e, fov);
+    a.st.sim_time_us[e] += total;
+    a.st.si_idx[e] = r.si;
+    a.st.ctrl_count[e] = r.ctrl_count;
+    a.st.n_events[e] += r.events;
+    a.st.n_transitions[e] += r.transitions;
+    a.st.status[e] = r.status;
+  }
+}
+
+// RateFunction seam: rates + successor sites, no state change.
+template <int RATE>
+__global__ void __launch_bounds__(kStepThreads)
+    k_rates(const StepArgs a, float* __restrict__ rates_out,
+            int32_t* __restrict__ nbr_out) {
+  GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
+                   reinterpret_cast<const int4*>(a.lat.nbr)};
+  const int64_t n = a.st.n_envs;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int si = a.st.si_idx[e];
+    const Lattice4 lat = load_lattice4(a.st.lattice, e);
+    const double2 psi = site_position(tab.position(si), lat);
+    int nb[3];
+    tab.neighbors(si, nb);
+    double2 pn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pn[i] = site_position(tab.position(nb[i]), lat);
+    const double2 beam = reinterpret_cast<const double2*>(a.controls_xy)[e];
+    float r[3];
+    eval_rates<RATE>(a.ra, beam, psi, pn, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rates_out) rates_out[3 * e + i] = r[i];
+      if (nbr_out) nbr_out[3 * e + i] = nb[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Launch helpers
+// ---------------------------------------------------------------------------
+// Staging the tables costs ~45 KB of L2 reads per CTA; it pays once every SM
+// holds at least a few full CTAs of envs.
+static bool use_staging(int64_t n_envs, int64_t work_per_env) {
+  return n_envs * work_per_env >= 4LL * sm_count() * kStepThreads;
+}
+
+static int grid_for(int64_t n_envs, bool staged) {
+  const int64_t blocks = (n_envs + kStepThreads - 1) / kStepThreads;
+  // Persistent grid-stride loop: a whole number of CTAs per SM.
+  const int64_t cap = static_cast<int64_t>(sm_count()) * (staged ? 4 : 16);
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <int RATE>
+static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
+  const bool staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
+  const int grid = grid_for(a.st.n_envs, staged);
+  if (staged) {
+    const size_t smem = static_cast<size_t>(a.lat.n_sites) *
+                        (sizeof(double2) + sizeof(ushort4));
+    auto kern = rollout ? k_rollout<RATE, true> : k_step<RATE, true>;
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem)));
+    kern<<<grid, kStepThreads, smem, stream>>>(a);
+  } else {
+    auto kern = rollout ? k_rollout<RATE, false> : k_step<RATE, false>;
+    kern<<<grid, kStepThreads, 0, stream>>>(a);
+  }
+  PD_CUDA_OK(cudaGetLastError());
+  return PD_OK;
+}
+
+static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
+                         cudaStream_t stream) {
+  switch (rc->rate_fn) {
+    case PD_RATE_SIMPLE:
+      return launch_step<PD_RATE_SIMPLE>(a, rollout, stream);
+    case PD_RATE_PRIOR:
+      return launch_step<PD_RATE_PRIOR>(a, rollout, stream);
+    case PD_RATE_CONSTANT:
+      for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
+      return launch_step<PD_RATE_CONSTANT>(a, rollout, stream);
+    default:
+      set_error("rate_fn %d is not handled by the scalar event kernel",
+                rc->rate_fn);
+      return PD_ERR_UNSUPPORTED;
+  }
+}
+
+int validate_common(const pd_lattice* lat, const pd_state* st,
+                    const pd_rate_config* rc) {
+  PD_REQUIRE(lat && st, "null lattice/state");
+  PD_REQUIRE(lat->base_xy && lat->nbr && lat->n_sites > 0, "lattice not built");
+  PD_REQUIRE(st->n_envs >= 0, "negative n_envs");
+  PD_REQUIRE(st->si_idx && st->lattice && st->fov && st->fov_scale &&
+                 st->ctrl_count && st->sim_time_us && st->n_events &&
+                 st->n_transitions && st->status,
+             "state has null arrays");
+  if (rc) {
+    PD_REQUIRE(rc->rate_fn >= PD_RATE_SIMPLE && rc->rate_fn <= PD_RATE_CONSTANT,
+               "unknown rate_fn");
+    if (rc->rate_fn == PD_RATE_LEARNED)
+      PD_REQUIRE(rc->mlp != nullptr, "PD_RATE_LEARNED needs rc->mlp");
+  }
+  return PD_OK;
+}
+
+// Implemented in pd_mlp.cu.
+int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
+                 const StepArgs& a, bool rollout, cudaStream_t stream);
+int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
+                  const double* beam_xy, float* rates_out, int32_t* nbr_out,
+                  cudaStream_t stream);
+
+}  // namespace pd
+
+using pd::StepArgs;
+
+extern "C" int pd_rates(const pd_lattice* lat, const pd_state* st,
+                        const pd_rate_config* rc, const double* beam_xy,
+                        float* rates_out, int32_t* nbr_out, void* stream) {
+  int rcode = pd::validate_common(lat, st, rc);
+  if (rcode != PD_OK) return rcode;
+  PD_REQUIRE(rc && beam_xy, "null rate config / beam");
+  if (st->n_envs == 0) return PD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rc->rate_fn == PD_RATE_LEARNED)
+    return pd::learned_rates(lat, st, rc->mlp, beam_xy, rates_out, nbr_out, s);
+  StepArgs a{};
+  a.lat = *lat;
+  a.st = *st;
+  a.controls_xy = beam_xy;
+  for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
+  const int grid = pd::grid_for(st->n_envs, false);
+  switch (rc->rate_fn) {
+    case PD_RATE_SIMPLE:
+      pd::k_rates<PD_RATE_SIMPLE><<<grid, pd::kStepThreads, 0, s>>>(
+          a, rates_out, nbr_out);
+      break;
+    case PD_RATE_PRIOR:
+      pd::k_rates<PD_RATE_PRIOR><<<grid, pd::kStepThreads, 0, s>>>(
+          a, rates_out, nbr_out);
+      break;
+    default:
+      pd::k_rates<PD_RATE_CONSTANT><<<grid, pd::kStepThreads, 0, s>>>(
+          a, rates_out, nbr_out);
+  }
+  PD_CUDA_OK(cudaGetLastError());
+  return PD_OK;
+}
+
+static int step_common(const pd_lattice* lat, const pd_state* st,
+                       const pd_rate_config* rc, const double* controls_xy,
+                       const int64_t* dwell_us, int64_t dwell_us_scalar,
+                       int32_t n_controls, int64_t image_duration_us,
+                       int material_frame, const pd_step_out* out,
+                       void* stream) {
+  int rcode = pd::validate_common(lat, st, rc);
+  if (rcode != PD_OK) return rcode;
+  PD_REQUIRE(rc != nullptr, "null rate config");
+  PD_REQUIRE(n_controls >= 0, "negative n_controls");
+  PD_REQUIRE(n_controls == 0 || controls_xy != nullptr, "null controls");
+  PD_REQUIRE(dwell_us != nullptr || dwell_us_scalar >= 0, "negative dwell");
+  PD_REQUIRE(image_duration_us >= 0, "negative image duration");
+  if (out && out->log_count) {
+    PD_REQUIRE(out->log_capacity > 0 && out->log_elapsed_us && out->log_site,
+               "event log requested without buffers");
+  }
+  if (st->n_envs == 0) return PD_OK;
+  StepArgs a{};
+  a.lat = *lat;
+  a.st = *st;
+  a.controls_xy = controls_xy;
+  a.dwell_us = dwell_us;
+  a.dwell_us_scalar = dwell_us_scalar;
+  a.n_controls = n_controls;
+  a.image_duration_us = image_duration_us;
+  a.material_frame = material_frame;
+  if (out) a.out = *out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rc->rate_fn == PD_RATE_LEARNED)
+    return pd::learned_step(lat, st, rc->mlp, a, false, s);
+  return pd::dispatch_step(rc, a, false, s);
+}
+
+extern "C" int pd_apply_control(const pd_lattice* lat, const pd_state* st,
+                                const pd_rate_config* rc, const double* beam_xy,
+                                const int64_t* dwell_us,
+                                int64_t dwell_us_scalar, const pd_step_out* out,
+                                void* stream) {
+  return step_common(lat, st, rc, beam_xy, dwell_us, dwell_us_scalar, 1, 0, 1,
+                     out, stream);
+}
+
+extern "C" int pd_step_and_image(const pd_lattice* lat, const pd_state* st,
+                                 const pd_rate_config* rc,
+                                 const double* controls_xy,
+                                 const int64_t* dwell_us,
+                                 int64_t dwell_us_scalar, int32_t n_controls,
+                                 int64_t image_duration_us,
+                                 const pd_step_out* out, void* stream) {
+  return step_common(lat, st, rc, controls_xy, dwell_us, dwell_us_scalar,
+                     n_controls, image_duration_us, 0, out, stream);
+}
+
+extern "C" int pd_step_and_image_host(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const double* h_controls_xy, const int64_t* h_dwell_us,
+    int64_t dwell_us_scalar, int32_t n_controls, int64_t image_duration_us,
+    double* d_controls_xy, int64_t* d_dwell_us, const pd_step_out* d_out,
+    int64_t* h_elapsed_us, double* h_si_xy, double* h_fov, void* stream) {
+  PD_REQUIRE(st != nullptr, "null state");
+  PD_REQUIRE(n_controls == 0 || (h_controls_xy && d_controls_xy),
+             "null controls / staging");
+  PD_REQUIRE(h_dwell_us == nullptr || d_dwell_us != nullptr,
+             "per-env dwell needs device staging");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(st->n_envs);
+  if (n_controls > 0)
+    PD_CUDA_OK(cudaMemcpyAsync(d_controls_xy, h_controls_xy,
+                               n * n_controls * 2 * sizeof(double),
+                               cudaMemcpyHostToDevice, s));
+  if (h_dwell_us)
+    PD_CUDA_OK(cudaMemcpyAsync(d_dwell_us, h_dwell_us,
+                               n * n_controls * sizeof(int64_t),
+                               cudaMemcpyHostToDevice, s));
+  int rcode = pd_step_and_image(lat, st, rc, d_controls_xy,
+                                h_dwell_us ? d_dwell_us : nullptr,
+                                dwell_us_scalar, n_controls, image_duration_us,
+                                d_out, stream);
+  if (rcode != PD_OK) return rcode;
+  if (h_elapsed_us) {
+    PD_REQUIRE(d_out && d_out->elapsed_us, "elapsed_us needs device staging");
+    PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us, d_out->elapsed_us,
+                               n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (h_si_xy) {
+    PD_REQUIRE(d_out && d_out->si_xy, "si_xy needs device staging");
+    PD_CUDA_OK(cudaMemcpyAsync(h_si_xy, d_out->si_xy, n * 2 * sizeof(double),
+                               cudaMemcpyDeviceToHost, s));
+  }
+  if (h_fov)
+    PD_CUDA_OK(cudaMemcpyAsync(h_fov, st->fov, n * 4 * sizeof(double),
+                               cudaMemcpyDeviceToHost, s));
+  PD_CUDA_OK(cudaStreamSynchronize(s));
+  return PD_OK;
+}
+
+extern "C" int pd_rollout(const pd_lattice* lat, const pd_state* st,
+                          const pd_rate_config* rc, const double* controls_xy,
+                          int64_t dwell_us_scalar, int32_t n_steps,
+                          int64_t image_duration_us, int32_t* si_idx_out,
+                          int64_t* elapsed_us_out, void* stream) {
+  int rcode = pd::validate_common(lat, st, rc);
+  if (rcode != PD_OK) return rcode;
+  PD_REQUIRE(rc != nullptr, "null rate config");
+  PD_REQUIRE(n_steps >= 0 && (n_steps == 0 || controls_xy), "bad action stream");
+  PD_REQUIRE(dwell_us_scalar >= 0 && image_duration_us >= 0, "negative time");
+  if (st->n_envs == 0 || n_steps == 0) return PD_OK;
+  StepArgs a{};
+  a.lat = *lat;
+  a.st = *st;
+  a.controls_xy = controls_xy;
+  a.dwell_us_scalar = dwell_us_scalar;
+  a.n_controls = 1;
+  a.n_steps = n_steps;
+  a.image_duration_us = image_duration_us;
+  a.si_idx_out = si_idx_out;
+  a.elapsed_us_out = elapsed_us_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rc->rate_fn == PD_RATE_LEARNED)
+    return pd::learned_step(lat, st, rc->mlp, a, true, s);
+  return pd::dispatch_step(rc, a, true, s);
+}

@@ -1,0 +1,126 @@
+"""ctypes binding of ``libpdune_b200.so`` (C ABI in ``include/pdune_b200.h``).
+
+There is no CPU fallback: if the CUDA library is missing or was not built,
+importing this module raises, and so does every product entry point.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = pathlib.Path(
+    os.environ.get('PDUNE_B200_LIB', _HERE.parent / 'lib' / 'libpdune_b200.so'))
+
+PD_OK = 0
+RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT = 0, 1, 2, 3
+ENV_BAD_RATE, ENV_LOG_OVERFLOW, ENV_NOT_RESET = 1, 2, 4
+STREAM_KMC, STREAM_RESET = 0, 1
+
+_p = C.c_void_p
+
+
+class PdLattice(C.Structure):
+  _fields_ = [('n_cols', C.c_int32), ('n_sites', C.c_int32),
+              ('base_xy', _p), ('nbr', _p)]
+
+
+class PdState(C.Structure):
+  _fields_ = [('n_envs', C.c_int64), ('seed', C.c_uint64),
+              ('env_offset', C.c_uint32), ('reserved_', C.c_uint32),
+              ('si_idx', _p), ('lattice', _p), ('fov', _p), ('fov_scale', _p),
+              ('image_params', _p), ('episode', _p), ('ctrl_count', _p),
+              ('frame_count', _p), ('sim_time_us', _p), ('n_events', _p),
+              ('n_transitions', _p), ('status', _p)]
+
+
+class PdMlp(C.Structure):
+  _fields_ = [('context_dim', C.c_int32), ('hidden1', C.c_int32),
+              ('hidden2', C.c_int32), ('batchnorm', C.c_int32),
+              ('bn_scale', _p), ('bn_offset', _p), ('bn_mean', _p),
+              ('bn_var', _p), ('w0', _p), ('b0', _p), ('w1', _p), ('b1', _p),
+              ('w2', _p), ('b2', _p)]
+
+
+class PdRateConfig(C.Structure):
+  _fields_ = [('rate_fn', C.c_int32), ('reserved_', C.c_int32),
+              ('mlp', C.POINTER(PdMlp)), ('constant_rates', C.c_float * 3),
+              ('reserved2_', C.c_float)]
+
+
+class PdStepOut(C.Structure):
+  _fields_ = [('elapsed_us', _p), ('transitions', _p), ('events', _p),
+              ('recentred', _p), ('si_xy', _p), ('log_capacity', C.c_int32),
+              ('reserved_', C.c_int32), ('log_count', _p),
+              ('log_elapsed_us', _p), ('log_site', _p), ('log_ctrl', _p)]
+
+
+class PdRenderOut(C.Structure):
+  _fields_ = [('frames', _p), ('clean', _p)]
+
+
+class NativeError(RuntimeError):
+  pass
+
+
+def _load() -> C.CDLL:
+  if not LIB_PATH.exists():
+    raise ImportError(
+        f'{LIB_PATH} not found: build the CUDA extension first '
+        '(python -c "import __graft_entry__ as g; g.build()" or '
+        'putting-dune_b200/build.sh). There is no CPU fallback.')
+  return C.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+_LP, _SP, _RP, _OP = (C.POINTER(PdLattice), C.POINTER(PdState),
+                      C.POINTER(PdRateConfig), C.POINTER(PdStepOut))
+_i32, _i64 = C.c_int32, C.c_int64
+
+_SIGNATURES = {
+    'pd_abi_version': ([], C.c_int),
+    'pd_last_error': ([], C.c_char_p),
+    'pd_device_sm_count': ([C.POINTER(C.c_int)], C.c_int),
+    'pd_lattice_size': ([_i32, C.POINTER(_i32), C.POINTER(_i32)], C.c_int),
+    'pd_build_lattice': ([_i32, _p, _p, _p], C.c_int),
+    'pd_reset': ([_LP, _SP, _p, _p], C.c_int),
+    'pd_rates': ([_LP, _SP, _RP, _p, _p, _p, _p], C.c_int),
+    'pd_apply_control': ([_LP, _SP, _RP, _p, _p, _i64, _OP, _p], C.c_int),
+    'pd_step_and_image': ([_LP, _SP, _RP, _p, _p, _i64, _i32, _i64, _OP, _p],
+                          C.c_int),
+    'pd_step_and_image_host': ([_LP, _SP, _RP, _p, _p, _i64, _i32, _i64, _p,
+                                _p, _OP, _p, _p, _p, _p], C.c_int),
+    'pd_rollout': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p], C.c_int),
+    'pd_get_atoms_in_bounds': ([_LP, _SP, _p, _i32, _p, _p, _p, _p, _p],
+                               C.c_int),
+    'pd_get_silicon_position': ([_LP, _SP, _p, _p], C.c_int),
+    'pd_get_grid': ([_LP, _SP, _p, _i32, _p, _p], C.c_int),
+}
+
+for _name, (_args, _res) in _SIGNATURES.items():
+  _fn = getattr(lib, _name)
+  _fn.argtypes = _args
+  _fn.restype = _res
+
+
+def bind_optional(name, args, res=C.c_int):
+  """Binds an entry point declared later in the header (renderer, episodes)."""
+  fn = getattr(lib, name)
+  fn.argtypes = args
+  fn.restype = res
+  _SIGNATURES[name] = (args, res)
+  return fn
+
+
+def check(rc: int) -> None:
+  if rc != PD_OK:
+    msg = lib.pd_last_error()
+    raise NativeError(
+        f'libpdune_b200 error {rc}: {msg.decode() if msg else "?"}')
+
+
+def exported_symbols():
+  return sorted(_SIGNATURES)

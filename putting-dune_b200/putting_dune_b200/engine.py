@@ -1,0 +1,371 @@
+"""Batched environment state and the calls into the CUDA library.
+
+PyTorch is used for device memory, streams and (in ``bench.py``)
+``torch.distributed`` only; every computation on the simulator path happens in
+``libpdune_b200.so``.  There is no CPU fallback: constructing an ``EnvBatch``
+without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from putting_dune_b200 import _native as nat
+
+IMAGE_PARAM_NAMES = (
+    'intensity_exponent', 'gaussian_variance', 'jitter_rate',
+    'poisson_rate_multiplier', 'salt_and_pepper_amount', 'blur_amount',
+    'contrast_gamma', 'exponential_lambda', 'uniform_noise_scale')
+
+
+def _require_cuda(device) -> torch.device:
+  if not torch.cuda.is_available():
+    raise RuntimeError(
+        'putting_dune_b200 needs a CUDA device (sm_100a); there is no CPU '
+        'fallback for the simulator path.')
+  device = torch.device('cuda' if device is None else device)
+  if device.type != 'cuda':
+    raise RuntimeError(f'device must be a CUDA device, got {device}')
+  if device.index is None:
+    device = torch.device('cuda', torch.cuda.current_device())
+  return device
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+  return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Lattice:
+  """Shared graphene lattice tables on the device (graphene.py:464-559 and the
+  canonical 3-NN table replacing geometry.py:93-111)."""
+
+  def __init__(self, grid_columns: int = 50, device=None):
+    self.device = _require_cuda(device)
+    n_sites, n_rows = C.c_int32(), C.c_int32()
+    nat.check(nat.lib.pd_lattice_size(grid_columns, C.byref(n_sites),
+                                      C.byref(n_rows)))
+    self.grid_columns = grid_columns
+    self.n_sites = n_sites.value
+    self.n_rows = n_rows.value
+    with torch.cuda.device(self.device):
+      self.base_xy = torch.empty((self.n_sites, 2), dtype=torch.float64,
+                                 device=self.device)
+      self.nbr = torch.empty((self.n_sites, 4), dtype=torch.int32,
+                             device=self.device)
+      nat.check(nat.lib.pd_build_lattice(grid_columns, _ptr(self.base_xy),
+                                         _ptr(self.nbr),
+                                         _stream(self.device)))
+    self.c = nat.PdLattice(grid_columns, self.n_sites,
+                           self.base_xy.data_ptr(), self.nbr.data_ptr())
+
+
+@dataclasses.dataclass
+class MlpWeights:
+  """Learned rate model parameters (Haiku tree of learn_rates.py:80-99)."""
+  bn_scale: np.ndarray
+  bn_offset: np.ndarray
+  bn_mean: np.ndarray
+  bn_var: np.ndarray
+  w0: np.ndarray
+  b0: np.ndarray
+  w1: np.ndarray
+  b1: np.ndarray
+  w2: np.ndarray
+  b2: np.ndarray
+  batchnorm: bool = True
+
+  NAMES = ('bn_scale', 'bn_offset', 'bn_mean', 'bn_var', 'w0', 'b0', 'w1',
+           'b1', 'w2', 'b2')
+
+  @classmethod
+  def from_haiku(cls, params: dict, state: Optional[dict] = None,
+                 batchnorm: bool = True) -> 'MlpWeights':
+    """Builds weights from flat Haiku trees (names in SURVEY.md appendix
+    A.4): params['batch_norm']['scale'], state['batch_norm/~/mean_ema']
+    ['average'], params['mlp/~/linear_0']['w'] ..."""
+    d = np.asarray(params['mlp/~/linear_0']['w']).shape[0]
+    one, zero = np.ones(d, np.float32), np.zeros(d, np.float32)
+    bn = params.get('batch_norm', {})
+    st = state or {}
+    return cls(
+        bn_scale=np.asarray(bn.get('scale', one)).reshape(-1),
+        bn_offset=np.asarray(bn.get('offset', zero)).reshape(-1),
+        bn_mean=np.asarray(st.get('batch_norm/~/mean_ema', {}).get(
+            'average', zero)).reshape(-1),
+        bn_var=np.asarray(st.get('batch_norm/~/var_ema', {}).get(
+            'average', one)).reshape(-1),
+        w0=np.asarray(params['mlp/~/linear_0']['w']),
+        b0=np.asarray(params['mlp/~/linear_0']['b']),
+        w1=np.asarray(params['mlp/~/linear_1']['w']),
+        b1=np.asarray(params['mlp/~/linear_1']['b']),
+        w2=np.asarray(params['mlp/~/linear_2']['w']),
+        b2=np.asarray(params['mlp/~/linear_2']['b']),
+        batchnorm=batchnorm)
+
+
+class RateSpec:
+  """Selects the rate function for a stepping call (the reference's
+  ``RateFunction`` seam, graphene.py:52-78) and owns device copies of the
+  learned model's weights."""
+
+  def __init__(self, kind: int, *, mlp: Optional[MlpWeights] = None,
+               constant: Optional[Sequence[float]] = None, device=None):
+    self.kind = int(kind)
+    self.c = nat.PdRateConfig()
+    self.c.rate_fn = self.kind
+    self._mlp_c = None
+    self._tensors = {}
+    if self.kind == nat.RATE_CONSTANT:
+      if constant is None or len(constant) != 3:
+        raise ValueError('RATE_CONSTANT needs three rates')
+      for i, r in enumerate(constant):
+        self.c.constant_rates[i] = float(r)
+    if self.kind == nat.RATE_LEARNED:
+      if mlp is None:
+        raise ValueError('RATE_LEARNED needs MlpWeights')
+      device = _require_cuda(device)
+      d, h1 = mlp.w0.shape
+      h2 = mlp.w1.shape[1]
+      if mlp.w1.shape[0] != h1 or mlp.w2.shape != (h2, 4):
+        raise ValueError('inconsistent MLP shapes')
+      for name in MlpWeights.NAMES:
+        self._tensors[name] = torch.as_tensor(
+            np.ascontiguousarray(getattr(mlp, name), dtype=np.float32),
+            device=device)
+      self._mlp_c = nat.PdMlp(d, h1, h2, int(mlp.batchnorm),
+                              *[self._tensors[n].data_ptr()
+                                for n in MlpWeights.NAMES])
+      self.c.mlp = C.pointer(self._mlp_c)
+      self.mlp = mlp
+
+  @classmethod
+  def simple(cls):
+    return cls(nat.RATE_SIMPLE)
+
+  @classmethod
+  def prior(cls):
+    return cls(nat.RATE_PRIOR)
+
+
+@dataclasses.dataclass
+class StepResult:
+  """Device-resident outputs of one batched step."""
+  elapsed_us: torch.Tensor  # int64 [E]
+  transitions: torch.Tensor  # int32 [E]
+  events: torch.Tensor  # int32 [E]
+  recentred: torch.Tensor  # uint8 [E]
+  si_xy: torch.Tensor  # float64 [E, 2] material frame
+  log_count: Optional[torch.Tensor] = None  # int32 [E]
+  log_elapsed_us: Optional[torch.Tensor] = None  # int64 [E, K]
+  log_site: Optional[torch.Tensor] = None  # int32 [E, K]
+  log_ctrl: Optional[torch.Tensor] = None  # int32 [E, K]
+
+
+class EnvBatch:
+  """Struct-of-arrays state of ``num_envs`` independent simulators in HBM."""
+
+  STATE_FIELDS = ('si_idx', 'lattice', 'fov', 'fov_scale', 'image_params',
+                  'episode', 'ctrl_count', 'frame_count', 'sim_time_us',
+                  'n_events', 'n_transitions', 'status')
+
+  def __init__(self, num_envs: int, *, seed: int = 0, grid_columns: int = 50,
+               device=None, env_offset: int = 0,
+               lattice: Optional[Lattice] = None, log_capacity: int = 0):
+    self.device = _require_cuda(device)
+    self.num_envs = int(num_envs)
+    self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    self.env_offset = int(env_offset)
+    self.lattice_tables = lattice or Lattice(grid_columns, self.device)
+    self.log_capacity = int(log_capacity)
+    e, dev = self.num_envs, self.device
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+    self.si_idx = z((e,), torch.int32)
+    self.lattice = z((e, 4), torch.float64)
+    self.fov = z((e, 4), torch.float64)
+    self.fov_scale = z((e,), torch.float64)
+    self.image_params = z((e, 9), torch.float64)
+    self.episode = z((e,), torch.int32)  # bit pattern of uint32
+    self.ctrl_count = z((e,), torch.int32)
+    self.frame_count = z((e,), torch.int32)
+    self.sim_time_us = z((e,), torch.int64)
+    self.n_events = z((e,), torch.int64)
+    self.n_transitions = z((e,), torch.int64)
+    self.status = torch.full((e,), nat.ENV_NOT_RESET, dtype=torch.uint8,
+                             device=dev)
+    # Per-call outputs, allocated once.
+    self._out = StepResult(
+        elapsed_us=z((e,), torch.int64), transitions=z((e,), torch.int32),
+        events=z((e,), torch.int32), recentred=z((e,), torch.uint8),
+        si_xy=z((e, 2), torch.float64))
+    if self.log_capacity > 0:
+      k = self.log_capacity
+      self._out.log_count = z((e,), torch.int32)
+      self._out.log_elapsed_us = z((e, k), torch.int64)
+      self._out.log_site = z((e, k), torch.int32)
+      self._out.log_ctrl = z((e, k), torch.int32)
+    self._refresh_c()
+
+  # -- plumbing -------------------------------------------------------------
+  def _refresh_c(self) -> None:
+    self.c = nat.PdState(
+        self.num_envs, self.seed, self.env_offset, 0,
+        *[getattr(self, f).data_ptr() for f in self.STATE_FIELDS])
+    o = self._out
+    self._out_c = nat.PdStepOut(
+        o.elapsed_us.data_ptr(), o.transitions.data_ptr(),
+        o.events.data_ptr(), o.recentred.data_ptr(), o.si_xy.data_ptr(),
+        self.log_capacity, 0,
+        *[(t.data_ptr() if t is not None else None)
+          for t in (o.log_count, o.log_elapsed_us, o.log_site, o.log_ctrl)])
+
+  def _f64(self, x, shape) -> torch.Tensor:
+    t = torch.as_tensor(x, dtype=torch.float64, device=self.device)
+    return t.reshape(shape).contiguous()
+
+  def _dwell(self, dwell_us, shape):
+    """Returns (device int64 tensor or None, scalar)."""
+    if isinstance(dwell_us, (int, np.integer)):
+      return None, int(dwell_us)
+    t = torch.as_tensor(dwell_us, dtype=torch.int64, device=self.device)
+    return t.expand(shape).contiguous(), 0
+
+  # -- simulator calls ------------------------------------------------------
+  def reset(self, mask=None) -> None:
+    m = None
+    if mask is not None:
+      m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_reset(C.byref(self.lattice_tables.c),
+                                 C.byref(self.c), _ptr(m),
+                                 _stream(self.device)))
+
+  def rates(self, beam_xy, rate: RateSpec):
+    beam = self._f64(beam_xy, (self.num_envs, 2))
+    r = torch.empty((self.num_envs, 3), dtype=torch.float32,
+                    device=self.device)
+    nb = torch.empty((self.num_envs, 3), dtype=torch.int32,
+                     device=self.device)
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_rates(C.byref(self.lattice_tables.c),
+                                 C.byref(self.c), C.byref(rate.c), _ptr(beam),
+                                 _ptr(r), _ptr(nb), _stream(self.device)))
+    return r, nb
+
+  def apply_control(self, beam_xy, dwell_us, rate: RateSpec) -> StepResult:
+    beam = self._f64(beam_xy, (self.num_envs, 2))
+    d, scalar = self._dwell(dwell_us, (self.num_envs,))
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_apply_control(
+          C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+          _ptr(beam), _ptr(d), scalar, C.byref(self._out_c),
+          _stream(self.device)))
+    return self._out
+
+  def step_and_image(self, controls_xy, dwell_us, rate: RateSpec,
+                     image_duration_us: int = 2000000) -> StepResult:
+    ctl = self._f64(controls_xy, (self.num_envs, -1, 2))
+    n_controls = ctl.shape[1]
+    d, scalar = self._dwell(dwell_us, (self.num_envs, n_controls))
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_step_and_image(
+          C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+          _ptr(ctl), _ptr(d), scalar, n_controls, int(image_duration_us),
+          C.byref(self._out_c), _stream(self.device)))
+    return self._out
+
+  def rollout(self, controls_xy, dwell_us: int, rate: RateSpec,
+              image_duration_us: int = 2000000, record: bool = False):
+    """``n_steps`` single-control steps fused in one launch.
+
+    controls_xy: [T, E, 2] microscope frame.  Returns (si_idx [T, E],
+    elapsed_us [T, E]) if ``record`` else None.
+    """
+    ctl = self._f64(controls_xy, (-1, self.num_envs, 2))
+    t = ctl.shape[0]
+    si = el = None
+    if record:
+      si = torch.empty((t, self.num_envs), dtype=torch.int32,
+                       device=self.device)
+      el = torch.empty((t, self.num_envs), dtype=torch.int64,
+                       device=self.device)
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_rollout(
+          C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+          _ptr(ctl), int(dwell_us), t, int(image_duration_us), _ptr(si),
+          _ptr(el), _stream(self.device)))
+    return (si, el) if record else None
+
+  # -- queries --------------------------------------------------------------
+  def max_atoms_in_view(self) -> int:
+    """Upper bound on atoms inside any current FOV (density 0.382 / A^2
+    with margin for the boundary rows)."""
+    w = (self.fov[:, 2] - self.fov[:, 0]).max().item()
+    h = (self.fov[:, 3] - self.fov[:, 1]).max().item()
+    return int(0.382 * (w + 3.0) * (h + 3.0)) + 16
+
+  def get_atoms_in_bounds(self, fov=None, max_atoms: Optional[int] = None,
+                          with_sites: bool = False):
+    f = None if fov is None else self._f64(fov, (self.num_envs, 4))
+    if max_atoms is None:
+      if f is None:
+        max_atoms = self.max_atoms_in_view()
+      else:
+        w = (f[:, 2] - f[:, 0]).max().item()
+        h = (f[:, 3] - f[:, 1]).max().item()
+        max_atoms = int(0.382 * (w + 3.0) * (h + 3.0)) + 16
+      max_atoms = min(max_atoms, self.lattice_tables.n_sites)
+    e, dev = self.num_envs, self.device
+    xy = torch.zeros((e, max_atoms, 2), dtype=torch.float64, device=dev)
+    z = torch.zeros((e, max_atoms), dtype=torch.uint8, device=dev)
+    site = (torch.zeros((e, max_atoms), dtype=torch.int32, device=dev)
+            if with_sites else None)
+    count = torch.zeros((e,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+      nat.check(nat.lib.pd_get_atoms_in_bounds(
+          C.byref(self.lattice_tables.c), C.byref(self.c), _ptr(f), max_atoms,
+          _ptr(xy), _ptr(z), _ptr(site), _ptr(count), _stream(dev)))
+    return (xy, z, count, site) if with_sites else (xy, z, count)
+
+  def silicon_position(self) -> torch.Tensor:
+    out = torch.empty((self.num_envs, 2), dtype=torch.float64,
+                      device=self.device)
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_get_silicon_position(
+          C.byref(self.lattice_tables.c), C.byref(self.c), _ptr(out),
+          _stream(self.device)))
+    return out
+
+  def grid_positions(self, env_ids) -> torch.Tensor:
+    ids = torch.as_tensor(env_ids, dtype=torch.int32,
+                          device=self.device).reshape(-1).contiguous()
+    out = torch.empty((ids.numel(), self.lattice_tables.n_sites, 2),
+                      dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_get_grid(
+          C.byref(self.lattice_tables.c), C.byref(self.c), _ptr(ids),
+          ids.numel(), _ptr(out), _stream(self.device)))
+    return out
+
+  # -- checkpoint / resume --------------------------------------------------
+  def state_dict(self) -> dict:
+    d = {f: getattr(self, f).detach().cpu().clone() for f in self.STATE_FIELDS}
+    d.update(seed=self.seed, env_offset=self.env_offset,
+             grid_columns=self.lattice_tables.grid_columns)
+    return d
+
+  def load_state_dict(self, d: dict) -> None:
+    if d['grid_columns'] != self.lattice_tables.grid_columns:
+      raise ValueError('grid_columns mismatch')
+    for f in self.STATE_FIELDS:
+      getattr(self, f).copy_(d[f])
+    self.seed, self.env_offset = int(d['seed']), int(d['env_offset'])
+    self._refresh_c()

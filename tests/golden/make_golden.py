@@ -1,0 +1,148 @@
+"""Generates the golden vectors under tests/golden/ from the UNMODIFIED
+reference (build container only; needs /root/reference).
+
+    python tests/golden/make_golden.py
+
+For each rate function the reference's own PuttingDuneSimulator /
+PristineSingleDopedGraphene run one env at a time under ``InjectedRng``
+(oracle/refrun.py); the closed-loop beam controls (Si position + U(-1,1)^2 bond
+lengths, dwell 1.5 s / 5 s alternating by env) are produced once and stored, so
+the fixtures are self-contained: nothing at test time reads the reference.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(
+    __file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import pdune_oracle as po  # pylint: disable=g-import-not-at-top
+from oracle import refrun
+from oracle import refshim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None):
+  """Controls that follow the Si (RelativeToSilicon-style), from the oracle."""
+  st = po.make_state(n_envs, seed)
+  po.reset(st)
+  rng = np.random.default_rng(ctrl_seed)
+  controls = np.zeros((n_steps, n_envs, 1, 2))
+  dwell = np.zeros((n_steps, n_envs, 1), dtype=np.int64)
+  for t in range(n_steps):
+    p = po.site_positions(st, st.si_idx, np.arange(n_envs))
+    q = po.material_to_microscope(st.fov, p)
+    a = rng.uniform(-1, 1, size=(n_envs, 2))
+    controls[t, :, 0] = q + a * po.BOND / st.fov_scale[:, None]
+    dwell[t, :, 0] = np.where(np.arange(n_envs) % 2 == 0, 1500000, 5000000)
+    po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn, mlp=mlp)
+  return controls, dwell
+
+
+def events_fixture(name, rate_fn, seed, n_envs, n_steps, mlp=None):
+  controls, dwell = closed_loop_controls(seed, n_envs, n_steps, rate_fn,
+                                         ctrl_seed=seed + 1, mlp=mlp)
+  out = {k: [] for k in ('si0', 'fov0', 'fov_scale', 'image_params', 'si',
+                         'elapsed_us', 'fov', 'n_observed', 'sample_positions',
+                         'obs0_positions', 'obs0_numbers')}
+  trans = []
+  for e in range(n_envs):
+    r = refrun.run_reference_env(seed, e, controls[:, e], dwell[:, e], rate_fn,
+                                 mlp=mlp)
+    for k in ('si0', 'fov0', 'fov_scale', 'image_params', 'si', 'elapsed_us',
+              'fov', 'n_observed'):
+      out[k].append(r[k])
+    out['sample_positions'].append(r['positions'][[0, 1, 940, 1880]])
+    if e < 4:
+      out['obs0_positions'].append(r['obs0_positions'])
+      out['obs0_numbers'].append(r['obs0_numbers'])
+    t = r['transitions']
+    trans.append(np.concatenate([np.full((t.shape[0], 1), e), t], axis=1))
+  arrays = {k: np.asarray(v) for k, v in out.items()
+            if k not in ('obs0_positions', 'obs0_numbers')}
+  for i, (p, z) in enumerate(zip(out['obs0_positions'], out['obs0_numbers'])):
+    arrays[f'obs0_positions_{i}'] = p
+    arrays[f'obs0_numbers_{i}'] = z
+  arrays['transitions'] = np.concatenate(trans, axis=0)  # env, ctrl, us, site
+  arrays['controls'] = controls
+  arrays['dwell_us'] = dwell
+  arrays['seed'] = np.int64(seed)
+  arrays['rate_fn'] = np.int64(rate_fn)
+  np.savez_compressed(os.path.join(HERE, name), **arrays)
+  print(name, 'envs', n_envs, 'steps', n_steps, 'transitions',
+        arrays['transitions'].shape[0])
+
+
+def rates_fixture():
+  """Rates of the reference's own rate functions at scattered beam offsets."""
+  mods = refshim.load_reference()
+  table = po.neighbor_table(50)
+  refrun.install_canonical_neighbors(mods, table)
+  seed, n = 77, 64
+  st = po.make_state(n, seed)
+  po.reset(st)
+  rng = np.random.default_rng(5)
+  beam = po.site_positions(st, st.si_idx, np.arange(n)) + rng.uniform(
+      -2.5, 2.5, size=(n, 2))
+  mlp = po.MlpParams.synthetic(3, hidden=(32, 32))
+  res = {'beam': beam, 'seed': np.int64(seed)}
+  for name, rate_fn in (('simple', po.RATE_SIMPLE), ('prior', po.RATE_PRIOR),
+                        ('learned', po.RATE_LEARNED)):
+    fn = refrun.make_rate_function(mods, rate_fn, mlp)
+    rates = np.zeros((n, 3), dtype=np.float32)
+    succ = np.zeros((n, 3), dtype=np.int32)
+    for e in range(n):
+      pos = po.all_positions(st, e)
+      z = np.full(pos.shape[0], 6)
+      z[st.si_idx[e]] = 14
+      grid = mods.microscope_utils.AtomicGrid(pos, z)
+      out = fn(grid, mods.Point(beam[e, 0], beam[e, 1]))
+      rates[e] = [s.rate for s in out.successor_states]
+      succ[e] = [int(np.argmax(s.grid.atomic_numbers == 14))
+                 for s in out.successor_states]
+    res[f'rates_{name}'] = rates
+    res[f'succ_{name}'] = succ
+  for k in MLP_FIELDS:
+    res[f'mlp_{k}'] = getattr(mlp, k)
+  refrun.uninstall_canonical_neighbors(mods)
+  np.savez_compressed(os.path.join(HERE, 'rates_reference.npz'), **res)
+  print('rates_reference.npz', n)
+
+
+MLP_FIELDS = ('bn_scale', 'bn_offset', 'bn_mean', 'bn_var', 'w0', 'b0', 'w1',
+              'b1', 'w2', 'b2')
+
+
+def standardize_fixture():
+  """standardize_beam_and_neighbors of the reference on random inputs."""
+  fn = refshim.reference_standardize_beam_and_neighbors()
+  rng = np.random.default_rng(11)
+  n = 256
+  ang0 = rng.uniform(0, 2 * np.pi, size=n)
+  nbr = np.stack([np.stack((np.cos(ang0 + k * 2 * np.pi / 3),
+                            np.sin(ang0 + k * 2 * np.pi / 3)), axis=1)
+                  for k in range(3)], axis=1) * po.BOND
+  nbr = nbr[:, rng.permutation(3)]
+  beam = rng.uniform(-1.5, 1.5, size=(n, 2))
+  nb, nn, order = [], [], []
+  for i in range(n):
+    a, b, c = fn(beam[i:i + 1], nbr[i])
+    nb.append(a[0]); nn.append(b); order.append(c)
+  np.savez_compressed(os.path.join(HERE, 'standardize_reference.npz'),
+                      beam=beam, nbr=nbr, new_beam=np.asarray(nb),
+                      new_nbr=np.asarray(nn), order=np.asarray(order))
+  print('standardize_reference.npz', n)
+
+
+if __name__ == '__main__':
+  if not refshim.reference_available():
+    sys.exit('reference not available; golden vectors are generated only in '
+             'the build container')
+  events_fixture('events_simple.npz', po.RATE_SIMPLE, 2024, 32, 30)
+  events_fixture('events_prior.npz', po.RATE_PRIOR, 2025, 32, 30)
+  rates_fixture()
+  standardize_fixture()

@@ -1,0 +1,342 @@
+"""GPU parity tests of the event path, through the C ABI, against the oracle
+and the committed reference golden vectors.
+
+Bars (BASELINE.json north_star): bit-exact Si lattice index, chosen
+transition, event counts and microsecond clocks; float64 geometry within
+1e-13 A; float32 rates: simple bit-exact, human prior |d| <= 2e-6*max + 1e-12.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdune_oracle as po
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+  from putting_dune_b200 import engine
+  return engine
+
+
+def test_lattice_tables_bit_exact(eng):
+  for cols in (50, 10, 13):
+    lat = eng.Lattice(cols)
+    np.testing.assert_array_equal(gh.np_(lat.base_xy), po.base_lattice(cols))
+    np.testing.assert_array_equal(gh.np_(lat.nbr)[:, :3],
+                                  po.neighbor_table(cols))
+
+
+def test_reset_matches_oracle(eng):
+  n, seed = 4096, 11
+  st = po.make_state(n, seed, env_offset=1000)
+  po.reset(st)
+  b = eng.EnvBatch(n, seed=seed, env_offset=1000)
+  b.reset()
+  np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+  # offsets are pure arithmetic (exact); cos/sin may differ in the last ulp
+  np.testing.assert_array_equal(gh.np_(b.lattice)[:, :2], st.lattice[:, :2])
+  np.testing.assert_allclose(gh.np_(b.lattice)[:, 2:], st.lattice[:, 2:],
+                             rtol=0, atol=3e-16)
+  np.testing.assert_array_equal(gh.np_(b.fov_scale), st.fov_scale)
+  np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+  np.testing.assert_allclose(gh.np_(b.image_params), st.image_params,
+                             rtol=1e-15, atol=0)
+  assert (gh.np_(b.status) == 0).all()
+  assert (gh.np_(b.episode) == 1).all()
+  # masked second reset: only masked envs advance their episode
+  mask = np.arange(n) % 3 == 0
+  po.reset(st, mask)
+  b.reset(mask)
+  np.testing.assert_array_equal(gh.np_(b.episode), st.episode.astype(np.int32))
+  np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+  np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+
+
+def test_rates_match_oracle_and_reference_golden(eng, golden_dir):
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  for name, rate_fn in (('simple', po.RATE_SIMPLE), ('prior', po.RATE_PRIOR)):
+    r, nb = b.rates(fix['beam'], gh.rate_spec(rate_fn))
+    r, nb = gh.np_(r), gh.np_(nb)
+    want, _ = po.rates_for(st, np.arange(n), fix['beam'], rate_fn)
+    np.testing.assert_array_equal(nb, fix[f'succ_{name}'])
+    if rate_fn == po.RATE_SIMPLE:
+      np.testing.assert_array_equal(r, want)
+      np.testing.assert_array_equal(r, fix['rates_simple'])
+    else:
+      tol = 2e-6 * want.max() + 1e-12
+      assert np.abs(r - want).max() <= tol
+      assert np.abs(r - fix['rates_prior']).max() <= tol
+
+
+@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz'])
+def test_reference_golden_trajectories(eng, golden_dir, name):
+  """The reference's own trajectories, replayed through the C ABI with the
+  device doing its own reset."""
+  fix = np.load(os.path.join(golden_dir, name))
+  controls, dwell = fix['controls'], fix['dwell_us']
+  n_steps, n = controls.shape[:2]
+  b = eng.EnvBatch(n, seed=int(fix['seed']), log_capacity=64)
+  b.reset()
+  np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si0'])
+  np.testing.assert_allclose(gh.np_(b.fov), fix['fov0'], rtol=0, atol=1e-13)
+  np.testing.assert_allclose(gh.np_(b.image_params), fix['image_params'],
+                             rtol=1e-15)
+  spec = gh.rate_spec(int(fix['rate_fn']))
+  trans = []
+  for t in range(n_steps):
+    out = b.step_and_image(controls[t], dwell[t], spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si'][:, t])
+    np.testing.assert_array_equal(gh.np_(out.elapsed_us),
+                                  fix['elapsed_us'][:, t])
+    np.testing.assert_allclose(gh.np_(b.fov), fix['fov'][:, t], rtol=0,
+                               atol=1e-13)
+    cnt = gh.np_(out.log_count)
+    el, site = gh.np_(out.log_elapsed_us), gh.np_(out.log_site)
+    for e in np.nonzero(cnt)[0]:
+      for k in range(cnt[e]):
+        trans.append((e, t, el[e, k], site[e, k]))
+  want = fix['transitions']
+  want = want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
+  got = np.asarray(sorted(trans), dtype=np.int64)
+  np.testing.assert_array_equal(got, want)
+  xy, z, count = b.get_atoms_in_bounds()
+  np.testing.assert_array_equal(gh.np_(count), fix['n_observed'][:, -1])
+
+
+@pytest.mark.parametrize('rate_fn', [po.RATE_SIMPLE, po.RATE_PRIOR])
+def test_config2_parity_4096_envs(eng, rate_fn):
+  """BASELINE config 2: 4096 envs, injected-RNG parity over 100 steps."""
+  n, n_steps, seed = 4096, 100, 42 + rate_fn
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  spec = gh.rate_spec(rate_fn)
+  rng = np.random.default_rng(1)
+  dwell = np.where(np.arange(n) % 2 == 0, 1500000, 5000000)[:, None]
+  for t in range(n_steps):
+    ctl = gh.closed_loop_control(st, rng)[:, None, :]
+    want = po.step_and_image(st, ctl, dwell, rate_fn=rate_fn)
+    out = b.step_and_image(ctl, dwell, spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+    np.testing.assert_array_equal(gh.np_(out.elapsed_us), want['elapsed_us'])
+    np.testing.assert_array_equal(gh.np_(out.transitions),
+                                  want['transitions'])
+    np.testing.assert_array_equal(gh.np_(out.events), want['events'])
+    np.testing.assert_array_equal(gh.np_(out.recentred).astype(bool),
+                                  want['recentred'])
+  np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+  np.testing.assert_array_equal(gh.np_(b.n_events), st.n_events)
+  np.testing.assert_array_equal(gh.np_(b.n_transitions), st.n_transitions)
+  np.testing.assert_array_equal(gh.np_(b.sim_time_us), st.sim_time_us)
+  np.testing.assert_array_equal(gh.np_(b.ctrl_count),
+                                st.ctrl_count.astype(np.int32))
+  assert st.n_transitions.sum() > 1000
+
+
+def test_multiple_controls_and_ragged_dwell(eng):
+  n, seed = 1000, 5  # not a multiple of the block size
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st, log_capacity=32)
+  rng = np.random.default_rng(2)
+  ctl = np.stack([gh.closed_loop_control(st, rng) for _ in range(3)], axis=1)
+  dwell = rng.integers(0, 6000000, size=(n, 3))
+  dwell[::7, 1] = 0  # zero dwell: no rate evaluation at all
+  want = po.step_and_image(st, ctl, dwell)
+  out = b.step_and_image(ctl, dwell, gh.rate_spec(po.RATE_SIMPLE))
+  np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+  np.testing.assert_array_equal(gh.np_(out.elapsed_us), want['elapsed_us'])
+  np.testing.assert_array_equal(gh.np_(out.events), want['events'])
+  np.testing.assert_array_equal(gh.np_(b.ctrl_count),
+                                st.ctrl_count.astype(np.int32))
+  # the transition log names the control each hop happened in
+  cnt = gh.np_(out.log_count)
+  np.testing.assert_array_equal(cnt, want['transitions'])
+  assert gh.np_(out.log_ctrl)[cnt > 0].max() <= 2
+
+
+def test_empty_and_no_control_edge_cases(eng):
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  b0 = eng.EnvBatch(0)
+  b0.reset()
+  b0.step_and_image(np.zeros((0, 1, 2)), 1500000, spec)
+  b = eng.EnvBatch(8, seed=1)
+  b.reset()
+  si = gh.np_(b.si_idx).copy()
+  out = b.step_and_image(np.zeros((8, 0, 2)), 0, spec, 2000000)
+  np.testing.assert_array_equal(gh.np_(out.elapsed_us), 2000000)
+  np.testing.assert_array_equal(gh.np_(b.si_idx), si)
+  assert (gh.np_(b.ctrl_count) == 0).all()
+
+
+def test_constant_rate_seam_reproduces_reference_tests(eng):
+  # simulator_test.py:147-168: zero rates => elapsed = sum(dwell) + image.
+  b = eng.EnvBatch(16, seed=3)
+  b.reset()
+  zero = gh.rate_spec(po.RATE_CONSTANT, constant=(0.0, 0.0, 0.0))
+  ctl = np.full((16, 3, 2), 0.5)
+  dwell = np.tile(np.array([[1500000, 3000000, 7230000]]), (16, 1))
+  out = b.step_and_image(ctl, dwell, zero, 3500000)
+  np.testing.assert_array_equal(gh.np_(out.elapsed_us), 15230000)
+  assert (gh.np_(out.transitions) == 0).all()
+  assert (gh.np_(out.events) == 3).all()
+  # graphene_test.py:228-281: rate 5 => several hops within the dwell.
+  st = po.make_state(256, seed=9)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  five_o = lambda s, idx, beam, it: (np.full((idx.size, 3), 5.0, np.float32),
+                                     s.nbr[s.si_idx[idx]])
+  want = po.apply_control(st, np.zeros((256, 2)), np.full(256, 1500000),
+                          rates_override=five_o)
+  out = b.apply_control(np.zeros((256, 2)), 1500000,
+                        gh.rate_spec(po.RATE_CONSTANT, constant=(5, 5, 5)))
+  np.testing.assert_array_equal(gh.np_(out.transitions), want['transitions'])
+  np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+  assert want['transitions'].mean() > 10
+  # negative rates: the reference asserts; the batch flags the env instead.
+  bad = gh.rate_spec(po.RATE_CONSTANT, constant=(-1.0, 1.0, 1.0))
+  b.apply_control(np.zeros((256, 2)), 1000, bad)
+  assert (gh.np_(b.status) & 1).all()
+
+
+def test_rollout_equals_repeated_steps(eng):
+  n, t_steps, seed = 5000, 12, 8
+  rng = np.random.default_rng(4)
+  ctl = 0.5 + rng.uniform(-0.08, 0.08, size=(t_steps, n, 2))
+  for rate_fn in (po.RATE_SIMPLE, po.RATE_PRIOR):
+    spec = gh.rate_spec(rate_fn)
+    a = eng.EnvBatch(n, seed=seed)
+    b = eng.EnvBatch(n, seed=seed)
+    a.reset()
+    b.reset()
+    si, el = a.rollout(ctl, 1500000, spec, record=True)
+    for t in range(t_steps):
+      out = b.step_and_image(ctl[t][:, None, :], 1500000, spec)
+      np.testing.assert_array_equal(gh.np_(si[t]), gh.np_(b.si_idx))
+      np.testing.assert_array_equal(gh.np_(el[t]), gh.np_(out.elapsed_us))
+    for f in ('si_idx', 'fov', 'ctrl_count', 'sim_time_us', 'n_events',
+              'n_transitions'):
+      np.testing.assert_array_equal(gh.np_(getattr(a, f)),
+                                    gh.np_(getattr(b, f)))
+
+
+def test_staged_and_global_table_paths_agree(eng):
+  """Large batches stage the lattice in shared memory; results must not
+  depend on the path (size-independent property at full size)."""
+  n, seed = 300000, 13
+  big = eng.EnvBatch(n, seed=seed)
+  big.reset()
+  small = eng.EnvBatch(2048, seed=seed)
+  small.reset()
+  rng = np.random.default_rng(6)
+  ctl = 0.5 + rng.uniform(-0.06, 0.06, size=(n, 1, 2))
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  o_big = big.step_and_image(ctl, 5000000, spec)
+  o_small = small.step_and_image(ctl[:2048], 5000000, spec)
+  np.testing.assert_array_equal(gh.np_(big.si_idx)[:2048],
+                                gh.np_(small.si_idx))
+  np.testing.assert_array_equal(gh.np_(o_big.elapsed_us)[:2048],
+                                gh.np_(o_small.elapsed_us))
+  # every hop lands on one of the three neighbours of the previous site
+  tr = gh.np_(o_big.transitions)
+  assert tr.sum() > n // 2 and tr.max() >= 4
+
+
+def test_sharding_invariance(eng):
+  """Philox is keyed by the global env id: a shard reproduces its slice."""
+  seed = 21
+  full = eng.EnvBatch(4096, seed=seed)
+  shard = eng.EnvBatch(1024, seed=seed, env_offset=2048)
+  full.reset()
+  shard.reset()
+  ctl = np.full((4096, 1, 2), 0.52)
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  for _ in range(5):
+    full.step_and_image(ctl, 5000000, spec)
+    shard.step_and_image(ctl[:1024], 5000000, spec)
+  np.testing.assert_array_equal(gh.np_(full.si_idx)[2048:3072],
+                                gh.np_(shard.si_idx))
+  np.testing.assert_array_equal(gh.np_(full.sim_time_us)[2048:3072],
+                                gh.np_(shard.sim_time_us))
+
+
+def test_queries_match_oracle(eng):
+  n, seed = 64, 17
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  np.testing.assert_allclose(
+      gh.np_(b.silicon_position()),
+      po.site_positions(st, st.si_idx, np.arange(n)), rtol=0, atol=0)
+  xy, z, count, site = b.get_atoms_in_bounds(with_sites=True)
+  xy, z, count, site = gh.np_(xy), gh.np_(z), gh.np_(count), gh.np_(site)
+  for e in range(n):
+    q, zz, idx = po.get_atoms_in_bounds(st, e)
+    assert count[e] == q.shape[0]
+    np.testing.assert_array_equal(site[e, :count[e]], idx)
+    np.testing.assert_array_equal(z[e, :count[e]], zz)
+    np.testing.assert_array_equal(xy[e, :count[e]], q)
+  # arbitrary (non-square, partly off-sheet) windows
+  fov = np.tile(np.array([[-5.5, -6.3, 12.0, 9.1]]), (n, 1))
+  fov[1] = [20.0, 20.0, 60.0, 60.0]
+  fov[2] = [100.0, 100.0, 110.0, 110.0]  # empty
+  xy, z, count = b.get_atoms_in_bounds(fov)
+  count = gh.np_(count)
+  for e in range(4):
+    q, zz, _ = po.get_atoms_in_bounds(st, e, fov[e])
+    assert count[e] == q.shape[0]
+    np.testing.assert_array_equal(gh.np_(xy)[e, :count[e]], q)
+  assert count[2] == 0
+  g = gh.np_(b.grid_positions([0, 5]))
+  np.testing.assert_array_equal(g[1], po.all_positions(st, 5))
+
+
+def test_host_buffer_entry_point(eng):
+  """pd_step_and_image_host: host controls in, host observation out."""
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  n, seed = 2048, 23
+  a = eng.EnvBatch(n, seed=seed)
+  b = eng.EnvBatch(n, seed=seed)
+  a.reset()
+  b.reset()
+  spec = gh.rate_spec(po.RATE_PRIOR)
+  ctl = torch.full((n, 1, 2), 0.5, dtype=torch.float64).pin_memory()
+  d_ctl = torch.empty((n, 1, 2), dtype=torch.float64, device=b.device)
+  h_el = torch.empty(n, dtype=torch.int64).pin_memory()
+  h_xy = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+  h_fov = torch.empty((n, 4), dtype=torch.float64).pin_memory()
+  P = lambda t: C.c_void_p(t.data_ptr())
+  nat.check(nat.lib.pd_step_and_image_host(
+      C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(ctl), None,
+      5000000, 1, 2000000, P(d_ctl), None, C.byref(b._out_c), P(h_el),
+      P(h_xy), P(h_fov), None))
+  out = a.step_and_image(ctl, 5000000, spec)
+  np.testing.assert_array_equal(h_el.numpy(), gh.np_(out.elapsed_us))
+  np.testing.assert_array_equal(h_xy.numpy(), gh.np_(out.si_xy))
+  np.testing.assert_array_equal(h_fov.numpy(), gh.np_(a.fov))
+
+
+def test_checkpoint_resume(eng):
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  a = eng.EnvBatch(512, seed=31)
+  a.reset()
+  ctl = np.full((512, 1, 2), 0.51)
+  a.step_and_image(ctl, 5000000, spec)
+  saved = a.state_dict()
+  b = eng.EnvBatch(512, seed=0)
+  b.load_state_dict(saved)
+  a.step_and_image(ctl, 5000000, spec)
+  b.step_and_image(ctl, 5000000, spec)
+  np.testing.assert_array_equal(gh.np_(a.si_idx), gh.np_(b.si_idx))
+  np.testing.assert_array_equal(gh.np_(a.sim_time_us), gh.np_(b.sim_time_us))

@@ -1,0 +1,257 @@
+"""CPU tests: the oracle against the reference's golden vectors.
+
+The fixtures under tests/golden/ were produced by the unmodified reference
+(tests/golden/make_golden.py); the known-answer cases restate the goldens of
+the reference's own tests.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pdune_oracle as po
+
+
+# -- Philox4x32-10 known-answer vectors (Random123 kat_vectors) ---------------
+@pytest.mark.parametrize('ctr,key,want', [
+    ([0, 0, 0, 0], [0, 0],
+     [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2,
+     [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+     [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+])
+def test_philox_kat(ctr, key, want):
+  got = po.philox4x32_10(*[np.uint32(c) for c in ctr], key[0], key[1])
+  assert [int(g) for g in got] == want
+
+
+def test_u53_range_and_exactness():
+  assert po.u53(0, 0) == 0.0
+  assert po.u53(0xffffffff, 0xffffffff) == 1.0 - 2.0**-53
+
+
+# -- lattice facts --------------------------------------
+def test_lattice_shape_and_bonds():
+  base = po.base_lattice(50)
+  assert base.shape == (1881, 2)
+  tab = po.neighbor_table(50)
+  d = np.linalg.norm(base[tab] - base[:, None, :], axis=2)
+  interior = d[:, 2] < 1.43
+  assert (~interior).sum() == 121  # edge sites with < 3 bonded neighbours
+  # graphene_test.py:41-87: three neighbours at exactly one bond length.
+  np.testing.assert_allclose(d[interior], 1.42, atol=1e-7)
+  # canonical order: ascending index among equidistant neighbours
+  assert (np.diff(tab[interior], axis=1) > 0).all()
+
+
+def test_si_never_initialised_on_edge():
+  # graphene_test.py:283-299 (grid_columns=10, many resets)
+  st = po.make_state(100, seed=3, num_cols=10)
+  po.reset(st)
+  p = po.site_positions(st, st.nbr[st.si_idx], np.arange(100))
+  c = po.site_positions(st, st.si_idx, np.arange(100))
+  d = np.linalg.norm(p - c[:, None, :], axis=2)
+  assert (d[:, 2] <= 1.42 + 1e-3).all()
+
+
+# -- event-path golden vectors from the reference ------------------------------
+def _replay(fix):
+  seed = int(fix['seed'])
+  rate_fn = int(fix['rate_fn'])
+  controls, dwell = fix['controls'], fix['dwell_us']
+  n_steps, n_envs = controls.shape[:2]
+  st = po.make_state(n_envs, seed)
+  po.reset(st)
+  reset_state = dict(si=st.si_idx.copy(), fov=st.fov.copy(),
+                     scale=st.fov_scale.copy(), ip=st.image_params.copy())
+  log = po.EventLog([], [], [], [], [], [])
+  si = np.zeros((n_envs, n_steps), np.int32)
+  el = np.zeros((n_envs, n_steps), np.int64)
+  fov = np.zeros((n_envs, n_steps, 4))
+  for t in range(n_steps):
+    out = po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn,
+                            log=log)
+    si[:, t], el[:, t], fov[:, t] = st.si_idx, out['elapsed_us'], st.fov
+  trans = sorted(zip(log.env, log.ctrl_seq, log.elapsed_us, log.new_si))
+  return st, reset_state, si, el, fov, np.asarray(trans, dtype=np.int64)
+
+
+@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz'])
+def test_oracle_matches_reference_trajectories(golden_dir, name):
+  fix = np.load(os.path.join(golden_dir, name))
+  st, r0, si, el, fov, trans = _replay(fix)
+  # reset: Si site, FOV, image parameters
+  np.testing.assert_array_equal(r0['si'], fix['si0'])
+  np.testing.assert_allclose(r0['fov'], fix['fov0'], rtol=0, atol=1e-13)
+  np.testing.assert_allclose(r0['scale'], fix['fov_scale'], rtol=0, atol=0)
+  np.testing.assert_allclose(r0['ip'], fix['image_params'], rtol=0, atol=0)
+  # bit-exact: Si lattice index, microsecond clocks, transition log
+  np.testing.assert_array_equal(si, fix['si'])
+  np.testing.assert_array_equal(el, fix['elapsed_us'])
+  want = fix['transitions']
+  want = want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
+  np.testing.assert_array_equal(trans, want)
+  np.testing.assert_allclose(fov, fix['fov'], rtol=0, atol=1e-13)
+  # lattice positions of a few sites (BLAS matmul rounding in the reference)
+  for e in range(si.shape[0]):
+    p = po.all_positions(st, e)[[0, 1, 940, 1880]]
+    np.testing.assert_allclose(p, fix['sample_positions'][e], rtol=0,
+                               atol=2e-14)
+  # observed grid right after reset for the first envs
+  st2 = po.make_state(4, int(fix['seed']))
+  po.reset(st2)
+  for e in range(4):
+    q, z, _ = po.get_atoms_in_bounds(st2, e)
+    np.testing.assert_array_equal(z, fix[f'obs0_numbers_{e}'])
+    np.testing.assert_allclose(q, fix[f'obs0_positions_{e}'], rtol=0,
+                               atol=1e-13)
+
+
+def test_oracle_rates_match_reference(golden_dir):
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  mlp = po.MlpParams(**{k: fix[f'mlp_{k}'] for k in (
+      'bn_scale', 'bn_offset', 'bn_mean', 'bn_var', 'w0', 'b0', 'w1', 'b1',
+      'w2', 'b2')})
+  envs = np.arange(n)
+  for name, rate_fn, rtol in (('simple', po.RATE_SIMPLE, 0.0),
+                              ('prior', po.RATE_PRIOR, 1e-6),
+                              ('learned', po.RATE_LEARNED, 1e-6)):
+    r32, nbr = po.rates_for(st, envs, fix['beam'], rate_fn, mlp)
+    np.testing.assert_array_equal(nbr, fix[f'succ_{name}'])
+    want = fix[f'rates_{name}']
+    if rtol == 0.0:
+      np.testing.assert_array_equal(r32, want)
+    else:
+      np.testing.assert_allclose(r32, want, rtol=rtol, atol=1e-30)
+
+
+def test_standardize_matches_reference(golden_dir):
+  fix = np.load(os.path.join(golden_dir, 'standardize_reference.npz'))
+  nb, nn, order = po.standardize_beam_and_neighbors(fix['beam'], fix['nbr'])
+  np.testing.assert_array_equal(order, fix['order'])
+  np.testing.assert_allclose(nb, fix['new_beam'], rtol=0, atol=1e-14)
+  np.testing.assert_allclose(nn, fix['new_nbr'], rtol=0, atol=1e-14)
+
+
+# -- known-answer cases restated from the reference's own tests ----------------
+@pytest.mark.parametrize('nbr,order,beam,new_beam,new_nbr', [
+    # data_utils_test.py:149-198 'aligned'
+    ([[1, 0], [-0.5, np.sqrt(3) / 2], [-0.5, -np.sqrt(3) / 2]], [0, 1, 2],
+     [1, 0], [1.0, 0.0],
+     [[1, 0], [-0.5, np.sqrt(3) / 2], [-0.5, -np.sqrt(3) / 2]]),
+    # 'rotated'
+    ([[0.5, np.sqrt(3) / 2], [0.5, -np.sqrt(3) / 2], [-1.0, 0.0]], [0, 2, 1],
+     [0, 1], [np.sqrt(3) / 2, 0.5],
+     [[1.0, 0.0], [-0.5, -np.sqrt(3) / 2], [-0.5, np.sqrt(3) / 2]]),
+])
+def test_standardize_goldens(nbr, order, beam, new_beam, new_nbr):
+  nb, nn, od = po.standardize_beam_and_neighbors(
+      np.asarray([beam], dtype=float), np.asarray([nbr], dtype=float))
+  np.testing.assert_allclose(nb[0], new_beam, rtol=1e-6)
+  np.testing.assert_allclose(nn[0], new_nbr, atol=1e-9)
+  np.testing.assert_array_equal(od[0], order)
+
+
+def test_geometry_goldens():
+  # geometry_test.py:25-59
+  xy = np.array([[1.0, 0.0], [0.0, -1.0], [-1.0, -1.0]])
+  np.testing.assert_allclose(po.get_angles(xy),
+                             [0.0, -np.pi / 2, -3 * np.pi / 4])
+  np.testing.assert_allclose(po.rotate_coordinates(xy, np.pi / 2),
+                             [[0.0, 1.0], [1.0, 0.0], [1.0, -1.0]],
+                             atol=1e-12)
+
+
+def test_frame_transform_goldens():
+  # microscope_utils_test.py:121-288: FOV [(-5, 0), (5, 20)]
+  fov = np.array([[-5.0, 0.0, 5.0, 20.0]])
+  np.testing.assert_allclose(
+      po.microscope_to_material(fov, np.array([[0.5, 1.0]])), [[0.0, 20.0]])
+  np.testing.assert_allclose(
+      po.microscope_to_material(fov, np.array([[-3.0, 2.5]])),
+      [[-35.0, 50.0]])
+  # simulator_test.py:86-115: (0, 1) in FOV [(-5.5, -6.3), (12, 9.1)]
+  fov = np.array([[-5.5, -6.3, 12.0, 9.1]])
+  np.testing.assert_allclose(
+      po.microscope_to_material(fov, np.array([[0.0, 1.0]])), [[-5.5, 9.1]])
+  back = po.material_to_microscope(fov, np.array([[-5.5, 9.1]]))
+  np.testing.assert_allclose(back, [[0.0, 1.0]], atol=1e-15)
+
+
+def test_simple_rate_closed_forms():
+  # graphene.py:151-166: beam on a neighbour -> 1; beam on the Si -> 1/17.
+  p_si = np.zeros((1, 2))
+  p_n = po.BOND * np.array([[[1.0, 0.0], [-0.5, np.sqrt(3) / 2],
+                             [-0.5, -np.sqrt(3) / 2]]])
+  r = po.simple_rates(p_n[:, 0], p_si, p_n)
+  assert r[0, 0] == 1.0
+  r = po.simple_rates(p_si, p_si, p_n)
+  np.testing.assert_allclose(r[0], 1 / 17, rtol=1e-14)
+
+
+def test_zero_rates_elapsed_time_sum():
+  # simulator_test.py:147-168: zero rates => elapsed == sum(dwell) + image.
+  st = po.make_state(3, seed=1)
+  po.reset(st)
+  zero = lambda s, idx, beam, it: (np.zeros((idx.size, 3), np.float32),
+                                   s.nbr[s.si_idx[idx]])
+  dwell = np.array([1500000, 3000000, 7230000], dtype=np.int64)
+  ctl = np.full((3, 3, 2), 0.5)
+  e = st.num_envs
+  elapsed = np.zeros(e, dtype=np.int64)
+  for c in range(3):
+    beam = po.microscope_to_material(st.fov, ctl[:, c])
+    out = po.apply_control(st, beam, np.full(e, dwell[c]), rates_override=zero)
+    assert (out['transitions'] == 0).all() and (out['events'] == 1).all()
+    elapsed += dwell[c]
+  assert (elapsed + 3500000 == 15230000).all()
+
+
+@pytest.mark.parametrize('pct,expect', [
+    ((0.2, 0.4), True), ((0.35, 0.95), True), ((0.751, 0.249), True),
+    ((0.749, 0.250), False)])
+def test_recentre_thresholds(pct, expect):
+  # simulator_test.py:263-335
+  st = po.make_state(1, seed=5)
+  po.reset(st)
+  p = po.site_positions(st, st.si_idx, np.arange(1))[0]
+  ll = p - 10.0 * np.asarray(pct)
+  st.fov[0] = np.concatenate((ll, ll + 10.0))
+  out = po.step_and_image(st, np.array([[[1.0, 1.0]]]), np.array([[0]]))
+  assert bool(out['recentred'][0]) == expect
+  q = po.material_to_microscope(st.fov, p[None])[0]
+  want = (0.5, 0.5) if expect else pct
+  np.testing.assert_allclose(q, want, atol=1e-12)
+  assert out['elapsed_us'][0] == (4000000 if expect else 2000000)
+
+
+def test_multiple_transitions_at_high_rate():
+  # graphene_test.py:228-281: rate 5 each => several hops within a dwell.
+  st = po.make_state(64, seed=9)
+  po.reset(st)
+  five = lambda s, idx, beam, it: (np.full((idx.size, 3), 5.0, np.float32),
+                                   s.nbr[s.si_idx[idx]])
+  out = po.apply_control(st, np.zeros((64, 2)), np.full(64, 1500000),
+                         rates_override=five)
+  assert out['transitions'].mean() > 10
+  assert (out['events'] == out['transitions'] + 1).all()
+
+
+def test_seconds_to_us_rounding():
+  # CPython timedelta: fractional microseconds round half to even.
+  t = np.array([0.0000005, 0.0000015, 1.0000025, 3600.0, 2.9999999])
+  import datetime as dt
+  want = [dt.timedelta(seconds=float(x)) // dt.timedelta(microseconds=1)
+          for x in t]
+  np.testing.assert_array_equal(po.seconds_to_us(t), want)
+  rng = np.random.default_rng(0)
+  t = rng.exponential(2.0, size=20000)
+  want = [dt.timedelta(seconds=float(x)) // dt.timedelta(microseconds=1)
+          for x in t]
+  np.testing.assert_array_equal(po.seconds_to_us(t), want)
