@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the batched putting-dune simulator hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's arm
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
+
+A *step* is one pass of the hot path over one batch of synthetic input: a
+beam-action stream of ``--beam-steps`` controls for each of ``--envs``
+environments per GPU (BASELINE.json configs[1]: 4096 batched envs, prior
+rates, event sampling only, no rendering), i.e. envs * beam_steps simulated
+env-steps per launch.  Environments shard across GPUs by global env id with no
+data-path collective (weak scaling: per-GPU work fixed).
+
+Printed line (rank 0): see DESIGN.md "Measurement".  `value` is device-timed
+whole-job env-steps/s with the action stream resident in HBM; `e2e` is the same
+metric through the host-buffer C-ABI call (pinned host controls copied in,
+per-step Si sites and clocks copied out, every step); `roofline` uses SURVEY.md
+section 8(d)'s 64 algorithmic bytes per env-step against the measured HBM copy
+bandwidth in MEASURED_PEAKS.json; `cpu_baseline` is the oracle port timed on
+this box's host cores.
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'putting-dune_b200')):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+ALGORITHMIC_BYTES_PER_ENV_STEP = 64
+DWELL_US = 1500000  # registry.py:263-266 relative_random: dwell 1.5 s
+IMAGE_US = 2000000  # simulator.py:37
+METRIC = 'simulated env-steps/sec'
+UNIT = 'env-steps/s'
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--workload', default='config2',
+                  choices=['config2', 'config5'])
+  ap.add_argument('--envs', type=int, default=None,
+                  help='envs per GPU (default: 4096 config2, 1Mi/N config5)')
+  ap.add_argument('--beam-steps', type=int, default=None,
+                  help='controls per env per launch')
+  ap.add_argument('--rate', default='prior', choices=['prior', 'simple'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-at-scale', action='store_true')
+  ap.add_argument('--cpu-seconds', type=float, default=12.0)
+  return ap.parse_args()
+
+
+def workload_config(args):
+  n = max(1, args.gpus)
+  if args.workload == 'config2':
+    envs = args.envs or 4096
+    beam_steps = args.beam_steps or 256
+    name = ('configs[1]: 4096 batched envs, prior rates, event sampling only '
+            '(no rendering)')
+    scaling = 'weak'
+  else:
+    envs = args.envs or (1 << 20) // n
+    beam_steps = args.beam_steps or 8
+    name = 'configs[4]-sized: 1Mi envs sharded over the GPUs, open-loop beam'
+    scaling = 'weak' if args.envs else 'strong'
+  return dict(workload=name, envs_per_gpu=envs, beam_steps_per_launch=beam_steps,
+              rate_function=args.rate, dwell_s=DWELL_US / 1e6,
+              image_duration_s=IMAGE_US / 1e6, grid_columns=50,
+              sharding=f'env-index x{n}', l2='flushed between timed steps',
+              scaling=scaling)
+
+
+def synthetic_controls(n_envs, beam_steps, seed):
+  """Beam positions U(-1,1)^2 bond lengths around the frame centre, which is
+  where the re-centring FOV keeps the Si (relative_random, registry.py:263)."""
+  rng = np.random.default_rng(seed)
+  # FOV is 15-30 A wide: one bond is 1.42/22.5 of the frame on average.
+  return 0.5 + rng.uniform(-1.0, 1.0, size=(beam_steps, n_envs, 2)) * (
+      1.42 / 22.5)
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+  FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+            'clocks_event_reasons.hw_thermal_slowdown,'
+            'clocks_event_reasons.sw_thermal_slowdown,'
+            'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.samples, self.proc = [], None
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.FIELDS}',
+           '--format=csv,noheader,nounits', '-lms', '100', '-i', str(index)],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.samples.append((time.perf_counter(), line.strip()))
+
+  def stop(self, t0, t1):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    rows = [s for t, s in self.samples if t0 - 0.1 <= t <= t1 + 0.1]
+    rows = rows or [s for _, s in self.samples]
+    mhz, mx, reasons = [], None, set()
+    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap')
+    for r in rows:
+      parts = [p.strip() for p in r.split(',')]
+      try:
+        mhz.append(float(parts[0]))
+        mx = float(parts[1])
+      except (ValueError, IndexError):
+        continue
+      for nme, v in zip(names, parts[2:]):
+        if v.lower().startswith('active'):
+          reasons.add(nme)
+    return {'sm_mhz': float(np.median(mhz)) if mhz else None,
+            'sm_max_mhz': mx, 'reasons': sorted(reasons),
+            'samples': len(mhz)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# ----------------------------------------------------------------------------
+def _cpu_worker(args):
+  seed, env_offset, n_envs, beam_steps, rate_fn, ctrl_seed = args
+  from oracle import pdune_oracle as po
+  st = po.make_state(n_envs, seed, env_offset=env_offset)
+  po.reset(st)
+  ctl = synthetic_controls(n_envs, beam_steps, ctrl_seed)
+  t0 = time.perf_counter()
+  for t in range(beam_steps):
+    po.step_and_image(st, ctl[t][:, None, :], DWELL_US, IMAGE_US,
+                      rate_fn=rate_fn)
+  return time.perf_counter() - t0, n_envs * beam_steps
+
+
+def cpu_port_throughput(n_envs, rate_fn, seconds, cores):
+  """Times oracle.step_and_image on `cores` processes, each owning a shard of
+  the env batch, for about `seconds`; returns (env-steps/s, sample text)."""
+  import multiprocessing as mp
+  shard = max(1, n_envs // cores)
+  # calibrate on one short run
+  dt, work = _cpu_worker((0, 0, shard, 2, rate_fn, 1))
+  per_step = dt / 2
+  beam_steps = int(max(2, min(20000, seconds / max(per_step, 1e-6))))
+  jobs = [(0, i * shard, shard, beam_steps, rate_fn, 1 + i)
+          for i in range(cores)]
+  t0 = time.perf_counter()
+  if cores == 1:
+    res = [_cpu_worker(jobs[0])]
+  else:
+    with mp.get_context('fork').Pool(cores) as pool:
+      res = pool.map(_cpu_worker, jobs)
+  wall = time.perf_counter() - t0
+  total = sum(w for _, w in res)
+  busy = max(d for d, _ in res)
+  sample = (f'{shard * cores} envs x {beam_steps} beam steps, NumPy oracle '
+            f'port (vectorised over envs), {cores} process(es), '
+            f'{busy:.1f} s busy / {wall:.1f} s wall')
+  return total / busy, sample, wall
+
+
+def run_reference_arm(args, cfg):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  from oracle import pdune_oracle as po
+  rate_fn = po.RATE_PRIOR if args.rate == 'prior' else po.RATE_SIMPLE
+  cores = os.cpu_count() or 1
+  n_envs = cfg['envs_per_gpu']
+  per_step_budget = 6.0
+  vals, samples, walls = [], [], []
+  t_all = time.perf_counter()
+  for i in range(args.warmup + args.steps):
+    v, s, w = cpu_port_throughput(n_envs, rate_fn, per_step_budget, cores)
+    if i >= args.warmup:
+      vals.append(v)
+      samples.append(s)
+      walls.append(w)
+    if time.perf_counter() - t_all > 240:
+      break
+  value = float(np.mean(vals)) if vals else 0.0
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
+      'ms_per_step': 1e3 * float(np.mean(walls)) if walls else None, 'higher_is_better': True,
+      'scaling': cfg['scaling'], 'vs_baseline': None, 'dtype': 'f64',
+      'data': 'synthetic', 'config': cfg,
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores,
+                       'kind': 'port', 'sample': samples[-1] if samples else ''},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'note': ('the Python reference cannot travel to the GPU box; this is '
+               'oracle/pdune_oracle.py (pinned against the unmodified '
+               'reference) on all host cores; the unmodified reference '
+               'measured 386 env-steps/s on one core (SURVEY.md section 6)'),
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def measured_peak():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  try:
+    return float(json.load(open(path))['hbm_gbs']), 'measured'
+  except (OSError, KeyError, ValueError):
+    return 6650.0, 'fallback'
+
+
+def run_ours(args, cfg):
+  import torch
+  import torch.distributed as dist
+  import putting_dune_b200 as pd
+  from putting_dune_b200 import _native as nat
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a GPU: there is no CPU fallback')
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  n, t_steps = cfg['envs_per_gpu'], cfg['beam_steps_per_launch']
+  rate = pd.RateSpec.prior() if args.rate == 'prior' else pd.RateSpec.simple()
+  batch = pd.EnvBatch(n, seed=0, env_offset=rank * n, device=dev)
+  batch.reset()
+  pool = 4
+  h_ctl = [torch.as_tensor(synthetic_controls(n, t_steps, 100 + rank * pool + i)
+                           ).pin_memory() for i in range(pool)]
+  d_ctl = [c.to(dev) for c in h_ctl]
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  lat_c, st_c = C.byref(batch.lattice_tables.c), C.byref(batch.c)
+  stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  P = lambda t: C.c_void_p(t.data_ptr())
+
+  def launch(i):
+    nat.check(nat.lib.pd_rollout(lat_c, st_c, C.byref(rate.c),
+                                 P(d_ctl[i % pool]), DWELL_US, t_steps,
+                                 IMAGE_US, None, None, stream))
+
+  # -- device-resident: value -----------------------------------------------
+  for i in range(args.warmup):
+    flush.zero_()
+    launch(i)
+  barrier()
+  sampler = ClockSampler(local) if rank == 0 else None
+  ev = [(torch.cuda.Event(enable_timing=True),
+         torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    flush.zero_()
+    ev[i][0].record()
+    launch(i)
+    ev[i][1].record()
+  barrier()
+  t1 = time.perf_counter()
+  clocks = sampler.stop(t0, t1) if sampler else None
+  dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+  tm = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+  dev_ms = float(tm.item())
+  env_steps_per_launch = n * t_steps
+  total_env_steps = env_steps_per_launch * args.steps * world
+  value = total_env_steps / (dev_ms / 1e3)
+
+  # -- end to end through the host-buffer C ABI -------------------------------
+  d_stage = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
+  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+  h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
+  h_el = torch.empty((t_steps, n), dtype=torch.int64).pin_memory()
+
+  def launch_host(i):
+    nat.check(nat.lib.pd_rollout_host(
+        lat_c, st_c, C.byref(rate.c), P(h_ctl[i % pool]), DWELL_US, t_steps,
+        IMAGE_US, P(d_stage), P(d_si), P(d_el), P(h_si), P(h_el), stream))
+
+  for i in range(args.warmup):
+    launch_host(i)
+  barrier()
+  e0 = time.perf_counter()
+  for i in range(args.steps):
+    launch_host(i)
+  barrier()
+  e2e_s = time.perf_counter() - e0
+  tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+  e2e_value = total_env_steps / float(tm.item())
+  h2d = h_ctl[0].numel() * 8
+  d2h = h_si.numel() * 4 + h_el.numel() * 8
+
+  # -- roofline of the dominant kernel ----------------------------------------
+  peak, peak_kind = measured_peak()
+  launch_s = dev_ms / 1e3 / args.steps
+  achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * env_steps_per_launch / launch_s / 1e9
+  roofline = {
+      'kernel': 'pd::k_rollout', 'bound': 'hbm', 'achieved': achieved,
+      'peak': peak, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
+      'unit': 'GB/s', 'frac': achieved / peak,
+      'algorithmic_bytes_per_env_step': ALGORITHMIC_BYTES_PER_ENV_STEP,
+      'env_steps_per_launch': env_steps_per_launch,
+      'launch_ms': launch_s * 1e3, 'traffic': None,
+  }
+
+  # -- the same kernel family with every SM filled (1Mi envs, one step) -------
+  at_scale = None
+  if rank == 0 and not args.no_at_scale:
+    big_n = 1 << 20
+    big = pd.EnvBatch(big_n, seed=1, device=dev,
+                      lattice=batch.lattice_tables)
+    big.reset()
+    ctl = [torch.as_tensor(synthetic_controls(big_n, 1, 7 + i)[0][:, None, :]
+                           ).to(dev).contiguous() for i in range(pool)]
+    out_c = C.byref(big._out_c)  # pylint: disable=protected-access
+    def big_launch(i):
+      nat.check(nat.lib.pd_step_and_image(
+          C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
+          P(ctl[i % pool]), None, DWELL_US, 1, IMAGE_US, out_c, stream))
+    for i in range(3):
+      big_launch(i)
+    torch.cuda.synchronize()
+    bev = [(torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for i in range(10):
+      flush.zero_()
+      bev[i][0].record()
+      big_launch(i)
+      bev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in bev) / 10
+    a_gbs = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n / (ms / 1e3) / 1e9
+    at_scale = {
+        'workload': '1Mi envs x 1 step_and_image per launch, 1 GPU',
+        'kernel': 'pd::k_step', 'value': big_n / (ms / 1e3), 'unit': UNIT,
+        'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak}
+    del big
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    from oracle import pdune_oracle as po
+    rate_fn = po.RATE_PRIOR if args.rate == 'prior' else po.RATE_SIMPLE
+    v, sample, _ = cpu_port_throughput(n, rate_fn, args.cpu_seconds, 1)
+    cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+           'sample': sample}
+
+  if rank == 0:
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+        'scaling': cfg['scaling'], 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': cfg, 'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h,
+                'api': 'pd_rollout_host (pinned host buffers)'},
+        'gpu_launches': args.steps, 'roofline': roofline,
+        'cpu_baseline': cpu, 'at_scale': at_scale,
+        'wall_s_timed_region': t1 - t0,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  cfg = workload_config(args)
+  if args.impl == 'reference':
+    run_reference_arm(args, cfg)
+  else:
+    run_ours(args, cfg)
+
+
+if __name__ == '__main__':
+  main()

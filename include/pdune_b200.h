@@ -222,6 +222,17 @@ int pd_rollout(const pd_lattice* lat, const pd_state* st,
                int64_t image_duration_us, int32_t* si_idx_out,
                int64_t* elapsed_us_out, void* stream);
 
+/* Same with HOST buffers: copies the action stream host->device into
+ * d_controls_xy, runs the fused steps, copies the per-step Si sites and
+ * elapsed times back and synchronises `stream`.  h_si_idx / h_elapsed_us may
+ * be NULL (then the matching d_* staging may be NULL too). */
+int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
+                    const pd_rate_config* rc, const double* h_controls_xy,
+                    int64_t dwell_us_scalar, int32_t n_steps,
+                    int64_t image_duration_us, double* d_controls_xy,
+                    int32_t* d_si_idx, int64_t* d_elapsed_us,
+                    int32_t* h_si_idx, int64_t* h_elapsed_us, void* stream);
+
 /* ---- queries: graphene.py:600-644 get_atoms_in_bounds,
  *      graphene.py:696-700 get_silicon_position --------------------------- */
 /* fov_override: device double [n][4] or NULL (use st->fov).  Outputs are

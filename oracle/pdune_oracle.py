@@ -61,6 +61,7 @@ STREAM_AGENT = 6
 RATE_SIMPLE = 0
 RATE_PRIOR = 1
 RATE_LEARNED = 2
+RATE_CONSTANT = 3  # fixed rates: the seam the reference's tests mock
 
 MAX_TRANSITION_SECONDS = 3600.0  # graphene.py:668
 
@@ -472,7 +473,7 @@ def apply_model(params_list: Sequence[MlpParams], x: np.ndarray) -> np.ndarray:
 
 
 def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
-              rate_fn: int, mlp: Optional[MlpParams] = None):
+              rate_fn: int, mlp: Optional[MlpParams] = None, constant=None):
   """graphene.py:238-259: Si + 3-NN geometry -> canonical fn -> float32[3]."""
   si = state.si_idx[envs]
   nbr = state.nbr[si]
@@ -484,6 +485,8 @@ def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
     r64 = prior_rates(beam, p_si, p_nbr)
   elif rate_fn == RATE_LEARNED:
     r64 = learned_rates(mlp, beam, p_si, p_nbr)
+  elif rate_fn == RATE_CONSTANT:
+    r64 = np.tile(np.asarray(constant, dtype=np.float64), (len(envs), 1))
   else:
     raise ValueError(rate_fn)
   r32 = r64.astype(np.float32)

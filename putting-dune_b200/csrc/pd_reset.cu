@@ -98,8 +98,8 @@ extern "C" int pd_reset(const pd_lattice* lat, const pd_state* st,
                         const uint8_t* mask, void* stream) {
   int rcode = pd::validate_common(lat, st, nullptr);
   if (rcode != PD_OK) return rcode;
-  PD_REQUIRE(st->image_params && st->episode, "state has null arrays");
   if (st->n_envs == 0) return PD_OK;
+  PD_REQUIRE(st->image_params && st->episode, "state has null arrays");
   const int64_t warps = st->n_envs;
   const int64_t blocks = (warps + 3) / 4;
   const int64_t cap = static_cast<int64_t>(pd::sm_count()) * 16;

@@ -275,9 +275,9 @@ int validate_common(const pd_lattice* lat, const pd_state* st,
   PD_REQUIRE(lat && st, "null lattice/state");
   PD_REQUIRE(lat->base_xy && lat->nbr && lat->n_sites > 0, "lattice not built");
   PD_REQUIRE(st->n_envs >= 0, "negative n_envs");
-  PD_REQUIRE(st->si_idx && st->lattice && st->fov && st->fov_scale &&
+  PD_REQUIRE(st->n_envs == 0 || (st->si_idx && st->lattice && st->fov && st->fov_scale &&
                  st->ctrl_count && st->sim_time_us && st->n_events &&
-                 st->n_transitions && st->status,
+                 st->n_transitions && st->status),
              "state has null arrays");
   if (rc) {
     PD_REQUIRE(rc->rate_fn >= PD_RATE_SIMPLE && rc->rate_fn <= PD_RATE_CONSTANT,
@@ -454,4 +454,39 @@ extern "C" int pd_rollout(const pd_lattice* lat, const pd_state* st,
   if (rc->rate_fn == PD_RATE_LEARNED)
     return pd::learned_step(lat, st, rc->mlp, a, true, s);
   return pd::dispatch_step(rc, a, true, s);
+}
+
+extern "C" int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
+                               const pd_rate_config* rc,
+                               const double* h_controls_xy,
+                               int64_t dwell_us_scalar, int32_t n_steps,
+                               int64_t image_duration_us,
+                               double* d_controls_xy, int32_t* d_si_idx,
+                               int64_t* d_elapsed_us, int32_t* h_si_idx,
+                               int64_t* h_elapsed_us, void* stream) {
+  PD_REQUIRE(st != nullptr, "null state");
+  PD_REQUIRE(n_steps >= 0, "negative n_steps");
+  PD_REQUIRE(n_steps == 0 || (h_controls_xy && d_controls_xy),
+             "null controls / staging");
+  PD_REQUIRE(!h_si_idx || d_si_idx, "si_idx needs device staging");
+  PD_REQUIRE(!h_elapsed_us || d_elapsed_us, "elapsed needs device staging");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t items = static_cast<size_t>(st->n_envs) * n_steps;
+  if (items > 0)
+    PD_CUDA_OK(cudaMemcpyAsync(d_controls_xy, h_controls_xy,
+                               items * 2 * sizeof(double),
+                               cudaMemcpyHostToDevice, s));
+  int rcode = pd_rollout(lat, st, rc, d_controls_xy, dwell_us_scalar, n_steps,
+                         image_duration_us, h_si_idx ? d_si_idx : nullptr,
+                         h_elapsed_us ? d_elapsed_us : nullptr, stream);
+  if (rcode != PD_OK) return rcode;
+  if (h_si_idx && items > 0)
+    PD_CUDA_OK(cudaMemcpyAsync(h_si_idx, d_si_idx, items * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, s));
+  if (h_elapsed_us && items > 0)
+    PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us, d_elapsed_us,
+                               items * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                               s));
+  PD_CUDA_OK(cudaStreamSynchronize(s));
+  return PD_OK;
 }

@@ -94,6 +94,8 @@ _SIGNATURES = {
     'pd_step_and_image_host': ([_LP, _SP, _RP, _p, _p, _i64, _i32, _i64, _p,
                                 _p, _OP, _p, _p, _p, _p], C.c_int),
     'pd_rollout': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p], C.c_int),
+    'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
+                         _p, _p], C.c_int),
     'pd_get_atoms_in_bounds': ([_LP, _SP, _p, _i32, _p, _p, _p, _p, _p],
                                C.c_int),
     'pd_get_silicon_position': ([_LP, _SP, _p, _p], C.c_int),

@@ -272,7 +272,13 @@ class EnvBatch:
 
   def step_and_image(self, controls_xy, dwell_us, rate: RateSpec,
                      image_duration_us: int = 2000000) -> StepResult:
-    ctl = self._f64(controls_xy, (self.num_envs, -1, 2))
+    ctl = torch.as_tensor(controls_xy, dtype=torch.float64,
+                          device=self.device)
+    if ctl.ndim == 2:
+      ctl = ctl[:, None, :]
+    if ctl.ndim != 3 or ctl.shape[0] != self.num_envs or ctl.shape[2] != 2:
+      raise ValueError(f'controls must be [E, C, 2], got {tuple(ctl.shape)}')
+    ctl = ctl.contiguous()
     n_controls = ctl.shape[1]
     d, scalar = self._dwell(dwell_us, (self.num_envs, n_controls))
     with torch.cuda.device(self.device):
@@ -289,7 +295,11 @@ class EnvBatch:
     controls_xy: [T, E, 2] microscope frame.  Returns (si_idx [T, E],
     elapsed_us [T, E]) if ``record`` else None.
     """
-    ctl = self._f64(controls_xy, (-1, self.num_envs, 2))
+    ctl = torch.as_tensor(controls_xy, dtype=torch.float64,
+                          device=self.device)
+    if ctl.ndim != 3 or ctl.shape[1] != self.num_envs or ctl.shape[2] != 2:
+      raise ValueError(f'controls must be [T, E, 2], got {tuple(ctl.shape)}')
+    ctl = ctl.contiguous()
     t = ctl.shape[0]
     si = el = None
     if record:
