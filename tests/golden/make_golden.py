@@ -138,6 +138,68 @@ def standardize_fixture():
   print('standardize_reference.npz', n)
 
 
+def frames_fixture():
+  """Frames from the reference's own imaging.py under RenderInjectedRng.
+
+  scikit-image is absent, so the three skimage calls inside the reference are
+  served by the restatements in oracle/pdune_oracle_imaging.py (parity
+  unpinned for those); every NumPy/SciPy stage is the reference's own code.
+  """
+  from oracle import pdune_oracle_imaging as oi
+  mods = refshim.load_reference()  # installs the empty skimage stubs
+  import skimage.exposure
+  import skimage.util
+
+  def random_noise(image, mode='gaussian', seed=None, clip=True, **kw):
+    if mode == 'gaussian':
+      return oi.random_noise_gaussian(image, kw['var'], seed)
+    return oi.random_noise_sp(image, kw['amount'], seed)
+
+  skimage.util.random_noise = random_noise
+  skimage.exposure.adjust_gamma = oi.adjust_gamma
+  skimage.exposure.equalize_adapthist = (
+      lambda img, clip_limit=0.01: oi.equalize_adapthist(img, clip_limit))
+  im, mu = mods.imaging, mods.microscope_utils
+  seed, n, size = 314, 4, 128
+  st = po.make_state(n, seed)
+  po.reset(st)
+  res = {'seed': np.int64(seed), 'size': np.int64(size)}
+  for e in range(n):
+    q, z, _ = po.get_atoms_in_bounds(st, e)
+    f = st.fov[e]
+    fov = mu.MicroscopeFieldOfView(mods.Point(f[0], f[1]),
+                                   mods.Point(f[2], f[3]))
+    grid = mu.AtomicGrid(q, z)
+    vals = [float(v) for v in st.image_params[e]]
+    p = im.ImageGenerationParameters(*vals, image_size=size)
+    rng = oi.RenderInjectedRng(seed, e, 0, size)
+    clean = im.generate_clean_image(
+        grid, fov, image_size=size, intensity_exponent=p.intensity_exponent)
+    blur = im.apply_blur(clean, p.blur_amount)
+    pois = im.apply_poisson_noise(blur, p.poisson_rate_multiplier, rng)
+    jit = im.apply_jitter(pois, p.jitter_rate, rng)
+    rng = oi.RenderInjectedRng(seed, e, 0, size)
+    final = im.generate_stem_image(grid, fov, p, rng)
+    res[f'clean_{e}'] = clean.astype(np.float32)
+    res[f'blur_{e}'] = blur.astype(np.float32)
+    res[f'poisson_{e}'] = pois.astype(np.float32)
+    res[f'jitter_{e}'] = jit.astype(np.float32)
+    res[f'final_{e}'] = final.astype(np.float32)
+  # one full-size frame, summarised
+  rng = oi.RenderInjectedRng(seed, 0, 0, 512)
+  q, z, _ = po.get_atoms_in_bounds(st, 0)
+  f = st.fov[0]
+  fov = mu.MicroscopeFieldOfView(mods.Point(f[0], f[1]),
+                                 mods.Point(f[2], f[3]))
+  p = im.ImageGenerationParameters(*[float(v) for v in st.image_params[0]])
+  full = im.generate_stem_image(mu.AtomicGrid(q, z), fov, p, rng)
+  res['full512_rowmean'] = full.mean(axis=1)
+  res['full512_colmean'] = full.mean(axis=0)
+  res['full512_patch'] = full[200:232, 300:332]
+  np.savez_compressed(os.path.join(HERE, 'frames_reference.npz'), **res)
+  print('frames_reference.npz', n, 'frames of', size)
+
+
 if __name__ == '__main__':
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
@@ -146,3 +208,4 @@ if __name__ == '__main__':
   events_fixture('events_prior.npz', po.RATE_PRIOR, 2025, 32, 30)
   rates_fixture()
   standardize_fixture()
+  frames_fixture()

@@ -255,3 +255,41 @@ def test_seconds_to_us_rounding():
   want = [dt.timedelta(seconds=float(x)) // dt.timedelta(microseconds=1)
           for x in t]
   np.testing.assert_array_equal(po.seconds_to_us(t), want)
+
+
+# -- renderer oracle vs frames produced by the reference's imaging.py ----------
+def test_imaging_oracle_matches_reference_frames(golden_dir):
+  from oracle import pdune_oracle_imaging as oi
+  fix = np.load(os.path.join(golden_dir, 'frames_reference.npz'))
+  seed, size = int(fix['seed']), int(fix['size'])
+  st = po.make_state(4, seed)
+  po.reset(st)
+  for e in range(4):
+    got = oi.render_env(st, e, size=size, stages=True)
+    for stage in ('clean', 'blur', 'poisson', 'jitter', 'final'):
+      np.testing.assert_allclose(got[stage], fix[f'{stage}_{e}'], rtol=0,
+                                 atol=2e-7, err_msg=f'{stage} env {e}')
+    assert got['final'].min() >= 0 and got['final'].max() <= 1  # imaging_test
+  st = po.make_state(1, seed)
+  po.reset(st)
+  full = oi.render_env(st, 0, size=512)
+  assert full.shape == (512, 512)  # imaging_test.py:51-78
+  np.testing.assert_allclose(full.mean(axis=1), fix['full512_rowmean'],
+                             atol=1e-12)
+  np.testing.assert_allclose(full[200:232, 300:332], fix['full512_patch'],
+                             atol=1e-12)
+
+
+def test_clahe_restatement_properties():
+  from oracle import pdune_oracle_imaging as oi
+  rng = np.random.default_rng(0)
+  img = rng.random((128, 128)) ** 3
+  out = oi.equalize_adapthist(img)
+  assert out.shape == img.shape and out.min() == 0.0 and out.max() == 1.0
+  # contrast-limited equalisation flattens the histogram
+  assert np.abs(np.median(out) - 0.5) < np.abs(np.median(img) - 0.5)
+  # clip_histogram conserves counts and respects the limit when it can
+  hist = rng.integers(0, 80, size=256)
+  clipped = oi.clip_histogram(hist, 40)
+  assert clipped.sum() == hist.sum() or clipped.max() <= 40
+  assert clipped.max() <= 40 + 1
