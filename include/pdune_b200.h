@@ -252,6 +252,36 @@ int pd_get_grid(const pd_lattice* lat, const pd_state* st,
                 const int32_t* env_ids, int32_t m, double* out_xy,
                 void* stream);
 
+/* ---- renderer: imaging.py:239-265 generate_stem_image (and the stages it
+ *      chains, :117-236) for a set of envs, using each env's current FOV,
+ *      image_params and Si position; simulator.py:206-221 _generate_image. -- */
+typedef enum pd_render_stage {
+  PD_RENDER_CLEAN = 0,       /* imaging.py:117-173 generate_clean_image       */
+  PD_RENDER_BLUR = 1,        /* :212-214 apply_blur                           */
+  PD_RENDER_POISSON = 2,     /* :199-203 apply_poisson_noise                  */
+  PD_RENDER_JITTER = 3,      /* :188-196 apply_jitter                         */
+  PD_RENDER_UNIFORM = 4,     /* :206-209 s&p, :217-218 gamma, :231-236 uniform */
+  PD_RENDER_EXPONENTIAL = 5, /* :221-228 apply_exponential_noise              */
+  PD_RENDER_GAUSSIAN = 6,    /* :176-185 apply_gaussian_noise                 */
+  PD_RENDER_FINAL = 7        /* :264 exposure.equalize_adapthist (CLAHE)      */
+} pd_render_stage;
+
+/* Workspace the renderer needs: *out_bytes of device memory (any alignment
+ * of 256 B), independent of the number of frames. */
+int pd_render_workspace_bytes(int32_t image_size, int64_t* out_bytes);
+
+/* Renders frames for envs env_ids[0..m) (device int32; NULL = envs 0..m-1).
+ * frames_out: device float [m][image_size][image_size], values in [0, 1]
+ * (the reference returns float64; pixels agree to float32 tolerance, see
+ * DESIGN.md).  image_size: power of two in [64, 512].  stop_stage < FINAL
+ * returns the image after that stage (parity tests).  advance_frame_count != 0
+ * increments pd_state.frame_count of the rendered envs (the Philox sequence of
+ * the noise fields). */
+int pd_render(const pd_lattice* lat, const pd_state* st, const int32_t* env_ids,
+              int32_t m, int32_t image_size, int32_t stop_stage,
+              int32_t advance_frame_count, float* frames_out, void* workspace,
+              int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

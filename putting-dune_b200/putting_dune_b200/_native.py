@@ -18,6 +18,8 @@ PD_OK = 0
 RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT = 0, 1, 2, 3
 ENV_BAD_RATE, ENV_LOG_OVERFLOW, ENV_NOT_RESET = 1, 2, 4
 STREAM_KMC, STREAM_RESET = 0, 1
+(RENDER_CLEAN, RENDER_BLUR, RENDER_POISSON, RENDER_JITTER, RENDER_UNIFORM,
+ RENDER_EXPONENTIAL, RENDER_GAUSSIAN, RENDER_FINAL) = range(8)
 
 _p = C.c_void_p
 
@@ -96,6 +98,9 @@ _SIGNATURES = {
     'pd_rollout': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p], C.c_int),
     'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
                          _p, _p], C.c_int),
+    'pd_render_workspace_bytes': ([_i32, C.POINTER(_i64)], C.c_int),
+    'pd_render': ([_LP, _SP, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p],
+                  C.c_int),
     'pd_get_atoms_in_bounds': ([_LP, _SP, _p, _i32, _p, _p, _p, _p, _p],
                                C.c_int),
     'pd_get_silicon_position': ([_LP, _SP, _p, _p], C.c_int),

@@ -29,5 +29,64 @@ class ImageGenerationParameters:
         self.uniform_noise_scale], dtype=np.float64)
 
 
-def render_batch(batch, image_size: int = 512):
-  raise NotImplementedError('renderer kernel not built yet')
+_workspaces = {}
+
+
+def _workspace(device, image_size: int):
+  import ctypes as C
+  import torch
+  from putting_dune_b200 import _native as nat
+  key = (str(device), image_size)
+  if key not in _workspaces:
+    need = C.c_int64()
+    with torch.cuda.device(device):
+      nat.check(nat.lib.pd_render_workspace_bytes(image_size, C.byref(need)))
+    _workspaces[key] = torch.empty(need.value, dtype=torch.uint8,
+                                   device=device)
+  return _workspaces[key]
+
+
+def render_batch(batch, env_ids=None, image_size: int = 512,
+                 stop_stage: int = 7, advance_frame_count: bool = True,
+                 out=None):
+  """Renders STEM frames for envs of an ``engine.EnvBatch`` on the device
+  (imaging.py:239-265 ``generate_stem_image`` with each env's current FOV,
+  Si position and image parameters).  Returns float32 [m, S, S] in [0, 1]."""
+  import ctypes as C
+  import torch
+  from putting_dune_b200 import _native as nat
+  dev = batch.device
+  ids = None
+  m = batch.num_envs
+  if env_ids is not None:
+    ids = torch.as_tensor(env_ids, dtype=torch.int32,
+                          device=dev).reshape(-1).contiguous()
+    m = ids.numel()
+  if out is None:
+    out = torch.empty((m, image_size, image_size), dtype=torch.float32,
+                      device=dev)
+  ws = _workspace(dev, image_size)
+  P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+  with torch.cuda.device(dev):
+    nat.check(nat.lib.pd_render(
+        C.byref(batch.lattice_tables.c), C.byref(batch.c), P(ids), m,
+        image_size, int(stop_stage), int(bool(advance_frame_count)), P(out),
+        P(ws), ws.numel(),
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+  return out
+
+
+def sample_image_parameters(rng, image_size: int = 512):
+  """imaging.py:42-54 on the host, for callers that want to choose their own
+  parameters (the simulator samples them on the device at reset)."""
+  return ImageGenerationParameters(
+      intensity_exponent=rng.uniform(1.4, 2.0),
+      gaussian_variance=rng.uniform(0.0, 5e-3),
+      jitter_rate=rng.uniform(0.0, 5.0),
+      poisson_rate_multiplier=rng.exponential(15) + 1.0,
+      salt_and_pepper_amount=rng.uniform(0.0, 1e-3),
+      blur_amount=rng.uniform(0.0, 1.0),
+      contrast_gamma=rng.uniform(0.7, 1.3),
+      exponential_lambda=rng.uniform(0.0, 0.2),
+      uniform_noise_scale=rng.uniform(0.0, 0.2),
+      image_size=image_size)
