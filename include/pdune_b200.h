@@ -252,6 +252,13 @@ int pd_get_grid(const pd_lattice* lat, const pd_state* st,
                 const int32_t* env_ids, int32_t m, double* out_xy,
                 void* stream);
 
+/* ---- learned model, batched form: rate_learning/learn_rates.py:704-732
+ *      LearnedTransitionRatePredictor.apply_model -- mean over an ensemble of
+ *      softmax(out[:3]) * out[3].  models: HOST array of n_models pd_mlp;
+ *      x: device float [n][2]; out: device float [n][3]. ------------------- */
+int pd_mlp_apply_model(const pd_mlp* models, int32_t n_models, const float* x,
+                       int64_t n, float* out, void* stream);
+
 /* ---- renderer: imaging.py:239-265 generate_stem_image (and the stages it
  *      chains, :117-236) for a set of envs, using each env's current FOV,
  *      image_params and Si position; simulator.py:206-221 _generate_image. -- */

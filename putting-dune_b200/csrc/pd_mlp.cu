@@ -1,18 +1,603 @@
-// K2: learned rate model (rate_learning/learn_rates.py:80-99, :925-972).
+// K2: learned rate model as the rate function of the event step.
+//
+//   rate_learning/learn_rates.py:80-99    get_mlp_fn (eval): BatchNorm(EMA) ->
+//                                         Linear(D,H1) swish Linear(H1,H2)
+//                                         swish Linear(H2,4) -> softplus
+//   rate_learning/learn_rates.py:925-972  LearnedTransitionRatePredictor.predict
+//   rate_learning/data_utils.py:389-432   standardize_beam_and_neighbors
+//   rate_learning/learn_rates.py:704-732  apply_model (softmax(o[:3]) * o[3])
+//
+// The KMC loop is data dependent (1..7+ rate evaluations per control), and one
+// evaluation is 2*(D*H1 + H1*H2 + 4*H2) flops (134k at H=256), so the step is
+// organised around the contraction: a persistent CTA keeps a work queue of
+// (env, control, iteration) items and evaluates the network for 128 items at
+// a time as a register-tiled FP32 GEMM (the hidden layer-1 activations are a
+// function of only two inputs and are recomputed per k-chunk instead of being
+// stored).  Survivors of an iteration go back into the queue and are topped
+// up with fresh environments, so every GEMM wave is full until the tail.
+//
+// FP32 FMA throughout (the parity path of BASELINE.json's north_star).
+#include <math.h>
+
+#include <type_traits>
+
 #include "pd_kmc.cuh"
 
 namespace pd {
 
-int learned_step(const pd_lattice*, const pd_state*, const pd_mlp*,
-                 const StepArgs&, bool, cudaStream_t) {
-  set_error("PD_RATE_LEARNED stepping is not built yet");
-  return PD_ERR_UNSUPPORTED;
+constexpr int kMlpThreads = 256;
+constexpr int kMlpBatch = 128;   // GEMM M tile = queue batch
+constexpr int kChunk = 16;       // k-chunk of the hidden contraction
+constexpr int kEnvPerThread = 8;
+
+struct MlpView {
+  int d, h1, h2, batchnorm;
+  const float *bn_scale, *bn_offset, *bn_mean, *bn_var;
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+};
+
+__device__ __forceinline__ float swishf(float z) {
+  return z / (1.0f + expf(-z));
 }
 
-int learned_rates(const pd_lattice*, const pd_state*, const pd_mlp*,
-                  const double*, float*, int32_t*, cudaStream_t) {
-  set_error("PD_RATE_LEARNED rates are not built yet");
-  return PD_ERR_UNSUPPORTED;
+__device__ __forceinline__ float softplusf(float z) {
+  // np.logaddexp(z, 0)
+  return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+}
+
+struct MlpShared {
+  float xs[kMlpBatch][2];             // normalised network inputs
+  float out[kMlpBatch][4];            // softplus heads
+  float a[kChunk][kMlpBatch];         // layer-1 activations, k-major
+  float b[kChunk][256];               // W1 chunk
+  float w0[2][256];
+  float b0[256];
+  float b1[256];
+  float w2[256][4];
+  float b2[4];
+  float bn_a[2], bn_b[2];             // x_hat = x * a + b
+};
+
+// Loads the small layers once per CTA.
+__device__ __forceinline__ void mlp_stage_small(const MlpView& w,
+                                                MlpShared& sh) {
+  for (int i = threadIdx.x; i < w.h1; i += blockDim.x) {
+    sh.w0[0][i] = w.w0[i];
+    sh.w0[1][i] = w.w0[w.h1 + i];
+    sh.b0[i] = w.b0[i];
+  }
+  for (int i = threadIdx.x; i < w.h2; i += blockDim.x) {
+    sh.b1[i] = w.b1[i];
+    sh.w2[i][0] = w.w2[4 * i + 0];
+    sh.w2[i][1] = w.w2[4 * i + 1];
+    sh.w2[i][2] = w.w2[4 * i + 2];
+    sh.w2[i][3] = w.w2[4 * i + 3];
+  }
+  if (threadIdx.x < 4) sh.b2[threadIdx.x] = w.b2[threadIdx.x];
+  if (threadIdx.x < 2) {
+    const int i = threadIdx.x;
+    if (w.batchnorm) {
+      // hk.BatchNorm eval: (x - mean) * rsqrt(var + 1e-5) * scale + offset
+      const float inv = 1.0f / sqrtf(w.bn_var[i] + 1e-5f);
+      const float g = inv * w.bn_scale[i];
+      sh.bn_a[i] = g;
+      sh.bn_b[i] = w.bn_offset[i] - w.bn_mean[i] * g;
+    } else {
+      sh.bn_a[i] = 1.0f;
+      sh.bn_b[i] = 0.0f;
+    }
+  }
+  __syncthreads();
+}
+
+// One GEMM wave: out[b][0..3] = softplus(MLP(xs[b])) for b < kMlpBatch.
+// NPT = H2 / 16 outputs per thread; thread (ty, tx) owns envs ty*8..ty*8+7 and
+// outputs tx*NPT..tx*NPT+NPT-1.
+template <int NPT>
+__device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[kEnvPerThread][NPT];
+#pragma unroll
+  for (int i = 0; i < kEnvPerThread; ++i)
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < w.h1; k0 += kChunk) {
+    __syncthreads();
+    // layer-1 chunk: a[k][b] = swish(x0*W0[0][k] + x1*W0[1][k] + b0[k])
+    for (int i = tid; i < kChunk * kMlpBatch; i += kMlpThreads) {
+      const int k = i / kMlpBatch, b = i - k * kMlpBatch;
+      const float x0 = sh.xs[b][0] * sh.bn_a[0] + sh.bn_b[0];
+      const float x1 = sh.xs[b][1] * sh.bn_a[1] + sh.bn_b[1];
+      const int kk = k0 + k;
+      float z = sh.b0[kk];
+      z = fmaf(x0, sh.w0[0][kk], z);
+      z = fmaf(x1, sh.w0[1][kk], z);
+      sh.a[k][b] = swishf(z);
+    }
+    // W1 chunk: rows k0..k0+15, all H2 columns
+    for (int i = tid; i < kChunk * (NPT * 16) / 4; i += kMlpThreads) {
+      const int k = i / (NPT * 4), c4 = i - k * (NPT * 4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+                                 w.w1 + static_cast<size_t>(k0 + k) * w.h2) +
+                             c4);
+      reinterpret_cast<float4*>(&sh.b[k][0])[c4] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      float av[kEnvPerThread], bv[NPT];
+      const float4 a0 = reinterpret_cast<const float4*>(&sh.a[k][ty * 8])[0];
+      const float4 a1 = reinterpret_cast<const float4*>(&sh.a[k][ty * 8])[1];
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) bv[j] = sh.b[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < kEnvPerThread; ++i)
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  // layer 2 activation, layer 3 partial products, reduce over the 16 tx lanes
+#pragma unroll
+  for (int i = 0; i < kEnvPerThread; ++i) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const int col = tx + 16 * j;
+      const float h = swishf(acc[i][j] + sh.b1[col]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = fmaf(h, sh.w2[col][q], o[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int s = 8; s > 0; s >>= 1)
+        o[q] += __shfl_xor_sync(0xffffffffu, o[q], s);
+    }
+    if (tx == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sh.out[ty * 8 + i][q] = softplusf(o[q] + sh.b2[q]);
+    }
+  }
+  __syncthreads();
+}
+
+// predict()'s frame canonicalisation for one env (float64 like the
+// reference): returns the network input and, for each neighbour slot, which
+// network head holds its rate.
+struct Canonical {
+  float x0, x1;
+  int head[3];
+};
+
+__device__ __forceinline__ Canonical canonicalise(const double2 beam,
+                                                  const double2 psi,
+                                                  const double2 pn[3]) {
+  const double kTwoPi = 6.283185307179586;
+  double nx[3], ny[3], ang[3];
+  // beam in bond lengths, neighbours in angstroms (learn_rates.py:952-955:
+  // the reference's unit mix).
+  const double bx = (beam.x - psi.x) / kBond, by = (beam.y - psi.y) / kBond;
+  int k = 0;
+  double best = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    nx[i] = pn[i].x - psi.x;
+    ny[i] = pn[i].y - psi.y;
+    const double dx = nx[i] - bx, dy = ny[i] - by;
+    const double dist = sqrt(dx * dx + dy * dy);
+    if (i == 0 || dist < best) {
+      best = dist;
+      k = i;
+    }
+    ang[i] = atan2(ny[i], nx[i]);
+  }
+  const double rot = -ang[k];
+  double s, c;
+  sincos(rot, &s, &c);
+  Canonical out;
+  // rotate_coordinates(beam, rot): (x c - y s, x s + y c)
+  out.x0 = static_cast<float>(bx * c - by * s);
+  out.x1 = static_cast<float>(bx * s + by * c);
+  // order = argsort((ang + rot) % 2pi); rates = heads[argsort(order)]
+  double pos[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double m = fmod(ang[i] + rot, kTwoPi);
+    if (m < 0.0) m += kTwoPi;  // NumPy remainder takes the divisor's sign
+    pos[i] = m;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      rank += (pos[j] < pos[i]) || (pos[j] == pos[i] && j < i);
+    out.head[i] = rank;
+  }
+  return out;
+}
+
+struct MlpStepShared {
+  MlpShared m;
+  int q_env[kMlpBatch], q_ctl[kMlpBatch], q_si[kMlpBatch];
+  uint32_t q_it[kMlpBatch];
+  long long q_elapsed[kMlpBatch], q_total[kMlpBatch];
+  int q_ev[kMlpBatch], q_tr[kMlpBatch], q_logn[kMlpBatch];
+  int warp_cnt[kMlpThreads / 32];
+  int q_count;
+};
+
+template <int NPT>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+    k_step_learned(const StepArgs a, const MlpView w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpStepShared& sh = *reinterpret_cast<MlpStepShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  mlp_stage_small(w, sh.m);
+  const double2* base = reinterpret_cast<const double2*>(a.lat.base_xy);
+  const int4* nbr_tab = reinterpret_cast<const int4*>(a.lat.nbr);
+  const LogSink log{a.out.log_count ? a.out.log_capacity : 0,
+                    a.out.log_elapsed_us, a.out.log_site, a.out.log_ctrl};
+  // contiguous env range of this CTA
+  const int64_t n = a.st.n_envs;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  int64_t cursor = per * blockIdx.x;
+  const int64_t hi = cursor + per < n ? cursor + per : n;
+  if (tid == 0) sh.q_count = 0;
+  __syncthreads();
+
+  while (true) {
+    const int n_pending = sh.q_count;
+    int64_t avail = hi - cursor;
+    if (avail < 0) avail = 0;
+    const int n_fresh = static_cast<int>(
+        avail < kMlpBatch - n_pending ? avail : kMlpBatch - n_pending);
+    const int n_act = n_pending + n_fresh;
+    if (n_act == 0) break;
+    // ---- build items (threads 0..n_act-1 own one item each) ----
+    int env = 0, ctl = 0, si = 0, ev = 0, tr = 0, logn = 0;
+    uint32_t it = 0;
+    long long elapsed = 0, total = 0, dwell = 0;
+    int nb[3] = {0, 0, 0};
+    double2 pn[3];
+    Canonical can;
+    can.x0 = can.x1 = 0.f;
+    can.head[0] = can.head[1] = can.head[2] = 0;
+    Fov4 fov{};
+    Lattice4 lt{};
+    const bool own = tid < n_act;
+    if (own) {
+      if (tid < n_pending) {
+        env = sh.q_env[tid]; ctl = sh.q_ctl[tid]; si = sh.q_si[tid];
+        it = sh.q_it[tid]; elapsed = sh.q_elapsed[tid];
+        total = sh.q_total[tid]; ev = sh.q_ev[tid]; tr = sh.q_tr[tid];
+        logn = sh.q_logn[tid];
+      } else {
+        env = static_cast<int>(cursor + (tid - n_pending));
+        si = a.st.si_idx[env];
+      }
+      lt = load_lattice4(a.st.lattice, env);
+      fov = load_fov4(a.st.fov, env);
+    }
+    // controls with zero dwell do no rate evaluation (graphene.py:658)
+    bool need_eval = false;
+    double2 psi = make_double2(0.0, 0.0);
+    if (own) {
+      while (ctl < a.n_controls) {
+        dwell = a.dwell_us ? a.dwell_us[static_cast<int64_t>(env) *
+                                            a.n_controls + ctl]
+                           : a.dwell_us_scalar;
+        if (elapsed < dwell) {
+          need_eval = true;
+          break;
+        }
+        total += dwell;
+        ++ctl;
+        elapsed = 0;
+        it = 0;
+      }
+      psi = site_position(__ldg(base + si), lt);
+      if (need_eval) {
+        const double2 c2 = reinterpret_cast<const double2*>(
+            a.controls_xy)[static_cast<int64_t>(env) * a.n_controls + ctl];
+        const double2 beam = a.material_frame
+                                 ? c2
+                                 : microscope_to_material(fov, c2.x, c2.y);
+        const int4 v = __ldg(nbr_tab + si);
+        nb[0] = v.x; nb[1] = v.y; nb[2] = v.z;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          pn[i] = site_position(__ldg(base + nb[i]), lt);
+        can = canonicalise(beam, psi, pn);
+      }
+    }
+    if (tid < kMlpBatch) {
+      sh.m.xs[tid][0] = can.x0;
+      sh.m.xs[tid][1] = can.x1;
+    }
+    __syncthreads();
+    // ---- network for the whole batch ----
+    mlp_wave<NPT>(w, sh.m);
+    // ---- events ----
+    bool survive = false;
+    if (own) {
+      if (need_eval) {
+        float r[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = sh.m.out[tid][can.head[i]];
+        const uint32_t seq = a.st.ctrl_count[env] + static_cast<uint32_t>(ctl);
+        const uint4 pw = philox4x32_10(
+            a.st.env_offset + static_cast<uint32_t>(env), seq, it,
+            PD_STREAM_KMC, a.st.seed);
+        int slot = 0;
+        bool bad = false;
+        const bool hit = kmc_event(r, u53(pw.x, pw.y), u53(pw.z, pw.w), dwell,
+                                   &elapsed, &slot, &bad);
+        if (bad) a.st.status[env] |= PD_ENV_BAD_RATE;
+        ++ev;
+        ++it;
+        if (hit) {
+          si = nb[slot];
+          psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
+          ++tr;
+          if (log.capacity > 0) {
+            if (logn < log.capacity) {
+              const int64_t o = static_cast<int64_t>(env) * log.capacity + logn;
+              log.elapsed_us[o] = elapsed;
+              log.site[o] = si;
+              if (log.ctrl) log.ctrl[o] = ctl;
+            } else {
+              a.st.status[env] |= PD_ENV_LOG_OVERFLOW;
+            }
+            ++logn;
+          }
+        }
+        if (elapsed >= dwell) {  // control finished
+          total += dwell;
+          ++ctl;
+          elapsed = 0;
+          it = 0;
+        }
+        survive = ctl < a.n_controls;
+      }
+      if (!survive) {
+        // ---- finalise the env: simulator.py:152-169 ----
+        uint8_t recentred = 0;
+        if (!a.material_frame) {
+          total += a.image_duration_us;
+          if (silicon_outside_safe_area(fov, psi)) {
+            store_fov4(a.st.fov, env, centred_fov(psi, a.st.fov_scale[env]));
+            total += a.image_duration_us;
+            recentred = 1;
+          }
+          a.st.sim_time_us[env] += total;
+        }
+        a.st.si_idx[env] = si;
+        a.st.ctrl_count[env] += static_cast<uint32_t>(a.n_controls);
+        a.st.n_events[env] += ev;
+        a.st.n_transitions[env] += tr;
+        if (a.out.elapsed_us) a.out.elapsed_us[env] = total;
+        if (a.out.transitions) a.out.transitions[env] = tr;
+        if (a.out.events) a.out.events[env] = ev;
+        if (a.out.recentred) a.out.recentred[env] = recentred;
+        if (a.out.si_xy) reinterpret_cast<double2*>(a.out.si_xy)[env] = psi;
+        if (a.out.log_count) a.out.log_count[env] = logn;
+      }
+    }
+    // ---- ordered compaction of the survivors into the queue ----
+    const unsigned bal = __ballot_sync(0xffffffffu, survive);
+    if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int offset = 0;
+    for (int w2 = 0; w2 < warp; ++w2) offset += sh.warp_cnt[w2];
+    int total_surv = 0;
+    for (int w2 = 0; w2 < kMlpThreads / 32; ++w2) total_surv += sh.warp_cnt[w2];
+    if (survive) {
+      const int pos = offset + __popc(bal & ((1u << lane) - 1u));
+      sh.q_env[pos] = env; sh.q_ctl[pos] = ctl; sh.q_si[pos] = si;
+      sh.q_it[pos] = it; sh.q_elapsed[pos] = elapsed; sh.q_total[pos] = total;
+      sh.q_ev[pos] = ev; sh.q_tr[pos] = tr; sh.q_logn[pos] = logn;
+    }
+    cursor += n_fresh;
+    __syncthreads();
+    if (tid == 0) sh.q_count = total_surv;
+    __syncthreads();
+  }
+}
+
+// RateFunction seam with the learned model: rates + successor sites.
+template <int NPT>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+    k_rates_learned(const pd_lattice lat, const pd_state st, const MlpView w,
+                    const double* __restrict__ beam_xy,
+                    float* __restrict__ rates_out,
+                    int32_t* __restrict__ nbr_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpShared& sh = *reinterpret_cast<MlpShared*>(smem_raw);
+  mlp_stage_small(w, sh);
+  const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
+  const int4* nbr_tab = reinterpret_cast<const int4*>(lat.nbr);
+  for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * kMlpBatch;
+       t0 < st.n_envs; t0 += static_cast<int64_t>(gridDim.x) * kMlpBatch) {
+    const int64_t e = t0 + threadIdx.x;
+    const bool own = threadIdx.x < kMlpBatch && e < st.n_envs;
+    Canonical can;
+    can.x0 = can.x1 = 0.f;
+    can.head[0] = can.head[1] = can.head[2] = 0;
+    int nb[3] = {0, 0, 0};
+    if (own) {
+      const Lattice4 lt = load_lattice4(st.lattice, e);
+      const int si = st.si_idx[e];
+      const double2 psi = site_position(__ldg(base + si), lt);
+      const int4 v = __ldg(nbr_tab + si);
+      nb[0] = v.x; nb[1] = v.y; nb[2] = v.z;
+      double2 pn[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pn[i] = site_position(__ldg(base + nb[i]), lt);
+      can = canonicalise(reinterpret_cast<const double2*>(beam_xy)[e], psi, pn);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMlpBatch) {
+      sh.xs[threadIdx.x][0] = can.x0;
+      sh.xs[threadIdx.x][1] = can.x1;
+    }
+    __syncthreads();
+    mlp_wave<NPT>(w, sh);
+    if (own) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (rates_out) rates_out[3 * e + i] = sh.out[threadIdx.x][can.head[i]];
+        if (nbr_out) nbr_out[3 * e + i] = nb[i];
+      }
+    }
+  }
+}
+
+// apply_model (learn_rates.py:704-732) for one model: softmax(o[:3]) * o[3].
+template <int NPT>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+    k_apply_model(const MlpView w, const float* __restrict__ x, int64_t n,
+                  float* __restrict__ out, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpShared& sh = *reinterpret_cast<MlpShared*>(smem_raw);
+  mlp_stage_small(w, sh);
+  for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * kMlpBatch; t0 < n;
+       t0 += static_cast<int64_t>(gridDim.x) * kMlpBatch) {
+    const int64_t e = t0 + threadIdx.x;
+    const bool own = threadIdx.x < kMlpBatch && e < n;
+    __syncthreads();
+    if (threadIdx.x < kMlpBatch) {
+      sh.xs[threadIdx.x][0] = own ? x[2 * e] : 0.f;
+      sh.xs[threadIdx.x][1] = own ? x[2 * e + 1] : 0.f;
+    }
+    __syncthreads();
+    mlp_wave<NPT>(w, sh);
+    if (own) {
+      const float* o = sh.out[threadIdx.x];
+      const float mx = fmaxf(o[0], fmaxf(o[1], o[2]));
+      const float e0 = expf(o[0] - mx), e1 = expf(o[1] - mx),
+                  e2 = expf(o[2] - mx);
+      const float s = o[3] / (e0 + e1 + e2) * scale;
+      out[3 * e + 0] += e0 * s;
+      out[3 * e + 1] += e1 * s;
+      out[3 * e + 2] += e2 * s;
+    }
+  }
+}
+
+static int mlp_view(const pd_mlp* mlp, MlpView* v) {
+  PD_REQUIRE(mlp != nullptr, "null pd_mlp");
+  PD_REQUIRE(mlp->context_dim == 2,
+             "only context_dim == 2 is a valid drop-in for predict() "
+             "(learn_rates.py:961-964 fails with voltage/current context)");
+  PD_REQUIRE(mlp->hidden1 % kChunk == 0 && mlp->hidden1 >= kChunk &&
+                 mlp->hidden1 <= 256,
+             "hidden1 must be a multiple of 16 in [16, 256]");
+  PD_REQUIRE(mlp->hidden2 == 32 || mlp->hidden2 == 64 || mlp->hidden2 == 128 ||
+                 mlp->hidden2 == 256,
+             "hidden2 must be 32, 64, 128 or 256");
+  PD_REQUIRE(mlp->w0 && mlp->b0 && mlp->w1 && mlp->b1 && mlp->w2 && mlp->b2,
+             "null MLP weights");
+  PD_REQUIRE(!mlp->batchnorm || (mlp->bn_scale && mlp->bn_offset &&
+                                 mlp->bn_mean && mlp->bn_var),
+             "null BatchNorm statistics");
+  *v = MlpView{mlp->context_dim, mlp->hidden1, mlp->hidden2, mlp->batchnorm,
+               mlp->bn_scale, mlp->bn_offset, mlp->bn_mean, mlp->bn_var,
+               mlp->w0, mlp->b0, mlp->w1, mlp->b1, mlp->w2, mlp->b2};
+  return PD_OK;
+}
+
+template <typename F>
+static int dispatch_npt(int h2, F&& f) {
+  switch (h2 / 16) {
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 8: return f(std::integral_constant<int, 8>());
+    default: return f(std::integral_constant<int, 16>());
+  }
+}
+
+int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
+                 const StepArgs& a, bool rollout, cudaStream_t stream) {
+  (void)lat;
+  if (rollout) {
+    set_error("pd_rollout with PD_RATE_LEARNED is not implemented; call "
+              "pd_step_and_image per step");
+    return PD_ERR_UNSUPPORTED;
+  }
+  MlpView v;
+  int rc = mlp_view(mlp, &v);
+  if (rc != PD_OK) return rc;
+  const int64_t tiles = (st->n_envs + kMlpBatch - 1) / kMlpBatch;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int smem = static_cast<int>(sizeof(MlpStepShared));
+  return dispatch_npt(v.h2, [&](auto npt) -> int {
+    auto kern = k_step_learned<decltype(npt)::value>;
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kMlpThreads, smem, stream>>>(a, v);
+    PD_CUDA_OK(cudaGetLastError());
+    return PD_OK;
+  });
+}
+
+int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
+                  const double* beam_xy, float* rates_out, int32_t* nbr_out,
+                  cudaStream_t stream) {
+  MlpView v;
+  int rc = mlp_view(mlp, &v);
+  if (rc != PD_OK) return rc;
+  const int64_t tiles = (st->n_envs + kMlpBatch - 1) / kMlpBatch;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int smem = static_cast<int>(sizeof(MlpShared));
+  return dispatch_npt(v.h2, [&](auto npt) -> int {
+    auto kern = k_rates_learned<decltype(npt)::value>;
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kMlpThreads, smem, stream>>>(*lat, *st, v, beam_xy, rates_out,
+                                              nbr_out);
+    PD_CUDA_OK(cudaGetLastError());
+    return PD_OK;
+  });
 }
 
 }  // namespace pd
+
+// learn_rates.py:704-732 apply_model: mean over an ensemble of
+// softmax(out[:3]) * out[3].  x: device float [n][2]; out: device float
+// [n][3] (overwritten).
+extern "C" int pd_mlp_apply_model(const pd_mlp* models, int32_t n_models,
+                                  const float* x, int64_t n, float* out,
+                                  void* stream) {
+  PD_REQUIRE(models != nullptr && n_models > 0, "no models");
+  PD_REQUIRE(n >= 0 && (n == 0 || (x && out)), "bad arguments");
+  if (n == 0) return PD_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PD_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * 3 * n, s));
+  const int64_t tiles = (n + pd::kMlpBatch - 1) / pd::kMlpBatch;
+  const int grid =
+      static_cast<int>(tiles < pd::sm_count() ? tiles : pd::sm_count());
+  const int smem = static_cast<int>(sizeof(pd::MlpShared));
+  for (int i = 0; i < n_models; ++i) {
+    pd::MlpView v;
+    int rc = pd::mlp_view(&models[i], &v);
+    if (rc != PD_OK) return rc;
+    rc = pd::dispatch_npt(v.h2, [&](auto npt) -> int {
+      auto kern = pd::k_apply_model<decltype(npt)::value>;
+      PD_CUDA_OK(cudaFuncSetAttribute(
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kern<<<grid, pd::kMlpThreads, smem, s>>>(v, x, n, out,
+                                               1.0f / n_models);
+      PD_CUDA_OK(cudaGetLastError());
+      return PD_OK;
+    });
+    if (rc != PD_OK) return rc;
+  }
+  return PD_OK;
+}

@@ -1,0 +1,171 @@
+"""GPU tests of the learned rate model (K2) through the C ABI.
+
+The network itself is "parity unpinned" (no Haiku/TF here, no reference test
+covers predict); the oracle is a NumPy restatement of the Haiku forward, and
+the frame canonicalisation around it is pinned by the reference's own code
+(tests/golden/rates_reference.npz).  Tolerance: FP32 FMA vs NumPy float32
+matmul, |d| <= 2e-5 * max(rate) + 1e-7.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdune_oracle as po
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(want):
+  return 2e-5 * np.abs(want).max() + 1e-7
+
+
+@pytest.mark.parametrize('hidden', [(32, 32), (64, 64), (128, 128),
+                                    (256, 256), (48, 128)])
+def test_learned_rates_match_oracle(hidden):
+  n, seed = 1000, 3
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(1, hidden=hidden)
+  rng = np.random.default_rng(2)
+  mlp.bn_mean = rng.normal(0, 0.3, 2).astype(np.float32)
+  mlp.bn_var = rng.uniform(0.5, 2.0, 2).astype(np.float32)
+  mlp.bn_scale = rng.uniform(0.5, 1.5, 2).astype(np.float32)
+  mlp.bn_offset = rng.normal(0, 0.2, 2).astype(np.float32)
+  mlp.b0 = rng.normal(0, 0.1, hidden[0]).astype(np.float32)
+  mlp.b1 = rng.normal(0, 0.1, hidden[1]).astype(np.float32)
+  mlp.b2 = rng.normal(0, 0.1, 4).astype(np.float32)
+  beam = po.site_positions(st, st.si_idx, np.arange(n)) + rng.uniform(
+      -2.5, 2.5, size=(n, 2))
+  b = gh.batch_from_oracle(st)
+  r, nb = b.rates(beam, gh.rate_spec(po.RATE_LEARNED, mlp))
+  want, nbr = po.rates_for(st, np.arange(n), beam, po.RATE_LEARNED, mlp)
+  np.testing.assert_array_equal(gh.np_(nb), nbr)
+  assert np.abs(gh.np_(r) - want).max() <= _tol(want)
+
+
+def test_learned_rates_match_reference_predict(golden_dir):
+  """rates_reference.npz: the reference's own predict() body around the
+  NumPy network."""
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  mlp = po.MlpParams(**{k: fix[f'mlp_{k}'] for k in (
+      'bn_scale', 'bn_offset', 'bn_mean', 'bn_var', 'w0', 'b0', 'w1', 'b1',
+      'w2', 'b2')})
+  b = gh.batch_from_oracle(st)
+  r, nb = b.rates(fix['beam'], gh.rate_spec(po.RATE_LEARNED, mlp))
+  np.testing.assert_array_equal(gh.np_(nb), fix['succ_learned'])
+  assert np.abs(gh.np_(r) - fix['rates_learned']).max() <= _tol(
+      fix['rates_learned'])
+
+
+def test_learned_step_event_machinery_is_exact():
+  """With the oracle fed the device's own rates, the learned-rate step must
+  reproduce sites, counters and the transition log bit-exactly."""
+  n, seed = 700, 12
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(5, hidden=(64, 64))
+  mlp.b2 = np.array([0.5, 0.2, 0.8, 0.0], np.float32)  # lively rates
+  spec = gh.rate_spec(po.RATE_LEARNED, mlp)
+  b = gh.batch_from_oracle(st, log_capacity=192)
+  shadow = gh.batch_from_oracle(st)
+
+  def device_rates(state, idx, beam, it):
+    shadow.si_idx.copy_(torch.as_tensor(state.si_idx, device=shadow.device))
+    full = np.zeros((n, 2))
+    full[idx] = beam
+    r, _ = shadow.rates(full, spec)
+    return gh.np_(r)[idx], state.nbr[state.si_idx[idx]]
+
+  rng = np.random.default_rng(3)
+  for step in range(6):
+    ctl = np.stack([gh.closed_loop_control(st, rng) for _ in range(2)], axis=1)
+    dwell = rng.integers(0, 4000000, size=(n, 2))
+    dwell[::9, 0] = 0
+    log = po.EventLog([], [], [], [], [], [])
+    elapsed = np.zeros(n, dtype=np.int64)
+    tr = np.zeros(n, dtype=np.int64)
+    ev = np.zeros(n, dtype=np.int64)
+    for c in range(2):
+      beam = po.microscope_to_material(st.fov, ctl[:, c])
+      o = po.apply_control(st, beam, dwell[:, c], log=log,
+                           rates_override=device_rates)
+      elapsed += dwell[:, c]
+      tr += o['transitions']
+      ev += o['events']
+    elapsed += 2000000
+    rec = po.silicon_outside_safe_area(st)
+    po.recenter_fov(st, np.nonzero(rec)[0])
+    elapsed[rec] += 2000000
+    out = b.step_and_image(ctl, dwell, spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+    np.testing.assert_array_equal(gh.np_(out.elapsed_us), elapsed)
+    np.testing.assert_array_equal(gh.np_(out.transitions), tr)
+    np.testing.assert_array_equal(gh.np_(out.events), ev)
+    np.testing.assert_array_equal(gh.np_(out.recentred).astype(bool), rec)
+    np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+    cnt = gh.np_(out.log_count)
+    assert cnt.max() <= 192 and not (gh.np_(b.status) & 2).any()
+    got = sorted((e, int(gh.np_(out.log_elapsed_us)[e, k]),
+                  int(gh.np_(out.log_site)[e, k]))
+                 for e in np.nonzero(cnt)[0] for k in range(cnt[e]))
+    want = sorted(zip(log.env, log.elapsed_us, log.new_si))
+    assert got == want
+  assert st.n_transitions.sum() > 500
+  np.testing.assert_array_equal(gh.np_(b.ctrl_count),
+                                st.ctrl_count.astype(np.int32))
+
+
+def test_learned_step_close_to_independent_oracle():
+  """Against the oracle's own NumPy network the trajectories agree except
+  where a float32 rounding difference moves a waiting time across the end of
+  the dwell (expected ~1e-6 per event)."""
+  n, seed = 4096, 4
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(9, hidden=(128, 128))
+  spec = gh.rate_spec(po.RATE_LEARNED, mlp)
+  b = gh.batch_from_oracle(st)
+  rng = np.random.default_rng(5)
+  for _ in range(8):
+    ctl = gh.closed_loop_control(st, rng)[:, None, :]
+    po.step_and_image(st, ctl, 5000000, rate_fn=po.RATE_LEARNED, mlp=mlp)
+    b.step_and_image(ctl, 5000000, spec)
+  same = gh.np_(b.si_idx) == st.si_idx
+  assert same.mean() >= 0.999, same.mean()
+  assert st.n_transitions.sum() > 1000
+
+
+def test_apply_model_ensemble():
+  from putting_dune_b200 import engine
+  from putting_dune_b200.rate_learning import learn_rates
+  models = [po.MlpParams.synthetic(s, hidden=(64, 64)) for s in (1, 2, 3)]
+  w = [engine.MlpWeights(**{k: getattr(m, k) for k in engine.MlpWeights.NAMES})
+       for m in models]
+  pred = learn_rates.LearnedTransitionRatePredictor(w)
+  x = np.random.default_rng(0).uniform(-1.5, 1.5, size=(777, 2)).astype(
+      np.float32)
+  got = gh.np_(pred.apply_model(x))
+  want = po.apply_model(models, x)
+  np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-7)
+  one = gh.np_(pred.apply_model(x, model_index=1))
+  np.testing.assert_allclose(one, po.apply_model(models[1:2], x), rtol=2e-5,
+                             atol=1e-7)
+  with pytest.raises(ValueError):
+    pred.rate_spec()
+
+
+def test_unsupported_shapes_fail_loudly():
+  from putting_dune_b200 import _native as nat
+  st = po.make_state(8, 1)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  bad = po.MlpParams.synthetic(1, hidden=(64, 40))
+  with pytest.raises(nat.NativeError, match='hidden2'):
+    b.rates(np.zeros((8, 2)), gh.rate_spec(po.RATE_LEARNED, bad))
