@@ -193,3 +193,99 @@ def run_reference_env(seed: int, env_id: int, controls: np.ndarray,
              last_obs_numbers=obs.grid.atomic_numbers.copy())
   uninstall_canonical_neighbors(mods)
   return out
+
+
+class _CanonicalKnn:
+  """Stand-in for sklearn.neighbors.NearestNeighbors inside the reference's
+  feature constructor (feature_constructors.py:200-208): same k-NN set,
+  neighbours ordered by (distance rounded to 1e-6, index) instead of float
+  noise -- the same canonical order the lattice table uses."""
+
+  def __init__(self, n_neighbors=4, metric='l2', algorithm='brute'):
+    self.k = n_neighbors
+
+  def fit(self, x):
+    self.x = np.asarray(x)
+    return self
+
+  def kneighbors(self, query):
+    q = np.asarray(query).reshape(-1, 2)
+    dist, idx = [], []
+    for row in q:
+      d = np.linalg.norm(self.x - row, axis=1)
+      order = np.lexsort((np.arange(d.size), np.round(d, 6)))[:self.k]
+      idx.append(order)
+      dist.append(d[order])
+    return np.asarray(dist), np.asarray(idx)
+
+
+def run_reference_episodes(seed: int, env_ids, rate_fn: int = po.RATE_SIMPLE,
+                           dwell_seconds: float = 5.0, step_limit: int = 600,
+                           timeout_minutes: float = 10.0) -> dict:
+  """`eval_lib.evaluate` of the unmodified reference for the
+  greedy_on_neighbor experiment (registry.py:287-298), one episode per env id.
+
+  The env's generator is replaced by InjectedRng(seed, env_id) (the reference
+  seeds one generator per episode, putting_dune_environment.py:72-76) and
+  `time.perf_counter` is frozen so that agent wall time is zero.
+  """
+  import time as _time
+  mods = refshim.load_reference_env_stack()
+  table = po.neighbor_table(50)
+  install_canonical_neighbors(mods, table)
+  fc = mods.feature_constructors
+  orig_nn = fc.neighbors.NearestNeighbors
+  fc.neighbors = type('N', (), {'NearestNeighbors': _CanonicalKnn})
+  mu = mods.microscope_utils
+  material = mods.graphene.PristineSingleDopedGraphene(
+      rate_function=make_rate_function(mods, rate_fn))
+  inner = mods.putting_dune_environment.PuttingDuneEnvironment(
+      material=material,
+      action_adapter=mods.action_adapters
+      .RelativeToSiliconMaterialFrameActionAdapter(
+          dwell_time_range=(dt.timedelta(seconds=dwell_seconds),
+                            dt.timedelta(seconds=dwell_seconds)),
+          max_distance_angstroms=2 * 1.42),
+      feature_constructor=fc.SingleSiliconMaterialFrameFeatureConstructor(),
+      goal=mods.goals.SingleSiliconGoalReaching(),
+      image_duration=dt.timedelta(seconds=2.0))
+
+  class Hook(mu.SimulatorObserver):
+    ctrl_seq = 0
+
+    def observe_reset(self, grid, fov):
+      Hook.ctrl_seq = 0
+
+    def observe_apply_control(self, control):
+      inner._rng.begin(po.STREAM_KMC, Hook.ctrl_seq)  # pylint: disable=protected-access
+      Hook.ctrl_seq += 1
+
+  inner.sim.add_observer(Hook())
+  inner.seed = lambda s: setattr(inner, '_rng', InjectedRng(seed, s))
+  env = mods.run_helpers.StepLimitWrapper(inner, step_limit=step_limit)
+  agent = mods.agent_lib.GreedyAgent(rng=np.random.default_rng(0),
+                                     argmax=np.array([1.42, 0.0]))
+  suite = mods.eval_lib.EvalSuite(seeds=tuple(int(e) for e in env_ids))
+  real_counter = _time.perf_counter
+  mods.eval_lib.time.perf_counter = lambda: 0.0
+  try:
+    with np.errstate(divide='ignore', over='ignore', invalid='ignore'):
+      results = mods.eval_lib.evaluate(
+          agent, env, suite, timeout=dt.timedelta(minutes=timeout_minutes))
+  finally:
+    mods.eval_lib.time.perf_counter = real_counter
+    fc.neighbors = type('N', (), {'NearestNeighbors': orig_nn})
+    uninstall_canonical_neighbors(mods)
+  agg = mods.eval_lib.aggregate_results(results)
+  return {
+      'seed': np.asarray([r.seed for r in results]),
+      'reached': np.asarray([r.reached_goal for r in results]),
+      'num_actions': np.asarray([r.num_actions_taken for r in results]),
+      'env_seconds': np.asarray([r.environment_seconds_to_goal
+                                 for r in results]),
+      'total_reward': np.asarray([r.total_reward for r in results]),
+      'aggregate': np.asarray([agg.average_num_times_reached_goal,
+                               agg.average_num_actions_taken,
+                               agg.average_environment_seconds_to_goal,
+                               agg.average_total_reward]),
+  }

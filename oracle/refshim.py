@@ -215,3 +215,63 @@ def reference_learned_predict(packaged_model, use_voltage=False,
       config=types.SimpleNamespace(use_voltage=use_voltage,
                                    use_current=use_current))
   return lambda grid, beam, si, nbrs: fn(fake_self, grid, beam, si, nbrs)
+
+
+def load_reference_env_stack():
+  """Imports the reference's RL layer (putting_dune_environment, adapters,
+  goals, feature constructors, agents, run_helpers, eval_lib) for pinning the
+  episode oracle (BASELINE configs[4]).  Adds stand-ins for dm_env,
+  matplotlib, frozendict and the plotting module (none are on the path that
+  is exercised)."""
+  import collections
+  import enum
+  mods = load_reference()
+  if 'dm_env' not in sys.modules:
+    class StepType(enum.IntEnum):
+      FIRST = 0
+      MID = 1
+      LAST = 2
+
+    class TimeStep(collections.namedtuple(
+        'TimeStep', ['step_type', 'reward', 'discount', 'observation'])):
+      def first(self): return self.step_type == StepType.FIRST
+      def mid(self): return self.step_type == StepType.MID
+      def last(self): return self.step_type == StepType.LAST
+
+    class Environment:
+      pass
+
+    class Array:
+      def __init__(self, shape, dtype, name=None):
+        self.shape, self.dtype, self.name = tuple(shape), np.dtype(dtype), name
+
+    class BoundedArray(Array):
+      def __init__(self, shape, dtype, minimum, maximum, name=None):
+        super().__init__(shape, dtype, name)
+        self.minimum, self.maximum = np.asarray(minimum), np.asarray(maximum)
+
+    specs = _module('dm_env.specs', Array=Array, BoundedArray=BoundedArray)
+    _module(
+        'dm_env', specs=specs, StepType=StepType, TimeStep=TimeStep,
+        Environment=Environment,
+        restart=lambda obs: TimeStep(StepType.FIRST, None, None, obs),
+        transition=lambda reward, observation, discount=1.0: TimeStep(
+            StepType.MID, reward, discount, observation),
+        termination=lambda reward, observation: TimeStep(
+            StepType.LAST, reward, 0.0, observation),
+        truncation=lambda reward, observation, discount=1.0: TimeStep(
+            StepType.LAST, reward, discount, observation))
+  if 'matplotlib' not in sys.modules:
+    plt = _module('matplotlib.pyplot')
+    _module('matplotlib', pyplot=plt)
+  if 'frozendict' not in sys.modules:
+    _module('frozendict', frozendict=dict)
+  if 'putting_dune.plotting_utils' not in sys.modules:
+    pu = types.ModuleType('putting_dune.plotting_utils')
+    sys.modules['putting_dune.plotting_utils'] = pu
+    sys.modules['putting_dune'].plotting_utils = pu
+  for name in ('action_adapters', 'goals', 'feature_constructors',
+               'putting_dune_environment', 'run_helpers', 'eval_lib'):
+    setattr(mods, name, importlib.import_module(f'putting_dune.{name}'))
+  mods.agent_lib = importlib.import_module('putting_dune.agents.agent_lib')
+  return mods

@@ -200,6 +200,20 @@ def frames_fixture():
   print('frames_reference.npz', n, 'frames of', size)
 
 
+def episodes_fixture():
+  """EvalResults of the reference's eval_lib.evaluate (greedy_on_neighbor,
+  registry.py:287-298) under InjectedRng; see refrun.run_reference_episodes."""
+  res = {}
+  for name, rate_fn, seed, n in (('simple', po.RATE_SIMPLE, 4242, 96),
+                                 ('prior', po.RATE_PRIOR, 4243, 24)):
+    r = refrun.run_reference_episodes(seed, range(n), rate_fn)
+    for k, v in r.items():
+      res[f'{name}_{k}'] = v
+    res[f'{name}_philox_seed'] = np.int64(seed)
+    print('episodes', name, 'reached', int(r['reached'].sum()), '/', n)
+  np.savez_compressed(os.path.join(HERE, 'episodes_reference.npz'), **res)
+
+
 if __name__ == '__main__':
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
@@ -209,3 +223,4 @@ if __name__ == '__main__':
   rates_fixture()
   standardize_fixture()
   frames_fixture()
+  episodes_fixture()

@@ -293,3 +293,39 @@ def test_clahe_restatement_properties():
   clipped = oi.clip_histogram(hist, 40)
   assert clipped.sum() == hist.sum() or clipped.max() <= 40
   assert clipped.max() <= 40 + 1
+
+
+# -- whole episodes (BASELINE configs[4]) vs the reference's eval_lib ----------
+@pytest.mark.parametrize('name,rate_fn', [('simple', po.RATE_SIMPLE),
+                                          ('prior', po.RATE_PRIOR)])
+def test_episode_oracle_matches_reference_eval(golden_dir, name, rate_fn):
+  from oracle import pdune_oracle_episode as oe
+  fix = np.load(os.path.join(golden_dir, 'episodes_reference.npz'))
+  n = fix[f'{name}_reached'].shape[0]
+  st = po.make_state(n, int(fix[f'{name}_philox_seed']))
+  got = oe.run_episodes(st, oe.EpisodeConfig(rate_fn=rate_fn))
+  np.testing.assert_array_equal(got['reached'], fix[f'{name}_reached'])
+  np.testing.assert_array_equal(got['num_actions'], fix[f'{name}_num_actions'])
+  np.testing.assert_array_equal(got['env_seconds'],
+                                fix[f'{name}_env_seconds'])
+  np.testing.assert_allclose(got['total_reward'], fix[f'{name}_total_reward'],
+                             rtol=1e-15)
+  agg = oe.aggregate(got)
+  np.testing.assert_allclose(
+      [agg['average_num_times_reached_goal'], agg['average_num_actions_taken'],
+       agg['average_environment_seconds_to_goal'],
+       agg['average_total_reward']], fix[f'{name}_aggregate'], rtol=1e-12)
+
+
+def test_aggregate_results_golden():
+  # eval_lib_test.py:90-129 arithmetic: averages over successful episodes only
+  from oracle import pdune_oracle_episode as oe
+  res = {'reached': np.array([True, False, True]),
+         'num_actions': np.array([10, 99, 20]),
+         'env_seconds': np.array([70.0, np.nan, 150.0]),
+         'total_reward': np.array([0.9, 0.0, 0.5])}
+  agg = oe.aggregate(res)
+  assert agg['average_num_times_reached_goal'] == 2 / 3
+  assert agg['average_num_actions_taken'] == 15.0
+  assert agg['average_environment_seconds_to_goal'] == 110.0
+  assert agg['average_total_reward'] == 0.7
