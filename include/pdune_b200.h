@@ -252,6 +252,45 @@ int pd_get_grid(const pd_lattice* lat, const pd_state* st,
                 const int32_t* env_ids, int32_t m, double* out_xy,
                 void* stream);
 
+/* ---- whole goal-reaching episodes on the device (BASELINE configs[4]):
+ *      eval_lib.py:77-184 evaluate for the greedy_on_neighbor experiment
+ *      (experiments/registry.py:287-298) = PuttingDuneEnvironment.reset/step
+ *      (putting_dune_environment.py:87-158) + SingleSiliconGoalReaching
+ *      (goals.py:70-185) + SingleSiliconMaterialFrameFeatureConstructor
+ *      (feature_constructors.py:157-228) + GreedyAgent.step
+ *      (agents/agent_lib.py:163-183) +
+ *      RelativeToSiliconMaterialFrameActionAdapter
+ *      (action_adapters.py:219-274) + StepLimitWrapper (run_helpers.py:120). */
+typedef struct pd_episode_config {
+  int64_t dwell_us;           /* 5 s  (registry.py:291-294)                    */
+  int64_t image_duration_us;  /* 2 s  (simulator.py:37)                        */
+  int64_t timeout_us;         /* 10 min simulated (eval_lib.py:82)             */
+  int32_t step_limit;         /* 600  (run_helpers.py:34)                      */
+  int32_t reserved_;
+  double argmax_x, argmax_y;  /* greedy beam offset for a neighbour on +x,     */
+                              /* angstroms: (1.42, 0) (registry.py:289)        */
+} pd_episode_config;
+
+/* One record per env: eval_lib.EvalResult (eval_lib.py:47-59), 16 bytes, the
+ * unit that is all-gathered across GPUs. */
+typedef struct pd_episode_stats {
+  int32_t num_actions;   /* num_actions_taken                                  */
+  float env_seconds;     /* environment_seconds_to_goal (NaN if not reached)   */
+  float total_reward;    /* gamma^elapsed of the terminal step, else 0         */
+  uint8_t reached_goal;
+  uint8_t pad_[3];
+} pd_episode_stats;
+
+/* Resets every env (pd_reset), draws its goal (draw 13 of the RESET stream)
+ * and runs the greedy controller until the goal is reached, the step limit or
+ * the simulated-time limit.  goal_xy: device double [n][2] workspace/output
+ * (goal position, material frame); goal_site: device int32 [n] or NULL;
+ * stats: device pd_episode_stats [n]. */
+int pd_run_episodes(const pd_lattice* lat, const pd_state* st,
+                    const pd_rate_config* rc, const pd_episode_config* cfg,
+                    double* goal_xy, int32_t* goal_site,
+                    pd_episode_stats* stats, void* stream);
+
 /* ---- learned model, batched form: rate_learning/learn_rates.py:704-732
  *      LearnedTransitionRatePredictor.apply_model -- mean over an ensemble of
  *      softmax(out[:3]) * out[3].  models: HOST array of n_models pd_mlp;

@@ -24,7 +24,7 @@
 //   P9 output    rescale to [0, 1], write the frame
 //
 // Noise fields follow the injected convention documented in DESIGN.md and
-// oracle/pdune_oracle_imaging.py (Philox streams 2, 3, 4).
+// include/pdune_b200.h (Philox streams 2, 3, 4).
 #include <math.h>
 
 #include "pd_common.cuh"

@@ -8,6 +8,7 @@ from putting_dune_b200 import microscope_utils
 from putting_dune_b200 import engine
 from putting_dune_b200 import graphene
 from putting_dune_b200 import imaging
+from putting_dune_b200 import episodes
 from putting_dune_b200 import simulator
 from putting_dune_b200 import simulator_observers
 from putting_dune_b200.engine import EnvBatch, Lattice, MlpWeights, RateSpec
@@ -15,4 +16,4 @@ from putting_dune_b200.simulator import BatchedSimulator, PuttingDuneSimulator
 
 __all__ = ['EnvBatch', 'Lattice', 'MlpWeights', 'RateSpec', 'BatchedSimulator',
            'PuttingDuneSimulator', 'constants', 'geometry', 'microscope_utils',
-           'engine', 'graphene', 'imaging', 'simulator', 'simulator_observers']
+           'engine', 'episodes', 'graphene', 'imaging', 'simulator', 'simulator_observers']

@@ -59,8 +59,11 @@ class PdStepOut(C.Structure):
               ('log_elapsed_us', _p), ('log_site', _p), ('log_ctrl', _p)]
 
 
-class PdRenderOut(C.Structure):
-  _fields_ = [('frames', _p), ('clean', _p)]
+class PdEpisodeConfig(C.Structure):
+  _fields_ = [('dwell_us', C.c_int64), ('image_duration_us', C.c_int64),
+              ('timeout_us', C.c_int64), ('step_limit', C.c_int32),
+              ('reserved_', C.c_int32), ('argmax_x', C.c_double),
+              ('argmax_y', C.c_double)]
 
 
 class NativeError(RuntimeError):
@@ -98,6 +101,8 @@ _SIGNATURES = {
     'pd_rollout': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p], C.c_int),
     'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
                          _p, _p], C.c_int),
+    'pd_run_episodes': ([_LP, _SP, _RP, C.POINTER(PdEpisodeConfig), _p, _p, _p,
+                         _p], C.c_int),
     'pd_mlp_apply_model': ([C.POINTER(PdMlp), _i32, _p, _i64, _p, _p], C.c_int),
     'pd_render_workspace_bytes': ([_i32, C.POINTER(_i64)], C.c_int),
     'pd_render': ([_LP, _SP, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p],

@@ -1,0 +1,84 @@
+"""GPU tests of whole episodes (BASELINE configs[4]) through the C ABI."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdune_oracle as po
+from oracle import pdune_oracle_episode as oe
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(n, seed, rate_fn, env_offset=0, **cfg):
+  from putting_dune_b200 import engine, episodes
+  b = engine.EnvBatch(n, seed=seed, env_offset=env_offset)
+  stats, goal_site, goal_xy = episodes.run_greedy_episodes(
+      b, gh.rate_spec(rate_fn), episodes.EpisodeConfig(**cfg))
+  return b, episodes.stats_to_numpy(stats), gh.np_(goal_site), gh.np_(goal_xy)
+
+
+@pytest.mark.parametrize('name,rate_fn', [('simple', po.RATE_SIMPLE),
+                                          ('prior', po.RATE_PRIOR)])
+def test_episodes_match_reference_eval(golden_dir, name, rate_fn):
+  """EvalResults of the unmodified reference's eval_lib.evaluate."""
+  fix = np.load(os.path.join(golden_dir, 'episodes_reference.npz'))
+  n = fix[f'{name}_reached'].shape[0]
+  _, s, _, _ = _run(n, int(fix[f'{name}_philox_seed']), rate_fn)
+  np.testing.assert_array_equal(s['reached_goal'].astype(bool),
+                                fix[f'{name}_reached'])
+  np.testing.assert_array_equal(s['num_actions'], fix[f'{name}_num_actions'])
+  np.testing.assert_allclose(s['env_seconds'], fix[f'{name}_env_seconds'],
+                             rtol=1e-6, equal_nan=True)
+  np.testing.assert_allclose(s['total_reward'], fix[f'{name}_total_reward'],
+                             rtol=1e-6)
+
+
+def test_episodes_match_oracle_4096():
+  from putting_dune_b200 import episodes
+  n, seed = 4096, 99
+  st = po.make_state(n, seed)
+  want = oe.run_episodes(st, oe.EpisodeConfig(rate_fn=po.RATE_SIMPLE))
+  b, s, goal_site, goal_xy = _run(n, seed, po.RATE_SIMPLE)
+  np.testing.assert_array_equal(goal_site, want['goal_site'])
+  np.testing.assert_allclose(goal_xy, want['goal_pos'], rtol=0, atol=1e-12)
+  # float32 trig in the controller can differ from NumPy's by an ulp, which
+  # moves a waiting time by ~1e-7 relative; episode outcomes only change when
+  # that crosses the end of a dwell (~1e-7 per event).
+  same = (s['num_actions'] == want['num_actions']) & (
+      s['reached_goal'].astype(bool) == want['reached'])
+  assert same.mean() >= 0.999, same.mean()
+  ok = same & want['reached']
+  np.testing.assert_allclose(s['env_seconds'][ok], want['env_seconds'][ok],
+                             rtol=1e-6)
+  np.testing.assert_allclose(s['total_reward'][ok], want['total_reward'][ok],
+                             rtol=1e-6)
+  np.testing.assert_array_equal(gh.np_(b.si_idx)[same], want['final_si'][same])
+  agg = episodes.aggregate_results(s)
+  ref = oe.aggregate(want)
+  for k in ref:
+    assert abs(agg[k] - ref[k]) <= 2e-3 * max(1.0, abs(ref[k])), k
+  assert agg['average_num_times_reached_goal'] > 0.9
+
+
+def test_episode_limits():
+  # step limit (StepLimitWrapper truncation): not reached, actions == limit
+  _, s, _, _ = _run(256, 3, po.RATE_PRIOR, step_limit=7)
+  assert (s['num_actions'] == 7).all() and not s['reached_goal'].any()
+  assert np.isnan(s['env_seconds']).all() and (s['total_reward'] == 0).all()
+  # simulated-time limit: 2 s + k * (5 + 2 [+2]) s must pass 30 s
+  import datetime as dt
+  _, s, _, _ = _run(256, 3, po.RATE_PRIOR, timeout=dt.timedelta(seconds=30))
+  assert ((s['num_actions'] == 4) | (s['num_actions'] == 3)).all()
+
+
+def test_sharded_episodes_equal_unsharded():
+  n, seed = 2048, 17
+  _, full, _, _ = _run(n, seed, po.RATE_SIMPLE)
+  parts = [_run(n // 4, seed, po.RATE_SIMPLE, env_offset=r * (n // 4))[1]
+           for r in range(4)]
+  np.testing.assert_array_equal(np.concatenate(parts).tobytes(),
+                                full.tobytes())
