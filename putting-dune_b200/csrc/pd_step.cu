@@ -342,6 +342,7 @@ static int step_common(const pd_lattice* lat, const pd_state* st,
   if (rcode != PD_OK) return rcode;
   PD_REQUIRE(rc != nullptr, "null rate config");
   PD_REQUIRE(n_controls >= 0, "negative n_controls");
+  if (st->n_envs == 0) return PD_OK;
   PD_REQUIRE(n_controls == 0 || controls_xy != nullptr, "null controls");
   PD_REQUIRE(dwell_us != nullptr || dwell_us_scalar >= 0, "negative dwell");
   PD_REQUIRE(image_duration_us >= 0, "negative image duration");
