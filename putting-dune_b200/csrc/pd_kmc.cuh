@@ -69,8 +69,18 @@ __device__ __forceinline__ SharedTables stage_tables(const pd_lattice& lat,
 
 // ---------------------------------------------------------------------------
 // Rate functions -> float32[3]
+//
+// The reference evaluates the rate in float64 and casts to float32
+// (graphene.py:256); everything downstream (total rate, waiting-time scale,
+// branch probabilities) is a function of those float32 values only.  The
+// float64 expression therefore has to be *accurate* (a few ulp, so that the
+// float32 cast lands on the same value except with probability ~1e-8 per
+// evaluation), not operation-for-operation identical.  The default forms
+// below use that freedom to drop the square root and all but one division;
+// -DPD_EXACT_RATE_OPS keeps the reference's operation sequence.
 // ---------------------------------------------------------------------------
-// graphene.py:133-166 simple_canonical_rate_function.
+#ifdef PD_EXACT_RATE_OPS
+// graphene.py:133-166 simple_canonical_rate_function, op for op.
 __device__ __forceinline__ void rates_simple(const double2 beam,
                                              const double2 psi,
                                              const double2 pn[3], float r[3]) {
@@ -90,19 +100,36 @@ __device__ __forceinline__ void rates_simple(const double2 beam,
     r[i] = __double2float_rn(__ddiv_rn(1.0, den));
   }
 }
+#else
+// graphene.py:133-166: r = 1 / ((4 |beam - nbr| / 1.42)^2 + 1)
+//                        = 1 / (|beam - nbr|^2 * 16 / 1.42^2 + 1).
+__device__ __forceinline__ void rates_simple(const double2 beam,
+                                             const double2 psi,
+                                             const double2 pn[3], float r[3]) {
+  const double kScale = 16.0 / (kBond * kBond);
+  (void)psi;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double dx = beam.x - pn[i].x;
+    const double dy = beam.y - pn[i].y;
+    const double d2 = fma(dx, dx, dy * dy);
+    r[i] = __double2float_rn(1.0 / fma(d2, kScale, 1.0));
+  }
+}
+#endif
 
 // graphene.py:191-229 HumanPriorRatePredictor.predict with the constants of
 // constants.py:26-28.  The reference rotates the mean (0.85, 0) by
 // rotate_coordinates(mean, -theta) with theta = atan2 of the neighbour, which
 // places the peak at 0.85*(cos theta, -sin theta) (mirror quirk, SURVEY
 // appendix B.1); cos/sin of atan2 are taken directly from the neighbour
-// vector here (identical value up to 1e-16 relative, far inside the float32
-// cast that follows).  With covariance 0.1*I,
-//   max_rate * pdf(x)/pdf(mu) = (ln 2 / 3) * exp(-0.5 * |x - mu|^2 / 0.1).
+// vector.  With covariance 0.1*I,
+//   max_rate * pdf(x)/pdf(mu) = (ln 2 / 3) * exp(-5 |x - mu|^2).
 __device__ __forceinline__ void rates_prior(const double2 beam,
                                             const double2 psi,
                                             const double2 pn[3], float r[3]) {
   const double kMaxRate = 0.23104906018664842;  // np.log(2) / 3
+#ifdef PD_EXACT_RATE_OPS
   const double x = __ddiv_rn(__dsub_rn(beam.x, psi.x), kBond);
   const double y = __ddiv_rn(__dsub_rn(beam.y, psi.y), kBond);
 #pragma unroll
@@ -118,6 +145,20 @@ __device__ __forceinline__ void rates_prior(const double2 beam,
         __ddiv_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.1);
     r[i] = __double2float_rn(__dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha))));
   }
+#else
+  const double kInvBond = 1.0 / kBond;
+  const double x = (beam.x - psi.x) * kInvBond;
+  const double y = (beam.y - psi.y) * kInvBond;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = pn[i].x - psi.x;
+    const double ny = pn[i].y - psi.y;
+    const double inv = 0.85 * rsqrt(fma(nx, nx, ny * ny));
+    const double dx = fma(-nx, inv, x);
+    const double dy = fma(ny, inv, y);
+    r[i] = __double2float_rn(kMaxRate * exp(-5.0 * fma(dx, dx, dy * dy)));
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -192,7 +233,10 @@ __device__ __forceinline__ Fov4 centred_fov(const double2 p, double scale) {
 // ---------------------------------------------------------------------------
 // Arguments and per-env registers shared by the stepping kernels.
 // ---------------------------------------------------------------------------
-constexpr int kStepThreads = 128;
+#ifndef PD_STEP_THREADS
+#define PD_STEP_THREADS 128
+#endif
+constexpr int kStepThreads = PD_STEP_THREADS;
 
 struct RateArgs {
   float constant_rates[3];
@@ -233,6 +277,19 @@ struct StepArgs {
   int32_t* si_idx_out;        // rollout [T][n]
   int64_t* elapsed_us_out;    // rollout [T][n]
 };
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// Pulls the HBM lines an environment's step will read into L1/L2 ahead of
+// time (no register, no scoreboard): si_idx, lattice, fov, ctrl_count.
+__device__ __forceinline__ void prefetch_env(const StepArgs& a, int64_t e) {
+  prefetch_l1(a.st.si_idx + e);
+  prefetch_l1(a.st.lattice + 4 * e);
+  prefetch_l1(a.st.fov + 4 * e);
+  prefetch_l1(a.st.ctrl_count + e);
+}
 
 template <class Tables>
 __device__ __forceinline__ EnvRegs load_env(const Tables& tab,

@@ -8,8 +8,13 @@
 //
 // Compiled with -fmad=false (see pd_kmc.cuh).
 #include <math.h>
+#include <stdlib.h>
 
 #include "pd_kmc.cuh"
+
+#ifndef PD_STEP_MIN_BLOCKS
+#define PD_STEP_MIN_BLOCKS 4
+#endif
 
 namespace pd {
 
@@ -118,12 +123,15 @@ __global__ void __launch_bounds__(kStepThreads)
         elapsed += a.image_duration_us;  // simulator.py:168-169
         recentred = 1;
       }
-      a.st.sim_time_us[e] += elapsed;
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + e),
+                static_cast<unsigned long long>(elapsed));
     }
     a.st.si_idx[e] = r.si;
     a.st.ctrl_count[e] = r.ctrl_count;
-    a.st.n_events[e] += r.events;
-    a.st.n_transitions[e] += r.transitions;
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + e),
+              static_cast<unsigned long long>(r.events));
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + e),
+              static_cast<unsigned long long>(r.transitions));
     a.st.status[e] = r.status;
     if (a.out.elapsed_us) a.out.elapsed_us[e] = elapsed;
     if (a.out.transitions) a.out.transitions[e] = r.transitions;
@@ -179,12 +187,232 @@ __global__ void __launch_bounds__(kStepThreads)
         a.elapsed_us_out[static_cast<int64_t>(t) * n + e] = elapsed;
     }
     if (fov_dirty) store_fov4(a.st.fov, e, fov);
-    a.st.sim_time_us[e] += total;
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + e),
+              static_cast<unsigned long long>(total));
     a.st.si_idx[e] = r.si;
     a.st.ctrl_count[e] = r.ctrl_count;
-    a.st.n_events[e] += r.events;
-    a.st.n_transitions[e] += r.transitions;
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + e),
+              static_cast<unsigned long long>(r.events));
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + e),
+              static_cast<unsigned long long>(r.transitions));
     a.st.status[e] = r.status;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_walk: the stepping kernel.  A *lane* owns one environment at a time and
+// walks it through its work (n_steps x n_controls controls); a *warp* owns a
+// contiguous range of environments.  Every trip of the main loop executes
+// exactly one KMC iteration for every lane that has one pending; lanes whose
+// control, step or environment just finished do their (short) bookkeeping and
+// pull the next control / step / environment before the next trip.  The
+// expensive part -- neighbour geometry, rate function, Philox, waiting time --
+// therefore always runs with all lanes active instead of the whole warp
+// waiting for its slowest environment (ncu on the one-thread-per-step kernel
+// this replaces: 17.7 of 32 lanes active, profiles/r01_*baseline*).
+//
+// One launch covers pd_apply_control (material frame, no observation),
+// pd_step_and_image (n_steps = 1) and pd_rollout (n_controls = 1).
+// ---------------------------------------------------------------------------
+template <int RATE, bool STAGE>
+__global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
+    k_walk(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
+  if constexpr (STAGE) {
+    tab = stage_tables(a.lat, smem);
+  } else {
+    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
+    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
+  }
+  const LogSink log{a.out.log_count ? a.out.log_capacity : 0,
+                    a.out.log_elapsed_us, a.out.log_site, a.out.log_ctrl};
+  const bool rollout = a.n_steps > 0;
+  const int n_steps = rollout ? a.n_steps : 1;
+  const int n_controls = a.n_controls;
+  const int64_t n = a.st.n_envs;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t warps_total =
+      static_cast<int64_t>(gridDim.x) * (kStepThreads / 32);
+  const int64_t wid =
+      static_cast<int64_t>(blockIdx.x) * (kStepThreads / 32) +
+      (threadIdx.x >> 5);
+  const int64_t per = (n + warps_total - 1) / warps_total;
+  int64_t cursor = wid * per;
+  const int64_t hi = cursor + per < n ? cursor + per : n;
+
+  // lane state
+  int64_t env = -1;
+  EnvRegs r;
+  Fov4 fov;
+  double2 beam, next_ctl = make_double2(0.0, 0.0);
+  long long dwell = 0, elapsed = 0, step_elapsed = 0, total = 0;
+  uint32_t it = 0;
+  int t = 0, c = 0;
+  bool fov_dirty = false, any_recentre = false;
+  bool ready = false;  // an iteration of the current control is pending
+  r.si = 0;
+
+  while (true) {
+    // Bookkeeping runs twice per trip so that a lane whose environment just
+    // ended (finalise -> pull the next one -> set up its first control) is
+    // ready again for this trip's iteration.
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+      // ---- next control / end of step / end of environment ----
+      if (env >= 0 && !ready) {
+        while (true) {
+          if (c < n_controls) {
+            const int64_t ci = rollout ? static_cast<int64_t>(t) * n + env
+                                       : env * n_controls + c;
+            dwell = a.dwell_us ? a.dwell_us[ci] : a.dwell_us_scalar;
+            if (dwell > 0) {
+              // controls are fetched one step ahead (the first one when the
+              // env is pulled) so their HBM latency hides behind arithmetic
+              double2 ctl = next_ctl;
+              if (rollout) {
+                if (t + 1 < n_steps)
+                  next_ctl = reinterpret_cast<const double2*>(
+                      a.controls_xy)[static_cast<int64_t>(t + 1) * n + env];
+              } else if (c > 0) {
+                ctl = reinterpret_cast<const double2*>(a.controls_xy)[ci];
+              }
+              // simulator.py:137 microscope frame -> material frame
+              beam = a.material_frame
+                         ? ctl
+                         : microscope_to_material(fov, ctl.x, ctl.y);
+              elapsed = 0;
+              it = 0;
+              ready = true;
+              break;
+            }
+            r.ctrl_count += 1;  // zero dwell: no rate evaluation
+            ++c;
+            continue;
+          }
+          // all controls applied: take the image (simulator.py:152)
+          if (!a.material_frame) {
+            step_elapsed += a.image_duration_us;
+            if (silicon_outside_safe_area(fov, r.psi)) {  // simulator.py:156
+              fov = centred_fov(r.psi, a.st.fov_scale[env]);
+              step_elapsed += a.image_duration_us;  // simulator.py:168-169
+              fov_dirty = true;
+              any_recentre = true;
+            }
+          }
+          if (rollout) {
+            if (a.si_idx_out)
+              a.si_idx_out[static_cast<int64_t>(t) * n + env] = r.si;
+            if (a.elapsed_us_out)
+              a.elapsed_us_out[static_cast<int64_t>(t) * n + env] =
+                  step_elapsed;
+          }
+          total += step_elapsed;
+          ++t;
+          if (t < n_steps) {
+            c = 0;
+            step_elapsed = 0;
+            continue;
+          }
+          // ---- environment finished: write back ----
+          if (fov_dirty) store_fov4(a.st.fov, env, fov);
+          if (!a.material_frame)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + env),
+                      static_cast<unsigned long long>(total));
+          a.st.si_idx[env] = r.si;
+          a.st.ctrl_count[env] = r.ctrl_count;
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + env),
+                    static_cast<unsigned long long>(r.events));
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + env),
+                    static_cast<unsigned long long>(r.transitions));
+          a.st.status[env] = r.status;
+          if (a.out.elapsed_us) a.out.elapsed_us[env] = total;
+          if (a.out.transitions) a.out.transitions[env] = r.transitions;
+          if (a.out.events) a.out.events[env] = r.events;
+          if (a.out.recentred) a.out.recentred[env] = any_recentre ? 1 : 0;
+          if (a.out.si_xy)
+            reinterpret_cast<double2*>(a.out.si_xy)[env] = r.psi;
+          if (a.out.log_count) a.out.log_count[env] = r.log_n;
+          env = -1;
+          break;
+        }
+      }
+      // ---- idle lanes pull the next environments, in order ----
+      const bool idle = env < 0;
+      const unsigned im = __ballot_sync(0xffffffffu, idle);
+      if (im && cursor < hi) {
+        const int64_t cand = cursor + __popc(im & lt_mask);
+        if (idle && cand < hi) {
+          env = cand;
+          // first control of this env, and the lines of the env this lane is
+          // likely to pull next, are requested before anything waits
+          if (n_controls > 0)
+            next_ctl = reinterpret_cast<const double2*>(
+                a.controls_xy)[rollout ? env : env * n_controls];
+          if (cand + 32 < hi) {
+            prefetch_env(a, cand + 32);
+            if (n_controls > 0)
+              prefetch_l1(reinterpret_cast<const double2*>(a.controls_xy) +
+                          (rollout ? cand + 32 : (cand + 32) * n_controls));
+          }
+          r = load_env(tab, a, env);
+          fov = load_fov4(a.st.fov, env);
+          t = 0;
+          c = 0;
+          total = 0;
+          step_elapsed = 0;
+          fov_dirty = false;
+          any_recentre = false;
+          ready = false;
+        }
+        cursor += __popc(im);
+      }
+    }
+    if (!__any_sync(0xffffffffu, env >= 0)) break;
+
+    if (ready) {
+      // ---- one KMC iteration (graphene.py:658-694) ----
+      int nb[3];
+      tab.neighbors(r.si, nb);
+      double2 pn[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        pn[i] = site_position(tab.position(nb[i]), r.lat);
+      float rt[3];
+      eval_rates<RATE>(a.ra, beam, r.psi, pn, rt);
+      const uint4 w = philox4x32_10(r.env_id, r.ctrl_count, it, PD_STREAM_KMC,
+                                    a.st.seed);
+      int slot = 0;
+      bool bad = false;
+      const bool hit = kmc_event(rt, u53(w.x, w.y), u53(w.z, w.w), dwell,
+                                 &elapsed, &slot, &bad);
+      if (bad) r.status |= PD_ENV_BAD_RATE;
+      r.events += 1;
+      ++it;
+      if (hit) {
+        r.si = slot == 0 ? nb[0] : (slot == 1 ? nb[1] : nb[2]);
+        r.psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
+        r.transitions += 1;
+        if (log.capacity > 0) {
+          if (r.log_n < log.capacity) {
+            const int64_t o = env * log.capacity + r.log_n;
+            log.elapsed_us[o] = elapsed;
+            log.site[o] = r.si;
+            if (log.ctrl) log.ctrl[o] = c;
+          } else {
+            r.status |= PD_ENV_LOG_OVERFLOW;
+          }
+          r.log_n += 1;
+        }
+      }
+      if (elapsed >= dwell) {  // control finished
+        step_elapsed += dwell;  // simulator.py:149
+        r.ctrl_count += 1;
+        ++c;
+        ready = false;
+      }
+    }
   }
 }
 
@@ -226,10 +454,24 @@ static bool use_staging(int64_t n_envs, int64_t work_per_env) {
   return n_envs * work_per_env >= 4LL * sm_count() * kStepThreads;
 }
 
+// Kernel choice.  Large (staged) batches use k_walk, whose converged KMC
+// iterations are 10-20 % faster once every scheduler has several warps
+// (profiles/r01_kernel_choice.md); small batches are latency-bound with one
+// warp per scheduler, where the shorter instruction stream of the
+// one-thread-per-step kernels wins.  PD_STEP_KERNEL=walk|simple overrides.
+static bool walk_kernel(bool staged) {
+  static const int choice = [] {
+    const char* v = getenv("PD_STEP_KERNEL");
+    return !v ? -1 : (v[0] == 'w' ? 1 : 0);
+  }();
+  return choice < 0 ? staged : choice == 1;
+}
+
 static int grid_for(int64_t n_envs, bool staged) {
   const int64_t blocks = (n_envs + kStepThreads - 1) / kStepThreads;
   // Persistent grid-stride loop: a whole number of CTAs per SM.
-  const int64_t cap = static_cast<int64_t>(sm_count()) * (staged ? 4 : 16);
+  const int64_t cap =
+      static_cast<int64_t>(sm_count()) * (staged ? PD_STEP_MIN_BLOCKS : 16);
   return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -240,13 +482,17 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
-    auto kern = rollout ? k_rollout<RATE, true> : k_step<RATE, true>;
+    auto kern = walk_kernel(true) ? k_walk<RATE, true>
+                : rollout     ? k_rollout<RATE, true>
+                              : k_step<RATE, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
         static_cast<int>(smem)));
     kern<<<grid, kStepThreads, smem, stream>>>(a);
   } else {
-    auto kern = rollout ? k_rollout<RATE, false> : k_step<RATE, false>;
+    auto kern = walk_kernel(false) ? k_walk<RATE, false>
+                : rollout     ? k_rollout<RATE, false>
+                              : k_step<RATE, false>;
     kern<<<grid, kStepThreads, 0, stream>>>(a);
   }
   PD_CUDA_OK(cudaGetLastError());
