@@ -58,6 +58,12 @@ def parse_args():
   ap.add_argument('--rate', default='prior', choices=['prior', 'simple'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-at-scale', action='store_true')
+  ap.add_argument('--no-frames', action='store_true')
+  ap.add_argument('--frames', type=int, default=296,
+                  help='frames per render launch (512x512)')
+  ap.add_argument('--episodes', type=int, default=0,
+                  help='total envs for the greedy-controller episode run '
+                       '(configs[4] uses 1048576); 0 = skip')
   ap.add_argument('--cpu-seconds', type=float, default=12.0)
   return ap.parse_args()
 
@@ -232,6 +238,64 @@ def measured_peak():
     return 6650.0, 'fallback'
 
 
+def measure_frames(pd, batch, dev, peak, args):
+  """Frames/s of pd_render (512x512, all noise stages + CLAHE)."""
+  import torch
+  from putting_dune_b200 import imaging
+  m = args.frames
+  fb = pd.EnvBatch(m, seed=3, device=dev, lattice=batch.lattice_tables)
+  fb.reset()
+  out = torch.empty((m, 512, 512), dtype=torch.float32, device=dev)
+  for _ in range(2):
+    imaging.render_batch(fb, out=out)
+  torch.cuda.synchronize()
+  ev = [(torch.cuda.Event(enable_timing=True),
+         torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+  for a, b in ev:
+    a.record()
+    imaging.render_batch(fb, out=out)
+    b.record()
+  torch.cuda.synchronize()
+  ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+  fps = m / (ms / 1e3)
+  gbs = fps * 512 * 512 * 4 / 1e9
+  return {'metric': 'STEM frames/sec', 'value': fps, 'unit': 'frames/s',
+          'frames_per_launch': m, 'image_size': 512, 'launch_ms': ms,
+          'kernel': 'pd::k_render',
+          'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak,
+                       'unit': 'GB/s', 'frac': gbs / peak,
+                       'algorithmic_bytes_per_frame': 512 * 512 * 4}}
+
+
+def measure_episodes(pd, args, world, rank, dev, barrier):
+  """BASELINE configs[4]: `--episodes` envs sharded over the ranks, greedy
+  controller to the end of every episode, stats all-gathered with NCCL."""
+  import torch
+  from putting_dune_b200 import episodes as ep
+  lo, n = ep.shard_bounds(args.episodes, rank, world)
+  b = pd.EnvBatch(n, seed=5, env_offset=lo, device=dev)
+  rate = pd.RateSpec.simple()
+  ep.run_greedy_episodes(b, rate)  # warm-up
+  barrier()
+  s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
+      enable_timing=True)
+  s.record()
+  stats, _, _ = ep.run_greedy_episodes(b, rate)
+  full = ep.gather_episode_stats(stats)
+  e.record()
+  barrier()
+  tm = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+  if world > 1:
+    import torch.distributed as dist
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+  agg = ep.aggregate_results(full)
+  ms = float(tm.item())
+  agg.update(launch_ms=ms, env_steps_per_s=agg['total_actions'] / (ms / 1e3),
+             collective='all_gather of 16 B/env episode records',
+             rate_function='simple', controller='GreedyAgent argmax (1.42, 0)')
+  return agg
+
+
 def run_ours(args, cfg):
   import torch
   import torch.distributed as dist
@@ -370,6 +434,16 @@ def run_ours(args, cfg):
         'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak}
     del big
 
+  # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
+  frames = None
+  if rank == 0 and not args.no_frames:
+    frames = measure_frames(pd, batch, dev, peak, args)
+
+  # -- goal-reaching episodes with the greedy controller (configs[4]) ---------
+  episodes = None
+  if args.episodes:
+    episodes = measure_episodes(pd, args, world, rank, dev, barrier)
+
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import pdune_oracle as po
@@ -389,7 +463,8 @@ def run_ours(args, cfg):
                 'd2h_bytes_per_step': d2h,
                 'api': 'pd_rollout_host (pinned host buffers)'},
         'gpu_launches': args.steps, 'roofline': roofline,
-        'cpu_baseline': cpu, 'at_scale': at_scale,
+        'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
+        'episodes': episodes,
         'wall_s_timed_region': t1 - t0,
     }
     print(json.dumps(line), flush=True)

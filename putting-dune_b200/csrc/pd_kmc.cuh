@@ -174,10 +174,27 @@ __device__ __forceinline__ long long seconds_to_us(double t) {
          static_cast<long long>(rint(__dmul_rn(frac, 1e6)));
 }
 
+__device__ __forceinline__ bool kmc_event_drawn(const float r[3], double draw,
+                                                double u_choice,
+                                                long long dwell_us,
+                                                long long* elapsed_us,
+                                                int* slot, bool* bad_rate);
+
 __device__ __forceinline__ bool kmc_event(const float r[3], double u_exp,
                                           double u_choice, long long dwell_us,
                                           long long* elapsed_us, int* slot,
                                           bool* bad_rate) {
+  return kmc_event_drawn(r, -log1p(-u_exp), u_choice, dwell_us, elapsed_us,
+                         slot, bad_rate);
+}
+
+// `draw` is the unit exponential variate -log1p(-u) (state independent, so
+// it can be produced by another lane or ahead of time).
+__device__ __forceinline__ bool kmc_event_drawn(const float r[3], double draw,
+                                                double u_choice,
+                                                long long dwell_us,
+                                                long long* elapsed_us,
+                                                int* slot, bool* bad_rate) {
   // assert (transition_rates >= 0).all()  (graphene.py:258)
   *bad_rate = !(r[0] >= 0.f) || !(r[1] >= 0.f) || !(r[2] >= 0.f);
   // Rates.total_rate: sequential float32 sum (graphene.py:47-49).
@@ -186,7 +203,7 @@ __device__ __forceinline__ bool kmc_event(const float r[3], double u_exp,
   if (tot > 0.f) {
     // rng.exponential(scale=1.0 / total): float32 scale under NumPy 2.
     const float scale = __fdiv_rn(1.0f, tot);
-    t = __dmul_rn(-log1p(-u_exp), static_cast<double>(scale));
+    t = __dmul_rn(draw, static_cast<double>(scale));
     t = fmin(t, kMaxTransitionSeconds);  // graphene.py:668
   }
   *elapsed_us += seconds_to_us(t);

@@ -482,7 +482,8 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
-    auto kern = walk_kernel(true) ? k_walk<RATE, true>
+    auto kern = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads)
+                    ? k_walk<RATE, true>
                 : rollout     ? k_rollout<RATE, true>
                               : k_step<RATE, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
