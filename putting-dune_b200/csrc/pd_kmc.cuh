@@ -293,6 +293,10 @@ struct StepArgs {
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]
   int64_t* elapsed_us_out;    // rollout [T][n]
+  // episode mode (pd_run_episodes): controls come from the greedy controller
+  pd_episode_config ep;
+  const double* goal_xy;      // [n][2] material frame
+  pd_episode_stats* stats;    // [n]
 };
 
 __device__ __forceinline__ void prefetch_l1(const void* p) {

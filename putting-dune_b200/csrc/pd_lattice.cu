@@ -103,7 +103,20 @@ __global__ void __launch_bounds__(1024, 1)
     nbr[4 * k + 0] = best_m[0];
     nbr[4 * k + 1] = best_m[1];
     nbr[4 * k + 2] = best_m[2];
-    nbr[4 * k + 3] = 0;
+    nbr[4 * k + 3] = -1;
+  }
+  __syncthreads();
+  // (5) column 3 of the table lists, in ascending order and terminated by -1,
+  //     the sites within 2.6 A of the lattice centre.  After the reset offset
+  //     (|off| <= 0.71*sqrt(2) A) the site nearest the origin is always one
+  //     of them (any point of a honeycomb is within one bond of a site), so
+  //     pd_reset searches this list instead of all sites.
+  if (threadIdx.x == 0) {
+    int j = 0;
+    for (int k = 0; k < s.n_sites && j < s.n_sites - 1; ++k) {
+      const double x = base_xy[2 * k], y = base_xy[2 * k + 1];
+      if (x * x + y * y <= 2.6 * 2.6) nbr[4 * (j++) + 3] = k;
+    }
   }
 }
 

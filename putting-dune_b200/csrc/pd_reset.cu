@@ -1,4 +1,4 @@
-// K4: reset.  One warp per environment.
+// K4: reset.  One thread per environment.
 //
 //   graphene.py:533-559  generate_pristine_graphene (offset + rotation draws)
 //   graphene.py:584-598  PristineSingleDopedGraphene.reset (Si = site nearest
@@ -21,71 +21,65 @@ constexpr int kResetThreads = 128;
 __global__ void __launch_bounds__(kResetThreads)
     k_reset(const pd_lattice lat, const pd_state st,
             const uint8_t* __restrict__ mask) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps_per_grid =
-      static_cast<int64_t>(gridDim.x) * (kResetThreads / 32);
   const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
-  for (int64_t e = blockIdx.x * (kResetThreads / 32) + (threadIdx.x >> 5);
-       e < st.n_envs; e += warps_per_grid) {
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       e < st.n_envs; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     if (mask && !mask[e]) continue;
     const uint32_t env = st.env_offset + static_cast<uint32_t>(e);
     const uint32_t ep = st.episode[e];
-    auto d = [&](uint32_t k) {
-      return draw_linear(st.seed, env, ep, PD_STREAM_RESET, k);
-    };
+    // draws 2k and 2k+1 share one Philox call
+    double d[14];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const uint4 w = philox4x32_10(env, ep, k, PD_STREAM_RESET, st.seed);
+      d[2 * k] = u53(w.x, w.y);
+      d[2 * k + 1] = u53(w.z, w.w);
+    }
     // rng.uniform(-0.71, 0.71, size=(1, 2)) == low + (high - low) * u
     const double half = kBond / 2.0;
     Lattice4 t;
-    t.ox = __dadd_rn(-half, __dmul_rn(__dsub_rn(half, -half), d(0)));
-    t.oy = __dadd_rn(-half, __dmul_rn(__dsub_rn(half, -half), d(1)));
-    const double angle = __dmul_rn(2.0 * 3.141592653589793, d(2));
+    t.ox = __dadd_rn(-half, __dmul_rn(__dsub_rn(half, -half), d[0]));
+    t.oy = __dadd_rn(-half, __dmul_rn(__dsub_rn(half, -half), d[1]));
+    const double angle = __dmul_rn(2.0 * 3.141592653589793, d[2]);
     sincos(angle, &t.s, &t.c);
-    // argmin of the Euclidean norm, first index on ties.
+    // argmin of the Euclidean norm over the central candidates (ascending
+    // site order, strict <: first index on ties, like np.argmin).
     double best = 1e300;
-    int best_k = 0x7fffffff;
-    for (int k = lane; k < lat.n_sites; k += 32) {
+    int best_k = 0;
+    double2 psi = make_double2(0.0, 0.0);
+    for (int j = 0; j < lat.n_sites; ++j) {
+      const int k = __ldg(lat.nbr + 4 * j + 3);
+      if (k < 0) break;
       const double2 p = site_position(__ldg(base + k), t);
       const double dist =
           __dsqrt_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)));
       if (dist < best) {
         best = dist;
         best_k = k;
+        psi = p;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-      if (ob < best || (ob == best && ok < best_k)) {
-        best = ob;
-        best_k = ok;
-      }
-    }
-    if (lane == 0) {
-      const double2 psi = site_position(__ldg(base + best_k), t);
-      const double scale = __dadd_rn(15.0, __dmul_rn(30.0 - 15.0, d(3)));
-      st.si_idx[e] = best_k;
-      reinterpret_cast<double2*>(st.lattice)[2 * e] = make_double2(t.ox, t.oy);
-      reinterpret_cast<double2*>(st.lattice)[2 * e + 1] =
-          make_double2(t.c, t.s);
-      st.fov_scale[e] = scale;
-      store_fov4(st.fov, e, centred_fov(psi, scale));
-      double* ip = st.image_params + 9 * e;
-      ip[0] = __dadd_rn(1.4, __dmul_rn(2.0 - 1.4, d(4)));
-      ip[1] = __dmul_rn(5e-3, d(5));
-      ip[2] = __dmul_rn(5.0, d(6));
-      ip[3] = __dadd_rn(__dmul_rn(-log1p(-d(7)), 15.0), 1.0);
-      ip[4] = __dmul_rn(1e-3, d(8));
-      ip[5] = d(9);
-      ip[6] = __dadd_rn(0.7, __dmul_rn(1.3 - 0.7, d(10)));
-      ip[7] = __dmul_rn(0.2, d(11));
-      ip[8] = __dmul_rn(0.2, d(12));
-      st.episode[e] = ep + 1;
-      st.sim_time_us[e] = 0;
-      st.n_events[e] = 0;
-      st.n_transitions[e] = 0;
-      st.status[e] = PD_ENV_OK;
-    }
+    const double scale = __dadd_rn(15.0, __dmul_rn(30.0 - 15.0, d[3]));
+    st.si_idx[e] = best_k;
+    reinterpret_cast<double2*>(st.lattice)[2 * e] = make_double2(t.ox, t.oy);
+    reinterpret_cast<double2*>(st.lattice)[2 * e + 1] = make_double2(t.c, t.s);
+    st.fov_scale[e] = scale;
+    store_fov4(st.fov, e, centred_fov(psi, scale));
+    double* ip = st.image_params + 9 * e;
+    ip[0] = __dadd_rn(1.4, __dmul_rn(2.0 - 1.4, d[4]));
+    ip[1] = __dmul_rn(5e-3, d[5]);
+    ip[2] = __dmul_rn(5.0, d[6]);
+    ip[3] = __dadd_rn(__dmul_rn(-log1p(-d[7]), 15.0), 1.0);
+    ip[4] = __dmul_rn(1e-3, d[8]);
+    ip[5] = d[9];
+    ip[6] = __dadd_rn(0.7, __dmul_rn(1.3 - 0.7, d[10]));
+    ip[7] = __dmul_rn(0.2, d[11]);
+    ip[8] = __dmul_rn(0.2, d[12]);
+    st.episode[e] = ep + 1;
+    st.sim_time_us[e] = 0;
+    st.n_events[e] = 0;
+    st.n_transitions[e] = 0;
+    st.status[e] = PD_ENV_OK;
   }
 }
 
@@ -100,8 +94,7 @@ extern "C" int pd_reset(const pd_lattice* lat, const pd_state* st,
   if (rcode != PD_OK) return rcode;
   if (st->n_envs == 0) return PD_OK;
   PD_REQUIRE(st->image_params && st->episode, "state has null arrays");
-  const int64_t warps = st->n_envs;
-  const int64_t blocks = (warps + 3) / 4;
+  const int64_t blocks = (st->n_envs + pd::kResetThreads - 1) / pd::kResetThreads;
   const int64_t cap = static_cast<int64_t>(pd::sm_count()) * 16;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   pd::k_reset<<<grid, pd::kResetThreads, 0,

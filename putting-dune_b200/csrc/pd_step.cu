@@ -10,7 +10,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "pd_kmc.cuh"
+#include "pd_episode.cuh"
 
 #ifndef PD_STEP_MIN_BLOCKS
 #define PD_STEP_MIN_BLOCKS 4
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kStepThreads)
 // One launch covers pd_apply_control (material frame, no observation),
 // pd_step_and_image (n_steps = 1) and pd_rollout (n_controls = 1).
 // ---------------------------------------------------------------------------
-template <int RATE, bool STAGE>
+template <int RATE, bool STAGE, bool EPISODE>
 __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     k_walk(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   bool fov_dirty = false, any_recentre = false;
   bool ready = false;  // an iteration of the current control is pending
   r.si = 0;
+  // episode mode: goal, simulated clock, actions taken (eval_lib.py:110-150)
+  double2 goal = make_double2(0.0, 0.0);
+  long long env_time = 0;
+  int actions = 0;
 
   while (true) {
     // Bookkeeping runs twice per trip so that a lane whose environment just
@@ -263,6 +267,74 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       // ---- next control / end of step / end of environment ----
       if (env >= 0 && !ready) {
         while (true) {
+          if constexpr (EPISODE) {
+            bool done = false, reached = false;
+            float reward = 0.f;
+            if (c > 0) {
+              // step end: image, re-centre, goal test (simulator.py:152-169,
+              // goals.py:143-181)
+              long long step_us = a.ep.dwell_us + a.ep.image_duration_us;
+              if (silicon_outside_safe_area(fov, r.psi)) {
+                fov = centred_fov(r.psi, a.st.fov_scale[env]);
+                step_us += a.ep.image_duration_us;
+              }
+              env_time += step_us;
+              ++actions;
+              c = 0;
+              if (goal_reached(fov, r.psi, goal)) {
+                done = reached = true;
+                reward = static_cast<float>(
+                    pow(kGamma, static_cast<double>(step_us) / 1e6));
+              } else if (actions >= a.ep.step_limit) {
+                done = true;  // StepLimitWrapper truncation
+              }
+            }
+            // eval_lib.py:128: simulated-time limit; no goal: nothing to do
+            if (!done && (!(goal.x == goal.x) ||
+                          !(env_time < a.ep.timeout_us)))
+              done = true;
+            if (!done) {
+              int nb[3];
+              tab.neighbors(r.si, nb);
+              double2 pn[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                pn[i] = site_position(tab.position(nb[i]), r.lat);
+              const double2 ctl = greedy_control(fov, r.psi, pn, goal,
+                                                 a.ep.argmax_x, a.ep.argmax_y);
+              beam = microscope_to_material(fov, ctl.x, ctl.y);
+              dwell = a.ep.dwell_us;
+              elapsed = 0;
+              it = 0;
+              if (dwell > 0) {
+                ready = true;
+                break;
+              }
+              r.ctrl_count += 1;  // zero dwell: the control is a no-op
+              c = 1;
+              continue;
+            }
+            // ---- episode finished: EvalResult + state write-back ----
+            store_fov4(a.st.fov, env, fov);
+            a.st.sim_time_us[env] = env_time;
+            a.st.si_idx[env] = r.si;
+            a.st.ctrl_count[env] = r.ctrl_count;
+            a.st.n_events[env] = r.events;
+            a.st.n_transitions[env] = r.transitions;
+            a.st.status[env] = r.status;
+            pd_episode_stats out;
+            out.num_actions = actions;
+            out.env_seconds =
+                reached ? static_cast<float>(
+                              static_cast<double>(env_time) / 1e6)
+                        : nanf("");
+            out.total_reward = reward;
+            out.reached_goal = reached ? 1 : 0;
+            out.pad_[0] = out.pad_[1] = out.pad_[2] = 0;
+            a.stats[env] = out;
+            env = -1;
+            break;
+          }
           if (c < n_controls) {
             const int64_t ci = rollout ? static_cast<int64_t>(t) * n + env
                                        : env * n_controls + c;
@@ -347,17 +419,22 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
           env = cand;
           // first control of this env, and the lines of the env this lane is
           // likely to pull next, are requested before anything waits
-          if (n_controls > 0)
+          if (!EPISODE && n_controls > 0)
             next_ctl = reinterpret_cast<const double2*>(
                 a.controls_xy)[rollout ? env : env * n_controls];
           if (cand + 32 < hi) {
             prefetch_env(a, cand + 32);
-            if (n_controls > 0)
+            if (!EPISODE && n_controls > 0)
               prefetch_l1(reinterpret_cast<const double2*>(a.controls_xy) +
                           (rollout ? cand + 32 : (cand + 32) * n_controls));
           }
           r = load_env(tab, a, env);
           fov = load_fov4(a.st.fov, env);
+          if constexpr (EPISODE) {
+            goal = reinterpret_cast<const double2*>(a.goal_xy)[env];
+            env_time = a.ep.image_duration_us;  // eval_lib.py:121
+            actions = 0;
+          }
           t = 0;
           c = 0;
           total = 0;
@@ -483,7 +560,7 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
     auto kern = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads)
-                    ? k_walk<RATE, true>
+                    ? k_walk<RATE, true, false>
                 : rollout     ? k_rollout<RATE, true>
                               : k_step<RATE, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
@@ -491,7 +568,7 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
         static_cast<int>(smem)));
     kern<<<grid, kStepThreads, smem, stream>>>(a);
   } else {
-    auto kern = walk_kernel(false) ? k_walk<RATE, false>
+    auto kern = walk_kernel(false) ? k_walk<RATE, false, false>
                 : rollout     ? k_rollout<RATE, false>
                               : k_step<RATE, false>;
     kern<<<grid, kStepThreads, 0, stream>>>(a);
@@ -513,6 +590,53 @@ static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
     default:
       set_error("rate_fn %d is not handled by the scalar event kernel",
                 rc->rate_fn);
+      return PD_ERR_UNSUPPORTED;
+  }
+}
+
+template <int RATE>
+static int launch_episode_walk(const StepArgs& a, cudaStream_t stream) {
+  const bool staged = a.st.n_envs >= 2LL * sm_count() * kStepThreads;
+  const int grid = grid_for(a.st.n_envs, staged);
+  if (staged) {
+    const size_t smem = static_cast<size_t>(a.lat.n_sites) *
+                        (sizeof(double2) + sizeof(ushort4));
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        k_walk<RATE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem)));
+    k_walk<RATE, true, true><<<grid, kStepThreads, smem, stream>>>(a);
+  } else {
+    k_walk<RATE, false, true><<<grid, kStepThreads, 0, stream>>>(a);
+  }
+  PD_CUDA_OK(cudaGetLastError());
+  return PD_OK;
+}
+
+// pd_run_episodes (after reset and goal selection, pd_episode.cu).
+int launch_episodes(const pd_lattice* lat, const pd_state* st,
+                    const pd_rate_config* rc, const pd_episode_config* cfg,
+                    const double* goal_xy, pd_episode_stats* stats,
+                    cudaStream_t stream) {
+  StepArgs a{};
+  a.lat = *lat;
+  a.st = *st;
+  a.n_controls = 1;
+  a.n_steps = 1;
+  a.ep = *cfg;
+  a.goal_xy = goal_xy;
+  a.stats = stats;
+  a.dwell_us_scalar = cfg->dwell_us;
+  a.image_duration_us = cfg->image_duration_us;
+  for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
+  switch (rc->rate_fn) {
+    case PD_RATE_SIMPLE:
+      return launch_episode_walk<PD_RATE_SIMPLE>(a, stream);
+    case PD_RATE_PRIOR:
+      return launch_episode_walk<PD_RATE_PRIOR>(a, stream);
+    case PD_RATE_CONSTANT:
+      return launch_episode_walk<PD_RATE_CONSTANT>(a, stream);
+    default:
+      set_error("pd_run_episodes: rate_fn %d is not supported", rc->rate_fn);
       return PD_ERR_UNSUPPORTED;
   }
 }

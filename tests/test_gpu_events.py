@@ -30,6 +30,11 @@ def test_lattice_tables_bit_exact(eng):
     np.testing.assert_array_equal(gh.np_(lat.base_xy), po.base_lattice(cols))
     np.testing.assert_array_equal(gh.np_(lat.nbr)[:, :3],
                                   po.neighbor_table(cols))
+    # column 3: the sites within 2.6 A of the lattice centre, then -1
+    cand = gh.np_(lat.nbr)[:, 3]
+    want = np.nonzero((po.base_lattice(cols) ** 2).sum(axis=1) <= 2.6 ** 2)[0]
+    np.testing.assert_array_equal(cand[:want.size], want)
+    assert (cand[want.size:] == -1).all()
 
 
 def test_reset_matches_oracle(eng):
