@@ -59,6 +59,7 @@ def parse_args():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-at-scale', action='store_true')
   ap.add_argument('--no-frames', action='store_true')
+  ap.add_argument('--no-mlp', action='store_true')
   ap.add_argument('--frames', type=int, default=296,
                   help='frames per render launch (512x512)')
   ap.add_argument('--episodes', type=int, default=0,
@@ -267,6 +268,43 @@ def measure_frames(pd, batch, dev, peak, args):
                        'algorithmic_bytes_per_frame': 512 * 512 * 4}}
 
 
+def measure_mlp(pd, batch, dev, args):
+  """BASELINE configs[2]: 65536 envs stepping with the learned rate-model MLP
+  (seeded synthetic weights) -- FP32 FMA GEMM path."""
+  import torch
+  from oracle import pdune_oracle as po  # weights generator only
+  out = {}
+  n = 65536
+  rng = np.random.default_rng(0)
+  for hidden in ((128, 128), (256, 256)):
+    mlp = po.MlpParams.synthetic(7, hidden=hidden)
+    w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
+    rate = pd.RateSpec(2, mlp=w, device=dev)
+    b = pd.EnvBatch(n, seed=11, device=dev, lattice=batch.lattice_tables)
+    b.reset()
+    ctl = torch.as_tensor(synthetic_controls(n, 1, 3)[0][:, None, :]).to(dev)
+    for _ in range(3):
+      b.step_and_image(ctl, DWELL_US, rate, IMAGE_US)
+    torch.cuda.synchronize()
+    ev0 = int(b.n_events.sum().item())
+    evs = [(torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, c in evs:
+      a.record()
+      b.step_and_image(ctl, DWELL_US, rate, IMAGE_US)
+      c.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(c) for a, c in evs) / len(evs)
+    evals = (int(b.n_events.sum().item()) - ev0) / len(evs)
+    flop = 2 * (2 * hidden[0] + hidden[0] * hidden[1] + 4 * hidden[1])
+    out[f'H{hidden[0]}'] = {
+        'envs': n, 'launch_ms': ms, 'env_steps_per_s': n / (ms / 1e3),
+        'rate_evals_per_step': evals / n, 'flop_per_eval': flop,
+        'tflops_fp32': evals * flop / (ms / 1e3) / 1e12,
+        'kernel': 'pd::k_step_learned (FP32 FMA, queue-batched GEMM)'}
+  return out
+
+
 def measure_episodes(pd, args, world, rank, dev, barrier):
   """BASELINE configs[4]: `--episodes` envs sharded over the ranks, greedy
   controller to the end of every episode, stats all-gathered with NCCL."""
@@ -444,6 +482,10 @@ def run_ours(args, cfg):
   if args.episodes:
     episodes = measure_episodes(pd, args, world, rank, dev, barrier)
 
+  mlp = None
+  if rank == 0 and not args.no_mlp:
+    mlp = measure_mlp(pd, batch, dev, args)
+
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import pdune_oracle as po
@@ -464,7 +506,7 @@ def run_ours(args, cfg):
                 'api': 'pd_rollout_host (pinned host buffers)'},
         'gpu_launches': args.steps, 'roofline': roofline,
         'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
-        'episodes': episodes,
+        'episodes': episodes, 'learned_mlp': mlp,
         'wall_s_timed_region': t1 - t0,
     }
     print(json.dumps(line), flush=True)

@@ -40,6 +40,10 @@ constexpr int kTiles = 8;         // CLAHE kernel = shape // 8
 constexpr int kBins = 256;
 constexpr int kGray = 16384;      // NR_OF_GRAY
 constexpr int kBinSize = 1 + kGray / kBins;  // 65
+constexpr int kBands = 16;        // 512 / 32 row bands
+constexpr int kBandCap = 1024;
+constexpr int kInvTable = 256;
+constexpr int kUnroll = 4;        // independent loads per thread per trip
 
 struct RenderArgs {
   pd_lattice lat;
@@ -69,6 +73,10 @@ struct RenderShared {
   int n_atoms;
   int lwy, lwx, lwb;
   unsigned short maps[kTiles * kTiles][kBins];
+  // P1: atoms that can touch each 32-row band, in atom order
+  unsigned short band_list[kBands][kBandCap];
+  int band_n[kBands];
+  double inv_k[kInvTable];     // 1/k for the Poisson recurrence
   // union: row accumulators (P1/P2) or histograms (P7)
   union {
     float rows[kRenderWarps][512];
@@ -92,6 +100,20 @@ __device__ __forceinline__ int poisson_icdf(double lam, double u) {
   while (u >= cdf && k < 100000) {
     ++k;
     p = p * lam / static_cast<double>(k);
+    cdf += p;
+  }
+  return k;
+}
+
+// Same recurrence with 1/k from a shared table (k < kInvTable).
+__device__ __forceinline__ int poisson_icdf_tab(double lam, double u,
+                                                const double* inv_k) {
+  double p = exp(-lam);
+  double cdf = p;
+  int k = 0;
+  while (u >= cdf && k < 100000) {
+    ++k;
+    p = p * lam * (k < kInvTable ? inv_k[k] : 1.0 / static_cast<double>(k));
     cdf += p;
   }
   return k;
@@ -181,6 +203,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
   float* v0 = a.scratch + static_cast<size_t>(blockIdx.x) * 2 * npix;
   float* v1 = v0 + npix;
   const double2* base = reinterpret_cast<const double2*>(a.lat.base_xy);
+
+  for (int i = tid; i < kInvTable; i += kRenderThreads)
+    sh.inv_k[i] = i > 0 ? 1.0 / static_cast<double>(i) : 0.0;
 
   for (int f = blockIdx.x; f < a.m; f += gridDim.x) {
     const int e = a.env_ids ? a.env_ids[f] : f;
@@ -298,6 +323,26 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
     }
     const int n_atoms = sh.n_atoms;
     const int lwy = sh.lwy, lwx = sh.lwx, lwb = sh.lwb;
+    // band lists: warp b collects, in atom order, the atoms whose kernel
+    // footprint reaches rows [32 b, 32 b + 31]
+    bool bands_ok = true;
+    if (warp < kBands) {
+      const int r_lo = warp * 32 - lwy, r_hi = warp * 32 + 31 + lwy;
+      int cnt = 0;
+      for (int i0 = 0; i0 < n_atoms; i0 += 32) {
+        const int i = i0 + lane;
+        const bool hit = i < n_atoms && sh.atom_rc[i].x >= r_lo &&
+                         sh.atom_rc[i].x <= r_hi;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < kBandCap)
+          sh.band_list[warp][pos] = static_cast<unsigned short>(i);
+        cnt += __popc(m);
+      }
+      if (lane == 0) sh.band_n[warp] = cnt;
+    }
+    __syncthreads();
+    for (int b = 0; b < kBands; ++b) bands_ok &= sh.band_n[b] <= kBandCap;
 
     // ---------------------------------------------------------------- P1
     float vmax = 0.f;
@@ -306,7 +351,10 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       for (int r = warp; r < S; r += kRenderWarps) {
         for (int c = lane; c < S; c += 32) acc[c] = 0.f;
         __syncwarp();
-        for (int i = 0; i < n_atoms; ++i) {
+        const int band = r >> 5;
+        const int n_list = bands_ok ? sh.band_n[band] : n_atoms;
+        for (int ii = 0; ii < n_list; ++ii) {
+          const int i = bands_ok ? sh.band_list[band][ii] : ii;
           const short2 rc = sh.atom_rc[i];
           int dr = r - rc.x;
           dr = dr < 0 ? -dr : dr;
@@ -377,12 +425,20 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float scale = poisson_mult / m_prev;
       vmax = 0.f;
       __syncthreads();
-      for (int p = tid; p < npix; p += kRenderThreads) {
-        const uint4 w = philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
-        const float k = static_cast<float>(poisson_icdf(
-            static_cast<double>(cur[p] * scale), u24(w.x)));
-        cur[p] = k;
-        vmax = fmaxf(vmax, k);
+      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
+        float v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = cur[p0 + u * kRenderThreads];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int p = p0 + u * kRenderThreads;
+          const uint4 w =
+              philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
+          const float k = static_cast<float>(poisson_icdf_tab(
+              static_cast<double>(v[u] * scale), u24(w.x), sh.inv_k));
+          cur[p] = k;
+          vmax = fmaxf(vmax, k);
+        }
       }
       m_prev = block_max(vmax, sh.red_a);
     }
@@ -399,21 +455,32 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const bool jitter_only = a.stop_stage == PD_RENDER_JITTER;
       vmax = 0.f;
       __syncthreads();
-      for (int p = tid; p < npix; p += kRenderThreads) {
-        const int r = p >> a.log2_size, c = p & mask;
-        // np.roll(row, k): out[(j + k) % S] = in[j]
-        float v = cur[r * S + ((c - sh.shift[r]) & mask)] * inv;
-        if (jitter_only) {
-          out[p] = v;
-          continue;
+      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
+        float vv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int p = p0 + u * kRenderThreads;
+          const int r = p >> a.log2_size, c = p & mask;
+          // np.roll(row, k): out[(j + k) % S] = in[j]
+          vv[u] = cur[r * S + ((c - sh.shift[r]) & mask)];
         }
-        const uint4 w = philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
-        if (u24(w.y) <= sp_amount) v = u24(w.z) <= 0.5f ? 1.0f : 0.0f;
-        v = fminf(fmaxf(v, 0.f), 1.f);
-        v = powf(v, gamma);
-        v += uniform_scale * u24(w.w);
-        other[p] = v;
-        vmax = fmaxf(vmax, v);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int p = p0 + u * kRenderThreads;
+          float v = vv[u] * inv;
+          if (jitter_only) {
+            out[p] = v;
+            continue;
+          }
+          const uint4 w =
+              philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
+          if (u24(w.y) <= sp_amount) v = u24(w.z) <= 0.5f ? 1.0f : 0.0f;
+          v = fminf(fmaxf(v, 0.f), 1.f);
+          v = powf(v, gamma);
+          v += uniform_scale * u24(w.w);
+          other[p] = v;
+          vmax = fmaxf(vmax, v);
+        }
       }
       if (jitter_only) continue;
       m_prev = block_max(vmax, sh.red_a);
@@ -433,13 +500,22 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float inv = 1.0f / m_prev;
       vmax = 0.f;
       __syncthreads();
-      for (int j = tid; j < npix / 2; j += kRenderThreads) {
-        const uint4 w = philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
-        float2 v = reinterpret_cast<float2*>(cur)[j];
-        v.x = v.x * inv - log1pf(-u24(w.x)) * exp_lambda;
-        v.y = v.y * inv - log1pf(-u24(w.y)) * exp_lambda;
-        reinterpret_cast<float2*>(cur)[j] = v;
-        vmax = fmaxf(vmax, fmaxf(v.x, v.y));
+      for (int j0 = tid; j0 < npix / 2; j0 += kUnroll * kRenderThreads) {
+        float2 vv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          vv[u] = reinterpret_cast<float2*>(cur)[j0 + u * kRenderThreads];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int j = j0 + u * kRenderThreads;
+          const uint4 w =
+              philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
+          float2 v = vv[u];
+          v.x = v.x * inv - log1pf(-u24(w.x)) * exp_lambda;
+          v.y = v.y * inv - log1pf(-u24(w.y)) * exp_lambda;
+          reinterpret_cast<float2*>(cur)[j] = v;
+          vmax = fmaxf(vmax, fmaxf(v.x, v.y));
+        }
       }
       m_prev = block_max(vmax, sh.red_a);
     }
@@ -456,17 +532,26 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float inv = 1.0f / m_prev;
       float lo = 1e30f, hi = -1e30f;
       __syncthreads();
-      for (int j = tid; j < npix / 2; j += kRenderThreads) {
-        const uint4 w = philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
-        const float rad = sqrtf(-2.0f * logf(u24_open(w.z)));
-        float sn, cs;
-        sincospif(2.0f * u24(w.w), &sn, &cs);
-        float2 v = reinterpret_cast<float2*>(cur)[j];
-        v.x = fminf(fmaxf(v.x * inv + gauss_sd * (rad * cs), 0.f), 1.f);
-        v.y = fminf(fmaxf(v.y * inv + gauss_sd * (rad * sn), 0.f), 1.f);
-        reinterpret_cast<float2*>(cur)[j] = v;
-        lo = fminf(lo, fminf(v.x, v.y));
-        hi = fmaxf(hi, fmaxf(v.x, v.y));
+      for (int j0 = tid; j0 < npix / 2; j0 += kUnroll * kRenderThreads) {
+        float2 vv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          vv[u] = reinterpret_cast<float2*>(cur)[j0 + u * kRenderThreads];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int j = j0 + u * kRenderThreads;
+          const uint4 w =
+              philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
+          const float rad = sqrtf(-2.0f * logf(u24_open(w.z)));
+          float sn, cs;
+          sincospif(2.0f * u24(w.w), &sn, &cs);
+          float2 v = vv[u];
+          v.x = fminf(fmaxf(v.x * inv + gauss_sd * (rad * cs), 0.f), 1.f);
+          v.y = fminf(fmaxf(v.y * inv + gauss_sd * (rad * sn), 0.f), 1.f);
+          reinterpret_cast<float2*>(cur)[j] = v;
+          lo = fminf(lo, fminf(v.x, v.y));
+          hi = fmaxf(hi, fmaxf(v.x, v.y));
+        }
       }
       g_max = block_max(hi, sh.red_a);
       g_min = block_min(lo, sh.red_b);
@@ -486,14 +571,21 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       __syncthreads();
       const float range = g_max - g_min;
       const float q_scale = range > 0.f ? (kGray - 1) / range : 0.f;
-      for (int p = tid; p < npix; p += kRenderThreads) {
-        const int r = p >> a.log2_size, c = p & mask;
-        // np.round(rescale_intensity(img, out_range=(0, 16383)))
-        const float q = rintf((cur[p] - g_min) * q_scale);
-        const int bin = static_cast<int>(q) / kBinSize;
-        other[p] = __int_as_float(bin);
-        atomicAdd(&sh.u.hist[(r >> log2_ts) * kTiles + (c >> log2_ts)][bin],
-                  1);
+      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
+        float vv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) vv[u] = cur[p0 + u * kRenderThreads];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int p = p0 + u * kRenderThreads;
+          const int r = p >> a.log2_size, c = p & mask;
+          // np.round(rescale_intensity(img, out_range=(0, 16383)))
+          const float q = rintf((vv[u] - g_min) * q_scale);
+          const int bin = static_cast<int>(q) / kBinSize;
+          other[p] = __int_as_float(bin);
+          atomicAdd(
+              &sh.u.hist[(r >> log2_ts) * kTiles + (c >> log2_ts)][bin], 1);
+        }
       }
       __syncthreads();
       if (tid < kTiles * kTiles) {
@@ -509,9 +601,16 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
     {
       const float inv_ts = 1.0f / ts;
       const int half = ts >> 1;
-      for (int p = tid; p < npix; p += kRenderThreads) {
+      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
+       int bins[kUnroll];
+#pragma unroll
+       for (int u = 0; u < kUnroll; ++u)
+         bins[u] = __float_as_int(other[p0 + u * kRenderThreads]);
+#pragma unroll
+       for (int u = 0; u < kUnroll; ++u) {
+        const int p = p0 + u * kRenderThreads;
         const int r = p >> a.log2_size, c = p & mask;
-        const int bin = __float_as_int(other[p]);
+        const int bin = bins[u];
         const int pr = r + half, pc = c + half;
         const int bi = pr >> log2_ts, bj = pc >> log2_ts;
         const float cy = (pr & (ts - 1)) * inv_ts;
@@ -533,6 +632,7 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
         cur[p] = __int_as_float(mv);
         m_lo = min(m_lo, mv);
         m_hi = max(m_hi, mv);
+       }
       }
       m_hi = static_cast<int>(block_max(static_cast<float>(m_hi), sh.red_a));
       m_lo = static_cast<int>(block_min(static_cast<float>(m_lo), sh.red_b));
@@ -542,10 +642,20 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
     {
       const float denom = static_cast<float>(m_hi - m_lo);
       __syncthreads();
-      for (int p = tid; p < npix; p += kRenderThreads) {
-        const int mv = __float_as_int(cur[p]);
-        out[p] = denom > 0.f ? static_cast<float>(mv - m_lo) / denom
-                             : fminf(fmaxf(static_cast<float>(mv), 0.f), 1.f);
+      const float inv_d = denom > 0.f ? 1.0f / denom : 0.f;
+      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
+        int mvs[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          mvs[u] = __float_as_int(cur[p0 + u * kRenderThreads]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int mv = mvs[u];
+          // rescale_intensity: (v - min) / (max - min)
+          out[p0 + u * kRenderThreads] =
+              denom > 0.f ? static_cast<float>(mv - m_lo) * inv_d
+                          : fminf(fmaxf(static_cast<float>(mv), 0.f), 1.f);
+        }
       }
     }
   }
