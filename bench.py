@@ -90,10 +90,18 @@ def workload_config(args):
 
 
 def synthetic_controls(n_envs, beam_steps, seed):
-  """Beam positions U(-1,1)^2 bond lengths around the frame centre, which is
-  where the re-centring FOV keeps the Si (relative_random, registry.py:263)."""
+  """The `relative_random` workload (experiments/registry.py:263-266): agent
+  actions U(-1, 1)^2, turned into beam positions within one bond length of the
+  Si by RelativeToSiliconActionAdapter (action_adapters.py:131-216).  The
+  adapter runs on the device (pd_rollout_actions); the CPU arm applies the
+  oracle's restatement of the same adapter."""
   rng = np.random.default_rng(seed)
-  # FOV is 15-30 A wide: one bond is 1.42/22.5 of the frame on average.
+  return rng.uniform(-1.0, 1.0, size=(beam_steps, n_envs, 2))
+
+
+def direct_controls(n_envs, beam_steps, seed):
+  """Microscope-frame beam positions near the frame centre (Direct adapter)."""
+  rng = np.random.default_rng(seed)
   return 0.5 + rng.uniform(-1.0, 1.0, size=(beam_steps, n_envs, 2)) * (
       1.42 / 22.5)
 
@@ -154,12 +162,14 @@ class ClockSampler:
 def _cpu_worker(args):
   seed, env_offset, n_envs, beam_steps, rate_fn, ctrl_seed = args
   from oracle import pdune_oracle as po
+  from oracle import pdune_oracle_episode as oe
   st = po.make_state(n_envs, seed, env_offset=env_offset)
   po.reset(st)
-  ctl = synthetic_controls(n_envs, beam_steps, ctrl_seed)
+  act = synthetic_controls(n_envs, beam_steps, ctrl_seed)
   t0 = time.perf_counter()
   for t in range(beam_steps):
-    po.step_and_image(st, ctl[t][:, None, :], DWELL_US, IMAGE_US,
+    ctl = oe.relative_to_silicon_controls(st, act[t])
+    po.step_and_image(st, ctl[:, None, :], DWELL_US, IMAGE_US,
                       rate_fn=rate_fn)
   return time.perf_counter() - t0, n_envs * beam_steps
 
@@ -282,7 +292,7 @@ def measure_mlp(pd, batch, dev, args):
     rate = pd.RateSpec(2, mlp=w, device=dev)
     b = pd.EnvBatch(n, seed=11, device=dev, lattice=batch.lattice_tables)
     b.reset()
-    ctl = torch.as_tensor(synthetic_controls(n, 1, 3)[0][:, None, :]).to(dev)
+    ctl = torch.as_tensor(direct_controls(n, 1, 3)[0][:, None, :]).to(dev)
     for _ in range(3):
       b.step_and_image(ctl, DWELL_US, rate, IMAGE_US)
     torch.cuda.synchronize()
@@ -369,9 +379,10 @@ def run_ours(args, cfg):
   P = lambda t: C.c_void_p(t.data_ptr())
 
   def launch(i):
-    nat.check(nat.lib.pd_rollout(lat_c, st_c, C.byref(rate.c),
-                                 P(d_ctl[i % pool]), DWELL_US, t_steps,
-                                 IMAGE_US, None, None, stream))
+    nat.check(nat.lib.pd_rollout_actions(
+        lat_c, st_c, C.byref(rate.c), P(d_ctl[i % pool]),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
+        None, None, stream))
 
   # -- device-resident: value -----------------------------------------------
   for i in range(args.warmup):
@@ -407,9 +418,10 @@ def run_ours(args, cfg):
   h_el = torch.empty((t_steps, n), dtype=torch.int64).pin_memory()
 
   def launch_host(i):
-    nat.check(nat.lib.pd_rollout_host(
-        lat_c, st_c, C.byref(rate.c), P(h_ctl[i % pool]), DWELL_US, t_steps,
-        IMAGE_US, P(d_stage), P(d_si), P(d_el), P(h_si), P(h_el), stream))
+    nat.check(nat.lib.pd_rollout_actions_host(
+        lat_c, st_c, C.byref(rate.c), P(h_ctl[i % pool]),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
+        P(d_stage), P(d_si), P(d_el), P(h_si), P(h_el), stream))
 
   for i in range(args.warmup):
     launch_host(i)
@@ -446,13 +458,13 @@ def run_ours(args, cfg):
     big = pd.EnvBatch(big_n, seed=1, device=dev,
                       lattice=batch.lattice_tables)
     big.reset()
-    ctl = [torch.as_tensor(synthetic_controls(big_n, 1, 7 + i)[0][:, None, :]
-                           ).to(dev).contiguous() for i in range(pool)]
-    out_c = C.byref(big._out_c)  # pylint: disable=protected-access
+    acts = [torch.as_tensor(synthetic_controls(big_n, 1, 7 + i)).to(dev)
+            for i in range(pool)]
     def big_launch(i):
-      nat.check(nat.lib.pd_step_and_image(
+      nat.check(nat.lib.pd_rollout_actions(
           C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
-          P(ctl[i % pool]), None, DWELL_US, 1, IMAGE_US, out_c, stream))
+          P(acts[i % pool]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US,
+          1, IMAGE_US, None, None, stream))
     for i in range(3):
       big_launch(i)
     torch.cuda.synchronize()
@@ -467,8 +479,9 @@ def run_ours(args, cfg):
     ms = sum(a.elapsed_time(b) for a, b in bev) / 10
     a_gbs = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n / (ms / 1e3) / 1e9
     at_scale = {
-        'workload': '1Mi envs x 1 step_and_image per launch, 1 GPU',
-        'kernel': 'pd::k_step', 'value': big_n / (ms / 1e3), 'unit': UNIT,
+        'workload': '1Mi envs x 1 step per launch, same actions/adapter, '
+                    '1 GPU',
+        'kernel': 'pd::k_walk', 'value': big_n / (ms / 1e3), 'unit': UNIT,
         'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak}
     del big
 
@@ -503,7 +516,7 @@ def run_ours(args, cfg):
         'data': 'synthetic', 'config': cfg, 'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h,
-                'api': 'pd_rollout_host (pinned host buffers)'},
+                'api': 'pd_rollout_actions_host (pinned host buffers)'},
         'gpu_launches': args.steps, 'roofline': roofline,
         'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
         'episodes': episodes, 'learned_mlp': mlp,

@@ -222,6 +222,26 @@ int pd_rollout(const pd_lattice* lat, const pd_state* st,
                int64_t image_duration_us, int32_t* si_idx_out,
                int64_t* elapsed_us_out, void* stream);
 
+/* Action adapters (action_adapters.py): how a value of the action stream
+ * becomes a beam position in the microscope frame. */
+typedef enum pd_action_mode {
+  PD_ACTION_DIRECT = 0,   /* the value IS the position (DirectActionAdapter,
+                             action_adapters.py:53-84, without the clip)     */
+  PD_ACTION_RELATIVE_TO_SILICON = 1 /* RelativeToSiliconActionAdapter
+                             (:131-216): clip(si + clip(a,-1,1) *
+                             max_distance / fov_extent, 0, 1)                */
+} pd_action_mode;
+
+/* pd_rollout with an action adapter applied on the device before each step
+ * (the observation the adapter reads is the env's own current one).
+ * actions_xy: device double [n_steps][n][2]. */
+int pd_rollout_actions(const pd_lattice* lat, const pd_state* st,
+                       const pd_rate_config* rc, const double* actions_xy,
+                       int32_t action_mode, double max_distance_angstroms,
+                       int64_t dwell_us_scalar, int32_t n_steps,
+                       int64_t image_duration_us, int32_t* si_idx_out,
+                       int64_t* elapsed_us_out, void* stream);
+
 /* Same with HOST buffers: copies the action stream host->device into
  * d_controls_xy, runs the fused steps, copies the per-step Si sites and
  * elapsed times back and synchronises `stream`.  h_si_idx / h_elapsed_us may
@@ -232,6 +252,15 @@ int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
                     int64_t image_duration_us, double* d_controls_xy,
                     int32_t* d_si_idx, int64_t* d_elapsed_us,
                     int32_t* h_si_idx, int64_t* h_elapsed_us, void* stream);
+int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
+                            const pd_rate_config* rc,
+                            const double* h_actions_xy, int32_t action_mode,
+                            double max_distance_angstroms,
+                            int64_t dwell_us_scalar, int32_t n_steps,
+                            int64_t image_duration_us, double* d_actions_xy,
+                            int32_t* d_si_idx, int64_t* d_elapsed_us,
+                            int32_t* h_si_idx, int64_t* h_elapsed_us,
+                            void* stream);
 
 /* ---- queries: graphene.py:600-644 get_atoms_in_bounds,
  *      graphene.py:696-700 get_silicon_position --------------------------- */

@@ -179,3 +179,17 @@ def aggregate(res: dict) -> dict:
           float(np.nansum(res['env_seconds'][r])) / den,
       'average_total_reward': float(res['total_reward'][r].sum()) / den,
   }
+
+
+def relative_to_silicon_controls(state: po.OracleState, actions: np.ndarray,
+                                 max_distance: float = po.BOND) -> np.ndarray:
+  """action_adapters.py:163-188 `RelativeToSiliconActionAdapter.get_action`
+  for every env: clip(si_observed + clip(a, -1, 1) * max_distance / fov, 0, 1).
+  actions: [E, 2] -> control positions [E, 2] in the microscope frame."""
+  envs = np.arange(state.num_envs)
+  a = np.clip(np.asarray(actions, dtype=np.float64), -1.0, 1.0)
+  q_si = observe_site(state, envs, state.si_idx)
+  f = state.fov
+  radius = np.stack((max_distance / (f[:, 2] - f[:, 0]),
+                     max_distance / (f[:, 3] - f[:, 1])), axis=1)
+  return np.clip(q_si + a * radius, 0.0, 1.0)

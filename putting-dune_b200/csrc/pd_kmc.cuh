@@ -290,6 +290,8 @@ struct StepArgs {
   int32_t n_steps;            // rollout only
   int64_t image_duration_us;
   int32_t material_frame;     // 1: apply_control (no observe phase)
+  int32_t action_mode;        // pd_action_mode (rollouts)
+  double max_distance;        // RelativeToSilicon adapter, angstroms
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]
   int64_t* elapsed_us_out;    // rollout [T][n]

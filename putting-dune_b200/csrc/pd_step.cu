@@ -172,7 +172,11 @@ __global__ void __launch_bounds__(kStepThreads)
       if (t + 1 < a.n_steps)
         next = reinterpret_cast<const double2*>(
             a.controls_xy)[static_cast<int64_t>(t + 1) * n + e];
-      const double2 beam = microscope_to_material(fov, ctl.x, ctl.y);
+      const double2 pos =
+          a.action_mode == PD_ACTION_RELATIVE_TO_SILICON
+              ? relative_to_silicon(fov, r.psi, ctl, a.max_distance)
+              : ctl;
+      const double2 beam = microscope_to_material(fov, pos.x, pos.y);
       run_control<RATE>(tab, a.ra, a.st.seed, beam, a.dwell_us_scalar, 0, e,
                         log, &r);
       long long elapsed = a.dwell_us_scalar + a.image_duration_us;
@@ -347,6 +351,8 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
                 if (t + 1 < n_steps)
                   next_ctl = reinterpret_cast<const double2*>(
                       a.controls_xy)[static_cast<int64_t>(t + 1) * n + env];
+                if (a.action_mode == PD_ACTION_RELATIVE_TO_SILICON)
+                  ctl = relative_to_silicon(fov, r.psi, ctl, a.max_distance);
               } else if (c > 0) {
                 ctl = reinterpret_cast<const double2*>(a.controls_xy)[ci];
               }
@@ -806,6 +812,23 @@ extern "C" int pd_rollout(const pd_lattice* lat, const pd_state* st,
                           int64_t dwell_us_scalar, int32_t n_steps,
                           int64_t image_duration_us, int32_t* si_idx_out,
                           int64_t* elapsed_us_out, void* stream) {
+  return pd_rollout_actions(lat, st, rc, controls_xy, PD_ACTION_DIRECT, 0.0,
+                            dwell_us_scalar, n_steps, image_duration_us,
+                            si_idx_out, elapsed_us_out, stream);
+}
+
+extern "C" int pd_rollout_actions(const pd_lattice* lat, const pd_state* st,
+                                  const pd_rate_config* rc,
+                                  const double* controls_xy,
+                                  int32_t action_mode,
+                                  double max_distance_angstroms,
+                                  int64_t dwell_us_scalar, int32_t n_steps,
+                                  int64_t image_duration_us,
+                                  int32_t* si_idx_out, int64_t* elapsed_us_out,
+                                  void* stream) {
+  PD_REQUIRE(action_mode == PD_ACTION_DIRECT ||
+                 action_mode == PD_ACTION_RELATIVE_TO_SILICON,
+             "unknown action_mode");
   int rcode = pd::validate_common(lat, st, rc);
   if (rcode != PD_OK) return rcode;
   PD_REQUIRE(rc != nullptr, "null rate config");
@@ -819,6 +842,8 @@ extern "C" int pd_rollout(const pd_lattice* lat, const pd_state* st,
   a.dwell_us_scalar = dwell_us_scalar;
   a.n_controls = 1;
   a.n_steps = n_steps;
+  a.action_mode = action_mode;
+  a.max_distance = max_distance_angstroms;
   a.image_duration_us = image_duration_us;
   a.si_idx_out = si_idx_out;
   a.elapsed_us_out = elapsed_us_out;
@@ -836,6 +861,49 @@ extern "C" int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
                                double* d_controls_xy, int32_t* d_si_idx,
                                int64_t* d_elapsed_us, int32_t* h_si_idx,
                                int64_t* h_elapsed_us, void* stream) {
+  return pd_rollout_actions_host(lat, st, rc, h_controls_xy, PD_ACTION_DIRECT,
+                                 0.0, dwell_us_scalar, n_steps,
+                                 image_duration_us, d_controls_xy, d_si_idx,
+                                 d_elapsed_us, h_si_idx, h_elapsed_us, stream);
+}
+
+namespace pd {
+// Side streams for the host-buffer entry points: the action stream is split
+// into chunks so that the H2D copy of chunk i+1, the kernel of chunk i and
+// the D2H copy of chunk i-1 overlap (PCIe is full duplex).
+struct HostPipeline {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t start = nullptr, copied[8] = {}, stepped[8] = {};
+  int device = -1;
+};
+
+static int host_pipeline(HostPipeline** out) {
+  static thread_local HostPipeline p;
+  int dev = 0;
+  PD_CUDA_OK(cudaGetDevice(&dev));
+  if (p.device != dev) {
+    PD_CUDA_OK(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+    PD_CUDA_OK(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+    PD_CUDA_OK(cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) {
+      PD_CUDA_OK(cudaEventCreateWithFlags(&p.copied[i], cudaEventDisableTiming));
+      PD_CUDA_OK(
+          cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming));
+    }
+    p.device = dev;
+  }
+  *out = &p;
+  return PD_OK;
+}
+}  // namespace pd
+
+extern "C" int pd_rollout_actions_host(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const double* h_controls_xy, int32_t action_mode,
+    double max_distance_angstroms, int64_t dwell_us_scalar, int32_t n_steps,
+    int64_t image_duration_us, double* d_controls_xy, int32_t* d_si_idx,
+    int64_t* d_elapsed_us, int32_t* h_si_idx, int64_t* h_elapsed_us,
+    void* stream) {
   PD_REQUIRE(st != nullptr, "null state");
   PD_REQUIRE(n_steps >= 0, "negative n_steps");
   PD_REQUIRE(n_steps == 0 || (h_controls_xy && d_controls_xy),
@@ -843,22 +911,49 @@ extern "C" int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
   PD_REQUIRE(!h_si_idx || d_si_idx, "si_idx needs device staging");
   PD_REQUIRE(!h_elapsed_us || d_elapsed_us, "elapsed needs device staging");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t items = static_cast<size_t>(st->n_envs) * n_steps;
-  if (items > 0)
-    PD_CUDA_OK(cudaMemcpyAsync(d_controls_xy, h_controls_xy,
-                               items * 2 * sizeof(double),
-                               cudaMemcpyHostToDevice, s));
-  int rcode = pd_rollout(lat, st, rc, d_controls_xy, dwell_us_scalar, n_steps,
-                         image_duration_us, h_si_idx ? d_si_idx : nullptr,
-                         h_elapsed_us ? d_elapsed_us : nullptr, stream);
+  const int64_t n = st->n_envs;
+  if (n == 0 || n_steps == 0) return PD_OK;
+  pd::HostPipeline* pipe = nullptr;
+  int rcode = pd::host_pipeline(&pipe);
   if (rcode != PD_OK) return rcode;
-  if (h_si_idx && items > 0)
-    PD_CUDA_OK(cudaMemcpyAsync(h_si_idx, d_si_idx, items * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, s));
-  if (h_elapsed_us && items > 0)
-    PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us, d_elapsed_us,
-                               items * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                               s));
+  const int n_chunks = n_steps >= 32 ? 4 : 1;
+  // staging may still be read by earlier work queued on `s`
+  PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
+  int t0[9];
+  for (int c = 0; c <= n_chunks; ++c)
+    t0[c] = static_cast<int>(static_cast<int64_t>(n_steps) * c / n_chunks);
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n * 2;
+    const size_t cnt = static_cast<size_t>(t0[c + 1] - t0[c]) * n * 2;
+    PD_CUDA_OK(cudaMemcpyAsync(d_controls_xy + off, h_controls_xy + off,
+                               cnt * sizeof(double), cudaMemcpyHostToDevice,
+                               pipe->h2d));
+    PD_CUDA_OK(cudaEventRecord(pipe->copied[c], pipe->h2d));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n;
+    const int steps = t0[c + 1] - t0[c];
+    PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->copied[c], 0));
+    rcode = pd_rollout_actions(
+        lat, st, rc, d_controls_xy + off * 2, action_mode,
+        max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
+        h_si_idx ? d_si_idx + off : nullptr,
+        h_elapsed_us ? d_elapsed_us + off : nullptr, stream);
+    if (rcode != PD_OK) return rcode;
+    PD_CUDA_OK(cudaEventRecord(pipe->stepped[c], s));
+    PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0));
+    if (h_si_idx)
+      PD_CUDA_OK(cudaMemcpyAsync(h_si_idx + off, d_si_idx + off,
+                                 static_cast<size_t>(steps) * n * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, pipe->d2h));
+    if (h_elapsed_us)
+      PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us + off, d_elapsed_us + off,
+                                 static_cast<size_t>(steps) * n * sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, pipe->d2h));
+  }
+  PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
   PD_CUDA_OK(cudaStreamSynchronize(s));
   return PD_OK;
 }

@@ -18,6 +18,7 @@ PD_OK = 0
 RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT = 0, 1, 2, 3
 ENV_BAD_RATE, ENV_LOG_OVERFLOW, ENV_NOT_RESET = 1, 2, 4
 STREAM_KMC, STREAM_RESET = 0, 1
+ACTION_DIRECT, ACTION_RELATIVE_TO_SILICON = 0, 1
 (RENDER_CLEAN, RENDER_BLUR, RENDER_POISSON, RENDER_JITTER, RENDER_UNIFORM,
  RENDER_EXPONENTIAL, RENDER_GAUSSIAN, RENDER_FINAL) = range(8)
 
@@ -99,6 +100,11 @@ _SIGNATURES = {
     'pd_step_and_image_host': ([_LP, _SP, _RP, _p, _p, _i64, _i32, _i64, _p,
                                 _p, _OP, _p, _p, _p, _p], C.c_int),
     'pd_rollout': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p], C.c_int),
+    'pd_rollout_actions': ([_LP, _SP, _RP, _p, _i32, C.c_double, _i64, _i32,
+                            _i64, _p, _p, _p], C.c_int),
+    'pd_rollout_actions_host': ([_LP, _SP, _RP, _p, _i32, C.c_double, _i64,
+                                 _i32, _i64, _p, _p, _p, _p, _p, _p],
+                                C.c_int),
     'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
                          _p, _p], C.c_int),
     'pd_run_episodes': ([_LP, _SP, _RP, C.POINTER(PdEpisodeConfig), _p, _p, _p,

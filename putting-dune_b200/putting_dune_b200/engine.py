@@ -289,11 +289,15 @@ class EnvBatch:
     return self._out
 
   def rollout(self, controls_xy, dwell_us: int, rate: RateSpec,
-              image_duration_us: int = 2000000, record: bool = False):
+              image_duration_us: int = 2000000, record: bool = False,
+              action_mode: int = nat.ACTION_DIRECT,
+              max_distance_angstroms: float = 1.42):
     """``n_steps`` single-control steps fused in one launch.
 
-    controls_xy: [T, E, 2] microscope frame.  Returns (si_idx [T, E],
-    elapsed_us [T, E]) if ``record`` else None.
+    controls_xy: [T, E, 2]: beam positions in the microscope frame
+    (ACTION_DIRECT) or actions in [-1, 1]^2 relative to the Si
+    (ACTION_RELATIVE_TO_SILICON, action_adapters.py:131-216).  Returns
+    (si_idx [T, E], elapsed_us [T, E]) if ``record`` else None.
     """
     ctl = torch.as_tensor(controls_xy, dtype=torch.float64,
                           device=self.device)
@@ -308,10 +312,11 @@ class EnvBatch:
       el = torch.empty((t, self.num_envs), dtype=torch.int64,
                        device=self.device)
     with torch.cuda.device(self.device):
-      nat.check(nat.lib.pd_rollout(
+      nat.check(nat.lib.pd_rollout_actions(
           C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
-          _ptr(ctl), int(dwell_us), t, int(image_duration_us), _ptr(si),
-          _ptr(el), _stream(self.device)))
+          _ptr(ctl), int(action_mode), float(max_distance_angstroms),
+          int(dwell_us), t, int(image_duration_us), _ptr(si), _ptr(el),
+          _stream(self.device)))
     return (si, el) if record else None
 
   # -- queries --------------------------------------------------------------

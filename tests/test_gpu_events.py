@@ -345,3 +345,75 @@ def test_checkpoint_resume(eng):
   b.step_and_image(ctl, 5000000, spec)
   np.testing.assert_array_equal(gh.np_(a.si_idx), gh.np_(b.si_idx))
   np.testing.assert_array_equal(gh.np_(a.sim_time_us), gh.np_(b.sim_time_us))
+
+
+def test_rollout_with_relative_to_silicon_adapter(eng):
+  """On-device RelativeToSiliconActionAdapter (action_adapters.py:131-216):
+  actions in [-1, 1]^2 around the Si, checked step by step against the
+  oracle's adapter + step_and_image."""
+  from oracle import pdune_oracle_episode as oe
+  from putting_dune_b200 import _native as nat
+  n, t_steps, seed = 3000, 10, 33
+  rng = np.random.default_rng(8)
+  actions = rng.uniform(-1.3, 1.3, size=(t_steps, n, 2))  # exercises the clip
+  for rate_fn in (po.RATE_SIMPLE, po.RATE_PRIOR):
+    st = po.make_state(n, seed)
+    po.reset(st)
+    b = gh.batch_from_oracle(st)
+    si, el = b.rollout(actions, 5000000, gh.rate_spec(rate_fn), record=True,
+                       action_mode=nat.ACTION_RELATIVE_TO_SILICON,
+                       max_distance_angstroms=1.42)
+    for t in range(t_steps):
+      ctl = oe.relative_to_silicon_controls(st, actions[t])[:, None, :]
+      want = po.step_and_image(st, ctl, 5000000, rate_fn=rate_fn)
+      np.testing.assert_array_equal(gh.np_(si[t]), st.si_idx)
+      np.testing.assert_array_equal(gh.np_(el[t]), want['elapsed_us'])
+    np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+    np.testing.assert_array_equal(gh.np_(b.n_transitions), st.n_transitions)
+    assert st.n_transitions.sum() > (2000 if rate_fn == po.RATE_SIMPLE else 300)
+  # the same through the large-batch kernel
+  big = eng.EnvBatch(160000, seed=seed)
+  small = eng.EnvBatch(3000, seed=seed)
+  big.reset()
+  small.reset()
+  acts = rng.uniform(-1, 1, size=(4, 160000, 2))
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  kw = dict(action_mode=nat.ACTION_RELATIVE_TO_SILICON, record=True)
+  s_big, _ = big.rollout(acts, 5000000, spec, **kw)
+  s_small, _ = small.rollout(acts[:, :3000].copy(), 5000000, spec, **kw)
+  np.testing.assert_array_equal(gh.np_(s_big)[:, :3000], gh.np_(s_small))
+
+
+def test_rollout_host_pipeline_matches_device_path(eng):
+  """pd_rollout_actions_host (chunked H2D / step / D2H overlap) returns what
+  the device-resident rollout computes."""
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  n, t_steps, seed = 4096, 37, 51
+  rng = np.random.default_rng(9)
+  acts = torch.as_tensor(rng.uniform(-1, 1, size=(t_steps, n, 2))).pin_memory()
+  a = eng.EnvBatch(n, seed=seed)
+  b = eng.EnvBatch(n, seed=seed)
+  a.reset()
+  b.reset()
+  spec = gh.rate_spec(po.RATE_PRIOR)
+  si, el = a.rollout(acts, 1500000, spec, record=True,
+                     action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+  dev = b.device
+  d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
+  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+  h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
+  h_el = torch.empty((t_steps, n), dtype=torch.int64).pin_memory()
+  P = lambda t: C.c_void_p(t.data_ptr())
+  for _ in range(2):  # second call re-uses the cached side streams
+    b.load_state_dict(a.state_dict()) if _ else None
+    nat.check(nat.lib.pd_rollout_actions_host(
+        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
+        P(d_ctl), P(d_si), P(d_el), P(h_si), P(h_el),
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    if _ == 0:
+      np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
+      np.testing.assert_array_equal(h_el.numpy(), gh.np_(el))
+      np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))

@@ -329,3 +329,20 @@ def test_aggregate_results_golden():
   assert agg['average_num_actions_taken'] == 15.0
   assert agg['average_environment_seconds_to_goal'] == 110.0
   assert agg['average_total_reward'] == 0.7
+
+
+@pytest.mark.parametrize('si,action,want', [
+    # action_adapters_test.py:124-186 (FOV 10 A wide, max distance 1.42 A)
+    ((0.5, 0.75), (0.0, 0.2), (0.5, 0.7784)),
+    ((0.31, 0.31), (-0.1, 0.0), (0.2958, 0.31)),
+    ((0.92, 0.11), (-1.0, 0.75), (0.778, 0.2165)),
+])
+def test_relative_to_silicon_adapter_goldens(si, action, want):
+  from oracle import pdune_oracle_episode as oe
+  st = po.make_state(1, seed=2)
+  po.reset(st)
+  p = po.site_positions(st, st.si_idx, np.arange(1))[0]
+  ll = p - 10.0 * np.asarray(si)
+  st.fov[0] = np.concatenate((ll, ll + 10.0))
+  got = oe.relative_to_silicon_controls(st, np.asarray([action]))
+  np.testing.assert_allclose(got[0], want, atol=1e-9)
