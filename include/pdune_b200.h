@@ -119,6 +119,16 @@ typedef struct pd_mlp {
   const float* b1;         /* [H2]                                             */
   const float* w2;         /* [H2][4]   mlp/~/linear_2/w                       */
   const float* b2;         /* [4]                                              */
+  /* Hidden contraction on the 5th-gen tensor cores (tcgen05.mma kind::f16,
+   * BF16 operands, FP32 accumulate in TMEM) instead of FP32 FMA.  Rates then
+   * agree with the FP32 path to ~1e-2 relative (bf16 operand rounding); the
+   * default (0) is the FP32 parity path.  w1_umma: device copy of W1
+   * transposed to [H2][H1], bf16, in the canonical no-swizzle K-major UMMA
+   * layout (see pd_mlp_umma_layout_bytes / DESIGN.md).  Needs H1 % 16 == 0,
+   * H2 % 16 == 0, 32 <= H2 <= 256, and H1*(128 + H2)*2 B of shared memory. */
+  int32_t tensor_core;
+  int32_t reserved_;
+  const void* w1_umma;
 } pd_mlp;
 
 /* Rate-function selection passed to every stepping call. */

@@ -34,6 +34,8 @@ struct MlpView {
   int d, h1, h2, batchnorm;
   const float *bn_scale, *bn_offset, *bn_mean, *bn_var;
   const float *w0, *b0, *w1, *b1, *w2, *b2;
+  int tensor_core;
+  const void* w1_umma;
 };
 
 __device__ __forceinline__ float swishf(float z) {
@@ -45,11 +47,9 @@ __device__ __forceinline__ float softplusf(float z) {
   return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
 }
 
-struct MlpShared {
-  float xs[kMlpBatch][2];             // normalised network inputs
+struct MlpSmall {
+  float xs[kMlpBatch][2];             // network inputs (before BatchNorm)
   float out[kMlpBatch][4];            // softplus heads
-  float a[kChunk][kMlpBatch];         // layer-1 activations, k-major
-  float b[kChunk][256];               // W1 chunk
   float w0[2][256];
   float b0[256];
   float b1[256];
@@ -58,9 +58,14 @@ struct MlpShared {
   float bn_a[2], bn_b[2];             // x_hat = x * a + b
 };
 
+struct MlpShared : MlpSmall {         // FP32 FMA path
+  float a[kChunk][kMlpBatch];         // layer-1 activations, k-major
+  float b[kChunk][256];               // W1 chunk
+};
+
 // Loads the small layers once per CTA.
 __device__ __forceinline__ void mlp_stage_small(const MlpView& w,
-                                                MlpShared& sh) {
+                                                MlpSmall& sh) {
   for (int i = threadIdx.x; i < w.h1; i += blockDim.x) {
     sh.w0[0][i] = w.w0[i];
     sh.w0[1][i] = w.w0[w.h1 + i];
@@ -166,6 +171,235 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core wave (pd_mlp.tensor_core): the hidden contraction
+//   acc[128 envs][H2] = h1[128][H1] (bf16) x W1[H1][H2] (bf16), FP32 in TMEM
+// as H1/16 tcgen05.mma (cta_group::1, kind::f16, M = 128, N = H2, K = 16)
+// issued by one thread.  Operands sit in shared memory in the canonical
+// no-swizzle K-major layout (8-row x 16-byte core matrices, LBO = 128 B
+// between the core matrices of one K step, SBO = H1 * 16 B between 8-row
+// groups); W1 is copied there once per CTA, h1 is regenerated from the two
+// network inputs every wave.  The epilogue reads the accumulator with
+// tcgen05.ld (thread = TMEM lane = env), applies bias + swish, contracts with
+// W2 in registers and finishes with softplus.
+// ---------------------------------------------------------------------------
+struct TcShared {
+  unsigned long long mbar;
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float partial[2][kMlpBatch][4];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr,
+                                              uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);         // [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;   // [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                            // version
+  return d;  // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4)                                  // D format F32
+         | (1u << 7) | (1u << 10)                   // A, B = BF16
+         | (static_cast<uint32_t>(n >> 3) << 17)    // N
+         | (static_cast<uint32_t>(m >> 4) << 24);   // M; K-major A and B
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+struct TcCtx {
+  unsigned char* a_tile;   // shared, [128][H1] bf16 canonical
+  uint32_t a_addr, b_addr; // shared-window addresses
+  TcShared* ts;
+  uint32_t phase;
+};
+
+__device__ __forceinline__ void tc_setup(const MlpView& w, TcCtx& tc,
+                                         unsigned char* a_tile,
+                                         unsigned char* b_tile, TcShared* ts) {
+  tc.a_tile = a_tile;
+  tc.a_addr = smem_u32(a_tile);
+  tc.b_addr = smem_u32(b_tile);
+  tc.ts = ts;
+  tc.phase = 0;
+  // W1^T in UMMA layout: verbatim 16-byte copies
+  const int n16 = w.h1 * w.h2 * 2 / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(w.w1_umma);
+  uint4* dst = reinterpret_cast<uint4*>(b_tile);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                     smem_u32(&ts->mbar)),
+                 "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (threadIdx.x < 32) {
+    int cols = 32;
+    while (cols < w.h2) cols <<= 1;
+    asm volatile(
+        "tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::
+            "r"(smem_u32(&ts->tmem_base)),
+        "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+}
+
+__device__ __forceinline__ void tc_teardown(const MlpView& w, TcCtx& tc) {
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int cols = 32;
+    while (cols < w.h2) cols <<= 1;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(
+                     tc.ts->tmem_base),
+                 "r"(cols));
+  }
+}
+
+__device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
+                                            TcCtx& tc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kblocks = w.h1 >> 3;          // 16-byte blocks along K
+  const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
+  // ---- h1 = swish(x_hat W0 + b0) as bf16, canonical K-major ----
+  {
+    const int m8 = lane & 7, kb_lo = lane >> 3;
+    const int n_pairs = 16 * (kblocks >> 2);
+    for (int pair = warp; pair < n_pairs; pair += kMlpThreads / 32) {
+      const int g = pair & 15;
+      const int kb = (pair >> 4) * 4 + kb_lo;
+      const int m = g * 8 + m8;
+      const float x0 = sh.xs[m][0] * sh.bn_a[0] + sh.bn_b[0];
+      const float x1 = sh.xs[m][1] * sh.bn_a[1] + sh.bn_b[1];
+      float h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = kb * 8 + j;
+        float z = sh.b0[k];
+        z = fmaf(x0, sh.w0[0][k], z);
+        z = fmaf(x1, sh.w0[1][k], z);
+        h[j] = swishf(z);
+      }
+      uint4 v;
+      v.x = pack_bf16x2(h[0], h[1]);
+      v.y = pack_bf16x2(h[2], h[3]);
+      v.z = pack_bf16x2(h[4], h[5]);
+      v.w = pack_bf16x2(h[6], h[7]);
+      *reinterpret_cast<uint4*>(tc.a_tile + static_cast<size_t>(g) * sbo +
+                                kb * 128 + m8 * 16) = v;
+    }
+  }
+  // generic-proxy writes -> visible to the tensor core (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  const uint32_t tmem = tc.ts->tmem_base;
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t idesc = umma_idesc_bf16(kMlpBatch, w.h2);
+    for (int kk = 0; kk < (w.h1 >> 4); ++kk) {
+      const uint64_t da = umma_desc(tc.a_addr + kk * 256, 128u, sbo);
+      const uint64_t db = umma_desc(tc.b_addr + kk * 256, 128u, sbo);
+      const uint32_t accumulate = kk > 0 ? 1u : 0u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+          "}\n" ::"r"(tmem),
+          "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+    }
+    // arrives on the mbarrier when every MMA above has completed
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
+        "[%0];" ::"r"(smem_u32(&tc.ts->mbar)));
+  }
+  // ---- wait for the accumulator ----
+  {
+    const uint32_t bar = smem_u32(&tc.ts->mbar);
+    uint32_t done = 0;
+    // try_wait suspends for a hardware-defined interval; the spin bound turns
+    // a lost completion into a trap instead of a hung GPU.
+    for (int spin = 0; !done && spin < (1 << 24); ++spin) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred P1;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, P1;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(tc.phase)
+          : "memory");
+    }
+    if (!done) __trap();
+    tc.phase ^= 1u;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // ---- epilogue: thread = TMEM lane = env row; two column halves ----
+  {
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = quarter * 32 + lane;
+    const int c_lo = half * (w.h2 >> 1), c_hi = c_lo + (w.h2 >> 1);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr =
+          tmem + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+          "%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]),
+            "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+            "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        const float hh = swishf(__uint_as_float(r[j]) + sh.b1[col]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = fmaf(hh, sh.w2[col][q], o[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tc.ts->partial[half][m][q] = o[q];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (tid < kMlpBatch) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      sh.out[tid][q] = softplusf(tc.ts->partial[0][tid][q] +
+                                 tc.ts->partial[1][tid][q] + sh.b2[q]);
+  }
+  __syncthreads();
+}
+
+// Shared-memory carve-up of the tensor-core kernels (dynamic, 1 KB aligned).
+__host__ __device__ inline size_t tc_a_bytes(int h1) {
+  return static_cast<size_t>(kMlpBatch) * h1 * 2;
+}
+__host__ __device__ inline size_t tc_b_bytes(int h1, int h2) {
+  return static_cast<size_t>(h2) * h1 * 2;
+}
+
 // predict()'s frame canonicalisation for one env (float64 like the
 // reference): returns the network input and, for each neighbour slot, which
 // network head holds its rate.
@@ -222,8 +456,9 @@ __device__ __forceinline__ Canonical canonicalise(const double2 beam,
   return out;
 }
 
-struct MlpStepShared {
-  MlpShared m;
+template <bool TC>
+struct MlpStepSharedT {
+  typename std::conditional<TC, MlpSmall, MlpShared>::type m;
   int q_env[kMlpBatch], q_ctl[kMlpBatch], q_si[kMlpBatch];
   uint32_t q_it[kMlpBatch];
   long long q_elapsed[kMlpBatch], q_total[kMlpBatch];
@@ -232,14 +467,34 @@ struct MlpStepShared {
   int q_count;
 };
 
-template <int NPT>
+// Carves the tensor-core operands out of the dynamic shared memory that
+// follows `used` bytes of fixed structures.
+__device__ __forceinline__ void tc_carve(const MlpView& w,
+                                         unsigned char* smem_raw, size_t used,
+                                         TcCtx& tc) {
+  TcShared* ts = reinterpret_cast<TcShared*>(
+      (reinterpret_cast<uintptr_t>(smem_raw + used) + 15) & ~uintptr_t(15));
+  unsigned char* a_tile = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(ts + 1) + 127) & ~uintptr_t(127));
+  tc_setup(w, tc, a_tile, a_tile + tc_a_bytes(w.h1), ts);
+}
+
+static size_t tc_smem_bytes(size_t used, int h1, int h2) {
+  return used + sizeof(TcShared) + 16 + 128 + tc_a_bytes(h1) +
+         tc_b_bytes(h1, h2);
+}
+
+template <int NPT, bool TC>
 __global__ void __launch_bounds__(kMlpThreads, 1)
     k_step_learned(const StepArgs a, const MlpView w) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MlpStepShared& sh = *reinterpret_cast<MlpStepShared*>(smem_raw);
+  using Shared = MlpStepSharedT<TC>;
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   mlp_stage_small(w, sh.m);
+  TcCtx tc{};
+  if constexpr (TC) tc_carve(w, smem_raw, sizeof(Shared), tc);
   const double2* base = reinterpret_cast<const double2*>(a.lat.base_xy);
   const int4* nbr_tab = reinterpret_cast<const int4*>(a.lat.nbr);
   const LogSink log{a.out.log_count ? a.out.log_capacity : 0,
@@ -323,7 +578,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     }
     __syncthreads();
     // ---- network for the whole batch ----
-    mlp_wave<NPT>(w, sh.m);
+    if constexpr (TC) {
+      mlp_wave_tc(w, sh.m, tc);
+    } else {
+      mlp_wave<NPT>(w, sh.m);
+    }
     // ---- events ----
     bool survive = false;
     if (own) {
@@ -409,18 +668,22 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     if (tid == 0) sh.q_count = total_surv;
     __syncthreads();
   }
+  if constexpr (TC) tc_teardown(w, tc);
 }
 
 // RateFunction seam with the learned model: rates + successor sites.
-template <int NPT>
+template <int NPT, bool TC>
 __global__ void __launch_bounds__(kMlpThreads, 1)
     k_rates_learned(const pd_lattice lat, const pd_state st, const MlpView w,
                     const double* __restrict__ beam_xy,
                     float* __restrict__ rates_out,
                     int32_t* __restrict__ nbr_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MlpShared& sh = *reinterpret_cast<MlpShared*>(smem_raw);
+  using Shared = typename std::conditional<TC, MlpSmall, MlpShared>::type;
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   mlp_stage_small(w, sh);
+  TcCtx tc{};
+  if constexpr (TC) tc_carve(w, smem_raw, sizeof(Shared), tc);
   const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
   const int4* nbr_tab = reinterpret_cast<const int4*>(lat.nbr);
   for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * kMlpBatch;
@@ -448,7 +711,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
       sh.xs[threadIdx.x][1] = can.x1;
     }
     __syncthreads();
-    mlp_wave<NPT>(w, sh);
+    if constexpr (TC) {
+      mlp_wave_tc(w, sh, tc);
+    } else {
+      mlp_wave<NPT>(w, sh);
+    }
     if (own) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -457,6 +724,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
       }
     }
   }
+  if constexpr (TC) tc_teardown(w, tc);
 }
 
 // apply_model (learn_rates.py:704-732) for one model: softmax(o[:3]) * o[3].
@@ -507,9 +775,14 @@ static int mlp_view(const pd_mlp* mlp, MlpView* v) {
   PD_REQUIRE(!mlp->batchnorm || (mlp->bn_scale && mlp->bn_offset &&
                                  mlp->bn_mean && mlp->bn_var),
              "null BatchNorm statistics");
+  if (mlp->tensor_core) {
+    PD_REQUIRE(mlp->w1_umma != nullptr, "tensor_core needs w1_umma");
+    PD_REQUIRE(mlp->hidden2 % 32 == 0, "tensor_core needs hidden2 % 32 == 0");
+  }
   *v = MlpView{mlp->context_dim, mlp->hidden1, mlp->hidden2, mlp->batchnorm,
                mlp->bn_scale, mlp->bn_offset, mlp->bn_mean, mlp->bn_var,
-               mlp->w0, mlp->b0, mlp->w1, mlp->b1, mlp->w2, mlp->b2};
+               mlp->w0, mlp->b0, mlp->w1, mlp->b1, mlp->w2, mlp->b2,
+               mlp->tensor_core, mlp->w1_umma};
   return PD_OK;
 }
 
@@ -536,9 +809,19 @@ int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   if (rc != PD_OK) return rc;
   const int64_t tiles = (st->n_envs + kMlpBatch - 1) / kMlpBatch;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  const int smem = static_cast<int>(sizeof(MlpStepShared));
+  if (v.tensor_core) {
+    const int smem = static_cast<int>(
+        tc_smem_bytes(sizeof(MlpStepSharedT<true>), v.h1, v.h2));
+    auto kern = k_step_learned<2, true>;
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kMlpThreads, smem, stream>>>(a, v);
+    PD_CUDA_OK(cudaGetLastError());
+    return PD_OK;
+  }
+  const int smem = static_cast<int>(sizeof(MlpStepSharedT<false>));
   return dispatch_npt(v.h2, [&](auto npt) -> int {
-    auto kern = k_step_learned<decltype(npt)::value>;
+    auto kern = k_step_learned<decltype(npt)::value, false>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, kMlpThreads, smem, stream>>>(a, v);
@@ -555,9 +838,20 @@ int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   if (rc != PD_OK) return rc;
   const int64_t tiles = (st->n_envs + kMlpBatch - 1) / kMlpBatch;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  if (v.tensor_core) {
+    const int smem =
+        static_cast<int>(tc_smem_bytes(sizeof(MlpSmall), v.h1, v.h2));
+    auto kern = k_rates_learned<2, true>;
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kMlpThreads, smem, stream>>>(*lat, *st, v, beam_xy, rates_out,
+                                              nbr_out);
+    PD_CUDA_OK(cudaGetLastError());
+    return PD_OK;
+  }
   const int smem = static_cast<int>(sizeof(MlpShared));
   return dispatch_npt(v.h2, [&](auto npt) -> int {
-    auto kern = k_rates_learned<decltype(npt)::value>;
+    auto kern = k_rates_learned<decltype(npt)::value, false>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, kMlpThreads, smem, stream>>>(*lat, *st, v, beam_xy, rates_out,

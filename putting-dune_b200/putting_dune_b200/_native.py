@@ -44,7 +44,8 @@ class PdMlp(C.Structure):
               ('hidden2', C.c_int32), ('batchnorm', C.c_int32),
               ('bn_scale', _p), ('bn_offset', _p), ('bn_mean', _p),
               ('bn_var', _p), ('w0', _p), ('b0', _p), ('w1', _p), ('b1', _p),
-              ('w2', _p), ('b2', _p)]
+              ('w2', _p), ('b2', _p), ('tensor_core', C.c_int32),
+              ('reserved_', C.c_int32), ('w1_umma', _p)]
 
 
 class PdRateConfig(C.Structure):

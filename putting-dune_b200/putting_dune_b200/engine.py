@@ -112,13 +112,36 @@ class MlpWeights:
         batchnorm=batchnorm)
 
 
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+  """float32 -> bfloat16 bit patterns (uint16), round to nearest even."""
+  u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+  rounded = u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))
+  return (rounded >> np.uint32(16)).astype(np.uint16)
+
+
+def umma_k_major_bf16(mat: np.ndarray) -> np.ndarray:
+  """[rows, K] float32 -> bf16 in the canonical no-swizzle K-major UMMA layout
+  (tcgen05 shared-memory descriptor, layout type INTERLEAVE): 8-row x 16-byte
+  core matrices; consecutive core matrices along K are 128 B apart (LBO) and
+  each group of 8 rows owns K/8 of them (SBO = K/8 * 128 B).  Returned as the
+  flat uint16 array to copy into shared memory verbatim."""
+  rows, k = mat.shape
+  if rows % 8 or k % 8:
+    raise ValueError('rows and K must be multiples of 8')
+  bits = to_bf16_bits(mat).reshape(rows // 8, 8, k // 8, 8)
+  # (row group, row in group, k block, k in block) ->
+  # (row group, k block, row in group, k in block)
+  return np.ascontiguousarray(bits.transpose(0, 2, 1, 3)).reshape(-1)
+
+
 class RateSpec:
   """Selects the rate function for a stepping call (the reference's
   ``RateFunction`` seam, graphene.py:52-78) and owns device copies of the
   learned model's weights."""
 
   def __init__(self, kind: int, *, mlp: Optional[MlpWeights] = None,
-               constant: Optional[Sequence[float]] = None, device=None):
+               constant: Optional[Sequence[float]] = None, device=None,
+               tensor_core: bool = False):
     self.kind = int(kind)
     self.c = nat.PdRateConfig()
     self.c.rate_fn = self.kind
@@ -141,9 +164,16 @@ class RateSpec:
         self._tensors[name] = torch.as_tensor(
             np.ascontiguousarray(getattr(mlp, name), dtype=np.float32),
             device=device)
+      umma_ptr = None
+      if tensor_core:
+        self._tensors['w1_umma'] = torch.as_tensor(
+            umma_k_major_bf16(np.asarray(mlp.w1, dtype=np.float32).T),
+            device=device)
+        umma_ptr = self._tensors['w1_umma'].data_ptr()
       self._mlp_c = nat.PdMlp(d, h1, h2, int(mlp.batchnorm),
                               *[self._tensors[n].data_ptr()
-                                for n in MlpWeights.NAMES])
+                                for n in MlpWeights.NAMES],
+                              int(bool(tensor_core)), 0, umma_ptr)
       self.c.mlp = C.pointer(self._mlp_c)
       self.mlp = mlp
 

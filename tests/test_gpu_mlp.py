@@ -169,3 +169,56 @@ def test_unsupported_shapes_fail_loudly():
   bad = po.MlpParams.synthetic(1, hidden=(64, 40))
   with pytest.raises(nat.NativeError, match='hidden2'):
     b.rates(np.zeros((8, 2)), gh.rate_spec(po.RATE_LEARNED, bad))
+
+
+@pytest.mark.parametrize('hidden', [(256, 256), (128, 128), (64, 64),
+                                    (128, 256), (32, 32)])
+def test_tensor_core_rates_close_to_fp32(hidden):
+  """pd_mlp.tensor_core: tcgen05 BF16 contraction with FP32 accumulation.
+  BF16 rounds the layer-1 activations and W1 to 8 bits of mantissa, so rates
+  agree with the FP32 path to ~1e-2 of the largest rate (not a parity path)."""
+  from putting_dune_b200 import engine
+  n, seed = 3000, 6
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(4, hidden=hidden)
+  rng = np.random.default_rng(1)
+  mlp.b1 = rng.normal(0, 0.2, hidden[1]).astype(np.float32)
+  mlp.b2 = rng.normal(0, 0.3, 4).astype(np.float32)
+  beam = po.site_positions(st, st.si_idx, np.arange(n)) + rng.uniform(
+      -2.0, 2.0, size=(n, 2))
+  b = gh.batch_from_oracle(st)
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  fp32 = engine.RateSpec(po.RATE_LEARNED, mlp=w)
+  tc = engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=True)
+  r32, nb32 = b.rates(beam, fp32)
+  rtc, nbtc = b.rates(beam, tc)
+  np.testing.assert_array_equal(gh.np_(nb32), gh.np_(nbtc))
+  r32, rtc = gh.np_(r32), gh.np_(rtc)
+  err = np.abs(rtc - r32).max() / np.abs(r32).max()
+  assert err <= 2e-2, err
+  assert err > 0  # it really is a different arithmetic path
+  # repeated calls (mbarrier phase, TMEM re-use) give identical results
+  rtc2, _ = b.rates(beam, tc)
+  np.testing.assert_array_equal(gh.np_(rtc2), rtc)
+
+
+def test_tensor_core_step_statistics():
+  from putting_dune_b200 import engine
+  n, seed = 20000, 8
+  mlp = po.MlpParams.synthetic(9, hidden=(128, 128))
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  rng = np.random.default_rng(2)
+  ctl = 0.5 + rng.uniform(-0.05, 0.05, size=(n, 1, 2))
+  tr = []
+  for tensor_core in (False, True):
+    b = engine.EnvBatch(n, seed=seed)
+    b.reset()
+    spec = engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=tensor_core)
+    for _ in range(4):
+      out = b.step_and_image(ctl, 1500000, spec)
+    assert (gh.np_(out.elapsed_us) >= 3500000).all()
+    tr.append(float(gh.np_(b.n_transitions).mean()))
+  assert tr[0] > 0.5 and abs(tr[1] - tr[0]) <= 0.03 * tr[0], tr
