@@ -286,10 +286,11 @@ def measure_mlp(pd, batch, dev, args):
   out = {}
   n = 65536
   rng = np.random.default_rng(0)
-  for hidden in ((128, 128), (256, 256)):
+  for hidden, tensor_core in (((128, 128), False), ((256, 256), False),
+                              ((128, 128), True), ((256, 256), True)):
     mlp = po.MlpParams.synthetic(7, hidden=hidden)
     w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
-    rate = pd.RateSpec(2, mlp=w, device=dev)
+    rate = pd.RateSpec(2, mlp=w, device=dev, tensor_core=tensor_core)
     b = pd.EnvBatch(n, seed=11, device=dev, lattice=batch.lattice_tables)
     b.reset()
     ctl = torch.as_tensor(direct_controls(n, 1, 3)[0][:, None, :]).to(dev)
@@ -307,11 +308,13 @@ def measure_mlp(pd, batch, dev, args):
     ms = sum(a.elapsed_time(c) for a, c in evs) / len(evs)
     evals = (int(b.n_events.sum().item()) - ev0) / len(evs)
     flop = 2 * (2 * hidden[0] + hidden[0] * hidden[1] + 4 * hidden[1])
-    out[f'H{hidden[0]}'] = {
+    out[f'H{hidden[0]}' + ('_tcgen05_bf16' if tensor_core else '_fp32')] = {
         'envs': n, 'launch_ms': ms, 'env_steps_per_s': n / (ms / 1e3),
         'rate_evals_per_step': evals / n, 'flop_per_eval': flop,
-        'tflops_fp32': evals * flop / (ms / 1e3) / 1e12,
-        'kernel': 'pd::k_step_learned (FP32 FMA, queue-batched GEMM)'}
+        'tflops': evals * flop / (ms / 1e3) / 1e12,
+        'kernel': ('pd::k_step_learned<TC> (tcgen05.mma kind::f16, BF16 '
+                   'operands, FP32 accumulate in TMEM)' if tensor_core else
+                   'pd::k_step_learned (FP32 FMA, queue-batched GEMM)')}
   return out
 
 

@@ -13,10 +13,11 @@ import putting_dune_b200 as pd
 from oracle import pdune_oracle as po
 
 h = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+tc = len(sys.argv) > 2 and sys.argv[2] == 'tc'
 n = 65536
 mlp = po.MlpParams.synthetic(7, hidden=(h, h))
 w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
-rate = pd.RateSpec(2, mlp=w)
+rate = pd.RateSpec(2, mlp=w, tensor_core=tc)
 b = pd.EnvBatch(n, seed=11)
 b.reset()
 rng = np.random.default_rng(0)

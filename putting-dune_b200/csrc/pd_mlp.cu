@@ -42,6 +42,12 @@ __device__ __forceinline__ float swishf(float z) {
   return z / (1.0f + expf(-z));
 }
 
+// Tensor-core path only: operands are rounded to bf16 anyway, so the
+// activations use the SFU approximations (ex2 / rcp, ~2^-21 relative).
+__device__ __forceinline__ float swish_fast(float z) {
+  return z * __frcp_rn(1.0f + __expf(-z));
+}
+
 __device__ __forceinline__ float softplusf(float z) {
   // np.logaddexp(z, 0)
   return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
@@ -293,7 +299,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
         float z = sh.b0[k];
         z = fmaf(x0, sh.w0[0][k], z);
         z = fmaf(x1, sh.w0[1][k], z);
-        h[j] = swishf(z);
+        h[j] = swish_fast(z);
       }
       uint4 v;
       v.x = pack_bf16x2(h[0], h[1]);
@@ -373,7 +379,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = c0 + j;
-        const float hh = swishf(__uint_as_float(r[j]) + sh.b1[col]);
+        const float hh = swish_fast(__uint_as_float(r[j]) + sh.b1[col]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) o[q] = fmaf(hh, sh.w2[col][q], o[q]);
       }
