@@ -57,9 +57,25 @@ typedef enum pd_rate_fn {
   PD_RATE_SIMPLE = 0,   /* graphene.py:133-166 simple_canonical_rate_function */
   PD_RATE_PRIOR = 1,    /* graphene.py:169-229 HumanPriorRatePredictor.predict */
   PD_RATE_LEARNED = 2,  /* rate_learning/learn_rates.py:925-972 predict        */
-  PD_RATE_CONSTANT = 3  /* fixed rates: the seam the reference's own tests     */
+  PD_RATE_CONSTANT = 3, /* fixed rates: the seam the reference's own tests     */
                         /* mock (simulator_test.py:139-168, graphene_test.py)  */
+  PD_RATE_GMM = 4       /* graphene.py:279-390 GaussianMixtureRateFunction     */
 } pd_rate_fn;
+
+/* graphene.py:279-390: per neighbour, a mixture of Gaussians placed along the
+ * Si->neighbour vector (mean = si + delta * loc_distance[m]) with variances
+ * (along, across) that vector, scaled so that the largest mixture mode equals
+ * max_rate.  Rates stay float64 in the reference (no float32 cast before the
+ * total, graphene.py:375-388). */
+#define PD_GMM_MAX_MIXTURES 16
+typedef struct pd_gmm {
+  int32_t n_mixtures;
+  int32_t reserved_;
+  double max_rate;
+  double mixture_weights[PD_GMM_MAX_MIXTURES];
+  double loc_distances[PD_GMM_MAX_MIXTURES];
+  double variances[PD_GMM_MAX_MIXTURES][2];
+} pd_gmm;
 
 /* Philox stream ids (counter word 3). */
 #define PD_STREAM_KMC 0u
@@ -138,6 +154,7 @@ typedef struct pd_rate_config {
   const pd_mlp* mlp;       /* HOST pointer to the struct; PD_RATE_LEARNED only */
   float constant_rates[3]; /* PD_RATE_CONSTANT only                            */
   float reserved2_;
+  const pd_gmm* gmm;       /* HOST pointer; PD_RATE_GMM only                   */
 } pd_rate_config;
 
 /* Optional per-call outputs of the stepping calls (any pointer may be NULL).

@@ -62,6 +62,7 @@ RATE_SIMPLE = 0
 RATE_PRIOR = 1
 RATE_LEARNED = 2
 RATE_CONSTANT = 3  # fixed rates: the seam the reference's tests mock
+RATE_GMM = 4  # graphene.py:279-390 GaussianMixtureRateFunction
 
 MAX_TRANSITION_SECONDS = 3600.0  # graphene.py:668
 
@@ -472,8 +473,36 @@ def apply_model(params_list: Sequence[MlpParams], x: np.ndarray) -> np.ndarray:
   return (acc / np.float32(len(params_list))).astype(np.float32)
 
 
+def gmm_rates(beam: np.ndarray, p_si: np.ndarray, p_nbr: np.ndarray,
+              gmm: dict) -> np.ndarray:
+  """graphene.py:303-388 `GaussianMixtureRateFunction.__call__`, float64 [E, 3].
+
+  The covariance `E diag(v) E^-1` (:352-361) has the unit Si->neighbour
+  vector and its normal as eigenvectors, so the density is
+  exp(-0.5 (d1^2/v1 + d2^2/v2)) / (2 pi sqrt(v1 v2)); the normalising factor
+  (:289-301) makes the largest mixture mode equal `max_rate`."""
+  w = np.asarray(gmm['mixture_weights'], dtype=np.float64)
+  loc = np.asarray(gmm['loc_distances'], dtype=np.float64)
+  var = np.asarray(gmm['variances'], dtype=np.float64).reshape(-1, 2)
+  mode = w / (2 * np.pi * np.sqrt(var[:, 0] * var[:, 1]))
+  norm = gmm['max_rate'] / mode.max()
+  delta = p_nbr - p_si[:, None, :]
+  e1 = delta / np.sqrt((delta ** 2).sum(axis=-1, keepdims=True))
+  rates = np.zeros(delta.shape[:2])
+  for m in range(w.size):
+    mean = p_si[:, None, :] + delta * loc[m]
+    d = beam[:, None, :] - mean
+    d1 = d[..., 0] * e1[..., 0] + d[..., 1] * e1[..., 1]
+    d2 = d[..., 1] * e1[..., 0] - d[..., 0] * e1[..., 1]
+    pdf = np.exp(-0.5 * (d1 * d1 / var[m, 0] + d2 * d2 / var[m, 1])) / (
+        2 * np.pi * np.sqrt(var[m, 0] * var[m, 1]))
+    rates += pdf * norm * w[m]
+  return rates
+
+
 def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
-              rate_fn: int, mlp: Optional[MlpParams] = None, constant=None):
+              rate_fn: int, mlp: Optional[MlpParams] = None, constant=None,
+              gmm: Optional[dict] = None, keep64: bool = False):
   """graphene.py:238-259: Si + 3-NN geometry -> canonical fn -> float32[3]."""
   si = state.si_idx[envs]
   nbr = state.nbr[si]
@@ -487,8 +516,12 @@ def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
     r64 = learned_rates(mlp, beam, p_si, p_nbr)
   elif rate_fn == RATE_CONSTANT:
     r64 = np.tile(np.asarray(constant, dtype=np.float64), (len(envs), 1))
+  elif rate_fn == RATE_GMM:
+    r64 = gmm_rates(beam, p_si, p_nbr, gmm)
   else:
     raise ValueError(rate_fn)
+  if keep64:
+    return r64, nbr
   r32 = r64.astype(np.float32)
   assert (r32 >= 0).all(), 'transition_rates were not positive.'
   return r32, nbr
@@ -518,7 +551,7 @@ class EventLog:
 def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
                   rate_fn: int = RATE_SIMPLE, mlp: Optional[MlpParams] = None,
                   log: Optional[EventLog] = None,
-                  rates_override=None) -> dict:
+                  rates_override=None, gmm: Optional[dict] = None) -> dict:
   """graphene.py:646-694 for all envs at once.
 
   beam: float64 [E, 2] material frame; dwell_us: int64 [E].
@@ -536,14 +569,23 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
     idx = np.nonzero(active)[0]
     if rates_override is not None:
       r32, nbr = rates_override(state, idx, beam[idx], it)
+    elif rate_fn == RATE_GMM:
+      # GaussianMixtureRateFunction returns float64 rates (graphene.py:375):
+      # the total and the exponential scale stay float64 (Python floats);
+      # only the branch probabilities go through float32 (:679-683).
+      r64, nbr = rates_for(state, idx, beam[idx], rate_fn, gmm=gmm,
+                           keep64=True)
+      r32 = r64.astype(np.float32)
     else:
       r32, nbr = rates_for(state, idx, beam[idx], rate_fn, mlp)
     if it == 0:
       first_rates[idx] = r32
     # Rates.total_rate: Python sum of np.float32 -> sequential float32 adds.
     tot = (r32[:, 0] + r32[:, 1]) + r32[:, 2]
+    if rate_fn == RATE_GMM and rates_override is None:
+      tot = (r64[:, 0] + r64[:, 1]) + r64[:, 2]
     with np.errstate(divide='ignore', over='ignore', invalid='ignore'):
-      scale = np.float32(1.0) / tot  # float32 under NumPy 2 (NEP 50)
+      scale = tot.dtype.type(1.0) / tot  # float32 under NumPy 2 (NEP 50)
       u1, u2 = draw_pair(state.seed, state.env_ids[idx], state.ctrl_count[idx],
                          it, STREAM_KMC)
       t = -np.log1p(-u1) * scale.astype(np.float64)
@@ -555,7 +597,7 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
     if hit.any():
       h = np.nonzero(hit)[0]
       with np.errstate(divide='ignore', invalid='ignore'):
-        p32 = r32[h] / tot[h, None]  # float32
+        p32 = r32[h] / tot[h, None].astype(np.float32)  # float32
       cdf = np.cumsum(p32.astype(np.float64), axis=1)
       cdf = cdf / cdf[:, -1:]
       slot = (cdf <= u2[h, None]).sum(axis=1)  # searchsorted side='right'
@@ -610,7 +652,8 @@ def step_and_image(state: OracleState, controls: np.ndarray,
                    dwell_us: np.ndarray, image_duration_us: int = 2000000,
                    rate_fn: int = RATE_SIMPLE,
                    mlp: Optional[MlpParams] = None,
-                   log: Optional[EventLog] = None) -> dict:
+                   log: Optional[EventLog] = None,
+                   gmm: Optional[dict] = None) -> dict:
   """simulator.py:107-182 for all envs (without rendering).
 
   controls: float64 [E, C, 2] microscope frame; dwell_us: int64 [E, C].
@@ -627,7 +670,8 @@ def step_and_image(state: OracleState, controls: np.ndarray,
   tr = np.zeros(e, dtype=np.int64)
   for c in range(controls.shape[1]):
     beam = microscope_to_material(state.fov, controls[:, c])  # :137
-    out = apply_control(state, beam, dwell_us[:, c], rate_fn, mlp, log)  # :147
+    out = apply_control(state, beam, dwell_us[:, c], rate_fn, mlp, log,
+                        gmm=gmm)  # :147
     ev += out['events']
     tr += out['transitions']
     elapsed += dwell_us[:, c]  # :149

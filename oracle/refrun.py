@@ -105,8 +105,14 @@ def uninstall_canonical_neighbors(mods):
     mods.geometry.nearest_neighbors3 = orig
 
 
-def make_rate_function(mods, rate_fn: int, mlp=None):
+def make_rate_function(mods, rate_fn: int, mlp=None, gmm=None):
   g = mods.graphene
+  if rate_fn == po.RATE_GMM:
+    return g.GaussianMixtureRateFunction(
+        max_rate=gmm['max_rate'],
+        mixture_weights=np.asarray(gmm['mixture_weights']),
+        loc_distances=np.asarray(gmm['loc_distances']),
+        variances=np.asarray(gmm['variances']))
   if rate_fn == po.RATE_SIMPLE:
     fn = g.simple_canonical_rate_function
   elif rate_fn == po.RATE_PRIOR:
@@ -122,7 +128,7 @@ def make_rate_function(mods, rate_fn: int, mlp=None):
 def run_reference_env(seed: int, env_id: int, controls: np.ndarray,
                       dwell_us: np.ndarray, rate_fn: int = po.RATE_SIMPLE,
                       mlp=None, image_duration_us: int = 2000000,
-                      num_cols: int = 50, table=None) -> dict:
+                      num_cols: int = 50, table=None, gmm=None) -> dict:
   """One env through ``PuttingDuneSimulator.reset`` + T ``step_and_image``.
 
   controls: [T, C, 2] microscope frame; dwell_us: [T, C].
@@ -149,7 +155,7 @@ def run_reference_env(seed: int, env_id: int, controls: np.ndarray,
           int(np.argmax(grid.atomic_numbers == 14))))
 
   material = mods.graphene.PristineSingleDopedGraphene(
-      rate_function=make_rate_function(mods, rate_fn, mlp),
+      rate_function=make_rate_function(mods, rate_fn, mlp, gmm),
       grid_columns=num_cols)
   sim = mods.simulator.PuttingDuneSimulator(
       material, image_duration=dt.timedelta(microseconds=image_duration_us),

@@ -67,6 +67,17 @@ __device__ __forceinline__ SharedTables stage_tables(const pd_lattice& lat,
   return SharedTables{sbase, snbr};
 }
 
+// Rate-function parameters that travel by value to the kernels.
+struct RateArgs {
+  float constant_rates[3];
+  // PD_RATE_GMM, precomputed on the host: coef = normalising factor * weight
+  // / (2 pi sqrt(v1 v2)); nh_inv_v = -0.5 / variance
+  int32_t gmm_n;
+  double gmm_coef[PD_GMM_MAX_MIXTURES];
+  double gmm_loc[PD_GMM_MAX_MIXTURES];
+  double gmm_nh_inv_v[PD_GMM_MAX_MIXTURES][2];
+};
+
 // ---------------------------------------------------------------------------
 // Rate functions -> float32[3]
 //
@@ -161,6 +172,34 @@ __device__ __forceinline__ void rates_prior(const double2 beam,
 #endif
 }
 
+// graphene.py:303-388 GaussianMixtureRateFunction.__call__ (float64 rates).
+// The covariance E diag(v) E^-1 has the unit Si->neighbour vector and its
+// normal as eigenvectors, so pdf = exp(-0.5 (d1^2/v1 + d2^2/v2)) /
+// (2 pi sqrt(v1 v2)) with d1, d2 the beam offset from the mean along them.
+__device__ __forceinline__ void rates_gmm(const RateArgs& ra,
+                                          const double2 beam,
+                                          const double2 psi,
+                                          const double2 pn[3], double r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = pn[i].x - psi.x, ny = pn[i].y - psi.y;
+    const double inv_len = rsqrt(fma(nx, nx, ny * ny));
+    const double e1x = nx * inv_len, e1y = ny * inv_len;
+    double acc = 0.0;
+    for (int m = 0; m < ra.gmm_n; ++m) {
+      const double dx = beam.x - fma(nx, ra.gmm_loc[m], psi.x);
+      const double dy = beam.y - fma(ny, ra.gmm_loc[m], psi.y);
+      const double d1 = fma(dx, e1x, dy * e1y);
+      const double d2 = fma(dy, e1x, -dx * e1y);
+      acc = fma(ra.gmm_coef[m],
+                exp(fma(d1 * d1, ra.gmm_nh_inv_v[m][0],
+                        d2 * d2 * ra.gmm_nh_inv_v[m][1])),
+                acc);
+    }
+    r[i] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // One event of the direct-method loop (graphene.py:658-694).
 // Returns true if a transition was accepted; *slot is the successor index.
@@ -217,6 +256,34 @@ __device__ __forceinline__ bool kmc_event_drawn(const float r[3], double draw,
   return true;
 }
 
+// Variant for rate functions that return float64 rates
+// (GaussianMixtureRateFunction): the total and the waiting-time scale stay
+// float64 (Python floats, graphene.py:47-49,666); the branch probabilities
+// are float32(rate) / float32(total) (graphene.py:679-683 under NumPy 2).
+__device__ __forceinline__ bool kmc_event_drawn64(const double r64[3],
+                                                  double draw, double u_choice,
+                                                  long long dwell_us,
+                                                  long long* elapsed_us,
+                                                  int* slot) {
+  const double tot = __dadd_rn(__dadd_rn(r64[0], r64[1]), r64[2]);
+  double t = kMaxTransitionSeconds;
+  if (tot > 0.0) {
+    t = __dmul_rn(draw, __ddiv_rn(1.0, tot));
+    t = fmin(t, kMaxTransitionSeconds);
+  }
+  *elapsed_us += seconds_to_us(t);
+  if (*elapsed_us > dwell_us) return false;
+  const float tot32 = __double2float_rn(tot);
+  const double c0 =
+      static_cast<double>(__fdiv_rn(__double2float_rn(r64[0]), tot32));
+  const double c1 = __dadd_rn(
+      c0, static_cast<double>(__fdiv_rn(__double2float_rn(r64[1]), tot32)));
+  const double c2 = __dadd_rn(
+      c1, static_cast<double>(__fdiv_rn(__double2float_rn(r64[2]), tot32)));
+  *slot = (__ddiv_rn(c0, c2) <= u_choice) + (__ddiv_rn(c1, c2) <= u_choice);
+  return true;
+}
+
 // Frame transforms: microscope_utils.py:362-369 / :421-428.
 __device__ __forceinline__ double2 microscope_to_material(const Fov4& f,
                                                           double px,
@@ -255,9 +322,6 @@ __device__ __forceinline__ Fov4 centred_fov(const double2 p, double scale) {
 #endif
 constexpr int kStepThreads = PD_STEP_THREADS;
 
-struct RateArgs {
-  float constant_rates[3];
-};
 
 // Per-env registers carried through a call.
 struct EnvRegs {

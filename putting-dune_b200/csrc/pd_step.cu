@@ -27,10 +27,39 @@ __device__ __forceinline__ void eval_rates(const RateArgs& ra,
     rates_simple(beam, psi, pn, r);
   } else if (RATE == PD_RATE_PRIOR) {
     rates_prior(beam, psi, pn, r);
+  } else if (RATE == PD_RATE_GMM) {
+    double r64[3];
+    rates_gmm(ra, beam, psi, pn, r64);
+    r[0] = __double2float_rn(r64[0]);
+    r[1] = __double2float_rn(r64[1]);
+    r[2] = __double2float_rn(r64[2]);
   } else {
     r[0] = ra.constant_rates[0];
     r[1] = ra.constant_rates[1];
     r[2] = ra.constant_rates[2];
+  }
+}
+
+// Rates + one event of the direct method.  Float64-rate functions (GMM) keep
+// the total in float64 (see kmc_event_drawn64).
+template <int RATE>
+__device__ __forceinline__ bool rate_event(const RateArgs& ra,
+                                           const double2 beam,
+                                           const double2 psi,
+                                           const double2 pn[3], double u_exp,
+                                           double u_choice, long long dwell_us,
+                                           long long* elapsed_us, int* slot,
+                                           bool* bad) {
+  if constexpr (RATE == PD_RATE_GMM) {
+    double r64[3];
+    rates_gmm(ra, beam, psi, pn, r64);
+    *bad = false;
+    return kmc_event_drawn64(r64, -log1p(-u_exp), u_choice, dwell_us,
+                             elapsed_us, slot);
+  } else {
+    float r[3];
+    eval_rates<RATE>(ra, beam, psi, pn, r);
+    return kmc_event(r, u_exp, u_choice, dwell_us, elapsed_us, slot, bad);
   }
 }
 
@@ -51,14 +80,13 @@ __device__ __forceinline__ void run_control(const Tables& tab,
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       pn[i] = site_position(tab.position(nb[i]), e->lat);
-    float r[3];
-    eval_rates<RATE>(ra, beam, e->psi, pn, r);
     const uint4 w =
         philox4x32_10(e->env_id, e->ctrl_count, it, PD_STREAM_KMC, seed);
     int slot = 0;
     bool bad = false;
-    const bool hit = kmc_event(r, u53(w.x, w.y), u53(w.z, w.w), dwell_us,
-                               &elapsed, &slot, &bad);
+    const bool hit =
+        rate_event<RATE>(ra, beam, e->psi, pn, u53(w.x, w.y), u53(w.z, w.w),
+                         dwell_us, &elapsed, &slot, &bad);
     if (bad) e->status |= PD_ENV_BAD_RATE;
     e->events += 1;
     if (hit) {
@@ -462,14 +490,13 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         pn[i] = site_position(tab.position(nb[i]), r.lat);
-      float rt[3];
-      eval_rates<RATE>(a.ra, beam, r.psi, pn, rt);
       const uint4 w = philox4x32_10(r.env_id, r.ctrl_count, it, PD_STREAM_KMC,
                                     a.st.seed);
       int slot = 0;
       bool bad = false;
-      const bool hit = kmc_event(rt, u53(w.x, w.y), u53(w.z, w.w), dwell,
-                                 &elapsed, &slot, &bad);
+      const bool hit =
+          rate_event<RATE>(a.ra, beam, r.psi, pn, u53(w.x, w.y), u53(w.z, w.w),
+                           dwell, &elapsed, &slot, &bad);
       if (bad) r.status |= PD_ENV_BAD_RATE;
       r.events += 1;
       ++it;
@@ -583,9 +610,46 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
   return PD_OK;
 }
 
+// Copies the rate-function parameters that travel by value to the kernels.
+int fill_rate_args(const pd_rate_config* rc, RateArgs* ra) {
+  for (int i = 0; i < 3; ++i) ra->constant_rates[i] = rc->constant_rates[i];
+  ra->gmm_n = 0;
+  if (rc->rate_fn != PD_RATE_GMM) return PD_OK;
+  const pd_gmm* g = rc->gmm;
+  PD_REQUIRE(g != nullptr, "PD_RATE_GMM needs rc->gmm");
+  PD_REQUIRE(g->n_mixtures >= 1 && g->n_mixtures <= PD_GMM_MAX_MIXTURES,
+             "n_mixtures out of range");
+  const double kTwoPi = 6.283185307179586;
+  // graphene.py:289-301 _normalizing_factor
+  double max_mode = 0.0;
+  for (int m = 0; m < g->n_mixtures; ++m) {
+    PD_REQUIRE(g->variances[m][0] > 0 && g->variances[m][1] > 0,
+               "variances must be positive");
+    const double mode = g->mixture_weights[m] /
+                        (kTwoPi * sqrt(g->variances[m][0] * g->variances[m][1]));
+    if (mode > max_mode) max_mode = mode;
+  }
+  PD_REQUIRE(max_mode > 0, "mixture weights must be positive");
+  const double norm = g->max_rate / max_mode;
+  ra->gmm_n = g->n_mixtures;
+  for (int m = 0; m < g->n_mixtures; ++m) {
+    ra->gmm_coef[m] =
+        norm * g->mixture_weights[m] /
+        (kTwoPi * sqrt(g->variances[m][0] * g->variances[m][1]));
+    ra->gmm_loc[m] = g->loc_distances[m];
+    ra->gmm_nh_inv_v[m][0] = -0.5 / g->variances[m][0];
+    ra->gmm_nh_inv_v[m][1] = -0.5 / g->variances[m][1];
+  }
+  return PD_OK;
+}
+
 static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
                          cudaStream_t stream) {
+  int frc = fill_rate_args(rc, &a.ra);
+  if (frc != PD_OK) return frc;
   switch (rc->rate_fn) {
+    case PD_RATE_GMM:
+      return launch_step<PD_RATE_GMM>(a, rollout, stream);
     case PD_RATE_SIMPLE:
       return launch_step<PD_RATE_SIMPLE>(a, rollout, stream);
     case PD_RATE_PRIOR:
@@ -633,8 +697,11 @@ int launch_episodes(const pd_lattice* lat, const pd_state* st,
   a.stats = stats;
   a.dwell_us_scalar = cfg->dwell_us;
   a.image_duration_us = cfg->image_duration_us;
-  for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
+  int frc = fill_rate_args(rc, &a.ra);
+  if (frc != PD_OK) return frc;
   switch (rc->rate_fn) {
+    case PD_RATE_GMM:
+      return launch_episode_walk<PD_RATE_GMM>(a, stream);
     case PD_RATE_SIMPLE:
       return launch_episode_walk<PD_RATE_SIMPLE>(a, stream);
     case PD_RATE_PRIOR:
@@ -657,7 +724,7 @@ int validate_common(const pd_lattice* lat, const pd_state* st,
                  st->n_transitions && st->status),
              "state has null arrays");
   if (rc) {
-    PD_REQUIRE(rc->rate_fn >= PD_RATE_SIMPLE && rc->rate_fn <= PD_RATE_CONSTANT,
+    PD_REQUIRE(rc->rate_fn >= PD_RATE_SIMPLE && rc->rate_fn <= PD_RATE_GMM,
                "unknown rate_fn");
     if (rc->rate_fn == PD_RATE_LEARNED)
       PD_REQUIRE(rc->mlp != nullptr, "PD_RATE_LEARNED needs rc->mlp");
@@ -690,9 +757,14 @@ extern "C" int pd_rates(const pd_lattice* lat, const pd_state* st,
   a.lat = *lat;
   a.st = *st;
   a.controls_xy = beam_xy;
-  for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
+  rcode = pd::fill_rate_args(rc, &a.ra);
+  if (rcode != PD_OK) return rcode;
   const int grid = pd::grid_for(st->n_envs, false);
   switch (rc->rate_fn) {
+    case PD_RATE_GMM:
+      pd::k_rates<PD_RATE_GMM><<<grid, pd::kStepThreads, 0, s>>>(
+          a, rates_out, nbr_out);
+      break;
     case PD_RATE_SIMPLE:
       pd::k_rates<PD_RATE_SIMPLE><<<grid, pd::kStepThreads, 0, s>>>(
           a, rates_out, nbr_out);

@@ -15,7 +15,7 @@ LIB_PATH = pathlib.Path(
     os.environ.get('PDUNE_B200_LIB', _HERE.parent / 'lib' / 'libpdune_b200.so'))
 
 PD_OK = 0
-RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT = 0, 1, 2, 3
+RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT, RATE_GMM = 0, 1, 2, 3, 4
 ENV_BAD_RATE, ENV_LOG_OVERFLOW, ENV_NOT_RESET = 1, 2, 4
 STREAM_KMC, STREAM_RESET = 0, 1
 ACTION_DIRECT, ACTION_RELATIVE_TO_SILICON = 0, 1
@@ -48,10 +48,21 @@ class PdMlp(C.Structure):
               ('reserved_', C.c_int32), ('w1_umma', _p)]
 
 
+GMM_MAX_MIXTURES = 16
+
+
+class PdGmm(C.Structure):
+  _fields_ = [('n_mixtures', C.c_int32), ('reserved_', C.c_int32),
+              ('max_rate', C.c_double),
+              ('mixture_weights', C.c_double * GMM_MAX_MIXTURES),
+              ('loc_distances', C.c_double * GMM_MAX_MIXTURES),
+              ('variances', (C.c_double * 2) * GMM_MAX_MIXTURES)]
+
+
 class PdRateConfig(C.Structure):
   _fields_ = [('rate_fn', C.c_int32), ('reserved_', C.c_int32),
               ('mlp', C.POINTER(PdMlp)), ('constant_rates', C.c_float * 3),
-              ('reserved2_', C.c_float)]
+              ('reserved2_', C.c_float), ('gmm', C.POINTER(PdGmm))]
 
 
 class PdStepOut(C.Structure):

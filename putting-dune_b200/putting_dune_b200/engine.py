@@ -141,7 +141,7 @@ class RateSpec:
 
   def __init__(self, kind: int, *, mlp: Optional[MlpWeights] = None,
                constant: Optional[Sequence[float]] = None, device=None,
-               tensor_core: bool = False):
+               tensor_core: bool = False, gmm: Optional[dict] = None):
     self.kind = int(kind)
     self.c = nat.PdRateConfig()
     self.c.rate_fn = self.kind
@@ -152,6 +152,24 @@ class RateSpec:
         raise ValueError('RATE_CONSTANT needs three rates')
       for i, r in enumerate(constant):
         self.c.constant_rates[i] = float(r)
+    if self.kind == nat.RATE_GMM:
+      if gmm is None:
+        raise ValueError('RATE_GMM needs the mixture parameters')
+      w = np.asarray(gmm['mixture_weights'], dtype=np.float64).reshape(-1)
+      loc = np.asarray(gmm['loc_distances'], dtype=np.float64).reshape(-1)
+      var = np.asarray(gmm['variances'], dtype=np.float64).reshape(-1, 2)
+      n = w.size
+      if not (1 <= n <= nat.GMM_MAX_MIXTURES) or loc.size != n or len(var) != n:
+        raise ValueError('inconsistent mixture parameters')
+      self._gmm_c = nat.PdGmm()
+      self._gmm_c.n_mixtures = n
+      self._gmm_c.max_rate = float(gmm['max_rate'])
+      for i in range(n):
+        self._gmm_c.mixture_weights[i] = w[i]
+        self._gmm_c.loc_distances[i] = loc[i]
+        self._gmm_c.variances[i][0] = var[i, 0]
+        self._gmm_c.variances[i][1] = var[i, 1]
+      self.c.gmm = C.pointer(self._gmm_c)
     if self.kind == nat.RATE_LEARNED:
       if mlp is None:
         raise ValueError('RATE_LEARNED needs MlpWeights')

@@ -173,6 +173,64 @@ class PristineSingleSiGrRatePredictor:
     return Rates(states)
 
 
+@dataclasses.dataclass(frozen=True, eq=False)
+class GaussianMixtureRateFunction:
+  """graphene.py:279-461: per-neighbour anisotropic Gaussian mixture placed
+  along the Si->neighbour vector; a ``RateFunction`` evaluated on the device
+  (PD_RATE_GMM).  File (de)serialisation of the reference (msgpack) is an
+  offline format and not provided."""
+  max_rate: float
+  mixture_weights: np.ndarray  # [n_mixtures]
+  loc_distances: np.ndarray  # [n_mixtures]
+  variances: np.ndarray  # [n_mixtures, 2]
+
+  def rate_spec(self) -> engine.RateSpec:
+    return engine.RateSpec(nat.RATE_GMM, gmm={
+        'max_rate': self.max_rate, 'mixture_weights': self.mixture_weights,
+        'loc_distances': self.loc_distances, 'variances': self.variances})
+
+  def __call__(self, grid: mu.AtomicGrid,
+               beam_position: geometry.Point) -> Rates:
+    material = getattr(grid, '_material', None)
+    if material is None:
+      raise NotImplementedError('grid must be a material.grid')
+    rates, nbr = material._device_rates(beam_position, self.rate_spec())  # pylint: disable=protected-access
+    states = []
+    for k, r in zip(nbr, rates):
+      numbers = np.full_like(grid.atomic_numbers, constants.CARBON)
+      numbers[int(k)] = constants.SILICON
+      states.append(SuccessorState(
+          mu.AtomicGrid(grid.atom_positions, numbers), float(r)))
+    return Rates(states)
+
+  @classmethod
+  def sample_new(cls, rng: np.random.Generator):
+    """graphene.py:429-444 (domain randomisation; host draws)."""
+    num_mixtures = rng.poisson(2.0) + 1
+    max_rate = rng.uniform(0.01, 1.0)
+    weights = rng.uniform(0.0, 10.0, size=(num_mixtures,))
+    weights = weights / np.sum(weights)
+    loc = rng.uniform(-2.0, 3.0, size=(num_mixtures,))
+    variances = rng.uniform(0.1, 5.0, size=(num_mixtures, 2))
+    return cls(max_rate=max_rate, mixture_weights=weights, loc_distances=loc,
+               variances=variances)
+
+  def __eq__(self, other) -> bool:
+    """graphene.py:446-461: equal up to 1e-3."""
+    a, b = self, other
+    if (np.shape(a.mixture_weights) != np.shape(b.mixture_weights) or
+        np.shape(a.loc_distances) != np.shape(b.loc_distances) or
+        np.shape(a.variances) != np.shape(b.variances) or
+        abs(a.max_rate - b.max_rate) > 1e-3):
+      return False
+    return not ((np.abs(np.asarray(a.mixture_weights) -
+                        np.asarray(b.mixture_weights)) > 1e-3).any() or
+                (np.abs(np.asarray(a.loc_distances) -
+                        np.asarray(b.loc_distances)) > 1e-3).any() or
+                (np.abs(np.asarray(a.variances) -
+                        np.asarray(b.variances)) > 1e-3).any())
+
+
 class Material(abc.ABC):
   """graphene.py:86-118."""
 

@@ -26,7 +26,17 @@ from oracle import refshim
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None):
+GMM_PARAMS = {  # graphene_test.py:337-345 parameter set
+    'max_rate': 5.0,
+    'mixture_weights': np.asarray((0.3, 0.3, 0.2, 0.1, 0.1)),
+    'loc_distances': np.asarray((0.0, 1.0, 0.5, 0.0, 1.5)),
+    'variances': np.asarray(((0.1, 0.1), (1.0, 1.0), (2.0, 0.5), (0.5, 2.0),
+                             (0.01, 0.01))),
+}
+
+
+def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None,
+                         gmm=None):
   """Controls that follow the Si (RelativeToSilicon-style), from the oracle."""
   st = po.make_state(n_envs, seed)
   po.reset(st)
@@ -39,20 +49,21 @@ def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None):
     a = rng.uniform(-1, 1, size=(n_envs, 2))
     controls[t, :, 0] = q + a * po.BOND / st.fov_scale[:, None]
     dwell[t, :, 0] = np.where(np.arange(n_envs) % 2 == 0, 1500000, 5000000)
-    po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn, mlp=mlp)
+    po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn, mlp=mlp,
+                      gmm=gmm)
   return controls, dwell
 
 
-def events_fixture(name, rate_fn, seed, n_envs, n_steps, mlp=None):
+def events_fixture(name, rate_fn, seed, n_envs, n_steps, mlp=None, gmm=None):
   controls, dwell = closed_loop_controls(seed, n_envs, n_steps, rate_fn,
-                                         ctrl_seed=seed + 1, mlp=mlp)
+                                         ctrl_seed=seed + 1, mlp=mlp, gmm=gmm)
   out = {k: [] for k in ('si0', 'fov0', 'fov_scale', 'image_params', 'si',
                          'elapsed_us', 'fov', 'n_observed', 'sample_positions',
                          'obs0_positions', 'obs0_numbers')}
   trans = []
   for e in range(n_envs):
     r = refrun.run_reference_env(seed, e, controls[:, e], dwell[:, e], rate_fn,
-                                 mlp=mlp)
+                                 mlp=mlp, gmm=gmm)
     for k in ('si0', 'fov0', 'fov_scale', 'image_params', 'si', 'elapsed_us',
               'fov', 'n_observed'):
       out[k].append(r[k])
@@ -91,9 +102,9 @@ def rates_fixture():
   mlp = po.MlpParams.synthetic(3, hidden=(32, 32))
   res = {'beam': beam, 'seed': np.int64(seed)}
   for name, rate_fn in (('simple', po.RATE_SIMPLE), ('prior', po.RATE_PRIOR),
-                        ('learned', po.RATE_LEARNED)):
-    fn = refrun.make_rate_function(mods, rate_fn, mlp)
-    rates = np.zeros((n, 3), dtype=np.float32)
+                        ('learned', po.RATE_LEARNED), ('gmm', po.RATE_GMM)):
+    fn = refrun.make_rate_function(mods, rate_fn, mlp, GMM_PARAMS)
+    rates = np.zeros((n, 3), dtype=np.float64 if name == 'gmm' else np.float32)
     succ = np.zeros((n, 3), dtype=np.int32)
     for e in range(n):
       pos = po.all_positions(st, e)
@@ -220,6 +231,7 @@ if __name__ == '__main__':
              'the build container')
   events_fixture('events_simple.npz', po.RATE_SIMPLE, 2024, 32, 30)
   events_fixture('events_prior.npz', po.RATE_PRIOR, 2025, 32, 30)
+  events_fixture('events_gmm.npz', po.RATE_GMM, 2026, 24, 20, gmm=GMM_PARAMS)
   rates_fixture()
   standardize_fixture()
   frames_fixture()

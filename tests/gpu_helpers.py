@@ -33,7 +33,10 @@ def load_from_oracle(b: engine.EnvBatch, st: po.OracleState) -> None:
   b.status.zero_()
 
 
-def rate_spec(rate_fn: int, mlp=None, constant=None) -> engine.RateSpec:
+def rate_spec(rate_fn: int, mlp=None, constant=None,
+              gmm=None) -> engine.RateSpec:
+  if rate_fn == po.RATE_GMM:
+    return engine.RateSpec(rate_fn, gmm=gmm)
   if rate_fn == po.RATE_LEARNED:
     w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
                              engine.MlpWeights.NAMES},

@@ -417,3 +417,80 @@ def test_rollout_host_pipeline_matches_device_path(eng):
       np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
       np.testing.assert_array_equal(h_el.numpy(), gh.np_(el))
       np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+
+
+GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
+    'max_rate': 5.0,
+    'mixture_weights': np.asarray((0.3, 0.3, 0.2, 0.1, 0.1)),
+    'loc_distances': np.asarray((0.0, 1.0, 0.5, 0.0, 1.5)),
+    'variances': np.asarray(((0.1, 0.1), (1.0, 1.0), (2.0, 0.5), (0.5, 2.0),
+                             (0.01, 0.01))),
+}
+
+
+def test_gmm_rate_function(eng, golden_dir):
+  """graphene.py:279-390 GaussianMixtureRateFunction on the device: rates vs
+  the reference's scipy evaluation, trajectories of the unmodified reference,
+  and 4096-env parity with the oracle (float64 total rate path)."""
+  spec = gh.rate_spec(po.RATE_GMM, gmm=GMM_PARAMS)
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  r, nb = b.rates(fix['beam'], spec)
+  np.testing.assert_array_equal(gh.np_(nb), fix['succ_gmm'])
+  np.testing.assert_allclose(gh.np_(r), fix['rates_gmm'].astype(np.float32),
+                             rtol=2e-7, atol=1e-37)
+  # reference golden trajectories
+  fix = np.load(os.path.join(golden_dir, 'events_gmm.npz'))
+  controls, dwell = fix['controls'], fix['dwell_us']
+  b = eng.EnvBatch(controls.shape[1], seed=int(fix['seed']))
+  b.reset()
+  for t in range(controls.shape[0]):
+    out = b.step_and_image(controls[t], dwell[t], spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si'][:, t])
+    np.testing.assert_array_equal(gh.np_(out.elapsed_us),
+                                  fix['elapsed_us'][:, t])
+  # oracle parity at BASELINE config-2 size, through both kernels
+  n, seed = 4096, 61
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  rng = np.random.default_rng(3)
+  for _ in range(25):
+    ctl = gh.closed_loop_control(st, rng)[:, None, :]
+    want = po.step_and_image(st, ctl, 1500000, rate_fn=po.RATE_GMM,
+                             gmm=GMM_PARAMS)
+    out = b.step_and_image(ctl, 1500000, spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+    np.testing.assert_array_equal(gh.np_(out.events), want['events'])
+  assert st.n_transitions.sum() > 20000
+  big = eng.EnvBatch(200000, seed=seed)
+  small = eng.EnvBatch(4096, seed=seed)
+  big.reset()
+  small.reset()
+  ctl = 0.5 + rng.uniform(-0.05, 0.05, size=(200000, 1, 2))
+  big.step_and_image(ctl, 1500000, spec)
+  small.step_and_image(ctl[:4096], 1500000, spec)
+  np.testing.assert_array_equal(gh.np_(big.si_idx)[:4096], gh.np_(small.si_idx))
+
+
+def test_gmm_facade_class():
+  # graphene_test.py:312-330, :355-359
+  import putting_dune_b200 as pd
+  fn = pd.graphene.GaussianMixtureRateFunction(
+      max_rate=1.0, mixture_weights=np.asarray((0.8, 0.2)),
+      loc_distances=np.asarray((0.0, 1.0)),
+      variances=np.asarray(((0.1, 0.1), (1.0, 1.0))))
+  m = pd.graphene.PristineSingleDopedGraphene(rate_function=fn)
+  m.reset(np.random.default_rng(0))
+  rates = fn(m.grid, pd.geometry.Point(m.get_silicon_position()))
+  assert abs(max(s.rate for s in rates.successor_states) - 1.0) < 0.05
+  rng = np.random.default_rng(0)
+  a = pd.graphene.GaussianMixtureRateFunction.sample_new(rng)
+  b = pd.graphene.GaussianMixtureRateFunction.sample_new(rng)
+  assert a != b and a == a
+  import datetime as dt
+  m.apply_control(np.random.default_rng(0), pd.microscope_utils.BeamControl(
+      pd.geometry.Point(m.get_silicon_position()), dt.timedelta(seconds=5)))

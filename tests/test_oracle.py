@@ -57,6 +57,15 @@ def test_si_never_initialised_on_edge():
   assert (d[:, 2] <= 1.42 + 1e-3).all()
 
 
+GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
+    'max_rate': 5.0,
+    'mixture_weights': np.asarray((0.3, 0.3, 0.2, 0.1, 0.1)),
+    'loc_distances': np.asarray((0.0, 1.0, 0.5, 0.0, 1.5)),
+    'variances': np.asarray(((0.1, 0.1), (1.0, 1.0), (2.0, 0.5), (0.5, 2.0),
+                             (0.01, 0.01))),
+}
+
+
 # -- event-path golden vectors from the reference ------------------------------
 def _replay(fix):
   seed = int(fix['seed'])
@@ -73,13 +82,14 @@ def _replay(fix):
   fov = np.zeros((n_envs, n_steps, 4))
   for t in range(n_steps):
     out = po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn,
-                            log=log)
+                            log=log, gmm=GMM_PARAMS)
     si[:, t], el[:, t], fov[:, t] = st.si_idx, out['elapsed_us'], st.fov
   trans = sorted(zip(log.env, log.ctrl_seq, log.elapsed_us, log.new_si))
   return st, reset_state, si, el, fov, np.asarray(trans, dtype=np.int64)
 
 
-@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz'])
+@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz',
+                                  'events_gmm.npz'])
 def test_oracle_matches_reference_trajectories(golden_dir, name):
   fix = np.load(os.path.join(golden_dir, name))
   st, r0, si, el, fov, trans = _replay(fix)
@@ -119,6 +129,10 @@ def test_oracle_rates_match_reference(golden_dir):
       'bn_scale', 'bn_offset', 'bn_mean', 'bn_var', 'w0', 'b0', 'w1', 'b1',
       'w2', 'b2')})
   envs = np.arange(n)
+  r64, nbr = po.rates_for(st, envs, fix['beam'], po.RATE_GMM, gmm=GMM_PARAMS,
+                          keep64=True)
+  np.testing.assert_array_equal(nbr, fix['succ_gmm'])
+  np.testing.assert_allclose(r64, fix['rates_gmm'], rtol=1e-12, atol=1e-300)
   for name, rate_fn, rtol in (('simple', po.RATE_SIMPLE, 0.0),
                               ('prior', po.RATE_PRIOR, 1e-6),
                               ('learned', po.RATE_LEARNED, 1e-6)):
@@ -346,3 +360,16 @@ def test_relative_to_silicon_adapter_goldens(si, action, want):
   st.fov[0] = np.concatenate((ll, ll + 10.0))
   got = oe.relative_to_silicon_controls(st, np.asarray([action]))
   np.testing.assert_allclose(got[0], want, atol=1e-9)
+
+
+def test_gmm_max_rate_at_mode():
+  # graphene_test.py:312-330: the dominant mode sits on the Si -> max ~ 1.0
+  gmm = {'max_rate': 1.0, 'mixture_weights': np.asarray((0.8, 0.2)),
+         'loc_distances': np.asarray((0.0, 1.0)),
+         'variances': np.asarray(((0.1, 0.1), (1.0, 1.0)))}
+  st = po.make_state(4, seed=1)
+  po.reset(st)
+  p_si = po.site_positions(st, st.si_idx, np.arange(4))
+  r, _ = po.rates_for(st, np.arange(4), p_si, po.RATE_GMM, gmm=gmm,
+                      keep64=True)
+  np.testing.assert_allclose(r.max(axis=1), 1.0, atol=0.05)
