@@ -551,7 +551,8 @@ class EventLog:
 def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
                   rate_fn: int = RATE_SIMPLE, mlp: Optional[MlpParams] = None,
                   log: Optional[EventLog] = None,
-                  rates_override=None, gmm: Optional[dict] = None) -> dict:
+                  rates_override=None, gmm: Optional[dict] = None,
+                  skip: Optional[np.ndarray] = None) -> dict:
   """graphene.py:646-694 for all envs at once.
 
   beam: float64 [E, 2] material frame; dwell_us: int64 [E].
@@ -564,7 +565,8 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
   tr = np.zeros(e, dtype=np.int64)
   first_rates = np.zeros((e, 3), dtype=np.float32)
   it = 0
-  active = elapsed < dwell_us  # graphene.py:658
+  live = np.ones(e, dtype=bool) if skip is None else ~np.asarray(skip, bool)
+  active = (elapsed < dwell_us) & live  # graphene.py:658
   while active.any():
     idx = np.nonzero(active)[0]
     if rates_override is not None:
@@ -613,9 +615,9 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
           log.elapsed_us.append(int(elapsed[idx[hh]]))
           log.slot.append(int(slot[j]))
           log.new_si.append(int(new_si[j]))
-    active = elapsed < dwell_us
+    active = (elapsed < dwell_us) & live
     it += 1
-  state.ctrl_count += np.uint32(1)
+  state.ctrl_count[live] += np.uint32(1)
   state.n_events += ev
   state.n_transitions += tr
   return {'events': ev, 'transitions': tr, 'first_rates': first_rates}
@@ -653,7 +655,8 @@ def step_and_image(state: OracleState, controls: np.ndarray,
                    rate_fn: int = RATE_SIMPLE,
                    mlp: Optional[MlpParams] = None,
                    log: Optional[EventLog] = None,
-                   gmm: Optional[dict] = None) -> dict:
+                   gmm: Optional[dict] = None,
+                   skip: Optional[np.ndarray] = None) -> dict:
   """simulator.py:107-182 for all envs (without rendering).
 
   controls: float64 [E, C, 2] microscope frame; dwell_us: int64 [E, C].
@@ -671,12 +674,15 @@ def step_and_image(state: OracleState, controls: np.ndarray,
   for c in range(controls.shape[1]):
     beam = microscope_to_material(state.fov, controls[:, c])  # :137
     out = apply_control(state, beam, dwell_us[:, c], rate_fn, mlp, log,
-                        gmm=gmm)  # :147
+                        gmm=gmm, skip=skip)  # :147
     ev += out['events']
     tr += out['transitions']
     elapsed += dwell_us[:, c]  # :149
   elapsed += image_duration_us  # :152-153
   recentre = silicon_outside_safe_area(state)  # :156
+  if skip is not None:  # envs that sit this call out
+    recentre &= ~np.asarray(skip, bool)
+    elapsed[np.asarray(skip, bool)] = 0
   if recentre.any():
     recenter_fov(state, np.nonzero(recentre)[0])  # :161-165
     elapsed[recentre] += image_duration_us  # :168-169

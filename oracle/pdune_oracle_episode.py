@@ -63,15 +63,18 @@ def observe_site(state: po.OracleState, envs, sites):
                    (p[..., 1] - f[..., 1]) / (f[..., 3] - f[..., 1])), axis=-1)
 
 
-def choose_goals(state: po.OracleState) -> tuple:
-  """goals.py:84-121 for every env, after reset.  Returns (goal site [E],
-  goal position in the material frame [E, 2])."""
+def choose_goals(state: po.OracleState, envs=None, draw_index: int = 13):
+  """goals.py:84-121 for every env (or `envs`), after reset.  Returns (goal
+  site [E], goal position in the material frame [E, 2]); rows of envs not
+  listed are zero.  `draw_index`: position of the goal draw on the RESET
+  stream (13, or 15 after the two draws of DeltaPositionActionAdapter.reset)."""
   e = state.num_envs
   goal_site = np.zeros(e, dtype=np.int32)
   goal_pos = np.zeros((e, 2))
   u = po.draw_linear(state.seed, state.env_ids,
-                     state.episode - np.uint32(1), po.STREAM_RESET, 13)
-  for i in range(e):
+                     state.episode - np.uint32(1), po.STREAM_RESET,
+                     draw_index)
+  for i in (range(e) if envs is None else envs):
     q, _, sites = po.get_atoms_in_bounds(state, i)
     f = state.fov[i]
     q_si = q[sites == state.si_idx[i]].reshape(1, 2)

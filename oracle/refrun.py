@@ -295,3 +295,76 @@ def run_reference_episodes(seed: int, env_ids, rate_fn: int = po.RATE_SIMPLE,
                                agg.average_environment_seconds_to_goal,
                                agg.average_total_reward]),
   }
+
+
+def run_reference_env_stack(seed: int, env_id: int, actions: np.ndarray,
+                            adapter: int, features: int,
+                            rate_fn: int = po.RATE_SIMPLE,
+                            min_dwell_s: float = 1.5, max_dwell_s: float = 1.5,
+                            max_distance: float = po.BOND,
+                            step_limit: int = 600) -> dict:
+  """T calls of `env.step(action)` on the unmodified reference
+  PuttingDuneEnvironment + StepLimitWrapper (the first call resets, as do the
+  calls after a LAST step).  Returns the TimeStep fields per call."""
+  from oracle import pdune_oracle_env as oenv
+  mods = refshim.load_reference_env_stack()
+  table = po.neighbor_table(50)
+  install_canonical_neighbors(mods, table)
+  fc = mods.feature_constructors
+  orig_nn = fc.neighbors.NearestNeighbors
+  fc.neighbors = type('N', (), {'NearestNeighbors': _CanonicalKnn})
+  mu, aa = mods.microscope_utils, mods.action_adapters
+  dwell = (dt.timedelta(seconds=min_dwell_s), dt.timedelta(seconds=max_dwell_s))
+  if adapter == oenv.ADAPTER_DIRECT:
+    ad = aa.DirectActionAdapter()
+  elif adapter == oenv.ADAPTER_DELTA:
+    ad = aa.DeltaPositionActionAdapter(np.random.default_rng(0))
+  elif adapter == oenv.ADAPTER_RELATIVE:
+    ad = aa.RelativeToSiliconActionAdapter(
+        dwell_time_range=dwell, max_distance_angstroms=max_distance)
+  else:
+    ad = aa.RelativeToSiliconMaterialFrameActionAdapter(
+        dwell_time_range=dwell, max_distance_angstroms=max_distance)
+  feat = (fc.SingleSiliconPristineGrapheneFeatureConstuctor()
+          if features == oenv.FEATURES_MICROSCOPE else
+          fc.SingleSiliconMaterialFrameFeatureConstructor())
+  inner = mods.putting_dune_environment.PuttingDuneEnvironment(
+      material=mods.graphene.PristineSingleDopedGraphene(
+          rate_function=make_rate_function(mods, rate_fn)),
+      action_adapter=ad, feature_constructor=feat,
+      goal=mods.goals.SingleSiliconGoalReaching(),
+      image_duration=dt.timedelta(seconds=2.0))
+  rng = InjectedRng(seed, env_id)
+  inner._rng = rng  # pylint: disable=protected-access
+  if hasattr(ad, 'rng'):
+    ad.rng = rng
+  state = {'episode': 0, 'ctrl': 0}
+
+  class Hook(mu.SimulatorObserver):
+    def observe_apply_control(self, control):
+      rng.begin(po.STREAM_KMC, state['ctrl'])
+      state['ctrl'] += 1
+
+  inner.sim.add_observer(Hook())
+  sim_reset = inner.sim.reset
+
+  def reset_with_stream(r, **kw):
+    r.begin(po.STREAM_RESET, state['episode'])
+    state['episode'] += 1
+    return sim_reset(r, **kw)
+
+  inner.sim.reset = reset_with_stream
+  env = mods.run_helpers.StepLimitWrapper(inner, step_limit=step_limit)
+  out = {'step_type': [], 'reward': [], 'discount': [], 'observation': []}
+  try:
+    with np.errstate(divide='ignore', over='ignore', invalid='ignore'):
+      for a in actions:
+        ts = env.step(np.asarray(a))
+        out['step_type'].append(int(ts.step_type))
+        out['reward'].append(0.0 if ts.reward is None else float(ts.reward))
+        out['discount'].append(float(ts.discount))
+        out['observation'].append(np.asarray(ts.observation, np.float32))
+  finally:
+    fc.neighbors = type('N', (), {'NearestNeighbors': orig_nn})
+    uninstall_canonical_neighbors(mods)
+  return {k: np.asarray(v) for k, v in out.items()}

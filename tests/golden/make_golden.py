@@ -225,6 +225,41 @@ def episodes_fixture():
   np.savez_compressed(os.path.join(HERE, 'episodes_reference.npz'), **res)
 
 
+ENV_CASES = (  # adapter, features, min dwell, max dwell, max distance, limit
+    (2, 0, 1.5, 1.5, 1.42, 600),   # relative_random (registry.py:263-266)
+    (2, 1, 1.0, 5.0, 2.84, 600),   # relative adapter with a dwell action
+    (3, 1, 5.0, 5.0, 2.84, 7),     # material-frame adapter, step limit 7
+    (0, 0, 1.5, 1.5, 1.42, 600),   # DirectActionAdapter
+    (1, 0, 1.5, 1.5, 1.42, 600),   # DeltaPositionActionAdapter
+)
+
+
+def env_actions(case, n_steps, n_envs, seed=3):
+  from oracle import pdune_oracle_env as oenv
+  ad, ft, d0, d1, md, lim = case
+  adim = oenv.EnvConfig(adapter=ad, min_dwell_s=d0, max_dwell_s=d1).action_dim
+  rng = np.random.default_rng(seed)
+  lo, hi = {0: (0.3, 0.7), 1: (-0.1, 0.1), 2: (-1.2, 1.2), 3: (-2.0, 2.0)}[ad]
+  return rng.uniform(lo, hi, size=(n_steps, n_envs, adim))
+
+
+def env_fixture():
+  """TimeSteps of the reference PuttingDuneEnvironment + StepLimitWrapper."""
+  seed, n, t_steps = 808, 4, 30
+  res = {'seed': np.int64(seed)}
+  for i, case in enumerate(ENV_CASES):
+    acts = env_actions(case, t_steps, n)
+    res[f'actions_{i}'] = acts
+    outs = [refrun.run_reference_env_stack(seed, e, acts[:, e], case[0],
+                                           case[1], po.RATE_SIMPLE, case[2],
+                                           case[3], case[4], case[5])
+            for e in range(n)]
+    for k in ('step_type', 'reward', 'discount', 'observation'):
+      res[f'{k}_{i}'] = np.stack([o[k] for o in outs], axis=1)  # [T, n, ...]
+    print('env case', i, 'LAST', int((res[f'step_type_{i}'] == 2).sum()))
+  np.savez_compressed(os.path.join(HERE, 'env_reference.npz'), **res)
+
+
 if __name__ == '__main__':
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
@@ -236,3 +271,4 @@ if __name__ == '__main__':
   standardize_fixture()
   frames_fixture()
   episodes_fixture()
+  env_fixture()

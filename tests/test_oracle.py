@@ -373,3 +373,32 @@ def test_gmm_max_rate_at_mode():
   r, _ = po.rates_for(st, np.arange(4), p_si, po.RATE_GMM, gmm=gmm,
                       keep64=True)
   np.testing.assert_allclose(r.max(axis=1), 1.0, atol=0.05)
+
+
+# -- batched dm_env layer vs the reference PuttingDuneEnvironment --------------
+ENV_CASES = ((2, 0, 1.5, 1.5, 1.42, 600), (2, 1, 1.0, 5.0, 2.84, 600),
+             (3, 1, 5.0, 5.0, 2.84, 7), (0, 0, 1.5, 1.5, 1.42, 600),
+             (1, 0, 1.5, 1.5, 1.42, 600))
+
+
+@pytest.mark.parametrize('case', range(5))
+def test_env_oracle_matches_reference_environment(golden_dir, case):
+  from oracle import pdune_oracle_env as oenv
+  fix = np.load(os.path.join(golden_dir, 'env_reference.npz'))
+  ad, ft, d0, d1, md, lim = ENV_CASES[case]
+  cfg = oenv.EnvConfig(adapter=ad, features=ft, min_dwell_s=d0, max_dwell_s=d1,
+                       max_distance=md, step_limit=lim)
+  acts = fix[f'actions_{case}']
+  env = oenv.OracleEnv(acts.shape[1], int(fix['seed']), cfg)
+  for t in range(acts.shape[0]):
+    ts = env.step(acts[t])
+    np.testing.assert_array_equal(ts['step_type'], fix[f'step_type_{case}'][t])
+    np.testing.assert_allclose(ts['reward'], fix[f'reward_{case}'][t],
+                               rtol=1e-6)
+    np.testing.assert_allclose(ts['discount'], fix[f'discount_{case}'][t],
+                               rtol=1e-6)
+    np.testing.assert_allclose(ts['observation'],
+                               fix[f'observation_{case}'][t], rtol=0,
+                               atol=2e-6)
+  # putting_dune_environment_test.py:110: the first step of a fresh env resets
+  assert (fix[f'step_type_{case}'][0] == 0).all()
