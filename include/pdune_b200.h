@@ -347,6 +347,59 @@ int pd_run_episodes(const pd_lattice* lat, const pd_state* st,
                     double* goal_xy, int32_t* goal_site,
                     pd_episode_stats* stats, void* stream);
 
+/* ---- batched RL environment layer:
+ *      PuttingDuneEnvironment.reset/step (putting_dune_environment.py:87-158)
+ *      under StepLimitWrapper (run_helpers.py:120-153), with the four action
+ *      adapters (action_adapters.py:53-274), the two 10-float feature
+ *      constructors (feature_constructors.py:79-228) and
+ *      SingleSiliconGoalReaching (goals.py:70-185), for every env at once. -- */
+typedef enum pd_adapter {
+  PD_ADAPTER_DIRECT = 0,            /* action_adapters.py:53-84               */
+  PD_ADAPTER_DELTA = 1,             /* :87-128 (stateful beam position)       */
+  PD_ADAPTER_RELATIVE = 2,          /* :131-216                               */
+  PD_ADAPTER_RELATIVE_MATERIAL = 3  /* :219-274                               */
+} pd_adapter;
+typedef enum pd_features {
+  PD_FEATURES_MICROSCOPE = 0,  /* feature_constructors.py:79-154              */
+  PD_FEATURES_MATERIAL = 1     /* :157-228                                    */
+} pd_features;
+/* dm_env.StepType */
+#define PD_STEP_FIRST 0
+#define PD_STEP_MID 1
+#define PD_STEP_LAST 2
+
+typedef struct pd_env_config {
+  int32_t adapter;      /* pd_adapter                                        */
+  int32_t features;     /* pd_features                                       */
+  int32_t action_dim;   /* 2, or 3 when the relative adapters take a dwell   */
+  int32_t step_limit;   /* StepLimitWrapper (600 in run_helpers.py:34)       */
+  double min_dwell_s, max_dwell_s;   /* adapter dwell range (1.5, 1.5)       */
+  double max_distance_angstroms;     /* RelativeToSilicon adapter            */
+  int64_t image_duration_us;
+} pd_env_config;
+
+/* Per-env environment state and scratch, device arrays of length n. */
+typedef struct pd_env_buffers {
+  double* goal_xy;          /* [n][2] goal position, material frame          */
+  double* beam_pos;         /* [n][2] DeltaPositionActionAdapter state       */
+  int32_t* elapsed_steps;   /* StepLimitWrapper counter (-1 = truncated)     */
+  uint8_t* needs_reset;     /* 1 = next step resets (initially 1)            */
+  double* controls_xy;      /* [n][2] scratch: adapter output                */
+  int64_t* dwell_us;        /* [n]    scratch                                */
+  int64_t* elapsed_us;      /* [n]    scratch: step elapsed time             */
+  uint8_t* resetting;       /* [n]    scratch: envs that reset in this call  */
+} pd_env_buffers;
+
+/* One env.step(action) per env: envs whose previous step was LAST (or that
+ * were never reset) reset instead and return FIRST.  actions: device double
+ * [n][action_dim]; outputs: observation float [n][10], reward float [n],
+ * discount float [n], step_type int32 [n]. */
+int pd_env_step(const pd_lattice* lat, const pd_state* st,
+                const pd_rate_config* rc, const pd_env_config* cfg,
+                const pd_env_buffers* buf, const double* actions,
+                float* observation, float* reward, float* discount,
+                int32_t* step_type, void* stream);
+
 /* ---- learned model, batched form: rate_learning/learn_rates.py:704-732
  *      LearnedTransitionRatePredictor.apply_model -- mean over an ensemble of
  *      softmax(out[:3]) * out[3].  models: HOST array of n_models pd_mlp;

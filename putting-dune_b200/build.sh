@@ -15,6 +15,7 @@ exact=(pd_lattice pd_reset pd_step pd_query)
 fast=(pd_api pd_mlp)
 [ -f "$src/pd_render.cu" ] && fast+=(pd_render)
 [ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
+[ -f "$src/pd_env.cu" ] && exact+=(pd_env)
 pids=()
 for f in "${exact[@]}"; do
   "$NVCC" "${COMMON[@]}" -fmad=false -c "$src/$f.cu" -o "$obj/$f.o" & pids+=($!)

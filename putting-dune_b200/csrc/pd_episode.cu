@@ -26,7 +26,8 @@ constexpr int kMaxChunks = 2048;  // 65535 sites / 32
 __global__ void __launch_bounds__(kGoalThreads)
     k_choose_goal(const pd_lattice lat, const pd_state st,
                   double* __restrict__ goal_xy,
-                  int32_t* __restrict__ goal_site) {
+                  int32_t* __restrict__ goal_site,
+                  const uint8_t* __restrict__ mask, uint32_t draw_index) {
   extern __shared__ unsigned goal_masks[];  // [warps][n_chunks]
   const int lane = threadIdx.x & 31;
   const int n_chunks = (lat.n_sites + 31) / 32;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kGoalThreads)
   const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
   for (int64_t e = blockIdx.x * (kGoalThreads / 32) + (threadIdx.x >> 5);
        e < st.n_envs; e += warps) {
+    if (mask && !mask[e]) continue;
     const Lattice4 t = load_lattice4(st.lattice, e);
     const Fov4 f = load_fov4(st.fov, e);
     const double w = __dsub_rn(f.urx, f.llx), h = __dsub_rn(f.ury, f.lly);
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(kGoalThreads)
         observe(f, site_position(__ldg(base + st.si_idx[e]), t));
     const double u =
         draw_linear(st.seed, st.env_offset + static_cast<uint32_t>(e),
-                    st.episode[e] - 1u, PD_STREAM_RESET, 13);
+                    st.episode[e] - 1u, PD_STREAM_RESET, draw_index);
     // Only lattice rows that can intersect the FOV's circumscribed circle are
     // scanned: rows are horizontal lines of the base lattice and site ids are
     // row-major, so they form one contiguous id range.
@@ -124,6 +126,21 @@ int launch_episodes(const pd_lattice* lat, const pd_state* st,
                     const double* goal_xy, pd_episode_stats* stats,
                     cudaStream_t stream);
 
+// pd_env.cu: goals for the envs with mask[e] != 0 (draw `draw_index` of the
+// RESET stream).
+int choose_goals_masked(const pd_lattice* lat, const pd_state* st,
+                        double* goal_xy, const uint8_t* mask,
+                        uint32_t draw_index, cudaStream_t s) {
+  const int64_t blocks = (st->n_envs + 3) / 4;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  const size_t smem =
+      sizeof(unsigned) * (kGoalThreads / 32) * ((lat->n_sites + 31) / 32);
+  k_choose_goal<<<static_cast<int>(blocks < cap ? blocks : cap), kGoalThreads,
+                  smem, s>>>(*lat, *st, goal_xy, nullptr, mask, draw_index);
+  PD_CUDA_OK(cudaGetLastError());
+  return PD_OK;
+}
+
 }  // namespace pd
 
 extern "C" int pd_run_episodes(const pd_lattice* lat, const pd_state* st,
@@ -149,7 +166,7 @@ extern "C" int pd_run_episodes(const pd_lattice* lat, const pd_state* st,
                         ((lat->n_sites + 31) / 32);
     pd::k_choose_goal<<<static_cast<int>(blocks < cap ? blocks : cap),
                         pd::kGoalThreads, smem, s>>>(*lat, *st, goal_xy,
-                                                     goal_site);
+                                                     goal_site, nullptr, 13u);
     PD_CUDA_OK(cudaGetLastError());
   }
   return pd::launch_episodes(lat, st, rc, cfg, goal_xy, stats, s);

@@ -354,6 +354,7 @@ struct StepArgs {
   int32_t n_steps;            // rollout only
   int64_t image_duration_us;
   int32_t material_frame;     // 1: apply_control (no observe phase)
+  const uint8_t* skip;        // [n] or null: envs that sit this call out
   int32_t action_mode;        // pd_action_mode (rollouts)
   double max_distance;        // RelativeToSilicon adapter, angstroms
   pd_step_out out;

@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     Fov4 fov{};
     Lattice4 lt{};
     const bool own = tid < n_act;
+    bool skipped = false;  // env sits this call out (pd_env_step resets it)
     if (own) {
       if (tid < n_pending) {
         env = sh.q_env[tid]; ctl = sh.q_ctl[tid]; si = sh.q_si[tid];
@@ -543,13 +544,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         env = static_cast<int>(cursor + (tid - n_pending));
         si = a.st.si_idx[env];
       }
+      skipped = a.skip && a.skip[env];
       lt = load_lattice4(a.st.lattice, env);
       fov = load_fov4(a.st.fov, env);
     }
     // controls with zero dwell do no rate evaluation (graphene.py:658)
     bool need_eval = false;
     double2 psi = make_double2(0.0, 0.0);
-    if (own) {
+    if (own && !skipped) {
       while (ctl < a.n_controls) {
         dwell = a.dwell_us ? a.dwell_us[static_cast<int64_t>(env) *
                                             a.n_controls + ctl]
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         }
         survive = ctl < a.n_controls;
       }
-      if (!survive) {
+      if (!survive && !skipped) {
         // ---- finalise the env: simulator.py:152-169 ----
         uint8_t recentred = 0;
         if (!a.material_frame) {

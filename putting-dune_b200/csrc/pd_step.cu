@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kStepThreads)
   const int64_t n = a.st.n_envs;
   for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
        e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (a.skip && a.skip[e]) continue;
     EnvRegs r = load_env(tab, a, e);
     Fov4 fov = load_fov4(a.st.fov, e);
     long long elapsed = 0;
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       const unsigned im = __ballot_sync(0xffffffffu, idle);
       if (im && cursor < hi) {
         const int64_t cand = cursor + __popc(im & lt_mask);
-        if (idle && cand < hi) {
+        if (idle && cand < hi && !(a.skip && a.skip[cand])) {
           env = cand;
           // first control of this env, and the lines of the env this lane is
           // likely to pull next, are requested before anything waits
@@ -786,7 +787,7 @@ static int step_common(const pd_lattice* lat, const pd_state* st,
                        const int64_t* dwell_us, int64_t dwell_us_scalar,
                        int32_t n_controls, int64_t image_duration_us,
                        int material_frame, const pd_step_out* out,
-                       void* stream) {
+                       void* stream, const uint8_t* skip = nullptr) {
   int rcode = pd::validate_common(lat, st, rc);
   if (rcode != PD_OK) return rcode;
   PD_REQUIRE(rc != nullptr, "null rate config");
@@ -809,12 +810,25 @@ static int step_common(const pd_lattice* lat, const pd_state* st,
   a.n_controls = n_controls;
   a.image_duration_us = image_duration_us;
   a.material_frame = material_frame;
+  a.skip = skip;
   if (out) a.out = *out;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (rc->rate_fn == PD_RATE_LEARNED)
     return pd::learned_step(lat, st, rc->mlp, a, false, s);
   return pd::dispatch_step(rc, a, false, s);
 }
+
+namespace pd {
+// pd_env.cu: step_and_image for the envs whose skip[e] == 0.
+int step_and_image_masked(const pd_lattice* lat, const pd_state* st,
+                          const pd_rate_config* rc, const double* controls_xy,
+                          const int64_t* dwell_us, int64_t image_duration_us,
+                          const uint8_t* skip, const pd_step_out* out,
+                          void* stream) {
+  return step_common(lat, st, rc, controls_xy, dwell_us, 0, 1,
+                     image_duration_us, 0, out, stream, skip);
+}
+}  // namespace pd
 
 extern "C" int pd_apply_control(const pd_lattice* lat, const pd_state* st,
                                 const pd_rate_config* rc, const double* beam_xy,

@@ -19,6 +19,10 @@ RATE_SIMPLE, RATE_PRIOR, RATE_LEARNED, RATE_CONSTANT, RATE_GMM = 0, 1, 2, 3, 4
 ENV_BAD_RATE, ENV_LOG_OVERFLOW, ENV_NOT_RESET = 1, 2, 4
 STREAM_KMC, STREAM_RESET = 0, 1
 ACTION_DIRECT, ACTION_RELATIVE_TO_SILICON = 0, 1
+(ADAPTER_DIRECT, ADAPTER_DELTA, ADAPTER_RELATIVE,
+ ADAPTER_RELATIVE_MATERIAL) = range(4)
+FEATURES_MICROSCOPE, FEATURES_MATERIAL = 0, 1
+STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
 (RENDER_CLEAN, RENDER_BLUR, RENDER_POISSON, RENDER_JITTER, RENDER_UNIFORM,
  RENDER_EXPONENTIAL, RENDER_GAUSSIAN, RENDER_FINAL) = range(8)
 
@@ -72,6 +76,20 @@ class PdStepOut(C.Structure):
               ('log_elapsed_us', _p), ('log_site', _p), ('log_ctrl', _p)]
 
 
+class PdEnvConfig(C.Structure):
+  _fields_ = [('adapter', C.c_int32), ('features', C.c_int32),
+              ('action_dim', C.c_int32), ('step_limit', C.c_int32),
+              ('min_dwell_s', C.c_double), ('max_dwell_s', C.c_double),
+              ('max_distance_angstroms', C.c_double),
+              ('image_duration_us', C.c_int64)]
+
+
+class PdEnvBuffers(C.Structure):
+  _fields_ = [('goal_xy', _p), ('beam_pos', _p), ('elapsed_steps', _p),
+              ('needs_reset', _p), ('controls_xy', _p), ('dwell_us', _p),
+              ('elapsed_us', _p), ('resetting', _p)]
+
+
 class PdEpisodeConfig(C.Structure):
   _fields_ = [('dwell_us', C.c_int64), ('image_duration_us', C.c_int64),
               ('timeout_us', C.c_int64), ('step_limit', C.c_int32),
@@ -119,6 +137,9 @@ _SIGNATURES = {
                                 C.c_int),
     'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
                          _p, _p], C.c_int),
+    'pd_env_step': ([_LP, _SP, _RP, C.POINTER(PdEnvConfig),
+                     C.POINTER(PdEnvBuffers), _p, _p, _p, _p, _p, _p],
+                    C.c_int),
     'pd_run_episodes': ([_LP, _SP, _RP, C.POINTER(PdEpisodeConfig), _p, _p, _p,
                          _p], C.c_int),
     'pd_mlp_apply_model': ([C.POINTER(PdMlp), _i32, _p, _i64, _p, _p], C.c_int),
