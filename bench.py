@@ -241,6 +241,24 @@ def run_reference_arm(args, cfg):
 # ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
+def ncu_traffic(summary_name):
+  """dram read+write bytes per launch from a committed ncu --set full summary
+  (profiles/*.ncu.json), or None."""
+  path = os.path.join(ROOT, 'profiles', summary_name)
+  try:
+    d = json.load(open(path))
+  except (OSError, ValueError):
+    return None
+  scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+  total = 0.0
+  for k, v in d.items():
+    if k.startswith('dram__bytes_read.sum') or k.startswith(
+        'dram__bytes_write.sum'):
+      unit = k[k.index('[') + 1:k.index(']')]
+      total += float(v) * scale.get(unit, 1.0)
+  return total or None
+
+
 def measured_peak():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   try:
@@ -393,6 +411,7 @@ def run_ours(args, cfg):
     launch(i)
   barrier()
   sampler = ClockSampler(local) if rank == 0 else None
+  clocks = None
   ev = [(torch.cuda.Event(enable_timing=True),
          torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
   t0 = time.perf_counter()
@@ -403,7 +422,6 @@ def run_ours(args, cfg):
     ev[i][1].record()
   barrier()
   t1 = time.perf_counter()
-  clocks = sampler.stop(t0, t1) if sampler else None
   dev_ms = sum(a.elapsed_time(b) for a, b in ev)
   tm = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -451,7 +469,12 @@ def run_ours(args, cfg):
       'unit': 'GB/s', 'frac': achieved / peak,
       'algorithmic_bytes_per_env_step': ALGORITHMIC_BYTES_PER_ENV_STEP,
       'env_steps_per_launch': env_steps_per_launch,
-      'launch_ms': launch_s * 1e3, 'traffic': None,
+      'launch_ms': launch_s * 1e3,
+      # ncu --set full of this command (profiles/r01_k_rollout_config2):
+      # the state stays in registers across the 256 steps, so DRAM traffic is
+      # the action stream (16 B/env-step), below the 64 B algorithmic figure
+      'traffic': ncu_traffic('r01_k_rollout_config2.ncu.json')
+      if cfg['envs_per_gpu'] == 4096 and t_steps == 256 else None,
   }
 
   # -- the same kernel family with every SM filled (1Mi envs, one step) -------
@@ -485,7 +508,8 @@ def run_ours(args, cfg):
         'workload': '1Mi envs x 1 step per launch, same actions/adapter, '
                     '1 GPU',
         'kernel': 'pd::k_walk', 'value': big_n / (ms / 1e3), 'unit': UNIT,
-        'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak}
+        'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak,
+        'traffic': ncu_traffic('r01_k_walk_1Mi_1step.ncu.json')}
     del big
 
   # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
@@ -504,12 +528,18 @@ def run_ours(args, cfg):
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if sampler:  # the CPU leg is not a GPU region
+      clocks = sampler.stop(t0, time.perf_counter())
+      sampler = None
     from oracle import pdune_oracle as po
     rate_fn = po.RATE_PRIOR if args.rate == 'prior' else po.RATE_SIMPLE
     v, sample, _ = cpu_port_throughput(n, rate_fn, args.cpu_seconds, 1)
     cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
            'sample': sample}
 
+  # clocks over every timed GPU region of this run (value, e2e, at_scale ...)
+  if sampler:
+    clocks = sampler.stop(t0, time.perf_counter())
   if rank == 0:
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
