@@ -355,6 +355,9 @@ struct StepArgs {
   int64_t image_duration_us;
   int32_t material_frame;     // 1: apply_control (no observe phase)
   const uint8_t* skip;        // [n] or null: envs that sit this call out
+  int32_t lane_stride;        // 1 thread in `lane_stride` owns an env (k_step /
+                              // k_rollout; small batches trade idle lanes for
+                              // more warps and less intra-warp divergence)
   int32_t action_mode;        // pd_action_mode (rollouts)
   double max_distance;        // RelativeToSilicon adapter, angstroms
   pd_step_out out;

@@ -125,8 +125,11 @@ __global__ void __launch_bounds__(kStepThreads)
   const LogSink log{a.out.log_count ? a.out.log_capacity : 0,
                     a.out.log_elapsed_us, a.out.log_site, a.out.log_ctrl};
   const int64_t n = a.st.n_envs;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-       e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t gtid =
+      blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (gtid % a.lane_stride) return;  // after the cooperative table staging
+  for (int64_t e = gtid / a.lane_stride; e < n;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x / a.lane_stride) {
     if (a.skip && a.skip[e]) continue;
     EnvRegs r = load_env(tab, a, e);
     Fov4 fov = load_fov4(a.st.fov, e);
@@ -186,8 +189,11 @@ __global__ void __launch_bounds__(kStepThreads)
   }
   const LogSink log{0, nullptr, nullptr, nullptr};
   const int64_t n = a.st.n_envs;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-       e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t gtid =
+      blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (gtid % a.lane_stride) return;  // after the cooperative table staging
+  for (int64_t e = gtid / a.lane_stride; e < n;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x / a.lane_stride) {
     EnvRegs r = load_env(tab, a, e);
     Fov4 fov = load_fov4(a.st.fov, e);
     const double scale = a.st.fov_scale[e];
@@ -196,23 +202,51 @@ __global__ void __launch_bounds__(kStepThreads)
     // Software prefetch of the next control hides the HBM latency of the
     // action stream behind the current step's arithmetic.
     double2 next = reinterpret_cast<const double2*>(a.controls_xy)[e];
+    // The observed Si position q = (P_si - ll) / (ur - ll) feeds both the
+    // RelativeToSilicon adapter and the safe-area test; it only changes when
+    // the Si hops or the FOV is re-centred, so its four divisions (and the
+    // adapter's two) are redone only then.  The cached values are the exact
+    // same expressions, so results are unchanged.
+    const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
+    bool q_stale = true, check_area = true;
+    double2 q = make_double2(0.0, 0.0);
+    double rx = 0.0, ry = 0.0;
     for (int t = 0; t < a.n_steps; ++t) {
       const double2 ctl = next;
       if (t + 1 < a.n_steps)
         next = reinterpret_cast<const double2*>(
             a.controls_xy)[static_cast<int64_t>(t + 1) * n + e];
-      const double2 pos =
-          a.action_mode == PD_ACTION_RELATIVE_TO_SILICON
-              ? relative_to_silicon(fov, r.psi, ctl, a.max_distance)
-              : ctl;
+      double2 pos = ctl;
+      if (relative) {
+        if (q_stale) {
+          q = observe(fov, r.psi);
+          rx = __ddiv_rn(a.max_distance, __dsub_rn(fov.urx, fov.llx));
+          ry = __ddiv_rn(a.max_distance, __dsub_rn(fov.ury, fov.lly));
+          q_stale = false;
+        }
+        // action_adapters.py:163-188
+        const double ax = fmin(fmax(ctl.x, -1.0), 1.0);
+        const double ay = fmin(fmax(ctl.y, -1.0), 1.0);
+        pos.x = fmin(fmax(__dadd_rn(q.x, __dmul_rn(ax, rx)), 0.0), 1.0);
+        pos.y = fmin(fmax(__dadd_rn(q.y, __dmul_rn(ay, ry)), 0.0), 1.0);
+      }
       const double2 beam = microscope_to_material(fov, pos.x, pos.y);
+      const int hops_before = r.transitions;
       run_control<RATE>(tab, a.ra, a.st.seed, beam, a.dwell_us_scalar, 0, e,
                         log, &r);
       long long elapsed = a.dwell_us_scalar + a.image_duration_us;
-      if (silicon_outside_safe_area(fov, r.psi)) {
-        fov = centred_fov(r.psi, scale);
-        elapsed += a.image_duration_us;
-        fov_dirty = true;
+      if (r.transitions != hops_before) {
+        q_stale = true;
+        check_area = true;
+      }
+      if (check_area) {
+        check_area = false;
+        if (silicon_outside_safe_area(fov, r.psi)) {
+          fov = centred_fov(r.psi, scale);
+          elapsed += a.image_duration_us;
+          fov_dirty = true;
+          q_stale = true;
+        }
       }
       total += elapsed;
       if (a.si_idx_out) a.si_idx_out[static_cast<int64_t>(t) * n + e] = r.si;
@@ -586,15 +620,36 @@ static int grid_for(int64_t n_envs, bool staged) {
   return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// Small batches cannot fill the machine with one env per lane: every
+// scheduler would hold at most one warp and each warp would pay for its
+// slowest lane.  Giving an env to only one lane in `stride` multiplies the
+// number of warps (latency hiding) and divides the chance that a warp needs a
+// second KMC iteration; the idle lanes cost nothing the batch could have used.
+// Target: ~2.5 warps per scheduler (profiles/r01_kernel_choice.md).
+static int lane_stride_for(int64_t n_envs) {
+  static const int forced = [] {
+    const char* v = getenv("PD_LANE_STRIDE");
+    return v ? atoi(v) : 0;
+  }();
+  if (forced > 0) return forced;
+  const int64_t want_threads = static_cast<int64_t>(sm_count()) * 4 * 32 * 5 / 2;
+  int stride = 1;
+  while (stride < 32 && n_envs * stride * 2 <= want_threads) stride *= 2;
+  return stride;
+}
+
 template <int RATE>
-static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
+static int launch_step(const StepArgs& a_in, bool rollout,
+                       cudaStream_t stream) {
+  StepArgs a = a_in;
   const bool staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
-  const int grid = grid_for(a.st.n_envs, staged);
+  const bool walk = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads);
+  a.lane_stride = walk ? 1 : lane_stride_for(a.st.n_envs);
+  const int grid = grid_for(a.st.n_envs * a.lane_stride, staged);
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
-    auto kern = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads)
-                    ? k_walk<RATE, true, false>
+    auto kern = walk ? k_walk<RATE, true, false>
                 : rollout     ? k_rollout<RATE, true>
                               : k_step<RATE, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
@@ -602,7 +657,7 @@ static int launch_step(const StepArgs& a, bool rollout, cudaStream_t stream) {
         static_cast<int>(smem)));
     kern<<<grid, kStepThreads, smem, stream>>>(a);
   } else {
-    auto kern = walk_kernel(false) ? k_walk<RATE, false, false>
+    auto kern = walk ? k_walk<RATE, false, false>
                 : rollout     ? k_rollout<RATE, false>
                               : k_step<RATE, false>;
     kern<<<grid, kStepThreads, 0, stream>>>(a);
