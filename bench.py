@@ -60,7 +60,7 @@ def parse_args():
   ap.add_argument('--no-at-scale', action='store_true')
   ap.add_argument('--no-frames', action='store_true')
   ap.add_argument('--no-mlp', action='store_true')
-  ap.add_argument('--frames', type=int, default=296,
+  ap.add_argument('--frames', type=int, default=512,
                   help='frames per render launch (512x512)')
   ap.add_argument('--episodes', type=int, default=0,
                   help='total envs for the greedy-controller episode run '
@@ -271,7 +271,12 @@ def measure_frames(pd, batch, dev, peak, args):
   """Frames/s of pd_render (512x512, all noise stages + CLAHE)."""
   import torch
   from putting_dune_b200 import imaging
-  m = args.frames
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  n_cl = C.c_int32()
+  nat.check(nat.lib.pd_render_clusters(512, C.byref(n_cl)))
+  # whole waves of clusters (one 8-CTA cluster renders one frame at a time)
+  m = max(n_cl.value, (args.frames // n_cl.value) * n_cl.value)
   fb = pd.EnvBatch(m, seed=3, device=dev, lattice=batch.lattice_tables)
   fb.reset()
   out = torch.empty((m, 512, 512), dtype=torch.float32, device=dev)
@@ -290,7 +295,8 @@ def measure_frames(pd, batch, dev, peak, args):
   gbs = fps * 512 * 512 * 4 / 1e9
   return {'metric': 'STEM frames/sec', 'value': fps, 'unit': 'frames/s',
           'frames_per_launch': m, 'image_size': 512, 'launch_ms': ms,
-          'kernel': 'pd::k_render',
+          'kernel': 'pd::k_render_cluster',
+          'clusters_resident': n_cl.value, 'ctas_per_frame': 8,
           'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak,
                        'unit': 'GB/s', 'frac': gbs / peak,
                        'algorithmic_bytes_per_frame': 512 * 512 * 4}}

@@ -80,11 +80,26 @@ typedef struct pd_gmm {
 /* Philox stream ids (counter word 3). */
 #define PD_STREAM_KMC 0u
 #define PD_STREAM_RESET 1u
-#define PD_STREAM_RENDER_A 2u
-#define PD_STREAM_RENDER_B 3u
+#define PD_STREAM_RENDER_POISSON 2u
+#define PD_STREAM_RENDER_SP 3u
 #define PD_STREAM_JITTER 4u
 #define PD_STREAM_GOAL 5u
 #define PD_STREAM_AGENT 6u
+#define PD_STREAM_RENDER_UNIFORM 7u
+#define PD_STREAM_RENDER_EXP 8u
+#define PD_STREAM_RENDER_GAUSS 9u
+/* Renderer noise fields (counter = (env, frame_count, index, stream)): pixel
+ * p = row * S + col takes word p % 4 of the call with index p / 4;
+ * u24(w) = (w >> 8) * 2^-24.
+ *   RENDER_POISSON  Poisson(image * mult): smallest k with CDF(k) > u24(w),
+ *                   CDF by the float64 recurrence p_k = p_{k-1} * lam / k
+ *   RENDER_SP       flip if u24(w) <= amount; salt if (w & 255) < 128
+ *   RENDER_UNIFORM  + scale * u24(w)
+ *   RENDER_EXP      + -log1p(-u24(w)) * scale
+ *   RENDER_GAUSS    Box-Muller: words (0,1) -> pixels 4g, 4g+1; words (2,3) ->
+ *                   4g+2, 4g+3; r = sqrt(-2 ln(((wa >> 8) + 1) 2^-24)),
+ *                   t = 2 pi u24(wb); first pixel r cos t, second r sin t
+ *   JITTER          index = image row, word 0: Poisson(jitter_rate) as above */
 
 /* Shared lattice (graphene.py:464-559): device pointers, env-independent. */
 typedef struct pd_lattice {
@@ -425,13 +440,20 @@ typedef enum pd_render_stage {
  * of 256 B), independent of the number of frames. */
 int pd_render_workspace_bytes(int32_t image_size, int64_t* out_bytes);
 
+/* Frames the device renders concurrently: one thread-block cluster of eight
+ * CTAs (eight SMs) per frame; benchmarks size their batches as a multiple. */
+int pd_render_clusters(int32_t image_size, int32_t* out_clusters);
+
 /* Renders frames for envs env_ids[0..m) (device int32; NULL = envs 0..m-1).
  * frames_out: device float [m][image_size][image_size], values in [0, 1]
  * (the reference returns float64; pixels agree to float32 tolerance, see
  * DESIGN.md).  image_size: power of two in [64, 512].  stop_stage < FINAL
  * returns the image after that stage (parity tests).  advance_frame_count != 0
  * increments pd_state.frame_count of the rendered envs (the Philox sequence of
- * the noise fields). */
+ * the noise fields).  Frames with at most 1024 atoms in view, a clean-image
+ * kernel radius <= 128 px and blur_amount < 1.125 (everything imaging.py:42-72
+ * samples at FOV >= 7.5 A) stay in shared memory of an 8-CTA cluster; others
+ * take a slower one-CTA path through the workspace.  Same results. */
 int pd_render(const pd_lattice* lat, const pd_state* st, const int32_t* env_ids,
               int32_t m, int32_t image_size, int32_t stop_stage,
               int32_t advance_frame_count, float* frames_out, void* workspace,

@@ -52,11 +52,14 @@ GAMMA_PER_SECOND = 0.9967  # constants.py:35
 
 STREAM_KMC = 0
 STREAM_RESET = 1
-STREAM_RENDER_A = 2
-STREAM_RENDER_B = 3
+STREAM_RENDER_POISSON = 2
+STREAM_RENDER_SP = 3
 STREAM_JITTER = 4
 STREAM_GOAL = 5
 STREAM_AGENT = 6
+STREAM_RENDER_UNIFORM = 7
+STREAM_RENDER_EXP = 8
+STREAM_RENDER_GAUSS = 9
 
 RATE_SIMPLE = 0
 RATE_PRIOR = 1

@@ -17,17 +17,21 @@ Parity status
     range for these stages (imaging_test.py:51-78).
 
 Injected noise convention (one Philox4x32-10 call = four 32-bit words; counter
-= (env, frame, index, stream)); u24(w) = (w >> 8) * 2**-24:
+= (env, frame, index, stream)); u24(w) = (w >> 8) * 2**-24.  Every per-pixel
+field is laid out the same way: pixel p = row * S + col (of the array at that
+stage) takes word p % 4 of the call with index p // 4, so one call serves four
+consecutive pixels of a row:
 
-  stream 2 RENDER_A, index = pixel (row * S + col of the array at that stage):
-      w0 -> Poisson(image * mult) by inverse CDF on u24(w0)
-      w1 -> salt&pepper flip:  u24(w1) <= amount
-      w2 -> salt vs pepper:    u24(w2) <= 0.5
-      w3 -> uniform noise:     scale * u24(w3)
-  stream 3 RENDER_B, index = pixel // 2:
-      w0/w1 -> exponential noise of pixel 2j / 2j+1: -log1p(-u24(w)) * scale
-      w2, w3 -> Box-Muller pair: r = sqrt(-2 ln((w2>>8)+1)/2**24),
-                t = 2 pi u24(w3); pixel 2j gets r cos t, pixel 2j+1 r sin t
+  stream 2 RENDER_POISSON: Poisson(image * mult) by inverse CDF on u24(w)
+  stream 3 RENDER_SP:      salt&pepper flip: u24(w) <= amount; salt vs pepper
+                           from the low byte of the same word (independent of
+                           the 24 bits above): ((w & 255) + 0.5) / 256 <= 0.5
+  stream 7 RENDER_UNIFORM: uniform noise: scale * u24(w)
+  stream 8 RENDER_EXP:     exponential noise: -log1p(-u24(w)) * scale
+  stream 9 RENDER_GAUSS:   Box-Muller pairs: words (0, 1) serve pixels 4g and
+                           4g+1, words (2, 3) pixels 4g+2 and 4g+3:
+                           r = sqrt(-2 ln(((wa >> 8) + 1) / 2**24)),
+                           t = 2 pi u24(wb); first pixel r cos t, second r sin t
   stream 4 JITTER, index = row: w0 -> Poisson(jitter_rate) by inverse CDF.
 """
 
@@ -73,27 +77,24 @@ class RenderInjectedRng:
   def __init__(self, seed: int, env_id: int, frame: int, size: int = 512):
     self.seed, self.env, self.frame, self.size = seed, env_id, frame, size
     self._random_calls = 0
-    self._a = None
-    self._b = None
+    self._cache = {}
 
   def _words(self, stream, n):
     idx = np.arange(n, dtype=np.uint64)
     return po.philox4x32_10(np.uint32(self.env), np.uint32(self.frame), idx,
                             stream, self.seed & 0xFFFFFFFF, self.seed >> 32)
 
-  def _wa(self):
-    if self._a is None:
-      self._a = self._words(po.STREAM_RENDER_A, self.size * self.size)
-    return self._a
-
-  def _wb(self):
-    if self._b is None:
-      self._b = self._words(po.STREAM_RENDER_B, self.size * self.size // 2)
-    return self._b
+  def _field(self, stream):
+    """uint32 word per pixel, flat [S*S]: word p % 4 of call p // 4."""
+    if stream not in self._cache:
+      w = self._words(stream, self.size * self.size // 4)
+      self._cache[stream] = np.stack(
+          [np.asarray(x, dtype=np.uint32) for x in w], axis=1).reshape(-1)
+    return self._cache[stream]
 
   def poisson(self, lam, size=None):
     if np.ndim(lam) == 2:  # apply_poisson_noise, imaging.py:202
-      u = u24(self._wa()[0]).reshape(lam.shape)
+      u = u24(self._field(po.STREAM_RENDER_POISSON)).reshape(lam.shape)
       return poisson_icdf(lam, u)
     # apply_jitter, imaging.py:192
     w = self._words(po.STREAM_JITTER, int(size))
@@ -101,22 +102,26 @@ class RenderInjectedRng:
 
   def random(self, size=None):
     # skimage random_noise 's&p': two fields, flip then salt
-    w = self._wa()[1 + self._random_calls]
+    w = self._field(po.STREAM_RENDER_SP)
+    first = self._random_calls % 2 == 0
     self._random_calls += 1
-    return u24(w).reshape(size)
+    if first:
+      return u24(w).reshape(size)
+    return (((w & np.uint32(255)).astype(np.float64) + 0.5) /
+            256.0).reshape(size)
 
   def uniform(self, low=0.0, high=1.0, size=None):
-    return low + (high - low) * u24(self._wa()[3]).reshape(size)
+    return low + (high - low) * u24(
+        self._field(po.STREAM_RENDER_UNIFORM)).reshape(size)
 
   def exponential(self, scale=1.0, size=None):
-    wb = self._wb()
-    u = np.stack((u24(wb[0]), u24(wb[1])), axis=1).reshape(size)
+    u = u24(self._field(po.STREAM_RENDER_EXP)).reshape(size)
     return -np.log1p(-u) * np.float64(scale)
 
   def normal(self, loc=0.0, scale=1.0, size=None):
-    wb = self._wb()
-    r = np.sqrt(-2.0 * np.log(u24_open(wb[2])))
-    t = 2.0 * np.pi * u24(wb[3])
+    w = self._field(po.STREAM_RENDER_GAUSS).reshape(-1, 2)
+    r = np.sqrt(-2.0 * np.log(u24_open(w[:, 0])))
+    t = 2.0 * np.pi * u24(w[:, 1])
     z = np.stack((r * np.cos(t), r * np.sin(t)), axis=1).reshape(size)
     return loc + scale * z
 

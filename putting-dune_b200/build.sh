@@ -14,6 +14,7 @@ COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
 exact=(pd_lattice pd_reset pd_step pd_query)
 fast=(pd_api pd_mlp)
 [ -f "$src/pd_render.cu" ] && fast+=(pd_render)
+[ -f "$src/pd_render_cluster.cu" ] && fast+=(pd_render_cluster)
 [ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
 [ -f "$src/pd_env.cu" ] && exact+=(pd_env)
 pids=()
@@ -26,5 +27,5 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 objs=()
 for f in "${exact[@]}" "${fast[@]}"; do objs+=("$obj/$f.o"); done
-"$NVCC" -shared -o "$out/libpdune_b200.so" "${objs[@]}" -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libpdune_b200.so" "${objs[@]}" -lcudart
 echo "built $out/libpdune_b200.so"

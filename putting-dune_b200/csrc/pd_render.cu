@@ -1,11 +1,14 @@
-// K3: STEM frame renderer (imaging.py:117-265 generate_stem_image).
+// K3 (generic form): STEM frame renderer, imaging.py:117-265
+// generate_stem_image, and the pd_render entry point.
 //
-// One persistent CTA (1024 threads) renders one frame at a time and loops
-// over frames.  A frame goes through ten passes separated by the image-wide
-// reductions the reference performs (five "/ max", CLAHE min/max and tile
-// histograms); intermediate images live in a per-CTA scratch slot (2 x S*S
-// floats) that stays hot in the 126 MB L2, and only the final frame is
-// written to its HBM destination.
+// pd_render runs the cluster kernel (pd_render_cluster.cu) over all frames;
+// that kernel keeps a frame in the shared memory of eight CTAs and therefore
+// bounds the atoms in view (1024), the clean-image kernel radius (128 px) and
+// the blur radius (4 px = blur_amount < 1.125; imaging.py:42-72 samples
+// blur < 1).  Frames outside those bounds are flagged and rendered by the
+// kernel in this file: one CTA (1024 threads) per frame, ten passes separated
+// by the image-wide reductions, intermediates in a per-CTA global scratch slot
+// (2 x S*S floats).  Same arithmetic, same noise fields.
 //
 //   P0 setup     atoms in view (graphene.py:600-644) -> pixel bins and Z^e
 //                weights; Gaussian kernel tables; per-row jitter shifts
@@ -23,11 +26,9 @@
 //   P8 clahe-2   bilinear blend of the four neighbouring tile maps; min & max
 //   P9 output    rescale to [0, 1], write the frame
 //
-// Noise fields follow the injected convention documented in DESIGN.md and
-// include/pdune_b200.h (Philox streams 2, 3, 4).
-#include <math.h>
-
-#include "pd_common.cuh"
+// Noise fields follow the injected convention documented in
+// include/pdune_b200.h: one Philox call per four consecutive pixels and stage.
+#include "pd_render.cuh"
 
 namespace pd {
 
@@ -36,27 +37,9 @@ constexpr int kRenderWarps = kRenderThreads / 32;
 constexpr int kMaxAtoms = 2048;
 constexpr int kMaxRadius = 255;   // clean-image kernel radius (4 sigma)
 constexpr int kMaxBlurRadius = 16;
-constexpr int kTiles = 8;         // CLAHE kernel = shape // 8
-constexpr int kBins = 256;
-constexpr int kGray = 16384;      // NR_OF_GRAY
-constexpr int kBinSize = 1 + kGray / kBins;  // 65
 constexpr int kBands = 16;        // 512 / 32 row bands
 constexpr int kBandCap = 1024;
-constexpr int kInvTable = 256;
 constexpr int kUnroll = 4;        // independent loads per thread per trip
-
-struct RenderArgs {
-  pd_lattice lat;
-  pd_state st;
-  const int32_t* env_ids;
-  int32_t m;
-  int32_t size;        // S
-  int32_t log2_size;
-  int32_t stop_stage;
-  int32_t advance;
-  float* out;          // [m][S][S]
-  float* scratch;      // [grid][2][S][S]
-};
 
 struct RenderShared {
   short2 atom_rc[kMaxAtoms];   // (row, col) pixel of each atom
@@ -84,41 +67,6 @@ struct RenderShared {
   } u;
 };
 
-__device__ __forceinline__ float u24(uint32_t w) {
-  return static_cast<float>(w >> 8) * (1.0f / 16777216.0f);
-}
-
-__device__ __forceinline__ float u24_open(uint32_t w) {
-  return (static_cast<float>(w >> 8) + 1.0f) * (1.0f / 16777216.0f);
-}
-
-// Inverse-CDF Poisson: smallest k with CDF(k) > u (float64 recurrence).
-__device__ __forceinline__ int poisson_icdf(double lam, double u) {
-  double p = exp(-lam);
-  double cdf = p;
-  int k = 0;
-  while (u >= cdf && k < 100000) {
-    ++k;
-    p = p * lam / static_cast<double>(k);
-    cdf += p;
-  }
-  return k;
-}
-
-// Same recurrence with 1/k from a shared table (k < kInvTable).
-__device__ __forceinline__ int poisson_icdf_tab(double lam, double u,
-                                                const double* inv_k) {
-  double p = exp(-lam);
-  double cdf = p;
-  int k = 0;
-  while (u >= cdf && k < 100000) {
-    ++k;
-    p = p * lam * (k < kInvTable ? inv_k[k] : 1.0 / static_cast<double>(k));
-    cdf += p;
-  }
-  return k;
-}
-
 __device__ __forceinline__ float block_max(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -143,55 +91,8 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
   return i;
 }
 
-// skimage exposure/_adapthist.py clip_histogram + map_histogram, one tile.
-__device__ void clahe_tile_map(int* hist, unsigned short* map, int clim,
-                               int n_pixels) {
-  int n_excess = 0;
-  for (int i = 0; i < kBins; ++i)
-    if (hist[i] > clim) {
-      n_excess += hist[i] - clim;
-      hist[i] = clim;
-    }
-  const int bin_incr = n_excess / kBins;
-  const int upper = clim - bin_incr;
-  for (int i = 0; i < kBins; ++i)
-    if (hist[i] < upper) {
-      n_excess -= bin_incr;
-      hist[i] += bin_incr;
-    }
-  for (int i = 0; i < kBins; ++i)
-    if (hist[i] >= upper && hist[i] < clim) {
-      n_excess += hist[i] - clim;
-      hist[i] = clim;
-    }
-  while (n_excess > 0) {
-    const int prev = n_excess;
-    for (int index = 0; index < kBins; ++index) {
-      int n_under = 0;
-      for (int i = 0; i < kBins; ++i) n_under += hist[i] < clim;
-      int step = n_under / n_excess;
-      if (step < 1) step = 1;
-      int cnt = 0;
-      for (int i = index; i < kBins; i += step)
-        if (hist[i] < clim) {
-          ++hist[i];
-          ++cnt;
-        }
-      n_excess -= cnt;
-      if (n_excess <= 0) break;
-    }
-    if (prev == n_excess) break;
-  }
-  long long cum = 0;
-  for (int i = 0; i < kBins; ++i) {
-    cum += hist[i];
-    long long v = cum * (kGray - 1) / n_pixels;
-    map[i] = static_cast<unsigned short>(v > kGray - 1 ? kGray - 1 : v);
-  }
-}
-
 __global__ void __launch_bounds__(kRenderThreads, 1)
-    k_render(const RenderArgs a) {
+    k_render_generic(const RenderArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RenderShared& sh = *reinterpret_cast<RenderShared*>(smem_raw);
   const int tid = threadIdx.x;
@@ -207,7 +108,9 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
   for (int i = tid; i < kInvTable; i += kRenderThreads)
     sh.inv_k[i] = i > 0 ? 1.0 / static_cast<double>(i) : 0.0;
 
+  if (a.generic != nullptr && *a.n_generic == 0) return;
   for (int f = blockIdx.x; f < a.m; f += gridDim.x) {
+    if (a.generic != nullptr && a.generic[f] == 0) continue;
     const int e = a.env_ids ? a.env_ids[f] : f;
     const uint32_t env = a.st.env_offset + static_cast<uint32_t>(e);
     const uint32_t frame = a.st.frame_count[e];
@@ -425,20 +328,21 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float scale = poisson_mult / m_prev;
       vmax = 0.f;
       __syncthreads();
-      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
-        float v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) v[u] = cur[p0 + u * kRenderThreads];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int p = p0 + u * kRenderThreads;
-          const uint4 w =
-              philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
-          const float k = static_cast<float>(poisson_icdf_tab(
-              static_cast<double>(v[u] * scale), u24(w.x), sh.inv_k));
-          cur[p] = k;
-          vmax = fmaxf(vmax, k);
-        }
+      for (int g = tid; g < npix / 4; g += kRenderThreads) {
+        const float4 v = reinterpret_cast<const float4*>(cur)[g];
+        const uint4 w =
+            philox4x32_10(env, frame, g, PD_STREAM_RENDER_POISSON, seed);
+        float4 o;
+        o.x = static_cast<float>(poisson_icdf_tab(
+            static_cast<double>(v.x * scale), u24(w.x), sh.inv_k));
+        o.y = static_cast<float>(poisson_icdf_tab(
+            static_cast<double>(v.y * scale), u24(w.y), sh.inv_k));
+        o.z = static_cast<float>(poisson_icdf_tab(
+            static_cast<double>(v.z * scale), u24(w.z), sh.inv_k));
+        o.w = static_cast<float>(poisson_icdf_tab(
+            static_cast<double>(v.w * scale), u24(w.w), sh.inv_k));
+        reinterpret_cast<float4*>(cur)[g] = o;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
       }
       m_prev = block_max(vmax, sh.red_a);
     }
@@ -455,32 +359,33 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const bool jitter_only = a.stop_stage == PD_RENDER_JITTER;
       vmax = 0.f;
       __syncthreads();
-      for (int p0 = tid; p0 < npix; p0 += kUnroll * kRenderThreads) {
-        float vv[kUnroll];
+      for (int g = tid; g < npix / 4; g += kRenderThreads) {
+        const int p = 4 * g;
+        const int r = p >> a.log2_size, c0 = p & mask;
+        float vv[4];
+        // np.roll(row, k): out[(j + k) % S] = in[j]
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int p = p0 + u * kRenderThreads;
-          const int r = p >> a.log2_size, c = p & mask;
-          // np.roll(row, k): out[(j + k) % S] = in[j]
-          vv[u] = cur[r * S + ((c - sh.shift[r]) & mask)];
+        for (int j = 0; j < 4; ++j)
+          vv[j] = cur[r * S + ((c0 + j - sh.shift[r]) & mask)] * inv;
+        if (jitter_only) {
+          reinterpret_cast<float4*>(out)[g] =
+              make_float4(vv[0], vv[1], vv[2], vv[3]);
+          continue;
         }
+        const uint4 ws = philox4x32_10(env, frame, g, PD_STREAM_RENDER_SP, seed);
+        const uint4 wu =
+            philox4x32_10(env, frame, g, PD_STREAM_RENDER_UNIFORM, seed);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int p = p0 + u * kRenderThreads;
-          float v = vv[u] * inv;
-          if (jitter_only) {
-            out[p] = v;
-            continue;
-          }
-          const uint4 w =
-              philox4x32_10(env, frame, p, PD_STREAM_RENDER_A, seed);
-          if (u24(w.y) <= sp_amount) v = u24(w.z) <= 0.5f ? 1.0f : 0.0f;
-          v = fminf(fmaxf(v, 0.f), 1.f);
-          v = powf(v, gamma);
-          v += uniform_scale * u24(w.w);
-          other[p] = v;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t sw = word_of(ws, j);
+          float v = powf(fminf(fmaxf(vv[j], 0.f), 1.f), gamma);
+          if (u24(sw) <= sp_amount) v = (sw & 255u) < 128u ? 1.0f : 0.0f;
+          v += uniform_scale * u24(word_of(wu, j));
+          vv[j] = v;
           vmax = fmaxf(vmax, v);
         }
+        reinterpret_cast<float4*>(other)[g] =
+            make_float4(vv[0], vv[1], vv[2], vv[3]);
       }
       if (jitter_only) continue;
       m_prev = block_max(vmax, sh.red_a);
@@ -500,22 +405,15 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float inv = 1.0f / m_prev;
       vmax = 0.f;
       __syncthreads();
-      for (int j0 = tid; j0 < npix / 2; j0 += kUnroll * kRenderThreads) {
-        float2 vv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          vv[u] = reinterpret_cast<float2*>(cur)[j0 + u * kRenderThreads];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int j = j0 + u * kRenderThreads;
-          const uint4 w =
-              philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
-          float2 v = vv[u];
-          v.x = v.x * inv - log1pf(-u24(w.x)) * exp_lambda;
-          v.y = v.y * inv - log1pf(-u24(w.y)) * exp_lambda;
-          reinterpret_cast<float2*>(cur)[j] = v;
-          vmax = fmaxf(vmax, fmaxf(v.x, v.y));
-        }
+      for (int g = tid; g < npix / 4; g += kRenderThreads) {
+        float4 v = reinterpret_cast<const float4*>(cur)[g];
+        const uint4 w = philox4x32_10(env, frame, g, PD_STREAM_RENDER_EXP, seed);
+        v.x = v.x * inv - __logf(1.0f - u24(w.x)) * exp_lambda;
+        v.y = v.y * inv - __logf(1.0f - u24(w.y)) * exp_lambda;
+        v.z = v.z * inv - __logf(1.0f - u24(w.z)) * exp_lambda;
+        v.w = v.w * inv - __logf(1.0f - u24(w.w)) * exp_lambda;
+        reinterpret_cast<float4*>(cur)[g] = v;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
       }
       m_prev = block_max(vmax, sh.red_a);
     }
@@ -532,26 +430,24 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
       const float inv = 1.0f / m_prev;
       float lo = 1e30f, hi = -1e30f;
       __syncthreads();
-      for (int j0 = tid; j0 < npix / 2; j0 += kUnroll * kRenderThreads) {
-        float2 vv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          vv[u] = reinterpret_cast<float2*>(cur)[j0 + u * kRenderThreads];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const int j = j0 + u * kRenderThreads;
-          const uint4 w =
-              philox4x32_10(env, frame, j, PD_STREAM_RENDER_B, seed);
-          const float rad = sqrtf(-2.0f * logf(u24_open(w.z)));
-          float sn, cs;
-          sincospif(2.0f * u24(w.w), &sn, &cs);
-          float2 v = vv[u];
-          v.x = fminf(fmaxf(v.x * inv + gauss_sd * (rad * cs), 0.f), 1.f);
-          v.y = fminf(fmaxf(v.y * inv + gauss_sd * (rad * sn), 0.f), 1.f);
-          reinterpret_cast<float2*>(cur)[j] = v;
-          lo = fminf(lo, fminf(v.x, v.y));
-          hi = fmaxf(hi, fmaxf(v.x, v.y));
-        }
+      for (int g = tid; g < npix / 4; g += kRenderThreads) {
+        float4 v = reinterpret_cast<const float4*>(cur)[g];
+        const uint4 w =
+            philox4x32_10(env, frame, g, PD_STREAM_RENDER_GAUSS, seed);
+        const float ra = gauss_sd * sqrtf(-2.0f * __logf(u24_open(w.x)));
+        const float rb = gauss_sd * sqrtf(-2.0f * __logf(u24_open(w.z)));
+        float sa, ca, sb, cb;
+        __sincosf(fmaf(u24(w.y), 6.28318530717958648f, -3.14159265358979324f),
+                  &sa, &ca);
+        __sincosf(fmaf(u24(w.w), 6.28318530717958648f, -3.14159265358979324f),
+                  &sb, &cb);
+        v.x = fminf(fmaxf(v.x * inv - ra * ca, 0.f), 1.f);
+        v.y = fminf(fmaxf(v.y * inv - ra * sa, 0.f), 1.f);
+        v.z = fminf(fmaxf(v.z * inv - rb * cb, 0.f), 1.f);
+        v.w = fminf(fmaxf(v.w * inv - rb * sb, 0.f), 1.f);
+        reinterpret_cast<float4*>(cur)[g] = v;
+        lo = fminf(lo, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+        hi = fmaxf(hi, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
       }
       g_max = block_max(hi, sh.red_a);
       g_min = block_min(lo, sh.red_b);
@@ -670,12 +566,12 @@ __global__ void k_advance_frames(const pd_state st, const int32_t* env_ids,
 int validate_common(const pd_lattice* lat, const pd_state* st,
                     const pd_rate_config* rc);
 
-static int render_grid(int m) {
-  const int sms = sm_count();
-  return m < sms ? m : sms;
-}
-
 }  // namespace pd
+
+// Workspace layout: [0, 256) counter of generic frames; [256, 256 + 2^18)
+// per-frame flags; then kGenericGrid scratch slots of 2 S^2 floats.
+static const int64_t kFlagOffset = 256;
+static const int64_t kScratchOffset = 256 + pd::kMaxFramesPerLaunch;
 
 extern "C" int pd_render_workspace_bytes(int32_t image_size,
                                          int64_t* out_bytes) {
@@ -683,9 +579,20 @@ extern "C" int pd_render_workspace_bytes(int32_t image_size,
   PD_REQUIRE(image_size >= 64 && image_size <= 512 &&
                  (image_size & (image_size - 1)) == 0,
              "image_size must be a power of two in [64, 512]");
-  *out_bytes = static_cast<int64_t>(pd::sm_count()) * 2 * image_size *
-               image_size * sizeof(float);
+  *out_bytes = kScratchOffset + static_cast<int64_t>(pd::kGenericGrid) * 2 *
+                                    image_size * image_size * sizeof(float);
   return PD_OK;
+}
+
+extern "C" int pd_render_clusters(int32_t image_size, int32_t* out_clusters) {
+  PD_REQUIRE(out_clusters != nullptr, "null output");
+  PD_REQUIRE(image_size >= 64 && image_size <= 512 &&
+                 (image_size & (image_size - 1)) == 0,
+             "image_size must be a power of two in [64, 512]");
+  int n = 0;
+  const int rc = pd::render_cluster_count(image_size, &n);
+  *out_clusters = n;
+  return rc;
 }
 
 extern "C" int pd_render(const pd_lattice* lat, const pd_state* st,
@@ -699,36 +606,57 @@ extern "C" int pd_render(const pd_lattice* lat, const pd_state* st,
   PD_REQUIRE(env_ids != nullptr || m <= st->n_envs, "m exceeds n_envs");
   PD_REQUIRE(stop_stage >= PD_RENDER_CLEAN && stop_stage <= PD_RENDER_FINAL,
              "unknown stop_stage");
+  PD_REQUIRE(lat->n_sites <= 2 * pd::kRenderThreads,
+             "renderer supports lattices of at most 2048 sites");
   int64_t need = 0;
   rcode = pd_render_workspace_bytes(image_size, &need);
   if (rcode != PD_OK) return rcode;
   if (m == 0) return PD_OK;
   PD_REQUIRE(frames_out != nullptr && st->image_params && st->frame_count,
              "null frames / state arrays");
-  const int grid = pd::render_grid(m);
-  PD_REQUIRE(workspace != nullptr &&
-                 workspace_bytes >= static_cast<int64_t>(grid) * 2 *
-                                        image_size * image_size * 4,
+  PD_REQUIRE(workspace != nullptr && workspace_bytes >= need,
              "workspace too small (pd_render_workspace_bytes)");
-  pd::RenderArgs a{};
-  a.lat = *lat;
-  a.st = *st;
-  a.env_ids = env_ids;
-  a.m = m;
-  a.size = image_size;
-  a.log2_size = 0;
-  while ((1 << a.log2_size) < image_size) ++a.log2_size;
-  a.stop_stage = stop_stage;
-  a.advance = advance_frame_count;
-  a.out = frames_out;
-  a.scratch = static_cast<float*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int smem = static_cast<int>(sizeof(pd::RenderShared));
-  PD_CUDA_OK(cudaFuncSetAttribute(pd::k_render,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-  pd::k_render<<<grid, pd::kRenderThreads, smem, s>>>(a);
-  PD_CUDA_OK(cudaGetLastError());
+  char* ws = static_cast<char*>(workspace);
+  int log2_size = 0;
+  while ((1 << log2_size) < image_size) ++log2_size;
+  const size_t frame_floats = static_cast<size_t>(image_size) * image_size;
+  for (int32_t first = 0; first < m; first += pd::kMaxFramesPerLaunch) {
+    const int32_t count = m - first < pd::kMaxFramesPerLaunch
+                              ? m - first : pd::kMaxFramesPerLaunch;
+    pd::RenderArgs a{};
+    a.lat = *lat;
+    a.st = *st;
+    a.env_ids = env_ids ? env_ids + first : nullptr;
+    if (env_ids == nullptr && first > 0) {
+      // envs [first, first + count): shift the per-env arrays
+      a.st.env_offset += first;
+      a.st.si_idx += first;
+      a.st.lattice += 4 * static_cast<size_t>(first);
+      a.st.fov += 4 * static_cast<size_t>(first);
+      a.st.image_params += 9 * static_cast<size_t>(first);
+      a.st.frame_count += first;
+    }
+    a.m = count;
+    a.size = image_size;
+    a.log2_size = log2_size;
+    a.stop_stage = stop_stage;
+    a.advance = advance_frame_count;
+    a.out = frames_out + static_cast<size_t>(first) * frame_floats;
+    a.n_generic = reinterpret_cast<int32_t*>(ws);
+    a.generic = reinterpret_cast<uint8_t*>(ws + kFlagOffset);
+    a.scratch = reinterpret_cast<float*>(ws + kScratchOffset);
+    PD_CUDA_OK(cudaMemsetAsync(ws, 0, kFlagOffset + count, s));
+    rcode = pd::launch_render_cluster(a, s);
+    if (rcode != PD_OK) return rcode;
+    const int smem = static_cast<int>(sizeof(pd::RenderShared));
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        pd::k_render_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        smem));
+    const int grid = count < pd::kGenericGrid ? count : pd::kGenericGrid;
+    pd::k_render_generic<<<grid, pd::kRenderThreads, smem, s>>>(a);
+    PD_CUDA_OK(cudaGetLastError());
+  }
   if (advance_frame_count) {
     pd::k_advance_frames<<<(m + 255) / 256, 256, 0, s>>>(*st, env_ids, m);
     PD_CUDA_OK(cudaGetLastError());

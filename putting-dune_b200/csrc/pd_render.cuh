@@ -1,0 +1,273 @@
+// Shared pieces of the STEM frame renderers (pd_render.cu: generic one-CTA
+// kernel; pd_render_cluster.cu: the 8-CTA-cluster kernel that keeps the frame
+// in shared memory).  Reference: putting_dune/imaging.py:117-265.
+#pragma once
+
+#include <math.h>
+
+#include "pd_common.cuh"
+
+namespace pd {
+
+constexpr int kTiles = 8;         // CLAHE kernel = shape // 8
+constexpr int kBins = 256;
+constexpr int kGray = 16384;      // NR_OF_GRAY
+constexpr int kBinSize = 1 + kGray / kBins;  // 65
+constexpr int kInvTable = 256;
+constexpr int kMaxFramesPerLaunch = 1 << 18;  // flag bytes in the workspace
+constexpr int kGenericGrid = 16;  // CTAs (and scratch slots) of the generic kernel
+
+struct RenderArgs {
+  pd_lattice lat;
+  pd_state st;
+  const int32_t* env_ids;
+  int32_t m;
+  int32_t size;        // S
+  int32_t log2_size;
+  int32_t stop_stage;
+  int32_t advance;
+  float* out;          // [m][S][S]
+  float* scratch;      // generic kernel: [grid][2][S][S]
+  int32_t* n_generic;  // frames the cluster kernel handed to the generic one
+  uint8_t* generic;    // [m] 1 = render with the generic kernel
+};
+
+__device__ __forceinline__ float u24(uint32_t w) {
+  return static_cast<float>(w >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float u24_open(uint32_t w) {
+  return (static_cast<float>(w >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ uint32_t word_of(const uint4& w, int j) {
+  return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
+}
+
+// Inverse-CDF Poisson: smallest k with CDF(k) > u (float64 recurrence; the
+// injected-noise convention of include/pdune_b200.h).
+__device__ __forceinline__ int poisson_icdf(double lam, double u) {
+  double p = exp(-lam);
+  double cdf = p;
+  int k = 0;
+  while (u >= cdf && k < 100000) {
+    ++k;
+    p = p * lam / static_cast<double>(k);
+    cdf += p;
+  }
+  return k;
+}
+
+// Same recurrence with 1/k from a shared table (k < kInvTable).  p * lam / k
+// and p * lam * (1/k) may differ in the last bit of p; the comparison u >= cdf
+// only changes if u sits within ~1e-16 of a threshold (u has 24 bits).
+__device__ __forceinline__ int poisson_icdf_tab(double lam, double u,
+                                                const double* inv_k) {
+  double p = exp(-lam);
+  double cdf = p;
+  int k = 0;
+  while (u >= cdf && k < 100000) {
+    ++k;
+    p = p * lam * (k < kInvTable ? inv_k[k] : 1.0 / static_cast<double>(k));
+    cdf += p;
+  }
+  return k;
+}
+
+// Four inverse-CDF searches advanced in lockstep in float32.  The float32
+// CDF differs from the float64 one by < (4k + 3) * 2^-24; a search whose u
+// lies within eps(k) = 1e-6 (k + 4) of the two thresholds that decide it (or
+// that leaves the float32 range) is redone in float64, so the result always
+// equals poisson_icdf_tab's.
+__device__ __forceinline__ void poisson4(const float (&lam)[4],
+                                         const float (&u)[4],
+                                         const float* inv_kf,
+                                         const double* inv_kd, int (&k)[4]) {
+  float p[4], cdf[4], prev[4];
+  unsigned act = 0, redo = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k[j] = 0;
+    prev[j] = 0.f;
+    if (lam[j] > 60.f) {
+      redo |= 1u << j;
+      p[j] = 0.f;
+      cdf[j] = 2.f;
+    } else {
+      p[j] = expf(-lam[j]);
+      cdf[j] = p[j];
+      if (u[j] >= cdf[j]) act |= 1u << j;
+    }
+  }
+  int kk = 0;
+  while (act != 0 && kk < kInvTable - 1) {
+    ++kk;
+    const float ik = inv_kf[kk];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (act & (1u << j)) {
+        p[j] = p[j] * lam[j] * ik;
+        prev[j] = cdf[j];
+        cdf[j] += p[j];
+        k[j] = kk;
+        if (!(u[j] >= cdf[j])) act &= ~(1u << j);
+      }
+    }
+  }
+  redo |= act;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float eps = 1e-6f * static_cast<float>(k[j] + 4);
+    if (cdf[j] - u[j] < eps || (k[j] > 0 && u[j] - prev[j] < eps))
+      redo |= 1u << j;
+  }
+  if (redo != 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (redo & (1u << j))
+        k[j] = poisson_icdf_tab(static_cast<double>(lam[j]),
+                                static_cast<double>(u[j]), inv_kd);
+  }
+}
+
+// skimage exposure/_adapthist.py clip_histogram + map_histogram for one tile,
+// one thread.
+__device__ inline void clahe_tile_map(int* hist, unsigned short* map, int clim,
+                                      int n_pixels) {
+  int n_excess = 0;
+  for (int i = 0; i < kBins; ++i)
+    if (hist[i] > clim) {
+      n_excess += hist[i] - clim;
+      hist[i] = clim;
+    }
+  const int bin_incr = n_excess / kBins;
+  const int upper = clim - bin_incr;
+  for (int i = 0; i < kBins; ++i)
+    if (hist[i] < upper) {
+      n_excess -= bin_incr;
+      hist[i] += bin_incr;
+    }
+  for (int i = 0; i < kBins; ++i)
+    if (hist[i] >= upper && hist[i] < clim) {
+      n_excess += hist[i] - clim;
+      hist[i] = clim;
+    }
+  while (n_excess > 0) {
+    const int prev = n_excess;
+    for (int index = 0; index < kBins; ++index) {
+      int n_under = 0;
+      for (int i = 0; i < kBins; ++i) n_under += hist[i] < clim;
+      int step = n_under / n_excess;
+      if (step < 1) step = 1;
+      int cnt = 0;
+      for (int i = index; i < kBins; i += step)
+        if (hist[i] < clim) {
+          ++hist[i];
+          ++cnt;
+        }
+      n_excess -= cnt;
+      if (n_excess <= 0) break;
+    }
+    if (prev == n_excess) break;
+  }
+  long long cum = 0;
+  for (int i = 0; i < kBins; ++i) {
+    cum += hist[i];
+    long long v = cum * (kGray - 1) / n_pixels;
+    map[i] = static_cast<unsigned short>(v > kGray - 1 ? kGray - 1 : v);
+  }
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The same computation by one warp: lane l owns bins [8 l, 8 l + 8).
+__device__ inline void clahe_tile_map_warp(const int* hist,
+                                           unsigned short* map, int clim,
+                                           int n_pixels, int lane) {
+  int h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = hist[8 * lane + j];
+  int part = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (h[j] > clim) {
+      part += h[j] - clim;
+      h[j] = clim;
+    }
+  int n_excess = warp_sum(part);
+  const int bin_incr = n_excess / kBins;
+  const int upper = clim - bin_incr;
+  part = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (h[j] < upper) {
+      h[j] += bin_incr;
+      ++part;
+    }
+  n_excess -= warp_sum(part) * bin_incr;
+  part = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (h[j] >= upper && h[j] < clim) {
+      part += h[j] - clim;
+      h[j] = clim;
+    }
+  n_excess += warp_sum(part);
+  bool stuck = false;
+  while (n_excess > 0 && !stuck) {
+    const int prev = n_excess;
+    for (int index = 0; index < kBins; ++index) {
+      part = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part += h[j] < clim;
+      const int n_under = warp_sum(part);
+      if (n_under == 0) {  // nothing can change any more
+        stuck = true;
+        break;
+      }
+      int step = n_under / n_excess;
+      if (step < 1) step = 1;
+      part = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = 8 * lane + j;
+        if (i >= index && (i - index) % step == 0 && h[j] < clim) {
+          ++h[j];
+          ++part;
+        }
+      }
+      n_excess -= warp_sum(part);
+      if (n_excess <= 0) break;
+    }
+    if (prev == n_excess) break;
+  }
+  int run = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) run += h[j];
+  int incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  long long cum = incl - run;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cum += h[j];
+    const long long v = cum * (kGray - 1) / n_pixels;
+    map[8 * lane + j] =
+        static_cast<unsigned short>(v > kGray - 1 ? kGray - 1 : v);
+  }
+}
+
+// Launches the cluster kernel over frames [0, a.m); frames it cannot take
+// (more atoms in view / wider kernels than its shared-memory tables hold) are
+// flagged in a.generic for the generic kernel.
+int launch_render_cluster(const RenderArgs& a, cudaStream_t stream);
+int render_cluster_count(int image_size, int* out_clusters);
+
+}  // namespace pd
