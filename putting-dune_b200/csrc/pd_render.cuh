@@ -74,51 +74,55 @@ __device__ __forceinline__ int poisson_icdf_tab(double lam, double u,
   return k;
 }
 
-// Four inverse-CDF searches advanced in lockstep in float32.  The float32
-// CDF differs from the float64 one by < (4k + 3) * 2^-24; a search whose u
-// lies within eps(k) = 1e-6 (k + 4) of the two thresholds that decide it (or
-// that leaves the float32 range) is redone in float64, so the result always
-// equals poisson_icdf_tab's.
+// Four inverse-CDF searches in float32.  inv_k1[i] = 1 / (i + 1) (8-byte
+// aligned).  The float32 CDF differs from the float64 one by
+// < (4k + 3) * 2^-24; a search whose u lies within eps(k) = 1e-6 (k + 4) of
+// the two thresholds that decide it, or with lam > 60 (exp(-lam) leaves the
+// float32 range) or u > 0.9999 (the float32 sum may never reach it), is redone
+// in float64, so the result always equals poisson_icdf_tab's.
 __device__ __forceinline__ void poisson4(const float (&lam)[4],
                                          const float (&u)[4],
-                                         const float* inv_kf,
+                                         const float* inv_k1,
                                          const double* inv_kd, int (&k)[4]) {
-  float p[4], cdf[4], prev[4];
-  unsigned act = 0, redo = 0;
+  unsigned redo = 0;
+  const float2* tp = reinterpret_cast<const float2*>(inv_k1);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    const float l = lam[j], uu = u[j];
     k[j] = 0;
-    prev[j] = 0.f;
-    if (lam[j] > 60.f) {
+    if (!(l <= 60.f) || !(uu <= 0.9999f)) {
       redo |= 1u << j;
-      p[j] = 0.f;
-      cdf[j] = 2.f;
-    } else {
-      p[j] = expf(-lam[j]);
-      cdf[j] = p[j];
-      if (u[j] >= cdf[j]) act |= 1u << j;
+      continue;
     }
-  }
-  int kk = 0;
-  while (act != 0 && kk < kInvTable - 1) {
-    ++kk;
-    const float ik = inv_kf[kk];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (act & (1u << j)) {
-        p[j] = p[j] * lam[j] * ik;
-        prev[j] = cdf[j];
-        cdf[j] += p[j];
-        k[j] = kk;
-        if (!(u[j] >= cdf[j])) act &= ~(1u << j);
+    float p = expf(-l);
+    float cdf = p;
+    int kk = 0;
+    if (uu >= cdf) {
+      // two terms per trip: Poisson(60) passes 0.9999 before k = 100
+      for (int i2 = 0;;) {
+        const float2 ik = tp[i2];  // 1 / (2 i2 + 1), 1 / (2 i2 + 2)
+        const float r1 = l * ik.x, r2 = l * ik.y;
+        const float c1 = fmaf(p, r1, cdf);
+        const float p1 = p * r1;
+        if (!(uu >= c1)) {
+          kk = 2 * i2 + 1;
+          p = p1;
+          cdf = c1;
+          break;
+        }
+        cdf = fmaf(p1, r2, c1);
+        p = p1 * r2;
+        ++i2;
+        if (!(uu >= cdf) || i2 >= kInvTable / 2) {
+          kk = 2 * i2;
+          break;
+        }
       }
     }
-  }
-  redo |= act;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float eps = 1e-6f * static_cast<float>(k[j] + 4);
-    if (cdf[j] - u[j] < eps || (k[j] > 0 && u[j] - prev[j] < eps))
+    k[j] = kk;
+    const float eps = 1e-6f * static_cast<float>(kk + 4);
+    // the thresholds that decided: cdf(kk - 1) = cdf - p (<= u) and cdf(kk)
+    if (!(cdf - uu >= eps) || (kk > 0 && !(uu - (cdf - p) >= eps)))
       redo |= 1u << j;
   }
   if (redo != 0) {
@@ -232,13 +236,16 @@ __device__ inline void clahe_tile_map_warp(const int* hist,
       int step = n_under / n_excess;
       if (step < 1) step = 1;
       part = 0;
+      // bins index, index + step, ...: offset of this lane's first bin
+      int r = 8 * lane - index;
+      r = r >= 0 ? r % step : (step - (-r) % step) % step;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = 8 * lane + j;
-        if (i >= index && (i - index) % step == 0 && h[j] < clim) {
+        if (8 * lane + j >= index && r == 0 && h[j] < clim) {
           ++h[j];
           ++part;
         }
+        r = r + 1 == step ? 0 : r + 1;
       }
       n_excess -= warp_sum(part);
       if (n_excess <= 0) break;
@@ -254,11 +261,13 @@ __device__ inline void clahe_tile_map_warp(const int* hist,
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  long long cum = incl - run;
+  // n_pixels = ts^2 is a power of two <= 4096: cum * 16383 fits 32 bits
+  const int sh_px = 31 - __clz(n_pixels);
+  int cum = incl - run;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     cum += h[j];
-    const long long v = cum * (kGray - 1) / n_pixels;
+    const int v = (cum * (kGray - 1)) >> sh_px;
     map[8 * lane + j] =
         static_cast<unsigned short>(v > kGray - 1 ? kGray - 1 : v);
   }

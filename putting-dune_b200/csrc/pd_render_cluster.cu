@@ -35,6 +35,23 @@ namespace cg = cooperative_groups;
 
 namespace pd {
 
+// -DPD_RENDER_PHASE_CLOCKS: thread 0 of every CTA adds the cycles spent up to
+// each phase boundary into RenderArgs::scratch (as long long [grid][16]);
+// profiles/prof_render_phases.py reads them.  Off in the product build.
+#ifdef PD_RENDER_PHASE_CLOCKS
+#define PD_PHASE(i)                                                   \
+  do {                                                                \
+    if (tid == 0) {                                                   \
+      const long long now_ = clock64();                               \
+      reinterpret_cast<long long*>(a.scratch)[blockIdx.x * 16 + (i)] += \
+          now_ - phase_t0;                                            \
+      phase_t0 = now_;                                                \
+    }                                                                 \
+  } while (0)
+#else
+#define PD_PHASE(i) do { } while (0)
+#endif
+
 constexpr int kCluster = 8;          // CTAs per frame = CLAHE tile rows
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
@@ -58,7 +75,7 @@ struct ClusterShared {
   // one of the four copies
   __align__(16) float kys[4][kKyLen];
   float kb[kHalo + 1];
-  float inv_kf[kInvTable];
+  __align__(8) float inv_k1[kInvTable];  // 1 / (i + 1)
   double inv_kd[kInvTable];
   float pow_tab[kPowTab];
   int shift[64];
@@ -66,6 +83,8 @@ struct ClusterShared {
   float red[2][kWarps];
   float cred[2][kStages][2][kCluster];  // [frame parity][stage][value][src]
   int n_atoms, lwy, lwx, lwb;
+  int work[2];                       // dynamic tile / chunk counters (P1, P3)
+  double tab_sum[12];                // partial sums of the Gaussian tables
   int hist[kTiles][kBins];
   unsigned short maps[3][kTiles][kBins];  // tile rows rank-1, rank, rank+1
 };
@@ -145,22 +164,41 @@ __device__ __forceinline__ void emit_band(Ctx& c, float4* band4, int n_groups,
   }
 }
 
+// Vertical pass of the blur, in place.  A thread owns `rows` consecutive rows
+// of one column: the originals it needs from above (R rows) stay in its
+// register window, the R originals below its range -- which the thread that
+// owns the next range overwrites -- are fetched before the barrier.
 template <int R>
-__device__ __forceinline__ void blur_vertical(float* img, int S, int rows,
-                                              const float* kb, int col) {
-  // img row j <-> image row r0 - kHalo + j; outputs rows [kHalo, kHalo+rows)
-  float w[2 * R + 1];
+__device__ __forceinline__ void blur_vertical(float* img, int S, int first,
+                                              int rows, const float* kb,
+                                              int col, bool on) {
+  // img row j <-> image row r0 - kHalo + j; outputs rows [first, first+rows)
+  float w[2 * R + 1], tail[R];
+  const float* kk = kb;
+  if (on) {
 #pragma unroll
-  for (int i = 0; i < 2 * R; ++i) w[i] = img[(kHalo - R + i) * S + col];
-  float kk[R + 1];
+    for (int i = 0; i < 2 * R; ++i) w[i] = img[(first - R + i) * S + col];
 #pragma unroll
-  for (int i = 0; i <= R; ++i) kk[i] = kb[i];
-  for (int j = 0; j < rows; ++j) {
-    w[2 * R] = img[(kHalo + j + R) * S + col];
+    for (int i = 0; i < R; ++i) tail[i] = img[(first + rows + i) * S + col];
+  }
+  __syncthreads();
+  if (!on) return;
+  for (int j = 0; j < rows - R; ++j) {
+    w[2 * R] = img[(first + j + R) * S + col];
     float s = kk[0] * w[R];
 #pragma unroll
     for (int k = 1; k <= R; ++k) s += kk[k] * (w[R - k] + w[R + k]);
-    img[(kHalo + j) * S + col] = s;
+    img[(first + j) * S + col] = s;
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i) w[i] = w[i + 1];
+  }
+#pragma unroll
+  for (int t = 0; t < R; ++t) {
+    w[2 * R] = tail[t];
+    float s = kk[0] * w[R];
+#pragma unroll
+    for (int k = 1; k <= R; ++k) s += kk[k] * (w[R - k] + w[R + k]);
+    img[(first + rows - R + t) * S + col] = s;
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) w[i] = w[i + 1];
   }
@@ -184,6 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int r0 = rank * B;
   const int n_groups = B * S / 4;       // float4 groups of the band
   const int groups_per_row = S / 4;
+  const int log2_gpr = a.log2_size - 2;
+  const int gpr_mask = groups_per_row - 1;
   const uint32_t g_base = static_cast<uint32_t>(r0) * groups_per_row;
   float4* band4 = reinterpret_cast<float4*>(img + kHalo * S);
   float* band = img + kHalo * S;
@@ -193,9 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   for (int i = tid; i < kInvTable; i += kThreads) {
     sh.inv_kd[i] = i > 0 ? 1.0 / static_cast<double>(i) : 0.0;
-    sh.inv_kf[i] = i > 0 ? 1.0f / static_cast<float>(i) : 0.f;
+    sh.inv_k1[i] = 1.0f / static_cast<float>(i + 1);
   }
 
+#ifdef PD_RENDER_PHASE_CLOCKS
+  long long phase_t0 = clock64();
+#endif
   for (int f = cluster_id; f < a.m; f += n_clusters) {
     const int e = a.env_ids ? a.env_ids[f] : f;
     const uint32_t env = a.st.env_offset + static_cast<uint32_t>(e);
@@ -217,61 +260,114 @@ __global__ void __launch_bounds__(kThreads, 1)
     float* out = a.out + static_cast<size_t>(f) * S * S +
                  static_cast<size_t>(r0) * S;
     __syncthreads();
+    PD_PHASE(10);
 
     // ---------------------------------------------------------------- P0
     const double fw = fv.urx - fv.llx, fh = fv.ury - fv.lly;
     int n_total;
     {
-      const float w_c = powf(6.0f, exponent), w_si = powf(14.0f, exponent);
+      // (a) which lattice sites are in view (graphene.py:600-644): the test
+      //     only; bins are computed after compaction
       bool keep[2];
-      uint32_t rc[2];
-      float wt[2];
 #pragma unroll
       for (int round = 0; round < 2; ++round) {
         const int k = round * kThreads + tid;
         keep[round] = false;
-        rc[round] = 0;
-        wt[round] = 0.f;
         if (k < a.lat.n_sites) {
           const double2 p = site_position(__ldg(base + k), lt);
-          if (fv.llx <= p.x && p.x <= fv.urx && fv.lly <= p.y &&
-              p.y <= fv.ury) {
-            const double qx = (p.x - fv.llx) / fw, qy = (p.y - fv.lly) / fh;
-            int bx = static_cast<int>(floor(qx * S));
-            int by = static_cast<int>(floor(qy * S));
-            if (bx > S - 1) bx = S - 1;  // q == 1 falls in the last bin
-            if (by > S - 1) by = S - 1;
-            keep[round] = true;
-            rc[round] = (static_cast<uint32_t>(S - 1 - by) << 16) |
-                        static_cast<uint32_t>(bx);
-            wt[round] = k == si ? w_si : w_c;
-          }
+          keep[round] = fv.llx <= p.x && p.x <= fv.urx && fv.lly <= p.y &&
+                        p.y <= fv.ury;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep[round]);
         if (lane == 0) sh.warp_count[round][warp] = __popc(m);
       }
-      if (tid == 0) {
-        const double sy = S / (2.15 * fw), sx = S / (2.15 * fh);
-        sh.lwy = static_cast<int>(4.0 * sy + 0.5);
-        sh.lwx = static_cast<int>(4.0 * sx + 0.5);
-        sh.lwb = blur_amount > 1e-15 ? static_cast<int>(4.0 * blur_amount + 0.5)
-                                     : -1;
+      // (b) meanwhile twelve warps start the Gaussian tables
+      //     w[x] = exp(-0.5 x^2 / sigma^2) / sum (scipy _gaussian_kernel1d
+      //     with radius int(4 sigma + 0.5)), four warps per table, and two
+      //     more draw the per-row jitter shifts (imaging.py:192)
+      double tab_v = 0.0, tab_v128 = 0.0;
+      const int tw = warp - (kWarps - 12);
+      const int which = tw >> 2;  // 0: rows, 1: columns, 2: blur
+      if (tw >= 0) {
+        // rows use the FOV width, columns its height (imaging.py:159-160)
+        const double sigma = which == 0 ? S / (2.15 * fw)
+                             : which == 1 ? S / (2.15 * fh) : blur_amount;
+        int lw = static_cast<int>(4.0 * sigma + 0.5);
+        if (which == 2 && !(blur_amount > 1e-15)) lw = -1;
+        const int x = lane + 32 * (tw & 3);
+        if (x == 0) (which == 0 ? sh.lwy : which == 1 ? sh.lwx : sh.lwb) = lw;
+        if (which == 0)
+          for (int i = x; i < 4 * kKyLen; i += 128) (&sh.kys[0][0])[i] = 0.f;
+        if (which == 2 && x <= kHalo) sh.kb[x] = 0.f;
+        const double a2 = -0.5 / (sigma * sigma);
+        if (x <= lw) tab_v = exp(a2 * x * x);
+        if (x == 0 && lw >= 128) tab_v128 = exp(a2 * 128.0 * 128.0);
+        double part = (x == 0 ? tab_v : 2.0 * tab_v) + 2.0 * tab_v128;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sh.tab_sum[tw] = part;
+      } else if (tid < B) {
+        const uint4 w =
+            philox4x32_10(env, frame, r0 + tid, PD_STREAM_JITTER, seed);
+        sh.shift[tid] = poisson_icdf_tab(jitter_rate, u24(w.x), sh.inv_kd) & mask;
       }
-      for (int i = tid; i < 4 * kKyLen; i += kThreads)
-        (&sh.kys[0][0])[i] = 0.f;
-      if (tid <= kHalo) sh.kb[tid] = 0.f;
       __syncthreads();
-      int off0 = 0, off1 = 0, total = 0;
-      for (int w2 = 0; w2 < kWarps; ++w2) {
-        if (w2 == warp) off0 = total;
-        total += sh.warp_count[0][w2];
+      PD_PHASE(11);
+      if (tw >= 0) {
+        const int lw = which == 0 ? sh.lwy : which == 1 ? sh.lwx : sh.lwb;
+        const int cap = which == 2 ? kHalo : kFastRadius;
+        if (lw >= 0 && lw <= cap) {
+          const double inv = 1.0 / (sh.tab_sum[4 * which] +
+                                    sh.tab_sum[4 * which + 1] +
+                                    sh.tab_sum[4 * which + 2] +
+                                    sh.tab_sum[4 * which + 3]);
+          const int x0 = lane + 32 * (tw & 3);
+#pragma unroll
+          for (int rep = 0; rep < 2; ++rep) {
+            const int x = rep == 0 ? x0 : 128;
+            if (rep == 1 && (x0 != 0 || lw < 128)) break;
+            if (x > lw) break;
+            const float t =
+                static_cast<float>((rep == 0 ? tab_v : tab_v128) * inv);
+            if (which == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                // padded index of offset d is d + kKyHalf
+                const int ip_ = kKyHalf + x - q, im_ = kKyHalf - x - q;
+                if (ip_ >= 0) sh.kys[q][ip_] = t;
+                if (im_ >= 0) sh.kys[q][im_] = t;
+              }
+            } else if (which == 1) {
+              sh.kx[x] = t;
+            } else {
+              sh.kb[x] = t;
+            }
+          }
+        }
       }
-      for (int w2 = 0; w2 < kWarps; ++w2) {
-        if (w2 == warp) off1 = total;
-        total += sh.warp_count[1][w2];
+      // (c) offsets of every warp's survivors, in site order
+      if (warp == 0) {
+        const int c0 = sh.warp_count[0][lane], c1 = sh.warp_count[1][lane];
+        int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t0 = __shfl_up_sync(0xffffffffu, i0, o);
+          const int t1 = __shfl_up_sync(0xffffffffu, i1, o);
+          if (lane >= o) {
+            i0 += t0;
+            i1 += t1;
+          }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        const int tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        sh.warp_count[0][lane] = i0 - c0;
+        sh.warp_count[1][lane] = tot0 + i1 - c1;
+        if (lane == 0) sh.n_atoms = tot0 + tot1;
       }
-      n_total = total;
-      const bool fast = total <= kFastAtoms && sh.lwy <= kFastRadius &&
+      __syncthreads();
+      n_total = sh.n_atoms;
+      const bool fast = n_total <= kFastAtoms && sh.lwy <= kFastRadius &&
                         sh.lwx <= kFastRadius && sh.lwb <= kHalo;
       if (!fast) {  // same decision in all eight CTAs
         if (rank == 0 && tid == 0) {
@@ -280,59 +376,37 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         continue;
       }
+      unsigned short* site_list = &sh.strip[0][0];  // free until the strips
 #pragma unroll
       for (int round = 0; round < 2; ++round) {
         const unsigned m = __ballot_sync(0xffffffffu, keep[round]);
-        const int pos = (round == 0 ? off0 : off1) +
+        const int pos = sh.warp_count[round][warp] +
                         __popc(m & ((1u << lane) - 1u));
         if (keep[round])
-          sh.atoms[pos] = make_uint2(rc[round], __float_as_uint(wt[round]));
+          site_list[pos] = static_cast<unsigned short>(round * kThreads + tid);
       }
-      // Gaussian tables: w[x] = exp(-0.5 x^2 / sigma^2) / sum (scipy
-      // _gaussian_kernel1d with radius int(4 sigma + 0.5)).
-      if (warp < 3) {
-        const double sigma = warp == 0 ? S / (2.15 * fw)
-                             : warp == 1 ? S / (2.15 * fh) : blur_amount;
-        const int lw = warp == 0 ? sh.lwy : warp == 1 ? sh.lwx : sh.lwb;
-        if (lw >= 0) {
-          double sum = 0.0;
-          for (int x = lane; x <= lw; x += 32) {
-            const double v = exp(-0.5 / (sigma * sigma) * x * x);
-            sum += x == 0 ? v : 2.0 * v;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          for (int x = lane; x <= lw; x += 32) {
-            const float v = static_cast<float>(
-                exp(-0.5 / (sigma * sigma) * x * x) / sum);
-            if (warp == 0) {
-#pragma unroll
-              for (int s = 0; s < 4; ++s) {
-                // padded index of offset d is d + kKyHalf
-                const int ip_ = kKyHalf + x - s, im_ = kKyHalf - x - s;
-                if (ip_ >= 0) sh.kys[s][ip_] = v;
-                if (im_ >= 0) sh.kys[s][im_] = v;
-              }
-            } else if (warp == 1) {
-              sh.kx[x] = v;
-            } else {
-              sh.kb[x] = v;
-            }
-          }
-        }
-      }
-      // per-row jitter shifts (imaging.py:192)
-      if (tid < B) {
-        const uint4 w =
-            philox4x32_10(env, frame, r0 + tid, PD_STREAM_JITTER, seed);
-        sh.shift[tid] = poisson_icdf(jitter_rate, u24(w.x)) & mask;
+      __syncthreads();
+      // (d) pixel bins and Z^e weights of the atoms in view
+      if (tid < n_total) {
+        const int k = site_list[tid];
+        const double2 p = site_position(__ldg(base + k), lt);
+        const double qx = (p.x - fv.llx) / fw, qy = (p.y - fv.lly) / fh;
+        int bx = static_cast<int>(floor(qx * S));
+        int by = static_cast<int>(floor(qy * S));
+        if (bx > S - 1) bx = S - 1;  // q == 1 falls in the last bin
+        if (by > S - 1) by = S - 1;
+        const float wt = powf(k == si ? 14.0f : 6.0f, exponent);
+        sh.atoms[tid] = make_uint2((static_cast<uint32_t>(S - 1 - by) << 16) |
+                                       static_cast<uint32_t>(bx),
+                                   __float_as_uint(wt));
       }
       if (tid == 0) {
-        sh.n_atoms = total;
+        sh.work[0] = 0;
+        sh.work[1] = 0;
         bulk_store_wait_read();  // the previous frame has left the band
       }
       __syncthreads();
+      PD_PHASE(12);
     }
     const int n_atoms = n_total;
     const int lwy = sh.lwy, lwx = sh.lwx, lwb = sh.lwb;
@@ -363,22 +437,27 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     __syncthreads();
 
+    PD_PHASE(0);
     // ---------------------------------------------------------------- P1
     float vmax = 0.f;
     {
-      const int n_rg = kWarps / n_strips;
+      // tiles of 32 columns x kAcc rows, handed to the warps dynamically
+      // (strips differ in how many atoms reach them)
       const int rows_total = B + 2 * hb;
-      const int rows_per_rg = (rows_total + n_rg - 1) / n_rg;
-      const int strip = warp % n_strips, rg = warp / n_strips;
       const int jb_first = kHalo - hb;
-      const int jb0 = jb_first + rg * rows_per_rg;
-      int jb1 = jb0 + rows_per_rg;
-      if (jb1 > jb_first + rows_total) jb1 = jb_first + rows_total;
-      const int col = strip * 32 + lane;
-      const int cnt = sh.strip_n[strip];
-      const bool listed = cnt <= kStripCap;
-      const int n_list = listed ? cnt : n_atoms;
-      for (int j0 = jb0; j0 < jb1; j0 += kAcc) {
+      const int jb1 = jb_first + rows_total;
+      const int n_tiles = n_strips * ((rows_total + kAcc - 1) / kAcc);
+      for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&sh.work[0], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        const int strip = t % n_strips;
+        const int j0 = jb_first + (t / n_strips) * kAcc;
+        const int col = strip * 32 + lane;
+        const int cnt = sh.strip_n[strip];
+        const bool listed = cnt <= kStripCap;
+        const int n_list = listed ? cnt : n_atoms;
         const int img_r0 = r0 - kHalo + j0;  // image row of acc[0]
         float acc[kAcc];
 #pragma unroll
@@ -426,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(1);
     // ---------------------------------------------------------------- P2
     // gaussian_filter(image / max, blur, mode='reflect'): axis 0 then axis 1
     // (a radius-0 kernel is [1.0]: the identity).
@@ -441,12 +521,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         __syncthreads();
       }
-      if (tid < S) {
+      {
+        // parts x S threads, each at least kHalo rows
+        int parts = kThreads / S;
+        if (parts > B / kHalo) parts = B / kHalo;
+        const int rows = B / parts;
+        const int part = tid / S, col = tid & mask;
+        const bool on = part < parts;
+        const int first = kHalo + part * rows;
         switch (lwb) {
-          case 1: blur_vertical<1>(img, S, B, sh.kb, tid); break;
-          case 2: blur_vertical<2>(img, S, B, sh.kb, tid); break;
-          case 3: blur_vertical<3>(img, S, B, sh.kb, tid); break;
-          default: blur_vertical<4>(img, S, B, sh.kb, tid); break;
+          case 1: blur_vertical<1>(img, S, first, rows, sh.kb, col, on); break;
+          case 2: blur_vertical<2>(img, S, first, rows, sh.kb, col, on); break;
+          case 3: blur_vertical<3>(img, S, first, rows, sh.kb, col, on); break;
+          default: blur_vertical<4>(img, S, first, rows, sh.kb, col, on); break;
         }
       }
       __syncthreads();
@@ -454,17 +541,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int g0 = 0; g0 < n_groups; g0 += kThreads) {
         const int g = g0 + tid;
         const bool on = g < n_groups;
-        float x[4 + 2 * kHalo];
-        int rowo = 0, cg0 = 0;
+        float x[4 + 2 * kHalo];  // columns cg0 - 4 .. cg0 + 7 (kHalo == 4)
         if (on) {
-          rowo = (g / groups_per_row) * S;
-          cg0 = (g % groups_per_row) * 4;
-#pragma unroll
-          for (int i = 0; i < 4 + 2 * kHalo; ++i) {
-            int cc = cg0 - kHalo + i;
-            cc = cc < 0 ? -cc - 1 : cc >= S ? 2 * S - 1 - cc : cc;
-            x[i] = band[rowo + cc];
-          }
+          const int gc = g & gpr_mask;
+          const float4 own = band4[g];
+          // scipy 'reflect' at the row ends: d c b a | a b c d | d c b a
+          const float4 rev = make_float4(own.w, own.z, own.y, own.x);
+          const float4 lft = gc == 0 ? rev : band4[g - 1];
+          const float4 rgt = gc == gpr_mask ? rev : band4[g + 1];
+          x[0] = lft.x; x[1] = lft.y; x[2] = lft.z; x[3] = lft.w;
+          x[4] = own.x; x[5] = own.y; x[6] = own.z; x[7] = own.w;
+          x[8] = rgt.x; x[9] = rgt.y; x[10] = rgt.z; x[11] = rgt.w;
         }
         __syncthreads();
         if (on) {
@@ -489,25 +576,45 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(2);
     // ---------------------------------------------------------------- P3
     {
       const float scale = poisson_mult / m_prev;
       vmax = 0.f;
-      for (int g = tid; g < n_groups; g += kThreads) {
-        const float4 v = band4[g];
-        const uint4 w =
-            philox4x32_10(env, frame, g_base + g, PD_STREAM_RENDER_POISSON,
-                          seed);
-        const float lam[4] = {v.x * scale, v.y * scale, v.z * scale,
-                              v.w * scale};
-        const float u[4] = {u24(w.x), u24(w.y), u24(w.z), u24(w.w)};
-        int k[4];
-        poisson4(lam, u, sh.inv_kf, sh.inv_kd, k);
-        const float4 o = make_float4(
-            static_cast<float>(k[0]), static_cast<float>(k[1]),
-            static_cast<float>(k[2]), static_cast<float>(k[3]));
-        band4[g] = o;
-        vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+      // 128-pixel chunks, handed to the warps dynamically (the search length
+      // follows the brightness); a CTA that runs out of chunks takes chunks of
+      // the other bands of the frame through distributed shared memory
+      const int n_chunks = n_groups / 32;
+      for (int hop = 0; hop < kCluster; ++hop) {
+        const int owner = (rank + hop) & (kCluster - 1);
+        int* ctr = hop == 0 ? &sh.work[1]
+                            : c.cl.map_shared_rank(&sh.work[1], owner);
+        float4* b4 = hop == 0 ? band4 : c.cl.map_shared_rank(band4, owner);
+        const uint32_t gb = static_cast<uint32_t>(owner * B) * groups_per_row;
+        for (;;) {
+          int t = 0;
+          if (lane == 0) t = atomicAdd(ctr, 1);
+          t = __shfl_sync(0xffffffffu, t, 0);
+          if (t >= n_chunks) break;
+          // chunk t = a 16-column x 8-row patch (smaller than the atom
+          // spacing), so the 128 searches of a warp have similar lengths
+          const int g = (((t >> (a.log2_size - 4)) * 8 + (lane >> 2))
+                         << log2_gpr) +
+                        (t & ((S >> 4) - 1)) * 4 + (lane & 3);
+          const float4 v = b4[g];
+          const uint4 w = philox4x32_10(env, frame, gb + g,
+                                        PD_STREAM_RENDER_POISSON, seed);
+          const float lam[4] = {v.x * scale, v.y * scale, v.z * scale,
+                                v.w * scale};
+          const float u[4] = {u24(w.x), u24(w.y), u24(w.z), u24(w.w)};
+          int k[4];
+          poisson4(lam, u, sh.inv_k1, sh.inv_kd, k);
+          const float4 o = make_float4(
+              static_cast<float>(k[0]), static_cast<float>(k[1]),
+              static_cast<float>(k[2]), static_cast<float>(k[3]));
+          b4[g] = o;
+          vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+        }
       }
       m_prev = frame_max2(c, vmax, 0.f, 2).x;
     }
@@ -517,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(3);
     // ---------------------------------------------------------------- P4
     {
       const float inv = 1.0f / m_prev;
@@ -533,8 +641,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const bool on = g < n_groups;
         float kf[4];
         if (on) {
-          const int row = g / groups_per_row;
-          const int cg0 = (g % groups_per_row) * 4;
+          const int row = g >> log2_gpr;
+          const int cg0 = (g & gpr_mask) * 4;
           const int sft = sh.shift[row];
           // np.roll(row, k): out[(j + k) % S] = in[j]
 #pragma unroll
@@ -582,6 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(4);
     // ---------------------------------------------------------------- P5
     {
       const float inv = 1.0f / m_prev;
@@ -606,6 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(5);
     // ---------------------------------------------------------------- P6
     float g_min, g_max;
     {
@@ -642,6 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       continue;
     }
 
+    PD_PHASE(6);
     // ---------------------------------------------------------------- P7
     const int ts = B;
     {
@@ -652,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float q_scale = range > 0.f ? (kGray - 1) / range : 0.f;
       for (int g = tid; g < n_groups; g += kThreads) {
         const float4 v = band4[g];
-        const int tc = ((g % groups_per_row) * 4) >> log2_ts;
+        const int tc = ((g & gpr_mask) * 4) >> log2_ts;
         // np.round(rescale_intensity(img, out_range=(0, 16383)))
         const int b0 = static_cast<int>(rintf((v.x - g_min) * q_scale)) /
                        kBinSize;
@@ -670,6 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                __int_as_float(b2), __int_as_float(b3));
       }
       __syncthreads();
+      PD_PHASE(13);
       if (warp < kTiles) {
         int clim = static_cast<int>(0.01 * ts * ts);
         if (clim < 1) clim = 1;
@@ -677,6 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                             lane);
       }
       c.cl.sync();
+      PD_PHASE(14);
       // tile rows above and below, from the neighbouring CTAs
       {
         constexpr int kWords = kTiles * kBins / 2;  // uint32 words per tile row
@@ -695,6 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncthreads();
     }
 
+    PD_PHASE(7);
     // ---------------------------------------------------------------- P8
     int m_lo = 1 << 30, m_hi = -1;
     {
@@ -704,8 +818,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const float4 v = band4[g];
         const int bins[4] = {__float_as_int(v.x), __float_as_int(v.y),
                              __float_as_int(v.z), __float_as_int(v.w)};
-        const int r = r0 + g / groups_per_row;
-        const int cg0 = (g % groups_per_row) * 4;
+        const int r = r0 + (g >> log2_gpr);
+        const int cg0 = (g & gpr_mask) * 4;
         const int pr = r + half;
         const int bi = pr >> log2_ts;
         const float cy = (pr & (ts - 1)) * inv_ts;
@@ -744,6 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       m_lo = -static_cast<int>(mm.y);
     }
 
+    PD_PHASE(8);
     // ---------------------------------------------------------------- P9
     {
       // rescale_intensity: (v - min) / (max - min)
@@ -768,6 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       emit_band(c, band4, n_groups, 1.0f, out);
       c.parity ^= 1;
     }
+    PD_PHASE(9);
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   // no CTA may exit while a neighbour can still read its shared memory
