@@ -304,6 +304,18 @@ int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
                             int32_t* h_si_idx, int64_t* h_elapsed_us,
                             void* stream);
 
+/* ---- imaging.py:42-72: re-draws the nine image parameters of the envs'
+ *      current episode from the uniforms the last pd_reset used (RESET draws
+ *      4..12): sample_image_parameters (DEFAULT, what pd_reset itself applies)
+ *      or sample_noisy_image_parameters (NOISY).  mask: device uint8 [n] or
+ *      NULL.  Call after pd_reset. ---------------------------------------- */
+typedef enum pd_image_params_mode {
+  PD_IMAGE_PARAMS_DEFAULT = 0,
+  PD_IMAGE_PARAMS_NOISY = 1
+} pd_image_params_mode;
+int pd_sample_image_params(const pd_state* st, const uint8_t* mask,
+                           int32_t mode, void* stream);
+
 /* ---- queries: graphene.py:600-644 get_atoms_in_bounds,
  *      graphene.py:696-700 get_silicon_position --------------------------- */
 /* fov_override: device double [n][4] or NULL (use st->fov).  Outputs are
@@ -458,6 +470,18 @@ int pd_render(const pd_lattice* lat, const pd_state* st, const int32_t* env_ids,
               int32_t m, int32_t image_size, int32_t stop_stage,
               int32_t advance_frame_count, float* frames_out, void* workspace,
               int64_t workspace_bytes, void* stream);
+
+/* ---- label masks: imaging.py:75-114 generate_grid_mask for envs
+ *      env_ids[0..m) (NULL = envs 0..m-1) with each env's current FOV.
+ *      mask_out: device uint8 [m][image_size][image_size], 0 / 6 / 14.
+ *      radius_carbon / radius_silicon = (Z / 6)^intensity_exponent * 0.1,
+ *      evaluated by the caller in float64 (the host mirror does) so that the
+ *      comparison `squared distance < radius` sees the reference's value.
+ *      image_size: multiple of 8. ----------------------------------------- */
+int pd_render_mask(const pd_lattice* lat, const pd_state* st,
+                   const int32_t* env_ids, int32_t m, int32_t image_size,
+                   double radius_carbon, double radius_silicon,
+                   uint8_t* mask_out, void* stream);
 
 #ifdef __cplusplus
 }

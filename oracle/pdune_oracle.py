@@ -313,6 +313,31 @@ def reset(state: OracleState, mask: Optional[np.ndarray] = None) -> None:
   state.episode[idx] += np.uint32(1)
 
 
+def sample_noisy_image_parameters(state: OracleState,
+                                  mask: Optional[np.ndarray] = None) -> None:
+  """imaging.py:57-72 `sample_noisy_image_parameters`, drawn from the same
+  nine RESET-stream uniforms (draws 4..12 of the env's current episode) the
+  reset used for `sample_image_parameters`."""
+  e = state.num_envs
+  mask = np.ones(e, dtype=bool) if mask is None else np.asarray(mask, bool)
+  idx = np.nonzero(mask)[0]
+  if idx.size == 0:
+    return
+  env, ep = state.env_ids[idx], state.episode[idx] - np.uint32(1)
+  d = lambda k: draw_linear(state.seed, env, ep, STREAM_RESET, k)
+  ip = np.empty((idx.size, 9))
+  ip[:, 0] = 1.4 + (2.0 - 1.4) * d(4)
+  ip[:, 1] = 0.0 + (0.3 - 0.0) * d(5)
+  ip[:, 2] = 0.0 + (5.0 - 0.0) * d(6)
+  ip[:, 3] = -np.log1p(-d(7)) * 15.0 + 1.0
+  ip[:, 4] = 0.0 + (1e-2 - 0.0) * d(8)
+  ip[:, 5] = 0.0 + (0.25 - 0.0) * d(9)
+  ip[:, 6] = 0.5 + (1.5 - 0.5) * d(10)
+  ip[:, 7] = 0.0 + (0.25 - 0.0) * d(11)
+  ip[:, 8] = 0.0 + (0.25 - 0.0) * d(12)
+  state.image_params[idx] = ip
+
+
 def recenter_fov(state: OracleState, idx: np.ndarray) -> None:
   """simulator.py:79-82,161-165: FOV = [P_si - s/2, P_si + s/2]."""
   p = site_positions(state, state.si_idx[idx], idx)

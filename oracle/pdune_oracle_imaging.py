@@ -340,6 +340,36 @@ def equalize_adapthist(img: np.ndarray, clip_limit: float = 0.01,
 
 
 # ----------------------------------------------------------------------------
+# imaging.py:75-114 generate_grid_mask
+# ----------------------------------------------------------------------------
+def grid_mask(q: np.ndarray, z: np.ndarray, fov: np.ndarray,
+              intensity_exponent: float = 1.7, size: int = 512) -> np.ndarray:
+  """Semantic mask of the atoms in view.  q: normalised positions [M, 2]
+  (microscope frame), fov: (ll_x, ll_y, ur_x, ur_y).  Quirk kept: the SQUARED
+  distance in angstrom^2 is compared with the radius (imaging.py:109-110)."""
+  xs = np.linspace(fov[0], fov[2], size + 1, endpoint=True)
+  xs = (xs[:-1] + xs[1:]) / 2
+  ys = np.linspace(fov[1], fov[3], size + 1, endpoint=True)
+  ys = (ys[:-1] + ys[1:]) / 2
+  xx, yy = np.meshgrid(xs, ys)
+  # microscope_utils.py:362-369 (grid branch): p * (ur - ll) + ll
+  pos = q * np.array([fov[2] - fov[0], fov[3] - fov[1]]) + np.array(
+      [fov[0], fov[1]])
+  mask = np.zeros((size, size), dtype=np.uint8)
+  for p, number in zip(pos, z):
+    radius = (number / 6) ** intensity_exponent * 0.1
+    distance = (xx - p[0]) ** 2.0 + (yy - p[1]) ** 2.0
+    mask[distance < radius] = number
+  return np.flipud(mask)
+
+
+def mask_env(state: po.OracleState, env: int, size: int = 512,
+             intensity_exponent: float = 1.7) -> np.ndarray:
+  q, z, _ = po.get_atoms_in_bounds(state, env)
+  return grid_mask(q, z, state.fov[env], intensity_exponent, size)
+
+
+# ----------------------------------------------------------------------------
 # imaging.py:239-265 generate_stem_image
 # ----------------------------------------------------------------------------
 def generate_stem_image(q, z, fov_w, fov_h, params, rng, size: int = 512,

@@ -17,6 +17,7 @@ fast=(pd_api pd_mlp)
 [ -f "$src/pd_render_cluster.cu" ] && fast+=(pd_render_cluster)
 [ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
 [ -f "$src/pd_env.cu" ] && exact+=(pd_env)
+[ -f "$src/pd_mask.cu" ] && exact+=(pd_mask)
 pids=()
 for f in "${exact[@]}"; do
   "$NVCC" "${COMMON[@]}" -fmad=false -c "$src/$f.cu" -o "$obj/$f.o" & pids+=($!)

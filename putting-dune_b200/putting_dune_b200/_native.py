@@ -145,6 +145,9 @@ _SIGNATURES = {
     'pd_mlp_apply_model': ([C.POINTER(PdMlp), _i32, _p, _i64, _p, _p], C.c_int),
     'pd_render_workspace_bytes': ([_i32, C.POINTER(_i64)], C.c_int),
     'pd_render_clusters': ([_i32, C.POINTER(_i32)], C.c_int),
+    'pd_render_mask': ([_LP, _SP, _p, _i32, _i32, C.c_double, C.c_double, _p,
+                        _p], C.c_int),
+    'pd_sample_image_params': ([_SP, _p, _i32, _p], C.c_int),
     'pd_render': ([_LP, _SP, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p],
                   C.c_int),
     'pd_get_atoms_in_bounds': ([_LP, _SP, _p, _i32, _p, _p, _p, _p, _p],

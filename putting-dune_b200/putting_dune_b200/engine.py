@@ -296,6 +296,17 @@ class EnvBatch:
                                  C.byref(self.c), _ptr(m),
                                  _stream(self.device)))
 
+  def sample_image_params(self, noisy: bool = False, mask=None) -> None:
+    """Re-draws the image parameters of the current episode on the device:
+    imaging.py:42-54 ``sample_image_parameters`` (what reset applies) or
+    :57-72 ``sample_noisy_image_parameters``."""
+    m = None
+    if mask is not None:
+      m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_sample_image_params(
+          C.byref(self.c), _ptr(m), 1 if noisy else 0, _stream(self.device)))
+
   def rates(self, beam_xy, rate: RateSpec):
     beam = self._f64(beam_xy, (self.num_envs, 2))
     r = torch.empty((self.num_envs, 3), dtype=torch.float32,

@@ -211,6 +211,39 @@ def frames_fixture():
   print('frames_reference.npz', n, 'frames of', size)
 
 
+def perception_fixture():
+  """imaging.py:57-72 sample_noisy_image_parameters and :75-114
+  generate_grid_mask from the reference itself (perception-data generators):
+  noisy parameters under InjectedRng positioned at draw 4 of the env's RESET
+  sequence; masks of the reset state at 128 x 128."""
+  mods = refshim.load_reference()
+  im, mu = mods.imaging, mods.microscope_utils
+  seed, n, size = 515, 6, 128
+  st = po.make_state(n, seed)
+  po.reset(st)
+  res = {'seed': np.int64(seed), 'size': np.int64(size)}
+  noisy = []
+  for e in range(n):
+    rng = refrun.InjectedRng(seed, e)
+    rng.begin(po.STREAM_RESET, 0)
+    rng.k = 4  # the reset consumed offset x/y, angle, FOV scale
+    p = im.sample_noisy_image_parameters(rng)
+    noisy.append([getattr(p, name) for name in po.IMAGE_PARAM_NAMES])
+    q, z, _ = po.get_atoms_in_bounds(st, e)
+    f = st.fov[e]
+    fov = mu.MicroscopeFieldOfView(mods.Point(f[0], f[1]),
+                                   mods.Point(f[2], f[3]))
+    expo = 1.7 if e % 2 == 0 else float(st.image_params[e, 0])
+    res[f'mask_{e}'] = im.generate_grid_mask(
+        mu.AtomicGrid(q, z), fov, intensity_exponent=expo,
+        image_dimensions=(size, size))
+    res[f'mask_exponent_{e}'] = np.float64(expo)
+  res['noisy_params'] = np.asarray(noisy, dtype=np.float64)
+  np.savez_compressed(os.path.join(HERE, 'perception_reference.npz'), **res)
+  print('perception_reference.npz', n, 'envs; mask classes',
+        sorted(set(res['mask_0'].reshape(-1).tolist())))
+
+
 def episodes_fixture():
   """EvalResults of the reference's eval_lib.evaluate (greedy_on_neighbor,
   registry.py:287-298) under InjectedRng; see refrun.run_reference_episodes."""
@@ -270,5 +303,6 @@ if __name__ == '__main__':
   rates_fixture()
   standardize_fixture()
   frames_fixture()
+  perception_fixture()
   episodes_fixture()
   env_fixture()

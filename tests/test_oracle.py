@@ -294,6 +294,22 @@ def test_imaging_oracle_matches_reference_frames(golden_dir):
                              atol=1e-12)
 
 
+def test_perception_oracle_matches_reference(golden_dir):
+  """sample_noisy_image_parameters and generate_grid_mask vs the reference."""
+  from oracle import pdune_oracle_imaging as oi
+  fix = np.load(os.path.join(golden_dir, 'perception_reference.npz'))
+  seed, size = int(fix['seed']), int(fix['size'])
+  n = fix['noisy_params'].shape[0]
+  st = po.make_state(n, seed)
+  po.reset(st)
+  for e in range(n):
+    got = oi.mask_env(st, e, size, float(fix[f'mask_exponent_{e}']))
+    np.testing.assert_array_equal(got, fix[f'mask_{e}'])
+    assert set(got.reshape(-1).tolist()) <= {0, 6, 14}
+  po.sample_noisy_image_parameters(st)
+  np.testing.assert_array_equal(st.image_params, fix['noisy_params'])
+
+
 def test_clahe_restatement_properties():
   from oracle import pdune_oracle_imaging as oi
   rng = np.random.default_rng(0)
