@@ -25,10 +25,27 @@
 
 namespace pd {
 
-constexpr int kMlpThreads = 256;
+// -DPD_MLP_PHASE_CLOCKS: thread 0 of every CTA accumulates the cycles between
+// phase marks of k_step_learned; pd_debug_mlp_phases() reads and clears them.
+#ifdef PD_MLP_PHASE_CLOCKS
+__device__ unsigned long long g_mlp_phase[16];
+#define PD_MLP_PHASE(i)                                         \
+  do {                                                          \
+    if (threadIdx.x == 0) {                                     \
+      const long long now_ = clock64();                         \
+      atomicAdd(&g_mlp_phase[i],                                \
+                static_cast<unsigned long long>(now_ - ph_t0)); \
+      ph_t0 = now_;                                             \
+    }                                                           \
+  } while (0)
+#else
+#define PD_MLP_PHASE(i) do { } while (0)
+#endif
+
+constexpr int kMlpThreads = 512;
 constexpr int kMlpBatch = 128;   // GEMM M tile = queue batch
 constexpr int kChunk = 16;       // k-chunk of the hidden contraction
-constexpr int kEnvPerThread = 8;
+constexpr int kEnvPerThread = 4;  // 32 row groups x 16 column groups
 
 struct MlpView {
   int d, h1, h2, batchnorm;
@@ -45,7 +62,7 @@ __device__ __forceinline__ float swishf(float z) {
 // Tensor-core path only: operands are rounded to bf16 anyway, so the
 // activations use the SFU approximations (ex2 / rcp, ~2^-21 relative).
 __device__ __forceinline__ float swish_fast(float z) {
-  return z * __frcp_rn(1.0f + __expf(-z));
+  return __fdividef(z, 1.0f + __expf(-z));
 }
 
 __device__ __forceinline__ float softplusf(float z) {
@@ -64,9 +81,9 @@ struct MlpSmall {
   float bn_a[2], bn_b[2];             // x_hat = x * a + b
 };
 
-struct MlpShared : MlpSmall {         // FP32 FMA path
-  float a[kChunk][kMlpBatch];         // layer-1 activations, k-major
-  float b[kChunk][256];               // W1 chunk
+struct MlpShared : MlpSmall {         // FP32 FMA path (double-buffered)
+  __align__(16) float a[2][kChunk][kMlpBatch];  // layer-1 activations, k-major
+  __align__(16) float b[2][kChunk][256];        // W1 chunk
 };
 
 // Loads the small layers once per CTA.
@@ -102,10 +119,43 @@ __device__ __forceinline__ void mlp_stage_small(const MlpView& w,
 }
 
 // One GEMM wave: out[b][0..3] = softplus(MLP(xs[b])) for b < kMlpBatch.
-// NPT = H2 / 16 outputs per thread; thread (ty, tx) owns envs ty*8..ty*8+7 and
-// outputs tx*NPT..tx*NPT+NPT-1.
+// NPT = H2 / 16 outputs per thread; thread (ty, tx) owns envs ty*4..ty*4+3 and
+// the NPT / VEC column vectors (j * 16 + tx) * VEC .. + VEC - 1, so that the 16
+// tx lanes read consecutive 16-byte words of the W1 chunk.  Chunks of 16 rows
+// of W1 arrive with cp.async into the buffer the previous chunk has left
+// while the current one is being contracted.
+template <int NPT>
+__device__ __forceinline__ void mlp_stage_chunk(const MlpView& w, MlpShared& sh,
+                                                int k0, int buf) {
+  const int tid = threadIdx.x;
+  // layer-1 chunk: a[k][b] = swish(x0*W0[0][k] + x1*W0[1][k] + b0[k])
+  for (int i = tid; i < kChunk * kMlpBatch; i += kMlpThreads) {
+    const int k = i / kMlpBatch, b = i - k * kMlpBatch;
+    const float x0 = sh.xs[b][0] * sh.bn_a[0] + sh.bn_b[0];
+    const float x1 = sh.xs[b][1] * sh.bn_a[1] + sh.bn_b[1];
+    const int kk = k0 + k;
+    float z = sh.b0[kk];
+    z = fmaf(x0, sh.w0[0][kk], z);
+    z = fmaf(x1, sh.w0[1][kk], z);
+    sh.a[buf][k][b] = swishf(z);
+  }
+  // W1 chunk: rows k0..k0+15, all H2 columns, 16 bytes per cp.async
+  for (int i = tid; i < kChunk * (NPT * 16) / 4; i += kMlpThreads) {
+    const int k = i / (NPT * 4), c4 = i - k * (NPT * 4);
+    const float* src = w.w1 + static_cast<size_t>(k0 + k) * w.h2 + 4 * c4;
+    const uint32_t dst = static_cast<uint32_t>(
+        __cvta_generic_to_shared(&sh.b[buf][k][4 * c4]));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                 "l"(src)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int NPT>
 __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
+  constexpr int VEC = NPT < 4 ? NPT : 4;
+  constexpr int NV = NPT / VEC;
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   float acc[kEnvPerThread][NPT];
@@ -114,37 +164,32 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
 #pragma unroll
     for (int j = 0; j < NPT; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < w.h1; k0 += kChunk) {
-    __syncthreads();
-    // layer-1 chunk: a[k][b] = swish(x0*W0[0][k] + x1*W0[1][k] + b0[k])
-    for (int i = tid; i < kChunk * kMlpBatch; i += kMlpThreads) {
-      const int k = i / kMlpBatch, b = i - k * kMlpBatch;
-      const float x0 = sh.xs[b][0] * sh.bn_a[0] + sh.bn_b[0];
-      const float x1 = sh.xs[b][1] * sh.bn_a[1] + sh.bn_b[1];
-      const int kk = k0 + k;
-      float z = sh.b0[kk];
-      z = fmaf(x0, sh.w0[0][kk], z);
-      z = fmaf(x1, sh.w0[1][kk], z);
-      sh.a[k][b] = swishf(z);
-    }
-    // W1 chunk: rows k0..k0+15, all H2 columns
-    for (int i = tid; i < kChunk * (NPT * 16) / 4; i += kMlpThreads) {
-      const int k = i / (NPT * 4), c4 = i - k * (NPT * 4);
-      const float4 v = __ldg(reinterpret_cast<const float4*>(
-                                 w.w1 + static_cast<size_t>(k0 + k) * w.h2) +
-                             c4);
-      reinterpret_cast<float4*>(&sh.b[k][0])[c4] = v;
-    }
-    __syncthreads();
+  __syncthreads();  // xs of this wave are in place; the last wave is done
+  mlp_stage_chunk<NPT>(w, sh, 0, 0);
+  const int n_chunks = w.h1 / kChunk;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int buf = c & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // chunk c visible; everyone has left chunk c - 1
+    if (c + 1 < n_chunks) mlp_stage_chunk<NPT>(w, sh, (c + 1) * kChunk, buf ^ 1);
 #pragma unroll
     for (int k = 0; k < kChunk; ++k) {
-      float av[kEnvPerThread], bv[NPT];
-      const float4 a0 = reinterpret_cast<const float4*>(&sh.a[k][ty * 8])[0];
-      const float4 a1 = reinterpret_cast<const float4*>(&sh.a[k][ty * 8])[1];
-      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
-      av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      float bv[NPT];
+      const float4 a0 =
+          *reinterpret_cast<const float4*>(&sh.a[buf][k][ty * kEnvPerThread]);
+      const float av[kEnvPerThread] = {a0.x, a0.y, a0.z, a0.w};
 #pragma unroll
-      for (int j = 0; j < NPT; ++j) bv[j] = sh.b[k][tx + 16 * j];
+      for (int j = 0; j < NV; ++j) {
+        const float* src = &sh.b[buf][k][(j * 16 + tx) * VEC];
+        if constexpr (VEC == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src);
+          bv[4 * j] = v.x; bv[4 * j + 1] = v.y;
+          bv[4 * j + 2] = v.z; bv[4 * j + 3] = v.w;
+        } else {
+          const float2 v = *reinterpret_cast<const float2*>(src);
+          bv[2 * j] = v.x; bv[2 * j + 1] = v.y;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < kEnvPerThread; ++i)
 #pragma unroll
@@ -157,7 +202,7 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
-      const int col = tx + 16 * j;
+      const int col = ((j / VEC) * 16 + tx) * VEC + (j % VEC);
       const float h = swishf(acc[i][j] + sh.b1[col]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) o[q] = fmaf(h, sh.w2[col][q], o[q]);
@@ -171,7 +216,7 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
     if (tx == 0) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        sh.out[ty * 8 + i][q] = softplusf(o[q] + sh.b2[q]);
+        sh.out[ty * kEnvPerThread + i][q] = softplusf(o[q] + sh.b2[q]);
     }
   }
   __syncthreads();
@@ -193,7 +238,7 @@ struct TcShared {
   unsigned long long mbar;
   uint32_t tmem_base;
   uint32_t pad_;
-  float partial[2][kMlpBatch][4];
+  float partial[4][kMlpBatch][4];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -283,24 +328,35 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   const int kblocks = w.h1 >> 3;          // 16-byte blocks along K
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
   // ---- h1 = swish(x_hat W0 + b0) as bf16, canonical K-major ----
+  // A warp writes 8 rows x 4 k-blocks (512 contiguous bytes) per trip; with
+  // kblocks / 4 dividing the warp count a thread keeps its 8 columns of W0 /
+  // b0 in registers for the whole wave.
   {
     const int m8 = lane & 7, kb_lo = lane >> 3;
-    const int n_pairs = 16 * (kblocks >> 2);
-    for (int pair = warp; pair < n_pairs; pair += kMlpThreads / 32) {
-      const int g = pair & 15;
-      const int kb = (pair >> 4) * 4 + kb_lo;
+    const int wcols = kblocks >> 2;  // warp columns
+    const int n_cells = 16 * wcols;
+    int cur_wc = -1;
+    float w0a[8], w0b[8], b0v[8];
+    for (int cell = warp; cell < n_cells; cell += kMlpThreads / 32) {
+      const int wc = cell % wcols, g = cell / wcols;
+      const int kb = wc * 4 + kb_lo;
+      if (wc != cur_wc) {
+        cur_wc = wc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          w0a[j] = sh.w0[0][kb * 8 + j];
+          w0b[j] = sh.w0[1][kb * 8 + j];
+          b0v[j] = sh.b0[kb * 8 + j];
+        }
+      }
       const int m = g * 8 + m8;
-      const float x0 = sh.xs[m][0] * sh.bn_a[0] + sh.bn_b[0];
-      const float x1 = sh.xs[m][1] * sh.bn_a[1] + sh.bn_b[1];
+      const float2 xr = *reinterpret_cast<const float2*>(sh.xs[m]);
+      const float x0 = xr.x * sh.bn_a[0] + sh.bn_b[0];
+      const float x1 = xr.y * sh.bn_a[1] + sh.bn_b[1];
       float h[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = kb * 8 + j;
-        float z = sh.b0[k];
-        z = fmaf(x0, sh.w0[0][k], z);
-        z = fmaf(x1, sh.w0[1][k], z);
-        h[j] = swish_fast(z);
-      }
+      for (int j = 0; j < 8; ++j)
+        h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
       uint4 v;
       v.x = pack_bf16x2(h[0], h[1]);
       v.y = pack_bf16x2(h[2], h[3]);
@@ -356,44 +412,53 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
     tc.phase ^= 1u;
   }
   asm volatile("tcgen05.fence::after_thread_sync;");
-  // ---- epilogue: thread = TMEM lane = env row; two column halves ----
+  // ---- epilogue: thread = TMEM lane = env row; up to four column slices ----
+  const int n_slices = (w.h2 >> 4) < 4 ? (w.h2 >> 4) : 4;
   {
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, slice = warp >> 2;
     const int m = quarter * 32 + lane;
-    const int c_lo = half * (w.h2 >> 1), c_hi = c_lo + (w.h2 >> 1);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-      uint32_t r[16];
-      const uint32_t taddr =
-          tmem + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-          "%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]),
-            "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-            "=r"(r[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (slice < n_slices) {
+      const int per = w.h2 / n_slices;
+      const int c_lo = slice * per, c_hi = c_lo + per;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+        uint32_t r[16];
+        const uint32_t taddr =
+            tmem + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]),
+              "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+              "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = c0 + j;
-        const float hh = swish_fast(__uint_as_float(r[j]) + sh.b1[col]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = fmaf(hh, sh.w2[col][q], o[q]);
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          const float hh = swish_fast(__uint_as_float(r[j]) + sh.b1[col]);
+          const float4 w2v = *reinterpret_cast<const float4*>(sh.w2[col]);
+          o[0] = fmaf(hh, w2v.x, o[0]);
+          o[1] = fmaf(hh, w2v.y, o[1]);
+          o[2] = fmaf(hh, w2v.z, o[2]);
+          o[3] = fmaf(hh, w2v.w, o[3]);
+        }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tc.ts->partial[half][m][q] = o[q];
+      for (int q = 0; q < 4; ++q) tc.ts->partial[slice][m][q] = o[q];
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (tid < kMlpBatch) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      sh.out[tid][q] = softplusf(tc.ts->partial[0][tid][q] +
-                                 tc.ts->partial[1][tid][q] + sh.b2[q]);
+    for (int q = 0; q < 4; ++q) {
+      float acc = sh.b2[q];
+      for (int sl = 0; sl < n_slices; ++sl) acc += tc.ts->partial[sl][tid][q];
+      sh.out[tid][q] = softplusf(acc);
+    }
   }
   __syncthreads();
 }
@@ -512,6 +577,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
   const int64_t hi = cursor + per < n ? cursor + per : n;
   if (tid == 0) sh.q_count = 0;
   __syncthreads();
+#ifdef PD_MLP_PHASE_CLOCKS
+  long long ph_t0 = clock64();
+#endif
 
   while (true) {
     const int n_pending = sh.q_count;
@@ -585,12 +653,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
       sh.m.xs[tid][1] = can.x1;
     }
     __syncthreads();
+    PD_MLP_PHASE(0);
     // ---- network for the whole batch ----
     if constexpr (TC) {
       mlp_wave_tc(w, sh.m, tc);
     } else {
       mlp_wave<NPT>(w, sh.m);
     }
+    PD_MLP_PHASE(1);
     // ---- events ----
     bool survive = false;
     if (own) {
@@ -661,6 +731,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     const unsigned bal = __ballot_sync(0xffffffffu, survive);
     if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
     __syncthreads();
+    PD_MLP_PHASE(2);
     int offset = 0;
     for (int w2 = 0; w2 < warp; ++w2) offset += sh.warp_cnt[w2];
     int total_surv = 0;
@@ -675,6 +746,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     __syncthreads();
     if (tid == 0) sh.q_count = total_surv;
     __syncthreads();
+    PD_MLP_PHASE(3);
   }
   if constexpr (TC) tc_teardown(w, tc);
 }
@@ -786,6 +858,7 @@ static int mlp_view(const pd_mlp* mlp, MlpView* v) {
   if (mlp->tensor_core) {
     PD_REQUIRE(mlp->w1_umma != nullptr, "tensor_core needs w1_umma");
     PD_REQUIRE(mlp->hidden2 % 32 == 0, "tensor_core needs hidden2 % 32 == 0");
+    PD_REQUIRE(mlp->hidden1 % 32 == 0, "tensor_core needs hidden1 % 32 == 0");
   }
   *v = MlpView{mlp->context_dim, mlp->hidden1, mlp->hidden2, mlp->batchnorm,
                mlp->bn_scale, mlp->bn_offset, mlp->bn_mean, mlp->bn_var,
@@ -903,3 +976,13 @@ extern "C" int pd_mlp_apply_model(const pd_mlp* models, int32_t n_models,
   }
   return PD_OK;
 }
+
+#ifdef PD_MLP_PHASE_CLOCKS
+extern "C" int pd_debug_mlp_phases(unsigned long long* out16) {
+  unsigned long long zero[16] = {0};
+  PD_CUDA_OK(cudaDeviceSynchronize());
+  PD_CUDA_OK(cudaMemcpyFromSymbol(out16, pd::g_mlp_phase, sizeof(zero)));
+  PD_CUDA_OK(cudaMemcpyToSymbol(pd::g_mlp_phase, zero, sizeof(zero)));
+  return PD_OK;
+}
+#endif
