@@ -60,8 +60,9 @@ def parse_args():
   ap.add_argument('--no-at-scale', action='store_true')
   ap.add_argument('--no-frames', action='store_true')
   ap.add_argument('--no-mlp', action='store_true')
-  ap.add_argument('--frames', type=int, default=512,
-                  help='frames per render launch (512x512)')
+  ap.add_argument('--frames', type=int, default=16384,
+                  help='frames per render launch (512x512; BASELINE '
+                       'configs[3]: 16384 envs per step = 17.2 GB of frames)')
   ap.add_argument('--episodes', type=int, default=0,
                   help='total envs for the greedy-controller episode run '
                        '(configs[4] uses 1048576); 0 = skip')
@@ -275,8 +276,9 @@ def measure_frames(pd, batch, dev, peak, args):
   from putting_dune_b200 import _native as nat
   n_cl = C.c_int32()
   nat.check(nat.lib.pd_render_clusters(512, C.byref(n_cl)))
-  # whole waves of clusters (one 8-CTA cluster renders one frame at a time)
-  m = max(n_cl.value, (args.frames // n_cl.value) * n_cl.value)
+  m = max(n_cl.value, args.frames)
+  free, _ = torch.cuda.mem_get_info(dev)
+  m = int(min(m, (free - (2 << 30)) // (512 * 512 * 4)))
   fb = pd.EnvBatch(m, seed=3, device=dev, lattice=batch.lattice_tables)
   fb.reset()
   out = torch.empty((m, 512, 512), dtype=torch.float32, device=dev)
@@ -291,15 +293,23 @@ def measure_frames(pd, batch, dev, peak, args):
     b.record()
   torch.cuda.synchronize()
   ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+  del out, fb
+  torch.cuda.empty_cache()
   fps = m / (ms / 1e3)
   gbs = fps * 512 * 512 * 4 / 1e9
   return {'metric': 'STEM frames/sec', 'value': fps, 'unit': 'frames/s',
           'frames_per_launch': m, 'image_size': 512, 'launch_ms': ms,
           'kernel': 'pd::k_render_cluster',
           'clusters_resident': n_cl.value, 'ctas_per_frame': 8,
+          'workload': 'configs[3]: batched STEM image rendering 512x512 with '
+                      'noise, %d envs per step' % m,
           'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak,
                        'unit': 'GB/s', 'frac': gbs / peak,
-                       'algorithmic_bytes_per_frame': 512 * 512 * 4}}
+                       'algorithmic_bytes_per_frame': 512 * 512 * 4,
+                       # ncu --set full of 120 frames, per frame
+                       'traffic_per_frame': (ncu_traffic(
+                           'r01_k_render_cluster_120frames.ncu.json') or 0) /
+                                            120 or None}}
 
 
 def measure_mlp(pd, batch, dev, args):
@@ -337,8 +347,10 @@ def measure_mlp(pd, batch, dev, args):
         'rate_evals_per_step': evals / n, 'flop_per_eval': flop,
         'tflops': evals * flop / (ms / 1e3) / 1e12,
         'kernel': ('pd::k_step_learned<TC> (tcgen05.mma kind::f16, BF16 '
-                   'operands, FP32 accumulate in TMEM)' if tensor_core else
-                   'pd::k_step_learned (FP32 FMA, queue-batched GEMM)')}
+                   'operands, FP32 accumulate in TMEM; 512 threads)'
+                   if tensor_core else
+                   'pd::k_step_learned (FP32 FMA, queue-batched GEMM, '
+                   'cp.async double-buffered W1 chunks; 512 threads)')}
   return out
 
 
