@@ -74,7 +74,7 @@ __device__ __forceinline__ int poisson_icdf_tab(double lam, double u,
   return k;
 }
 
-// Four inverse-CDF searches in float32.  inv_k1[i] = 1 / (i + 1) (8-byte
+// Four inverse-CDF searches in float32.  inv_k1[i] = 1 / (i + 1) (16-byte
 // aligned).  The float32 CDF differs from the float64 one by
 // < (4k + 3) * 2^-24; a search whose u lies within eps(k) = 1e-6 (k + 4) of
 // the two thresholds that decide it, or with lam > 60 (exp(-lam) leaves the
@@ -85,7 +85,7 @@ __device__ __forceinline__ void poisson4(const float (&lam)[4],
                                          const float* inv_k1,
                                          const double* inv_kd, int (&k)[4]) {
   unsigned redo = 0;
-  const float2* tp = reinterpret_cast<const float2*>(inv_k1);
+  const float4* tp = reinterpret_cast<const float4*>(inv_k1);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float l = lam[j], uu = u[j];
@@ -94,35 +94,40 @@ __device__ __forceinline__ void poisson4(const float (&lam)[4],
       redo |= 1u << j;
       continue;
     }
+    // (p, cdf) = pmf and CDF at kk; below = CDF(kk - 1)
     float p = expf(-l);
-    float cdf = p;
+    float cdf = p, below = 0.f;
     int kk = 0;
     if (uu >= cdf) {
-      // two terms per trip: Poisson(60) passes 0.9999 before k = 100
-      for (int i2 = 0;;) {
-        const float2 ik = tp[i2];  // 1 / (2 i2 + 1), 1 / (2 i2 + 2)
-        const float r1 = l * ik.x, r2 = l * ik.y;
-        const float c1 = fmaf(p, r1, cdf);
-        const float p1 = p * r1;
+      // four terms per trip: Poisson(60) passes 0.9999 before k = 100
+      for (int i4 = 0;; ++i4) {
+        const float4 ik = tp[i4];  // 1 / (4 i4 + 1) ... 1 / (4 i4 + 4)
+        const float r1 = l * ik.x, r2 = l * ik.y, r3 = l * ik.z, r4 = l * ik.w;
+        const float p1 = p * r1, p2 = p1 * r2, p3 = p2 * r3, p4 = p3 * r4;
+        const float c1 = cdf + p1, c2 = c1 + p2, c3 = c2 + p3, c4 = c3 + p4;
+        if (uu >= c4 && i4 < kInvTable / 4 - 1) {
+          p = p4;
+          cdf = c4;
+          continue;
+        }
+        // the answer is among 4 i4 + 1 .. 4 i4 + 4 (or the table ended)
+        const int base = 4 * i4;
         if (!(uu >= c1)) {
-          kk = 2 * i2 + 1;
-          p = p1;
-          cdf = c1;
-          break;
+          kk = base + 1; p = p1; below = cdf; cdf = c1;
+        } else if (!(uu >= c2)) {
+          kk = base + 2; p = p2; below = c1; cdf = c2;
+        } else if (!(uu >= c3)) {
+          kk = base + 3; p = p3; below = c2; cdf = c3;
+        } else {
+          kk = base + 4; p = p4; below = c3; cdf = c4;
         }
-        cdf = fmaf(p1, r2, c1);
-        p = p1 * r2;
-        ++i2;
-        if (!(uu >= cdf) || i2 >= kInvTable / 2) {
-          kk = 2 * i2;
-          break;
-        }
+        break;
       }
     }
     k[j] = kk;
     const float eps = 1e-6f * static_cast<float>(kk + 4);
-    // the thresholds that decided: cdf(kk - 1) = cdf - p (<= u) and cdf(kk)
-    if (!(cdf - uu >= eps) || (kk > 0 && !(uu - (cdf - p) >= eps)))
+    // the thresholds that decided: CDF(kk - 1) (<= u) and CDF(kk) (> u)
+    if (!(cdf - uu >= eps) || (kk > 0 && !(uu - below >= eps)))
       redo |= 1u << j;
   }
   if (redo != 0) {

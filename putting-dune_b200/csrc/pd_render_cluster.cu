@@ -75,7 +75,7 @@ struct ClusterShared {
   // one of the four copies
   __align__(16) float kys[4][kKyLen];
   float kb[kHalo + 1];
-  __align__(8) float inv_k1[kInvTable];  // 1 / (i + 1)
+  __align__(16) float inv_k1[kInvTable];  // 1 / (i + 1)
   double inv_kd[kInvTable];
   float pow_tab[kPowTab];
   int shift[64];
@@ -582,39 +582,33 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float scale = poisson_mult / m_prev;
       vmax = 0.f;
       // 128-pixel chunks, handed to the warps dynamically (the search length
-      // follows the brightness); a CTA that runs out of chunks takes chunks of
-      // the other bands of the frame through distributed shared memory
+      // follows the brightness).  Taking chunks of the other bands through
+      // distributed shared memory was measured and dropped: the remote
+      // counter traffic cost more than the imbalance it removed (-4 %).
       const int n_chunks = n_groups / 32;
-      for (int hop = 0; hop < kCluster; ++hop) {
-        const int owner = (rank + hop) & (kCluster - 1);
-        int* ctr = hop == 0 ? &sh.work[1]
-                            : c.cl.map_shared_rank(&sh.work[1], owner);
-        float4* b4 = hop == 0 ? band4 : c.cl.map_shared_rank(band4, owner);
-        const uint32_t gb = static_cast<uint32_t>(owner * B) * groups_per_row;
-        for (;;) {
-          int t = 0;
-          if (lane == 0) t = atomicAdd(ctr, 1);
-          t = __shfl_sync(0xffffffffu, t, 0);
-          if (t >= n_chunks) break;
-          // chunk t = a 16-column x 8-row patch (smaller than the atom
-          // spacing), so the 128 searches of a warp have similar lengths
-          const int g = (((t >> (a.log2_size - 4)) * 8 + (lane >> 2))
-                         << log2_gpr) +
-                        (t & ((S >> 4) - 1)) * 4 + (lane & 3);
-          const float4 v = b4[g];
-          const uint4 w = philox4x32_10(env, frame, gb + g,
-                                        PD_STREAM_RENDER_POISSON, seed);
-          const float lam[4] = {v.x * scale, v.y * scale, v.z * scale,
-                                v.w * scale};
-          const float u[4] = {u24(w.x), u24(w.y), u24(w.z), u24(w.w)};
-          int k[4];
-          poisson4(lam, u, sh.inv_k1, sh.inv_kd, k);
-          const float4 o = make_float4(
-              static_cast<float>(k[0]), static_cast<float>(k[1]),
-              static_cast<float>(k[2]), static_cast<float>(k[3]));
-          b4[g] = o;
-          vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
-        }
+      for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&sh.work[1], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_chunks) break;
+        // chunk t = a 16-column x 8-row patch (smaller than the atom
+        // spacing), so the 128 searches of a warp have similar lengths
+        const int g = (((t >> (a.log2_size - 4)) * 8 + (lane >> 2))
+                       << log2_gpr) +
+                      (t & ((S >> 4) - 1)) * 4 + (lane & 3);
+        const float4 v = band4[g];
+        const uint4 w = philox4x32_10(env, frame, g_base + g,
+                                      PD_STREAM_RENDER_POISSON, seed);
+        const float lam[4] = {v.x * scale, v.y * scale, v.z * scale,
+                              v.w * scale};
+        const float u[4] = {u24(w.x), u24(w.y), u24(w.z), u24(w.w)};
+        int k[4];
+        poisson4(lam, u, sh.inv_k1, sh.inv_kd, k);
+        const float4 o = make_float4(
+            static_cast<float>(k[0]), static_cast<float>(k[1]),
+            static_cast<float>(k[2]), static_cast<float>(k[3]));
+        band4[g] = o;
+        vmax = fmaxf(vmax, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
       }
       m_prev = frame_max2(c, vmax, 0.f, 2).x;
     }
