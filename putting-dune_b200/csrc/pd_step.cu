@@ -1057,14 +1057,21 @@ extern "C" int pd_rollout_actions_host(
   pd::HostPipeline* pipe = nullptr;
   int rcode = pd::host_pipeline(&pipe);
   if (rcode != PD_OK) return rcode;
-  const int n_chunks = n_steps >= 32 ? 4 : 1;
+  // Short first and last chunks keep the pipeline's fill (first H2D copy) and
+  // drain (last D2H copy) small; the kernels in between overlap both copies.
+  const int n_chunks = n_steps >= 64 ? 5 : (n_steps >= 32 ? 4 : 1);
   // staging may still be read by earlier work queued on `s`
   PD_CUDA_OK(cudaEventRecord(pipe->start, s));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
   int t0[9];
+  static const int kSixteenths[6] = {0, 1, 6, 11, 15, 16};
   for (int c = 0; c <= n_chunks; ++c)
-    t0[c] = static_cast<int>(static_cast<int64_t>(n_steps) * c / n_chunks);
+    t0[c] = n_chunks == 5
+                ? static_cast<int>(static_cast<int64_t>(n_steps) *
+                                   kSixteenths[c] / 16)
+                : static_cast<int>(static_cast<int64_t>(n_steps) * c /
+                                   n_chunks);
   for (int c = 0; c < n_chunks; ++c) {
     const size_t off = static_cast<size_t>(t0[c]) * n * 2;
     const size_t cnt = static_cast<size_t>(t0[c + 1] - t0[c]) * n * 2;
