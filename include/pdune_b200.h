@@ -465,11 +465,16 @@ int pd_render_clusters(int32_t image_size, int32_t* out_clusters);
  * the noise fields).  Frames with at most 1024 atoms in view, a clean-image
  * kernel radius <= 128 px and blur_amount < 1.125 (everything imaging.py:42-72
  * samples at FOV >= 7.5 A) stay in shared memory of an 8-CTA cluster; others
- * take a slower one-CTA path through the workspace.  Same results. */
+ * take a slower one-CTA path through the workspace.  Same results.
+ * buffer_size (imaging.py:123, in [0, 0.25]): 0 renders the atoms inside the
+ * FOV, as the simulator does; > 0 is generate_clean_image's buffered form with
+ * the whole lattice as its grid -- atoms up to buffer_size FOV widths outside
+ * the frame contribute their Gaussian tails. */
 int pd_render(const pd_lattice* lat, const pd_state* st, const int32_t* env_ids,
               int32_t m, int32_t image_size, int32_t stop_stage,
-              int32_t advance_frame_count, float* frames_out, void* workspace,
-              int64_t workspace_bytes, void* stream);
+              int32_t advance_frame_count, double buffer_size,
+              float* frames_out, void* workspace, int64_t workspace_bytes,
+              void* stream);
 
 /* ---- label masks: imaging.py:75-114 generate_grid_mask for envs
  *      env_ids[0..m) (NULL = envs 0..m-1) with each env's current FOV.

@@ -169,23 +169,31 @@ def gaussian_filter(img: np.ndarray, sigma, mode: str) -> np.ndarray:
 # imaging.py stages
 # ----------------------------------------------------------------------------
 def clean_image(q: np.ndarray, z: np.ndarray, fov_w: float, fov_h: float,
-                intensity_exponent: float, size: int = 512) -> np.ndarray:
-  """imaging.py:117-173 with buffer_size=0.  q: normalised positions [M, 2]."""
-  img = np.zeros((size, size))
-  edges = np.linspace(0.0, 1.0, size + 1)
+                intensity_exponent: float, size: int = 512,
+                buffer_size: float = 0.0) -> np.ndarray:
+  """imaging.py:117-173.  q: positions [M, 2] in the microscope frame (atoms
+  outside [-buffer, 1 + buffer] are dropped, like np.histogram2d does)."""
+  bw = int(buffer_size * size)
+  n = size + 2 * bw
+  img = np.zeros((n, n))
+  lo, hi = -buffer_size, 1 + buffer_size
+  edges = np.linspace(lo, hi, n + 1)
   for number in sorted(set(int(v) for v in z)):
     sel = q[z == number]
+    ok = ((sel[:, 0] >= lo) & (sel[:, 0] <= hi) & (sel[:, 1] >= lo) &
+          (sel[:, 1] <= hi))
+    sel = sel[ok]
     bx = np.searchsorted(edges, sel[:, 0], side='right') - 1
     by = np.searchsorted(edges, sel[:, 1], side='right') - 1
-    bx[sel[:, 0] == 1.0] = size - 1
-    by[sel[:, 1] == 1.0] = size - 1
-    ok = (bx >= 0) & (bx < size) & (by >= 0) & (by < size)
-    counts = np.zeros((size, size))
-    np.add.at(counts, (bx[ok], by[ok]), 1.0)
+    bx[sel[:, 0] == edges[-1]] = n - 1
+    by[sel[:, 1] == edges[-1]] = n - 1
+    counts = np.zeros((n, n))
+    np.add.at(counts, (bx, by), 1.0)
     img = img + counts * (np.int64(number) ** np.float64(intensity_exponent))
   img = np.flipud(np.transpose(img))
   sigma = (size / (2.15 * fov_w), size / (2.15 * fov_h))
   img = gaussian_filter(img, sigma, 'constant')
+  img = img[bw:bw + size, bw:bw + size]
   return img / np.max(img)
 
 
@@ -373,12 +381,12 @@ def mask_env(state: po.OracleState, env: int, size: int = 512,
 # imaging.py:239-265 generate_stem_image
 # ----------------------------------------------------------------------------
 def generate_stem_image(q, z, fov_w, fov_h, params, rng, size: int = 512,
-                        stages: bool = False):
+                        stages: bool = False, buffer_size: float = 0.0):
   """params: the 9 values in dataclass order (po.IMAGE_PARAM_NAMES)."""
   (exponent, gauss_var, jitter_rate, poisson_mult, sp_amount, blur_amount,
    gamma, exp_lambda, uniform_scale) = [float(v) for v in params]
   out = {}
-  img = clean_image(q, z, fov_w, fov_h, exponent, size)
+  img = clean_image(q, z, fov_w, fov_h, exponent, size, buffer_size)
   out['clean'] = img
   img = apply_blur(img, blur_amount)
   out['blur'] = img
@@ -399,15 +407,33 @@ def generate_stem_image(q, z, fov_w, fov_h, params, rng, size: int = 512,
   return out if stages else img
 
 
+def grid_in_microscope_frame(state: po.OracleState, env: int):
+  """The whole material grid in the microscope frame of the env's FOV
+  (microscope_utils.py:421-428): what a caller hands generate_stem_image when
+  it renders with a buffer."""
+  f = state.fov[env]
+  p = po.all_positions(state, env)
+  q = np.stack(((p[:, 0] - f[0]) / (f[2] - f[0]),
+                (p[:, 1] - f[1]) / (f[3] - f[1])), axis=1)
+  z = np.full(p.shape[0], po.CARBON, dtype=np.int64)
+  z[state.si_idx[env]] = po.SILICON
+  return q, z
+
+
 def render_env(state: po.OracleState, env: int, size: int = 512,
-               stages: bool = False):
+               stages: bool = False, buffer_size: float = 0.0):
   """simulator.py:206-221 `_generate_image` for one env of the oracle state;
-  advances the env's frame counter."""
-  q, z, _ = po.get_atoms_in_bounds(state, env)
+  advances the env's frame counter.  buffer_size > 0: imaging.py:129-168 with
+  the whole grid as input."""
+  if buffer_size > 0:
+    q, z = grid_in_microscope_frame(state, env)
+  else:
+    q, z, _ = po.get_atoms_in_bounds(state, env)
   f = state.fov[env]
   rng = RenderInjectedRng(state.seed, int(state.env_ids[env]),
                           int(state.frame_count[env]), size)
   res = generate_stem_image(q, z, f[2] - f[0], f[3] - f[1],
-                            state.image_params[env], rng, size, stages)
+                            state.image_params[env], rng, size, stages,
+                            buffer_size)
   state.frame_count[env] += np.uint32(1)
   return res

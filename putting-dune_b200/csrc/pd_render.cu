@@ -144,16 +144,11 @@ __global__ void __launch_bounds__(kRenderThreads, 1)
         keep[round] = false;
         if (k < a.lat.n_sites) {
           const double2 p = site_position(__ldg(base + k), lt);
-          if (fv.llx <= p.x && p.x <= fv.urx && fv.lly <= p.y &&
-              p.y <= fv.ury) {
-            const double qx = (p.x - fv.llx) / fw, qy = (p.y - fv.lly) / fh;
-            int bx = static_cast<int>(floor(qx * S));
-            int by = static_cast<int>(floor(qy * S));
-            if (bx > S - 1) bx = S - 1;  // q == 1 falls in the last bin
-            if (by > S - 1) by = S - 1;
+          const AtomBin ab = atom_bin(p, fv, S, a.buffer, a.bw);
+          if (ab.keep) {
             keep[round] = true;
-            rc[round] = make_short2(static_cast<short>(S - 1 - by),
-                                    static_cast<short>(bx));
+            rc[round] = make_short2(static_cast<short>(ab.row),
+                                    static_cast<short>(ab.col));
             wt[round] = k == si ? w_si : w_c;
           }
         }
@@ -598,7 +593,7 @@ extern "C" int pd_render_clusters(int32_t image_size, int32_t* out_clusters) {
 extern "C" int pd_render(const pd_lattice* lat, const pd_state* st,
                          const int32_t* env_ids, int32_t m, int32_t image_size,
                          int32_t stop_stage, int32_t advance_frame_count,
-                         float* frames_out, void* workspace,
+                         double buffer_size, float* frames_out, void* workspace,
                          int64_t workspace_bytes, void* stream) {
   int rcode = pd::validate_common(lat, st, nullptr);
   if (rcode != PD_OK) return rcode;
@@ -606,6 +601,8 @@ extern "C" int pd_render(const pd_lattice* lat, const pd_state* st,
   PD_REQUIRE(env_ids != nullptr || m <= st->n_envs, "m exceeds n_envs");
   PD_REQUIRE(stop_stage >= PD_RENDER_CLEAN && stop_stage <= PD_RENDER_FINAL,
              "unknown stop_stage");
+  PD_REQUIRE(buffer_size >= 0.0 && buffer_size <= 0.25,
+             "buffer_size must lie in [0, 0.25]");
   PD_REQUIRE(lat->n_sites <= 2 * pd::kRenderThreads,
              "renderer supports lattices of at most 2048 sites");
   int64_t need = 0;
@@ -642,6 +639,8 @@ extern "C" int pd_render(const pd_lattice* lat, const pd_state* st,
     a.log2_size = log2_size;
     a.stop_stage = stop_stage;
     a.advance = advance_frame_count;
+    a.buffer = buffer_size;
+    a.bw = static_cast<int32_t>(buffer_size * image_size);
     a.out = frames_out + static_cast<size_t>(first) * frame_floats;
     a.n_generic = reinterpret_cast<int32_t*>(ws);
     a.generic = reinterpret_cast<uint8_t*>(ws + kFlagOffset);

@@ -30,7 +30,69 @@ struct RenderArgs {
   float* scratch;      // generic kernel: [grid][2][S][S]
   int32_t* n_generic;  // frames the cluster kernel handed to the generic one
   uint8_t* generic;    // [m] 1 = render with the generic kernel
+  double buffer;       // imaging.py:123 buffer_size (0: atoms in view only)
+  int32_t bw;          // int(buffer * S) pixels
 };
+
+// Pixel bin of an atom (imaging.py:129-143 np.histogram2d, then the flipud /
+// transpose of :150 and the crop of :165-168), in coordinates of the cropped
+// S x S image: row = S_ext - 1 - by - bw, col = bx - bw, both possibly
+// outside [0, S) when a buffer is used.
+struct AtomBin {
+  bool keep;
+  int row, col;
+};
+
+// np.linspace(lo, hi, n + 1)[i]: arange * step + start, last point = stop.
+__device__ __forceinline__ double hist_edge(double lo, double hi, double step,
+                                            int i, int n) {
+  return i == n ? hi : __dadd_rn(__dmul_rn(static_cast<double>(i), step), lo);
+}
+
+// searchsorted(edges, q, 'right') - 1 with the rightmost edge closed
+// (np.histogramdd); q must lie in [lo, hi].
+__device__ __forceinline__ int hist_bin(double q, double lo, double hi,
+                                        double step, int n) {
+  int j = static_cast<int>(floor((q - lo) / step));
+  j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+  while (j < n - 1 && hist_edge(lo, hi, step, j + 1, n) <= q) ++j;
+  while (j > 0 && hist_edge(lo, hi, step, j, n) > q) --j;
+  return j;
+}
+
+__device__ __forceinline__ AtomBin atom_bin(const double2 p, const Fov4& fv,
+                                            int S, double buffer, int bw) {
+  AtomBin out{false, 0, 0};
+  const double fw = __dsub_rn(fv.urx, fv.llx), fh = __dsub_rn(fv.ury, fv.lly);
+  if (buffer <= 0.0) {
+    // the caller passes get_atoms_in_bounds(fov): graphene.py:600-644
+    if (!(fv.llx <= p.x && p.x <= fv.urx && fv.lly <= p.y && p.y <= fv.ury))
+      return out;
+    const double qx = __ddiv_rn(__dsub_rn(p.x, fv.llx), fw);
+    const double qy = __ddiv_rn(__dsub_rn(p.y, fv.lly), fh);
+    int bx = static_cast<int>(floor(__dmul_rn(qx, static_cast<double>(S))));
+    int by = static_cast<int>(floor(__dmul_rn(qy, static_cast<double>(S))));
+    if (bx > S - 1) bx = S - 1;  // q == 1 falls in the last bin
+    if (by > S - 1) by = S - 1;
+    out.keep = true;
+    out.row = S - 1 - by;
+    out.col = bx;
+    return out;
+  }
+  // the caller passes the whole grid in the microscope frame
+  const double qx = __ddiv_rn(__dsub_rn(p.x, fv.llx), fw);
+  const double qy = __ddiv_rn(__dsub_rn(p.y, fv.lly), fh);
+  const double lo = -buffer, hi = __dadd_rn(1.0, buffer);
+  if (!(qx >= lo && qx <= hi && qy >= lo && qy <= hi)) return out;
+  const int n = S + 2 * bw;
+  const double step = __ddiv_rn(__dsub_rn(hi, lo), static_cast<double>(n));
+  const int bx = hist_bin(qx, lo, hi, step, n);
+  const int by = hist_bin(qy, lo, hi, step, n);
+  out.keep = true;
+  out.row = n - 1 - by - bw;
+  out.col = bx - bw;
+  return out;
+}
 
 __device__ __forceinline__ float u24(uint32_t w) {
   return static_cast<float>(w >> 8) * (1.0f / 16777216.0f);

@@ -65,6 +65,7 @@ constexpr int kKyHalf = kFastRadius + kAcc;      // zero-padded half width
 constexpr int kKyLen = 2 * kKyHalf + 8;
 constexpr int kPowTab = 1024;
 constexpr int kStages = 8;
+constexpr int kBias = 1024;           // atom rows / columns are stored + kBias
 
 struct ClusterShared {
   uint2 atoms[kFastAtoms];           // x = row << 16 | col, y = Z^e (float)
@@ -275,8 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         keep[round] = false;
         if (k < a.lat.n_sites) {
           const double2 p = site_position(__ldg(base + k), lt);
-          keep[round] = fv.llx <= p.x && p.x <= fv.urx && fv.lly <= p.y &&
-                        p.y <= fv.ury;
+          // with a buffer the exact test is on the normalised position, in
+          // (d); this box is a little generous
+          const double mx = (a.buffer > 0.0 ? a.buffer + 1e-9 : 0.0) * fw;
+          const double my = (a.buffer > 0.0 ? a.buffer + 1e-9 : 0.0) * fh;
+          keep[round] = fv.llx - mx <= p.x && p.x <= fv.urx + mx &&
+                        fv.lly - my <= p.y && p.y <= fv.ury + my;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep[round]);
         if (lane == 0) sh.warp_count[round][warp] = __popc(m);
@@ -390,15 +395,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (tid < n_total) {
         const int k = site_list[tid];
         const double2 p = site_position(__ldg(base + k), lt);
-        const double qx = (p.x - fv.llx) / fw, qy = (p.y - fv.lly) / fh;
-        int bx = static_cast<int>(floor(qx * S));
-        int by = static_cast<int>(floor(qy * S));
-        if (bx > S - 1) bx = S - 1;  // q == 1 falls in the last bin
-        if (by > S - 1) by = S - 1;
+        const AtomBin ab = atom_bin(p, fv, S, a.buffer, a.bw);
         const float wt = powf(k == si ? 14.0f : 6.0f, exponent);
-        sh.atoms[tid] = make_uint2((static_cast<uint32_t>(S - 1 - by) << 16) |
-                                       static_cast<uint32_t>(bx),
-                                   __float_as_uint(wt));
+        // an atom the exact test drops keeps its slot with zero weight, far
+        // from every strip
+        const uint32_t r16 = static_cast<uint32_t>(ab.keep ? ab.row + kBias : 0);
+        const uint32_t c16 = static_cast<uint32_t>(ab.keep ? ab.col + kBias : 0);
+        sh.atoms[tid] = make_uint2((r16 << 16) | c16,
+                                   __float_as_uint(ab.keep ? wt : 0.f));
       }
       if (tid == 0) {
         sh.work[0] = 0;
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         bool hit = false;
         if (i < n_atoms) {
           const uint32_t rcv = sh.atoms[i].x;
-          const int ar = static_cast<int>(rcv >> 16);
-          const int ac = static_cast<int>(rcv & 0xffffu);
+          const int ar = static_cast<int>(rcv >> 16) - kBias;
+          const int ac = static_cast<int>(rcv & 0xffffu) - kBias;
           hit = ar >= r_lo && ar <= r_hi && ac >= c_lo && ac <= c_hi;
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -465,10 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int ii = 0; ii < n_list; ++ii) {
           const int i = listed ? sh.strip[strip][ii] : ii;
           const uint2 at = sh.atoms[i];
-          const int ar = static_cast<int>(at.x >> 16);
+          const int ar = static_cast<int>(at.x >> 16) - kBias;
           const int d0 = img_r0 - ar;
           if (d0 > lwy || d0 + kAcc - 1 < -lwy) continue;
-          int dc = col - static_cast<int>(at.x & 0xffffu);
+          int dc = col - (static_cast<int>(at.x & 0xffffu) - kBias);
           dc = dc < 0 ? -dc : dc;
           const float wx = dc <= lwx ? __uint_as_float(at.y) * sh.kx[dc] : 0.f;
           const int idx = d0 + kKyHalf;  // >= 0: d0 >= -lwy - kAcc + 1

@@ -148,8 +148,8 @@ _SIGNATURES = {
     'pd_render_mask': ([_LP, _SP, _p, _i32, _i32, C.c_double, C.c_double, _p,
                         _p], C.c_int),
     'pd_sample_image_params': ([_SP, _p, _i32, _p], C.c_int),
-    'pd_render': ([_LP, _SP, _p, _i32, _i32, _i32, _i32, _p, _p, _i64, _p],
-                  C.c_int),
+    'pd_render': ([_LP, _SP, _p, _i32, _i32, _i32, _i32, C.c_double, _p, _p,
+                   _i64, _p], C.c_int),
     'pd_get_atoms_in_bounds': ([_LP, _SP, _p, _i32, _p, _p, _p, _p, _p],
                                C.c_int),
     'pd_get_silicon_position': ([_LP, _SP, _p, _p], C.c_int),

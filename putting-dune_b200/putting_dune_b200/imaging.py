@@ -48,10 +48,12 @@ def _workspace(device, image_size: int):
 
 def render_batch(batch, env_ids=None, image_size: int = 512,
                  stop_stage: int = 7, advance_frame_count: bool = True,
-                 out=None):
+                 out=None, buffer_size: float = 0.0):
   """Renders STEM frames for envs of an ``engine.EnvBatch`` on the device
   (imaging.py:239-265 ``generate_stem_image`` with each env's current FOV,
-  Si position and image parameters).  Returns float32 [m, S, S] in [0, 1]."""
+  Si position and image parameters).  Returns float32 [m, S, S] in [0, 1].
+  ``buffer_size`` > 0 is imaging.py:129-168 with the whole lattice as the
+  grid: atoms just outside the frame contribute their Gaussian tails."""
   import ctypes as C
   import torch
   from putting_dune_b200 import _native as nat
@@ -70,8 +72,8 @@ def render_batch(batch, env_ids=None, image_size: int = 512,
   with torch.cuda.device(dev):
     nat.check(nat.lib.pd_render(
         C.byref(batch.lattice_tables.c), C.byref(batch.c), P(ids), m,
-        image_size, int(stop_stage), int(bool(advance_frame_count)), P(out),
-        P(ws), ws.numel(),
+        image_size, int(stop_stage), int(bool(advance_frame_count)),
+        float(buffer_size), P(out), P(ws), ws.numel(),
         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
   return out
 

@@ -238,6 +238,18 @@ def perception_fixture():
         mu.AtomicGrid(q, z), fov, intensity_exponent=expo,
         image_dimensions=(size, size))
     res[f'mask_exponent_{e}'] = np.float64(expo)
+  # imaging.py:129-168: clean image with a buffer, whole grid as input
+  from oracle import pdune_oracle_imaging as oi
+  for e, buf in ((0, 0.1), (1, 0.25), (2, 0.07)):
+    q, z = oi.grid_in_microscope_frame(st, e)
+    f = st.fov[e]
+    fov = mu.MicroscopeFieldOfView(mods.Point(f[0], f[1]),
+                                   mods.Point(f[2], f[3]))
+    res[f'buffered_clean_{e}'] = im.generate_clean_image(
+        mu.AtomicGrid(q, z), fov, image_size=size,
+        intensity_exponent=float(st.image_params[e, 0]),
+        buffer_size=buf).astype(np.float32)
+    res[f'buffer_{e}'] = np.float64(buf)
   res['noisy_params'] = np.asarray(noisy, dtype=np.float64)
   np.savez_compressed(os.path.join(HERE, 'perception_reference.npz'), **res)
   print('perception_reference.npz', n, 'envs; mask classes',

@@ -96,3 +96,35 @@ def test_noisy_frames_match_oracle():
                                       advance_frame_count=False))
     for e in range(n):
       _check_stage(name, got[e], want[e][name])
+
+
+def test_buffered_clean_image(golden_dir):
+  """imaging.py:129-168 generate_clean_image(buffer_size > 0): atoms outside
+  the frame contribute their tails.  |d| <= 2e-6 like the unbuffered stage."""
+  from putting_dune_b200 import engine, imaging
+  fix = np.load(os.path.join(golden_dir, 'perception_reference.npz'))
+  seed, size = int(fix['seed']), int(fix['size'])
+  b = engine.EnvBatch(6, seed=seed)
+  b.reset()
+  for e in (0, 1, 2):
+    buf = float(fix[f'buffer_{e}'])
+    got = gh.np_(imaging.render_batch(b, env_ids=[e], image_size=size,
+                                      stop_stage=0, buffer_size=buf,
+                                      advance_frame_count=False))[0]
+    d = np.abs(got.astype(np.float64) - fix[f'buffered_clean_{e}'])
+    assert d.max() <= 2e-6, (e, d.max())
+  # full size, all stages, against the oracle; and the buffer matters
+  st = po.make_state(2, 19)
+  po.reset(st)
+  bb = gh.batch_from_oracle(st)
+  want = oi.render_env(st, 1, size=512, stages=True, buffer_size=0.1)
+  from tests.test_gpu_render import STAGES, _check_stage
+  for k, name in enumerate(STAGES):
+    got = gh.np_(imaging.render_batch(bb, env_ids=[1], image_size=512,
+                                      stop_stage=k, buffer_size=0.1,
+                                      advance_frame_count=False))[0]
+    _check_stage(name, got, want[name])
+  plain = gh.np_(imaging.render_batch(bb, env_ids=[1], image_size=512,
+                                      stop_stage=0,
+                                      advance_frame_count=False))[0]
+  assert np.abs(plain - want['clean']).max() > 1e-3

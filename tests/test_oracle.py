@@ -306,6 +306,14 @@ def test_perception_oracle_matches_reference(golden_dir):
     got = oi.mask_env(st, e, size, float(fix[f'mask_exponent_{e}']))
     np.testing.assert_array_equal(got, fix[f'mask_{e}'])
     assert set(got.reshape(-1).tolist()) <= {0, 6, 14}
+  for e in (0, 1, 2):  # imaging.py:129-168 buffered clean image
+    q, z = oi.grid_in_microscope_frame(st, e)
+    f = st.fov[e]
+    got = oi.clean_image(q, z, f[2] - f[0], f[3] - f[1],
+                         float(st.image_params[e, 0]), size,
+                         float(fix[f'buffer_{e}']))
+    np.testing.assert_allclose(got, fix[f'buffered_clean_{e}'], rtol=0,
+                               atol=2e-7)
   po.sample_noisy_image_parameters(st)
   np.testing.assert_array_equal(st.image_params, fix['noisy_params'])
 
