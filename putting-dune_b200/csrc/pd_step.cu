@@ -267,6 +267,228 @@ __global__ void __launch_bounds__(kStepThreads)
 }
 
 // ---------------------------------------------------------------------------
+// k_rollout_spec: the small-batch rollout with exact speculation.
+//
+// A small batch (BASELINE configs[1]: 4096 envs) leaves most lanes of the
+// machine idle and the rollout is one long dependent chain per env: one KMC
+// iteration (~1000 cycles of float64 latency) after the other.  But a control
+// whose first iteration draws a waiting time beyond the dwell time changes
+// nothing except the control counter, and that is the common case (~70 % of
+// the controls of the relative_random workload).  So a group of G lanes owns
+// one env and every round evaluates G iterations at once:
+//   lane 0      the true next iteration: (step t, iteration `it`);
+//   lane j > 0  iteration 0 of step t + j, assuming the control of step t ends
+//               without a further hop and steps t+1 .. t+j-1 do not hop.
+// Philox is counter based, so lane j simply uses (ctrl_count + j, 0).  After
+// the round the group commits the longest prefix whose assumptions held:
+// lane 0 alone if it hopped, otherwise lane 0 and the following no-hop steps
+// up to and including the first lane that hopped (its control then continues
+// in lane 0 of the next round).  Discarded lanes cost nothing the batch could
+// have used.  Every committed value is computed by the same expressions as
+// k_rollout from the same inputs, so results are bit-identical
+// (test_rollout_speculative_equals_serial).
+//
+// The FOV re-centre of simulator.py:156-169 happens at the end of a step that
+// hopped; whether it will happen is known as soon as the hop is (it depends on
+// the Si position only), so the speculative lanes already use the re-centred
+// FOV for the steps that follow.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_double(unsigned mask, double v,
+                                              int src) {
+  const int lo = __shfl_sync(mask, __double2loint(v), src);
+  const int hi = __shfl_sync(mask, __double2hiint(v), src);
+  return __hiloint2double(hi, lo);
+}
+
+template <int RATE, bool STAGE>
+__global__ void __launch_bounds__(kStepThreads)
+    k_rollout_spec(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
+  if constexpr (STAGE) {
+    tab = stage_tables(a.lat, smem);
+  } else {
+    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
+    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
+  }
+  const int G = a.lane_stride;  // power of two, 2..32
+  const int lane = threadIdx.x & 31;
+  const int j = lane & (G - 1);
+  const int gbase = lane - j;
+  const unsigned gmask = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const int64_t n = a.st.n_envs;
+  const int64_t gtid =
+      blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / G;
+  const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
+  const long long dwell = a.dwell_us_scalar;
+  const long long step_us = dwell + a.image_duration_us;
+  const double2* ctl = reinterpret_cast<const double2*>(a.controls_xy);
+  const int n_steps = a.n_steps;
+
+  for (int64_t e = gtid / G; e < n; e += n_groups) {
+    // ---- state of the env, replicated in the G lanes of its group ----
+    int si = a.st.si_idx[e];
+    const Lattice4 lat = load_lattice4(a.st.lattice, e);
+    double2 psi = site_position(tab.position(si), lat);
+    Fov4 fov = load_fov4(a.st.fov, e);
+    const double scale = a.st.fov_scale[e];
+    const uint32_t env_id = a.st.env_offset + static_cast<uint32_t>(e);
+    uint32_t ctrl_count = a.st.ctrl_count[e];
+    uint8_t status = a.st.status[e];
+    int transitions = 0, events = 0;
+    long long total = 0;
+    bool fov_dirty = false;
+    int t = 0;              // current step
+    uint32_t it = 0;        // next iteration of the current step's control
+    long long elapsed = 0;  // clock of the current control
+    double2 beam0 = make_double2(0.0, 0.0);  // beam of the current control
+    bool first = true;       // first round: lane 0 only, un-re-centred FOV
+    bool need_check = true;  // simulator.py:156 runs at t = 0 and after a hop
+    bool geo_stale = true, obs_stale = true;
+    bool pending_rec = false;
+    int nb[3] = {0, 0, 0};
+    double2 pn[3];
+    pn[0] = pn[1] = pn[2] = make_double2(0.0, 0.0);
+    Fov4 fov_n = fov;
+    double2 q_n = make_double2(0.0, 0.0);
+    double rx_n = 0.0, ry_n = 0.0;
+
+    if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
+    if (G + j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
+
+    while (t < n_steps) {
+      if (geo_stale) {
+        tab.neighbors(si, nb);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          pn[i] = site_position(tab.position(nb[i]), lat);
+        geo_stale = false;
+      }
+      if (obs_stale) {
+        // What the steps after the current control will see if it ends
+        // without another hop: the FOV after the pending re-centre and the
+        // observed Si position in it (action_adapters.py:163-188).
+        pending_rec = need_check && silicon_outside_safe_area(fov, psi);
+        fov_n = (pending_rec && !first) ? centred_fov(psi, scale) : fov;
+        if (relative) {
+          q_n = observe(fov_n, psi);
+          rx_n = __ddiv_rn(a.max_distance, __dsub_rn(fov_n.urx, fov_n.llx));
+          ry_n = __ddiv_rn(a.max_distance, __dsub_rn(fov_n.ury, fov_n.lly));
+        }
+        obs_stale = false;
+      }
+      const bool cont = it > 0;  // lane 0 continues a control already begun
+      const int step = t + j;
+      const bool valid = (first ? j == 0 : true) && step < n_steps;
+      double2 beam = beam0;
+      if (valid && !(j == 0 && cont)) {
+        const double2 c = ctl[static_cast<int64_t>(step) * n + e];
+        double2 pos = c;
+        if (relative) {
+          const double ax = fmin(fmax(c.x, -1.0), 1.0);
+          const double ay = fmin(fmax(c.y, -1.0), 1.0);
+          pos.x = fmin(fmax(__dadd_rn(q_n.x, __dmul_rn(ax, rx_n)), 0.0), 1.0);
+          pos.y = fmin(fmax(__dadd_rn(q_n.y, __dmul_rn(ay, ry_n)), 0.0), 1.0);
+        }
+        beam = microscope_to_material(fov_n, pos.x, pos.y);
+      }
+      if (step + 2 * G < n_steps)
+        prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
+
+      // ---- one KMC iteration per lane (graphene.py:658-694) ----
+      // A control whose clock landed exactly on the dwell time has ended
+      // (graphene.py:658): lane 0 then has nothing to evaluate.
+      const bool c_done = cont && elapsed >= dwell;
+      long long el = j == 0 ? elapsed : 0;
+      const uint4 w =
+          philox4x32_10(env_id, ctrl_count + static_cast<uint32_t>(j),
+                        j == 0 ? it : 0u, PD_STREAM_KMC, a.st.seed);
+      int slot = 0;
+      bool bad = false;
+      bool hop = rate_event<RATE>(a.ra, beam, psi, pn, u53(w.x, w.y),
+                                  u53(w.z, w.w), dwell, &el, &slot, &bad);
+      if (!valid || (j == 0 && c_done)) hop = bad = false;
+      const unsigned hops = (__ballot_sync(gmask, hop) & gmask) >> gbase;
+      const unsigned bads = (__ballot_sync(gmask, bad) & gmask) >> gbase;
+      const unsigned valids = (__ballot_sync(gmask, valid) & gmask) >> gbase;
+
+      // ---- commit the prefix whose assumptions held ----
+      int n_done = 0;  // steps completed by this round
+      int jh = -1;     // lane whose hop is applied
+      if (hops & 1u) {
+        jh = 0;
+        events += 1;
+        if (bads & 1u) status |= PD_ENV_BAD_RATE;
+      } else {
+        // the control of step t has ended: the step completes
+        const unsigned later = hops & ~1u;
+        if (later) {
+          jh = __ffs(later) - 1;
+          n_done = jh;
+        } else {
+          n_done = __popc(valids);
+        }
+        const int n_iter = n_done + (jh > 0 ? 1 : 0);  // iterations committed
+        events += n_iter - (c_done ? 1 : 0);
+        if (bads & ((n_iter >= 32 ? 0u : (1u << n_iter)) - 1u))
+          status |= PD_ENV_BAD_RATE;
+        const bool rec = pending_rec;  // simulator.py:156-169
+        if (j < n_done) {
+          if (a.si_idx_out)
+            a.si_idx_out[static_cast<int64_t>(step) * n + e] = si;
+          if (a.elapsed_us_out)
+            a.elapsed_us_out[static_cast<int64_t>(step) * n + e] =
+                step_us + ((j == 0 && rec) ? a.image_duration_us : 0);
+        }
+        total += static_cast<long long>(n_done) * step_us +
+                 (rec ? a.image_duration_us : 0);
+        if (rec) {
+          fov = centred_fov(psi, scale);
+          fov_dirty = true;
+          obs_stale = true;
+        }
+        need_check = false;
+        ctrl_count += static_cast<uint32_t>(n_done);
+        t += n_done;
+        it = 0;
+        elapsed = 0;
+      }
+      if (jh >= 0) {
+        const int src = gbase + jh;
+        const int slot_h = __shfl_sync(gmask, slot, src);
+        const long long el_h = __shfl_sync(gmask, el, src);
+        beam0.x = shfl_double(gmask, beam.x, src);
+        beam0.y = shfl_double(gmask, beam.y, src);
+        si = slot_h == 0 ? nb[0] : (slot_h == 1 ? nb[1] : nb[2]);
+        psi = slot_h == 0 ? pn[0] : (slot_h == 1 ? pn[1] : pn[2]);
+        transitions += 1;
+        elapsed = el_h;
+        it += 1;  // it was reset to 0 if the hop came from a later lane
+        need_check = true;
+        geo_stale = obs_stale = true;
+      }
+      if (first) {
+        first = false;
+        obs_stale = true;
+      }
+    }
+    if (j == 0) {
+      if (fov_dirty) store_fov4(a.st.fov, e, fov);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + e),
+                static_cast<unsigned long long>(total));
+      a.st.si_idx[e] = si;
+      a.st.ctrl_count[e] = ctrl_count;
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + e),
+                static_cast<unsigned long long>(events));
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + e),
+                static_cast<unsigned long long>(transitions));
+      a.st.status[e] = status;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // k_walk: the stepping kernel.  A *lane* owns one environment at a time and
 // walks it through its work (n_steps x n_controls controls); a *warp* owns a
 // contiguous range of environments.  Every trip of the main loop executes
@@ -638,6 +860,12 @@ static int lane_stride_for(int64_t n_envs) {
   return stride;
 }
 
+// PD_ROLLOUT_SPEC=0 keeps the serial k_rollout (A/B timing, parity tests).
+static bool speculation_enabled() {
+  const char* v = getenv("PD_ROLLOUT_SPEC");
+  return !v || v[0] != '0';
+}
+
 template <int RATE>
 static int launch_step(const StepArgs& a_in, bool rollout,
                        cudaStream_t stream) {
@@ -645,11 +873,15 @@ static int launch_step(const StepArgs& a_in, bool rollout,
   const bool staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
   const bool walk = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads);
   a.lane_stride = walk ? 1 : lane_stride_for(a.st.n_envs);
+  // Rollouts of small batches speculate over the idle lanes (k_rollout_spec).
+  const bool spec = rollout && !walk && a.lane_stride >= 2 && a.n_steps >= 2 &&
+                    a.dwell_us_scalar > 0 && speculation_enabled();
   const int grid = grid_for(a.st.n_envs * a.lane_stride, staged);
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
     auto kern = walk ? k_walk<RATE, true, false>
+                : spec        ? k_rollout_spec<RATE, true>
                 : rollout     ? k_rollout<RATE, true>
                               : k_step<RATE, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
@@ -658,6 +890,7 @@ static int launch_step(const StepArgs& a_in, bool rollout,
     kern<<<grid, kStepThreads, smem, stream>>>(a);
   } else {
     auto kern = walk ? k_walk<RATE, false, false>
+                : spec        ? k_rollout_spec<RATE, false>
                 : rollout     ? k_rollout<RATE, false>
                               : k_step<RATE, false>;
     kern<<<grid, kStepThreads, 0, stream>>>(a);

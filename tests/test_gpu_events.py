@@ -384,6 +384,47 @@ def test_rollout_with_relative_to_silicon_adapter(eng):
   np.testing.assert_array_equal(gh.np_(s_big)[:, :3000], gh.np_(s_small))
 
 
+@pytest.mark.parametrize('n', [37, 700, 4096, 11000, 21000])
+def test_rollout_speculative_equals_serial(eng, n, monkeypatch):
+  """k_rollout_spec (small batches: a group of 2..32 lanes evaluates the next
+  iterations of one env speculatively) commits exactly what the serial
+  k_rollout computes: per-step Si site and elapsed time, FOV, clocks, event
+  and transition counts, Philox control counter."""
+  from putting_dune_b200 import _native as nat
+  t_steps, seed = 45, 77
+  rng = np.random.default_rng(n)
+  acts = rng.uniform(-1.2, 1.2, size=(t_steps, n, 2))
+  direct = 0.5 + rng.uniform(-0.1, 0.1, size=(t_steps, n, 2))
+  cases = [
+      (po.RATE_PRIOR, None, 1500000, acts, nat.ACTION_RELATIVE_TO_SILICON),
+      (po.RATE_SIMPLE, None, 5000000, acts, nat.ACTION_RELATIVE_TO_SILICON),
+      (po.RATE_SIMPLE, None, 700000, direct, 0),
+      # many hops per control, re-centres every few steps
+      (po.RATE_CONSTANT, (2.0, 1.0, 3.0), 1500000, direct, 0),
+      # one-microsecond clock ticks: controls that end exactly on the dwell
+      (po.RATE_CONSTANT, (4e5, 3e5, 3e5), 3, direct, 0),
+  ]
+  for rate_fn, const, dwell, ctl, mode in cases:
+    spec = gh.rate_spec(rate_fn, constant=const)
+    res = []
+    for flag in ('1', '0'):
+      monkeypatch.setenv('PD_ROLLOUT_SPEC', flag)
+      b = eng.EnvBatch(n, seed=seed)
+      b.reset()
+      # a FOV the Si is not centred in: the t = 0 safe-area check matters
+      b.fov[::3] += 3.9
+      si, el = b.rollout(ctl, dwell, spec, record=True, action_mode=mode,
+                         max_distance_angstroms=1.42)
+      res.append((gh.np_(si), gh.np_(el), b.state_dict()))
+    (si_a, el_a, st_a), (si_b, el_b, st_b) = res
+    np.testing.assert_array_equal(si_a, si_b)
+    np.testing.assert_array_equal(el_a, el_b)
+    for k in ('si_idx', 'fov', 'ctrl_count', 'sim_time_us', 'n_events',
+              'n_transitions', 'status'):
+      np.testing.assert_array_equal(gh.np_(st_a[k]), gh.np_(st_b[k]), err_msg=k)
+    assert gh.np_(st_a['n_transitions']).sum() > 0
+
+
 def test_rollout_host_pipeline_matches_device_path(eng):
   """pd_rollout_actions_host (chunked H2D / step / D2H overlap) returns what
   the device-resident rollout computes."""
