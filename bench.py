@@ -482,7 +482,7 @@ def run_ours(args, cfg):
   launch_s = dev_ms / 1e3 / args.steps
   achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * env_steps_per_launch / launch_s / 1e9
   roofline = {
-      'kernel': 'pd::k_rollout', 'bound': 'hbm', 'achieved': achieved,
+      'kernel': 'pd::k_rollout_spec', 'bound': 'hbm', 'achieved': achieved,
       'peak': peak, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
       'unit': 'GB/s', 'frac': achieved / peak,
       'algorithmic_bytes_per_env_step': ALGORITHMIC_BYTES_PER_ENV_STEP,

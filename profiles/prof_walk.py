@@ -1,0 +1,68 @@
+"""Timing driver for the large-batch stepping kernel (k_walk) on the bench's
+workload: relative_random actions through the on-device
+RelativeToSiliconActionAdapter, prior rates, dwell 1.5 s.
+
+  python profiles/prof_walk.py [n_envs] [steps_per_launch] [rate] [reps]
+
+Prints env-steps/s (median of `reps` launches, L2 flushed between them).
+Knobs are read by the library from the environment: PD_PREPASS,
+PD_WALK_MIN_READY, PD_WALK_MAX_REPS.
+"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'putting-dune_b200'))
+
+import numpy as np
+import torch
+
+import putting_dune_b200 as pd
+from putting_dune_b200 import _native as nat
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+rate_name = sys.argv[3] if len(sys.argv) > 3 else 'prior'
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+rate = pd.RateSpec.prior() if rate_name == 'prior' else pd.RateSpec.simple()
+b = pd.EnvBatch(n, seed=0)
+b.reset()
+dev = b.device
+gen = torch.Generator(device=dev)
+gen.manual_seed(1)
+acts = [(torch.rand((steps, n, 2), generator=gen, device=dev,
+                    dtype=torch.float64) * 2 - 1) for _ in range(3)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+P = lambda t: C.c_void_p(t.data_ptr())
+
+
+def launch(i):
+  nat.check(nat.lib.pd_rollout_actions(
+      C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(rate.c),
+      P(acts[i % 3]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, steps,
+      2000000, None, None, stream))
+
+
+for i in range(3):
+  launch(i)
+torch.cuda.synchronize()
+ms = []
+for i in range(reps):
+  flush.zero_()
+  s, e = (torch.cuda.Event(enable_timing=True),
+          torch.cuda.Event(enable_timing=True))
+  s.record()
+  launch(i)
+  e.record()
+  torch.cuda.synchronize()
+  ms.append(s.elapsed_time(e))
+m = float(np.median(ms))
+ev = float(b.n_events.sum().item()) / float(b.ctrl_count.sum().item())
+print('n=%d steps=%d rate=%s prepass=%s min_ready=%s max_reps=%s: %.4f ms  '
+      '%.3e env-steps/s  (%.2f iterations per control)' %
+      (n, steps, rate_name, os.environ.get('PD_PREPASS', '1'),
+       os.environ.get('PD_WALK_MIN_READY', '-'),
+       os.environ.get('PD_WALK_MAX_REPS', '-'), m, n * steps / (m / 1e3), ev))

@@ -284,6 +284,94 @@ __device__ __forceinline__ bool kmc_event_drawn64(const double r64[3],
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// Float32 pre-pass: "does this iteration certainly end its control without a
+// hop?"
+//
+// An iteration whose waiting time overshoots the dwell time changes nothing
+// but the event and control counters (graphene.py:677: elapsed > dwell ->
+// break), and with the prior / simple rates that is ~70 % of all iterations.
+// Deciding it does not need the float64 chain: a float32 evaluation with
+// *one-sided* bounds -- an upper bound of the total rate and a lower bound of
+// the unit-exponential draw -- gives a lower bound of the waiting time; if
+// even that overshoots, the exact computation does too.  Everything else
+// (hops, near misses, non-finite inputs) falls through to the float64
+// iteration, so results are unchanged bit for bit
+// (tests: test_prepass_equals_exact).
+//
+// Error budget (relative): beam offset 2e-6 A absolute -> 1e-4 on a rate that
+// matters; __expf 1e-5; the sum 2e-7; folded into tot * 1.002 + 1e-30.  The
+// draw uses the top 24 bits of the Philox word the exact path turns into u53
+// (truncation: u24 <= u53, and 1 - u24 is exact in float32), __logf absolute
+// error 4e-7: draw * 0.999 - 1e-6.  Waiting time * 0.998 against the remaining
+// microseconds + 2 covers the division, the float32 scale of the exact path
+// and the microsecond rounding.
+// ---------------------------------------------------------------------------
+template <int RATE>
+struct PrepassGeo {
+  // PD_RATE_PRIOR: peak positions 0.85 * (cos, -sin) of the three neighbour
+  // directions (bond units); PD_RATE_SIMPLE: neighbour offsets (angstrom).
+  float cx[3], cy[3];
+};
+
+template <int RATE, class Tables>
+__device__ __forceinline__ void prepass_geometry(const Tables& tab, int si,
+                                                 const Lattice4& lat,
+                                                 PrepassGeo<RATE>* g) {
+  int nb[3];
+  tab.neighbors(si, nb);
+  const double2 b0 = tab.position(si);
+  const float c = static_cast<float>(lat.c), s = static_cast<float>(lat.s);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double2 bi = tab.position(nb[i]);
+    const float dx = static_cast<float>(bi.x - b0.x);
+    const float dy = static_cast<float>(bi.y - b0.y);
+    const float nx = dx * c + dy * s;  // graphene.py:545-557
+    const float ny = dy * c - dx * s;
+    if (RATE == PD_RATE_PRIOR) {
+      const float inv = 0.85f * rsqrtf(nx * nx + ny * ny);
+      g->cx[i] = nx * inv;
+      g->cy[i] = -ny * inv;  // mirror quirk, see rates_prior
+    } else {
+      g->cx[i] = nx;
+      g->cy[i] = ny;
+    }
+  }
+}
+
+// bx, by: beam - Si in angstrom; word: Philox word x of the iteration;
+// rem_us: dwell - elapsed (> 0).
+template <int RATE>
+__device__ __forceinline__ bool certainly_no_hop(const PrepassGeo<RATE>& g,
+                                                 float bx, float by,
+                                                 uint32_t word,
+                                                 long long rem_us) {
+  float tot = 0.f;
+  if (RATE == PD_RATE_PRIOR) {
+    const float x = bx * (1.0f / 1.42f), y = by * (1.0f / 1.42f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float dx = x - g.cx[i], dy = y - g.cy[i];
+      tot += 0.23104906f * __expf(-5.0f * (dx * dx + dy * dy));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float dx = bx - g.cx[i], dy = by - g.cy[i];
+      tot += __fdividef(
+          1.0f, (dx * dx + dy * dy) * (16.0f / (1.42f * 1.42f)) + 1.0f);
+    }
+  }
+  const float u24 = static_cast<float>(word >> 8) * (1.0f / 16777216.0f);
+  const float draw_lb = -__logf(1.0f - u24) * 0.999f - 1e-6f;
+  const float t_lb =
+      fminf(__fdividef(draw_lb, tot * 1.002f + 1e-30f), 3600.0f);
+  // tot >= 0 is false for NaN inputs: those take the exact path (and its
+  // PD_ENV_BAD_RATE flag).
+  return (tot >= 0.f) && (t_lb * 0.998e6f > __ll2float_ru(rem_us) + 2.0f);
+}
+
 // Frame transforms: microscope_utils.py:362-369 / :421-428.
 __device__ __forceinline__ double2 microscope_to_material(const Fov4& f,
                                                           double px,
@@ -359,6 +447,10 @@ struct StepArgs {
                               // k_rollout; small batches trade idle lanes for
                               // more warps and less intra-warp divergence)
   int32_t action_mode;        // pd_action_mode (rollouts)
+  int32_t prepass;            // 1: float32 pre-pass (certainly_no_hop) enabled
+  int32_t walk_min_ready;     // k_walk: lanes with an exact iteration pending
+  int32_t walk_max_reps;      //   that end the bookkeeping repeats / their cap
+  int32_t walk_controls_per_pass;  // controls a lane may settle per pass
   double max_distance;        // RelativeToSilicon adapter, angstroms
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]

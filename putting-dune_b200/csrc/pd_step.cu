@@ -541,6 +541,18 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   int t = 0, c = 0;
   bool fov_dirty = false, any_recentre = false;
   bool ready = false;  // an iteration of the current control is pending
+  // float32 pre-pass (pd_kmc.cuh certainly_no_hop): `checked` = the pending
+  // iteration went through it and needs the float64 chain; `beam` holds the
+  // raw control until the float64 beam is needed (beam_ready).
+  constexpr int kCtlPrefetch = 5;
+  constexpr bool kPrepass =
+      !EPISODE && (RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR);
+  bool checked = false, beam_ready = false, geo_ok = false, obs_ok = false;
+  bool need_check = true;
+  PrepassGeo<RATE> geo;
+  float qfx = 0.f, qfy = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) geo.cx[i] = geo.cy[i] = 0.f;
   r.si = 0;
   // episode mode: goal, simulated clock, actions taken (eval_lib.py:110-150)
   double2 goal = make_double2(0.0, 0.0);
@@ -548,156 +560,240 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   int actions = 0;
 
   while (true) {
-    // Bookkeeping runs twice per trip so that a lane whose environment just
-    // ended (finalise -> pull the next one -> set up its first control) is
-    // ready again for this trip's iteration.
+    // Bookkeeping repeats until enough lanes hold an iteration that needs the
+    // float64 chain (a lane whose environment just ended finalises it, pulls
+    // the next one and sets up its first control; with the pre-pass most
+    // controls are consumed here as well), or until nothing can change.
 #pragma unroll 1
-    for (int rep = 0; rep < 2; ++rep) {
+    for (int rep = 0;; ++rep) {
       // ---- next control / end of step / end of environment ----
-      if (env >= 0 && !ready) {
+      // A lane leaves this block with an iteration that needs the float64
+      // chain pending (ready && checked) or without an env.  Controls whose
+      // iteration the float32 pre-pass can settle (certainly_no_hop) are
+      // consumed right here.
+      if (env >= 0 && !(ready && checked)) {
+        // A lane settles at most walk_controls_per_pass controls per pass
+        // (it still finishes its step / env): without a cap the warp waits
+        // for its luckiest lane's run of settled controls, with a cap of one
+        // the per-pass overhead (ballots, env pull) is paid per control.
+        int settled = 0;
         while (true) {
-          if constexpr (EPISODE) {
-            bool done = false, reached = false;
-            float reward = 0.f;
-            if (c > 0) {
-              // step end: image, re-centre, goal test (simulator.py:152-169,
-              // goals.py:143-181)
-              long long step_us = a.ep.dwell_us + a.ep.image_duration_us;
-              if (silicon_outside_safe_area(fov, r.psi)) {
-                fov = centred_fov(r.psi, a.st.fov_scale[env]);
-                step_us += a.ep.image_duration_us;
+          if (!ready) {
+            if constexpr (EPISODE) {
+              bool done = false, reached = false;
+              float reward = 0.f;
+              if (c > 0) {
+                // step end: image, re-centre, goal test (simulator.py:152-169,
+                // goals.py:143-181)
+                long long step_us = a.ep.dwell_us + a.ep.image_duration_us;
+                if (silicon_outside_safe_area(fov, r.psi)) {
+                  fov = centred_fov(r.psi, a.st.fov_scale[env]);
+                  step_us += a.ep.image_duration_us;
+                }
+                env_time += step_us;
+                ++actions;
+                c = 0;
+                if (goal_reached(fov, r.psi, goal)) {
+                  done = reached = true;
+                  reward = static_cast<float>(
+                      pow(kGamma, static_cast<double>(step_us) / 1e6));
+                } else if (actions >= a.ep.step_limit) {
+                  done = true;  // StepLimitWrapper truncation
+                }
               }
-              env_time += step_us;
-              ++actions;
-              c = 0;
-              if (goal_reached(fov, r.psi, goal)) {
-                done = reached = true;
-                reward = static_cast<float>(
-                    pow(kGamma, static_cast<double>(step_us) / 1e6));
-              } else if (actions >= a.ep.step_limit) {
-                done = true;  // StepLimitWrapper truncation
-              }
-            }
-            // eval_lib.py:128: simulated-time limit; no goal: nothing to do
-            if (!done && (!(goal.x == goal.x) ||
-                          !(env_time < a.ep.timeout_us)))
-              done = true;
-            if (!done) {
-              int nb[3];
-              tab.neighbors(r.si, nb);
-              double2 pn[3];
+              // eval_lib.py:128: simulated-time limit; no goal: nothing to do
+              if (!done && (!(goal.x == goal.x) ||
+                            !(env_time < a.ep.timeout_us)))
+                done = true;
+              if (!done) {
+                int nb[3];
+                tab.neighbors(r.si, nb);
+                double2 pn[3];
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
-                pn[i] = site_position(tab.position(nb[i]), r.lat);
-              const double2 ctl = greedy_control(fov, r.psi, pn, goal,
-                                                 a.ep.argmax_x, a.ep.argmax_y);
-              beam = microscope_to_material(fov, ctl.x, ctl.y);
-              dwell = a.ep.dwell_us;
-              elapsed = 0;
-              it = 0;
-              if (dwell > 0) {
-                ready = true;
-                break;
+                for (int i = 0; i < 3; ++i)
+                  pn[i] = site_position(tab.position(nb[i]), r.lat);
+                const double2 ctl = greedy_control(
+                    fov, r.psi, pn, goal, a.ep.argmax_x, a.ep.argmax_y);
+                beam = microscope_to_material(fov, ctl.x, ctl.y);
+                beam_ready = true;
+                dwell = a.ep.dwell_us;
+                elapsed = 0;
+                it = 0;
+                if (dwell > 0) {
+                  ready = true;
+                  checked = true;  // the greedy beam sits on a neighbour: hops
+                  break;
+                }
+                r.ctrl_count += 1;  // zero dwell: the control is a no-op
+                c = 1;
+                continue;
               }
-              r.ctrl_count += 1;  // zero dwell: the control is a no-op
-              c = 1;
-              continue;
-            }
-            // ---- episode finished: EvalResult + state write-back ----
-            store_fov4(a.st.fov, env, fov);
-            a.st.sim_time_us[env] = env_time;
-            a.st.si_idx[env] = r.si;
-            a.st.ctrl_count[env] = r.ctrl_count;
-            a.st.n_events[env] = r.events;
-            a.st.n_transitions[env] = r.transitions;
-            a.st.status[env] = r.status;
-            pd_episode_stats out;
-            out.num_actions = actions;
-            out.env_seconds =
-                reached ? static_cast<float>(
-                              static_cast<double>(env_time) / 1e6)
-                        : nanf("");
-            out.total_reward = reward;
-            out.reached_goal = reached ? 1 : 0;
-            out.pad_[0] = out.pad_[1] = out.pad_[2] = 0;
-            a.stats[env] = out;
-            env = -1;
-            break;
-          }
-          if (c < n_controls) {
-            const int64_t ci = rollout ? static_cast<int64_t>(t) * n + env
-                                       : env * n_controls + c;
-            dwell = a.dwell_us ? a.dwell_us[ci] : a.dwell_us_scalar;
-            if (dwell > 0) {
+              // ---- episode finished: EvalResult + state write-back ----
+              store_fov4(a.st.fov, env, fov);
+              a.st.sim_time_us[env] = env_time;
+              a.st.si_idx[env] = r.si;
+              a.st.ctrl_count[env] = r.ctrl_count;
+              a.st.n_events[env] = r.events;
+              a.st.n_transitions[env] = r.transitions;
+              a.st.status[env] = r.status;
+              pd_episode_stats out;
+              out.num_actions = actions;
+              out.env_seconds =
+                  reached ? static_cast<float>(
+                                static_cast<double>(env_time) / 1e6)
+                          : nanf("");
+              out.total_reward = reward;
+              out.reached_goal = reached ? 1 : 0;
+              out.pad_[0] = out.pad_[1] = out.pad_[2] = 0;
+              a.stats[env] = out;
+              env = -1;
+              break;
+            } else if (c < n_controls) {
+              if (settled >= a.walk_controls_per_pass) break;
+              const int64_t ci = rollout ? static_cast<int64_t>(t) * n + env
+                                         : env * n_controls + c;
+              dwell = a.dwell_us ? a.dwell_us[ci] : a.dwell_us_scalar;
+              if (dwell <= 0) {
+                r.ctrl_count += 1;  // zero dwell: no rate evaluation
+                ++c;
+                continue;
+              }
               // controls are fetched one step ahead (the first one when the
               // env is pulled) so their HBM latency hides behind arithmetic
-              double2 ctl = next_ctl;
+              beam = next_ctl;  // raw control until beam_ready
               if (rollout) {
                 if (t + 1 < n_steps)
                   next_ctl = reinterpret_cast<const double2*>(
                       a.controls_xy)[static_cast<int64_t>(t + 1) * n + env];
-                if (a.action_mode == PD_ACTION_RELATIVE_TO_SILICON)
-                  ctl = relative_to_silicon(fov, r.psi, ctl, a.max_distance);
+                // a control the pre-pass settles takes a few hundred cycles:
+                // pull the action stream into L1 several steps ahead
+                if (t + kCtlPrefetch < n_steps)
+                  prefetch_l1(reinterpret_cast<const double2*>(a.controls_xy) +
+                              static_cast<int64_t>(t + kCtlPrefetch) * n + env);
               } else if (c > 0) {
-                ctl = reinterpret_cast<const double2*>(a.controls_xy)[ci];
+                beam = reinterpret_cast<const double2*>(a.controls_xy)[ci];
               }
-              // simulator.py:137 microscope frame -> material frame
-              beam = a.material_frame
-                         ? ctl
-                         : microscope_to_material(fov, ctl.x, ctl.y);
+              beam_ready = false;
               elapsed = 0;
               it = 0;
               ready = true;
+              checked = false;
+            } else {
+              // all controls applied: take the image (simulator.py:152)
+              if (!a.material_frame) {
+                step_elapsed += a.image_duration_us;
+                // simulator.py:156; the answer only changes when the Si hops
+                // (need_check: set when the env is pulled and by every hop)
+                if (need_check) {
+                  need_check = false;
+                  if (silicon_outside_safe_area(fov, r.psi)) {
+                    fov = centred_fov(r.psi, a.st.fov_scale[env]);
+                    step_elapsed += a.image_duration_us;  // simulator.py:168-169
+                    fov_dirty = true;
+                    any_recentre = true;
+                    obs_ok = false;
+                  }
+                }
+              }
+              if (rollout) {
+                if (a.si_idx_out)
+                  a.si_idx_out[static_cast<int64_t>(t) * n + env] = r.si;
+                if (a.elapsed_us_out)
+                  a.elapsed_us_out[static_cast<int64_t>(t) * n + env] =
+                      step_elapsed;
+              }
+              total += step_elapsed;
+              ++t;
+              if (t < n_steps) {
+                c = 0;
+                step_elapsed = 0;
+                continue;
+              }
+              // ---- environment finished: write back ----
+              if (fov_dirty) store_fov4(a.st.fov, env, fov);
+              if (!a.material_frame)
+                atomicAdd(reinterpret_cast<unsigned long long*>(
+                              a.st.sim_time_us + env),
+                          static_cast<unsigned long long>(total));
+              a.st.si_idx[env] = r.si;
+              a.st.ctrl_count[env] = r.ctrl_count;
+              atomicAdd(
+                  reinterpret_cast<unsigned long long*>(a.st.n_events + env),
+                  static_cast<unsigned long long>(r.events));
+              atomicAdd(reinterpret_cast<unsigned long long*>(
+                            a.st.n_transitions + env),
+                        static_cast<unsigned long long>(r.transitions));
+              a.st.status[env] = r.status;
+              if (a.out.elapsed_us) a.out.elapsed_us[env] = total;
+              if (a.out.transitions) a.out.transitions[env] = r.transitions;
+              if (a.out.events) a.out.events[env] = r.events;
+              if (a.out.recentred) a.out.recentred[env] = any_recentre ? 1 : 0;
+              if (a.out.si_xy)
+                reinterpret_cast<double2*>(a.out.si_xy)[env] = r.psi;
+              if (a.out.log_count) a.out.log_count[env] = r.log_n;
+              env = -1;
               break;
             }
-            r.ctrl_count += 1;  // zero dwell: no rate evaluation
-            ++c;
-            continue;
           }
-          // all controls applied: take the image (simulator.py:152)
-          if (!a.material_frame) {
-            step_elapsed += a.image_duration_us;
-            if (silicon_outside_safe_area(fov, r.psi)) {  // simulator.py:156
-              fov = centred_fov(r.psi, a.st.fov_scale[env]);
-              step_elapsed += a.image_duration_us;  // simulator.py:168-169
-              fov_dirty = true;
-              any_recentre = true;
+          // ---- an iteration is pending: can float32 settle it? ----
+          if (checked) break;
+          checked = true;
+          if constexpr (kPrepass) {
+            if (a.prepass) {
+              if (!geo_ok) {
+                prepass_geometry<RATE>(tab, r.si, r.lat, &geo);
+                geo_ok = true;
+              }
+              float bx, by;
+              if (beam_ready || a.material_frame) {
+                bx = static_cast<float>(beam.x - r.psi.x);
+                by = static_cast<float>(beam.y - r.psi.y);
+              } else {
+                // beam - Si through the microscope frame, as the exact path
+                // forms it (action_adapters.py:163-188, simulator.py:137)
+                const float wx = static_cast<float>(fov.urx - fov.llx);
+                const float wy = static_cast<float>(fov.ury - fov.lly);
+                if (!obs_ok) {
+                  qfx = static_cast<float>(r.psi.x - fov.llx) / wx;
+                  qfy = static_cast<float>(r.psi.y - fov.lly) / wy;
+                  obs_ok = true;
+                }
+                float px = static_cast<float>(beam.x);
+                float py = static_cast<float>(beam.y);
+                if (rollout &&
+                    a.action_mode == PD_ACTION_RELATIVE_TO_SILICON) {
+                  const float md = static_cast<float>(a.max_distance);
+                  px = fminf(fmaxf(px, -1.f), 1.f);
+                  py = fminf(fmaxf(py, -1.f), 1.f);
+                  px = fminf(fmaxf(qfx + px * __fdividef(md, wx), 0.f), 1.f);
+                  py = fminf(fmaxf(qfy + py * __fdividef(md, wy), 0.f), 1.f);
+                }
+                bx = (px - qfx) * wx;
+                by = (py - qfy) * wy;
+              }
+              const uint4 w = philox4x32_10(r.env_id, r.ctrl_count, it,
+                                            PD_STREAM_KMC, a.st.seed);
+              if (certainly_no_hop<RATE>(geo, bx, by, w.x, dwell - elapsed)) {
+                r.events += 1;
+                step_elapsed += dwell;  // simulator.py:149
+                r.ctrl_count += 1;
+                ++c;
+                ready = false;
+                ++settled;
+                continue;
+              }
             }
           }
-          if (rollout) {
-            if (a.si_idx_out)
-              a.si_idx_out[static_cast<int64_t>(t) * n + env] = r.si;
-            if (a.elapsed_us_out)
-              a.elapsed_us_out[static_cast<int64_t>(t) * n + env] =
-                  step_elapsed;
+          if (!beam_ready) {
+            double2 ctl = beam;
+            if (rollout && a.action_mode == PD_ACTION_RELATIVE_TO_SILICON)
+              ctl = relative_to_silicon(fov, r.psi, ctl, a.max_distance);
+            // simulator.py:137 microscope frame -> material frame
+            beam = a.material_frame
+                       ? ctl
+                       : microscope_to_material(fov, ctl.x, ctl.y);
+            beam_ready = true;
           }
-          total += step_elapsed;
-          ++t;
-          if (t < n_steps) {
-            c = 0;
-            step_elapsed = 0;
-            continue;
-          }
-          // ---- environment finished: write back ----
-          if (fov_dirty) store_fov4(a.st.fov, env, fov);
-          if (!a.material_frame)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + env),
-                      static_cast<unsigned long long>(total));
-          a.st.si_idx[env] = r.si;
-          a.st.ctrl_count[env] = r.ctrl_count;
-          atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + env),
-                    static_cast<unsigned long long>(r.events));
-          atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + env),
-                    static_cast<unsigned long long>(r.transitions));
-          a.st.status[env] = r.status;
-          if (a.out.elapsed_us) a.out.elapsed_us[env] = total;
-          if (a.out.transitions) a.out.transitions[env] = r.transitions;
-          if (a.out.events) a.out.events[env] = r.events;
-          if (a.out.recentred) a.out.recentred[env] = any_recentre ? 1 : 0;
-          if (a.out.si_xy)
-            reinterpret_cast<double2*>(a.out.si_xy)[env] = r.psi;
-          if (a.out.log_count) a.out.log_count[env] = r.log_n;
-          env = -1;
           break;
         }
       }
@@ -710,9 +806,17 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
           env = cand;
           // first control of this env, and the lines of the env this lane is
           // likely to pull next, are requested before anything waits
-          if (!EPISODE && n_controls > 0)
+          if (!EPISODE && n_controls > 0) {
             next_ctl = reinterpret_cast<const double2*>(
                 a.controls_xy)[rollout ? env : env * n_controls];
+            if (rollout) {
+#pragma unroll
+              for (int k = 2; k < kCtlPrefetch; ++k)
+                if (k < n_steps)
+                  prefetch_l1(reinterpret_cast<const double2*>(a.controls_xy) +
+                              static_cast<int64_t>(k) * n + env);
+            }
+          }
           if (cand + 32 < hi) {
             prefetch_env(a, cand + 32);
             if (!EPISODE && n_controls > 0)
@@ -733,9 +837,20 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
           fov_dirty = false;
           any_recentre = false;
           ready = false;
+          checked = false;
+          geo_ok = obs_ok = false;
+          need_check = true;
         }
         cursor += __popc(im);
       }
+      const unsigned busy = __ballot_sync(0xffffffffu, env >= 0);
+      const unsigned pending =
+          __ballot_sync(0xffffffffu, env >= 0 && ready && checked);
+      const bool can_change =
+          (busy & ~pending) != 0u || (cursor < hi && busy != 0xffffffffu);
+      if (!can_change || __popc(pending) >= a.walk_min_ready ||
+          rep + 1 >= a.walk_max_reps)
+        break;
     }
     if (!__any_sync(0xffffffffu, env >= 0)) break;
 
@@ -773,11 +888,17 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
           r.log_n += 1;
         }
       }
+      if (hit) {
+        geo_ok = obs_ok = false;
+        need_check = true;
+      }
       if (elapsed >= dwell) {  // control finished
         step_elapsed += dwell;  // simulator.py:149
         r.ctrl_count += 1;
         ++c;
         ready = false;
+      } else {
+        checked = false;  // the control continues: pre-pass its next iteration
       }
     }
   }
@@ -848,16 +969,33 @@ static int grid_for(int64_t n_envs, bool staged) {
 // number of warps (latency hiding) and divides the chance that a warp needs a
 // second KMC iteration; the idle lanes cost nothing the batch could have used.
 // Target: ~2.5 warps per scheduler (profiles/r01_kernel_choice.md).
-static int lane_stride_for(int64_t n_envs) {
+static int lane_stride_forced() {
   static const int forced = [] {
     const char* v = getenv("PD_LANE_STRIDE");
     return v ? atoi(v) : 0;
   }();
+  return forced;
+}
+
+static int lane_stride_for(int64_t n_envs) {
+  const int forced = lane_stride_forced();
   if (forced > 0) return forced;
   const int64_t want_threads = static_cast<int64_t>(sm_count()) * 4 * 32 * 5 / 2;
   int stride = 1;
   while (stride < 32 && n_envs * stride * 2 <= want_threads) stride *= 2;
   return stride;
+}
+
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : fallback;
+}
+
+// PD_PREPASS=0 sends every iteration through the float64 chain (A/B timing,
+// parity tests).
+static bool prepass_enabled() {
+  const char* v = getenv("PD_PREPASS");
+  return !v || v[0] != '0';
 }
 
 // PD_ROLLOUT_SPEC=0 keeps the serial k_rollout (A/B timing, parity tests).
@@ -873,9 +1011,17 @@ static int launch_step(const StepArgs& a_in, bool rollout,
   const bool staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
   const bool walk = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads);
   a.lane_stride = walk ? 1 : lane_stride_for(a.st.n_envs);
-  // Rollouts of small batches speculate over the idle lanes (k_rollout_spec).
+  a.prepass = prepass_enabled() ? 1 : 0;
+  a.walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
+  a.walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
+  a.walk_controls_per_pass = env_int("PD_WALK_CONTROLS", 4);
+  // Rollouts of small batches speculate over the idle lanes (k_rollout_spec);
+  // every lane then does useful work, so the group is twice as wide as the
+  // idle-lane stride (measured at 4096 envs: G = 8: 5.1e9, 16: 6.0e9, 32:
+  // 4.1e9 env-steps/s).
   const bool spec = rollout && !walk && a.lane_stride >= 2 && a.n_steps >= 2 &&
                     a.dwell_us_scalar > 0 && speculation_enabled();
+  if (spec && a.lane_stride < 32 && !lane_stride_forced()) a.lane_stride *= 2;
   const int grid = grid_for(a.st.n_envs * a.lane_stride, staged);
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
@@ -954,7 +1100,11 @@ static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
 }
 
 template <int RATE>
-static int launch_episode_walk(const StepArgs& a, cudaStream_t stream) {
+static int launch_episode_walk(const StepArgs& a_in, cudaStream_t stream) {
+  StepArgs a = a_in;
+  a.walk_min_ready = 33;  // episodes: two bookkeeping passes per trip
+  a.walk_max_reps = 2;
+  a.walk_controls_per_pass = 1 << 30;
   const bool staged = a.st.n_envs >= 2LL * sm_count() * kStepThreads;
   const int grid = grid_for(a.st.n_envs, staged);
   if (staged) {
@@ -1247,7 +1397,7 @@ namespace pd {
 // the D2H copy of chunk i-1 overlap (PCIe is full duplex).
 struct HostPipeline {
   cudaStream_t h2d = nullptr, d2h = nullptr;
-  cudaEvent_t start = nullptr, copied[8] = {}, stepped[8] = {};
+  cudaEvent_t start = nullptr, copied[16] = {}, stepped[16] = {};
   int device = -1;
 };
 
@@ -1259,7 +1409,7 @@ static int host_pipeline(HostPipeline** out) {
     PD_CUDA_OK(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
     PD_CUDA_OK(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
     PD_CUDA_OK(cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming));
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
       PD_CUDA_OK(cudaEventCreateWithFlags(&p.copied[i], cudaEventDisableTiming));
       PD_CUDA_OK(
           cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming));
@@ -1290,21 +1440,29 @@ extern "C" int pd_rollout_actions_host(
   pd::HostPipeline* pipe = nullptr;
   int rcode = pd::host_pipeline(&pipe);
   if (rcode != PD_OK) return rcode;
-  // Short first and last chunks keep the pipeline's fill (first H2D copy) and
-  // drain (last D2H copy) small; the kernels in between overlap both copies.
-  const int n_chunks = n_steps >= 64 ? 5 : (n_steps >= 32 ? 4 : 1);
+  // The call is bound by the H2D copy of the actions (16 B per env-step over
+  // PCIe, 47 GB/s with both directions busy: profiles/prof_pcie.py); the
+  // kernel and the D2H copy of chunk i hide behind the H2D copy of chunk i+1,
+  // what is left over is the last chunk's kernel + D2H copy.  Each chunk costs
+  // ~10 us of stream hand-offs, so chunks are 4 MiB (measured at 16.8 MB in:
+  // 4 or 8 chunks 0.51 ms, 12: 0.56, 16: 0.60).  PD_HOST_CHUNKS overrides.
+  static const int forced_chunks = [] {
+    const char* v = getenv("PD_HOST_CHUNKS");
+    return v ? atoi(v) : 0;
+  }();
+  int n_chunks = static_cast<int>(
+      static_cast<int64_t>(n_steps) * n * 2 * sizeof(double) >> 22);
+  if (forced_chunks > 0) n_chunks = forced_chunks;
+  if (n_chunks > 16) n_chunks = 16;
+  if (n_chunks > n_steps) n_chunks = n_steps;
+  if (n_chunks < 1) n_chunks = 1;
   // staging may still be read by earlier work queued on `s`
   PD_CUDA_OK(cudaEventRecord(pipe->start, s));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
-  int t0[9];
-  static const int kSixteenths[6] = {0, 1, 6, 11, 15, 16};
+  int t0[17];
   for (int c = 0; c <= n_chunks; ++c)
-    t0[c] = n_chunks == 5
-                ? static_cast<int>(static_cast<int64_t>(n_steps) *
-                                   kSixteenths[c] / 16)
-                : static_cast<int>(static_cast<int64_t>(n_steps) * c /
-                                   n_chunks);
+    t0[c] = static_cast<int>(static_cast<int64_t>(n_steps) * c / n_chunks);
   for (int c = 0; c < n_chunks; ++c) {
     const size_t off = static_cast<size_t>(t0[c]) * n * 2;
     const size_t cnt = static_cast<size_t>(t0[c + 1] - t0[c]) * n * 2;

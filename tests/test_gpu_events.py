@@ -425,6 +425,51 @@ def test_rollout_speculative_equals_serial(eng, n, monkeypatch):
     assert gh.np_(st_a['n_transitions']).sum() > 0
 
 
+def test_prepass_equals_exact(eng, monkeypatch):
+  """The float32 pre-pass of the large-batch kernel (certainly_no_hop: controls
+  whose waiting time certainly overshoots the dwell time skip the float64
+  chain) never changes a result: rollouts, multi-control steps with ragged
+  dwell times and material-frame apply_control agree bit for bit with
+  PD_PREPASS=0, including event counts and the Philox control counter."""
+  from putting_dune_b200 import _native as nat
+  n, t_steps, seed = 90000, 7, 91
+  rng = np.random.default_rng(12)
+  acts = rng.uniform(-1.3, 1.3, size=(t_steps, n, 2))
+  direct = 0.5 + rng.uniform(-0.12, 0.12, size=(t_steps, n, 2))
+  direct[0, :50] = np.nan            # non-finite controls take the exact path
+  direct[1, 50:100] = 1e9
+  ctl3 = 0.5 + rng.uniform(-0.1, 0.1, size=(n, 3, 2))
+  dwell3 = rng.integers(0, 4000000, size=(n, 3))
+  beam_m = rng.uniform(-3, 3, size=(n, 1, 2))
+  results = []
+  for flag in ('1', '0'):
+    monkeypatch.setenv('PD_PREPASS', flag)
+    out = []
+    for rate_fn in (po.RATE_PRIOR, po.RATE_SIMPLE):
+      spec = gh.rate_spec(rate_fn)
+      b = eng.EnvBatch(n, seed=seed)
+      b.reset()
+      b.fov[::5] += 4.1
+      for ctl, dwell, mode in ((acts, 1500000, nat.ACTION_RELATIVE_TO_SILICON),
+                               (acts, 9000000, nat.ACTION_RELATIVE_TO_SILICON),
+                               (direct, 2500000, 0)):
+        si, el = b.rollout(ctl, dwell, spec, record=True, action_mode=mode,
+                           max_distance_angstroms=1.42)
+        out += [gh.np_(si), gh.np_(el)]
+      o = b.step_and_image(ctl3, dwell3, spec)
+      out += [gh.np_(o.elapsed_us), gh.np_(o.transitions), gh.np_(o.events)]
+      b.apply_control(gh.np_(b.silicon_position()) + beam_m[:, 0, :],
+                      3000000, spec)
+      st = b.state_dict()
+      out += [gh.np_(st[k]) for k in ('si_idx', 'fov', 'ctrl_count',
+                                      'sim_time_us', 'n_events',
+                                      'n_transitions', 'status')]
+    results.append(out)
+  for x, y in zip(*results):
+    np.testing.assert_array_equal(x, y)
+  assert results[0][-2].sum() > n  # transitions happened
+
+
 def test_rollout_host_pipeline_matches_device_path(eng):
   """pd_rollout_actions_host (chunked H2D / step / D2H overlap) returns what
   the device-resident rollout computes."""
