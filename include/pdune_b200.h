@@ -335,6 +335,50 @@ int pd_get_grid(const pd_lattice* lat, const pd_state* st,
                 const int32_t* env_ids, int32_t m, double* out_xy,
                 void* stream);
 
+/* ---- trajectory export: microscope_utils.py:72-131 AtomicGrid.to_proto,
+ *      :180-230 BeamControl.to_proto, :496-501 MicroscopeFieldOfView.to_proto,
+ *      :589-604 MicroscopeObservation.to_proto, :737-757 Trajectory.to_proto,
+ *      io.py:65-82 write_records (putting_dune.proto:7-49) ----------------- */
+/* Serialises every env's current observation -- observed grid (atoms inside
+ * st->fov in lattice order, microscope frame), FOV, the controls just applied
+ * and the elapsed time -- as the protobuf wire bytes of MicroscopeObservation
+ * (fields 1-4; float64 -> float32 round-to-nearest as the protobuf runtime
+ * does), on the device.
+ *   controls_xy device double [n][n_controls][2] (microscope frame);
+ *   dwell_us device int64 [n][n_controls] or NULL (dwell_us_scalar);
+ *   elapsed_us device int64 [n] or NULL (st->sim_time_us);
+ *   max_atoms: staging bound per record; records with more atoms (or beyond
+ *   `capacity` bytes of out_bytes) are skipped and flagged in out_overflow
+ *   (uint8 [n], may be NULL);
+ *   out_offsets device int64 [n + 1]: record e starts at out_offsets[e]
+ *   (16-byte aligned), out_offsets[n] = bytes needed; out_len int32 [n]: its
+ *   length (= pd_observation_bytes(out_atoms[e], n_controls)); out_atoms
+ *   int32 [n]. */
+int pd_encode_observations(const pd_lattice* lat, const pd_state* st,
+                           const double* controls_xy, const int64_t* dwell_us,
+                           int64_t dwell_us_scalar, int32_t n_controls,
+                           const int64_t* elapsed_us, float voltage_kv,
+                           float current_na, int32_t max_atoms,
+                           uint8_t* out_bytes, int64_t capacity,
+                           int64_t* out_offsets, int32_t* out_len,
+                           int32_t* out_atoms, uint8_t* out_overflow,
+                           void* stream);
+/* Wire size of an observation with `atoms` atoms and n_controls controls. */
+int64_t pd_observation_bytes(int32_t atoms, int32_t n_controls);
+/* HOST: frames one Trajectory record per env (its observations of steps
+ * 0..n_steps-1, each as field 1) into a TFRecord stream: uint64 length,
+ * masked CRC-32C of the length, payload, masked CRC-32C of the payload.
+ * step_bytes[t] / step_offsets[t] / step_len[t] are HOST copies of one
+ * pd_encode_observations call's outputs.  out == NULL only sizes the stream
+ * (*out_size). */
+int pd_tfrecord_trajectories(int32_t n_steps, int64_t n_envs,
+                             const uint8_t* const* step_bytes,
+                             const int64_t* const* step_offsets,
+                             const int32_t* const* step_len, uint8_t* out,
+                             int64_t out_capacity, int64_t* out_size);
+/* HOST: CRC-32C (Castagnoli) of a buffer. */
+uint32_t pd_crc32c(const void* data, int64_t size);
+
 /* ---- whole goal-reaching episodes on the device (BASELINE configs[4]):
  *      eval_lib.py:77-184 evaluate for the greedy_on_neighbor experiment
  *      (experiments/registry.py:287-298) = PuttingDuneEnvironment.reset/step

@@ -137,7 +137,19 @@ def load_reference():
   if REFERENCE_ROOT not in sys.path:
     sys.path.insert(0, REFERENCE_ROOT)
   pkg = importlib.import_module('putting_dune')
-  pb2 = _AnyAttrModule('putting_dune.putting_dune_pb2')
+  # The generated putting_dune_pb2 is not in the tree; pdune_oracle_proto
+  # restates putting_dune.proto as a descriptor and has the official protobuf
+  # runtime build the same message classes, so the reference's own to_proto /
+  # from_proto run for real.  tf.make_tensor_proto / tf.make_ndarray (images
+  # inside observations) are stood in for there as well.
+  try:
+    from oracle import pdune_oracle_proto  # pylint: disable=g-import-not-at-top
+    pb2 = pdune_oracle_proto.build_pb2()
+    tf = sys.modules['tensorflow']
+    tf.make_tensor_proto = pdune_oracle_proto.make_tensor_proto
+    tf.make_ndarray = pdune_oracle_proto.make_ndarray
+  except ImportError:
+    pb2 = _AnyAttrModule('putting_dune.putting_dune_pb2')
   sys.modules['putting_dune.putting_dune_pb2'] = pb2
   pkg.putting_dune_pb2 = pb2
 

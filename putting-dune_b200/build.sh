@@ -18,6 +18,7 @@ fast=(pd_api pd_mlp)
 [ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
 [ -f "$src/pd_env.cu" ] && exact+=(pd_env)
 [ -f "$src/pd_mask.cu" ] && exact+=(pd_mask)
+[ -f "$src/pd_export.cu" ] && exact+=(pd_export)
 pids=()
 for f in "${exact[@]}"; do
   "$NVCC" "${COMMON[@]}" -fmad=false -c "$src/$f.cu" -o "$obj/$f.o" & pids+=($!)

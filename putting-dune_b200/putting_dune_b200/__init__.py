@@ -8,6 +8,7 @@ from putting_dune_b200 import microscope_utils
 from putting_dune_b200 import engine
 from putting_dune_b200 import graphene
 from putting_dune_b200 import imaging
+from putting_dune_b200 import io
 from putting_dune_b200 import episodes
 from putting_dune_b200 import putting_dune_environment
 from putting_dune_b200 import simulator

@@ -154,6 +154,13 @@ _SIGNATURES = {
                                C.c_int),
     'pd_get_silicon_position': ([_LP, _SP, _p, _p], C.c_int),
     'pd_get_grid': ([_LP, _SP, _p, _i32, _p, _p], C.c_int),
+    'pd_encode_observations': ([_LP, _SP, _p, _p, _i64, _i32, _p, C.c_float,
+                                C.c_float, _i32, _p, _i64, _p, _p, _p, _p,
+                                _p], C.c_int),
+    'pd_observation_bytes': ([_i32, _i32], _i64),
+    'pd_tfrecord_trajectories': ([_i32, _i64, _p, _p, _p, _p, _i64,
+                                  C.POINTER(_i64)], C.c_int),
+    'pd_crc32c': ([_p, _i64], C.c_uint32),
 }
 
 for _name, (_args, _res) in _SIGNATURES.items():

@@ -305,6 +305,85 @@ def env_fixture():
   np.savez_compressed(os.path.join(HERE, 'env_reference.npz'), **res)
 
 
+def proto_fixture():
+  """Wire bytes from the reference's own to_proto code (microscope_utils.py)
+  running against the official protobuf runtime (pdune_oracle_proto builds the
+  message classes from the restated putting_dune.proto): value types with
+  scattered float64 contents, a Trajectory of simulator observations and a
+  Transition.  Inputs are stored beside the bytes."""
+  import datetime as dt
+  mods = refshim.load_reference()
+  mu, Point = mods.microscope_utils, mods.Point
+  rng = np.random.default_rng(77)
+  res = {}
+
+  def fov_of(v):
+    return mu.MicroscopeFieldOfView(Point(v[0], v[1]), Point(v[2], v[3]))
+
+  def controls_of(xy, dwell_us):
+    return tuple(mu.BeamControl(Point(*p), dt.timedelta(microseconds=int(d)))
+                 for p, d in zip(xy, dwell_us))
+
+  n_cases = 12
+  res['n_cases'] = np.int64(n_cases)
+  for i in range(n_cases):
+    m = int(rng.integers(0, 160)) if i else 0
+    pos = rng.uniform(-0.2, 1.2, size=(m, 2))
+    num = rng.choice([6, 14], size=m).astype(np.int64)
+    fov = rng.uniform(-40, 40, size=4)
+    c = int(rng.integers(0, 4))
+    ctl = rng.uniform(0, 1, size=(c, 2))
+    dwell = rng.integers(1, 9_000_000, size=c)
+    elapsed = int(rng.integers(0, 900_000_000))
+    obs = mu.MicroscopeObservation(
+        grid=mu.AtomicGrid(pos, num), fov=fov_of(fov),
+        controls=controls_of(ctl, dwell),
+        elapsed_time=dt.timedelta(microseconds=elapsed))
+    for k, v in (('pos', pos), ('num', num), ('fov', fov), ('ctl', ctl),
+                 ('dwell_us', dwell), ('elapsed_us', np.int64(elapsed))):
+      res[f'{k}_{i}'] = v
+    res[f'grid_bytes_{i}'] = np.frombuffer(
+        obs.grid.to_proto().SerializeToString(), dtype=np.uint8)
+    res[f'obs_bytes_{i}'] = np.frombuffer(
+        obs.to_proto().SerializeToString(), dtype=np.uint8)
+    back = mu.MicroscopeObservation.from_proto_string(
+        obs.to_proto().SerializeToString())
+    assert back.grid.atom_positions.dtype == np.float32
+  # a trajectory and a transition built from the cases above
+  def obs_case(i):
+    return mu.MicroscopeObservation(
+        grid=mu.AtomicGrid(res[f'pos_{i}'], res[f'num_{i}']),
+        fov=fov_of(res[f'fov_{i}']),
+        controls=controls_of(res[f'ctl_{i}'], res[f'dwell_us_{i}']),
+        elapsed_time=dt.timedelta(microseconds=int(res[f'elapsed_us_{i}'])))
+  traj = mu.Trajectory(observations=[obs_case(i) for i in range(n_cases)])
+  res['trajectory_bytes'] = np.frombuffer(
+      traj.to_proto().SerializeToString(), dtype=np.uint8)
+  a, b = obs_case(3), obs_case(4)
+  tr = mu.Transition(grid_before=a.grid, grid_after=b.grid, fov_before=a.fov,
+                     fov_after=b.fov, controls=b.controls)
+  res['transition_bytes'] = np.frombuffer(
+      tr.to_proto().SerializeToString(), dtype=np.uint8)
+  # observations of the reference simulator itself (reset + 6 steps)
+  sim_bytes = []
+  mat = mods.graphene.PristineSingleDopedGraphene()
+  sim = mods.simulator.PuttingDuneSimulator(mat)
+  srng = np.random.default_rng(5)
+  o = sim.reset(srng)
+  sim_bytes.append(o.to_proto().SerializeToString())
+  for _ in range(6):
+    ctl = mu.BeamControl(Point(*srng.uniform(0.4, 0.6, size=2)),
+                         dt.timedelta(seconds=1.5))
+    o = sim.step_and_image(srng, [ctl])
+    sim_bytes.append(o.to_proto().SerializeToString())
+  res['sim_n'] = np.int64(len(sim_bytes))
+  for i, by in enumerate(sim_bytes):
+    res[f'sim_obs_bytes_{i}'] = np.frombuffer(by, dtype=np.uint8)
+  np.savez_compressed(os.path.join(HERE, 'proto_reference.npz'), **res)
+  print('proto fixture:', n_cases, 'cases,', len(res['trajectory_bytes']),
+        'trajectory bytes')
+
+
 if __name__ == '__main__':
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
@@ -318,3 +397,4 @@ if __name__ == '__main__':
   perception_fixture()
   episodes_fixture()
   env_fixture()
+  proto_fixture()

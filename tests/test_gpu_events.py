@@ -407,8 +407,11 @@ def test_rollout_speculative_equals_serial(eng, n, monkeypatch):
   for rate_fn, const, dwell, ctl, mode in cases:
     spec = gh.rate_spec(rate_fn, constant=const)
     res = []
-    for flag in ('1', '0'):
+    # k_rollout_pre (float32 look-ahead), k_rollout_spec (float64
+    # speculation), k_rollout (serial)
+    for flag, pre in (('1', '1'), ('1', '0'), ('0', '0')):
       monkeypatch.setenv('PD_ROLLOUT_SPEC', flag)
+      monkeypatch.setenv('PD_PREPASS', pre)
       b = eng.EnvBatch(n, seed=seed)
       b.reset()
       # a FOV the Si is not centred in: the t = 0 safe-area check matters
@@ -416,13 +419,15 @@ def test_rollout_speculative_equals_serial(eng, n, monkeypatch):
       si, el = b.rollout(ctl, dwell, spec, record=True, action_mode=mode,
                          max_distance_angstroms=1.42)
       res.append((gh.np_(si), gh.np_(el), b.state_dict()))
-    (si_a, el_a, st_a), (si_b, el_b, st_b) = res
-    np.testing.assert_array_equal(si_a, si_b)
-    np.testing.assert_array_equal(el_a, el_b)
-    for k in ('si_idx', 'fov', 'ctrl_count', 'sim_time_us', 'n_events',
-              'n_transitions', 'status'):
-      np.testing.assert_array_equal(gh.np_(st_a[k]), gh.np_(st_b[k]), err_msg=k)
-    assert gh.np_(st_a['n_transitions']).sum() > 0
+    si_b, el_b, st_b = res[-1]
+    for si_a, el_a, st_a in res[:-1]:
+      np.testing.assert_array_equal(si_a, si_b)
+      np.testing.assert_array_equal(el_a, el_b)
+      for k in ('si_idx', 'fov', 'ctrl_count', 'sim_time_us', 'n_events',
+                'n_transitions', 'status'):
+        np.testing.assert_array_equal(gh.np_(st_a[k]), gh.np_(st_b[k]),
+                                      err_msg=k)
+    assert gh.np_(st_b['n_transitions']).sum() > 0
 
 
 def test_prepass_equals_exact(eng, monkeypatch):
