@@ -88,6 +88,7 @@ typedef struct pd_gmm {
 #define PD_STREAM_RENDER_UNIFORM 7u
 #define PD_STREAM_RENDER_EXP 8u
 #define PD_STREAM_RENDER_GAUSS 9u
+#define PD_STREAM_SYNTH 10u
 /* Renderer noise fields (counter = (env, frame_count, index, stream)): pixel
  * p = row * S + col takes word p % 4 of the call with index p / 4;
  * u24(w) = (w >> 8) * 2^-24.
@@ -378,6 +379,20 @@ int pd_tfrecord_trajectories(int32_t n_steps, int64_t n_envs,
                              int64_t out_capacity, int64_t* out_size);
 /* HOST: CRC-32C (Castagnoli) of a buffer. */
 uint32_t pd_crc32c(const void* data, int64_t size);
+
+/* ---- synthetic rate-learning data: rate_learning/data_utils.py:158-303
+ *      generate_synthetic_data, PRIOR mode (the NETWORK mode draws a random
+ *      Haiku network and is not provided) ------------------------------------ */
+/* n samples of split `split` (0 = train, 1 = test; data_utils.py:297-300):
+ * next_state int32 [n] (0 = no transition, k + 1 = state k), dt float [n]
+ * (the observation window), rates float [n][num_states], context float
+ * [n][context_dim], position float [n][2]; all device pointers.  Draws are
+ * keyed by Philox (PD_STREAM_SYNTH), not jax.random. */
+int pd_generate_synthetic_data(uint64_t seed, int32_t split, int64_t n,
+                               int32_t num_states, int32_t context_dim,
+                               float time_lo, float time_hi,
+                               int32_t* next_state, float* dt, float* rates,
+                               float* context, float* position, void* stream);
 
 /* ---- whole goal-reaching episodes on the device (BASELINE configs[4]):
  *      eval_lib.py:77-184 evaluate for the greedy_on_neighbor experiment

@@ -14,6 +14,7 @@ COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
 exact=(pd_lattice pd_reset pd_step pd_query)
 fast=(pd_api pd_mlp)
 [ -f "$src/pd_render.cu" ] && fast+=(pd_render)
+[ -f "$src/pd_synth.cu" ] && fast+=(pd_synth)
 [ -f "$src/pd_render_cluster.cu" ] && fast+=(pd_render_cluster)
 [ -f "$src/pd_episode.cu" ] && exact+=(pd_episode)
 [ -f "$src/pd_env.cu" ] && exact+=(pd_env)

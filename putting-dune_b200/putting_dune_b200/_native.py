@@ -161,6 +161,9 @@ _SIGNATURES = {
     'pd_tfrecord_trajectories': ([_i32, _i64, _p, _p, _p, _p, _i64,
                                   C.POINTER(_i64)], C.c_int),
     'pd_crc32c': ([_p, _i64], C.c_uint32),
+    'pd_generate_synthetic_data': ([C.c_uint64, _i32, _i64, _i32, _i32,
+                                    C.c_float, C.c_float, _p, _p, _p, _p, _p,
+                                    _p], C.c_int),
 }
 
 for _name, (_args, _res) in _SIGNATURES.items():

@@ -384,6 +384,52 @@ def proto_fixture():
         'trajectory bytes')
 
 
+def synth_fixture():
+  """The deterministic helpers of rate_learning/data_utils.py
+  (get_all_position_rotations, rotate_attributes, rotate_index) and
+  graphene.single_silicon_prior_rates from the reference itself, composed as
+  sample_from_prior composes them (data_utils.py:252-269), on random
+  positions and rotation factors.  jax.jit / jax.vmap are given identity
+  stand-ins (jax is absent; jax.numpy is NumPy under the shim)."""
+  import importlib
+  import types
+  mods = refshim.load_reference()
+  jax = sys.modules['jax']
+  jax.jit = lambda f=None, **kw: f if f is not None else (lambda g: g)
+  jax.vmap = lambda f, *a, **kw: f
+  stub = types.ModuleType('putting_dune.rate_learning.learn_rates')
+  sys.modules.setdefault('putting_dune.rate_learning.learn_rates', stub)
+  du = importlib.import_module('putting_dune.rate_learning.data_utils')
+  consts = mods.constants
+  rng = np.random.default_rng(99)
+  res = {}
+  for num_states in (3, 6):
+    n = 64
+    pos = consts.SIGR_PRIOR_RATE_MEAN + np.sqrt(0.15) * rng.normal(size=(n, 2))
+    rf = rng.integers(0, num_states, size=n)
+    state = rng.integers(0, num_states, size=n)
+    rates, pos_rot, rates_rot, state_rot = [], [], [], []
+    for i in range(n):
+      r = mods.graphene.single_silicon_prior_rates(
+          du.get_all_position_rotations(pos[i], num_states=num_states),
+          mean=consts.SIGR_PRIOR_RATE_MEAN, cov=consts.SIGR_PRIOR_RATE_COV,
+          max_rate=consts.SIGR_PRIOR_MAX_RATE)
+      rates.append(r)
+      pos_rot.append(mods.geometry.jnp_rotate_coordinates(
+          pos[i], 2 * rf[i] * np.pi / num_states))
+      rates_rot.append(du.rotate_attributes(r, int(rf[i])))
+      state_rot.append(du.rotate_index(state[i], rf[i],
+                                       num_states=num_states))
+    res.update({f'pos_{num_states}': pos, f'rf_{num_states}': rf,
+                f'state_{num_states}': state,
+                f'rates_{num_states}': np.asarray(rates),
+                f'pos_rot_{num_states}': np.asarray(pos_rot),
+                f'rates_rot_{num_states}': np.asarray(rates_rot),
+                f'state_rot_{num_states}': np.asarray(state_rot)})
+  np.savez_compressed(os.path.join(HERE, 'synth_reference.npz'), **res)
+  print('synth fixture written')
+
+
 if __name__ == '__main__':
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
@@ -398,3 +444,4 @@ if __name__ == '__main__':
   episodes_fixture()
   env_fixture()
   proto_fixture()
+  synth_fixture()

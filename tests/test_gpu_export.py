@@ -106,3 +106,47 @@ def test_encoder_overflow_and_empty_views(eng):
   small = pio.TrajectoryRecorder(b, max_atoms=64)
   with pytest.raises(RuntimeError, match='max_atoms'):
     small.record(np.full((n, 1, 2), 0.5), 1500000)
+
+
+@pytest.mark.parametrize('num_states,context_dim,time_range',
+                         [(3, 2, (0.0, 5.0)), (6, 2, (0.0, 1.0)),
+                          (3, 5, (0.5, 2.0)), (3, 0, (0.0, 5.0))])
+def test_synthetic_rate_learning_data(eng, num_states, context_dim,
+                                      time_range):
+  """pd_generate_synthetic_data against the oracle on the same Philox draws
+  (float32 tolerance 2e-5 relative; states exact away from decision
+  boundaries) and the properties the reference's own test checks
+  (data_utils_test.py:62-93: shapes, dt inside the window)."""
+  from oracle import pdune_oracle_synth as osy
+  from putting_dune_b200.rate_learning import data_utils
+  n, seed = 20000, 1234
+  train, test = data_utils.generate_synthetic_data(
+      num_data=n, data_seed=seed, num_states=num_states,
+      context_dim=context_dim, actual_time_range=time_range)
+  for split, data in enumerate((train, test)):
+    want = osy.generate_synthetic_data(n, seed, split, num_states,
+                                       context_dim, time_range)
+    got = {k: gh.np_(v) for k, v in data.items()}
+    assert got['position'].shape == (n, 2)
+    assert got['context'].shape == (n, context_dim)
+    assert got['next_state'].shape == (n, 1) and got['dt'].shape == (n, 1)
+    assert got['rates'].shape == (n, num_states)
+    # float32 sums with cancellation (x c - y s): absolute 5e-5 on O(1) values
+    np.testing.assert_allclose(got['position'], want['position'], rtol=2e-5,
+                               atol=5e-5)
+    np.testing.assert_allclose(got['rates'], want['rates'], rtol=2e-3,
+                               atol=1e-9)
+    np.testing.assert_allclose(got['context'], want['context'], rtol=2e-5,
+                               atol=5e-5)
+    np.testing.assert_allclose(got['dt'], want['dt'], rtol=1e-6, atol=1e-7)
+    safe = (want['cdf_margin'] > 1e-5) & (want['time_margin'] > 1e-4)
+    assert safe.mean() > 0.99
+    np.testing.assert_array_equal(got['next_state'][safe],
+                                  want['next_state'][safe])
+    assert ((got['dt'] >= time_range[0]) & (got['dt'] <= time_range[1])).all()
+    assert set(np.unique(got['next_state'])) <= set(range(num_states + 1))
+  assert not np.array_equal(gh.np_(train['position']),
+                            gh.np_(test['position']))
+  # statistics of the generator: position ~ N(rotations of (0.85, 0), 0.15 I)
+  p = gh.np_(train['position']).astype(np.float64)
+  assert abs(np.hypot(p[:, 0], p[:, 1]).mean() - 0.93) < 0.05

@@ -426,3 +426,36 @@ def test_env_oracle_matches_reference_environment(golden_dir, case):
                                atol=2e-6)
   # putting_dune_environment_test.py:110: the first step of a fresh env resets
   assert (fix[f'step_type_{case}'][0] == 0).all()
+
+
+def test_synthetic_data_oracle_matches_reference_helpers(golden_dir):
+  """oracle/pdune_oracle_synth.py against the reference's own
+  get_all_position_rotations / single_silicon_prior_rates /
+  jnp_rotate_coordinates / rotate_attributes / rotate_index
+  (tests/golden/synth_reference.npz)."""
+  from oracle import pdune_oracle_synth as osy
+  ref = np.load(os.path.join(golden_dir, 'synth_reference.npz'))
+  for ns in (3, 6):
+    pos, rf, state = ref[f'pos_{ns}'], ref[f'rf_{ns}'], ref[f'state_{ns}']
+    np.testing.assert_allclose(osy.prior_rates(pos, ns), ref[f'rates_{ns}'],
+                               rtol=1e-12, atol=0)
+    np.testing.assert_allclose(
+        osy.rotate_coordinates(pos, 2 * rf * np.pi / ns), ref[f'pos_rot_{ns}'],
+        rtol=1e-12, atol=1e-15)
+    # the composition inside sample_from_draws: feed draws that reproduce the
+    # fixture's position, state and rotation factor
+    z = (pos - osy.MEAN) / np.sqrt(1.5 * osy.COV)
+    rates = ref[f'rates_{ns}']
+    cdf = np.cumsum(rates / rates.sum(-1, keepdims=True), -1)
+    lo = np.concatenate((np.zeros((len(pos), 1)), cdf[:, :-1]), 1)
+    u_state = (0.5 * (lo + cdf))[np.arange(len(pos)), state]
+    out = osy.sample_from_draws(z, u_state, (rf + 0.5) / ns,
+                                np.ones(len(pos)),  # next_time = 0: transitions
+                                np.full(len(pos), 0.5),
+                                np.zeros((len(pos), 2)), ns, (0.0, 5.0))
+    np.testing.assert_array_equal(out['next_state'][:, 0],
+                                  ref[f'state_rot_{ns}'] + 1)
+    np.testing.assert_allclose(out['rates'], ref[f'rates_rot_{ns}'],
+                               rtol=1e-6)
+    np.testing.assert_allclose(out['position'], ref[f'pos_rot_{ns}'],
+                               rtol=1e-6, atol=1e-7)
