@@ -60,6 +60,7 @@ def parse_args():
   ap.add_argument('--no-at-scale', action='store_true')
   ap.add_argument('--no-frames', action='store_true')
   ap.add_argument('--no-mlp', action='store_true')
+  ap.add_argument('--no-export', action='store_true')
   ap.add_argument('--frames', type=int, default=16384,
                   help='frames per render launch (512x512; BASELINE '
                        'configs[3]: 16384 envs per step = 17.2 GB of frames)')
@@ -266,6 +267,53 @@ def measured_peak():
     return float(json.load(open(path))['hbm_gbs']), 'measured'
   except (OSError, KeyError, ValueError):
     return 6650.0, 'fallback'
+
+
+def measure_export(pd, batch, dev, peak):
+  """Observation records/s of pd_encode_observations (protobuf wire bytes of
+  MicroscopeObservation for every env): byte work
+  bounded by HBM -- the records written plus the 76 B of env state read."""
+  import torch
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  n = 65536
+  eb = pd.EnvBatch(n, seed=5, device=dev, lattice=batch.lattice_tables)
+  eb.reset()
+  max_atoms = min(eb.max_atoms_in_view(), eb.lattice_tables.n_sites)
+  slot = (int(nat.lib.pd_observation_bytes(max_atoms, 1)) + 15) & ~15
+  out = torch.empty(n * slot, dtype=torch.uint8, device=dev)
+  offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+  length = torch.empty(n, dtype=torch.int32, device=dev)
+  atoms = torch.empty(n, dtype=torch.int32, device=dev)
+  ctl = torch.full((n, 1, 2), 0.5, dtype=torch.float64, device=dev)
+  P = lambda t: C.c_void_p(t.data_ptr())
+  stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  def launch():
+    nat.check(nat.lib.pd_encode_observations(
+        C.byref(eb.lattice_tables.c), C.byref(eb.c), P(ctl), None, DWELL_US, 1,
+        None, 60.0, 0.1, max_atoms, P(out), out.numel(), P(offsets), P(length),
+        P(atoms), None, stream))
+  for _ in range(3):
+    launch()
+  torch.cuda.synchronize()
+  reps = 10
+  a, b = (torch.cuda.Event(enable_timing=True),
+          torch.cuda.Event(enable_timing=True))
+  a.record()
+  for _ in range(reps):
+    launch()
+  b.record()
+  torch.cuda.synchronize()
+  ms = a.elapsed_time(b) / reps
+  nbytes = int(offsets[n].item())
+  gbs = nbytes / (ms / 1e3) / 1e9
+  return {'metric': 'observation records/sec', 'value': n / (ms / 1e3),
+          'records_per_launch': n, 'bytes_per_launch': nbytes,
+          'mean_atoms': float(atoms.float().mean().item()), 'launch_ms': ms,
+          'kernels': 'pd::k_obs_sizes + k_obs_offsets + k_obs_encode',
+          'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak,
+                       'unit': 'GB/s', 'frac': gbs / peak,
+                       'algorithmic_bytes_per_record': nbytes / n}}
 
 
 def measure_frames(pd, batch, dev, peak, args):
@@ -482,16 +530,17 @@ def run_ours(args, cfg):
   launch_s = dev_ms / 1e3 / args.steps
   achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * env_steps_per_launch / launch_s / 1e9
   roofline = {
-      'kernel': 'pd::k_rollout_spec', 'bound': 'hbm', 'achieved': achieved,
+      'kernel': 'pd::k_rollout_pre', 'bound': 'hbm', 'achieved': achieved,
       'peak': peak, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
       'unit': 'GB/s', 'frac': achieved / peak,
       'algorithmic_bytes_per_env_step': ALGORITHMIC_BYTES_PER_ENV_STEP,
       'env_steps_per_launch': env_steps_per_launch,
       'launch_ms': launch_s * 1e3,
-      # ncu --set full of this command (profiles/r01_k_rollout_config2):
-      # the state stays in registers across the 256 steps, so DRAM traffic is
-      # the action stream (16 B/env-step), below the 64 B algorithmic figure
-      'traffic': ncu_traffic('r01_k_rollout_config2.ncu.json')
+      # ncu --set full of the same workload (profiles/
+      # r01_k_rollout_pre_config2): the state stays in registers across the
+      # 256 steps, so DRAM traffic is the action stream (16 B/env-step), below
+      # the 64 B algorithmic figure
+      'traffic': ncu_traffic('r01_k_rollout_pre_config2.ncu.json')
       if cfg['envs_per_gpu'] == 4096 and t_steps == 256 else None,
   }
 
@@ -528,7 +577,32 @@ def run_ours(args, cfg):
         'kernel': 'pd::k_walk', 'value': big_n / (ms / 1e3), 'unit': UNIT,
         'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak,
         'traffic': ncu_traffic('r01_k_walk_1Mi_1step.ncu.json')}
-    del big
+    # the same batch in 8-step rollouts (state read and written once per 8)
+    acts8 = [torch.as_tensor(synthetic_controls(big_n, 8, 17 + i)).to(dev)
+             for i in range(2)]
+    def big_launch8(i):
+      nat.check(nat.lib.pd_rollout_actions(
+          C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
+          P(acts8[i % 2]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US,
+          8, IMAGE_US, None, None, stream))
+    for i in range(2):
+      big_launch8(i)
+    torch.cuda.synchronize()
+    bev = [(torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(6)]
+    for i in range(6):
+      flush.zero_()
+      bev[i][0].record()
+      big_launch8(i)
+      bev[i][1].record()
+    torch.cuda.synchronize()
+    ms8 = sum(a.elapsed_time(b) for a, b in bev) / 6
+    g8 = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n * 8 / (ms8 / 1e3) / 1e9
+    at_scale['rollout8'] = {
+        'workload': '1Mi envs x 8 steps per launch', 'kernel': 'pd::k_walk',
+        'value': big_n * 8 / (ms8 / 1e3), 'unit': UNIT, 'launch_ms': ms8,
+        'achieved': g8, 'peak': peak, 'frac': g8 / peak}
+    del big, acts8
 
   # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
   frames = None
@@ -539,6 +613,10 @@ def run_ours(args, cfg):
   episodes = None
   if args.episodes:
     episodes = measure_episodes(pd, args, world, rank, dev, barrier)
+
+  export = None
+  if rank == 0 and not args.no_export:
+    export = measure_export(pd, batch, dev, peak)
 
   mlp = None
   if rank == 0 and not args.no_mlp:
@@ -570,7 +648,7 @@ def run_ours(args, cfg):
                 'api': 'pd_rollout_actions_host (pinned host buffers)'},
         'gpu_launches': args.steps, 'roofline': roofline,
         'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
-        'episodes': episodes, 'learned_mlp': mlp,
+        'episodes': episodes, 'learned_mlp': mlp, 'export': export,
         'wall_s_timed_region': t1 - t0,
     }
     print(json.dumps(line), flush=True)
