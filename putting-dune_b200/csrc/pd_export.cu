@@ -88,8 +88,10 @@ __global__ void __launch_bounds__(kExportThreads)
        e < st.n_envs; e += warps) {
     const Lattice4 t = load_lattice4(st.lattice, e);
     const Fov4 f = load_fov4(st.fov, e);
+    int c_lo, c_hi;
+    fov_chunk_range(lat, t, f, &c_lo, &c_hi);
     int count = 0;
-    for (int k0 = 0; k0 < lat.n_sites; k0 += 32) {
+    for (int k0 = 32 * c_lo; k0 < 32 * c_hi; k0 += 32) {
       const int k = k0 + lane;
       bool keep = false;
       if (k < lat.n_sites) {
@@ -106,20 +108,29 @@ __global__ void __launch_bounds__(kExportThreads)
   }
 }
 
-// Exclusive scan of the 16-byte-aligned record sizes (one CTA; n is at most a
-// few million and the pass is a small fraction of the encode).
+// Exclusive scan of the 16-byte-aligned record sizes (one CTA, eight
+// consecutive records per thread and trip; a small fraction of the encode).
 __global__ void __launch_bounds__(1024)
     k_obs_offsets(const int32_t* __restrict__ len, int64_t n,
                   int64_t* __restrict__ offsets) {
+  constexpr int kPer = 8;
   __shared__ int64_t warp_sum[32];
   __shared__ int64_t carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t i0 = 0; i0 < n; i0 += 1024) {
-    const int64_t i = i0 + threadIdx.x;
-    const int64_t v = i < n ? ((static_cast<int64_t>(len[i]) + 15) & ~15LL) : 0;
-    int64_t x = v;
+  for (int64_t i0 = 0; i0 < n; i0 += 1024 * kPer) {
+    const int64_t first = i0 + static_cast<int64_t>(threadIdx.x) * kPer;
+    int64_t v[kPer];
+    int64_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      v[k] = first + k < n
+                 ? ((static_cast<int64_t>(len[first + k]) + 15) & ~15LL)
+                 : 0;
+      mine += v[k];
+    }
+    int64_t x = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int64_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -137,17 +148,30 @@ __global__ void __launch_bounds__(1024)
       warp_sum[lane] = s;
     }
     __syncthreads();
-    const int64_t before = carry + (wid ? warp_sum[wid - 1] : 0) + x - v;
-    if (i < n) offsets[i] = before;
+    int64_t run = carry + (wid ? warp_sum[wid - 1] : 0) + x - mine;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (first + k < n) offsets[first + k] = run;
+      run += v[k];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = before + v;
+    if (threadIdx.x == 1023) carry = run;
     __syncthreads();
   }
   if (threadIdx.x == 0) offsets[n] = carry;
 }
 
-// Pass 2: one warp per env builds the record in shared memory (byte stores)
-// and streams it out in 16-byte words (records start 16-byte aligned).
+// Pass 2: one warp per env builds the record in shared memory and streams it
+// out in 16-byte words (records start 16-byte aligned in `out`).
+//   A  in-view test over the candidate rows; the ids of the atoms in view are
+//      compacted, in lattice order, into a list behind the record;
+//   B  dense pass over the list: position, normalisation (two float64
+//      divisions, as graphene.py:637-641 forms them), one 16-byte atom record
+//      per lane as four aligned word stores -- the record is placed so that
+//      the atom array (which follows a 2..4-byte header) is word aligned;
+//   C  header, FOV, controls, elapsed time (byte stores, < 100 B);
+//   D  copy-out: each 16-byte output word is funnel-shifted out of the
+//      staged words to undo the placement offset.
 __global__ void __launch_bounds__(kExportThreads)
     k_obs_encode(const pd_lattice lat, const pd_state st,
                  const double* __restrict__ controls_xy,
@@ -156,12 +180,15 @@ __global__ void __launch_bounds__(kExportThreads)
                  const int64_t* __restrict__ elapsed_us, float voltage_kv,
                  float current_na, const int32_t* __restrict__ atoms,
                  const int32_t* __restrict__ len,
-                 const int64_t* __restrict__ offsets, int32_t smem_per_warp,
-                 uint8_t* __restrict__ out, int64_t capacity,
-                 uint8_t* __restrict__ overflow) {
+                 const int64_t* __restrict__ offsets, int32_t record_cap,
+                 int32_t smem_per_warp, uint8_t* __restrict__ out,
+                 int64_t capacity, uint8_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t stage_all[];
   const int lane = threadIdx.x & 31;
   uint8_t* stage = stage_all + (threadIdx.x >> 5) * smem_per_warp;
+  // ids of the atoms in view; behind the record (+16: placement shift, tail
+  // word of the funnel shift)
+  uint16_t* list = reinterpret_cast<uint16_t*>(stage + record_cap + 16);
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (kExportThreads / 32);
   const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
   for (int64_t e = blockIdx.x * (kExportThreads / 32) + (threadIdx.x >> 5);
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(kExportThreads)
     const int32_t bytes = len[e];
     const int64_t off = offsets[e];
     const int32_t padded = (bytes + 15) & ~15;
-    if (padded > smem_per_warp || off + padded > capacity) {
+    if (padded > record_cap || off + padded > capacity) {
       if (lane == 0 && overflow) overflow[e] = 1;
       continue;
     }
@@ -180,41 +207,52 @@ __global__ void __launch_bounds__(kExportThreads)
     const int si = st.si_idx[e];
     const double w = __dsub_rn(f.urx, f.llx);
     const double h = __dsub_rn(f.ury, f.lly);
-    // ---- grid (field 1) ----
     const uint32_t grid_bytes = 16u * static_cast<uint32_t>(m_atoms);
-    int hdr = 0;
-    if (lane == 0) {
-      stage[0] = 0x0A;
-      hdr = 1 + put_varint(stage + 1, grid_bytes);
-    }
-    hdr = __shfl_sync(0xffffffffu, hdr, 0);
+    const int hdr = 1 + varint_len(grid_bytes);
+    const int shift = (4 - (hdr & 3)) & 3;  // record starts at stage + shift
+    uint8_t* rec = stage + shift;
+    // ---- A: compact the ids of the atoms in view ----
+    int c_lo, c_hi;
+    fov_chunk_range(lat, t, f, &c_lo, &c_hi);
     int count = 0;
-    for (int k0 = 0; k0 < lat.n_sites; k0 += 32) {
+#pragma unroll 2
+    for (int k0 = 32 * c_lo; k0 < 32 * c_hi; k0 += 32) {
       const int k = k0 + lane;
       bool keep = false;
-      double2 p = make_double2(0.0, 0.0);
       if (k < lat.n_sites) {
-        p = site_position(__ldg(base + k), t);
+        const double2 p = site_position(__ldg(base + k), t);
         keep = (f.llx <= p.x) && (p.x <= f.urx) && (f.lly <= p.y) &&
                (p.y <= f.ury);
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        uint8_t* a = stage + hdr + 16 * (count + __popc(m & ((1u << lane) - 1u)));
-        a[0] = 0x0A;  // AtomicGrid.atoms
-        a[1] = 0x0E;
-        a[2] = 0x08;  // Atom.atomic_number
-        a[3] = static_cast<uint8_t>(k == si ? kSilicon : kCarbon);
-        a[4] = 0x12;  // Atom.position
-        a[5] = 0x0A;
-        put_point(a + 6, __ddiv_rn(__dsub_rn(p.x, f.llx), w),
-                  __ddiv_rn(__dsub_rn(p.y, f.lly), h));
-      }
+      if (keep)
+        list[count + __popc(m & ((1u << lane) - 1u))] =
+            static_cast<uint16_t>(k);
       count += __popc(m);
     }
-    // ---- fov (2), controls (3), elapsed time (4) ----
-    uint8_t* tail = stage + hdr + grid_bytes;
+    __syncwarp();
+    // ---- B: atom records, AtomicGrid.atoms (field 1 of the grid) ----
+    uint32_t* arec = reinterpret_cast<uint32_t*>(rec + hdr);
+    for (int i = lane; i < m_atoms; i += 32) {
+      const int k = list[i];
+      const double2 p = site_position(__ldg(base + k), t);
+      const uint32_t x = __float_as_uint(
+          __double2float_rn(__ddiv_rn(__dsub_rn(p.x, f.llx), w)));
+      const uint32_t y = __float_as_uint(
+          __double2float_rn(__ddiv_rn(__dsub_rn(p.y, f.lly), h)));
+      const uint32_t z = k == si ? kSilicon : kCarbon;
+      // 0A 0E 08 Z | 12 0A 0D x0 | x1 x2 x3 15 | y0 y1 y2 y3
+      arec[4 * i + 0] = 0x0A | (0x0E << 8) | (0x08 << 16) | (z << 24);
+      arec[4 * i + 1] = 0x12 | (0x0A << 8) | (0x0D << 16) | (x << 24);
+      arec[4 * i + 2] = (x >> 8) | (0x15u << 24);
+      arec[4 * i + 3] = y;
+    }
+    // ---- C: grid header, fov (2), controls (3), elapsed time (4) ----
+    uint8_t* tail = rec + hdr + grid_bytes;
     if (lane == 0) {
+      for (int i = 0; i < shift; ++i) stage[i] = 0;
+      rec[0] = 0x0A;
+      put_varint(rec + 1, grid_bytes);
       tail[0] = 0x12;
       tail[1] = 0x18;
       tail[2] = 0x0A;
@@ -248,11 +286,19 @@ __global__ void __launch_bounds__(kExportThreads)
       b[24] = 0x25;
       put_f32(b + 25, current_na);
     }
-    for (int i = bytes + lane; i < padded; i += 32) stage[i] = 0;
+    // zero the padding and the word the last funnel shift reads
+    for (int i = shift + bytes + lane; i < padded + 8; i += 32) stage[i] = 0;
     __syncwarp();
-    const uint4* src = reinterpret_cast<const uint4*>(stage);
+    // ---- D: copy out ----
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
     uint4* dst = reinterpret_cast<uint4*>(out + off);
-    for (int i = lane; i < padded / 16; i += 32) dst[i] = src[i];
+    const int sh = 8 * shift;
+    for (int i = lane; i < padded / 16; i += 32) {
+      const uint32_t w0 = sw[4 * i], w1 = sw[4 * i + 1], w2 = sw[4 * i + 2],
+                     w3 = sw[4 * i + 3], w4 = sw[4 * i + 4];
+      dst[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                          __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
     __syncwarp();
   }
 }
@@ -342,7 +388,7 @@ extern "C" int pd_encode_observations(
   const int64_t n = st->n_envs;
   const int warps_per_cta = pd::kExportThreads / 32;
   const int64_t want = (n + warps_per_cta - 1) / warps_per_cta;
-  const int64_t cap = static_cast<int64_t>(pd::sm_count()) * 8;
+  const int64_t cap = static_cast<int64_t>(pd::sm_count()) * 16;
   const int grid = static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
   if (n > 0) {
     pd::k_obs_sizes<<<grid, pd::kExportThreads, 0, s>>>(*lat, *st, n_controls,
@@ -352,8 +398,11 @@ extern "C" int pd_encode_observations(
   pd::k_obs_offsets<<<1, 1024, 0, s>>>(out_len, n, out_offsets);
   PD_CUDA_OK(cudaGetLastError());
   if (n == 0) return PD_OK;
-  const int64_t per_warp =
+  PD_REQUIRE(lat->n_sites <= 65535, "lattice too large for the export ids");
+  const int64_t record_cap =
       (pd::observation_bytes(max_atoms, n_controls) + 15) & ~15LL;
+  // record + placement shift / funnel tail + the list of atom ids
+  const int64_t per_warp = (record_cap + 16 + 2LL * max_atoms + 15) & ~15LL;
   const int64_t smem = per_warp * warps_per_cta;
   PD_REQUIRE(smem <= 200 * 1024, "max_atoms too large for one staging buffer");
   PD_CUDA_OK(cudaFuncSetAttribute(pd::k_obs_encode,
@@ -362,7 +411,8 @@ extern "C" int pd_encode_observations(
   pd::k_obs_encode<<<grid, pd::kExportThreads, smem, s>>>(
       *lat, *st, controls_xy, dwell_us, dwell_us_scalar, n_controls, elapsed_us,
       voltage_kv, current_na, out_atoms, out_len, out_offsets,
-      static_cast<int32_t>(per_warp), out_bytes, capacity, out_overflow);
+      static_cast<int32_t>(record_cap), static_cast<int32_t>(per_warp),
+      out_bytes, capacity, out_overflow);
   PD_CUDA_OK(cudaGetLastError());
   return PD_OK;
 }

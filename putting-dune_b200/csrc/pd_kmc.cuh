@@ -394,6 +394,43 @@ __device__ __forceinline__ bool silicon_outside_safe_area(const Fov4& f,
   return !in_view || near_edge;
 }
 
+// Site ids are row-major over the horizontal rows of the base lattice
+// (graphene.py:483-499), so the rows that can intersect a FOV's circumscribed
+// circle form one contiguous id range: [*c_lo, *c_hi) in 32-site chunks.  A
+// conservative bound (margin 0.05 A); callers still test every site.
+__device__ __forceinline__ void fov_chunk_range(const pd_lattice& lat,
+                                                const Lattice4& t,
+                                                const Fov4& f, int* c_lo,
+                                                int* c_hi) {
+  const double w = f.urx - f.llx, h = f.ury - f.lly;
+  const double cx = 0.5 * (f.llx + f.urx), cy = 0.5 * (f.lly + f.ury);
+  const double by = cx * t.s + cy * t.c - t.oy;  // base-frame y of the centre
+  const double rad = 0.5 * sqrt(w * w + h * h) + 0.05;
+  const double y0 = __ldg(reinterpret_cast<const double2*>(lat.base_xy)).y;
+  const double hrow = 0.8660254037844386 * kBond;
+  const int ce = lat.n_cols - (lat.n_cols + 2) / 3;  // sites on even rows
+  const int co = lat.n_cols - (lat.n_cols + 1) / 3;  // sites on odd rows
+  const int n_chunks = (lat.n_sites + 31) / 32;
+  const double lo = floor((by - rad - y0) / hrow);
+  const double hi = ceil((by + rad - y0) / hrow) + 1.0;
+  if (!(lo == lo) || !(hi == hi)) {  // non-finite FOV: scan everything
+    *c_lo = 0;
+    *c_hi = n_chunks;
+    return;
+  }
+  const double rows = 1.0e6;  // ids are clamped to n_sites below
+  const int j_lo = static_cast<int>(fmin(fmax(lo, 0.0), rows));
+  const int j_hi = static_cast<int>(fmin(fmax(hi, 0.0), rows));
+  long long k_lo =
+      static_cast<long long>(j_lo / 2) * (ce + co) + (j_lo & 1) * ce;
+  long long k_hi =
+      static_cast<long long>(j_hi / 2) * (ce + co) + (j_hi & 1) * ce;
+  if (k_lo > lat.n_sites) k_lo = lat.n_sites;
+  if (k_hi > lat.n_sites) k_hi = lat.n_sites;
+  *c_lo = static_cast<int>(k_lo / 32);
+  *c_hi = static_cast<int>((k_hi + 31) / 32);
+}
+
 // simulator.py:161-165: FOV = [P_si - s/2, P_si + s/2].
 __device__ __forceinline__ Fov4 centred_fov(const double2 p, double scale) {
   const double h = __ddiv_rn(scale, 2.0);
