@@ -510,20 +510,38 @@ def run_ours(args, cfg):
         nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
         P(d_stage), P(d_si), P(d_el), P(h_si), P(h_el), stream))
 
-  for i in range(args.warmup):
-    launch_host(i)
-  barrier()
-  e0 = time.perf_counter()
-  for i in range(args.steps):
-    launch_host(i)
-  barrier()
-  e2e_s = time.perf_counter() - e0
-  tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-  e2e_value = total_env_steps / float(tm.item())
-  h2d = h_ctl[0].numel() * 8
-  d2h = h_si.numel() * 4 + h_el.numel() * 8
+  def time_host(fn):
+    for i in range(args.warmup):
+      fn(i)
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(args.steps):
+      fn(i)
+    barrier()
+    tm = torch.tensor([time.perf_counter() - e0], dtype=torch.float64,
+                      device=dev)
+    if world > 1:
+      dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    return total_env_steps / float(tm.item())
+
+  # float64 actions in, int64 elapsed out (the reference's in-memory dtypes)
+  e2e_f64 = time_host(launch_host)
+  # compact formats: float32 actions (action_spec dtype), int32 elapsed us
+  h_ctl32 = [c.float().pin_memory() for c in h_ctl]
+  d_a32 = torch.empty((t_steps, n, 2), dtype=torch.float32, device=dev)
+  d_el32 = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  h_el32 = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
+
+  def launch_host32(i):
+    nat.check(nat.lib.pd_rollout_actions_host_f32(
+        lat_c, st_c, C.byref(rate.c), P(h_ctl32[i % pool]),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
+        P(d_a32), P(d_stage), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el32),
+        stream))
+
+  e2e_value = time_host(launch_host32)
+  h2d = h_ctl32[0].numel() * 4
+  d2h = h_si.numel() * 4 + h_el32.numel() * 4
 
   # -- roofline of the dominant kernel ----------------------------------------
   peak, peak_kind = measured_peak()
@@ -645,7 +663,15 @@ def run_ours(args, cfg):
         'data': 'synthetic', 'config': cfg, 'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h,
-                'api': 'pd_rollout_actions_host (pinned host buffers)'},
+                'api': 'pd_rollout_actions_host_f32 (pinned host buffers: '
+                       'float32 actions in = the adapters\' action_spec '
+                       'dtype, int32 Si site + int32 elapsed us out)',
+                'float64_io': {
+                    'value': e2e_f64, 'unit': UNIT,
+                    'h2d_bytes_per_step': h_ctl[0].numel() * 8,
+                    'd2h_bytes_per_step': h_si.numel() * 4 + h_el.numel() * 8,
+                    'api': 'pd_rollout_actions_host (float64 actions, int64 '
+                           'elapsed us)'}},
         'gpu_launches': args.steps, 'roofline': roofline,
         'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
         'episodes': episodes, 'learned_mlp': mlp, 'export': export,

@@ -304,6 +304,20 @@ int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
                             int32_t* d_si_idx, int64_t* d_elapsed_us,
                             int32_t* h_si_idx, int64_t* h_elapsed_us,
                             void* stream);
+/* pd_rollout_actions_host with compact host formats: actions as float32 (the
+ * dtype the action adapters' action_spec declares, action_adapters.py:80-84,
+ * 202-216; widened exactly on the device) and per-step elapsed time as int32
+ * microseconds (dwell + 2 * image_duration must fit).  Results equal
+ * pd_rollout_actions_host on the widened actions.  Staging (device):
+ * d_actions_f32 float [n_steps][n][2], d_controls_xy double [n_steps][n][2],
+ * d_si_idx int32 / d_elapsed_us int64 / d_elapsed_us32 int32 [n_steps][n]. */
+int pd_rollout_actions_host_f32(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const float* h_actions_xy, int32_t action_mode,
+    double max_distance_angstroms, int64_t dwell_us_scalar, int32_t n_steps,
+    int64_t image_duration_us, float* d_actions_f32, double* d_controls_xy,
+    int32_t* d_si_idx, int64_t* d_elapsed_us, int32_t* d_elapsed_us32,
+    int32_t* h_si_idx, int32_t* h_elapsed_us32, void* stream);
 
 /* ---- imaging.py:42-72: re-draws the nine image parameters of the envs'
  *      current episode from the uniforms the last pd_reset used (RESET draws

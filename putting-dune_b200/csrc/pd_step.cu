@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "pd_episode.cuh"
 
 #ifndef PD_STEP_MIN_BLOCKS
@@ -1738,6 +1740,144 @@ extern "C" int pd_rollout_actions_host(
     if (h_elapsed_us)
       PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us + off, d_elapsed_us + off,
                                  static_cast<size_t>(steps) * n * sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, pipe->d2h));
+  }
+  PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+  PD_CUDA_OK(cudaStreamSynchronize(s));
+  return PD_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Compact host formats: float32 actions in (the dtype every action adapter
+// declares, action_adapters.py:80-84,124-128,202-216), int32 elapsed
+// microseconds out.  Both conversions are exact (float32 -> float64 widening;
+// dwell + 2 x image duration is checked to fit int32), so results equal
+// pd_rollout_actions_host fed the widened actions.  8 + 8 instead of 16 + 12
+// bytes per env-step cross PCIe, which is what bounds the call.
+// ---------------------------------------------------------------------------
+namespace pd {
+__global__ void __launch_bounds__(256)
+    k_widen_actions(const float2* __restrict__ in, double2* __restrict__ out,
+                    int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       i < count; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float2 v = in[i];
+    out[i] = make_double2(static_cast<double>(v.x), static_cast<double>(v.y));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_narrow_elapsed(const int64_t* __restrict__ in, int32_t* __restrict__ out,
+                     int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       i < count; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<int32_t>(in[i]);
+}
+
+static int convert_grid(int64_t count) {
+  const int64_t want = (count + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+}  // namespace pd
+
+extern "C" int pd_rollout_actions_host_f32(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const float* h_actions_xy, int32_t action_mode,
+    double max_distance_angstroms, int64_t dwell_us_scalar, int32_t n_steps,
+    int64_t image_duration_us, float* d_actions_f32, double* d_controls_xy,
+    int32_t* d_si_idx, int64_t* d_elapsed_us, int32_t* d_elapsed_us32,
+    int32_t* h_si_idx, int32_t* h_elapsed_us32, void* stream) {
+  PD_REQUIRE(st != nullptr, "null state");
+  PD_REQUIRE(n_steps >= 0, "negative n_steps");
+  PD_REQUIRE(n_steps == 0 || (h_actions_xy && d_actions_f32 && d_controls_xy),
+             "null actions / staging");
+  PD_REQUIRE(!h_si_idx || d_si_idx, "si_idx needs device staging");
+  PD_REQUIRE(!h_elapsed_us32 || (d_elapsed_us && d_elapsed_us32),
+             "elapsed needs device staging");
+  PD_REQUIRE(dwell_us_scalar >= 0 && image_duration_us >= 0 &&
+                 dwell_us_scalar + 2 * image_duration_us < (1LL << 31),
+             "per-step elapsed time does not fit int32 microseconds");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n = st->n_envs;
+  if (n == 0 || n_steps == 0) return PD_OK;
+  pd::HostPipeline* pipe = nullptr;
+  int rcode = pd::host_pipeline(&pipe);
+  if (rcode != PD_OK) return rcode;
+  // With 8 + 8 bytes per env-step the copies no longer bound the call: the
+  // kernels of the chunks run back to back and what is left over is the fill
+  // (H2D copy of the first chunk) and the drain (kernel + D2H copy of the
+  // last one) plus ~20 us of stream hand-offs per chunk, so the schedule has
+  // few chunks and a short last one (measured at 4096 envs x 256 steps, in
+  // sixteenths: "2,5,5,3,1" 0.38 ms, "1,3,4,4,3,1" 0.41, "1,2,3,4,3,2,1" 0.44,
+  // one chunk 0.54).  PD_HOST_SCHEDULE overrides.
+  static const std::vector<int> schedule = [] {
+    std::vector<int> w;
+    const char* v = getenv("PD_HOST_SCHEDULE");
+    const char* p = v ? v : "2,5,5,3,1";
+    while (*p) {
+      w.push_back(atoi(p));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+    if (w.empty() || w.size() > 16) w.assign(1, 1);
+    return w;
+  }();
+  int total_w = 0;
+  for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
+  int n_chunks = static_cast<int>(schedule.size());
+  const bool small = static_cast<int64_t>(n_steps) * n < (1 << 18) ||
+                     n_steps < 2 * n_chunks;
+  if (small) n_chunks = 1;
+  PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
+  int t0[17];
+  t0[0] = 0;
+  for (int c = 0, acc = 0; c < n_chunks; ++c) {
+    acc += schedule[c] > 0 ? schedule[c] : 1;
+    t0[c + 1] = small ? n_steps
+                      : static_cast<int>(static_cast<int64_t>(n_steps) * acc /
+                                         total_w);
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n * 2;
+    const size_t cnt = static_cast<size_t>(t0[c + 1] - t0[c]) * n * 2;
+    PD_CUDA_OK(cudaMemcpyAsync(d_actions_f32 + off, h_actions_xy + off,
+                               cnt * sizeof(float), cudaMemcpyHostToDevice,
+                               pipe->h2d));
+    PD_CUDA_OK(cudaEventRecord(pipe->copied[c], pipe->h2d));
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n;
+    const int steps = t0[c + 1] - t0[c];
+    const int64_t items = static_cast<int64_t>(steps) * n;
+    PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->copied[c], 0));
+    pd::k_widen_actions<<<pd::convert_grid(items), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(d_actions_f32) + off,
+        reinterpret_cast<double2*>(d_controls_xy) + off, items);
+    PD_CUDA_OK(cudaGetLastError());
+    rcode = pd_rollout_actions(
+        lat, st, rc, d_controls_xy + off * 2, action_mode,
+        max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
+        h_si_idx ? d_si_idx + off : nullptr,
+        h_elapsed_us32 ? d_elapsed_us + off : nullptr, stream);
+    if (rcode != PD_OK) return rcode;
+    if (h_elapsed_us32) {
+      pd::k_narrow_elapsed<<<pd::convert_grid(items), 256, 0, s>>>(
+          d_elapsed_us + off, d_elapsed_us32 + off, items);
+      PD_CUDA_OK(cudaGetLastError());
+    }
+    PD_CUDA_OK(cudaEventRecord(pipe->stepped[c], s));
+    PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0));
+    if (h_si_idx)
+      PD_CUDA_OK(cudaMemcpyAsync(h_si_idx + off, d_si_idx + off,
+                                 static_cast<size_t>(items) * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, pipe->d2h));
+    if (h_elapsed_us32)
+      PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us32 + off, d_elapsed_us32 + off,
+                                 static_cast<size_t>(items) * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, pipe->d2h));
   }
   PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));

@@ -135,6 +135,9 @@ _SIGNATURES = {
     'pd_rollout_actions_host': ([_LP, _SP, _RP, _p, _i32, C.c_double, _i64,
                                  _i32, _i64, _p, _p, _p, _p, _p, _p],
                                 C.c_int),
+    'pd_rollout_actions_host_f32': ([_LP, _SP, _RP, _p, _i32, C.c_double,
+                                     _i64, _i32, _i64, _p, _p, _p, _p, _p, _p,
+                                     _p, _p], C.c_int),
     'pd_rollout_host': ([_LP, _SP, _RP, _p, _i64, _i32, _i64, _p, _p, _p, _p,
                          _p, _p], C.c_int),
     'pd_env_step': ([_LP, _SP, _RP, C.POINTER(PdEnvConfig),

@@ -510,6 +510,50 @@ def test_rollout_host_pipeline_matches_device_path(eng):
       np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
 
 
+def test_rollout_host_compact_formats(eng):
+  """pd_rollout_actions_host_f32: float32 actions in (action_spec dtype,
+  action_adapters.py:202-216), int32 elapsed microseconds out; equals the
+  device rollout on the widened actions, for chunked and unchunked sizes."""
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  for n, t_steps in ((4096, 300), (700, 9)):
+    rng = np.random.default_rng(n)
+    acts32 = torch.as_tensor(
+        rng.uniform(-1.1, 1.1, size=(t_steps, n, 2)).astype(np.float32)
+    ).pin_memory()
+    a = eng.EnvBatch(n, seed=52)
+    b = eng.EnvBatch(n, seed=52)
+    a.reset()
+    b.reset()
+    spec = gh.rate_spec(po.RATE_PRIOR)
+    si, el = a.rollout(acts32.double(), 1500000, spec, record=True,
+                       action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+    dev = b.device
+    d_a32 = torch.empty((t_steps, n, 2), dtype=torch.float32, device=dev)
+    d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
+    d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+    d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+    d_el32 = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+    h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
+    h_el = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    nat.check(nat.lib.pd_rollout_actions_host_f32(
+        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
+        P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el),
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
+    np.testing.assert_array_equal(h_el.numpy().astype(np.int64), gh.np_(el))
+    np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+    np.testing.assert_array_equal(gh.np_(b.sim_time_us), gh.np_(a.sim_time_us))
+  with pytest.raises(nat.NativeError, match='int32'):
+    nat.check(nat.lib.pd_rollout_actions_host_f32(
+        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 3000000000, t_steps, 2000000,
+        P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el),
+        None))
+
+
 GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
     'max_rate': 5.0,
     'mixture_weights': np.asarray((0.3, 0.3, 0.2, 0.1, 0.1)),
