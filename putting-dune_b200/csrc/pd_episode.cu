@@ -70,6 +70,15 @@ __global__ void __launch_bounds__(kGoalThreads)
       c_lo = static_cast<int>(k_lo / 32);
       c_hi = static_cast<int>((k_hi + 31) / 32);
     }
+    // goals.py:96-108 keeps the atoms whose distance from the Si, formed from
+    // the observed (normalised) coordinates, lies in (0.1, 50) angstrom.  When
+    // the FOV diagonal is below 49.9 A every atom in view is closer than 50
+    // (the reference's value differs from the true distance by ~1e-14), and
+    // every atom but the Si itself is farther than 0.1 (the lattice spacing
+    // is 1.42), so the test reduces to "in view and not the Si" and its two
+    // divisions and square root per atom are skipped.
+    const bool whole_view = w * w + h * h < 49.9 * 49.9;
+    const int si = st.si_idx[e];
     int count = 0;
     for (int c = c_lo; c < c_hi; ++c) {
       const int k = c * 32 + lane;
@@ -77,12 +86,16 @@ __global__ void __launch_bounds__(kGoalThreads)
       if (k < lat.n_sites) {
         const double2 p = site_position(__ldg(base + k), t);
         if (f.llx <= p.x && p.x <= f.urx && f.lly <= p.y && p.y <= f.ury) {
+          if (whole_view) {
+            valid = k != si;
+          } else {
           const double2 q = observe(f, p);
           const double dx = __dmul_rn(w, __dsub_rn(q.x, q_si.x));
           const double dy = __dmul_rn(h, __dsub_rn(q.y, q_si.y));
           const double dist =
               __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
           valid = dist < 50.0 && dist > 0.1;
+          }
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, valid);
