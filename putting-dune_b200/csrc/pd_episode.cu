@@ -11,6 +11,7 @@
 // Compiled with -fmad=false: the observation round trips
 // (material -> microscope -> material) are reproduced operation by operation.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pd_episode.cuh"
 
@@ -27,11 +28,12 @@ __global__ void __launch_bounds__(kGoalThreads)
     k_choose_goal(const pd_lattice lat, const pd_state st,
                   double* __restrict__ goal_xy,
                   int32_t* __restrict__ goal_site,
-                  const uint8_t* __restrict__ mask, uint32_t draw_index) {
-  extern __shared__ unsigned goal_masks[];  // [warps][n_chunks]
+                  const uint8_t* __restrict__ mask, uint32_t draw_index,
+                  int32_t by_rows, int32_t words_per_warp) {
+  extern __shared__ unsigned goal_masks[];  // [warps][words_per_warp]
   const int lane = threadIdx.x & 31;
   const int n_chunks = (lat.n_sites + 31) / 32;
-  unsigned* masks = goal_masks + (threadIdx.x >> 5) * n_chunks;
+  unsigned* masks = goal_masks + (threadIdx.x >> 5) * words_per_warp;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (kGoalThreads / 32);
   const double2* base = reinterpret_cast<const double2*>(lat.base_xy);
   for (int64_t e = blockIdx.x * (kGoalThreads / 32) + (threadIdx.x >> 5);
@@ -45,6 +47,85 @@ __global__ void __launch_bounds__(kGoalThreads)
     const double u =
         draw_linear(st.seed, st.env_offset + static_cast<uint32_t>(e),
                     st.episode[e] - 1u, PD_STREAM_RESET, draw_index);
+    // ---- row-analytic path ----
+    // When the FOV diagonal is below 49.9 A the valid goals are exactly the
+    // atoms in view other than the Si (see below), and the atoms in view are
+    // one run per lattice row: a lane takes a row, the warp scans the run
+    // lengths, and the k-th atom is read off the row that holds it.
+    if (by_rows && w * w + h * h < 49.9 * 49.9 && fabs(t.c) >= 1e-6 &&
+        fabs(t.s) >= 1e-6) {
+      const int ce = lat.n_cols - (lat.n_cols + 2) / 3;
+      const int co = lat.n_cols - (lat.n_cols + 1) / 3;
+      const int si = st.si_idx[e];
+      int total = 0;
+      int n_rows = 0;
+      for (int j0 = 0;; j0 += 32) {
+        const int j = j0 + lane;
+        const int k0 = (j >> 1) * (ce + co) + (j & 1) * ce;
+        const int cnt_row = (j & 1) ? co : ce;
+        const bool row_ok = k0 + cnt_row <= lat.n_sites;
+        int m_lo = 0, m_hi = -1;
+        if (row_ok) row_run_in_view(base, k0, cnt_row, t, f, &m_lo, &m_hi);
+        int cnt = m_hi >= m_lo ? m_hi - m_lo + 1 : 0;
+        // the Si is in view but is not a goal (distance 0 < 0.1)
+        if (cnt > 0 && si >= k0 + m_lo && si <= k0 + m_hi) --cnt;
+        if (row_ok) masks[j] = (static_cast<unsigned>(m_lo) << 16) |
+                               static_cast<unsigned>(cnt);
+        total += cnt;
+        const unsigned any = __ballot_sync(0xffffffffu, row_ok);
+        n_rows = j0 + __popc(any);
+        if (any != 0xffffffffu) break;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+        total += __shfl_xor_sync(0xffffffffu, total, d);
+      __syncwarp();
+      // locate the row that holds atom number floor(u * total): scan the run
+      // lengths 32 rows at a time
+      int found_site = -1;
+      if (total > 0) {
+        int target = static_cast<int>(floor(u * total));  // rng.choice(n)
+        for (int j0 = 0; j0 < n_rows; j0 += 32) {
+          const int j = j0 + lane;
+          const unsigned word = j < n_rows ? masks[j] : 0u;
+          const int cnt = static_cast<int>(word & 0xffffu);
+          int incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, incl > target);
+          if (hit) {
+            const int src = __ffs(hit) - 1;
+            if (lane == src) {
+              const int k0 = (j >> 1) * (ce + co) + (j & 1) * ce;
+              const int first = k0 + static_cast<int>(word >> 16);
+              int k = first + (target - (incl - cnt));
+              if (si >= first && si <= k) ++k;
+              found_site = k;
+            }
+            found_site = __shfl_sync(0xffffffffu, found_site, src);
+            break;
+          }
+          target -= __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
+      if (lane == 0) {
+        double2 g = make_double2(nan(""), nan(""));
+        if (found_site >= 0) {
+          const double2 q =
+              observe(f, site_position(__ldg(base + found_site), t));
+          g = microscope_to_material(f, q.x, q.y);
+        }
+        reinterpret_cast<double2*>(goal_xy)[e] = g;
+        if (goal_site) goal_site[e] = found_site;
+        if (found_site < 0) st.status[e] |= PD_ENV_NOT_RESET;  // no valid goal
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- exhaustive path ----
     // Only lattice rows that can intersect the FOV's circumscribed circle are
     // scanned: rows are horizontal lines of the base lattice and site ids are
     // row-major, so they form one contiguous id range.
@@ -131,6 +212,22 @@ __global__ void __launch_bounds__(kGoalThreads)
   }
 }
 
+// Shared-memory words per warp: chunk ballots (exhaustive path) or one word
+// per lattice row (row-analytic path).
+static int goal_words_per_warp(const pd_lattice* lat) {
+  const int chunks = (lat->n_sites + 31) / 32;
+  const int ce = lat->n_cols - (lat->n_cols + 2) / 3;
+  const int co = lat->n_cols - (lat->n_cols + 1) / 3;
+  const int rows = 2 * (lat->n_sites / (ce + co)) + 2;
+  return chunks > rows + 32 ? chunks : rows + 32;
+}
+
+// PD_GOAL_SCAN=1 forces the exhaustive scan (A/B timing, parity tests).
+static int goal_by_rows() {
+  const char* v = getenv("PD_GOAL_SCAN");
+  return (v && v[0] == '1') ? 0 : 1;
+}
+
 int validate_common(const pd_lattice* lat, const pd_state* st,
                     const pd_rate_config* rc);
 // pd_step.cu: k_walk in episode mode.
@@ -146,10 +243,11 @@ int choose_goals_masked(const pd_lattice* lat, const pd_state* st,
                         uint32_t draw_index, cudaStream_t s) {
   const int64_t blocks = (st->n_envs + 3) / 4;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  const size_t smem =
-      sizeof(unsigned) * (kGoalThreads / 32) * ((lat->n_sites + 31) / 32);
+  const int words = goal_words_per_warp(lat);
+  const size_t smem = sizeof(unsigned) * (kGoalThreads / 32) * words;
   k_choose_goal<<<static_cast<int>(blocks < cap ? blocks : cap), kGoalThreads,
-                  smem, s>>>(*lat, *st, goal_xy, nullptr, mask, draw_index);
+                  smem, s>>>(*lat, *st, goal_xy, nullptr, mask, draw_index,
+                             goal_by_rows(), words);
   PD_CUDA_OK(cudaGetLastError());
   return PD_OK;
 }
@@ -175,11 +273,11 @@ extern "C" int pd_run_episodes(const pd_lattice* lat, const pd_state* st,
   {
     const int64_t blocks = (st->n_envs + 3) / 4;
     const int64_t cap = static_cast<int64_t>(pd::sm_count()) * 16;
-    const size_t smem = sizeof(unsigned) * (pd::kGoalThreads / 32) *
-                        ((lat->n_sites + 31) / 32);
+    const int words = pd::goal_words_per_warp(lat);
+    const size_t smem = sizeof(unsigned) * (pd::kGoalThreads / 32) * words;
     pd::k_choose_goal<<<static_cast<int>(blocks < cap ? blocks : cap),
-                        pd::kGoalThreads, smem, s>>>(*lat, *st, goal_xy,
-                                                     goal_site, nullptr, 13u);
+                        pd::kGoalThreads, smem, s>>>(
+        *lat, *st, goal_xy, goal_site, nullptr, 13u, pd::goal_by_rows(), words);
     PD_CUDA_OK(cudaGetLastError());
   }
   return pd::launch_episodes(lat, st, rc, cfg, goal_xy, stats, s);

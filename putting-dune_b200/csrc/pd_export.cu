@@ -70,6 +70,11 @@ __device__ __forceinline__ void put_point(uint8_t* p, double x, double y) {
   put_f32(p + 6, __double2float_rn(y));
 }
 
+// row_run_in_view divides by cos / sin of the lattice angle.
+__device__ __forceinline__ bool rows_usable(const Lattice4& t) {
+  return fabs(t.c) >= 1e-6 && fabs(t.s) >= 1e-6;
+}
+
 __host__ __device__ inline int64_t observation_bytes(int32_t atoms,
                                                      int32_t n_controls) {
   const uint32_t grid = 16u * static_cast<uint32_t>(atoms);
@@ -88,18 +93,37 @@ __global__ void __launch_bounds__(kExportThreads)
        e < st.n_envs; e += warps) {
     const Lattice4 t = load_lattice4(st.lattice, e);
     const Fov4 f = load_fov4(st.fov, e);
-    int c_lo, c_hi;
-    fov_chunk_range(lat, t, f, &c_lo, &c_hi);
     int count = 0;
-    for (int k0 = 32 * c_lo; k0 < 32 * c_hi; k0 += 32) {
-      const int k = k0 + lane;
-      bool keep = false;
-      if (k < lat.n_sites) {
-        const double2 p = site_position(__ldg(base + k), t);
-        keep = (f.llx <= p.x) && (p.x <= f.urx) && (f.lly <= p.y) &&
-               (p.y <= f.ury);
+    if (rows_usable(t)) {
+      // one lane per lattice row: the atoms in view are one run per row
+      const int ce = lat.n_cols - (lat.n_cols + 2) / 3;
+      const int co = lat.n_cols - (lat.n_cols + 1) / 3;
+      for (int j0 = 0;; j0 += 32) {
+        const int j = j0 + lane;
+        const int k0 = (j >> 1) * (ce + co) + (j & 1) * ce;
+        const int cnt_row = (j & 1) ? co : ce;
+        const bool row_ok = k0 + cnt_row <= lat.n_sites;
+        int m_lo = 0, m_hi = -1;
+        if (row_ok) row_run_in_view(base, k0, cnt_row, t, f, &m_lo, &m_hi);
+        if (m_hi >= m_lo) count += m_hi - m_lo + 1;
+        if (__ballot_sync(0xffffffffu, row_ok) != 0xffffffffu) break;
       }
-      count += __popc(__ballot_sync(0xffffffffu, keep));
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+        count += __shfl_xor_sync(0xffffffffu, count, d);
+    } else {
+      int c_lo, c_hi;
+      fov_chunk_range(lat, t, f, &c_lo, &c_hi);
+      for (int k0 = 32 * c_lo; k0 < 32 * c_hi; k0 += 32) {
+        const int k = k0 + lane;
+        bool keep = false;
+        if (k < lat.n_sites) {
+          const double2 p = site_position(__ldg(base + k), t);
+          keep = (f.llx <= p.x) && (p.x <= f.urx) && (f.lly <= p.y) &&
+                 (p.y <= f.ury);
+        }
+        count += __popc(__ballot_sync(0xffffffffu, keep));
+      }
     }
     if (lane == 0) {
       out_atoms[e] = count;
@@ -212,6 +236,9 @@ __global__ void __launch_bounds__(kExportThreads)
     const int shift = (4 - (hdr & 3)) & 3;  // record starts at stage + shift
     uint8_t* rec = stage + shift;
     // ---- A: compact the ids of the atoms in view ----
+    // (a lane-per-row variant of this pass -- runs from row_run_in_view, a
+    // per-atom search of the row prefix in pass B -- was measured slower:
+    // 324 vs 274 us per 65 536 records; the size pass does use the rows)
     int c_lo, c_hi;
     fov_chunk_range(lat, t, f, &c_lo, &c_hi);
     int count = 0;

@@ -431,6 +431,51 @@ __device__ __forceinline__ void fov_chunk_range(const pd_lattice& lat,
   *c_hi = static_cast<int>((k_hi + 31) / 32);
 }
 
+// In-view run of one lattice row.  Along a row the base y is fixed and the
+// site position (graphene.py:545-557) is linear in the base x, so the four
+// inclusive bounds of graphene.py:600-644 cut out one interval of base x; the
+// sites of a row are 1.23 A or more apart, so only the first and the last
+// site of the run can sit within rounding distance of a bound and those two
+// are tested with the exact expression.  Returns the run [*m_lo, *m_hi] as
+// positions inside the row (empty if *m_lo > *m_hi).  Requires |c|, |s| >=
+// 1e-6 (the caller falls back to the exhaustive scan otherwise).
+__device__ __forceinline__ void row_run_in_view(const double2* base, int k0,
+                                                int cnt, const Lattice4& t,
+                                                const Fov4& f, int* m_lo,
+                                                int* m_hi) {
+  const double Y = __ldg(base + k0).y + t.oy;
+  // llx <= X c + Y s <= urx ; lly <= Y c - X s <= ury, X = base x + ox
+  double a0 = (f.llx - Y * t.s) / t.c, a1 = (f.urx - Y * t.s) / t.c;
+  double b0 = (Y * t.c - f.ury) / t.s, b1 = (Y * t.c - f.lly) / t.s;
+  if (a0 > a1) { const double tmp = a0; a0 = a1; a1 = tmp; }
+  if (b0 > b1) { const double tmp = b0; b0 = b1; b1 = tmp; }
+  const double kSlack = 1e-6;
+  const double xa = fmax(a0, b0) - t.ox - kSlack;
+  const double xb = fmin(a1, b1) - t.ox + kSlack;
+  // first site with x >= xa, last site with x <= xb (x increases along a row)
+  int lo = 0, hi = cnt;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(base + k0 + mid).x < xa) lo = mid + 1; else hi = mid;
+  }
+  int first = lo;
+  lo = first;
+  hi = cnt;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(base + k0 + mid).x <= xb) lo = mid + 1; else hi = mid;
+  }
+  int last = lo - 1;
+  auto in_view = [&](int m) {
+    const double2 p = site_position(__ldg(base + k0 + m), t);
+    return f.llx <= p.x && p.x <= f.urx && f.lly <= p.y && p.y <= f.ury;
+  };
+  if (first <= last && !in_view(first)) ++first;
+  if (first <= last && !in_view(last)) --last;
+  *m_lo = first;
+  *m_hi = last;
+}
+
 // simulator.py:161-165: FOV = [P_si - s/2, P_si + s/2].
 __device__ __forceinline__ Fov4 centred_fov(const double2 p, double scale) {
   const double h = __ddiv_rn(scale, 2.0);

@@ -87,3 +87,27 @@ def test_sharded_episodes_equal_unsharded():
            for r in range(4)]
   np.testing.assert_array_equal(np.concatenate(parts).tobytes(),
                                 full.tobytes())
+
+
+def test_goal_selection_row_path_equals_scan(monkeypatch):
+  """k_choose_goal's row-analytic path (one lane per lattice row: the in-view
+  run from the FOV bounds, exact test at the run's ends) picks the same goal
+  site as the exhaustive scan for every env -- at full batch size, on the
+  default lattice and on a small sheet that the FOV overhangs."""
+  from putting_dune_b200 import engine, episodes
+  for n, cols in ((300000, 50), (20000, 14)):
+    out = []
+    for flag in ('0', '1'):
+      monkeypatch.setenv('PD_GOAL_SCAN', flag)
+      b = engine.EnvBatch(n, seed=7, lattice=engine.Lattice(cols))
+      stats, goal_site, goal_xy = episodes.run_greedy_episodes(
+          b, gh.rate_spec(po.RATE_SIMPLE),
+          episodes.EpisodeConfig(step_limit=3))
+      out.append((gh.np_(goal_site), gh.np_(goal_xy),
+                  episodes.stats_to_numpy(stats)))
+    (site_a, xy_a, st_a), (site_b, xy_b, st_b) = out
+    np.testing.assert_array_equal(site_a, site_b)
+    np.testing.assert_array_equal(xy_a, xy_b)
+    np.testing.assert_array_equal(st_a['num_actions'], st_b['num_actions'])
+    assert (site_a >= 0).all()
+    assert len(np.unique(site_a)) > 100
