@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kGoalThreads)
         const int cnt_row = (j & 1) ? co : ce;
         const bool row_ok = k0 + cnt_row <= lat.n_sites;
         int m_lo = 0, m_hi = -1;
-        if (row_ok) row_run_in_view(base, k0, cnt_row, t, f, &m_lo, &m_hi);
+        if (row_ok) row_run_in_view(base, k0, cnt_row, j, lat.n_cols, t, f, &m_lo,
+                                    &m_hi);
         int cnt = m_hi >= m_lo ? m_hi - m_lo + 1 : 0;
         // the Si is in view but is not a goal (distance 0 < 0.1)
         if (cnt > 0 && si >= k0 + m_lo && si <= k0 + m_hi) --cnt;

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(kExportThreads)
         const int cnt_row = (j & 1) ? co : ce;
         const bool row_ok = k0 + cnt_row <= lat.n_sites;
         int m_lo = 0, m_hi = -1;
-        if (row_ok) row_run_in_view(base, k0, cnt_row, t, f, &m_lo, &m_hi);
+        if (row_ok) row_run_in_view(base, k0, cnt_row, j, lat.n_cols, t, f, &m_lo,
+                                    &m_hi);
         if (m_hi >= m_lo) count += m_hi - m_lo + 1;
         if (__ballot_sync(0xffffffffu, row_ok) != 0xffffffffu) break;
       }

@@ -436,36 +436,50 @@ __device__ __forceinline__ void fov_chunk_range(const pd_lattice& lat,
 // inclusive bounds of graphene.py:600-644 cut out one interval of base x; the
 // sites of a row are 1.23 A or more apart, so only the first and the last
 // site of the run can sit within rounding distance of a bound and those two
-// are tested with the exact expression.  Returns the run [*m_lo, *m_hi] as
+// are tested with the exact expression; the run itself comes from the column
+// arithmetic of the lattice, widened by 1e-6 A.  Returns the run [*m_lo, *m_hi] as
 // positions inside the row (empty if *m_lo > *m_hi).  Requires |c|, |s| >=
 // 1e-6 (the caller falls back to the exhaustive scan otherwise).
 __device__ __forceinline__ void row_run_in_view(const double2* base, int k0,
-                                                int cnt, const Lattice4& t,
+                                                int cnt, int row, int n_cols,
+                                                const Lattice4& t,
                                                 const Fov4& f, int* m_lo,
                                                 int* m_hi) {
   const double Y = __ldg(base + k0).y + t.oy;
   // llx <= X c + Y s <= urx ; lly <= Y c - X s <= ury, X = base x + ox
-  double a0 = (f.llx - Y * t.s) / t.c, a1 = (f.urx - Y * t.s) / t.c;
-  double b0 = (Y * t.c - f.ury) / t.s, b1 = (Y * t.c - f.lly) / t.s;
+  // (only an estimate, widened by kSlack: reciprocals instead of divisions)
+  const double inv_c = 1.0 / t.c, inv_s = 1.0 / t.s;  // loop invariant
+  double a0 = (f.llx - Y * t.s) * inv_c, a1 = (f.urx - Y * t.s) * inv_c;
+  double b0 = (Y * t.c - f.ury) * inv_s, b1 = (Y * t.c - f.lly) * inv_s;
   if (a0 > a1) { const double tmp = a0; a0 = a1; a1 = tmp; }
   if (b0 > b1) { const double tmp = b0; b0 = b1; b1 = tmp; }
   const double kSlack = 1e-6;
   const double xa = fmax(a0, b0) - t.ox - kSlack;
   const double xb = fmin(a1, b1) - t.ox + kSlack;
-  // first site with x >= xa, last site with x <= xb (x increases along a row)
-  int lo = 0, hi = cnt;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(base + k0 + mid).x < xa) lo = mid + 1; else hi = mid;
+  // Column i of a row sits at base x = (i + 0.5 [odd rows]) * 1.42 + x0 with
+  // x0 = base[0].x - 1.42 (site 0 is column 1 of row 0); even rows lack the
+  // columns i % 3 == 0, odd rows i % 3 == 1 (graphene.py:483-499).  The table
+  // differs from this formula by ~1e-14, far inside the slack.
+  const int odd = row & 1;
+  const double x0 = __ldg(base).x - kBond + (odd ? 0.5 * kBond : 0.0);
+  const double kInvBond = 1.0 / kBond;
+  const double ia = ceil((xa - x0) * kInvBond);
+  const double ib = floor((xb - x0) * kInvBond);
+  int first = cnt, last = -1;
+  if (ia <= ib && ib >= 0.0 && ia <= static_cast<double>(n_cols - 1)) {
+    int i_lo = ia < 0.0 ? 0 : static_cast<int>(ia);
+    int i_hi = ib > static_cast<double>(n_cols - 1) ? n_cols - 1
+                                                    : static_cast<int>(ib);
+    const int gap = odd ? 1 : 0;  // residue of the missing columns
+    if (i_lo % 3 == gap) ++i_lo;
+    if (i_hi % 3 == gap) --i_hi;
+    if (i_lo <= i_hi) {
+      // position inside the row of a present column
+      first = odd ? i_lo - (i_lo + 1) / 3 : (i_lo - 1) - (i_lo - 1) / 3;
+      last = odd ? i_hi - (i_hi + 1) / 3 : (i_hi - 1) - (i_hi - 1) / 3;
+      if (last > cnt - 1) last = cnt - 1;
+    }
   }
-  int first = lo;
-  lo = first;
-  hi = cnt;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(base + k0 + mid).x <= xb) lo = mid + 1; else hi = mid;
-  }
-  int last = lo - 1;
   auto in_view = [&](int m) {
     const double2 p = site_position(__ldg(base + k0 + m), t);
     return f.llx <= p.x && p.x <= f.urx && f.lly <= p.y && p.y <= f.ury;
