@@ -90,86 +90,83 @@ struct RateArgs {
 // below use that freedom to drop the square root and all but one division;
 // -DPD_EXACT_RATE_OPS keeps the reference's operation sequence.
 // ---------------------------------------------------------------------------
+// One neighbour of graphene.py:133-166 simple_canonical_rate_function:
+//   r = 1 / ((4 |beam - nbr| / 1.42)^2 + 1) = 1 / (|beam - nbr|^2 16/1.42^2 + 1)
+__device__ __forceinline__ float rate_simple_one(const double2 beam,
+                                                 const double2 psi,
+                                                 const double2 p) {
 #ifdef PD_EXACT_RATE_OPS
-// graphene.py:133-166 simple_canonical_rate_function, op for op.
-__device__ __forceinline__ void rates_simple(const double2 beam,
-                                             const double2 psi,
-                                             const double2 pn[3], float r[3]) {
+  // op for op
   const double bx = __dsub_rn(beam.x, psi.x);
   const double by = __dsub_rn(beam.y, psi.y);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double nx = __dsub_rn(pn[i].x, psi.x);
-    const double ny = __dsub_rn(pn[i].y, psi.y);
-    const double dx = __dsub_rn(bx, nx);
-    const double dy = __dsub_rn(by, ny);
-    // np.linalg.norm(axis=-1) == sqrt(dx*dx + dy*dy)
-    double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    d = __ddiv_rn(d, kBond);
-    const double a = __dmul_rn(d, 4.0);
-    const double den = __dadd_rn(__dmul_rn(a, a), 1.0);
-    r[i] = __double2float_rn(__ddiv_rn(1.0, den));
-  }
-}
+  const double nx = __dsub_rn(p.x, psi.x);
+  const double ny = __dsub_rn(p.y, psi.y);
+  const double dx = __dsub_rn(bx, nx);
+  const double dy = __dsub_rn(by, ny);
+  // np.linalg.norm(axis=-1) == sqrt(dx*dx + dy*dy)
+  double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  d = __ddiv_rn(d, kBond);
+  const double a = __dmul_rn(d, 4.0);
+  const double den = __dadd_rn(__dmul_rn(a, a), 1.0);
+  return __double2float_rn(__ddiv_rn(1.0, den));
 #else
-// graphene.py:133-166: r = 1 / ((4 |beam - nbr| / 1.42)^2 + 1)
-//                        = 1 / (|beam - nbr|^2 * 16 / 1.42^2 + 1).
+  const double kScale = 16.0 / (kBond * kBond);
+  (void)psi;
+  const double dx = beam.x - p.x;
+  const double dy = beam.y - p.y;
+  const double d2 = fma(dx, dx, dy * dy);
+  return __double2float_rn(1.0 / fma(d2, kScale, 1.0));
+#endif
+}
+
 __device__ __forceinline__ void rates_simple(const double2 beam,
                                              const double2 psi,
                                              const double2 pn[3], float r[3]) {
-  const double kScale = 16.0 / (kBond * kBond);
-  (void)psi;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double dx = beam.x - pn[i].x;
-    const double dy = beam.y - pn[i].y;
-    const double d2 = fma(dx, dx, dy * dy);
-    r[i] = __double2float_rn(1.0 / fma(d2, kScale, 1.0));
-  }
+  for (int i = 0; i < 3; ++i) r[i] = rate_simple_one(beam, psi, pn[i]);
 }
-#endif
 
-// graphene.py:191-229 HumanPriorRatePredictor.predict with the constants of
-// constants.py:26-28.  The reference rotates the mean (0.85, 0) by
-// rotate_coordinates(mean, -theta) with theta = atan2 of the neighbour, which
-// places the peak at 0.85*(cos theta, -sin theta) (mirror quirk, SURVEY
-// appendix B.1); cos/sin of atan2 are taken directly from the neighbour
-// vector.  With covariance 0.1*I,
+// One neighbour of graphene.py:191-229 HumanPriorRatePredictor.predict with
+// the constants of constants.py:26-28.  The reference rotates the mean
+// (0.85, 0) by rotate_coordinates(mean, -theta) with theta = atan2 of the
+// neighbour, which places the peak at 0.85*(cos theta, -sin theta) (mirror
+// quirk); cos/sin of atan2 are taken directly from the
+// neighbour vector.  With covariance 0.1*I,
 //   max_rate * pdf(x)/pdf(mu) = (ln 2 / 3) * exp(-5 |x - mu|^2).
-__device__ __forceinline__ void rates_prior(const double2 beam,
-                                            const double2 psi,
-                                            const double2 pn[3], float r[3]) {
+__device__ __forceinline__ float rate_prior_one(const double2 beam,
+                                                const double2 psi,
+                                                const double2 p) {
   const double kMaxRate = 0.23104906018664842;  // np.log(2) / 3
 #ifdef PD_EXACT_RATE_OPS
   const double x = __ddiv_rn(__dsub_rn(beam.x, psi.x), kBond);
   const double y = __ddiv_rn(__dsub_rn(beam.y, psi.y), kBond);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double nx = __dsub_rn(pn[i].x, psi.x);
-    const double ny = __dsub_rn(pn[i].y, psi.y);
-    const double inv =
-        __ddiv_rn(0.85, __dsqrt_rn(__dadd_rn(__dmul_rn(nx, nx),
-                                             __dmul_rn(ny, ny))));
-    const double dx = __dsub_rn(x, __dmul_rn(nx, inv));
-    const double dy = __dadd_rn(y, __dmul_rn(ny, inv));
-    const double maha =
-        __ddiv_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.1);
-    r[i] = __double2float_rn(__dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha))));
-  }
+  const double nx = __dsub_rn(p.x, psi.x);
+  const double ny = __dsub_rn(p.y, psi.y);
+  const double inv = __ddiv_rn(
+      0.85, __dsqrt_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny))));
+  const double dx = __dsub_rn(x, __dmul_rn(nx, inv));
+  const double dy = __dadd_rn(y, __dmul_rn(ny, inv));
+  const double maha =
+      __ddiv_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.1);
+  return __double2float_rn(__dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha))));
 #else
   const double kInvBond = 1.0 / kBond;
   const double x = (beam.x - psi.x) * kInvBond;
   const double y = (beam.y - psi.y) * kInvBond;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double nx = pn[i].x - psi.x;
-    const double ny = pn[i].y - psi.y;
-    const double inv = 0.85 * rsqrt(fma(nx, nx, ny * ny));
-    const double dx = fma(-nx, inv, x);
-    const double dy = fma(ny, inv, y);
-    r[i] = __double2float_rn(kMaxRate * exp(-5.0 * fma(dx, dx, dy * dy)));
-  }
+  const double nx = p.x - psi.x;
+  const double ny = p.y - psi.y;
+  const double inv = 0.85 * rsqrt(fma(nx, nx, ny * ny));
+  const double dx = fma(-nx, inv, x);
+  const double dy = fma(ny, inv, y);
+  return __double2float_rn(kMaxRate * exp(-5.0 * fma(dx, dx, dy * dy)));
 #endif
+}
+
+__device__ __forceinline__ void rates_prior(const double2 beam,
+                                            const double2 psi,
+                                            const double2 pn[3], float r[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[i] = rate_prior_one(beam, psi, pn[i]);
 }
 
 // graphene.py:303-388 GaussianMixtureRateFunction.__call__ (float64 rates).

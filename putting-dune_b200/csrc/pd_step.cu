@@ -594,6 +594,8 @@ __global__ void __launch_bounds__(kStepThreads)
       const int step = t + j;
       const bool valid = (first ? j == 0 : true) && step < n_steps;
       bool certain = false;
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);  // Philox words of this lane's
+                                             // iteration (re-used by phase B)
       if (valid) {
         if (j == 0 && c_done) {
           certain = true;
@@ -614,8 +616,7 @@ __global__ void __launch_bounds__(kStepThreads)
             bx = (px - qfx) * wfx;
             by = (py - qfy) * wfy;
           }
-          const uint4 w =
-              philox4x32_10(env_id, ctrl_count + static_cast<uint32_t>(j),
+          w = philox4x32_10(env_id, ctrl_count + static_cast<uint32_t>(j),
                             j == 0 ? it : 0u, PD_STREAM_KMC, a.st.seed);
           certain = certainly_no_hop<RATE>(geo, bx, by, w.x,
                                            dwell - (j == 0 ? elapsed : 0));
@@ -656,30 +657,59 @@ __global__ void __launch_bounds__(kStepThreads)
       if (!unsure) continue;
 
       // ---- phase B: the current iteration (t, it), exactly ----
-      int nb[3];
-      tab.neighbors(si, nb);
-      double2 pn[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        pn[i] = site_position(tab.position(nb[i]), lat);
+      // It is the iteration lane `ju` looked at in phase A, so its Philox
+      // words come from there; the three neighbour rates are evaluated by
+      // three lanes (lane j takes neighbour j % 3) and gathered, instead of
+      // three times by every lane.
+      const int ju = __ffs(unsure) - 1;
+      const uint4 wb = make_uint4(__shfl_sync(gmask, w.x, gbase + ju),
+                                  __shfl_sync(gmask, w.y, gbase + ju),
+                                  __shfl_sync(gmask, w.z, gbase + ju),
+                                  __shfl_sync(gmask, w.w, gbase + ju));
       if (it == 0) {
         const double2 c = ctl[static_cast<int64_t>(t) * n + e];
         double2 pos = c;
         if (relative) pos = relative_to_silicon(fov, psi, c, a.max_distance);
         beam0 = microscope_to_material(fov, pos.x, pos.y);
       }
-      const uint4 w =
-          philox4x32_10(env_id, ctrl_count, it, PD_STREAM_KMC, a.st.seed);
+      int nb[3];
+      tab.neighbors(si, nb);
+      float r[3];
+      double2 pm;  // position of this lane's neighbour
+      if (G >= 4) {
+        const int mine = j % 3;
+        pm = site_position(
+            tab.position(mine == 0 ? nb[0] : (mine == 1 ? nb[1] : nb[2])), lat);
+        const float rm = RATE == PD_RATE_PRIOR ? rate_prior_one(beam0, psi, pm)
+                                               : rate_simple_one(beam0, psi, pm);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] = __shfl_sync(gmask, rm, gbase + i);
+      } else {
+        double2 pn[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          pn[i] = site_position(tab.position(nb[i]), lat);
+        eval_rates<RATE>(a.ra, beam0, psi, pn, r);
+        pm = make_double2(0.0, 0.0);
+      }
       int slot = 0;
       bool bad = false;
       long long el = elapsed;
-      const bool hop = rate_event<RATE>(a.ra, beam0, psi, pn, u53(w.x, w.y),
-                                        u53(w.z, w.w), dwell, &el, &slot, &bad);
+      const bool hop = kmc_event(r, u53(wb.x, wb.y), u53(wb.z, wb.w), dwell,
+                                 &el, &slot, &bad);
+      double2 p_new;
+      if (G >= 4) {
+        p_new.x = shfl_double(gmask, pm.x, gbase + slot);
+        p_new.y = shfl_double(gmask, pm.y, gbase + slot);
+      } else {
+        p_new = site_position(
+            tab.position(slot == 0 ? nb[0] : (slot == 1 ? nb[1] : nb[2])), lat);
+      }
       if (bad) status |= PD_ENV_BAD_RATE;
       events += 1;
       if (hop) {
         si = slot == 0 ? nb[0] : (slot == 1 ? nb[1] : nb[2]);
-        psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
+        psi = p_new;
         transitions += 1;
         elapsed = el;
         it += 1;
