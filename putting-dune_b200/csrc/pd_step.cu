@@ -669,7 +669,30 @@ __global__ void __launch_bounds__(kStepThreads)
       if (it == 0) {
         const double2 c = ctl[static_cast<int64_t>(t) * n + e];
         double2 pos = c;
-        if (relative) pos = relative_to_silicon(fov, psi, c, a.max_distance);
+        if (relative) {
+          if (G >= 4) {
+            // relative_to_silicon(fov, psi, c, max_distance) with its four
+            // divisions (observed Si x, y; max_distance / FOV width, height)
+            // taken by four lanes
+            const int part = j & 3;
+            const double den = (part & 1) ? __dsub_rn(fov.ury, fov.lly)
+                                          : __dsub_rn(fov.urx, fov.llx);
+            const double num = part == 0   ? __dsub_rn(psi.x, fov.llx)
+                               : part == 1 ? __dsub_rn(psi.y, fov.lly)
+                                           : a.max_distance;
+            const double val = __ddiv_rn(num, den);
+            const double qx = shfl_double(gmask, val, gbase + 0);
+            const double qy = shfl_double(gmask, val, gbase + 1);
+            const double rx = shfl_double(gmask, val, gbase + 2);
+            const double ry = shfl_double(gmask, val, gbase + 3);
+            const double ax = fmin(fmax(c.x, -1.0), 1.0);
+            const double ay = fmin(fmax(c.y, -1.0), 1.0);
+            pos.x = fmin(fmax(__dadd_rn(qx, __dmul_rn(ax, rx)), 0.0), 1.0);
+            pos.y = fmin(fmax(__dadd_rn(qy, __dmul_rn(ay, ry)), 0.0), 1.0);
+          } else {
+            pos = relative_to_silicon(fov, psi, c, a.max_distance);
+          }
+        }
         beam0 = microscope_to_material(fov, pos.x, pos.y);
       }
       int nb[3];
