@@ -310,7 +310,19 @@ int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
  * microseconds (dwell + 2 * image_duration must fit).  Results equal
  * pd_rollout_actions_host on the widened actions.  Staging (device):
  * d_actions_f32 float [n_steps][n][2], d_controls_xy double [n_steps][n][2],
- * d_si_idx int32 / d_elapsed_us int64 / d_elapsed_us32 int32 [n_steps][n]. */
+ * d_si_idx int32 / d_elapsed_us int64 / d_elapsed_us32 int32 [n_steps][n];
+ * their contents after the call are unspecified.
+ *
+ * Small batches on the prior / simple rates (what k_rollout_pre covers in one
+ * wave of CTAs; n a multiple of 16, >= 2^18 env-steps, <= 16384 steps) with
+ * page-locked, device-visible host buffers (cudaHostAlloc / torch
+ * pin_memory) run as ONE launch that is its own copy pipeline: the CTAs of a
+ * few SMs read the action rows straight from the host buffer into
+ * d_actions_f32 and write finished result rows straight to h_si_idx /
+ * h_elapsed_us32, the CTAs of the other SMs step the environments a few rows
+ * behind the copy front.  Everything else (and PD_HOST_STREAMED=0) takes the
+ * chunked copy-engine pipeline of pd_rollout_actions_host.  Both forms return
+ * the same bytes. */
 int pd_rollout_actions_host_f32(
     const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
     const float* h_actions_xy, int32_t action_mode,

@@ -8,8 +8,10 @@
 //
 // Compiled with -fmad=false (see pd_kmc.cuh).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <vector>
 
 #include "pd_episode.cuh"
@@ -505,11 +507,227 @@ __global__ void __launch_bounds__(kStepThreads)
 //            exactly (float64, same expressions as k_rollout) and applies the
 //            outcome.  No shuffles: the lanes stay bit-identical replicas.
 // ~89 % of the controls of the relative_random workload never reach phase B.
+//
+// STREAM (pd_rollout_actions_host_f32): one launch that is its own copy
+// pipeline over PCIe.  CTAs 0..R-1 are readers: reader r pulls the action
+// rows r, r + R, ... from the caller's pinned buffer (device-visible host
+// memory, 16-byte loads, eight in flight per thread) into the HBM staging and
+// raises row_ready[row] behind a fence.  The stepping groups only look at
+// rows whose flag they have seen (`arr` = the ready prefix), so they follow
+// the copy front a few microseconds behind it.  The int32 results go to HBM
+// stagings that the call pre-fills with 0xFF bytes; -1 is neither a site nor
+// an elapsed time and every word is stored exactly once, so a word that is
+// not -1 is final.  CTAs R..R+W-1 are writers: they walk the result rows in
+// order, re-read (from L2) the 16-byte units that still hold a -1 and stream
+// the complete ones to the caller's pinned buffers -- the stepping groups pay
+// no fence and no counter for that.  No copy engine, no side streams, no
+// per-chunk stream hand-offs: the call is the fills, one launch and one
+// synchronize.
 // ---------------------------------------------------------------------------
-template <int RATE, bool STAGE>
+// Four row flags at once, straight from L2 (no L1 allocation or invalidation:
+// the rows themselves are only ever read after their flag was seen, so L1
+// never holds a stale line of them).
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ bool unit_final(const uint4 v) {
+  return v.x != 0xFFFFFFFFu && v.y != 0xFFFFFFFFu && v.z != 0xFFFFFFFFu &&
+         v.w != 0xFFFFFFFFu;
+}
+
+// sm_ctl words: election and tickets of the streamed rollout (zeroed by the
+// call).  Roles per SM id follow at kCtlRoles.
+enum : int {
+  kCtlCopySms = 0,   // SMs that have been given the copy role so far
+  kCtlCopyIdx = 1,   // copy CTAs so far
+  kCtlStepTicket = 2,
+  kCtlReadTicket = 3,
+  kCtlWriteTicket = 4,
+  kCtlRoles = 8,
+  kCtlSmSlots = 1024,
+  kCtlWords = kCtlRoles + kCtlSmSlots
+};
+constexpr int kGroupRows = 8;  // action rows a reader work unit spans
+
+struct StreamCopyArgs {
+  const float2* h_actions_f32;
+  const float2* actions_f32;
+  const int32_t *si_idx_out, *elapsed32_out;
+  int32_t *h_si_idx_out, *h_elapsed32_out;
+  uint32_t *row_ready, *sm_ctl;
+  int64_t n;
+  int T;
+  unsigned long long* trace;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// trace[0] = first CTA start (min), [1] = last reader end, [2] = last stepping
+// CTA end, [3] = last writer end, [4] = first row ready
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int slot,
+                                           bool is_min) {
+  if (trace && threadIdx.x == 0) {
+    if (is_min)
+      atomicMin(trace + slot, globaltimer_ns());
+    else
+      atomicMax(trace + slot, globaltimer_ns());
+  }
+}
+
+// Next ticket of a counter for the whole CTA.
+__device__ __forceinline__ uint32_t cta_ticket(uint32_t* counter,
+                                               uint32_t* s_slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) *s_slot = atomicAdd(counter, 1u);
+  __syncthreads();
+  return *s_slot;
+}
+
+// Reader work: unit u = (group of kGroupRows rows, slice of kStepThreads
+// 16-byte units), in row order.  One load per row in flight per thread, then
+// the stores, a fence and one count per row; a row is complete at
+// row_parts = slices per row.
+__device__ __forceinline__ void stream_read(const StreamCopyArgs& a,
+                                            uint32_t* s_slot) {
+  const int64_t row_units = a.n * 8 / 16;  // one row of float2 actions
+  const uint32_t Q =
+      static_cast<uint32_t>((row_units + kStepThreads - 1) / kStepThreads);
+  const uint32_t groups = (a.T + kGroupRows - 1) / kGroupRows;
+  const uint4* src = reinterpret_cast<const uint4*>(a.h_actions_f32);
+  uint4* dst = reinterpret_cast<uint4*>(const_cast<float2*>(a.actions_f32));
+  for (;;) {
+    const uint32_t tk = cta_ticket(a.sm_ctl + kCtlReadTicket, s_slot);
+    if (tk >= groups * Q) break;
+    const int r0 = static_cast<int>(tk / Q) * kGroupRows;
+    const int64_t u = static_cast<int64_t>(tk % Q) * kStepThreads + threadIdx.x;
+    const int rows = a.T - r0 < kGroupRows ? a.T - r0 : kGroupRows;
+    if (u < row_units) {
+      uint4 v[kGroupRows];
+#pragma unroll
+      for (int k = 0; k < kGroupRows; ++k)
+        if (k < rows) v[k] = __ldcs(src + (r0 + k) * row_units + u);
+#pragma unroll
+      for (int k = 0; k < kGroupRows; ++k)
+        if (k < rows) dst[(r0 + k) * row_units + u] = v[k];
+    }
+    __threadfence();
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < rows)
+      atomicAdd(a.row_ready + r0 + threadIdx.x, 1u);
+    if (tk == Q - 1) trace_mark(a.trace, 4, false);
+  }
+  trace_mark(a.trace, 1, false);
+}
+
+// Writer work: blocks of kStepThreads * 8 units (16 KB) of the result
+// stagings in row order.  The CTA re-reads (L2) the units of its block that
+// still hold a -1 until the whole block is final, then stores it to the
+// caller's buffer with full-warp 16-byte stores.
+__device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
+                                             uint32_t* s_slot) {
+  constexpr int kInFlight = 8;
+  const int64_t block = static_cast<int64_t>(kStepThreads) * kInFlight;
+  const int64_t units = static_cast<int64_t>(a.T) * a.n * 4 / 16;
+  const uint32_t blocks = static_cast<uint32_t>((units + block - 1) / block);
+  for (;;) {
+    const uint32_t tk = cta_ticket(a.sm_ctl + kCtlWriteTicket, s_slot);
+    if (tk >= blocks) break;
+    const int64_t base = block * tk;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint4* src = reinterpret_cast<const uint4*>(
+          which ? a.elapsed32_out : a.si_idx_out);
+      uint4* dst =
+          reinterpret_cast<uint4*>(which ? a.h_elapsed32_out : a.h_si_idx_out);
+      if (!dst) continue;
+      uint4 v[kInFlight];
+      unsigned pending = 0u;
+#pragma unroll
+      for (int k = 0; k < kInFlight; ++k)
+        if (base + k * kStepThreads + threadIdx.x < units) pending |= 1u << k;
+      const unsigned mine = pending;
+      for (;;) {
+#pragma unroll
+        for (int k = 0; k < kInFlight; ++k)
+          if (pending >> k & 1u) {
+            v[k] = ld_relaxed_v4(reinterpret_cast<const uint32_t*>(
+                src + base + k * kStepThreads + threadIdx.x));
+            if (unit_final(v[k])) pending &= ~(1u << k);
+          }
+        if (__syncthreads_and(pending == 0u)) break;
+        __nanosleep(300);
+      }
+#pragma unroll
+      for (int k = 0; k < kInFlight; ++k)
+        if (mine >> k & 1u) dst[base + k * kStepThreads + threadIdx.x] = v[k];
+    }
+  }
+  trace_mark(a.trace, 3, false);
+}
+
+// A copy CTA: readers (the first n_readers copy CTAs) read until the action
+// rows are exhausted and then help writing; the others write, and look at
+// the read tickets afterwards (none are left unless no reader ever ran).
+__device__ __noinline__ void stream_copy_role(const StreamCopyArgs a,
+                                              bool reader, uint32_t* s_slot) {
+  trace_mark(a.trace, 0, true);
+  if (reader) {
+    stream_read(a, s_slot);
+    if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
+  } else {
+    if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
+    stream_read(a, s_slot);
+  }
+}
+
+template <int RATE, bool STAGE, bool STREAM = false>
 __global__ void __launch_bounds__(kStepThreads)
     k_rollout_pre(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t s_slot[2];
+  uint32_t block_id = blockIdx.x;
+  if constexpr (STREAM) {
+    // Role by SM: the first `copy_sms` SMs on which a CTA of this launch
+    // starts run only reader / writer CTAs, so that no stepping CTA shares
+    // its SM's load/store path with the PCIe traffic; every other CTA takes
+    // stepping blocks from a ticket counter.  All work is handed out by
+    // tickets and every CTA ends by draining the stepping tickets, so the
+    // launch completes whatever subset of its CTAs is resident.
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      uint32_t* role_p = a.sm_ctl + kCtlRoles + (smid & (kCtlSmSlots - 1));
+      uint32_t r = atomicCAS(role_p, 0u, 1u);  // 0 unset, 1 being decided,
+                                               // 2 copy, 3 stepping
+      if (r == 0u) {
+        const uint32_t k = atomicAdd(a.sm_ctl + kCtlCopySms, 1u);
+        r = k < static_cast<uint32_t>(a.copy_sms) ? 2u : 3u;
+        atomicExch(role_p, r);
+      } else {
+        while (r == 1u) r = *reinterpret_cast<volatile uint32_t*>(role_p);
+      }
+      s_slot[1] = r == 2u ? atomicAdd(a.sm_ctl + kCtlCopyIdx, 1u) : ~0u;
+    }
+    __syncthreads();
+    const uint32_t copy_idx = s_slot[1];
+    if (copy_idx != ~0u)
+      stream_copy_role(
+          StreamCopyArgs{a.h_actions_f32, a.actions_f32, a.si_idx_out,
+                         a.elapsed32_out, a.h_si_idx_out, a.h_elapsed32_out,
+                         a.row_ready, a.sm_ctl, a.st.n_envs, a.n_steps,
+                         a.trace},
+          copy_idx < static_cast<uint32_t>(a.n_readers), s_slot);
+    block_id = cta_ticket(a.sm_ctl + kCtlStepTicket, s_slot);
+    if (block_id >= static_cast<uint32_t>(a.step_ctas)) return;
+  }
   typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
   if constexpr (STAGE) {
     tab = stage_tables(a.lat, smem);
@@ -521,11 +739,11 @@ __global__ void __launch_bounds__(kStepThreads)
   const int lane = threadIdx.x & 31;
   const int j = lane & (G - 1);
   const int gbase = lane - j;
-  const unsigned gmask = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const unsigned gfull = G >= 32 ? 0xffffffffu : ((1u << G) - 1u);
+  const unsigned gmask = gfull << gbase;
   const int64_t n = a.st.n_envs;
-  const int64_t gtid =
-      blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / G;
+  const int64_t n_groups =
+      static_cast<int64_t>(STREAM ? a.step_ctas : gridDim.x) * blockDim.x / G;
   const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const long long dwell = a.dwell_us_scalar;
   const long long step_us = dwell + a.image_duration_us;
@@ -533,6 +751,9 @@ __global__ void __launch_bounds__(kStepThreads)
   const int n_steps = a.n_steps;
   const float md = static_cast<float>(a.max_distance);
 
+  for (;;) {  // STREAM: one pass per stepping ticket; otherwise one pass
+  const int64_t gtid =
+      block_id * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   for (int64_t e = gtid / G; e < n; e += n_groups) {
     // ---- state of the env, replicated in the G lanes of its group ----
     int si = a.st.si_idx[e];
@@ -559,10 +780,42 @@ __global__ void __launch_bounds__(kStepThreads)
     for (int i = 0; i < 3; ++i) geo.cx[i] = geo.cy[i] = 0.f;
     float qfx = 0.f, qfy = 0.f, wfx = 1.f, wfy = 1.f;
 
-    if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
-    if (G + j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
+    if constexpr (!STREAM) {
+      if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
+      if (G + j < n_steps)
+        prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
+    }
+    int arr = STREAM ? 0 : n_steps;  // steps whose actions are in HBM
 
     while (t < n_steps) {
+      if constexpr (STREAM) {
+        // make sure the current step's actions are there (and as much
+        // look-ahead as has arrived)
+        if (arr < n_steps && arr < t + G) {
+          // lane j polls the four rows from (arr & ~3) + 4 j; the ready
+          // prefix grows by the leading run of set flags (up to 4 G rows)
+          do {
+            const int base = arr & ~3;
+            const int idx = base + 4 * j;
+            unsigned bits = 0u;
+            if (idx < n_steps) {
+              const uint4 f = ld_relaxed_v4(a.row_ready + idx);
+              const uint32_t full = a.row_parts;
+              bits = (f.x >= full ? 1u : 0u) | (f.y >= full ? 2u : 0u) |
+                     (f.z >= full ? 4u : 0u) | (f.w >= full ? 8u : 0u);
+            }
+            if (j == 0) bits |= (1u << (arr - base)) - 1u;
+            const unsigned m =
+                (__ballot_sync(gmask, bits == 0xFu) & gmask) >> gbase;
+            const int lead = m == gfull ? G : __ffs(~m) - 1;
+            const unsigned pb =
+                __shfl_sync(gmask, bits, gbase + (lead < G ? lead : 0));
+            const int got =
+                base + 4 * lead + (lead < G ? __ffs(~pb) - 1 : 0);
+            arr = got < n_steps ? got : n_steps;
+          } while (arr <= t);
+        }
+      }
       if (stale) {
         prepass_geometry<RATE>(tab, si, lat, &geo);
         // Will the step that ends the current control re-centre the FOV
@@ -592,7 +845,7 @@ __global__ void __launch_bounds__(kStepThreads)
       // a control whose clock landed exactly on the dwell time has ended
       const bool c_done = cont && elapsed >= dwell;
       const int step = t + j;
-      const bool valid = (first ? j == 0 : true) && step < n_steps;
+      const bool valid = (first ? j == 0 : true) && step < arr;
       bool certain = false;
       uint4 w = make_uint4(0u, 0u, 0u, 0u);  // Philox words of this lane's
                                              // iteration (re-used by phase B)
@@ -605,8 +858,16 @@ __global__ void __launch_bounds__(kStepThreads)
             bx = static_cast<float>(beam0.x - psi.x);
             by = static_cast<float>(beam0.y - psi.y);
           } else {
-            const double2 c = ctl[static_cast<int64_t>(step) * n + e];
-            float px = static_cast<float>(c.x), py = static_cast<float>(c.y);
+            float px, py;
+            if constexpr (STREAM) {
+              const float2 c = a.actions_f32[static_cast<int64_t>(step) * n + e];
+              px = c.x;
+              py = c.y;
+            } else {
+              const double2 c = ctl[static_cast<int64_t>(step) * n + e];
+              px = static_cast<float>(c.x);
+              py = static_cast<float>(c.y);
+            }
             if (relative) {
               px = fminf(fmaxf(px, -1.f), 1.f);
               py = fminf(fmaxf(py, -1.f), 1.f);
@@ -622,8 +883,15 @@ __global__ void __launch_bounds__(kStepThreads)
                                            dwell - (j == 0 ? elapsed : 0));
         }
       }
-      if (step + 2 * G < n_steps)
-        prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
+      if constexpr (STREAM) {
+        // rows are whole 128-byte lines (n % 16 == 0), so a line is only ever
+        // touched once its chunk is complete
+        if (step + 2 * G < arr)
+          prefetch_l1(a.actions_f32 + static_cast<int64_t>(step + 2 * G) * n + e);
+      } else {
+        if (step + 2 * G < n_steps)
+          prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
+      }
       const unsigned valids = (__ballot_sync(gmask, valid) & gmask) >> gbase;
       const unsigned certs = (__ballot_sync(gmask, certain) & gmask) >> gbase;
       const unsigned unsure = valids & ~certs;
@@ -635,9 +903,16 @@ __global__ void __launch_bounds__(kStepThreads)
         if (j < n_done) {
           if (a.si_idx_out)
             a.si_idx_out[static_cast<int64_t>(step) * n + e] = si;
-          if (a.elapsed_us_out)
-            a.elapsed_us_out[static_cast<int64_t>(step) * n + e] =
-                step_us + ((j == 0 && rec) ? a.image_duration_us : 0);
+          const long long el_out =
+              step_us + ((j == 0 && rec) ? a.image_duration_us : 0);
+          if constexpr (STREAM) {
+            if (a.elapsed32_out)
+              a.elapsed32_out[static_cast<int64_t>(step) * n + e] =
+                  static_cast<int32_t>(el_out);
+          } else {
+            if (a.elapsed_us_out)
+              a.elapsed_us_out[static_cast<int64_t>(step) * n + e] = el_out;
+          }
         }
         total += static_cast<long long>(n_done) * step_us +
                  (rec ? a.image_duration_us : 0);
@@ -667,7 +942,13 @@ __global__ void __launch_bounds__(kStepThreads)
                                   __shfl_sync(gmask, w.z, gbase + ju),
                                   __shfl_sync(gmask, w.w, gbase + ju));
       if (it == 0) {
-        const double2 c = ctl[static_cast<int64_t>(t) * n + e];
+        double2 c;
+        if constexpr (STREAM) {
+          const float2 cf = a.actions_f32[static_cast<int64_t>(t) * n + e];
+          c = make_double2(static_cast<double>(cf.x), static_cast<double>(cf.y));
+        } else {
+          c = ctl[static_cast<int64_t>(t) * n + e];
+        }
         double2 pos = c;
         if (relative) {
           if (G >= 4) {
@@ -744,9 +1025,15 @@ __global__ void __launch_bounds__(kStepThreads)
         if (j == 0) {
           if (a.si_idx_out)
             a.si_idx_out[static_cast<int64_t>(t) * n + e] = si;
-          if (a.elapsed_us_out)
-            a.elapsed_us_out[static_cast<int64_t>(t) * n + e] =
-                step_us + (rec ? a.image_duration_us : 0);
+          const long long el_out = step_us + (rec ? a.image_duration_us : 0);
+          if constexpr (STREAM) {
+            if (a.elapsed32_out)
+              a.elapsed32_out[static_cast<int64_t>(t) * n + e] =
+                  static_cast<int32_t>(el_out);
+          } else {
+            if (a.elapsed_us_out)
+              a.elapsed_us_out[static_cast<int64_t>(t) * n + e] = el_out;
+          }
         }
         total += step_us + (rec ? a.image_duration_us : 0);
         if (rec) {
@@ -773,6 +1060,14 @@ __global__ void __launch_bounds__(kStepThreads)
                 static_cast<unsigned long long>(transitions));
       a.st.status[e] = status;
     }
+  }
+  if constexpr (STREAM) {
+    trace_mark(a.trace, 2, false);
+    block_id = cta_ticket(a.sm_ctl + kCtlStepTicket, s_slot);
+    if (block_id >= static_cast<uint32_t>(a.step_ctas)) break;
+  } else {
+    break;
+  }
   }
 }
 
@@ -1292,38 +1587,117 @@ static bool speculation_enabled() {
   return !v || v[0] != '0';
 }
 
-template <int RATE, bool STAGE>
+template <int RATE, bool STAGE, bool STREAM = false>
 static auto rollout_pre_kernel() -> void (*)(const StepArgs) {
   if constexpr (RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR)
-    return k_rollout_pre<RATE, STAGE>;
+    return k_rollout_pre<RATE, STAGE, STREAM>;
   else
     return nullptr;
+}
+
+// What launch_step will run for a call (shared with the streamed host rollout,
+// which needs to know beforehand that k_rollout_pre covers the batch in one
+// wave).
+struct StepPlan {
+  bool staged, walk, spec, pre;
+  int lane_stride, grid;
+};
+
+static StepPlan plan_step(const StepArgs& a, bool rollout, bool has_prepass) {
+  StepPlan p;
+  p.staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
+  p.walk = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads);
+  p.lane_stride = p.walk ? 1 : lane_stride_for(a.st.n_envs);
+  // Rollouts of small batches speculate over the idle lanes (k_rollout_spec);
+  // every lane then does useful work, so the group is twice as wide as the
+  // idle-lane stride (measured at 4096 envs: G = 8: 5.1e9, 16: 6.0e9, 32:
+  // 4.1e9 env-steps/s).
+  p.spec = rollout && !p.walk && p.lane_stride >= 2 && a.n_steps >= 2 &&
+           a.dwell_us_scalar > 0 && speculation_enabled();
+  // ... and on the float32 pre-pass where the rate function has one
+  // (k_rollout_pre; G = 8: 5.3e9, 16: 6.0e9, 32: 4.0e9).
+  p.pre = p.spec && has_prepass && prepass_enabled();
+  if (p.spec && p.lane_stride < 32 && !lane_stride_forced()) p.lane_stride *= 2;
+  p.grid = grid_for(a.st.n_envs * p.lane_stride, p.staged);
+  return p;
+}
+
+// The streamed host rollout: k_rollout_pre<.., STREAM> launched with one full
+// wave of CTAs (resident CTAs per SM x SMs).  `copy_sms` SMs are set aside
+// for the reader / writer CTAs; the others must hold every stepping block at
+// once for the pipeline to flow (the launch still completes if they do not:
+// all work goes by tickets).  Needs action rows that are whole 128-byte
+// lines.  wave = 0 if the call does not qualify.
+struct StreamPlan {
+  int wave, step_ctas, copy_sms, per_sm;
+};
+
+template <int RATE>
+static StreamPlan stream_plan_for(const StepArgs& a, int want_copy_sms) {
+  StreamPlan sp{0, 0, 0, 0};
+  const StepPlan p = plan_step(a, true, true);
+  if (!p.pre || !p.staged || a.st.n_envs % 16 != 0) return sp;
+  const int64_t want =
+      (a.st.n_envs * p.lane_stride + kStepThreads - 1) / kStepThreads;
+  auto kern = rollout_pre_kernel<RATE, true, true>();
+  const size_t smem = static_cast<size_t>(a.lat.n_sites) *
+                      (sizeof(double2) + sizeof(ushort4));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStepThreads,
+                                                    smem) != cudaSuccess ||
+      per_sm < 1) {
+    (void)cudaGetLastError();
+    return sp;
+  }
+  const int64_t step_sms = (want + per_sm - 1) / per_sm;
+  int copy_sms = sm_count() - static_cast<int>(step_sms);
+  if (copy_sms > want_copy_sms) copy_sms = want_copy_sms;
+  if (copy_sms < 1) return sp;
+  sp.wave = per_sm * sm_count();
+  sp.step_ctas = static_cast<int>(want);
+  sp.copy_sms = copy_sms;
+  sp.per_sm = per_sm;
+  return sp;
+}
+
+static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
+                              int want_copy_sms) {
+  if (rc->rate_fn == PD_RATE_SIMPLE)
+    return stream_plan_for<PD_RATE_SIMPLE>(a, want_copy_sms);
+  if (rc->rate_fn == PD_RATE_PRIOR)
+    return stream_plan_for<PD_RATE_PRIOR>(a, want_copy_sms);
+  return StreamPlan{0, 0, 0, 0};
 }
 
 template <int RATE>
 static int launch_step(const StepArgs& a_in, bool rollout,
                        cudaStream_t stream) {
   StepArgs a = a_in;
-  const bool staged = use_staging(a.st.n_envs, rollout ? a.n_steps : 1);
-  const bool walk = walk_kernel(a.st.n_envs >= 4LL * sm_count() * kStepThreads);
-  a.lane_stride = walk ? 1 : lane_stride_for(a.st.n_envs);
+  constexpr bool kHasPrepass =
+      RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR;
+  const StepPlan plan = plan_step(a, rollout, kHasPrepass);
+  const bool staged = plan.staged, walk = plan.walk, spec = plan.spec,
+             pre = plan.pre;
+  const int grid = plan.grid;
+  a.lane_stride = plan.lane_stride;
   a.prepass = prepass_enabled() ? 1 : 0;
   a.walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
   a.walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
   a.walk_controls_per_pass = env_int("PD_WALK_CONTROLS", 4);
-  // Rollouts of small batches speculate over the idle lanes (k_rollout_spec);
-  // every lane then does useful work, so the group is twice as wide as the
-  // idle-lane stride (measured at 4096 envs: G = 8: 5.1e9, 16: 6.0e9, 32:
-  // 4.1e9 env-steps/s).
-  const bool spec = rollout && !walk && a.lane_stride >= 2 && a.n_steps >= 2 &&
-                    a.dwell_us_scalar > 0 && speculation_enabled();
-  // ... and on the float32 pre-pass where the rate function has one
-  // (k_rollout_pre; G = 8: 5.3e9, 16: 6.0e9, 32: 4.0e9).
-  constexpr bool kHasPrepass =
-      RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR;
-  const bool pre = spec && kHasPrepass && a.prepass;
-  if (spec && a.lane_stride < 32 && !lane_stride_forced()) a.lane_stride *= 2;
-  const int grid = grid_for(a.st.n_envs * a.lane_stride, staged);
+  if (a.actions_f32) {
+    // streamed host rollout: the caller went through stream_plan
+    PD_REQUIRE(pre && staged && kHasPrepass,
+               "streamed rollout needs the staged k_rollout_pre");
+    const size_t smem = static_cast<size_t>(a.lat.n_sites) *
+                        (sizeof(double2) + sizeof(ushort4));
+    auto kern = rollout_pre_kernel<RATE, true, true>();
+    PD_CUDA_OK(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(smem)));
+    kern<<<a.stream_wave, kStepThreads, smem, stream>>>(a);
+    PD_CUDA_OK(cudaGetLastError());
+    return PD_OK;
+  }
   if (staged) {
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
@@ -1698,10 +2072,13 @@ namespace pd {
 // Side streams for the host-buffer entry points: the action stream is split
 // into chunks so that the H2D copy of chunk i+1, the kernel of chunk i and
 // the D2H copy of chunk i-1 overlap (PCIe is full duplex).
+constexpr int kMaxStreamRows = 16384;  // steps per streamed call
 struct HostPipeline {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t start = nullptr, copied[16] = {}, stepped[16] = {};
   int device = -1;
+  // streamed rollout: sm_ctl[kCtlWords], row_ready[kMaxStreamRows], trace marks
+  uint32_t* flags = nullptr;
 };
 
 static int host_pipeline(HostPipeline** out) {
@@ -1716,6 +2093,12 @@ static int host_pipeline(HostPipeline** out) {
       PD_CUDA_OK(cudaEventCreateWithFlags(&p.copied[i], cudaEventDisableTiming));
       PD_CUDA_OK(
           cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming));
+    }
+    p.flags = nullptr;
+    if (cudaMalloc(&p.flags, (kCtlWords + kMaxStreamRows + 16) * sizeof(uint32_t)) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      p.flags = nullptr;  // the chunked pipeline is used instead
     }
     p.device = dev;
   }
@@ -1877,6 +2260,115 @@ extern "C" int pd_rollout_actions_host_f32(
     if (w.empty() || w.size() > 16) w.assign(1, 1);
     return w;
   }();
+  // ---- streamed form: one launch that is its own copy pipeline -----------
+  // (k_rollout_pre<.., STREAM>).  Small batches on the prior / simple rates
+  // with pinned, device-visible host buffers; anything else takes the chunked
+  // copy-engine pipeline below.  PD_HOST_STREAMED=0 forces the latter;
+  // PD_HOST_COPY_SMS / PD_HOST_READER_PCT tune the copy CTAs.
+  static const int copy_sms = [] {
+    const char* off = getenv("PD_HOST_STREAMED");
+    if (off && off[0] == '0') return 0;
+    const char* v = getenv("PD_HOST_COPY_SMS");
+    const int c = v ? atoi(v) : 12;
+    return c < 1 ? 1 : (c > 64 ? 64 : c);
+  }();
+  // percentage of the copy CTAs that start as readers
+  static const int reader_pct = [] {
+    const char* v = getenv("PD_HOST_READER_PCT");
+    const int c = v ? atoi(v) : 75;
+    return c < 1 ? 1 : (c > 100 ? 100 : c);
+  }();
+  auto device_visible = [](const void* h) -> void* {
+    if (!h) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  if (copy_sms > 0 && pipe->flags && rc && lat &&
+      static_cast<int64_t>(n_steps) * n >= (1 << 18) && n_steps >= 32 &&
+      n_steps <= pd::kMaxStreamRows && n < (1LL << 31) &&
+      (reinterpret_cast<uintptr_t>(d_actions_f32) & 127) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_si_idx) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_elapsed_us32) & 15) == 0 &&
+      (action_mode == PD_ACTION_DIRECT ||
+       action_mode == PD_ACTION_RELATIVE_TO_SILICON) &&
+      pd::validate_common(lat, st, rc) == PD_OK) {
+    void* hv_act = device_visible(h_actions_xy);
+    void* hv_si = device_visible(h_si_idx);
+    void* hv_el = device_visible(h_elapsed_us32);
+    StepArgs a{};
+    a.lat = *lat;
+    a.st = *st;
+    a.dwell_us_scalar = dwell_us_scalar;
+    a.n_controls = 1;
+    a.n_steps = n_steps;
+    a.action_mode = action_mode;
+    a.max_distance = max_distance_angstroms;
+    a.image_duration_us = image_duration_us;
+    const bool ptrs_ok =
+        hv_act && (reinterpret_cast<uintptr_t>(hv_act) & 15) == 0 &&
+        (!h_si_idx || (hv_si && (reinterpret_cast<uintptr_t>(hv_si) & 15) == 0)) &&
+        (!h_elapsed_us32 ||
+         (hv_el && (reinterpret_cast<uintptr_t>(hv_el) & 15) == 0));
+    const pd::StreamPlan sp =
+        ptrs_ok ? pd::stream_plan(rc, a, copy_sms) : pd::StreamPlan{0, 0, 0, 0};
+    if (sp.wave > 0) {
+      a.actions_f32 = reinterpret_cast<const float2*>(d_actions_f32);
+      a.h_actions_f32 = static_cast<const float2*>(hv_act);
+      a.si_idx_out = h_si_idx ? d_si_idx : nullptr;
+      a.elapsed32_out = h_elapsed_us32 ? d_elapsed_us32 : nullptr;
+      a.h_si_idx_out = static_cast<int32_t*>(hv_si);
+      a.h_elapsed32_out = static_cast<int32_t*>(hv_el);
+      const int flag_rows = (n_steps + 3) & ~3;
+      a.sm_ctl = pipe->flags;
+      a.row_ready = pipe->flags + pd::kCtlWords;
+      a.row_parts = static_cast<uint32_t>((n * 8 / 16 + pd::kStepThreads - 1) /
+                                          pd::kStepThreads);
+      a.copy_sms = sp.copy_sms;
+      const int copy_ctas = sp.copy_sms * sp.per_sm;
+      a.n_readers = (h_si_idx || h_elapsed_us32)
+                        ? (copy_ctas * reader_pct + 99) / 100
+                        : copy_ctas;
+      a.step_ctas = sp.step_ctas;
+      a.stream_wave = sp.wave;
+      static const bool trace = getenv("PD_HOST_TRACE") != nullptr;
+      unsigned long long* d_trace = reinterpret_cast<unsigned long long*>(
+          pipe->flags + pd::kCtlWords + pd::kMaxStreamRows);
+      if (trace) {
+        const unsigned long long init[5] = {~0ull, 0, 0, 0, 0};
+        PD_CUDA_OK(cudaMemcpyAsync(d_trace, init, sizeof(init),
+                                   cudaMemcpyHostToDevice, s));
+        a.trace = d_trace;
+      }
+      const double cpu0 = std::chrono::duration<double, std::micro>(
+          std::chrono::steady_clock::now().time_since_epoch()).count();
+      PD_CUDA_OK(cudaMemsetAsync(
+          pipe->flags, 0, (pd::kCtlWords + flag_rows) * sizeof(uint32_t), s));
+      const size_t out_bytes = static_cast<size_t>(n_steps) * n * sizeof(int32_t);
+      if (h_si_idx) PD_CUDA_OK(cudaMemsetAsync(d_si_idx, 0xFF, out_bytes, s));
+      if (h_elapsed_us32)
+        PD_CUDA_OK(cudaMemsetAsync(d_elapsed_us32, 0xFF, out_bytes, s));
+      rcode = pd::dispatch_step(rc, a, true, s);
+      if (rcode != PD_OK) return rcode;
+      PD_CUDA_OK(cudaStreamSynchronize(s));
+      if (trace) {
+        const double cpu1 = std::chrono::duration<double, std::micro>(
+            std::chrono::steady_clock::now().time_since_epoch()).count();
+        unsigned long long h[5];
+        PD_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr,
+                "pd host trace (us): call %.1f | kernel: first row %.1f, "
+                "readers done %.1f, stepping done %.1f, writers done %.1f\n",
+                cpu1 - cpu0, (h[4] - h[0]) * 1e-3, (h[1] - h[0]) * 1e-3,
+                (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3);
+      }
+      return PD_OK;
+    }
+  }
+
   int total_w = 0;
   for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
   int n_chunks = static_cast<int>(schedule.size());

@@ -510,48 +510,86 @@ def test_rollout_host_pipeline_matches_device_path(eng):
       np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
 
 
+def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
+                   want_elapsed=True):
+  """One pd_rollout_actions_host_f32 call against the device rollout on the
+  widened actions."""
+  import ctypes as C
+  from putting_dune_b200 import _native as nat
+  rng = np.random.default_rng(n + t_steps)
+  if mode == nat.ACTION_RELATIVE_TO_SILICON:
+    acts = rng.uniform(-1.1, 1.1, size=(t_steps, n, 2))
+  else:
+    acts = 0.5 + rng.uniform(-0.06, 0.06, size=(t_steps, n, 2))
+  acts32 = torch.as_tensor(acts.astype(np.float32)).pin_memory()
+  a = eng.EnvBatch(n, seed=52)
+  b = eng.EnvBatch(n, seed=52)
+  a.reset()
+  b.reset()
+  spec = gh.rate_spec(rate_fn)
+  si, el = a.rollout(acts32.double(), 1500000, spec, record=True,
+                     action_mode=mode)
+  dev = b.device
+  d_a32 = torch.empty((t_steps, n, 2), dtype=torch.float32, device=dev)
+  d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
+  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+  d_el32 = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  h_si = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
+  h_el = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
+  P = lambda t: C.c_void_p(t.data_ptr())
+  args = lambda dwell, stream: (
+      C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
+      mode, 1.42, dwell, t_steps, 2000000, P(d_a32), P(d_ctl), P(d_si),
+      P(d_el), P(d_el32), P(h_si), P(h_el) if want_elapsed else None, stream)
+  nat.check(nat.lib.pd_rollout_actions_host_f32(*args(
+      1500000, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))))
+  np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
+  if want_elapsed:
+    np.testing.assert_array_equal(h_el.numpy().astype(np.int64), gh.np_(el))
+  np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+  np.testing.assert_array_equal(gh.np_(b.sim_time_us), gh.np_(a.sim_time_us))
+  np.testing.assert_array_equal(gh.np_(b.n_events), gh.np_(a.n_events))
+  np.testing.assert_array_equal(gh.np_(b.ctrl_count), gh.np_(a.ctrl_count))
+  return args
+
+
 def test_rollout_host_compact_formats(eng):
   """pd_rollout_actions_host_f32: float32 actions in (action_spec dtype,
   action_adapters.py:202-216), int32 elapsed microseconds out; equals the
-  device rollout on the widened actions, for chunked and unchunked sizes."""
-  import ctypes as C
+  device rollout on the widened actions.  (4096, 300), (4112, 100) and
+  (2048, 200) take the streamed form (one launch with reader / writer CTAs;
+  partial row groups, a partial last slice per row), (700, 9) and (4100, 70)
+  the chunked copy-engine pipeline."""
   from putting_dune_b200 import _native as nat
-  for n, t_steps in ((4096, 300), (700, 9)):
-    rng = np.random.default_rng(n)
-    acts32 = torch.as_tensor(
-        rng.uniform(-1.1, 1.1, size=(t_steps, n, 2)).astype(np.float32)
-    ).pin_memory()
-    a = eng.EnvBatch(n, seed=52)
-    b = eng.EnvBatch(n, seed=52)
-    a.reset()
-    b.reset()
-    spec = gh.rate_spec(po.RATE_PRIOR)
-    si, el = a.rollout(acts32.double(), 1500000, spec, record=True,
-                       action_mode=nat.ACTION_RELATIVE_TO_SILICON)
-    dev = b.device
-    d_a32 = torch.empty((t_steps, n, 2), dtype=torch.float32, device=dev)
-    d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
-    d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-    d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
-    d_el32 = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-    h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
-    h_el = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
-    P = lambda t: C.c_void_p(t.data_ptr())
-    nat.check(nat.lib.pd_rollout_actions_host_f32(
-        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
-        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
-        P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el),
-        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-    np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
-    np.testing.assert_array_equal(h_el.numpy().astype(np.int64), gh.np_(el))
-    np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
-    np.testing.assert_array_equal(gh.np_(b.sim_time_us), gh.np_(a.sim_time_us))
+  rel = nat.ACTION_RELATIVE_TO_SILICON
+  args = _host_f32_case(eng, 4096, 300, rel)
+  _host_f32_case(eng, 4112, 100, rel)
+  _host_f32_case(eng, 2048, 200, rel, rate_fn=po.RATE_SIMPLE)
+  _host_f32_case(eng, 4096, 64, nat.ACTION_DIRECT)
+  _host_f32_case(eng, 4096, 96, rel, want_elapsed=False)
+  _host_f32_case(eng, 700, 9, rel)
+  _host_f32_case(eng, 4100, 70, rel)
   with pytest.raises(nat.NativeError, match='int32'):
-    nat.check(nat.lib.pd_rollout_actions_host_f32(
-        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
-        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 3000000000, t_steps, 2000000,
-        P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el),
-        None))
+    nat.check(nat.lib.pd_rollout_actions_host_f32(*args(3000000000, None)))
+
+
+def test_rollout_host_streamed_equals_chunked():
+  """The two forms of pd_rollout_actions_host_f32 (PD_HOST_STREAMED=0 forces
+  the chunked copy-engine pipeline) return the same bytes; the environment
+  variable is read once per process, hence the subprocesses."""
+  import subprocess
+  import sys
+  script = os.path.join(os.path.dirname(__file__), '..', 'profiles',
+                        'prof_e2e.py')
+  digests = []
+  for streamed in ('1', '0'):
+    env = dict(os.environ, PD_HOST_STREAMED=streamed, REPS='3')
+    out = subprocess.run([sys.executable, script], env=env, check=True,
+                         capture_output=True, text=True, timeout=300).stdout
+    assert 'streamed=' + streamed in out
+    digests.append(out.strip().rsplit('digest ', 1)[1])
+  assert digests[0] == digests[1]
 
 
 GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
