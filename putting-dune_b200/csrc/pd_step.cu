@@ -603,9 +603,19 @@ __device__ __forceinline__ void stream_read(const StreamCopyArgs& a,
   const uint32_t groups = (a.T + kGroupRows - 1) / kGroupRows;
   const uint4* src = reinterpret_cast<const uint4*>(a.h_actions_f32);
   uint4* dst = reinterpret_cast<uint4*>(const_cast<float2*>(a.actions_f32));
+  bool first = true;
   for (;;) {
     const uint32_t tk = cta_ticket(a.sm_ctl + kCtlReadTicket, s_slot);
     if (tk >= groups * Q) break;
+    if (first) {
+      // All readers start together; pace their first requests at the link's
+      // rate (~50 GB/s) so that the first groups come over in order instead
+      // of group 0 arriving with everything else that was asked for.
+      first = false;
+      const unsigned group_ns =
+          static_cast<unsigned>(kGroupRows * a.n * 8 / 50);
+      if (tk >= Q) __nanosleep((tk / Q) * group_ns);
+    }
     const int r0 = static_cast<int>(tk / Q) * kGroupRows;
     const int64_t u = static_cast<int64_t>(tk % Q) * kStepThreads + threadIdx.x;
     const int rows = a.T - r0 < kGroupRows ? a.T - r0 : kGroupRows;
