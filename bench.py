@@ -666,9 +666,9 @@ def run_ours(args, cfg):
                 'api': 'pd_rollout_actions_host_f32 (pinned host buffers: '
                        'float32 actions in = the adapters\' action_spec '
                        'dtype, int32 Si site + int32 elapsed us out; one '
-                       'k_rollout_pre<STREAM> launch whose reader / writer '
-                       'CTAs move the rows over PCIe while the other CTAs '
-                       'step)',
+                       'k_rollout_pre<STREAM> launch that follows the H2D '
+                       'copy of the actions while writer CTAs stream the '
+                       'result rows to the host buffers)',
                 'float64_io': {
                     'value': e2e_f64, 'unit': UNIT,
                     'h2d_bytes_per_step': h_ctl[0].numel() * 8,

@@ -314,15 +314,15 @@ int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
  * their contents after the call are unspecified.
  *
  * Small batches on the prior / simple rates (what k_rollout_pre covers in one
- * wave of CTAs; n a multiple of 16, >= 2^18 env-steps, <= 16384 steps) with
- * page-locked, device-visible host buffers (cudaHostAlloc / torch
- * pin_memory) run as ONE launch that is its own copy pipeline: the CTAs of a
- * few SMs read the action rows straight from the host buffer into
- * d_actions_f32 and write finished result rows straight to h_si_idx /
- * h_elapsed_us32, the CTAs of the other SMs step the environments a few rows
- * behind the copy front.  Everything else (and PD_HOST_STREAMED=0) takes the
- * chunked copy-engine pipeline of pd_rollout_actions_host.  Both forms return
- * the same bytes. */
+ * wave of CTAs; n a multiple of 16, >= 2^18 env-steps) with page-locked host
+ * buffers (cudaHostAlloc / torch pin_memory; the result buffers must be
+ * device-visible) run as ONE launch that overlaps both copies: the actions
+ * come in through a single copy-engine copy that the stepping CTAs follow
+ * element by element, the CTAs of a few SMs write finished result rows
+ * straight to h_si_idx / h_elapsed_us32.  An action whose two float32 words
+ * are both 0xFFFFFFFF is only consumed once the copy has ended.  Everything
+ * else (and PD_HOST_STREAMED=0) takes the chunked copy-engine pipeline of
+ * pd_rollout_actions_host.  Both forms return the same bytes. */
 int pd_rollout_actions_host_f32(
     const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
     const float* h_actions_xy, int32_t action_mode,

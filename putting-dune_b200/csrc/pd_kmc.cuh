@@ -548,21 +548,21 @@ struct StepArgs {
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]
   int64_t* elapsed_us_out;    // rollout [T][n]
-  // streamed host rollout (k_rollout_pre<.., STREAM>): a few CTAs of the
-  // launch move the float32 actions from the caller's pinned buffer into HBM
-  // row by row and the int32 results back chunk by chunk, the others step
-  const float2* actions_f32;  // [T][n] device staging (filled by the reader CTAs)
+  // streamed host rollout (k_rollout_pre<.., STREAM>): the float32 actions
+  // are still arriving (one copy-engine H2D copy into a staging pre-filled
+  // with 0xFF) while the launch runs, and the CTAs of a few SMs write the
+  // int32 results back to the caller's pinned buffers row by row
+  const float2* actions_f32;  // [T][n] device staging; an element whose words
+                              // are not both 0xFFFFFFFF has arrived
+  const uint32_t* copy_done;  // set behind the H2D copy: whatever is in the
+                              // staging now is data
   int32_t* elapsed32_out;     // [T][n] int32 microseconds (device staging);
                               // both result stagings start as 0xFF bytes and
                               // a word is final once it is not -1
-  const float2* h_actions_f32;  // [T][n] pinned host memory (device-visible)
   int32_t* h_si_idx_out;      // [T][n] pinned host memory or null
   int32_t* h_elapsed32_out;   // [T][n] pinned host memory or null
-  uint32_t* row_ready;        // [T] slices of the row of step t that are in HBM
-  uint32_t row_parts;         //     ... the row is complete at this count
   uint32_t* sm_ctl;           // role election and work tickets (pd_step.cu)
-  int32_t copy_sms;           // SMs that only run reader / writer CTAs
-  int32_t n_readers;          // copy CTAs that start as readers
+  int32_t copy_sms;           // SMs that only run writer CTAs
   int32_t step_ctas;          // blocks of kStepThreads stepping lanes
   int32_t stream_wave;        // CTAs of the launch (one full wave)
   unsigned long long* trace;  // PD_HOST_TRACE: globaltimer marks, else null

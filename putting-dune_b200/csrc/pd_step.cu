@@ -508,25 +508,27 @@ __global__ void __launch_bounds__(kStepThreads)
 //            outcome.  No shuffles: the lanes stay bit-identical replicas.
 // ~89 % of the controls of the relative_random workload never reach phase B.
 //
-// STREAM (pd_rollout_actions_host_f32): one launch that is its own copy
-// pipeline over PCIe.  CTAs 0..R-1 are readers: reader r pulls the action
-// rows r, r + R, ... from the caller's pinned buffer (device-visible host
-// memory, 16-byte loads, eight in flight per thread) into the HBM staging and
-// raises row_ready[row] behind a fence.  The stepping groups only look at
-// rows whose flag they have seen (`arr` = the ready prefix), so they follow
-// the copy front a few microseconds behind it.  The int32 results go to HBM
-// stagings that the call pre-fills with 0xFF bytes; -1 is neither a site nor
-// an elapsed time and every word is stored exactly once, so a word that is
-// not -1 is final.  CTAs R..R+W-1 are writers: they walk the result rows in
-// order, re-read (from L2) the 16-byte units that still hold a -1 and stream
-// the complete ones to the caller's pinned buffers -- the stepping groups pay
-// no fence and no counter for that.  No copy engine, no side streams, no
-// per-chunk stream hand-offs: the call is the fills, one launch and one
-// synchronize.
+// STREAM (pd_rollout_actions_host_f32): the launch runs WHILE the actions
+// arrive and the results leave over PCIe, instead of between copy-engine
+// chunks.  In: one copy-engine H2D copy of the whole float32 action stream
+// into a staging the call pre-filled with 0xFF bytes; a stepping lane reads
+// its action straight from L2 and treats an element whose two words are both
+// 0xFFFFFFFF (a NaN no adapter produces) as not there yet -- the groups follow
+// the copy front element by element, no flags, no chunks.  (`copy_done`, a
+// word copied behind the stream, settles the pathological case of real data
+// with that bit pattern.)  Out: the int32 results go to HBM stagings that are
+// pre-filled with 0xFF too; -1 is neither a site nor an elapsed time and every
+// word is stored exactly once, so a word that is not -1 is final.  The CTAs
+// of a few SMs are writers: they walk the result rows in order, re-read (from
+// L2) the 16-byte units that still hold a -1 and stream complete 16 KB blocks
+// to the caller's pinned buffers with full-warp stores -- the stepping groups
+// pay no fence and no counter for that.  Measured on this box
+// (profiles/pcie_sm_copy.cu): copy engine in + SM stores out sustain 43.5 GB/s
+// per direction, SM loads in + SM stores out only 35 (the SMs' host reads
+// slow down under write traffic), the copy engines both ways 49.
 // ---------------------------------------------------------------------------
-// Four row flags at once, straight from L2 (no L1 allocation or invalidation:
-// the rows themselves are only ever read after their flag was seen, so L1
-// never holds a stale line of them).
+// Loads that go to L2 (no L1 allocation: a line that was read before its data
+// arrived must not be served from L1 later).
 __device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -534,6 +536,23 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
                : "l"(p)
                : "memory");
   return v;
+}
+__device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];"
+               : "=f"(v.x), "=f"(v.y)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool action_missing(const float2 v) {
+  return __float_as_uint(v.x) == 0xFFFFFFFFu &&
+         __float_as_uint(v.y) == 0xFFFFFFFFu;
 }
 __device__ __forceinline__ bool unit_final(const uint4 v) {
   return v.x != 0xFFFFFFFFu && v.y != 0xFFFFFFFFu && v.z != 0xFFFFFFFFu &&
@@ -546,20 +565,17 @@ enum : int {
   kCtlCopySms = 0,   // SMs that have been given the copy role so far
   kCtlCopyIdx = 1,   // copy CTAs so far
   kCtlStepTicket = 2,
-  kCtlReadTicket = 3,
-  kCtlWriteTicket = 4,
+  kCtlWriteTicket = 3,
+  kCtlCopyDone = 4,  // written by the H2D stream behind the action copy
   kCtlRoles = 8,
   kCtlSmSlots = 1024,
   kCtlWords = kCtlRoles + kCtlSmSlots
 };
-constexpr int kGroupRows = 8;  // action rows a reader work unit spans
 
 struct StreamCopyArgs {
-  const float2* h_actions_f32;
-  const float2* actions_f32;
   const int32_t *si_idx_out, *elapsed32_out;
   int32_t *h_si_idx_out, *h_elapsed32_out;
-  uint32_t *row_ready, *sm_ctl;
+  uint32_t* sm_ctl;
   int64_t n;
   int T;
   unsigned long long* trace;
@@ -570,8 +586,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// trace[0] = first CTA start (min), [1] = last reader end, [2] = last stepping
-// CTA end, [3] = last writer end, [4] = first row ready
+// trace[0] = first CTA start (min), [2] = last stepping CTA end, [3] = last
+// writer end, [4] = first stepping block past its first step
 __device__ __forceinline__ void trace_mark(unsigned long long* trace, int slot,
                                            bool is_min) {
   if (trace && threadIdx.x == 0) {
@@ -589,52 +605,6 @@ __device__ __forceinline__ uint32_t cta_ticket(uint32_t* counter,
   if (threadIdx.x == 0) *s_slot = atomicAdd(counter, 1u);
   __syncthreads();
   return *s_slot;
-}
-
-// Reader work: unit u = (group of kGroupRows rows, slice of kStepThreads
-// 16-byte units), in row order.  One load per row in flight per thread, then
-// the stores, a fence and one count per row; a row is complete at
-// row_parts = slices per row.
-__device__ __forceinline__ void stream_read(const StreamCopyArgs& a,
-                                            uint32_t* s_slot) {
-  const int64_t row_units = a.n * 8 / 16;  // one row of float2 actions
-  const uint32_t Q =
-      static_cast<uint32_t>((row_units + kStepThreads - 1) / kStepThreads);
-  const uint32_t groups = (a.T + kGroupRows - 1) / kGroupRows;
-  const uint4* src = reinterpret_cast<const uint4*>(a.h_actions_f32);
-  uint4* dst = reinterpret_cast<uint4*>(const_cast<float2*>(a.actions_f32));
-  bool first = true;
-  for (;;) {
-    const uint32_t tk = cta_ticket(a.sm_ctl + kCtlReadTicket, s_slot);
-    if (tk >= groups * Q) break;
-    if (first) {
-      // All readers start together; pace their first requests at the link's
-      // rate (~50 GB/s) so that the first groups come over in order instead
-      // of group 0 arriving with everything else that was asked for.
-      first = false;
-      const unsigned group_ns =
-          static_cast<unsigned>(kGroupRows * a.n * 8 / 50);
-      if (tk >= Q) __nanosleep((tk / Q) * group_ns);
-    }
-    const int r0 = static_cast<int>(tk / Q) * kGroupRows;
-    const int64_t u = static_cast<int64_t>(tk % Q) * kStepThreads + threadIdx.x;
-    const int rows = a.T - r0 < kGroupRows ? a.T - r0 : kGroupRows;
-    if (u < row_units) {
-      uint4 v[kGroupRows];
-#pragma unroll
-      for (int k = 0; k < kGroupRows; ++k)
-        if (k < rows) v[k] = __ldcs(src + (r0 + k) * row_units + u);
-#pragma unroll
-      for (int k = 0; k < kGroupRows; ++k)
-        if (k < rows) dst[(r0 + k) * row_units + u] = v[k];
-    }
-    __threadfence();
-    __syncthreads();
-    if (static_cast<int>(threadIdx.x) < rows)
-      atomicAdd(a.row_ready + r0 + threadIdx.x, 1u);
-    if (tk == Q - 1) trace_mark(a.trace, 4, false);
-  }
-  trace_mark(a.trace, 1, false);
 }
 
 // Writer work: blocks of kStepThreads * 8 units (16 KB) of the result
@@ -683,19 +653,11 @@ __device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
   trace_mark(a.trace, 3, false);
 }
 
-// A copy CTA: readers (the first n_readers copy CTAs) read until the action
-// rows are exhausted and then help writing; the others write, and look at
-// the read tickets afterwards (none are left unless no reader ever ran).
+// A copy CTA of the streamed rollout: a writer.
 __device__ __noinline__ void stream_copy_role(const StreamCopyArgs a,
-                                              bool reader, uint32_t* s_slot) {
+                                              uint32_t* s_slot) {
   trace_mark(a.trace, 0, true);
-  if (reader) {
-    stream_read(a, s_slot);
-    if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
-  } else {
-    if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
-    stream_read(a, s_slot);
-  }
+  if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
 }
 
 template <int RATE, bool STAGE, bool STREAM = false>
@@ -706,8 +668,8 @@ __global__ void __launch_bounds__(kStepThreads)
   uint32_t block_id = blockIdx.x;
   if constexpr (STREAM) {
     // Role by SM: the first `copy_sms` SMs on which a CTA of this launch
-    // starts run only reader / writer CTAs, so that no stepping CTA shares
-    // its SM's load/store path with the PCIe traffic; every other CTA takes
+    // starts run only writer CTAs, so that no stepping CTA shares its SM's
+    // load/store path with the PCIe traffic; every other CTA takes
     // stepping blocks from a ticket counter.  All work is handed out by
     // tickets and every CTA ends by draining the stepping tickets, so the
     // launch completes whatever subset of its CTAs is resident.
@@ -730,11 +692,10 @@ __global__ void __launch_bounds__(kStepThreads)
     const uint32_t copy_idx = s_slot[1];
     if (copy_idx != ~0u)
       stream_copy_role(
-          StreamCopyArgs{a.h_actions_f32, a.actions_f32, a.si_idx_out,
-                         a.elapsed32_out, a.h_si_idx_out, a.h_elapsed32_out,
-                         a.row_ready, a.sm_ctl, a.st.n_envs, a.n_steps,
+          StreamCopyArgs{a.si_idx_out, a.elapsed32_out, a.h_si_idx_out,
+                         a.h_elapsed32_out, a.sm_ctl, a.st.n_envs, a.n_steps,
                          a.trace},
-          copy_idx < static_cast<uint32_t>(a.n_readers), s_slot);
+          s_slot);
     block_id = cta_ticket(a.sm_ctl + kCtlStepTicket, s_slot);
     if (block_id >= static_cast<uint32_t>(a.step_ctas)) return;
   }
@@ -795,37 +756,8 @@ __global__ void __launch_bounds__(kStepThreads)
       if (G + j < n_steps)
         prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
     }
-    int arr = STREAM ? 0 : n_steps;  // steps whose actions are in HBM
 
     while (t < n_steps) {
-      if constexpr (STREAM) {
-        // make sure the current step's actions are there (and as much
-        // look-ahead as has arrived)
-        if (arr < n_steps && arr < t + G) {
-          // lane j polls the four rows from (arr & ~3) + 4 j; the ready
-          // prefix grows by the leading run of set flags (up to 4 G rows)
-          do {
-            const int base = arr & ~3;
-            const int idx = base + 4 * j;
-            unsigned bits = 0u;
-            if (idx < n_steps) {
-              const uint4 f = ld_relaxed_v4(a.row_ready + idx);
-              const uint32_t full = a.row_parts;
-              bits = (f.x >= full ? 1u : 0u) | (f.y >= full ? 2u : 0u) |
-                     (f.z >= full ? 4u : 0u) | (f.w >= full ? 8u : 0u);
-            }
-            if (j == 0) bits |= (1u << (arr - base)) - 1u;
-            const unsigned m =
-                (__ballot_sync(gmask, bits == 0xFu) & gmask) >> gbase;
-            const int lead = m == gfull ? G : __ffs(~m) - 1;
-            const unsigned pb =
-                __shfl_sync(gmask, bits, gbase + (lead < G ? lead : 0));
-            const int got =
-                base + 4 * lead + (lead < G ? __ffs(~pb) - 1 : 0);
-            arr = got < n_steps ? got : n_steps;
-          } while (arr <= t);
-        }
-      }
       if (stale) {
         prepass_geometry<RATE>(tab, si, lat, &geo);
         // Will the step that ends the current control re-centre the FOV
@@ -855,7 +787,31 @@ __global__ void __launch_bounds__(kStepThreads)
       // a control whose clock landed exactly on the dwell time has ended
       const bool c_done = cont && elapsed >= dwell;
       const int step = t + j;
-      const bool valid = (first ? j == 0 : true) && step < arr;
+      bool valid = (first ? j == 0 : true) && step < n_steps;
+      float2 act = make_float2(0.f, 0.f);
+      if constexpr (STREAM) {
+        // this lane's action, if it has arrived; the lanes up to the first
+        // one whose action has not are this round's look-ahead
+        if (valid && !(j == 0 && cont)) {
+          const float2* src = a.actions_f32 + static_cast<int64_t>(step) * n + e;
+          act = ld_relaxed_f2(src);
+          if (action_missing(act)) {
+            if (ld_relaxed_u32(a.copy_done))
+              act = ld_relaxed_f2(src);  // the copy has ended: it is data
+            else
+              valid = false;
+          }
+        }
+        const unsigned vm = (__ballot_sync(gmask, valid) & gmask) >> gbase;
+        const unsigned inv = ~vm & gfull;
+        const unsigned keep = inv ? (inv & (0u - inv)) - 1u : gfull;
+        valid = valid && ((keep >> j) & 1u);
+        if (!(vm & keep & 1u)) {
+          // not even the current step is there: the copy front is behind us
+          __nanosleep(100);
+          continue;
+        }
+      }
       bool certain = false;
       uint4 w = make_uint4(0u, 0u, 0u, 0u);  // Philox words of this lane's
                                              // iteration (re-used by phase B)
@@ -870,9 +826,8 @@ __global__ void __launch_bounds__(kStepThreads)
           } else {
             float px, py;
             if constexpr (STREAM) {
-              const float2 c = a.actions_f32[static_cast<int64_t>(step) * n + e];
-              px = c.x;
-              py = c.y;
+              px = act.x;
+              py = act.y;
             } else {
               const double2 c = ctl[static_cast<int64_t>(step) * n + e];
               px = static_cast<float>(c.x);
@@ -893,12 +848,7 @@ __global__ void __launch_bounds__(kStepThreads)
                                            dwell - (j == 0 ? elapsed : 0));
         }
       }
-      if constexpr (STREAM) {
-        // rows are whole 128-byte lines (n % 16 == 0), so a line is only ever
-        // touched once its chunk is complete
-        if (step + 2 * G < arr)
-          prefetch_l1(a.actions_f32 + static_cast<int64_t>(step + 2 * G) * n + e);
-      } else {
+      if constexpr (!STREAM) {
         if (step + 2 * G < n_steps)
           prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
       }
@@ -954,8 +904,10 @@ __global__ void __launch_bounds__(kStepThreads)
       if (it == 0) {
         double2 c;
         if constexpr (STREAM) {
-          const float2 cf = a.actions_f32[static_cast<int64_t>(t) * n + e];
-          c = make_double2(static_cast<double>(cf.x), static_cast<double>(cf.y));
+          // lane ju loaded it in phase A
+          c = make_double2(
+              static_cast<double>(__shfl_sync(gmask, act.x, gbase + ju)),
+              static_cast<double>(__shfl_sync(gmask, act.y, gbase + ju)));
         } else {
           c = ctl[static_cast<int64_t>(t) * n + e];
         }
@@ -2082,13 +2034,13 @@ namespace pd {
 // Side streams for the host-buffer entry points: the action stream is split
 // into chunks so that the H2D copy of chunk i+1, the kernel of chunk i and
 // the D2H copy of chunk i-1 overlap (PCIe is full duplex).
-constexpr int kMaxStreamRows = 16384;  // steps per streamed call
 struct HostPipeline {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   cudaEvent_t start = nullptr, copied[16] = {}, stepped[16] = {};
   int device = -1;
-  // streamed rollout: sm_ctl[kCtlWords], row_ready[kMaxStreamRows], trace marks
+  // streamed rollout: sm_ctl[kCtlWords] + trace marks (device), a pinned 1
   uint32_t* flags = nullptr;
+  uint32_t* h_one = nullptr;
 };
 
 static int host_pipeline(HostPipeline** out) {
@@ -2105,10 +2057,15 @@ static int host_pipeline(HostPipeline** out) {
           cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming));
     }
     p.flags = nullptr;
-    if (cudaMalloc(&p.flags, (kCtlWords + kMaxStreamRows + 16) * sizeof(uint32_t)) !=
-        cudaSuccess) {
+    p.h_one = nullptr;
+    if (cudaMalloc(&p.flags, (kCtlWords + 16) * sizeof(uint32_t)) !=
+            cudaSuccess ||
+        cudaHostAlloc(&p.h_one, sizeof(uint32_t), cudaHostAllocDefault) !=
+            cudaSuccess) {
       (void)cudaGetLastError();
       p.flags = nullptr;  // the chunked pipeline is used instead
+    } else {
+      *p.h_one = 1u;
     }
     p.device = dev;
   }
@@ -2221,6 +2178,26 @@ __global__ void __launch_bounds__(256)
     out[i] = static_cast<int32_t>(in[i]);
 }
 
+// One launch for the fills of the streamed rollout: zeroes the control words
+// and sets the action / result stagings to 0xFF bytes (null or empty ranges
+// are skipped).  16-byte stores.
+struct FillRange {
+  uint4* p;
+  int64_t units;
+  uint32_t word;
+};
+__global__ void __launch_bounds__(256) k_stream_fill(FillRange r0, FillRange r1,
+                                                     FillRange r2, FillRange r3) {
+  const FillRange rs[4] = {r0, r1, r2, r3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 v = make_uint4(rs[k].word, rs[k].word, rs[k].word, rs[k].word);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+         i < rs[k].units; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      rs[k].p[i] = v;
+  }
+}
+
 static int convert_grid(int64_t count) {
   const int64_t want = (count + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -2274,19 +2251,13 @@ extern "C" int pd_rollout_actions_host_f32(
   // (k_rollout_pre<.., STREAM>).  Small batches on the prior / simple rates
   // with pinned, device-visible host buffers; anything else takes the chunked
   // copy-engine pipeline below.  PD_HOST_STREAMED=0 forces the latter;
-  // PD_HOST_COPY_SMS / PD_HOST_READER_PCT tune the copy CTAs.
+  // PD_HOST_COPY_SMS sets the SMs given to the writer CTAs.
   static const int copy_sms = [] {
     const char* off = getenv("PD_HOST_STREAMED");
     if (off && off[0] == '0') return 0;
     const char* v = getenv("PD_HOST_COPY_SMS");
-    const int c = v ? atoi(v) : 12;
+    const int c = v ? atoi(v) : 4;
     return c < 1 ? 1 : (c > 64 ? 64 : c);
-  }();
-  // percentage of the copy CTAs that start as readers
-  static const int reader_pct = [] {
-    const char* v = getenv("PD_HOST_READER_PCT");
-    const int c = v ? atoi(v) : 75;
-    return c < 1 ? 1 : (c > 100 ? 100 : c);
   }();
   auto device_visible = [](const void* h) -> void* {
     if (!h) return nullptr;
@@ -2297,16 +2268,23 @@ extern "C" int pd_rollout_actions_host_f32(
     }
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
   };
+  auto page_locked = [](const void* h) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+  };
   if (copy_sms > 0 && pipe->flags && rc && lat &&
       static_cast<int64_t>(n_steps) * n >= (1 << 18) && n_steps >= 32 &&
-      n_steps <= pd::kMaxStreamRows && n < (1LL << 31) &&
-      (reinterpret_cast<uintptr_t>(d_actions_f32) & 127) == 0 &&
+      n < (1LL << 31) &&
+      (reinterpret_cast<uintptr_t>(d_actions_f32) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_si_idx) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_elapsed_us32) & 15) == 0 &&
       (action_mode == PD_ACTION_DIRECT ||
        action_mode == PD_ACTION_RELATIVE_TO_SILICON) &&
       pd::validate_common(lat, st, rc) == PD_OK) {
-    void* hv_act = device_visible(h_actions_xy);
     void* hv_si = device_visible(h_si_idx);
     void* hv_el = device_visible(h_elapsed_us32);
     StepArgs a{};
@@ -2319,7 +2297,7 @@ extern "C" int pd_rollout_actions_host_f32(
     a.max_distance = max_distance_angstroms;
     a.image_duration_us = image_duration_us;
     const bool ptrs_ok =
-        hv_act && (reinterpret_cast<uintptr_t>(hv_act) & 15) == 0 &&
+        page_locked(h_actions_xy) &&
         (!h_si_idx || (hv_si && (reinterpret_cast<uintptr_t>(hv_si) & 15) == 0)) &&
         (!h_elapsed_us32 ||
          (hv_el && (reinterpret_cast<uintptr_t>(hv_el) & 15) == 0));
@@ -2327,26 +2305,18 @@ extern "C" int pd_rollout_actions_host_f32(
         ptrs_ok ? pd::stream_plan(rc, a, copy_sms) : pd::StreamPlan{0, 0, 0, 0};
     if (sp.wave > 0) {
       a.actions_f32 = reinterpret_cast<const float2*>(d_actions_f32);
-      a.h_actions_f32 = static_cast<const float2*>(hv_act);
       a.si_idx_out = h_si_idx ? d_si_idx : nullptr;
       a.elapsed32_out = h_elapsed_us32 ? d_elapsed_us32 : nullptr;
       a.h_si_idx_out = static_cast<int32_t*>(hv_si);
       a.h_elapsed32_out = static_cast<int32_t*>(hv_el);
-      const int flag_rows = (n_steps + 3) & ~3;
       a.sm_ctl = pipe->flags;
-      a.row_ready = pipe->flags + pd::kCtlWords;
-      a.row_parts = static_cast<uint32_t>((n * 8 / 16 + pd::kStepThreads - 1) /
-                                          pd::kStepThreads);
+      a.copy_done = pipe->flags + pd::kCtlCopyDone;
       a.copy_sms = sp.copy_sms;
-      const int copy_ctas = sp.copy_sms * sp.per_sm;
-      a.n_readers = (h_si_idx || h_elapsed_us32)
-                        ? (copy_ctas * reader_pct + 99) / 100
-                        : copy_ctas;
       a.step_ctas = sp.step_ctas;
       a.stream_wave = sp.wave;
       static const bool trace = getenv("PD_HOST_TRACE") != nullptr;
       unsigned long long* d_trace = reinterpret_cast<unsigned long long*>(
-          pipe->flags + pd::kCtlWords + pd::kMaxStreamRows);
+          pipe->flags + pd::kCtlWords);
       if (trace) {
         const unsigned long long init[5] = {~0ull, 0, 0, 0, 0};
         PD_CUDA_OK(cudaMemcpyAsync(d_trace, init, sizeof(init),
@@ -2355,25 +2325,44 @@ extern "C" int pd_rollout_actions_host_f32(
       }
       const double cpu0 = std::chrono::duration<double, std::micro>(
           std::chrono::steady_clock::now().time_since_epoch()).count();
-      PD_CUDA_OK(cudaMemsetAsync(
-          pipe->flags, 0, (pd::kCtlWords + flag_rows) * sizeof(uint32_t), s));
-      const size_t out_bytes = static_cast<size_t>(n_steps) * n * sizeof(int32_t);
-      if (h_si_idx) PD_CUDA_OK(cudaMemsetAsync(d_si_idx, 0xFF, out_bytes, s));
-      if (h_elapsed_us32)
-        PD_CUDA_OK(cudaMemsetAsync(d_elapsed_us32, 0xFF, out_bytes, s));
+      // fills -> (H2D stream) the action copy and the word behind it
+      //       -> (s) the launch, which follows the copy front
+      const int64_t in_units = static_cast<int64_t>(n_steps) * n * 8 / 16;
+      const int64_t out_units = static_cast<int64_t>(n_steps) * n * 4 / 16;
+      pd::k_stream_fill<<<pd::sm_count() * 4, 256, 0, s>>>(
+          pd::FillRange{reinterpret_cast<uint4*>(pipe->flags),
+                        pd::kCtlWords / 4, 0u},
+          pd::FillRange{reinterpret_cast<uint4*>(d_actions_f32), in_units,
+                        0xFFFFFFFFu},
+          pd::FillRange{reinterpret_cast<uint4*>(d_si_idx),
+                        h_si_idx ? out_units : 0, 0xFFFFFFFFu},
+          pd::FillRange{reinterpret_cast<uint4*>(d_elapsed_us32),
+                        h_elapsed_us32 ? out_units : 0, 0xFFFFFFFFu});
+      PD_CUDA_OK(cudaGetLastError());
+      PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+      PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+      PD_CUDA_OK(cudaMemcpyAsync(d_actions_f32, h_actions_xy,
+                                 static_cast<size_t>(in_units) * 16,
+                                 cudaMemcpyHostToDevice, pipe->h2d));
+      PD_CUDA_OK(cudaMemcpyAsync(pipe->flags + pd::kCtlCopyDone, pipe->h_one,
+                                 sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                 pipe->h2d));
       rcode = pd::dispatch_step(rc, a, true, s);
-      if (rcode != PD_OK) return rcode;
+      if (rcode != PD_OK) {
+        cudaStreamSynchronize(pipe->h2d);
+        return rcode;
+      }
       PD_CUDA_OK(cudaStreamSynchronize(s));
+      PD_CUDA_OK(cudaStreamSynchronize(pipe->h2d));
       if (trace) {
         const double cpu1 = std::chrono::duration<double, std::micro>(
             std::chrono::steady_clock::now().time_since_epoch()).count();
         unsigned long long h[5];
         PD_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr,
-                "pd host trace (us): call %.1f | kernel: first row %.1f, "
-                "readers done %.1f, stepping done %.1f, writers done %.1f\n",
-                cpu1 - cpu0, (h[4] - h[0]) * 1e-3, (h[1] - h[0]) * 1e-3,
-                (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3);
+                "pd host trace (us): call %.1f | kernel: stepping done %.1f, "
+                "writers done %.1f\n",
+                cpu1 - cpu0, (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3);
       }
       return PD_OK;
     }
