@@ -6,7 +6,8 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 src="$here/csrc"
 out="$here/lib"
-obj="$here/build"
+obj="${PD_OBJ_DIR:-$here/build}"
+libname="${PD_LIB_NAME:-libpdune_b200.so}"
 mkdir -p "$out" "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
@@ -30,5 +31,5 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 objs=()
 for f in "${exact[@]}" "${fast[@]}"; do objs+=("$obj/$f.o"); done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libpdune_b200.so" "${objs[@]}" -lcudart
-echo "built $out/libpdune_b200.so"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$libname" "${objs[@]}" -lcudart
+echo "built $out/$libname"

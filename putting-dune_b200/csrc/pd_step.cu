@@ -1484,6 +1484,11 @@ __global__ void __launch_bounds__(kStepThreads)
 // Staging the tables costs ~45 KB of L2 reads per CTA; it pays once every SM
 // holds at least a few full CTAs of envs.
 static bool use_staging(int64_t n_envs, int64_t work_per_env) {
+  static const int forced = [] {  // PD_STAGE=0|1 overrides (A/B timing)
+    const char* v = getenv("PD_STAGE");
+    return v ? (v[0] != '0' ? 1 : 0) : -1;
+  }();
+  if (forced >= 0) return forced == 1;
   return n_envs * work_per_env >= 4LL * sm_count() * kStepThreads;
 }
 
@@ -2276,6 +2281,12 @@ extern "C" int pd_rollout_actions_host_f32(
     }
     return at.type == cudaMemoryTypeHost;
   };
+  auto now_us = [] {
+    return std::chrono::duration<double, std::micro>(
+               std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+  };
+  const double cpu_in = now_us();
   if (copy_sms > 0 && pipe->flags && rc && lat &&
       static_cast<int64_t>(n_steps) * n >= (1 << 18) && n_steps >= 32 &&
       n < (1LL << 31) &&
@@ -2323,8 +2334,7 @@ extern "C" int pd_rollout_actions_host_f32(
                                    cudaMemcpyHostToDevice, s));
         a.trace = d_trace;
       }
-      const double cpu0 = std::chrono::duration<double, std::micro>(
-          std::chrono::steady_clock::now().time_since_epoch()).count();
+      const double cpu0 = now_us();
       // fills -> (H2D stream) the action copy and the word behind it
       //       -> (s) the launch, which follows the copy front
       const int64_t in_units = static_cast<int64_t>(n_steps) * n * 8 / 16;
@@ -2347,16 +2357,22 @@ extern "C" int pd_rollout_actions_host_f32(
       PD_CUDA_OK(cudaMemcpyAsync(pipe->flags + pd::kCtlCopyDone, pipe->h_one,
                                  sizeof(uint32_t), cudaMemcpyHostToDevice,
                                  pipe->h2d));
+      const double cpu_copy = now_us();
       rcode = pd::dispatch_step(rc, a, true, s);
       if (rcode != PD_OK) {
         cudaStreamSynchronize(pipe->h2d);
         return rcode;
       }
+      const double cpu_launch = now_us();
       PD_CUDA_OK(cudaStreamSynchronize(s));
       PD_CUDA_OK(cudaStreamSynchronize(pipe->h2d));
       if (trace) {
-        const double cpu1 = std::chrono::duration<double, std::micro>(
-            std::chrono::steady_clock::now().time_since_epoch()).count();
+        const double cpu1 = now_us();
+        fprintf(stderr,
+                "pd host trace (us): cpu checks %.1f, fill+copy enqueued %.1f, "
+                "launched %.1f, synced %.1f\n",
+                cpu0 - cpu_in, cpu_copy - cpu_in, cpu_launch - cpu_in,
+                cpu1 - cpu_in);
         unsigned long long h[5];
         PD_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr,
