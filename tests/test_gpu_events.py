@@ -511,7 +511,7 @@ def test_rollout_host_pipeline_matches_device_path(eng):
 
 
 def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
-                   want_elapsed=True):
+                   want_elapsed=True, poison=False):
   """One pd_rollout_actions_host_f32 call against the device rollout on the
   widened actions."""
   import ctypes as C
@@ -521,7 +521,14 @@ def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
     acts = rng.uniform(-1.1, 1.1, size=(t_steps, n, 2))
   else:
     acts = 0.5 + rng.uniform(-0.06, 0.06, size=(t_steps, n, 2))
-  acts32 = torch.as_tensor(acts.astype(np.float32)).pin_memory()
+  acts = acts.astype(np.float32)
+  if poison:
+    # actions whose two words are 0xFFFFFFFF (the streamed form's "not yet
+    # arrived" pattern): consumed as data once the copy has ended
+    bits = acts.view(np.uint32)
+    for t, e in ((0, 0), (5, 7), (t_steps // 2, n // 2), (t_steps - 1, n - 1)):
+      bits[t, e, :] = 0xFFFFFFFF
+  acts32 = torch.as_tensor(acts).pin_memory()
   a = eng.EnvBatch(n, seed=52)
   b = eng.EnvBatch(n, seed=52)
   a.reset()
@@ -557,10 +564,11 @@ def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
 def test_rollout_host_compact_formats(eng):
   """pd_rollout_actions_host_f32: float32 actions in (action_spec dtype,
   action_adapters.py:202-216), int32 elapsed microseconds out; equals the
-  device rollout on the widened actions.  (4096, 300), (4112, 100) and
-  (2048, 200) take the streamed form (one launch with reader / writer CTAs;
-  partial row groups, a partial last slice per row), (700, 9) and (4100, 70)
-  the chunked copy-engine pipeline."""
+  device rollout on the widened actions.  (4096, 300), (4112, 100), (2048,
+  200) and the 4096-env cases after them take the streamed form (one launch
+  that follows the H2D copy, writer CTAs; a ragged last result block; actions
+  that look like the "not arrived" pattern), (700, 9) and (4100, 70) the
+  chunked copy-engine pipeline."""
   from putting_dune_b200 import _native as nat
   rel = nat.ACTION_RELATIVE_TO_SILICON
   args = _host_f32_case(eng, 4096, 300, rel)
@@ -568,6 +576,7 @@ def test_rollout_host_compact_formats(eng):
   _host_f32_case(eng, 2048, 200, rel, rate_fn=po.RATE_SIMPLE)
   _host_f32_case(eng, 4096, 64, nat.ACTION_DIRECT)
   _host_f32_case(eng, 4096, 96, rel, want_elapsed=False)
+  _host_f32_case(eng, 4096, 80, rel, poison=True)
   _host_f32_case(eng, 700, 9, rel)
   _host_f32_case(eng, 4100, 70, rel)
   with pytest.raises(nat.NativeError, match='int32'):
