@@ -311,7 +311,9 @@ int pd_rollout_actions_host(const pd_lattice* lat, const pd_state* st,
  * pd_rollout_actions_host on the widened actions.  Staging (device):
  * d_actions_f32 float [n_steps][n][2], d_controls_xy double [n_steps][n][2],
  * d_si_idx int32 / d_elapsed_us int64 / d_elapsed_us32 int32 [n_steps][n];
- * their contents after the call are unspecified.
+ * their contents after the call are unspecified.  All five may be NULL: the
+ * library then keeps its own (grow-only, per calling thread and device) and
+ * prepares them for the next call behind the current one.
  *
  * Small batches on the prior / simple rates (what k_rollout_pre covers in one
  * wave of CTAs; n a multiple of 16, >= 2^18 env-steps) with page-locked host

@@ -40,12 +40,16 @@ P = lambda t: C.c_void_p(t.data_ptr())
 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+# OWNED=1: stagings kept by the library (re-filled behind each call)
+STAGE = ((None,) * 5 if os.environ.get('OWNED') == '1' else
+         (P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32)))
+
+
 def call(i):
   nat.check(nat.lib.pd_rollout_actions_host_f32(
       C.byref(batch.lattice_tables.c), C.byref(batch.c), C.byref(rate.c),
       P(h_a[i % pool]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000,
-      t_steps, 2000000, P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32),
-      P(h_si), P(h_el), stream))
+      t_steps, 2000000, *STAGE, P(h_si), P(h_el), stream))
 
 
 digest = hashlib.sha256()
@@ -64,9 +68,9 @@ for i in range(reps):
   call(i)
   times.append(time.perf_counter() - t0)
 times = np.asarray(times) * 1e3
-print('streamed=%s chunks=%s n=%d steps=%d: median %.4f ms  min %.4f ms  '
+print('streamed=%s owned=%s n=%d steps=%d: median %.4f ms  min %.4f ms  '
       '%.3e env-steps/s  digest %s' % (
           os.environ.get('PD_HOST_STREAMED', '1'),
-          os.environ.get('PD_HOST_STREAM_CHUNKS', 'default'), n, t_steps,
+          os.environ.get('OWNED', '0'), n, t_steps,
           np.median(times), times.min(), n * t_steps / np.median(times) * 1e3,
           digest.hexdigest()[:16]))

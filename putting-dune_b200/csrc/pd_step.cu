@@ -2046,7 +2046,29 @@ struct HostPipeline {
   // streamed rollout: sm_ctl[kCtlWords] + trace marks (device), a pinned 1
   uint32_t* flags = nullptr;
   uint32_t* h_one = nullptr;
+  // Stagings the library keeps when the caller passes none (grow-only):
+  // [0] float32 actions, [1] float64 controls, [2] si, [3] int64 elapsed,
+  // [4] int32 elapsed.  The streamed form re-fills [0], [2], [4] and the
+  // control words behind each call on the d2h stream, so that the next call
+  // finds them ready: `clean_*` = leading 16-byte units known to hold 0xFF.
+  void* own[5] = {};
+  size_t own_bytes[5] = {};
+  int64_t clean_in = 0, clean_out = 0;
+  cudaEvent_t done = nullptr, copied_all = nullptr, cleaned = nullptr;
 };
+
+// Makes sure the library-owned staging `k` holds `bytes` bytes.
+static int own_staging(HostPipeline* p, int k, size_t bytes) {
+  if (p->own_bytes[k] >= bytes) return PD_OK;
+  PD_CUDA_OK(cudaDeviceSynchronize());
+  if (p->own[k]) PD_CUDA_OK(cudaFree(p->own[k]));
+  p->own[k] = nullptr;
+  p->own_bytes[k] = 0;
+  p->clean_in = p->clean_out = 0;
+  PD_CUDA_OK(cudaMalloc(&p->own[k], bytes));
+  p->own_bytes[k] = bytes;
+  return PD_OK;
+}
 
 static int host_pipeline(HostPipeline** out) {
   static thread_local HostPipeline p;
@@ -2061,6 +2083,14 @@ static int host_pipeline(HostPipeline** out) {
       PD_CUDA_OK(
           cudaEventCreateWithFlags(&p.stepped[i], cudaEventDisableTiming));
     }
+    PD_CUDA_OK(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    PD_CUDA_OK(cudaEventCreateWithFlags(&p.copied_all, cudaEventDisableTiming));
+    PD_CUDA_OK(cudaEventCreateWithFlags(&p.cleaned, cudaEventDisableTiming));
+    for (int k = 0; k < 5; ++k) {
+      p.own[k] = nullptr;  // (a previous device's buffers stay with it)
+      p.own_bytes[k] = 0;
+    }
+    p.clean_in = p.clean_out = 0;
     p.flags = nullptr;
     p.h_one = nullptr;
     if (cudaMalloc(&p.flags, (kCtlWords + 16) * sizeof(uint32_t)) !=
@@ -2219,10 +2249,14 @@ extern "C" int pd_rollout_actions_host_f32(
     int32_t* h_si_idx, int32_t* h_elapsed_us32, void* stream) {
   PD_REQUIRE(st != nullptr, "null state");
   PD_REQUIRE(n_steps >= 0, "negative n_steps");
-  PD_REQUIRE(n_steps == 0 || (h_actions_xy && d_actions_f32 && d_controls_xy),
-             "null actions / staging");
-  PD_REQUIRE(!h_si_idx || d_si_idx, "si_idx needs device staging");
-  PD_REQUIRE(!h_elapsed_us32 || (d_elapsed_us && d_elapsed_us32),
+  // all five stagings NULL: the library keeps its own
+  const bool owned = !d_actions_f32 && !d_controls_xy && !d_si_idx &&
+                     !d_elapsed_us && !d_elapsed_us32;
+  PD_REQUIRE(n_steps == 0 || h_actions_xy, "null actions");
+  PD_REQUIRE(owned || n_steps == 0 || (d_actions_f32 && d_controls_xy),
+             "null staging (pass all five stagings or none)");
+  PD_REQUIRE(owned || !h_si_idx || d_si_idx, "si_idx needs device staging");
+  PD_REQUIRE(owned || !h_elapsed_us32 || (d_elapsed_us && d_elapsed_us32),
              "elapsed needs device staging");
   PD_REQUIRE(dwell_us_scalar >= 0 && image_duration_us >= 0 &&
                  dwell_us_scalar + 2 * image_duration_us < (1LL << 31),
@@ -2233,6 +2267,15 @@ extern "C" int pd_rollout_actions_host_f32(
   pd::HostPipeline* pipe = nullptr;
   int rcode = pd::host_pipeline(&pipe);
   if (rcode != PD_OK) return rcode;
+  if (owned) {
+    const size_t items = static_cast<size_t>(n_steps) * n;
+    if ((rcode = pd::own_staging(pipe, 0, items * 8)) != PD_OK) return rcode;
+    if ((rcode = pd::own_staging(pipe, 2, items * 4)) != PD_OK) return rcode;
+    if ((rcode = pd::own_staging(pipe, 4, items * 4)) != PD_OK) return rcode;
+    d_actions_f32 = static_cast<float*>(pipe->own[0]);
+    d_si_idx = static_cast<int32_t*>(pipe->own[2]);
+    d_elapsed_us32 = static_cast<int32_t*>(pipe->own[4]);
+  }
   // With 8 + 8 bytes per env-step the copies no longer bound the call: the
   // kernels of the chunks run back to back and what is left over is the fill
   // (H2D copy of the first chunk) and the drain (kernel + D2H copy of the
@@ -2336,21 +2379,37 @@ extern "C" int pd_rollout_actions_host_f32(
       }
       const double cpu0 = now_us();
       // fills -> (H2D stream) the action copy and the word behind it
-      //       -> (s) the launch, which follows the copy front
+      //       -> (s) the launch, which follows the copy front.
+      // With library-owned stagings the fills were done behind the previous
+      // call (d2h stream), and this call leaves the same behind itself.
       const int64_t in_units = static_cast<int64_t>(n_steps) * n * 8 / 16;
       const int64_t out_units = static_cast<int64_t>(n_steps) * n * 4 / 16;
-      pd::k_stream_fill<<<pd::sm_count() * 4, 256, 0, s>>>(
-          pd::FillRange{reinterpret_cast<uint4*>(pipe->flags),
-                        pd::kCtlWords / 4, 0u},
-          pd::FillRange{reinterpret_cast<uint4*>(d_actions_f32), in_units,
-                        0xFFFFFFFFu},
-          pd::FillRange{reinterpret_cast<uint4*>(d_si_idx),
-                        h_si_idx ? out_units : 0, 0xFFFFFFFFu},
-          pd::FillRange{reinterpret_cast<uint4*>(d_elapsed_us32),
-                        h_elapsed_us32 ? out_units : 0, 0xFFFFFFFFu});
-      PD_CUDA_OK(cudaGetLastError());
-      PD_CUDA_OK(cudaEventRecord(pipe->start, s));
-      PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+      auto fill = [&](cudaStream_t fs) {
+        pd::k_stream_fill<<<pd::sm_count() * 4, 256, 0, fs>>>(
+            pd::FillRange{reinterpret_cast<uint4*>(pipe->flags),
+                          pd::kCtlWords / 4, 0u},
+            pd::FillRange{reinterpret_cast<uint4*>(d_actions_f32), in_units,
+                          0xFFFFFFFFu},
+            pd::FillRange{reinterpret_cast<uint4*>(d_si_idx),
+                          h_si_idx ? out_units : 0, 0xFFFFFFFFu},
+            pd::FillRange{reinterpret_cast<uint4*>(d_elapsed_us32),
+                          h_elapsed_us32 ? out_units : 0, 0xFFFFFFFFu});
+        return cudaGetLastError();
+      };
+      const bool ready = owned && !trace && pipe->clean_in >= in_units &&
+                         pipe->clean_out >= out_units;
+      if (ready) {
+        PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->cleaned, 0));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->cleaned, 0));
+      } else {
+        if (owned) {  // an earlier re-fill may still be running
+          PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+          pipe->clean_in = pipe->clean_out = 0;
+        }
+        PD_CUDA_OK(fill(s));
+        PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+      }
       PD_CUDA_OK(cudaMemcpyAsync(d_actions_f32, h_actions_xy,
                                  static_cast<size_t>(in_units) * 16,
                                  cudaMemcpyHostToDevice, pipe->h2d));
@@ -2361,9 +2420,23 @@ extern "C" int pd_rollout_actions_host_f32(
       rcode = pd::dispatch_step(rc, a, true, s);
       if (rcode != PD_OK) {
         cudaStreamSynchronize(pipe->h2d);
+        pipe->clean_in = pipe->clean_out = 0;
         return rcode;
       }
       const double cpu_launch = now_us();
+      if (owned && !trace) {
+        PD_CUDA_OK(cudaEventRecord(pipe->done, s));
+        PD_CUDA_OK(cudaEventRecord(pipe->copied_all, pipe->h2d));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->done, 0));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->copied_all, 0));
+        PD_CUDA_OK(fill(pipe->d2h));
+        PD_CUDA_OK(cudaEventRecord(pipe->cleaned, pipe->d2h));
+        pipe->clean_in = in_units;
+        pipe->clean_out = (h_si_idx && h_elapsed_us32) ? out_units : 0;
+        // the results are in the caller's buffers once the launch has ended
+        PD_CUDA_OK(cudaEventSynchronize(pipe->done));
+        return PD_OK;
+      }
       PD_CUDA_OK(cudaStreamSynchronize(s));
       PD_CUDA_OK(cudaStreamSynchronize(pipe->h2d));
       if (trace) {
@@ -2384,6 +2457,15 @@ extern "C" int pd_rollout_actions_host_f32(
     }
   }
 
+  if (owned) {
+    const size_t items = static_cast<size_t>(n_steps) * n;
+    PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));  // a re-fill may be running
+    pipe->clean_in = pipe->clean_out = 0;
+    if ((rcode = pd::own_staging(pipe, 1, items * 16)) != PD_OK) return rcode;
+    if ((rcode = pd::own_staging(pipe, 3, items * 8)) != PD_OK) return rcode;
+    d_controls_xy = static_cast<double*>(pipe->own[1]);
+    d_elapsed_us = static_cast<int64_t*>(pipe->own[3]);
+  }
   int total_w = 0;
   for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
   int n_chunks = static_cast<int>(schedule.size());

@@ -511,7 +511,7 @@ def test_rollout_host_pipeline_matches_device_path(eng):
 
 
 def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
-                   want_elapsed=True, poison=False):
+                   want_elapsed=True, poison=False, owned=False):
   """One pd_rollout_actions_host_f32 call against the device rollout on the
   widened actions."""
   import ctypes as C
@@ -545,10 +545,12 @@ def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
   h_si = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
   h_el = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
   P = lambda t: C.c_void_p(t.data_ptr())
+  stage = ((None,) * 5 if owned else
+           (P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32)))
   args = lambda dwell, stream: (
       C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts32),
-      mode, 1.42, dwell, t_steps, 2000000, P(d_a32), P(d_ctl), P(d_si),
-      P(d_el), P(d_el32), P(h_si), P(h_el) if want_elapsed else None, stream)
+      mode, 1.42, dwell, t_steps, 2000000) + stage + (
+          P(h_si), P(h_el) if want_elapsed else None, stream)
   nat.check(nat.lib.pd_rollout_actions_host_f32(*args(
       1500000, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))))
   np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
@@ -577,6 +579,13 @@ def test_rollout_host_compact_formats(eng):
   _host_f32_case(eng, 4096, 64, nat.ACTION_DIRECT)
   _host_f32_case(eng, 4096, 96, rel, want_elapsed=False)
   _host_f32_case(eng, 4096, 80, rel, poison=True)
+  # stagings kept by the library (all five NULL): the first call fills them,
+  # the following ones find them re-filled behind the previous call; sizes
+  # going up and down, one output only, and the chunked form in between
+  for n, t_steps, kw in ((4096, 128, {}), (4096, 128, {}), (2048, 160, {}),
+                         (4096, 200, {}), (4096, 64, {'want_elapsed': False}),
+                         (4096, 128, {}), (700, 9, {}), (4096, 128, {})):
+    _host_f32_case(eng, n, t_steps, rel, owned=True, **kw)
   _host_f32_case(eng, 700, 9, rel)
   _host_f32_case(eng, 4100, 70, rel)
   with pytest.raises(nat.NativeError, match='int32'):
