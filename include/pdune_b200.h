@@ -409,8 +409,8 @@ int pd_tfrecord_trajectories(int32_t n_steps, int64_t n_envs,
 uint32_t pd_crc32c(const void* data, int64_t size);
 
 /* ---- synthetic rate-learning data: rate_learning/data_utils.py:158-303
- *      generate_synthetic_data, PRIOR mode (the NETWORK mode draws a random
- *      Haiku network and is not provided) ------------------------------------ */
+ *      generate_synthetic_data, PRIOR mode (sample_from_prior :237-283) and
+ *      NETWORK mode (sample_network_rates :201-234) ------------------------- */
 /* n samples of split `split` (0 = train, 1 = test; data_utils.py:297-300):
  * next_state int32 [n] (0 = no transition, k + 1 = state k), dt float [n]
  * (the observation window), rates float [n][num_states], context float
@@ -421,6 +421,21 @@ int pd_generate_synthetic_data(uint64_t seed, int32_t split, int64_t n,
                                float time_lo, float time_hi,
                                int32_t* next_state, float* dt, float* rates,
                                float* context, float* position, void* stream);
+
+/* NETWORK mode: x ~ N(0, I) [context_dim + position_dim], rates =
+ * softplus(MLP(x))[:num_states] with the MLP of learn_rates.py:80-99
+ * (batchnorm=False; swish between layers; sizes x -> hidden0 -> hidden1 ->
+ * num_states + 1; the reference uses (1, 64)).  Weights: device float,
+ * row-major [in][out] like Haiku's hk.Linear (the reference draws them with
+ * jax.random; here they are the caller's).  context float [n][context_dim] =
+ * x[:context_dim], position float [n][position_dim] = x[context_dim:]. */
+int pd_generate_synthetic_data_network(
+    uint64_t seed, int32_t split, int64_t n, int32_t num_states,
+    int32_t context_dim, int32_t position_dim, float time_lo, float time_hi,
+    const float* w0, const float* b0, const float* w1, const float* b1,
+    const float* w2, const float* b2, int32_t hidden0, int32_t hidden1,
+    int32_t* next_state, float* dt, float* rates, float* context,
+    float* position, void* stream);
 
 /* ---- whole goal-reaching episodes on the device (BASELINE configs[4]):
  *      eval_lib.py:77-184 evaluate for the greedy_on_neighbor experiment

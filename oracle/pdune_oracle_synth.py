@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE -- NumPy restatement of the PRIOR mode of
-rate_learning/data_utils.py:158-303 generate_synthetic_data.  Only tests/ and
+"""TEST INFRASTRUCTURE -- NumPy restatement of
+rate_learning/data_utils.py:158-303 generate_synthetic_data (PRIOR mode; the
+NETWORK mode at the end of the file).  Only tests/ and
 tests/golden/make_golden.py may import it.
 
 The reference keys its draws by jax.random (absent here, and not
@@ -93,3 +94,57 @@ def generate_synthetic_data(n, seed, split, num_states=3, context_dim=2,
   f32 = lambda v: v.astype(np.float32).astype(np.float64)
   return sample_from_draws(np.stack((zx, zy), -1), f32(a), f32(b),
                            f32(1.0 - c), f32(d), ctx, num_states, time_range)
+
+
+# ---------------------------------------------------------------------------
+# NETWORK mode (data_utils.py:196-234).  The reference draws the MLP's weights
+# and every sample with jax.random and runs a Haiku network (neither is in
+# this container): **parity unpinned**.  The forward pass is po.mlp_forward,
+# the restatement of learn_rates.py:80-99 that the learned-rate path uses.
+# ---------------------------------------------------------------------------
+def network_sample_from_draws(x, u_state, u_time, u_win, weights, num_states,
+                              context_dim, time_range):
+  """data_utils.py:201-234 sample_network_rates given its draws: x [n, D]
+  standard normals, uniforms u_state / u_win in [0, 1), u_time in (0, 1]."""
+  d = x.shape[1]
+  f32 = np.float32
+  params = po.MlpParams(
+      bn_scale=np.ones(d, f32), bn_offset=np.zeros(d, f32),
+      bn_mean=np.zeros(d, f32), bn_var=np.ones(d, f32),
+      w0=weights['w0'], b0=weights['b0'], w1=weights['w1'], b1=weights['b1'],
+      w2=weights['w2'], b2=weights['b2'], batchnorm=False)
+  rates = po.mlp_forward(params, x)[:, :num_states].astype(np.float64)  # :213
+  total = rates.sum(-1)
+  cdf = np.cumsum(rates / total[:, None], axis=-1)
+  state = np.minimum((u_state[:, None] >= cdf).sum(-1), num_states - 1)
+  next_time = -np.log(u_time) / total
+  actual = time_range[0] + u_win * (time_range[1] - time_range[0])
+  next_state = np.where(next_time < actual, state + 1, 0)
+  return {'next_state': next_state.astype(np.int32)[:, None],
+          'dt': actual.astype(f32)[:, None],
+          'rates': rates.astype(f32),
+          'context': x[:, :context_dim].astype(f32),
+          'position': x[:, context_dim:].astype(f32),
+          'cdf_margin': np.abs(u_state[:, None] - cdf).min(-1),
+          'time_margin': np.abs(next_time - actual)}
+
+
+def generate_synthetic_data_network(n, seed, split, weights, num_states=3,
+                                    context_dim=2, position_dim=2,
+                                    time_range=(0.0, 5.0)):
+  """The device kernel's draws (csrc/pd_synth.cu k_synthetic_network) +
+  network_sample_from_draws."""
+  ids = np.arange(n, dtype=np.uint32)
+  d = context_dim + position_dim
+  x = np.zeros((n, d))
+  for k in range(0, d, 2):
+    g0, g1 = _normals(seed, ids, split, 3 + k // 2)
+    x[:, k] = g0
+    if k + 1 < d:
+      x[:, k + 1] = g1
+  a, _ = po.draw_pair(seed, ids, split, 1, STREAM_SYNTH)
+  c, dd = po.draw_pair(seed, ids, split, 2, STREAM_SYNTH)
+  f32 = lambda v: v.astype(np.float32).astype(np.float64)
+  return network_sample_from_draws(
+      x.astype(np.float32), f32(a), f32(1.0 - c), f32(dd), weights,
+      num_states, context_dim, time_range)

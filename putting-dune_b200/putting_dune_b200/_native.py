@@ -167,6 +167,9 @@ _SIGNATURES = {
     'pd_generate_synthetic_data': ([C.c_uint64, _i32, _i64, _i32, _i32,
                                     C.c_float, C.c_float, _p, _p, _p, _p, _p,
                                     _p], C.c_int),
+    'pd_generate_synthetic_data_network': (
+        [C.c_uint64, _i32, _i64, _i32, _i32, _i32, C.c_float, C.c_float,
+         _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p], C.c_int),
 }
 
 for _name, (_args, _res) in _SIGNATURES.items():

@@ -150,3 +150,57 @@ def test_synthetic_rate_learning_data(eng, num_states, context_dim,
   # statistics of the generator: position ~ N(rotations of (0.85, 0), 0.15 I)
   p = gh.np_(train['position']).astype(np.float64)
   assert abs(np.hypot(p[:, 0], p[:, 1]).mean() - 0.93) < 0.05
+
+
+@pytest.mark.parametrize('num_states,context_dim,position_dim,hidden',
+                         [(3, 2, 2, (1, 64)), (5, 3, 2, (8, 32)),
+                          (3, 0, 3, (4, 100))])
+def test_synthetic_rate_learning_data_network(eng, num_states, context_dim,
+                                              position_dim, hidden):
+  """NETWORK mode of generate_synthetic_data (data_utils.py:196-234) against
+  the oracle on the same Philox draws and the same weights (float32 MLP:
+  2e-4 relative; states exact away from decision boundaries) and the
+  properties data_utils_test.py:62-93 checks (shapes, dt inside the window)."""
+  from oracle import pdune_oracle_synth as osy
+  from putting_dune_b200.rate_learning import data_utils
+  n, seed, time_range = 20000, 77, (0.0, 5.0)
+  net = data_utils.init_network(seed, context_dim + position_dim, num_states,
+                                hidden)
+  net['b0'] += 0.1  # the biases take part
+  net['b2'] -= 0.3
+  train, test = data_utils.generate_synthetic_data(
+      num_data=n, data_seed=seed, num_states=num_states,
+      position_dim=position_dim, context_dim=context_dim,
+      actual_time_range=time_range, mode='network', network=net)
+  for split, data in enumerate((train, test)):
+    want = osy.generate_synthetic_data_network(
+        n, seed, split, net, num_states, context_dim, position_dim, time_range)
+    got = {k: gh.np_(v) for k, v in data.items()}
+    assert got['position'].shape == (n, position_dim)
+    assert got['context'].shape == (n, context_dim)
+    assert got['next_state'].shape == (n, 1) and got['dt'].shape == (n, 1)
+    assert got['rates'].shape == (n, num_states)
+    np.testing.assert_allclose(got['position'], want['position'], rtol=2e-5,
+                               atol=5e-5)
+    np.testing.assert_allclose(got['context'], want['context'], rtol=2e-5,
+                               atol=5e-5)
+    np.testing.assert_allclose(got['rates'], want['rates'], rtol=2e-4,
+                               atol=1e-6)
+    np.testing.assert_allclose(got['dt'], want['dt'], rtol=1e-6, atol=1e-7)
+    assert (got['rates'] > 0).all()
+    safe = (want['cdf_margin'] > 1e-4) & (want['time_margin'] > 1e-3)
+    assert safe.mean() > 0.98
+    np.testing.assert_array_equal(got['next_state'][safe],
+                                  want['next_state'][safe])
+    assert ((got['dt'] >= time_range[0]) & (got['dt'] <= time_range[1])).all()
+    assert set(np.unique(got['next_state'])) <= set(range(num_states + 1))
+  # default weights: drawn from the seed, same call twice = same data
+  a, _ = data_utils.generate_synthetic_data(num_data=256, data_seed=5,
+                                            mode='network')
+  b, _ = data_utils.generate_synthetic_data(num_data=256, data_seed=5,
+                                            mode='network')
+  np.testing.assert_array_equal(gh.np_(a['rates']), gh.np_(b['rates']))
+  with pytest.raises(ValueError, match='weights'):
+    data_utils.generate_synthetic_data(
+        num_data=8, data_seed=5, mode='network', num_states=num_states,
+        context_dim=context_dim + 1, position_dim=position_dim, network=net)

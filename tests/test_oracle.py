@@ -459,3 +459,34 @@ def test_synthetic_data_oracle_matches_reference_helpers(golden_dir):
                                rtol=1e-6)
     np.testing.assert_allclose(out['position'], ref[f'pos_rot_{ns}'],
                                rtol=1e-6, atol=1e-7)
+
+
+def test_synthetic_data_oracle_network_mode():
+  """NETWORK mode of the synthetic-data oracle (data_utils.py:201-234) on a
+  network whose output is known in closed form: zero weights, so rates =
+  softplus(b2)[:num_states] for every sample (parity unpinned: the
+  reference's Haiku / jax.random are not in this container)."""
+  from oracle import pdune_oracle_synth as osy
+  f32 = np.float32
+  want = np.array((0.5, 1.0, 2.5), dtype=np.float64)
+  b2 = np.concatenate((np.log(np.expm1(want)), (7.0,))).astype(f32)
+  net = {'w0': np.zeros((4, 1), f32), 'b0': np.zeros(1, f32),
+         'w1': np.zeros((1, 64), f32), 'b1': np.zeros(64, f32),
+         'w2': np.zeros((64, 4), f32), 'b2': b2}
+  n = 50000
+  out = osy.generate_synthetic_data_network(n, 11, 0, net)
+  assert out['rates'].shape == (n, 3) and out['next_state'].shape == (n, 1)
+  assert out['context'].shape == (n, 2) and out['position'].shape == (n, 2)
+  np.testing.assert_allclose(out['rates'], np.tile(want, (n, 1)), rtol=1e-6)
+  # x ~ N(0, I): context / position are its halves
+  x = np.concatenate((out['context'], out['position']), 1).astype(np.float64)
+  assert abs(x.mean()) < 0.02 and abs(x.std() - 1.0) < 0.02
+  # P(transition) = E_T[1 - exp(-total T)], T ~ U(0, 5); branch ratios = rates
+  total = want.sum()
+  p_tr = 1.0 - (1.0 - np.exp(-5.0 * total)) / (5.0 * total)
+  ns = out['next_state'][:, 0]
+  assert abs((ns > 0).mean() - p_tr) < 0.01
+  frac = np.bincount(ns[ns > 0] - 1, minlength=3) / (ns > 0).sum()
+  np.testing.assert_allclose(frac, want / total, atol=0.01)
+  other = osy.generate_synthetic_data_network(n, 11, 1, net)
+  assert not np.array_equal(other['position'], out['position'])
