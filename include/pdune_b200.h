@@ -288,7 +288,9 @@ int pd_rollout_actions(const pd_lattice* lat, const pd_state* st,
 /* Same with HOST buffers: copies the action stream host->device into
  * d_controls_xy, runs the fused steps, copies the per-step Si sites and
  * elapsed times back and synchronises `stream`.  h_si_idx / h_elapsed_us may
- * be NULL (then the matching d_* staging may be NULL too). */
+ * be NULL (then the matching d_* staging may be NULL too).  Small batches with
+ * page-locked buffers take the streamed launch described at
+ * pd_rollout_actions_host_f32 (float64 actions, int64 elapsed). */
 int pd_rollout_host(const pd_lattice* lat, const pd_state* st,
                     const pd_rate_config* rc, const double* h_controls_xy,
                     int64_t dwell_us_scalar, int32_t n_steps,

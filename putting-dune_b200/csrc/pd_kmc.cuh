@@ -561,6 +561,10 @@ struct StepArgs {
                               // a word is final once it is not -1
   int32_t* h_si_idx_out;      // [T][n] pinned host memory or null
   int32_t* h_elapsed32_out;   // [T][n] pinned host memory or null
+  int64_t* h_elapsed64_out;   // stream_mode 2: [T][n] pinned host memory or null
+  int32_t stream_mode;        // 0 off; 1 float32 actions (actions_f32) / int32
+                              // elapsed; 2 float64 actions (controls_xy is the
+                              // staging) / int64 elapsed (elapsed_us_out)
   uint32_t* sm_ctl;           // role election and work tickets (pd_step.cu)
   int32_t copy_sms;           // SMs that only run writer CTAs
   int32_t step_ctas;          // blocks of kStepThreads stepping lanes

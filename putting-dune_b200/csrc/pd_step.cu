@@ -550,11 +550,27 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ double2 ld_relaxed_d2(const double2* p) {
+  double2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ bool action_missing(const double2 v) {
+  return __double_as_longlong(v.x) == -1LL && __double_as_longlong(v.y) == -1LL;
+}
 __device__ __forceinline__ bool action_missing(const float2 v) {
   return __float_as_uint(v.x) == 0xFFFFFFFFu &&
          __float_as_uint(v.y) == 0xFFFFFFFFu;
 }
-__device__ __forceinline__ bool unit_final(const uint4 v) {
+// A 16-byte unit of results is final when none of its elements (int32 words,
+// or int64 as word pairs) is -1 any more.
+__device__ __forceinline__ bool unit_final(const uint4 v, int words) {
+  if (words == 2)
+    return !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu) &&
+           !(v.z == 0xFFFFFFFFu && v.w == 0xFFFFFFFFu);
   return v.x != 0xFFFFFFFFu && v.y != 0xFFFFFFFFu && v.z != 0xFFFFFFFFu &&
          v.w != 0xFFFFFFFFu;
 }
@@ -573,11 +589,14 @@ enum : int {
 };
 
 struct StreamCopyArgs {
-  const int32_t *si_idx_out, *elapsed32_out;
-  int32_t *h_si_idx_out, *h_elapsed32_out;
+  const int32_t* si_idx_out;
+  const void* elapsed_out;  // int32 (el_words 1) or int64 (el_words 2)
+  int32_t* h_si_idx_out;
+  void* h_elapsed_out;
   uint32_t* sm_ctl;
   int64_t n;
   int T;
+  int el_words;
   unsigned long long* trace;
 };
 
@@ -620,19 +639,25 @@ __device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
   for (;;) {
     const uint32_t tk = cta_ticket(a.sm_ctl + kCtlWriteTicket, s_slot);
     if (tk >= blocks) break;
-    const int64_t base = block * tk;
+    // a ticket = the same result elements of both arrays: one block of si
+    // words, el_words blocks of elapsed words
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    for (int part = 0; part < 1 + a.el_words; ++part) {
+      const bool el = part > 0;
       const uint4* src = reinterpret_cast<const uint4*>(
-          which ? a.elapsed32_out : a.si_idx_out);
-      uint4* dst =
-          reinterpret_cast<uint4*>(which ? a.h_elapsed32_out : a.h_si_idx_out);
+          el ? a.elapsed_out : static_cast<const void*>(a.si_idx_out));
+      uint4* dst = reinterpret_cast<uint4*>(
+          el ? a.h_elapsed_out : static_cast<void*>(a.h_si_idx_out));
       if (!dst) continue;
+      const int64_t base =
+          el ? block * (static_cast<int64_t>(tk) * a.el_words + (part - 1))
+             : block * tk;
+      const int64_t lim = el ? units * a.el_words : units;
       uint4 v[kInFlight];
       unsigned pending = 0u;
 #pragma unroll
       for (int k = 0; k < kInFlight; ++k)
-        if (base + k * kStepThreads + threadIdx.x < units) pending |= 1u << k;
+        if (base + k * kStepThreads + threadIdx.x < lim) pending |= 1u << k;
       const unsigned mine = pending;
       for (;;) {
 #pragma unroll
@@ -640,7 +665,7 @@ __device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
           if (pending >> k & 1u) {
             v[k] = ld_relaxed_v4(reinterpret_cast<const uint32_t*>(
                 src + base + k * kStepThreads + threadIdx.x));
-            if (unit_final(v[k])) pending &= ~(1u << k);
+            if (unit_final(v[k], el ? a.el_words : 1)) pending &= ~(1u << k);
           }
         if (__syncthreads_and(pending == 0u)) break;
         __nanosleep(300);
@@ -657,16 +682,16 @@ __device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
 __device__ __noinline__ void stream_copy_role(const StreamCopyArgs a,
                                               uint32_t* s_slot) {
   trace_mark(a.trace, 0, true);
-  if (a.h_si_idx_out || a.h_elapsed32_out) stream_write(a, s_slot);
+  if (a.h_si_idx_out || a.h_elapsed_out) stream_write(a, s_slot);
 }
 
-template <int RATE, bool STAGE, bool STREAM = false>
+template <int RATE, bool STAGE, int STREAM = 0>
 __global__ void __launch_bounds__(kStepThreads)
     k_rollout_pre(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t s_slot[2];
   uint32_t block_id = blockIdx.x;
-  if constexpr (STREAM) {
+  if constexpr (STREAM != 0) {
     // Role by SM: the first `copy_sms` SMs on which a CTA of this launch
     // starts run only writer CTAs, so that no stepping CTA shares its SM's
     // load/store path with the PCIe traffic; every other CTA takes
@@ -692,9 +717,14 @@ __global__ void __launch_bounds__(kStepThreads)
     const uint32_t copy_idx = s_slot[1];
     if (copy_idx != ~0u)
       stream_copy_role(
-          StreamCopyArgs{a.si_idx_out, a.elapsed32_out, a.h_si_idx_out,
-                         a.h_elapsed32_out, a.sm_ctl, a.st.n_envs, a.n_steps,
-                         a.trace},
+          StreamCopyArgs{
+              a.si_idx_out,
+              STREAM == 2 ? static_cast<const void*>(a.elapsed_us_out)
+                          : static_cast<const void*>(a.elapsed32_out),
+              a.h_si_idx_out,
+              STREAM == 2 ? static_cast<void*>(a.h_elapsed64_out)
+                          : static_cast<void*>(a.h_elapsed32_out),
+              a.sm_ctl, a.st.n_envs, a.n_steps, STREAM == 2 ? 2 : 1, a.trace},
           s_slot);
     block_id = cta_ticket(a.sm_ctl + kCtlStepTicket, s_slot);
     if (block_id >= static_cast<uint32_t>(a.step_ctas)) return;
@@ -714,7 +744,7 @@ __global__ void __launch_bounds__(kStepThreads)
   const unsigned gmask = gfull << gbase;
   const int64_t n = a.st.n_envs;
   const int64_t n_groups =
-      static_cast<int64_t>(STREAM ? a.step_ctas : gridDim.x) * blockDim.x / G;
+      static_cast<int64_t>(STREAM != 0 ? a.step_ctas : gridDim.x) * blockDim.x / G;
   const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const long long dwell = a.dwell_us_scalar;
   const long long step_us = dwell + a.image_duration_us;
@@ -751,7 +781,7 @@ __global__ void __launch_bounds__(kStepThreads)
     for (int i = 0; i < 3; ++i) geo.cx[i] = geo.cy[i] = 0.f;
     float qfx = 0.f, qfy = 0.f, wfx = 1.f, wfy = 1.f;
 
-    if constexpr (!STREAM) {
+    if constexpr (STREAM == 0) {
       if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
       if (G + j < n_steps)
         prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
@@ -789,17 +819,32 @@ __global__ void __launch_bounds__(kStepThreads)
       const int step = t + j;
       bool valid = (first ? j == 0 : true) && step < n_steps;
       float2 act = make_float2(0.f, 0.f);
-      if constexpr (STREAM) {
+      double2 actd = make_double2(0.0, 0.0);  // STREAM == 2: the float64 action
+      if constexpr (STREAM != 0) {
         // this lane's action, if it has arrived; the lanes up to the first
         // one whose action has not are this round's look-ahead
         if (valid && !(j == 0 && cont)) {
-          const float2* src = a.actions_f32 + static_cast<int64_t>(step) * n + e;
-          act = ld_relaxed_f2(src);
-          if (action_missing(act)) {
-            if (ld_relaxed_u32(a.copy_done))
-              act = ld_relaxed_f2(src);  // the copy has ended: it is data
-            else
-              valid = false;
+          if constexpr (STREAM == 2) {
+            const double2* src = ctl + static_cast<int64_t>(step) * n + e;
+            actd = ld_relaxed_d2(src);
+            if (action_missing(actd)) {
+              if (ld_relaxed_u32(a.copy_done))
+                actd = ld_relaxed_d2(src);  // the copy has ended: it is data
+              else
+                valid = false;
+            }
+            act = make_float2(static_cast<float>(actd.x),
+                              static_cast<float>(actd.y));
+          } else {
+            const float2* src =
+                a.actions_f32 + static_cast<int64_t>(step) * n + e;
+            act = ld_relaxed_f2(src);
+            if (action_missing(act)) {
+              if (ld_relaxed_u32(a.copy_done))
+                act = ld_relaxed_f2(src);  // the copy has ended: it is data
+              else
+                valid = false;
+            }
           }
         }
         const unsigned vm = (__ballot_sync(gmask, valid) & gmask) >> gbase;
@@ -825,7 +870,7 @@ __global__ void __launch_bounds__(kStepThreads)
             by = static_cast<float>(beam0.y - psi.y);
           } else {
             float px, py;
-            if constexpr (STREAM) {
+            if constexpr (STREAM != 0) {
               px = act.x;
               py = act.y;
             } else {
@@ -848,7 +893,7 @@ __global__ void __launch_bounds__(kStepThreads)
                                            dwell - (j == 0 ? elapsed : 0));
         }
       }
-      if constexpr (!STREAM) {
+      if constexpr (STREAM == 0) {
         if (step + 2 * G < n_steps)
           prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
       }
@@ -865,7 +910,7 @@ __global__ void __launch_bounds__(kStepThreads)
             a.si_idx_out[static_cast<int64_t>(step) * n + e] = si;
           const long long el_out =
               step_us + ((j == 0 && rec) ? a.image_duration_us : 0);
-          if constexpr (STREAM) {
+          if constexpr (STREAM == 1) {
             if (a.elapsed32_out)
               a.elapsed32_out[static_cast<int64_t>(step) * n + e] =
                   static_cast<int32_t>(el_out);
@@ -903,11 +948,15 @@ __global__ void __launch_bounds__(kStepThreads)
                                   __shfl_sync(gmask, w.w, gbase + ju));
       if (it == 0) {
         double2 c;
-        if constexpr (STREAM) {
+        if constexpr (STREAM != 0) {
           // lane ju loaded it in phase A
-          c = make_double2(
-              static_cast<double>(__shfl_sync(gmask, act.x, gbase + ju)),
-              static_cast<double>(__shfl_sync(gmask, act.y, gbase + ju)));
+          if constexpr (STREAM == 2)
+            c = make_double2(shfl_double(gmask, actd.x, gbase + ju),
+                             shfl_double(gmask, actd.y, gbase + ju));
+          else
+            c = make_double2(
+                static_cast<double>(__shfl_sync(gmask, act.x, gbase + ju)),
+                static_cast<double>(__shfl_sync(gmask, act.y, gbase + ju)));
         } else {
           c = ctl[static_cast<int64_t>(t) * n + e];
         }
@@ -988,7 +1037,7 @@ __global__ void __launch_bounds__(kStepThreads)
           if (a.si_idx_out)
             a.si_idx_out[static_cast<int64_t>(t) * n + e] = si;
           const long long el_out = step_us + (rec ? a.image_duration_us : 0);
-          if constexpr (STREAM) {
+          if constexpr (STREAM == 1) {
             if (a.elapsed32_out)
               a.elapsed32_out[static_cast<int64_t>(t) * n + e] =
                   static_cast<int32_t>(el_out);
@@ -1023,7 +1072,7 @@ __global__ void __launch_bounds__(kStepThreads)
       a.st.status[e] = status;
     }
   }
-  if constexpr (STREAM) {
+  if constexpr (STREAM != 0) {
     trace_mark(a.trace, 2, false);
     block_id = cta_ticket(a.sm_ctl + kCtlStepTicket, s_slot);
     if (block_id >= static_cast<uint32_t>(a.step_ctas)) break;
@@ -1554,7 +1603,7 @@ static bool speculation_enabled() {
   return !v || v[0] != '0';
 }
 
-template <int RATE, bool STAGE, bool STREAM = false>
+template <int RATE, bool STAGE, int STREAM = 0>
 static auto rollout_pre_kernel() -> void (*)(const StepArgs) {
   if constexpr (RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR)
     return k_rollout_pre<RATE, STAGE, STREAM>;
@@ -1600,13 +1649,15 @@ struct StreamPlan {
 };
 
 template <int RATE>
-static StreamPlan stream_plan_for(const StepArgs& a, int want_copy_sms) {
+static StreamPlan stream_plan_for(const StepArgs& a, int want_copy_sms,
+                                  int mode) {
   StreamPlan sp{0, 0, 0, 0};
   const StepPlan p = plan_step(a, true, true);
   if (!p.pre || !p.staged || a.st.n_envs % 16 != 0) return sp;
   const int64_t want =
       (a.st.n_envs * p.lane_stride + kStepThreads - 1) / kStepThreads;
-  auto kern = rollout_pre_kernel<RATE, true, true>();
+  auto kern = mode == 2 ? rollout_pre_kernel<RATE, true, 2>()
+                        : rollout_pre_kernel<RATE, true, 1>();
   const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                       (sizeof(double2) + sizeof(ushort4));
   int per_sm = 0;
@@ -1628,11 +1679,11 @@ static StreamPlan stream_plan_for(const StepArgs& a, int want_copy_sms) {
 }
 
 static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
-                              int want_copy_sms) {
+                              int want_copy_sms, int mode) {
   if (rc->rate_fn == PD_RATE_SIMPLE)
-    return stream_plan_for<PD_RATE_SIMPLE>(a, want_copy_sms);
+    return stream_plan_for<PD_RATE_SIMPLE>(a, want_copy_sms, mode);
   if (rc->rate_fn == PD_RATE_PRIOR)
-    return stream_plan_for<PD_RATE_PRIOR>(a, want_copy_sms);
+    return stream_plan_for<PD_RATE_PRIOR>(a, want_copy_sms, mode);
   return StreamPlan{0, 0, 0, 0};
 }
 
@@ -1651,13 +1702,14 @@ static int launch_step(const StepArgs& a_in, bool rollout,
   a.walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
   a.walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
   a.walk_controls_per_pass = env_int("PD_WALK_CONTROLS", 4);
-  if (a.actions_f32) {
+  if (a.stream_mode) {
     // streamed host rollout: the caller went through stream_plan
     PD_REQUIRE(pre && staged && kHasPrepass,
                "streamed rollout needs the staged k_rollout_pre");
     const size_t smem = static_cast<size_t>(a.lat.n_sites) *
                         (sizeof(double2) + sizeof(ushort4));
-    auto kern = rollout_pre_kernel<RATE, true, true>();
+    auto kern = a.stream_mode == 2 ? rollout_pre_kernel<RATE, true, 2>()
+                                   : rollout_pre_kernel<RATE, true, 1>();
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
         static_cast<int>(smem)));
@@ -2109,6 +2161,220 @@ static int host_pipeline(HostPipeline** out) {
 }
 }  // namespace pd
 
+namespace pd {
+// One launch for the fills of the streamed rollout: zeroes the control words
+// and sets the action / result stagings to 0xFF bytes (null or empty ranges
+// are skipped).  16-byte stores.
+struct FillRange {
+  uint4* p;
+  int64_t units;
+  uint32_t word;
+};
+__global__ void __launch_bounds__(256) k_stream_fill(FillRange r0, FillRange r1,
+                                                     FillRange r2, FillRange r3) {
+  const FillRange rs[4] = {r0, r1, r2, r3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 v = make_uint4(rs[k].word, rs[k].word, rs[k].word, rs[k].word);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+         i < rs[k].units; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      rs[k].p[i] = v;
+  }
+}
+
+// ---- streamed form of the host-buffer rollouts: one launch that overlaps
+// both PCIe copies (k_rollout_pre<.., STREAM>; see the comment above that
+// kernel).  mode 1: float32 actions / int32 elapsed; mode 2: float64 actions
+// / int64 elapsed.  Small batches on the prior / simple rates with
+// page-locked host buffers (device-visible result buffers); sets *handled =
+// false when the call does not qualify, and the caller takes the chunked
+// copy-engine pipeline.  PD_HOST_STREAMED=0 forces the latter;
+// PD_HOST_COPY_SMS sets the SMs given to the writer CTAs.
+static int streamed_rollout(HostPipeline* pipe, const pd_lattice* lat,
+                            const pd_state* st, const pd_rate_config* rc,
+                            const void* h_actions, int mode,
+                            int32_t action_mode, double max_distance_angstroms,
+                            int64_t dwell_us_scalar, int32_t n_steps,
+                            int64_t image_duration_us, void* d_actions,
+                            int32_t* d_si_idx, void* d_elapsed,
+                            int32_t* h_si_idx, void* h_elapsed, bool owned,
+                            cudaStream_t s, bool* handled) {
+  *handled = false;
+  const int64_t n = st->n_envs;
+  const int in_bytes = mode == 2 ? 16 : 8;   // per env-step
+  const int el_bytes = mode == 2 ? 8 : 4;
+  int rcode = PD_OK;
+  static const int copy_sms = [] {
+    const char* off = getenv("PD_HOST_STREAMED");
+    if (off && off[0] == '0') return 0;
+    const char* v = getenv("PD_HOST_COPY_SMS");
+    const int c = v ? atoi(v) : 4;
+    return c < 1 ? 1 : (c > 64 ? 64 : c);
+  }();
+  auto device_visible = [](const void* h) -> void* {
+    if (!h) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  auto page_locked = [](const void* h) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+  };
+  auto now_us = [] {
+    return std::chrono::duration<double, std::micro>(
+               std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+  };
+  const double cpu_in = now_us();
+  if (copy_sms > 0 && pipe->flags && rc && lat &&
+      static_cast<int64_t>(n_steps) * n >= (1 << 18) && n_steps >= 32 &&
+      n < (1LL << 31) &&
+      (reinterpret_cast<uintptr_t>(d_actions) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_si_idx) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_elapsed) & 15) == 0 &&
+      (action_mode == PD_ACTION_DIRECT ||
+       action_mode == PD_ACTION_RELATIVE_TO_SILICON) &&
+      validate_common(lat, st, rc) == PD_OK) {
+    void* hv_si = device_visible(h_si_idx);
+    void* hv_el = device_visible(h_elapsed);
+    StepArgs a{};
+    a.lat = *lat;
+    a.st = *st;
+    a.dwell_us_scalar = dwell_us_scalar;
+    a.n_controls = 1;
+    a.n_steps = n_steps;
+    a.action_mode = action_mode;
+    a.max_distance = max_distance_angstroms;
+    a.image_duration_us = image_duration_us;
+    const bool ptrs_ok =
+        page_locked(h_actions) &&
+        (!h_si_idx || (hv_si && (reinterpret_cast<uintptr_t>(hv_si) & 15) == 0)) &&
+        (!h_elapsed ||
+         (hv_el && (reinterpret_cast<uintptr_t>(hv_el) & 15) == 0));
+    const StreamPlan sp =
+        ptrs_ok ? stream_plan(rc, a, copy_sms, mode) : StreamPlan{0, 0, 0, 0};
+    if (sp.wave > 0) {
+      a.stream_mode = mode;
+      a.si_idx_out = h_si_idx ? d_si_idx : nullptr;
+      a.h_si_idx_out = static_cast<int32_t*>(hv_si);
+      if (mode == 2) {
+        a.controls_xy = static_cast<const double*>(d_actions);
+        a.elapsed_us_out = h_elapsed ? static_cast<int64_t*>(d_elapsed) : nullptr;
+        a.h_elapsed64_out = static_cast<int64_t*>(hv_el);
+      } else {
+        a.actions_f32 = static_cast<const float2*>(d_actions);
+        a.elapsed32_out = h_elapsed ? static_cast<int32_t*>(d_elapsed) : nullptr;
+        a.h_elapsed32_out = static_cast<int32_t*>(hv_el);
+      }
+      a.sm_ctl = pipe->flags;
+      a.copy_done = pipe->flags + kCtlCopyDone;
+      a.copy_sms = sp.copy_sms;
+      a.step_ctas = sp.step_ctas;
+      a.stream_wave = sp.wave;
+      static const bool trace = getenv("PD_HOST_TRACE") != nullptr;
+      unsigned long long* d_trace = reinterpret_cast<unsigned long long*>(
+          pipe->flags + kCtlWords);
+      if (trace) {
+        const unsigned long long init[5] = {~0ull, 0, 0, 0, 0};
+        PD_CUDA_OK(cudaMemcpyAsync(d_trace, init, sizeof(init),
+                                   cudaMemcpyHostToDevice, s));
+        a.trace = d_trace;
+      }
+      const double cpu0 = now_us();
+      // fills -> (H2D stream) the action copy and the word behind it
+      //       -> (s) the launch, which follows the copy front.
+      // With library-owned stagings the fills were done behind the previous
+      // call (d2h stream), and this call leaves the same behind itself.
+      const int64_t in_units = static_cast<int64_t>(n_steps) * n * in_bytes / 16;
+      const int64_t out_units = static_cast<int64_t>(n_steps) * n * 4 / 16;
+      const int64_t el_units = static_cast<int64_t>(n_steps) * n * el_bytes / 16;
+      auto fill = [&](cudaStream_t fs) {
+        k_stream_fill<<<sm_count() * 4, 256, 0, fs>>>(
+            FillRange{reinterpret_cast<uint4*>(pipe->flags),
+                          kCtlWords / 4, 0u},
+            FillRange{reinterpret_cast<uint4*>(d_actions), in_units,
+                      0xFFFFFFFFu},
+            FillRange{reinterpret_cast<uint4*>(d_si_idx),
+                      h_si_idx ? out_units : 0, 0xFFFFFFFFu},
+            FillRange{reinterpret_cast<uint4*>(d_elapsed),
+                      h_elapsed ? el_units : 0, 0xFFFFFFFFu});
+        return cudaGetLastError();
+      };
+      const bool ready = owned && !trace && pipe->clean_in >= in_units &&
+                         pipe->clean_out >= out_units;
+      if (ready) {
+        PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->cleaned, 0));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->cleaned, 0));
+      } else {
+        if (owned) {  // an earlier re-fill may still be running
+          PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+          pipe->clean_in = pipe->clean_out = 0;
+        }
+        PD_CUDA_OK(fill(s));
+        PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+      }
+      PD_CUDA_OK(cudaMemcpyAsync(d_actions, h_actions,
+                                 static_cast<size_t>(in_units) * 16,
+                                 cudaMemcpyHostToDevice, pipe->h2d));
+      PD_CUDA_OK(cudaMemcpyAsync(pipe->flags + kCtlCopyDone, pipe->h_one,
+                                 sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                 pipe->h2d));
+      const double cpu_copy = now_us();
+      rcode = dispatch_step(rc, a, true, s);
+      if (rcode != PD_OK) {
+        cudaStreamSynchronize(pipe->h2d);
+        pipe->clean_in = pipe->clean_out = 0;
+        return rcode;
+      }
+      const double cpu_launch = now_us();
+      if (owned && !trace) {
+        PD_CUDA_OK(cudaEventRecord(pipe->done, s));
+        PD_CUDA_OK(cudaEventRecord(pipe->copied_all, pipe->h2d));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->done, 0));
+        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->copied_all, 0));
+        PD_CUDA_OK(fill(pipe->d2h));
+        PD_CUDA_OK(cudaEventRecord(pipe->cleaned, pipe->d2h));
+        pipe->clean_in = in_units;
+        pipe->clean_out = (h_si_idx && h_elapsed) ? out_units : 0;
+        // the results are in the caller's buffers once the launch has ended
+        PD_CUDA_OK(cudaEventSynchronize(pipe->done));
+        *handled = true;
+        return PD_OK;
+      }
+      PD_CUDA_OK(cudaStreamSynchronize(s));
+      PD_CUDA_OK(cudaStreamSynchronize(pipe->h2d));
+      if (trace) {
+        const double cpu1 = now_us();
+        fprintf(stderr,
+                "pd host trace (us): cpu checks %.1f, fill+copy enqueued %.1f, "
+                "launched %.1f, synced %.1f\n",
+                cpu0 - cpu_in, cpu_copy - cpu_in, cpu_launch - cpu_in,
+                cpu1 - cpu_in);
+        unsigned long long h[5];
+        PD_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr,
+                "pd host trace (us): call %.1f | kernel: stepping done %.1f, "
+                "writers done %.1f\n",
+                cpu1 - cpu0, (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3);
+      }
+      *handled = true;
+      return PD_OK;
+    }
+  }
+
+  return PD_OK;
+}
+}  // namespace pd
+
 extern "C" int pd_rollout_actions_host(
     const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
     const double* h_controls_xy, int32_t action_mode,
@@ -2128,6 +2394,18 @@ extern "C" int pd_rollout_actions_host(
   pd::HostPipeline* pipe = nullptr;
   int rcode = pd::host_pipeline(&pipe);
   if (rcode != PD_OK) return rcode;
+  {
+    // small batches: one launch that follows the H2D copy and writes the
+    // results back itself (float64 actions, int64 elapsed)
+    bool handled = false;
+    rcode = pd::streamed_rollout(
+        pipe, lat, st, rc, h_controls_xy, 2, action_mode,
+        max_distance_angstroms, dwell_us_scalar, n_steps, image_duration_us,
+        d_controls_xy, d_si_idx, d_elapsed_us, h_si_idx, h_elapsed_us, false, s,
+        &handled);
+    if (rcode != PD_OK || handled) return rcode;
+  }
+  // Otherwise: copy-engine chunks.
   // The call is bound by the H2D copy of the actions (16 B per env-step over
   // PCIe, 47 GB/s with both directions busy: profiles/prof_pcie.py); the
   // kernel and the D2H copy of chunk i hide behind the H2D copy of chunk i+1,
@@ -2213,26 +2491,6 @@ __global__ void __launch_bounds__(256)
     out[i] = static_cast<int32_t>(in[i]);
 }
 
-// One launch for the fills of the streamed rollout: zeroes the control words
-// and sets the action / result stagings to 0xFF bytes (null or empty ranges
-// are skipped).  16-byte stores.
-struct FillRange {
-  uint4* p;
-  int64_t units;
-  uint32_t word;
-};
-__global__ void __launch_bounds__(256) k_stream_fill(FillRange r0, FillRange r1,
-                                                     FillRange r2, FillRange r3) {
-  const FillRange rs[4] = {r0, r1, r2, r3};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint4 v = make_uint4(rs[k].word, rs[k].word, rs[k].word, rs[k].word);
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-         i < rs[k].units; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-      rs[k].p[i] = v;
-  }
-}
-
 static int convert_grid(int64_t count) {
   const int64_t want = (count + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -2295,166 +2553,13 @@ extern "C" int pd_rollout_actions_host_f32(
     if (w.empty() || w.size() > 16) w.assign(1, 1);
     return w;
   }();
-  // ---- streamed form: one launch that is its own copy pipeline -----------
-  // (k_rollout_pre<.., STREAM>).  Small batches on the prior / simple rates
-  // with pinned, device-visible host buffers; anything else takes the chunked
-  // copy-engine pipeline below.  PD_HOST_STREAMED=0 forces the latter;
-  // PD_HOST_COPY_SMS sets the SMs given to the writer CTAs.
-  static const int copy_sms = [] {
-    const char* off = getenv("PD_HOST_STREAMED");
-    if (off && off[0] == '0') return 0;
-    const char* v = getenv("PD_HOST_COPY_SMS");
-    const int c = v ? atoi(v) : 4;
-    return c < 1 ? 1 : (c > 64 ? 64 : c);
-  }();
-  auto device_visible = [](const void* h) -> void* {
-    if (!h) return nullptr;
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return nullptr;
-    }
-    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
-  };
-  auto page_locked = [](const void* h) {
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return false;
-    }
-    return at.type == cudaMemoryTypeHost;
-  };
-  auto now_us = [] {
-    return std::chrono::duration<double, std::micro>(
-               std::chrono::steady_clock::now().time_since_epoch())
-        .count();
-  };
-  const double cpu_in = now_us();
-  if (copy_sms > 0 && pipe->flags && rc && lat &&
-      static_cast<int64_t>(n_steps) * n >= (1 << 18) && n_steps >= 32 &&
-      n < (1LL << 31) &&
-      (reinterpret_cast<uintptr_t>(d_actions_f32) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(d_si_idx) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(d_elapsed_us32) & 15) == 0 &&
-      (action_mode == PD_ACTION_DIRECT ||
-       action_mode == PD_ACTION_RELATIVE_TO_SILICON) &&
-      pd::validate_common(lat, st, rc) == PD_OK) {
-    void* hv_si = device_visible(h_si_idx);
-    void* hv_el = device_visible(h_elapsed_us32);
-    StepArgs a{};
-    a.lat = *lat;
-    a.st = *st;
-    a.dwell_us_scalar = dwell_us_scalar;
-    a.n_controls = 1;
-    a.n_steps = n_steps;
-    a.action_mode = action_mode;
-    a.max_distance = max_distance_angstroms;
-    a.image_duration_us = image_duration_us;
-    const bool ptrs_ok =
-        page_locked(h_actions_xy) &&
-        (!h_si_idx || (hv_si && (reinterpret_cast<uintptr_t>(hv_si) & 15) == 0)) &&
-        (!h_elapsed_us32 ||
-         (hv_el && (reinterpret_cast<uintptr_t>(hv_el) & 15) == 0));
-    const pd::StreamPlan sp =
-        ptrs_ok ? pd::stream_plan(rc, a, copy_sms) : pd::StreamPlan{0, 0, 0, 0};
-    if (sp.wave > 0) {
-      a.actions_f32 = reinterpret_cast<const float2*>(d_actions_f32);
-      a.si_idx_out = h_si_idx ? d_si_idx : nullptr;
-      a.elapsed32_out = h_elapsed_us32 ? d_elapsed_us32 : nullptr;
-      a.h_si_idx_out = static_cast<int32_t*>(hv_si);
-      a.h_elapsed32_out = static_cast<int32_t*>(hv_el);
-      a.sm_ctl = pipe->flags;
-      a.copy_done = pipe->flags + pd::kCtlCopyDone;
-      a.copy_sms = sp.copy_sms;
-      a.step_ctas = sp.step_ctas;
-      a.stream_wave = sp.wave;
-      static const bool trace = getenv("PD_HOST_TRACE") != nullptr;
-      unsigned long long* d_trace = reinterpret_cast<unsigned long long*>(
-          pipe->flags + pd::kCtlWords);
-      if (trace) {
-        const unsigned long long init[5] = {~0ull, 0, 0, 0, 0};
-        PD_CUDA_OK(cudaMemcpyAsync(d_trace, init, sizeof(init),
-                                   cudaMemcpyHostToDevice, s));
-        a.trace = d_trace;
-      }
-      const double cpu0 = now_us();
-      // fills -> (H2D stream) the action copy and the word behind it
-      //       -> (s) the launch, which follows the copy front.
-      // With library-owned stagings the fills were done behind the previous
-      // call (d2h stream), and this call leaves the same behind itself.
-      const int64_t in_units = static_cast<int64_t>(n_steps) * n * 8 / 16;
-      const int64_t out_units = static_cast<int64_t>(n_steps) * n * 4 / 16;
-      auto fill = [&](cudaStream_t fs) {
-        pd::k_stream_fill<<<pd::sm_count() * 4, 256, 0, fs>>>(
-            pd::FillRange{reinterpret_cast<uint4*>(pipe->flags),
-                          pd::kCtlWords / 4, 0u},
-            pd::FillRange{reinterpret_cast<uint4*>(d_actions_f32), in_units,
-                          0xFFFFFFFFu},
-            pd::FillRange{reinterpret_cast<uint4*>(d_si_idx),
-                          h_si_idx ? out_units : 0, 0xFFFFFFFFu},
-            pd::FillRange{reinterpret_cast<uint4*>(d_elapsed_us32),
-                          h_elapsed_us32 ? out_units : 0, 0xFFFFFFFFu});
-        return cudaGetLastError();
-      };
-      const bool ready = owned && !trace && pipe->clean_in >= in_units &&
-                         pipe->clean_out >= out_units;
-      if (ready) {
-        PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->cleaned, 0));
-        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->cleaned, 0));
-      } else {
-        if (owned) {  // an earlier re-fill may still be running
-          PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
-          pipe->clean_in = pipe->clean_out = 0;
-        }
-        PD_CUDA_OK(fill(s));
-        PD_CUDA_OK(cudaEventRecord(pipe->start, s));
-        PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
-      }
-      PD_CUDA_OK(cudaMemcpyAsync(d_actions_f32, h_actions_xy,
-                                 static_cast<size_t>(in_units) * 16,
-                                 cudaMemcpyHostToDevice, pipe->h2d));
-      PD_CUDA_OK(cudaMemcpyAsync(pipe->flags + pd::kCtlCopyDone, pipe->h_one,
-                                 sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                 pipe->h2d));
-      const double cpu_copy = now_us();
-      rcode = pd::dispatch_step(rc, a, true, s);
-      if (rcode != PD_OK) {
-        cudaStreamSynchronize(pipe->h2d);
-        pipe->clean_in = pipe->clean_out = 0;
-        return rcode;
-      }
-      const double cpu_launch = now_us();
-      if (owned && !trace) {
-        PD_CUDA_OK(cudaEventRecord(pipe->done, s));
-        PD_CUDA_OK(cudaEventRecord(pipe->copied_all, pipe->h2d));
-        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->done, 0));
-        PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->copied_all, 0));
-        PD_CUDA_OK(fill(pipe->d2h));
-        PD_CUDA_OK(cudaEventRecord(pipe->cleaned, pipe->d2h));
-        pipe->clean_in = in_units;
-        pipe->clean_out = (h_si_idx && h_elapsed_us32) ? out_units : 0;
-        // the results are in the caller's buffers once the launch has ended
-        PD_CUDA_OK(cudaEventSynchronize(pipe->done));
-        return PD_OK;
-      }
-      PD_CUDA_OK(cudaStreamSynchronize(s));
-      PD_CUDA_OK(cudaStreamSynchronize(pipe->h2d));
-      if (trace) {
-        const double cpu1 = now_us();
-        fprintf(stderr,
-                "pd host trace (us): cpu checks %.1f, fill+copy enqueued %.1f, "
-                "launched %.1f, synced %.1f\n",
-                cpu0 - cpu_in, cpu_copy - cpu_in, cpu_launch - cpu_in,
-                cpu1 - cpu_in);
-        unsigned long long h[5];
-        PD_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-        fprintf(stderr,
-                "pd host trace (us): call %.1f | kernel: stepping done %.1f, "
-                "writers done %.1f\n",
-                cpu1 - cpu0, (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3);
-      }
-      return PD_OK;
-    }
+  {
+    bool handled = false;
+    rcode = pd::streamed_rollout(
+        pipe, lat, st, rc, h_actions_xy, 1, action_mode, max_distance_angstroms,
+        dwell_us_scalar, n_steps, image_duration_us, d_actions_f32, d_si_idx,
+        d_elapsed_us32, h_si_idx, h_elapsed_us32, owned, s, &handled);
+    if (rcode != PD_OK || handled) return rcode;
   }
 
   if (owned) {

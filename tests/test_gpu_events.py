@@ -476,38 +476,51 @@ def test_prepass_equals_exact(eng, monkeypatch):
 
 
 def test_rollout_host_pipeline_matches_device_path(eng):
-  """pd_rollout_actions_host (chunked H2D / step / D2H overlap) returns what
-  the device-resident rollout computes."""
+  """pd_rollout_actions_host (float64 actions, int64 elapsed) returns what the
+  device-resident rollout computes: (4096, 37) through the chunked H2D / step
+  / D2H pipeline, (4096, 100) and (2048, 130) through the streamed launch
+  (k_rollout_pre<STREAM = 2>), the last with actions that carry the
+  "not arrived" bit pattern."""
   import ctypes as C
   from putting_dune_b200 import _native as nat
-  n, t_steps, seed = 4096, 37, 51
-  rng = np.random.default_rng(9)
-  acts = torch.as_tensor(rng.uniform(-1, 1, size=(t_steps, n, 2))).pin_memory()
-  a = eng.EnvBatch(n, seed=seed)
-  b = eng.EnvBatch(n, seed=seed)
-  a.reset()
-  b.reset()
-  spec = gh.rate_spec(po.RATE_PRIOR)
-  si, el = a.rollout(acts, 1500000, spec, record=True,
-                     action_mode=nat.ACTION_RELATIVE_TO_SILICON)
-  dev = b.device
-  d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
-  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
-  h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
-  h_el = torch.empty((t_steps, n), dtype=torch.int64).pin_memory()
-  P = lambda t: C.c_void_p(t.data_ptr())
-  for _ in range(2):  # second call re-uses the cached side streams
-    b.load_state_dict(a.state_dict()) if _ else None
-    nat.check(nat.lib.pd_rollout_actions_host(
-        C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts),
-        nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
-        P(d_ctl), P(d_si), P(d_el), P(h_si), P(h_el),
-        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-    if _ == 0:
-      np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
-      np.testing.assert_array_equal(h_el.numpy(), gh.np_(el))
-      np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+  for n, t_steps, poison in ((4096, 37, False), (4096, 100, False),
+                             (2048, 130, True)):
+    seed = 51
+    rng = np.random.default_rng(9 + t_steps)
+    acts_np = rng.uniform(-1, 1, size=(t_steps, n, 2))
+    if poison:
+      bits = acts_np.view(np.uint64)
+      for t, e in ((0, 0), (3, 11), (t_steps - 1, n - 1)):
+        bits[t, e, :] = 0xFFFFFFFFFFFFFFFF
+    acts = torch.as_tensor(acts_np).pin_memory()
+    a = eng.EnvBatch(n, seed=seed)
+    b = eng.EnvBatch(n, seed=seed)
+    a.reset()
+    b.reset()
+    spec = gh.rate_spec(po.RATE_PRIOR)
+    si, el = a.rollout(acts, 1500000, spec, record=True,
+                       action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+    dev = b.device
+    d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
+    d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+    d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+    h_si = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
+    h_el = torch.zeros((t_steps, n), dtype=torch.int64).pin_memory()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    for rep in range(2):  # second call re-uses the cached side streams
+      if rep:
+        b.load_state_dict(a.state_dict())
+      nat.check(nat.lib.pd_rollout_actions_host(
+          C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts),
+          nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
+          P(d_ctl), P(d_si), P(d_el), P(h_si), P(h_el),
+          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+      if rep == 0:
+        np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
+        np.testing.assert_array_equal(h_el.numpy(), gh.np_(el))
+        np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+        np.testing.assert_array_equal(gh.np_(b.sim_time_us),
+                                      gh.np_(a.sim_time_us))
 
 
 def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
