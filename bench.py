@@ -510,7 +510,9 @@ def run_ours(args, cfg):
         nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
         P(d_stage), P(d_si), P(d_el), P(h_si), P(h_el), stream))
 
-  E2E_REPEATS = 5
+  # odd, and long enough (~0.1 s) to span the clock sampler's 100 ms period:
+  # an nvidia-smi query in flight delays launches for a few milliseconds
+  E2E_REPEATS = 15
 
   def time_host(fn):
     """Median over E2E_REPEATS timings of exactly args.steps calls each (a
