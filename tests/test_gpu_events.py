@@ -550,13 +550,16 @@ def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
   si, el = a.rollout(acts32.double(), 1500000, spec, record=True,
                      action_mode=mode)
   dev = b.device
-  d_a32 = torch.empty((t_steps, n, 2), dtype=torch.float32, device=dev)
-  d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
-  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
-  d_el32 = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-  h_si = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
-  h_el = torch.zeros((t_steps, n), dtype=torch.int32).pin_memory()
+  # one guard row behind every buffer the call writes: nothing may touch it
+  GUARD = 0x5A5A5A5A
+  d_a32 = torch.full((t_steps + 1, n, 2), 1.5, dtype=torch.float32, device=dev)
+  d_ctl = torch.full((t_steps + 1, n, 2), 1.5, dtype=torch.float64, device=dev)
+  d_si = torch.full((t_steps + 1, n), GUARD, dtype=torch.int32, device=dev)
+  d_el = torch.full((t_steps + 1, n), GUARD, dtype=torch.int64, device=dev)
+  d_el32 = torch.full((t_steps + 1, n), GUARD, dtype=torch.int32, device=dev)
+  h_si_all = torch.full((t_steps + 1, n), GUARD, dtype=torch.int32).pin_memory()
+  h_el_all = torch.full((t_steps + 1, n), GUARD, dtype=torch.int32).pin_memory()
+  h_si, h_el = h_si_all[:t_steps], h_el_all[:t_steps]
   P = lambda t: C.c_void_p(t.data_ptr())
   stage = ((None,) * 5 if owned else
            (P(d_a32), P(d_ctl), P(d_si), P(d_el), P(d_el32)))
@@ -569,6 +572,15 @@ def _host_f32_case(eng, n, t_steps, mode, rate_fn=po.RATE_PRIOR,
   np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
   if want_elapsed:
     np.testing.assert_array_equal(h_el.numpy().astype(np.int64), gh.np_(el))
+  else:
+    assert (h_el.numpy() == GUARD).all()
+  assert (h_si_all[t_steps].numpy() == GUARD).all()
+  assert (h_el_all[t_steps].numpy() == GUARD).all()
+  assert (gh.np_(d_si[t_steps]) == GUARD).all()
+  assert (gh.np_(d_el[t_steps]) == GUARD).all()
+  assert (gh.np_(d_el32[t_steps]) == GUARD).all()
+  assert (gh.np_(d_a32[t_steps]) == 1.5).all()
+  assert (gh.np_(d_ctl[t_steps]) == 1.5).all()
   np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
   np.testing.assert_array_equal(gh.np_(b.sim_time_us), gh.np_(a.sim_time_us))
   np.testing.assert_array_equal(gh.np_(b.n_events), gh.np_(a.n_events))
