@@ -1,8 +1,11 @@
 """Host-buffer rollout (pd_rollout_actions_host_f32) at configs[1]: wall time
-per call and a digest of the results, for the streamed / chunked forms.
+per call and a digest of the results.
 
-  PD_HOST_STREAMED=0 python profiles/prof_e2e.py     # chunked pipeline
-  PD_HOST_STREAM_CHUNKS=8 python profiles/prof_e2e.py
+  python profiles/prof_e2e.py                        # streamed launch
+  PD_HOST_STREAMED=0 python profiles/prof_e2e.py     # chunked copy-engine pipeline
+  PD_HOST_TRACE=1 REPS=4 python profiles/prof_e2e.py # timeline of each call
+  OWNED=1 python profiles/prof_e2e.py                # library-owned stagings
+  PD_HOST_COPY_SMS=8 python profiles/prof_e2e.py     # SMs given to the writers
 """
 import ctypes as C
 import hashlib
