@@ -2314,10 +2314,11 @@ static int streamed_rollout(HostPipeline* pipe, const pd_lattice* lat,
         PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->cleaned, 0));
         PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->cleaned, 0));
       } else {
-        if (owned) {  // an earlier re-fill may still be running
-          PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
-          pipe->clean_in = pipe->clean_out = 0;
-        }
+        // A re-fill behind an earlier call (library-owned stagings) may still
+        // be running, and it writes the control words this call is about to
+        // use; after this call they are used, whoever owns the stagings.
+        PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+        pipe->clean_in = pipe->clean_out = 0;
         PD_CUDA_OK(fill(s));
         PD_CUDA_OK(cudaEventRecord(pipe->start, s));
         PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));

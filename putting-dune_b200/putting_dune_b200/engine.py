@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-from typing import Optional, Sequence, Union
+from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -377,6 +377,72 @@ class EnvBatch:
           int(dwell_us), t, int(image_duration_us), _ptr(si), _ptr(el),
           _stream(self.device)))
     return (si, el) if record else None
+
+  def rollout_host(self, actions_xy, dwell_us: int, rate: RateSpec,
+                   image_duration_us: int = 2000000,
+                   action_mode: int = nat.ACTION_DIRECT,
+                   max_distance_angstroms: float = 1.42,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """`rollout` with HOST buffers in and out (the C ABI's
+    pd_rollout_actions_host_f32 / pd_rollout_actions_host).
+
+    actions_xy: [T, E, 2] NumPy array or CPU tensor; float32 (the dtype the
+    action adapters' action_spec declares: 8 B per env-step over PCIe, int32
+    elapsed microseconds back) or float64 (int64 elapsed back).  Page-locked
+    input (``tensor.pin_memory()``) is used as is, anything else is copied
+    into a pinned buffer first.  Returns (si_idx [T, E] int32, elapsed_us
+    [T, E]) as pinned CPU tensors (``out`` re-uses a previous result).  Small
+    batches on the prior / simple rates run as one launch that steps while
+    the actions arrive and the results leave over PCIe.
+    """
+    act = torch.as_tensor(actions_xy)
+    if act.device.type != 'cpu':
+      raise ValueError('rollout_host takes host buffers; use rollout() for '
+                       'device tensors')
+    if act.dtype not in (torch.float32, torch.float64):
+      act = act.to(torch.float64)
+    if act.ndim != 3 or act.shape[1] != self.num_envs or act.shape[2] != 2:
+      raise ValueError(f'actions must be [T, E, 2], got {tuple(act.shape)}')
+    act = act.contiguous()
+    if not act.is_pinned():
+      act = act.pin_memory()
+    t, e = act.shape[0], self.num_envs
+    wide = act.dtype == torch.float64
+    el_dtype = torch.int64 if wide else torch.int32
+    if out is not None:
+      h_si, h_el = out
+      if (h_si.shape != (t, e) or h_el.shape != (t, e) or
+          h_si.dtype != torch.int32 or h_el.dtype != el_dtype or
+          not h_si.is_pinned() or not h_el.is_pinned()):
+        raise ValueError('out does not match this call')
+    else:
+      h_si = torch.empty((t, e), dtype=torch.int32).pin_memory()
+      h_el = torch.empty((t, e), dtype=el_dtype).pin_memory()
+    if t == 0:
+      return h_si, h_el
+    with torch.cuda.device(self.device):
+      if wide:
+        key = ('wide', t)
+        if getattr(self, '_host_stage_key', None) != key:
+          self._host_stage = (
+              torch.empty((t, e, 2), dtype=torch.float64, device=self.device),
+              torch.empty((t, e), dtype=torch.int32, device=self.device),
+              torch.empty((t, e), dtype=torch.int64, device=self.device))
+          self._host_stage_key = key
+        d_ctl, d_si, d_el = self._host_stage
+        nat.check(nat.lib.pd_rollout_actions_host(
+            C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+            _ptr(act), int(action_mode), float(max_distance_angstroms),
+            int(dwell_us), t, int(image_duration_us), _ptr(d_ctl), _ptr(d_si),
+            _ptr(d_el), _ptr(h_si), _ptr(h_el), _stream(self.device)))
+      else:
+        # stagings kept (and prepared for the next call) by the library
+        nat.check(nat.lib.pd_rollout_actions_host_f32(
+            C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+            _ptr(act), int(action_mode), float(max_distance_angstroms),
+            int(dwell_us), t, int(image_duration_us), None, None, None, None,
+            None, _ptr(h_si), _ptr(h_el), _stream(self.device)))
+    return h_si, h_el
 
   # -- queries --------------------------------------------------------------
   def max_atoms_in_view(self) -> int:

@@ -217,5 +217,17 @@ class BatchedSimulator:
     return self.batch.rollout(controls_xy, mu.timedelta_to_us(dwell_time),
                               self.rate, self.image_duration_us, record)
 
+  def rollout_host(self, actions_xy, dwell_time, action_mode=None,
+                   max_distance_angstroms: float = 1.42, out=None):
+    """`rollout` with host buffers in and out (EnvBatch.rollout_host)."""
+    if not self._has_been_reset:
+      raise RuntimeError('Must call reset before rollout.')
+    from putting_dune_b200 import _native as nat
+    return self.batch.rollout_host(
+        actions_xy, mu.timedelta_to_us(dwell_time), self.rate,
+        self.image_duration_us,
+        nat.ACTION_DIRECT if action_mode is None else action_mode,
+        max_distance_angstroms, out)
+
   def get_atoms_in_bounds(self, fov=None, max_atoms=None):
     return self.batch.get_atoms_in_bounds(fov, max_atoms)

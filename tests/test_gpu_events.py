@@ -611,10 +611,63 @@ def test_rollout_host_compact_formats(eng):
                          (4096, 200, {}), (4096, 64, {'want_elapsed': False}),
                          (4096, 128, {}), (700, 9, {}), (4096, 128, {})):
     _host_f32_case(eng, n, t_steps, rel, owned=True, **kw)
+  # a call with the caller's stagings in between uses (and dirties) the same
+  # control words: the next library-owned call must not assume them ready
+  _host_f32_case(eng, 4096, 128, rel, owned=True)
+  _host_f32_case(eng, 4096, 128, rel)
+  _host_f32_case(eng, 4096, 128, rel, owned=True)
+  _host_f32_case(eng, 4096, 128, rel, owned=True)
   _host_f32_case(eng, 700, 9, rel)
   _host_f32_case(eng, 4100, 70, rel)
   with pytest.raises(nat.NativeError, match='int32'):
     nat.check(nat.lib.pd_rollout_actions_host_f32(*args(3000000000, None)))
+
+
+def test_envbatch_rollout_host(eng):
+  """EnvBatch.rollout_host / BatchedSimulator.rollout_host: host arrays in,
+  pinned host tensors out, equal to the device rollout (float32 actions ->
+  int32 elapsed, float64 -> int64; pageable and pinned inputs; `out`
+  re-used)."""
+  import datetime as dt
+  from putting_dune_b200 import _native as nat
+  from putting_dune_b200 import simulator as sim_lib
+  rel = nat.ACTION_RELATIVE_TO_SILICON
+  n, t_steps = 4096, 72
+  spec = gh.rate_spec(po.RATE_PRIOR)
+  rng = np.random.default_rng(4)
+  out32 = None
+  for dtype, pinned in ((np.float32, False), (np.float32, True),
+                        (np.float64, False)):
+    acts = rng.uniform(-1, 1, size=(t_steps, n, 2)).astype(dtype)
+    a = eng.EnvBatch(n, seed=8)
+    b = eng.EnvBatch(n, seed=8)
+    a.reset()
+    b.reset()
+    si, el = a.rollout(torch.as_tensor(acts).double(), 1500000, spec,
+                       record=True, action_mode=rel)
+    src = torch.as_tensor(acts).pin_memory() if pinned else acts
+    got = b.rollout_host(src, 1500000, spec, action_mode=rel,
+                         out=out32 if dtype == np.float32 else None)
+    if dtype == np.float32:
+      out32 = got
+    h_si, h_el = got
+    assert h_si.is_pinned() and h_el.is_pinned()
+    assert h_el.dtype == (torch.int32 if dtype == np.float32 else torch.int64)
+    np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
+    np.testing.assert_array_equal(h_el.numpy().astype(np.int64), gh.np_(el))
+    np.testing.assert_array_equal(gh.np_(b.si_idx), gh.np_(a.si_idx))
+  with pytest.raises(ValueError, match='T, E, 2'):
+    b.rollout_host(np.zeros((3, n + 1, 2), np.float32), 1500000, spec)
+  with pytest.raises(ValueError, match='host buffers'):
+    b.rollout_host(torch.zeros((3, n, 2), device=b.device), 1500000, spec)
+  s = sim_lib.BatchedSimulator(n, seed=8)
+  with pytest.raises(RuntimeError, match='reset'):
+    s.rollout_host(np.zeros((4, n, 2), np.float32), dt.timedelta(seconds=1.5))
+  s.reset()
+  h_si, h_el = s.rollout_host(
+      rng.uniform(0.45, 0.55, size=(64, n, 2)).astype(np.float32),
+      dt.timedelta(seconds=1.5))
+  assert h_si.shape == (64, n) and (h_el.numpy() >= 3500000).all()
 
 
 def test_rollout_host_streamed_equals_chunked():
