@@ -508,7 +508,9 @@ __global__ void __launch_bounds__(kStepThreads)
 //            outcome.  No shuffles: the lanes stay bit-identical replicas.
 // ~89 % of the controls of the relative_random workload never reach phase B.
 //
-// STREAM (pd_rollout_actions_host_f32): the launch runs WHILE the actions
+// STREAM (1: pd_rollout_actions_host_f32, float32 actions / int32 elapsed;
+// 2: pd_rollout_actions_host, float64 actions / int64 elapsed, the "not yet"
+// pattern being two all-ones 64-bit words): the launch runs WHILE the actions
 // arrive and the results leave over PCIe, instead of between copy-engine
 // chunks.  In: one copy-engine H2D copy of the whole float32 action stream
 // into a staging the call pre-filled with 0xFF bytes; a stepping lane reads
