@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -63,6 +64,34 @@ def test_no_cpu_fallback_without_device():
   with pytest.raises(RuntimeError, match='no CPU fallback'):
     pd.graphene.PristineSingleDopedGraphene().reset(
         pd.graphene.PhiloxKey(0))
+
+
+def test_synthetic_data_host_side():
+  """rate_learning/data_utils.py host logic that needs no device: the
+  NETWORK mode's weight initialiser (Haiku hk.Linear defaults:
+  TruncatedNormal(stddev = 1 / sqrt(fan_in)) cut at two standard deviations,
+  zero biases; learn_rates.py:80-99 with hidden (1, 64),
+  data_utils.py:196-201) and the loud failure without a CUDA device."""
+  import torch
+  from putting_dune_b200.rate_learning import data_utils
+  net = data_utils.init_network(3, 4, num_states=3)
+  assert net['w0'].shape == (4, 1) and net['w1'].shape == (1, 64)
+  assert net['w2'].shape == (64, 4) and net['b2'].shape == (4,)
+  for k, fan_in in (('w0', 4), ('w1', 1), ('w2', 64)):
+    w = net[k]
+    assert w.dtype == np.float32
+    assert np.abs(w).max() <= 2.0 / np.sqrt(fan_in) + 1e-6
+  assert not net['b0'].any() and not net['b1'].any() and not net['b2'].any()
+  big = data_utils.init_network(3, 4, num_states=5, hidden=(32, 200))
+  assert abs(big['w1'].std() * np.sqrt(32) - 0.88) < 0.05  # truncated normal
+  again = data_utils.init_network(3, 4, num_states=3)
+  np.testing.assert_array_equal(net['w1'], again['w1'])
+  assert data_utils.SyntheticDataType('network') == \
+      data_utils.SyntheticDataType.NETWORK
+  if not torch.cuda.is_available():
+    for mode in ('prior', 'network'):
+      with pytest.raises(RuntimeError, match='no CPU fallback'):
+        data_utils.generate_synthetic_data(num_data=4, data_seed=1, mode=mode)
 
 
 def test_product_never_imports_oracle():
