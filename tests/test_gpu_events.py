@@ -479,15 +479,20 @@ def test_rollout_host_pipeline_matches_device_path(eng):
   """pd_rollout_actions_host (float64 actions, int64 elapsed) returns what the
   device-resident rollout computes: (4096, 37) through the chunked H2D / step
   / D2H pipeline, (4096, 100) and (2048, 130) through the streamed launch
-  (k_rollout_pre<STREAM = 2>), the last with actions that carry the
-  "not arrived" bit pattern."""
+  (k_rollout_pre<STREAM = 2>), the third with actions that carry the
+  "not arrived" bit pattern, the last through pd_rollout_host (beam positions
+  instead of adapter actions)."""
   import ctypes as C
   from putting_dune_b200 import _native as nat
-  for n, t_steps, poison in ((4096, 37, False), (4096, 100, False),
-                             (2048, 130, True)):
+  rel, direct = nat.ACTION_RELATIVE_TO_SILICON, nat.ACTION_DIRECT
+  for n, t_steps, poison, mode in ((4096, 37, False, rel),
+                                   (4096, 100, False, rel),
+                                   (2048, 130, True, rel),
+                                   (4096, 70, False, direct)):
     seed = 51
     rng = np.random.default_rng(9 + t_steps)
-    acts_np = rng.uniform(-1, 1, size=(t_steps, n, 2))
+    acts_np = (rng.uniform(-1, 1, size=(t_steps, n, 2)) if mode == rel else
+               0.5 + rng.uniform(-0.06, 0.06, size=(t_steps, n, 2)))
     if poison:
       bits = acts_np.view(np.uint64)
       for t, e in ((0, 0), (3, 11), (t_steps - 1, n - 1)):
@@ -498,8 +503,7 @@ def test_rollout_host_pipeline_matches_device_path(eng):
     a.reset()
     b.reset()
     spec = gh.rate_spec(po.RATE_PRIOR)
-    si, el = a.rollout(acts, 1500000, spec, record=True,
-                       action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+    si, el = a.rollout(acts, 1500000, spec, record=True, action_mode=mode)
     dev = b.device
     d_ctl = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
     d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
@@ -510,11 +514,17 @@ def test_rollout_host_pipeline_matches_device_path(eng):
     for rep in range(2):  # second call re-uses the cached side streams
       if rep:
         b.load_state_dict(a.state_dict())
-      nat.check(nat.lib.pd_rollout_actions_host(
-          C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c), P(acts),
-          nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, t_steps, 2000000,
-          P(d_ctl), P(d_si), P(d_el), P(h_si), P(h_el),
-          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+      stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+      if mode == direct:  # pd_rollout_host = the DIRECT form
+        nat.check(nat.lib.pd_rollout_host(
+            C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c),
+            P(acts), 1500000, t_steps, 2000000, P(d_ctl), P(d_si), P(d_el),
+            P(h_si), P(h_el), stream))
+      else:
+        nat.check(nat.lib.pd_rollout_actions_host(
+            C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(spec.c),
+            P(acts), mode, 1.42, 1500000, t_steps, 2000000, P(d_ctl), P(d_si),
+            P(d_el), P(h_si), P(h_el), stream))
       if rep == 0:
         np.testing.assert_array_equal(h_si.numpy(), gh.np_(si))
         np.testing.assert_array_equal(h_el.numpy(), gh.np_(el))
