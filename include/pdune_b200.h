@@ -107,7 +107,10 @@ typedef struct pd_lattice {
   int32_t n_cols;        /* grid_columns (reference default 50)              */
   int32_t n_sites;       /* 1881 for 50 columns                              */
   const double* base_xy; /* [n_sites][2] (G*1.42 - mean), graphene.py:537-543 */
-  const int32_t* nbr;    /* [n_sites][4] 3-NN site ids + pad, geometry.py:93  */
+  const int32_t* nbr;    /* [n_sites][4] 3-NN site ids, geometry.py:93; column
+                          * 3 is library data: bits 0-23 list the sites near
+                          * the lattice centre (terminated by 0xFFFFFF), bits
+                          * 24-25 hold the site's neighbour-geometry class    */
 } pd_lattice;
 
 /* Per-env simulator state, struct of arrays, all device pointers of length
@@ -334,6 +337,40 @@ int pd_rollout_actions_host_f32(
     int64_t image_duration_us, float* d_actions_f32, double* d_controls_xy,
     int32_t* d_si_idx, int64_t* d_elapsed_us, int32_t* d_elapsed_us32,
     int32_t* h_si_idx, int32_t* h_elapsed_us32, void* stream);
+
+/* ---- the guarded float32 iteration (rollouts on the prior / simple rates).
+ * pd_rollout_actions with one positive dwell time below 3000 s decides every
+ * iteration of graphene.py:658-694 (hop or not, which neighbour) in float32
+ * when the float32 result is further from the deciding threshold than a bound
+ * of its own error, and replays the control with the float64 code otherwise,
+ * so results equal the float64 kernels' bit for bit (csrc/pd_fast.cuh).
+ * pd_set_fast_path(0) sends every iteration through the float64 code (A/B
+ * timing, parity tests); returns the previous setting.  Default 1; the
+ * environment variable PD_FAST=0 sets the default to 0. */
+int pd_set_fast_path(int enabled);
+
+/* Measures the float32 quantities of that iteration against the float64 ones
+ * over n_samples random iterations (random site, lattice angle, beam offset
+ * within max_distance of the Si, Philox draw, clock).  The *_over_bound
+ * fields are the largest observed error divided by the bound the fast path
+ * assumes for it (must stay below 1, in practice below ~0.3);
+ * wrong_decision / wrong_slot count decided iterations that differ from the
+ * exact code (must be 0). */
+typedef struct pd_fast_audit {
+  int64_t samples, no_hop, hop, unsure;
+  int64_t wrong_decision, wrong_slot, waiting_time_outside_bounds;
+  double total_rate_error_over_bound;
+  double waiting_time_error_over_bound;
+  double choice_error_over_bound;
+  /* the float32 unit-exponential draw against float64 over all 2^24 values
+   * of its 24-bit uniform (exhaustive), and the bound assumed for it */
+  double draw_error_abs_max;
+  double draw_error_bound;
+} pd_fast_audit;
+int pd_fast_path_audit(const pd_lattice* lat, int32_t rate_fn, uint64_t seed,
+                       int64_t n_samples, int64_t dwell_us,
+                       double max_distance_angstroms, pd_fast_audit* out,
+                       void* stream);
 
 /* ---- imaging.py:42-72: re-draws the nine image parameters of the envs'
  *      current episode from the uniforms the last pd_reset used (RESET draws

@@ -12,7 +12,7 @@ mkdir -p "$out" "$obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 COMMON=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
         -Xcompiler -fPIC -I"$here/../include" -I"$src" ${PD_NVCC_EXTRA:-})
-exact=(pd_lattice pd_reset pd_step pd_query)
+exact=(pd_lattice pd_reset pd_step pd_step_fast pd_query)
 fast=(pd_api pd_mlp)
 [ -f "$src/pd_render.cu" ] && fast+=(pd_render)
 [ -f "$src/pd_synth.cu" ] && fast+=(pd_synth)

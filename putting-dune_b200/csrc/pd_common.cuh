@@ -13,6 +13,12 @@ constexpr double kMaxTransitionSeconds = 3600; // graphene.py:668
 constexpr int kCarbon = 6;                     // constants.py:20
 constexpr int kSilicon = 14;                   // constants.py:21
 
+// Column 3 of pd_lattice.nbr: bits 0-23 an entry of the list of sites near the
+// lattice centre (pd_reset), bits 24-25 the site's geometry class
+// (pd_lattice.cu).
+constexpr int kCentreListEnd = 0xFFFFFF;
+constexpr int kSiteClassShift = 24;
+
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t err, const char* what);
 int sm_count();

@@ -31,6 +31,14 @@ struct GlobalTables {
     out[1] = v.y;
     out[2] = v.z;
   }
+  // neighbours + geometry class of site k (pd_lattice.cu)
+  __device__ __forceinline__ int neighbors_class(int k, int out[3]) const {
+    const int4 v = __ldg(nbr + k);
+    out[0] = v.x;
+    out[1] = v.y;
+    out[2] = v.z;
+    return (v.w >> kSiteClassShift) & 3;
+  }
 };
 
 struct SharedTables {
@@ -42,6 +50,13 @@ struct SharedTables {
     out[0] = v.x;
     out[1] = v.y;
     out[2] = v.z;
+  }
+  __device__ __forceinline__ int neighbors_class(int k, int out[3]) const {
+    const ushort4 v = nbr[k];
+    out[0] = v.x;
+    out[1] = v.y;
+    out[2] = v.z;
+    return v.w;
   }
 };
 
@@ -61,7 +76,9 @@ __device__ __forceinline__ SharedTables stage_tables(const pd_lattice& lat,
     const int4 v = __ldg(gnbr + k);
     snbr[k] = make_ushort4(static_cast<unsigned short>(v.x),
                            static_cast<unsigned short>(v.y),
-                           static_cast<unsigned short>(v.z), 0);
+                           static_cast<unsigned short>(v.z),
+                           static_cast<unsigned short>(
+                               (v.w >> kSiteClassShift) & 3));
   }
   __syncthreads();
   return SharedTables{sbase, snbr};
@@ -524,10 +541,30 @@ struct LogSink {
   int32_t* ctrl;
 };
 
+// Philox4x32-10 round keys: they depend on the seed only, so the host computes
+// them once per launch and the kernels read them as constant-bank operands.
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+};
+
+inline PhiloxKeys philox_keys_host(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = static_cast<uint32_t>(seed);
+  uint32_t b = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.k0[r] = a;
+    k.k1[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return k;
+}
+
 struct StepArgs {
   pd_lattice lat;
   pd_state st;
   RateArgs ra;
+  PhiloxKeys keys;            // of st.seed (filled by launch_step)
   const double* controls_xy;  // [n][C][2] or [T][n][2] (rollout)
   const int64_t* dwell_us;    // [n][C] or null
   int64_t dwell_us_scalar;
@@ -603,6 +640,108 @@ __device__ __forceinline__ EnvRegs load_env(const Tables& tab,
   r.log_n = 0;
   r.status = a.st.status[e];
   return r;
+}
+
+// ---------------------------------------------------------------------------
+// The exact (float64) control: shared by every stepping kernel.
+// ---------------------------------------------------------------------------
+template <int RATE>
+__device__ __forceinline__ void eval_rates(const RateArgs& ra,
+                                           const double2 beam,
+                                           const double2 psi,
+                                           const double2 pn[3], float r[3]) {
+  if (RATE == PD_RATE_SIMPLE) {
+    rates_simple(beam, psi, pn, r);
+  } else if (RATE == PD_RATE_PRIOR) {
+    rates_prior(beam, psi, pn, r);
+  } else if (RATE == PD_RATE_GMM) {
+    double r64[3];
+    rates_gmm(ra, beam, psi, pn, r64);
+    r[0] = __double2float_rn(r64[0]);
+    r[1] = __double2float_rn(r64[1]);
+    r[2] = __double2float_rn(r64[2]);
+  } else {
+    r[0] = ra.constant_rates[0];
+    r[1] = ra.constant_rates[1];
+    r[2] = ra.constant_rates[2];
+  }
+}
+
+// Rates + one event of the direct method.  Float64-rate functions (GMM) keep
+// the total in float64 (see kmc_event_drawn64).
+template <int RATE>
+__device__ __forceinline__ bool rate_event(const RateArgs& ra,
+                                           const double2 beam,
+                                           const double2 psi,
+                                           const double2 pn[3], double u_exp,
+                                           double u_choice, long long dwell_us,
+                                           long long* elapsed_us, int* slot,
+                                           bool* bad) {
+  if constexpr (RATE == PD_RATE_GMM) {
+    double r64[3];
+    rates_gmm(ra, beam, psi, pn, r64);
+    *bad = false;
+    return kmc_event_drawn64(r64, -log1p(-u_exp), u_choice, dwell_us,
+                             elapsed_us, slot);
+  } else {
+    float r[3];
+    eval_rates<RATE>(ra, beam, psi, pn, r);
+    return kmc_event(r, u_exp, u_choice, dwell_us, elapsed_us, slot, bad);
+  }
+}
+
+// graphene.py:646-694 for one env.
+template <int RATE, class Tables>
+__device__ __forceinline__ void run_control(const Tables& tab,
+                                            const RateArgs& ra, uint64_t seed,
+                                            const double2 beam,
+                                            long long dwell_us, int ctrl_index,
+                                            int64_t env_local,
+                                            const LogSink& log, EnvRegs* e) {
+  long long elapsed = 0;
+  uint32_t it = 0;
+  while (elapsed < dwell_us) {  // graphene.py:658
+    int nb[3];
+    tab.neighbors(e->si, nb);
+    double2 pn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      pn[i] = site_position(tab.position(nb[i]), e->lat);
+    const uint4 w =
+        philox4x32_10(e->env_id, e->ctrl_count, it, PD_STREAM_KMC, seed);
+    int slot = 0;
+    bool bad = false;
+    const bool hit =
+        rate_event<RATE>(ra, beam, e->psi, pn, u53(w.x, w.y), u53(w.z, w.w),
+                         dwell_us, &elapsed, &slot, &bad);
+    if (bad) e->status |= PD_ENV_BAD_RATE;
+    e->events += 1;
+    if (hit) {
+      e->si = nb[slot];
+      e->psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
+      e->transitions += 1;
+      if (log.capacity > 0) {
+        if (e->log_n < log.capacity) {
+          const int64_t o = env_local * log.capacity + e->log_n;
+          log.elapsed_us[o] = elapsed;
+          log.site[o] = e->si;
+          if (log.ctrl) log.ctrl[o] = ctrl_index;
+        } else {
+          e->status |= PD_ENV_LOG_OVERFLOW;
+        }
+        e->log_n += 1;
+      }
+    }
+    ++it;
+  }
+  e->ctrl_count += 1;
+}
+
+__device__ __forceinline__ double shfl_double(unsigned mask, double v,
+                                              int src) {
+  const int lo = __shfl_sync(mask, __double2loint(v), src);
+  const int hi = __shfl_sync(mask, __double2hiint(v), src);
+  return __hiloint2double(hi, lo);
 }
 
 }  // namespace pd

@@ -103,11 +103,33 @@ __global__ void __launch_bounds__(1024, 1)
     nbr[4 * k + 0] = best_m[0];
     nbr[4 * k + 1] = best_m[1];
     nbr[4 * k + 2] = best_m[2];
-    nbr[4 * k + 3] = -1;
+    // Geometry class of the site (bits 24-25 of column 3; pd_kmc.cuh
+    // site_class): in the bulk the three neighbours are the bonded ones, in
+    // the order (row below, same row, row above), and their offsets take one
+    // of two forms -- class 0: (-1/2, -r), (1, 0), (-1/2, r) bond lengths
+    // with r = sqrt(3)/2, class 1: the negatives in reverse order.  Sites at
+    // the sheet edge whose nearest three are not of that form are class 2.
+    int cls = 2;
+    if (best_d[0] == 4 && best_d[1] == 4 && best_d[2] == 4) {
+      int ox[3], oj[3];
+      for (int q = 0; q < 3; ++q) {
+        int im, jm;
+        site_ij(s, best_m[q], &im, &jm);
+        ox[q] = 2 * im + (jm & 1) - xk;
+        oj[q] = jm - jk;
+      }
+      if (ox[0] == -1 && oj[0] == -1 && ox[1] == 2 && oj[1] == 0 &&
+          ox[2] == -1 && oj[2] == 1)
+        cls = 0;
+      else if (ox[0] == 1 && oj[0] == -1 && ox[1] == -2 && oj[1] == 0 &&
+               ox[2] == 1 && oj[2] == 1)
+        cls = 1;
+    }
+    nbr[4 * k + 3] = (cls << kSiteClassShift) | kCentreListEnd;
   }
   __syncthreads();
-  // (5) column 3 of the table lists, in ascending order and terminated by -1,
-  //     the sites within 2.6 A of the lattice centre.  After the reset offset
+  // (5) the low 24 bits of column 3 list, in ascending order and terminated
+  //     by kCentreListEnd, the sites within 2.6 A of the lattice centre.  After the reset offset
   //     (|off| <= 0.71*sqrt(2) A) the site nearest the origin is always one
   //     of them (any point of a honeycomb is within one bond of a site), so
   //     pd_reset searches this list instead of all sites.
@@ -115,7 +137,10 @@ __global__ void __launch_bounds__(1024, 1)
     int j = 0;
     for (int k = 0; k < s.n_sites && j < s.n_sites - 1; ++k) {
       const double x = base_xy[2 * k], y = base_xy[2 * k + 1];
-      if (x * x + y * y <= 2.6 * 2.6) nbr[4 * (j++) + 3] = k;
+      if (x * x + y * y <= 2.6 * 2.6) {
+        nbr[4 * j + 3] = (nbr[4 * j + 3] & ~kCentreListEnd) | k;
+        ++j;
+      }
     }
   }
 }

@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(kResetThreads)
     int best_k = 0;
     double2 psi = make_double2(0.0, 0.0);
     for (int j = 0; j < lat.n_sites; ++j) {
-      const int k = __ldg(lat.nbr + 4 * j + 3);
-      if (k < 0) break;
+      const int k = __ldg(lat.nbr + 4 * j + 3) & kCentreListEnd;
+      if (k == kCentreListEnd) break;
       const double2 p = site_position(__ldg(base + k), t);
       const double dist =
           __dsqrt_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)));

@@ -22,98 +22,6 @@
 
 namespace pd {
 
-template <int RATE>
-__device__ __forceinline__ void eval_rates(const RateArgs& ra,
-                                           const double2 beam,
-                                           const double2 psi,
-                                           const double2 pn[3], float r[3]) {
-  if (RATE == PD_RATE_SIMPLE) {
-    rates_simple(beam, psi, pn, r);
-  } else if (RATE == PD_RATE_PRIOR) {
-    rates_prior(beam, psi, pn, r);
-  } else if (RATE == PD_RATE_GMM) {
-    double r64[3];
-    rates_gmm(ra, beam, psi, pn, r64);
-    r[0] = __double2float_rn(r64[0]);
-    r[1] = __double2float_rn(r64[1]);
-    r[2] = __double2float_rn(r64[2]);
-  } else {
-    r[0] = ra.constant_rates[0];
-    r[1] = ra.constant_rates[1];
-    r[2] = ra.constant_rates[2];
-  }
-}
-
-// Rates + one event of the direct method.  Float64-rate functions (GMM) keep
-// the total in float64 (see kmc_event_drawn64).
-template <int RATE>
-__device__ __forceinline__ bool rate_event(const RateArgs& ra,
-                                           const double2 beam,
-                                           const double2 psi,
-                                           const double2 pn[3], double u_exp,
-                                           double u_choice, long long dwell_us,
-                                           long long* elapsed_us, int* slot,
-                                           bool* bad) {
-  if constexpr (RATE == PD_RATE_GMM) {
-    double r64[3];
-    rates_gmm(ra, beam, psi, pn, r64);
-    *bad = false;
-    return kmc_event_drawn64(r64, -log1p(-u_exp), u_choice, dwell_us,
-                             elapsed_us, slot);
-  } else {
-    float r[3];
-    eval_rates<RATE>(ra, beam, psi, pn, r);
-    return kmc_event(r, u_exp, u_choice, dwell_us, elapsed_us, slot, bad);
-  }
-}
-
-// graphene.py:646-694 for one env.
-template <int RATE, class Tables>
-__device__ __forceinline__ void run_control(const Tables& tab,
-                                            const RateArgs& ra, uint64_t seed,
-                                            const double2 beam,
-                                            long long dwell_us, int ctrl_index,
-                                            int64_t env_local,
-                                            const LogSink& log, EnvRegs* e) {
-  long long elapsed = 0;
-  uint32_t it = 0;
-  while (elapsed < dwell_us) {  // graphene.py:658
-    int nb[3];
-    tab.neighbors(e->si, nb);
-    double2 pn[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      pn[i] = site_position(tab.position(nb[i]), e->lat);
-    const uint4 w =
-        philox4x32_10(e->env_id, e->ctrl_count, it, PD_STREAM_KMC, seed);
-    int slot = 0;
-    bool bad = false;
-    const bool hit =
-        rate_event<RATE>(ra, beam, e->psi, pn, u53(w.x, w.y), u53(w.z, w.w),
-                         dwell_us, &elapsed, &slot, &bad);
-    if (bad) e->status |= PD_ENV_BAD_RATE;
-    e->events += 1;
-    if (hit) {
-      e->si = nb[slot];
-      e->psi = slot == 0 ? pn[0] : (slot == 1 ? pn[1] : pn[2]);
-      e->transitions += 1;
-      if (log.capacity > 0) {
-        if (e->log_n < log.capacity) {
-          const int64_t o = env_local * log.capacity + e->log_n;
-          log.elapsed_us[o] = elapsed;
-          log.site[o] = e->si;
-          if (log.ctrl) log.ctrl[o] = ctrl_index;
-        } else {
-          e->status |= PD_ENV_LOG_OVERFLOW;
-        }
-        e->log_n += 1;
-      }
-    }
-    ++it;
-  }
-  e->ctrl_count += 1;
-}
-
 // One step_and_image (or apply_control) call for every env.
 template <int RATE, bool STAGE>
 __global__ void __launch_bounds__(kStepThreads)
@@ -297,13 +205,6 @@ __global__ void __launch_bounds__(kStepThreads)
 // the Si position only), so the speculative lanes already use the re-centred
 // FOV for the steps that follow.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double shfl_double(unsigned mask, double v,
-                                              int src) {
-  const int lo = __shfl_sync(mask, __double2loint(v), src);
-  const int hi = __shfl_sync(mask, __double2hiint(v), src);
-  return __hiloint2double(hi, lo);
-}
-
 template <int RATE, bool STAGE>
 __global__ void __launch_bounds__(kStepThreads)
     k_rollout_spec(const StepArgs a) {
@@ -1689,6 +1590,22 @@ static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
   return StreamPlan{0, 0, 0, 0};
 }
 
+// pd_step_fast.cu: the guarded float32 kernels (prior / simple rates).
+template <int RATE>
+int launch_fast(const StepArgs& a, bool walk, bool staged, int grid,
+                cudaStream_t stream);
+
+// PD_FAST=0 keeps every iteration on the float64 chain (A/B timing; the
+// parity tests compare the two).
+static int& fast_flag() {
+  static int on = [] {
+    const char* v = getenv("PD_FAST");
+    return (!v || v[0] != '0') ? 1 : 0;
+  }();
+  return on;
+}
+static bool fast_enabled() { return fast_flag() != 0; }
+
 template <int RATE>
 static int launch_step(const StepArgs& a_in, bool rollout,
                        cudaStream_t stream) {
@@ -1700,10 +1617,28 @@ static int launch_step(const StepArgs& a_in, bool rollout,
              pre = plan.pre;
   const int grid = plan.grid;
   a.lane_stride = plan.lane_stride;
+  a.keys = philox_keys_host(a.st.seed);
   a.prepass = prepass_enabled() ? 1 : 0;
   a.walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
   a.walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
   a.walk_controls_per_pass = env_int("PD_WALK_CONTROLS", 4);
+  if constexpr (kHasPrepass) {
+    // Rollouts with one positive dwell time below the reference's waiting
+    // time cap (graphene.py:668; pd_fast.cuh kFastMaxDwellS): every decision
+    // in float32 with an error bound, exact replay of what it cannot settle.
+    if (rollout && !a.stream_mode && fast_enabled() && a.dwell_us_scalar > 0 &&
+        a.dwell_us_scalar < 3000LL * 1000000LL && !a.skip) {
+      // The tables are read through L1 (a hop touches one 16-byte row, 10 % of
+      // the iterations): staging them would cost more than it saves and take
+      // the shared memory the action stream's L1 lines need.
+      static const bool stage_fast = env_int("PD_FAST_STAGE", 0) != 0;
+      const bool st = staged && stage_fast;
+      if (walk || !spec)
+        return launch_fast<RATE>(a, true, st, grid_for(a.st.n_envs, true),
+                                 stream);
+      return launch_fast<RATE>(a, false, st, grid, stream);
+    }
+  }
   if (a.stream_mode) {
     // streamed host rollout: the caller went through stream_plan
     PD_REQUIRE(pre && staged && kHasPrepass,
@@ -1879,6 +1814,12 @@ int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
 }  // namespace pd
 
 using pd::StepArgs;
+
+extern "C" int pd_set_fast_path(int enabled) {
+  const int before = pd::fast_flag();
+  pd::fast_flag() = enabled ? 1 : 0;
+  return before;
+}
 
 extern "C" int pd_rates(const pd_lattice* lat, const pd_state* st,
                         const pd_rate_config* rc, const double* beam_xy,

@@ -172,6 +172,24 @@ _SIGNATURES = {
          _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p], C.c_int),
 }
 
+class PdFastAudit(C.Structure):
+  """pd_fast_audit (include/pdune_b200.h)."""
+  _fields_ = [('samples', C.c_int64), ('no_hop', C.c_int64),
+              ('hop', C.c_int64), ('unsure', C.c_int64),
+              ('wrong_decision', C.c_int64), ('wrong_slot', C.c_int64),
+              ('waiting_time_outside_bounds', C.c_int64),
+              ('total_rate_error_over_bound', C.c_double),
+              ('waiting_time_error_over_bound', C.c_double),
+              ('choice_error_over_bound', C.c_double),
+              ('draw_error_abs_max', C.c_double),
+              ('draw_error_bound', C.c_double)]
+
+
+_SIGNATURES['pd_set_fast_path'] = ([C.c_int], C.c_int)
+_SIGNATURES['pd_fast_path_audit'] = (
+    [_LP, _i32, C.c_uint64, _i64, _i64, C.c_double, C.POINTER(PdFastAudit),
+     _p], C.c_int)
+
 for _name, (_args, _res) in _SIGNATURES.items():
   _fn = getattr(lib, _name)
   _fn.argtypes = _args

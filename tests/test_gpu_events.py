@@ -24,17 +24,34 @@ def eng():
   return engine
 
 
+def site_classes(cols):
+  """0 / 1: bulk site whose three nearest neighbours are the bonded ones at
+  (-1/2, -r), (1, 0), (-1/2, r) bond lengths (r = sqrt(3)/2) / the negatives
+  in reverse order; 2: anything else (sheet edge)."""
+  base, nbr = po.base_lattice(cols), po.neighbor_table(cols)
+  off = (base[nbr] - base[:, None, :]) / po.BOND
+  r = np.sqrt(3.0) / 2
+  a = np.array([[-0.5, -r], [1.0, 0.0], [-0.5, r]])
+  cls = np.full(len(base), 2)
+  cls[np.abs(off - a).max(axis=(1, 2)) < 1e-9] = 0
+  cls[np.abs(off + a[::-1]).max(axis=(1, 2)) < 1e-9] = 1
+  return cls
+
+
 def test_lattice_tables_bit_exact(eng):
   for cols in (50, 10, 13):
     lat = eng.Lattice(cols)
     np.testing.assert_array_equal(gh.np_(lat.base_xy), po.base_lattice(cols))
     np.testing.assert_array_equal(gh.np_(lat.nbr)[:, :3],
                                   po.neighbor_table(cols))
-    # column 3: the sites within 2.6 A of the lattice centre, then -1
-    cand = gh.np_(lat.nbr)[:, 3]
+    # column 3, low 24 bits: the sites within 2.6 A of the lattice centre,
+    # then 0xFFFFFF; bits 24-25: the neighbour-geometry class of the site
+    col3 = gh.np_(lat.nbr)[:, 3]
+    cand = col3 & 0xFFFFFF
     want = np.nonzero((po.base_lattice(cols) ** 2).sum(axis=1) <= 2.6 ** 2)[0]
     np.testing.assert_array_equal(cand[:want.size], want)
-    assert (cand[want.size:] == -1).all()
+    assert (cand[want.size:] == 0xFFFFFF).all()
+    np.testing.assert_array_equal(col3 >> 24, site_classes(cols))
 
 
 def test_reset_matches_oracle(eng):

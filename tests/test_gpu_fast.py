@@ -1,0 +1,221 @@
+"""The guarded float32 iteration (csrc/pd_fast.cuh, pd_step_fast.cu).
+
+Rollouts on the prior / simple rates decide every KMC iteration of
+graphene.py:658-694 in float32 when an error bound allows it and replay the
+control with the float64 code otherwise.  These tests hold that claim to
+'bit for bit': against the float64 kernels of the same library
+(pd_set_fast_path(0)), against the oracle at the benchmarked configurations
+(BASELINE configs[1]: 4096 envs x 256 steps; 1 Mi envs x 8 steps), and through
+pd_fast_path_audit, which measures the float32 quantities against the bounds
+the decisions assume.
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdune_oracle as po
+from oracle import pdune_oracle_episode as oe
+from tests import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+STATE_KEYS = ('si_idx', 'fov', 'ctrl_count', 'sim_time_us', 'n_events',
+              'n_transitions', 'status')
+
+
+@pytest.fixture(scope='module')
+def eng():
+  from putting_dune_b200 import engine
+  return engine
+
+
+@pytest.fixture
+def nat():
+  from putting_dune_b200 import _native
+  yield _native
+  _native.lib.pd_set_fast_path(1)
+
+
+def _rollout(eng, nat, fast, n, seed, ctl, dwell, spec, mode, shift_fov,
+             env_offset=0):
+  nat.lib.pd_set_fast_path(1 if fast else 0)
+  b = eng.EnvBatch(n, seed=seed, env_offset=env_offset)
+  b.reset()
+  if shift_fov:
+    # a FOV the Si is not centred in: the t = 0 safe-area check and the
+    # relative adapter's clip to the frame matter
+    b.fov[::3] += 3.9
+    b.fov[1::7] -= 9.0
+  si, el = b.rollout(ctl, dwell, spec, record=True, action_mode=mode,
+                     max_distance_angstroms=1.42)
+  sd = b.state_dict()
+  return gh.np_(si), gh.np_(el), {k: gh.np_(sd[k]) for k in STATE_KEYS}
+
+
+@pytest.mark.parametrize('n', [37, 700, 4096, 21000, 300000])
+def test_fast_rollout_equals_float64_kernels(eng, nat, n):
+  """k_rollout_fast (small batches) and k_walk_fast (large ones) return what
+  the float64 kernels return: per-step Si site and elapsed time, FOV, clocks,
+  event / transition counts, Philox control counter, status bits."""
+  t_steps, seed = (45 if n < 100000 else 9), 77
+  rng = np.random.default_rng(n)
+  acts = rng.uniform(-1.2, 1.2, size=(t_steps, n, 2))
+  direct = 0.5 + rng.uniform(-0.1, 0.1, size=(t_steps, n, 2))
+  direct[0, :5] = np.nan           # non-finite controls: exact replay
+  direct[1, 5:10] = 1e9
+  direct[2, 10:15] = np.inf
+  far = 0.5 + rng.uniform(-0.6, 0.6, size=(t_steps, n, 2))  # beam off the Si
+  cases = [
+      (po.RATE_PRIOR, 1500000, acts, nat.ACTION_RELATIVE_TO_SILICON, True),
+      (po.RATE_PRIOR, 1500000, acts, nat.ACTION_RELATIVE_TO_SILICON, False),
+      (po.RATE_SIMPLE, 5000000, acts, nat.ACTION_RELATIVE_TO_SILICON, True),
+      (po.RATE_SIMPLE, 700000, direct, nat.ACTION_DIRECT, True),
+      (po.RATE_PRIOR, 30000000, direct, nat.ACTION_DIRECT, False),
+      (po.RATE_PRIOR, 1500000, far, nat.ACTION_DIRECT, False),
+      (po.RATE_SIMPLE, 3, acts, nat.ACTION_RELATIVE_TO_SILICON, False),
+  ]
+  for rate_fn, dwell, ctl, mode, shift in cases:
+    spec = gh.rate_spec(rate_fn)
+    si_a, el_a, st_a = _rollout(eng, nat, True, n, seed, ctl, dwell, spec,
+                                mode, shift)
+    si_b, el_b, st_b = _rollout(eng, nat, False, n, seed, ctl, dwell, spec,
+                                mode, shift)
+    np.testing.assert_array_equal(si_a, si_b)
+    np.testing.assert_array_equal(el_a, el_b)
+    for k in STATE_KEYS:
+      np.testing.assert_array_equal(st_a[k], st_b[k], err_msg=k)
+    if dwell > 1000:
+      assert st_b['n_transitions'].sum() > 0
+
+
+def test_fast_rollout_single_step_and_edge_sites(eng, nat):
+  """One-step rollouts (the fast walk kernel without look-ahead) and a Si that
+  starts on the sheet's edge, where the three nearest sites are not the three
+  bonded ones (geometry class 2: tables instead of the bulk constants)."""
+  n, seed = 5000, 5
+  rng = np.random.default_rng(3)
+  spec = gh.rate_spec(po.RATE_SIMPLE)
+  cls = None
+  for t_steps in (1, 40):
+    acts = rng.uniform(-1, 1, size=(t_steps, n, 2))
+    res = []
+    for fast in (True, False):
+      nat.lib.pd_set_fast_path(1 if fast else 0)
+      b = eng.EnvBatch(n, seed=seed)
+      b.reset()
+      if cls is None:
+        cls = gh.np_(b.lattice_tables.nbr)[:, 3] >> 24
+      edge = np.nonzero(cls == 2)[0]
+      assert edge.size > 50
+      # park every second env's Si on an edge site, FOV centred on it
+      sites = edge[np.arange(n // 2) % edge.size]
+      b.si_idx[::2] = torch.as_tensor(sites.astype(np.int32), device=b.device)
+      xy = gh.np_(b.silicon_position())
+      half = gh.np_(b.fov_scale)[:, None] / 2
+      b.fov.copy_(torch.as_tensor(np.concatenate([xy - half, xy + half], 1),
+                                  device=b.device))
+      si, el = b.rollout(acts, 5000000, spec, record=True,
+                         action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+      sd = b.state_dict()
+      res.append((gh.np_(si), gh.np_(el),
+                  {k: gh.np_(sd[k]) for k in STATE_KEYS}))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    for k in STATE_KEYS:
+      np.testing.assert_array_equal(res[0][2][k], res[1][2][k], err_msg=k)
+    assert res[1][2]['n_transitions'][::2].sum() > 100
+
+
+@pytest.mark.parametrize('rate_fn', [po.RATE_PRIOR, po.RATE_SIMPLE])
+def test_benchmarked_config_vs_oracle(eng, nat, rate_fn):
+  """BASELINE configs[1] exactly as bench.py runs it -- 4096 envs x 256 beam
+  steps, relative_random actions, dwell 1.5 s -- against the oracle's
+  step_and_image for all 1,048,576 env-steps: Si site and elapsed
+  microseconds of every step, final FOV, clocks and counters."""
+  n, t_steps, seed = 4096, 256, 0
+  rng = np.random.default_rng(100)
+  acts = rng.uniform(-1.0, 1.0, size=(t_steps, n, 2))
+  st = po.make_state(n, seed)
+  po.reset(st)
+  nat.lib.pd_set_fast_path(1)
+  b = gh.batch_from_oracle(st)
+  si, el = b.rollout(acts, 1500000, gh.rate_spec(rate_fn), record=True,
+                     action_mode=nat.ACTION_RELATIVE_TO_SILICON,
+                     max_distance_angstroms=1.42)
+  si, el = gh.np_(si), gh.np_(el)
+  for t in range(t_steps):
+    ctl = oe.relative_to_silicon_controls(st, acts[t])[:, None, :]
+    want = po.step_and_image(st, ctl, 1500000, rate_fn=rate_fn)
+    np.testing.assert_array_equal(si[t], st.si_idx, err_msg=f'step {t}')
+    np.testing.assert_array_equal(el[t], want['elapsed_us'],
+                                  err_msg=f'step {t}')
+  np.testing.assert_array_equal(gh.np_(b.n_transitions), st.n_transitions)
+  np.testing.assert_array_equal(gh.np_(b.n_events), st.n_events)
+  np.testing.assert_array_equal(gh.np_(b.sim_time_us), st.sim_time_us)
+  np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+  assert st.n_transitions.sum() > 50000
+
+
+def test_at_scale_config_vs_oracle_sample(eng, nat):
+  """bench.py's at_scale case: 1 Mi envs x 8 steps through k_walk_fast; a
+  block of 65,536 of those envs (Philox is keyed by the global env id)
+  against the oracle, every step."""
+  n, t_steps, seed, lo, m = 1 << 20, 8, 1, 413696, 65536
+  rng = np.random.default_rng(17)
+  acts = rng.uniform(-1.0, 1.0, size=(t_steps, n, 2))
+  nat.lib.pd_set_fast_path(1)
+  b = eng.EnvBatch(n, seed=seed)
+  b.reset()
+  st = po.make_state(m, seed, env_offset=lo)
+  po.reset(st)
+  np.testing.assert_array_equal(gh.np_(b.si_idx[lo:lo + m]), st.si_idx)
+  # identical transform / FOV on both sides (reset's sincos differs by an ulp)
+  b.lattice[lo:lo + m] = torch.as_tensor(st.lattice, device=b.device)
+  b.fov[lo:lo + m] = torch.as_tensor(st.fov, device=b.device)
+  si, el = b.rollout(acts, 1500000, gh.rate_spec(po.RATE_PRIOR), record=True,
+                     action_mode=nat.ACTION_RELATIVE_TO_SILICON,
+                     max_distance_angstroms=1.42)
+  si, el = gh.np_(si[:, lo:lo + m]), gh.np_(el[:, lo:lo + m])
+  for t in range(t_steps):
+    ctl = oe.relative_to_silicon_controls(st, acts[t, lo:lo + m])[:, None, :]
+    want = po.step_and_image(st, ctl, 1500000, rate_fn=po.RATE_PRIOR)
+    np.testing.assert_array_equal(si[t], st.si_idx, err_msg=f'step {t}')
+    np.testing.assert_array_equal(el[t], want['elapsed_us'])
+  np.testing.assert_array_equal(gh.np_(b.n_events[lo:lo + m]), st.n_events)
+  assert st.n_transitions.sum() > 30000
+
+
+@pytest.mark.parametrize('rate_fn,dwell,dist', [
+    (po.RATE_PRIOR, 1500000, 1.42), (po.RATE_SIMPLE, 1500000, 1.42),
+    (po.RATE_PRIOR, 5000000, 1.42), (po.RATE_SIMPLE, 200000, 1.42),
+    (po.RATE_PRIOR, 1500000, 4.0), (po.RATE_SIMPLE, 60000000, 6.0)])
+def test_fast_path_audit(eng, nat, rate_fn, dwell, dist):
+  """5e7 random iterations per case: no decided iteration differs from the
+  float64 code, the exact waiting time always lies inside the float32
+  interval, and the largest observed errors stay well below the bounds the
+  decisions assume (the printed ratios are the safety factors DESIGN.md
+  quotes)."""
+  lat = eng.Lattice(50)
+  out = nat.PdFastAudit()
+  nat.check(nat.lib.pd_fast_path_audit(C.byref(lat.c), rate_fn, 12345,
+                                       50_000_000, dwell, dist, C.byref(out),
+                                       None))
+  print(f'audit rate={rate_fn} dwell={dwell} dist={dist}: '
+        f'no_hop={out.no_hop} hop={out.hop} unsure={out.unsure} '
+        f'tot={out.total_rate_error_over_bound:.3f} '
+        f't={out.waiting_time_error_over_bound:.3f} '
+        f'choice={out.choice_error_over_bound:.3f} '
+        f'draw_abs={out.draw_error_abs_max:.3e} (bound '
+        f'{out.draw_error_bound:.1e})')
+  assert out.samples == 50_000_000
+  assert out.wrong_decision == 0 and out.wrong_slot == 0
+  assert out.waiting_time_outside_bounds == 0
+  assert out.total_rate_error_over_bound < 0.5
+  assert out.waiting_time_error_over_bound < 0.6
+  assert out.choice_error_over_bound < 0.5
+  assert out.draw_error_abs_max < 0.5 * out.draw_error_bound
+  assert out.unsure < 0.01 * out.samples
+  assert out.hop > 0.01 * out.samples
