@@ -12,12 +12,14 @@ env-steps per launch.  Environments shard across GPUs by global env id with no
 data-path collective (weak scaling: per-GPU work fixed).
 
 Printed line (rank 0): see DESIGN.md "Measurement".  `value` is device-timed
-whole-job env-steps/s with the action stream resident in HBM; `e2e` is the same
-metric through the host-buffer C-ABI call (pinned host controls copied in,
-per-step Si sites and clocks copied out, every step); `roofline` uses SURVEY.md
+whole-job env-steps/s with the action stream resident in HBM and the per-step
+observation (Si site, elapsed microseconds) written for every env-step; `e2e`
+is the same metric through the host-buffer C-ABI call (pinned host actions
+copied in, per-step results copied out, every step); `roofline` uses SURVEY.md
 section 8(d)'s 64 algorithmic bytes per env-step against the measured HBM copy
-bandwidth in MEASURED_PEAKS.json; `cpu_baseline` is the oracle port timed on
-this box's host cores.
+bandwidth in MEASURED_PEAKS.json and carries the issue-slot figure beside it;
+`cpu_baseline` is the UNMODIFIED reference simulator (baseline/_ref) timed on
+this box's host cores, with the NumPy port of the oracle next to it.
 """
 
 import argparse
@@ -64,9 +66,10 @@ def parse_args():
   ap.add_argument('--frames', type=int, default=16384,
                   help='frames per render launch (512x512; BASELINE '
                        'configs[3]: 16384 envs per step = 17.2 GB of frames)')
-  ap.add_argument('--episodes', type=int, default=0,
-                  help='total envs for the greedy-controller episode run '
-                       '(configs[4] uses 1048576); 0 = skip')
+  ap.add_argument('--episodes', type=int, default=1 << 20,
+                  help='total envs of the greedy-controller episode run, '
+                       'sharded over the GPUs, stats all-gathered (BASELINE '
+                       'configs[4]: 1048576); 0 = skip')
   ap.add_argument('--cpu-seconds', type=float, default=12.0)
   return ap.parse_args()
 
@@ -202,40 +205,74 @@ def cpu_port_throughput(n_envs, rate_fn, seconds, cores):
   return total / busy, sample, wall
 
 
+def reference_throughput(seconds, cores, rate):
+  """env-steps/s of the UNMODIFIED reference (oracle/refbench.py: its own
+  PuttingDuneSimulator, KD-tree, rate functions, adapter and
+  np.random.default_rng) on `cores` processes, one env each, for about
+  `seconds`; None if the reference sources are not on this box."""
+  from oracle import refbench
+  if not refbench.reference_available():
+    return None
+  refbench.run_steps(20, 0, rate)  # imports + first-call costs, once
+  n_steps = int(max(50, min(5000, 230 * seconds)))  # ~230-300 steps/s/core
+  v, busy, hops, sample = refbench.throughput(n_steps, cores, rate)
+  return {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+          'sample': sample}
+
+
 def run_reference_arm(args, cfg):
+  """The reference's own CPU implementation of the path on all host cores:
+  the unmodified PuttingDuneSimulator from baseline/_ref, one env per process
+  (it has no batch dimension: configs[1]'s 4096 envs are 4096 such
+  simulators, so env-steps/s is the same per-core figure), each timed step a
+  bounded sample.  The NumPy port of the oracle, vectorised over the 4096
+  envs, is reported beside it."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   from oracle import pdune_oracle as po
+  from oracle import refbench
   rate_fn = po.RATE_PRIOR if args.rate == 'prior' else po.RATE_SIMPLE
   cores = os.cpu_count() or 1
   n_envs = cfg['envs_per_gpu']
-  per_step_budget = 6.0
+  have_ref = refbench.reference_available()
   vals, samples, walls = [], [], []
   t_all = time.perf_counter()
   for i in range(args.warmup + args.steps):
-    v, s, w = cpu_port_throughput(n_envs, rate_fn, per_step_budget, cores)
+    t0 = time.perf_counter()
+    if have_ref:
+      r = reference_throughput(2.0, cores, args.rate)
+      v, smp = r['value'], r['sample']
+    else:
+      v, smp, _ = cpu_port_throughput(n_envs, rate_fn, 6.0, cores)
     if i >= args.warmup:
       vals.append(v)
-      samples.append(s)
-      walls.append(w)
+      samples.append(smp)
+      walls.append(time.perf_counter() - t0)
     if time.perf_counter() - t_all > 240:
       break
   value = float(np.mean(vals)) if vals else 0.0
+  port_v, port_sample, _ = cpu_port_throughput(n_envs, rate_fn, 6.0, cores)
+  kind = 'reference' if have_ref else 'port'
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
       'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
-      'ms_per_step': 1e3 * float(np.mean(walls)) if walls else None, 'higher_is_better': True,
+      'ms_per_step': 1e3 * float(np.mean(walls)) if walls else None,
+      'higher_is_better': True,
       'scaling': cfg['scaling'], 'vs_baseline': None, 'dtype': 'f64',
       'data': 'synthetic', 'config': cfg,
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores,
-                       'kind': 'port', 'sample': samples[-1] if samples else ''},
+                       'kind': kind, 'sample': samples[-1] if samples else ''},
+      'cpu_port': {'value': port_v, 'unit': UNIT, 'cores': cores,
+                   'kind': 'port', 'sample': port_sample},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
-      'note': ('the Python reference cannot travel to the GPU box; this is '
-               'oracle/pdune_oracle.py (pinned against the unmodified '
-               'reference) on all host cores; the unmodified reference '
-               'measured 386 env-steps/s on one core (SURVEY.md section 6)'),
+      'note': ('unmodified reference simulator from baseline/_ref on all host '
+               'cores (oracle/refbench.py); cpu_port = oracle/pdune_oracle.py, '
+               'the NumPy restatement vectorised over the envs'
+               if have_ref else
+               'reference sources not on this box: oracle/pdune_oracle.py '
+               '(NumPy port, pinned against the unmodified reference)'),
   }
   print(json.dumps(line), flush=True)
 
@@ -259,6 +296,84 @@ def ncu_traffic(summary_name):
       unit = k[k.index('[') + 1:k.index(']')]
       total += float(v) * scale.get(unit, 1.0)
   return total or None
+
+
+def ncu_value(summary_name, key):
+  """One metric of a committed ncu summary (profiles/*.ncu.json), or None."""
+  path = os.path.join(ROOT, 'profiles', summary_name)
+  try:
+    d = json.load(open(path))
+  except (OSError, ValueError):
+    return None
+  for k, v in d.items():
+    if k.startswith(key):
+      try:
+        return float(v)
+      except ValueError:
+        return None
+  return None
+
+
+def issue_slots(warp_instructions, seconds, sm_mhz, sms=148):
+  """Issue-slot roofline: warp-instructions of one launch over the issue
+  slots the launch had (4 schedulers per SM, one issue per cycle each)."""
+  if not warp_instructions or not sm_mhz:
+    return None
+  slots = 4 * sms * sm_mhz * 1e6 * seconds
+  return {'warp_instructions_per_launch': warp_instructions,
+          'schedulers': 4 * sms, 'sm_mhz': sm_mhz,
+          'frac': warp_instructions / slots,
+          'source': 'smsp__inst_executed.sum of the committed ncu summary / '
+                    '(schedulers x SM clock x measured launch time)'}
+
+
+def bind_to_gpu_numa(index):
+  """Pins this process (and so the pinned buffers it first touches) to the
+  CPUs next to GPU `index` (NVML affinity); returns the CPU count or None."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(index)
+    words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+    cpus = [64 * i + b for i, w in enumerate(words) for b in range(64)
+            if (w >> b) & 1]
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return len(cpus)
+  except Exception:  # pylint: disable=broad-except
+    return None
+  return None
+
+
+def measure_link(dev, mb=64):
+  """Pinned-memory copy rates of this box's host link in the same run: H2D
+  alone, D2H alone, and both at once (GB/s per direction)."""
+  import torch
+  n = mb << 20
+  h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+  h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+  d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+  d_out = torch.zeros(n, dtype=torch.uint8, device=dev)
+  s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+  def timed(h2d, d2h):
+    best = 1e9
+    for _ in range(4):
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      if h2d:
+        with torch.cuda.stream(s1):
+          d_in.copy_(h_in, non_blocking=True)
+      if d2h:
+        with torch.cuda.stream(s2):
+          h_out.copy_(d_out, non_blocking=True)
+      torch.cuda.synchronize()
+      best = min(best, time.perf_counter() - t0)
+    return n / best / 1e9
+
+  return {'h2d_gbs': timed(True, False), 'd2h_gbs': timed(False, True),
+          'both_gbs_per_direction': timed(True, True), 'mbytes': mb,
+          'how': 'pinned cudaMemcpyAsync, best of 4, host wall clock'}
 
 
 def measured_peak():
@@ -410,24 +525,38 @@ def measure_episodes(pd, args, world, rank, dev, barrier):
   lo, n = ep.shard_bounds(args.episodes, rank, world)
   b = pd.EnvBatch(n, seed=5, env_offset=lo, device=dev)
   rate = pd.RateSpec.simple()
-  ep.run_greedy_episodes(b, rate)  # warm-up
+  stats, _, _ = ep.run_greedy_episodes(b, rate)  # warm-up
+  ep.gather_episode_stats(stats)
   barrier()
-  s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(
-      enable_timing=True)
-  s.record()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+  ev[0].record()
   stats, _, _ = ep.run_greedy_episodes(b, rate)
+  ev[1].record()
   full = ep.gather_episode_stats(stats)
-  e.record()
+  ev[2].record()
   barrier()
-  tm = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+  tm = torch.tensor([ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])],
+                    dtype=torch.float64, device=dev)
   if world > 1:
     import torch.distributed as dist
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
   agg = ep.aggregate_results(full)
-  ms = float(tm.item())
+  ms, gather_ms = float(tm[0].item()), float(tm[1].item())
+  import hashlib
+  digest = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16]
   agg.update(launch_ms=ms, env_steps_per_s=agg['total_actions'] / (ms / 1e3),
-             collective='all_gather of 16 B/env episode records',
-             rate_function='simple', controller='GreedyAgent argmax (1.42, 0)')
+             allgather_us=gather_ms * 1e3 if world > 1 else 0.0,
+             collective=('NCCL all_gather of 16 B/env episode records '
+                         f'({16 * args.episodes / 1e6:.1f} MB total)'
+                         if world > 1 else 'none (one rank)'),
+             records_sha256_16=digest,
+             note='records_sha256_16 is over the gathered per-env records: '
+                  'identical for every number of GPUs (Philox is keyed by '
+                  'the global env id)',
+             rate_function='simple', controller='GreedyAgent argmax (1.42, 0)',
+             workload='configs[4]: %d envs sharded over %d GPU(s), greedy '
+                      'goal-reaching controller, step limit 600, 10 simulated '
+                      'minutes' % (args.episodes, world))
   return agg
 
 
@@ -444,6 +573,7 @@ def run_ours(args, cfg):
     raise SystemExit('bench.py needs a GPU: there is no CPU fallback')
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
+  numa_cpus = bind_to_gpu_numa(local)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
@@ -465,11 +595,16 @@ def run_ours(args, cfg):
   stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
   P = lambda t: C.c_void_p(t.data_ptr())
 
+  # the per-step observation of every env-step is part of the timed call:
+  # Si site (int32) and MicroscopeObservation.elapsed_time (int64 us)
+  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
+  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
+
   def launch(i):
     nat.check(nat.lib.pd_rollout_actions(
         lat_c, st_c, C.byref(rate.c), P(d_ctl[i % pool]),
         nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
-        None, None, stream))
+        P(d_si), P(d_el), stream))
 
   # -- device-resident: value -----------------------------------------------
   for i in range(args.warmup):
@@ -499,8 +634,6 @@ def run_ours(args, cfg):
 
   # -- end to end through the host-buffer C ABI -------------------------------
   d_stage = torch.empty((t_steps, n, 2), dtype=torch.float64, device=dev)
-  d_si = torch.empty((t_steps, n), dtype=torch.int32, device=dev)
-  d_el = torch.empty((t_steps, n), dtype=torch.int64, device=dev)
   h_si = torch.empty((t_steps, n), dtype=torch.int32).pin_memory()
   h_el = torch.empty((t_steps, n), dtype=torch.int64).pin_memory()
 
@@ -549,28 +682,42 @@ def run_ours(args, cfg):
         P(d_a32), P(d_stage), P(d_si), P(d_el), P(d_el32), P(h_si), P(h_el32),
         stream))
 
-  e2e_value = time_host(launch_host32)
+  e2e_f32 = time_host(launch_host32)
+  # packed results: uint16 Si site | re-centred << 15 (the elapsed time is
+  # dwell + image * (1 + re-centred)): 8 B in + 2 B out per env-step
+  h_packed = torch.empty((t_steps, n), dtype=torch.uint16).pin_memory()
+
+  def launch_packed(i):
+    nat.check(nat.lib.pd_rollout_actions_host_packed(
+        lat_c, st_c, C.byref(rate.c), P(h_ctl32[i % pool]),
+        nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US, t_steps, IMAGE_US,
+        P(h_packed), stream))
+
+  e2e_value = time_host(launch_packed)
   h2d = h_ctl32[0].numel() * 4
-  d2h = h_si.numel() * 4 + h_el32.numel() * 4
+  d2h = h_packed.numel() * 2
+  link = measure_link(dev) if rank == 0 else None
 
   # -- roofline of the dominant kernel ----------------------------------------
   peak, peak_kind = measured_peak()
   launch_s = dev_ms / 1e3 / args.steps
   achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * env_steps_per_launch / launch_s / 1e9
   roofline = {
-      'kernel': 'pd::k_rollout_pre', 'bound': 'hbm', 'achieved': achieved,
+      'kernel': 'pd::k_rollout_fast', 'bound': 'hbm', 'achieved': achieved,
       'peak': peak, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
       'unit': 'GB/s', 'frac': achieved / peak,
       'algorithmic_bytes_per_env_step': ALGORITHMIC_BYTES_PER_ENV_STEP,
       'env_steps_per_launch': env_steps_per_launch,
       'launch_ms': launch_s * 1e3,
       # ncu --set full of the same workload (profiles/
-      # r01_k_rollout_pre_config2): the state stays in registers across the
-      # 256 steps, so DRAM traffic is the action stream (16 B/env-step), below
-      # the 64 B algorithmic figure
-      'traffic': ncu_traffic('r01_k_rollout_pre_config2.ncu.json')
+      # r02_k_rollout_fast_config2): the state stays in registers across the
+      # 256 steps, so DRAM traffic is the action stream in (16 B/env-step)
+      # and the observations out (12 B/env-step), below the 64 B figure
+      'traffic': ncu_traffic('r02_k_rollout_fast_config2.ncu.json')
       if cfg['envs_per_gpu'] == 4096 and t_steps == 256 else None,
   }
+  issue_src = ('r02_k_rollout_fast_config2.ncu.json'
+               if cfg['envs_per_gpu'] == 4096 and t_steps == 256 else None)
 
   # -- the same kernel family with every SM filled (1Mi envs, one step) -------
   at_scale = None
@@ -581,11 +728,13 @@ def run_ours(args, cfg):
     big.reset()
     acts = [torch.as_tensor(synthetic_controls(big_n, 1, 7 + i)).to(dev)
             for i in range(pool)]
+    b_si = torch.empty((8, big_n), dtype=torch.int32, device=dev)
+    b_el = torch.empty((8, big_n), dtype=torch.int64, device=dev)
     def big_launch(i):
       nat.check(nat.lib.pd_rollout_actions(
           C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
           P(acts[i % pool]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US,
-          1, IMAGE_US, None, None, stream))
+          1, IMAGE_US, P(b_si), P(b_el), stream))
     for i in range(3):
       big_launch(i)
     torch.cuda.synchronize()
@@ -602,9 +751,10 @@ def run_ours(args, cfg):
     at_scale = {
         'workload': '1Mi envs x 1 step per launch, same actions/adapter, '
                     '1 GPU',
-        'kernel': 'pd::k_walk', 'value': big_n / (ms / 1e3), 'unit': UNIT,
+        'kernel': 'pd::k_walk_fast', 'value': big_n / (ms / 1e3), 'unit': UNIT,
+        'outputs': 'Si site int32 + elapsed us int64 per env-step',
         'launch_ms': ms, 'achieved': a_gbs, 'peak': peak, 'frac': a_gbs / peak,
-        'traffic': ncu_traffic('r01_k_walk_1Mi_1step.ncu.json')}
+        'traffic': ncu_traffic('r02_k_walk_fast_1Mi_1step.ncu.json')}
     # the same batch in 8-step rollouts (state read and written once per 8)
     acts8 = [torch.as_tensor(synthetic_controls(big_n, 8, 17 + i)).to(dev)
              for i in range(2)]
@@ -612,7 +762,7 @@ def run_ours(args, cfg):
       nat.check(nat.lib.pd_rollout_actions(
           C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
           P(acts8[i % 2]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US,
-          8, IMAGE_US, None, None, stream))
+          8, IMAGE_US, P(b_si), P(b_el), stream))
     for i in range(2):
       big_launch8(i)
     torch.cuda.synchronize()
@@ -627,10 +777,14 @@ def run_ours(args, cfg):
     ms8 = sum(a.elapsed_time(b) for a, b in bev) / 6
     g8 = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n * 8 / (ms8 / 1e3) / 1e9
     at_scale['rollout8'] = {
-        'workload': '1Mi envs x 8 steps per launch', 'kernel': 'pd::k_walk',
+        'workload': '1Mi envs x 8 steps per launch',
+        'kernel': 'pd::k_walk_fast',
         'value': big_n * 8 / (ms8 / 1e3), 'unit': UNIT, 'launch_ms': ms8,
-        'achieved': g8, 'peak': peak, 'frac': g8 / peak}
-    del big, acts8
+        'achieved': g8, 'peak': peak, 'frac': g8 / peak,
+        'traffic': ncu_traffic('r02_k_walk_fast_1Mi_8step.ncu.json'),
+        'warp_instructions': ncu_value('r02_k_walk_fast_1Mi_8step.ncu.json',
+                                       'smsp__inst_executed.sum')}
+    del big, acts8, b_si, b_el
 
   # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
   frames = None
@@ -658,13 +812,27 @@ def run_ours(args, cfg):
     from oracle import pdune_oracle as po
     rate_fn = po.RATE_PRIOR if args.rate == 'prior' else po.RATE_SIMPLE
     v, sample, _ = cpu_port_throughput(n, rate_fn, args.cpu_seconds, 1)
-    cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-           'sample': sample}
+    port = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': sample}
+    # the unmodified reference simulator (BASELINE configs[0]) on one core
+    cpu = reference_throughput(args.cpu_seconds, 1, args.rate)
+    if cpu is None:
+      cpu = port
+    else:
+      cpu['port'] = port
 
   # clocks over every timed GPU region of this run (value, e2e, at_scale ...)
   if sampler:
     clocks = sampler.stop(t0, time.perf_counter())
   if rank == 0:
+    sm_mhz = (clocks or {}).get('sm_mhz') or (clocks or {}).get('sm_max_mhz')
+    roofline['issue_slots'] = issue_slots(
+        ncu_value(issue_src, 'smsp__inst_executed.sum') if issue_src else None,
+        launch_s, sm_mhz)
+    if at_scale and at_scale.get('rollout8'):
+      r8 = at_scale['rollout8']
+      r8['issue_slots'] = issue_slots(r8.pop('warp_instructions'),
+                                      r8['launch_ms'] / 1e3, sm_mhz)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup,
@@ -675,12 +843,22 @@ def run_ours(args, cfg):
                 'd2h_bytes_per_step': d2h,
                 'timing': f'median of {E2E_REPEATS} timings of {args.steps} '
                           'calls each, host wall clock, max over ranks',
-                'api': 'pd_rollout_actions_host_f32 (pinned host buffers: '
+                'api': 'pd_rollout_actions_host_packed (pinned host buffers: '
                        'float32 actions in = the adapters\' action_spec '
-                       'dtype, int32 Si site + int32 elapsed us out; one '
-                       'k_rollout_pre<STREAM> launch that follows the H2D '
-                       'copy of the actions while writer CTAs stream the '
-                       'result rows to the host buffers)',
+                       'dtype; one uint16 per env-step out = Si site | '
+                       're-centred << 15, from which elapsed = dwell + image '
+                       '* (1 + re-centred); copy-engine chunks of whole '
+                       'steps that the k_rollout_fast launches and the '
+                       'result copies follow)',
+                'link': link, 'numa_bound_cpus': numa_cpus,
+                'f32_int32_io': {
+                    'value': e2e_f32, 'unit': UNIT,
+                    'h2d_bytes_per_step': h_ctl32[0].numel() * 4,
+                    'd2h_bytes_per_step': h_si.numel() * 4 +
+                                          h_el32.numel() * 4,
+                    'api': 'pd_rollout_actions_host_f32 (int32 Si site + '
+                           'int32 elapsed us out; one k_rollout_pre<STREAM> '
+                           'launch that follows the H2D copy)'},
                 'float64_io': {
                     'value': e2e_f64, 'unit': UNIT,
                     'h2d_bytes_per_step': h_ctl[0].numel() * 8,
@@ -688,7 +866,10 @@ def run_ours(args, cfg):
                     'api': 'pd_rollout_actions_host (float64 actions, int64 '
                            'elapsed us; the same streamed launch, '
                            'k_rollout_pre<STREAM = 2>)'}},
-        'gpu_launches': args.steps, 'roofline': roofline,
+        'gpu_launches': args.steps,
+        'value_outputs': 'Si site int32 + elapsed us int64 written for every '
+                         'env-step inside the timed launch',
+        'roofline': roofline,
         'cpu_baseline': cpu, 'at_scale': at_scale, 'frames': frames,
         'episodes': episodes, 'learned_mlp': mlp, 'export': export,
         'wall_s_timed_region': t1 - t0,

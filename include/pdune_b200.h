@@ -338,6 +338,24 @@ int pd_rollout_actions_host_f32(
     int32_t* d_si_idx, int64_t* d_elapsed_us, int32_t* d_elapsed_us32,
     int32_t* h_si_idx, int32_t* h_elapsed_us32, void* stream);
 
+/* Packed host format of the same call (prior / simple rates, one positive
+ * dwell time below 3000 s, at most 32768 lattice sites): float32 actions
+ * [n_steps][n][2] in, one uint16 per env-step out, [n_steps][n]:
+ *   bits 0-14  Si lattice site after the step,
+ *   bit 15     the step re-centred the FOV (simulator.py:156-169),
+ * from which MicroscopeObservation.elapsed_time follows as dwell + image
+ * duration * (1 + bit 15) (simulator.py:131-169).  8 + 2 bytes per env-step
+ * cross PCIe instead of 8 + 8.  The library keeps the device stagings; the
+ * action stream goes through the copy engines in a few chunks of whole steps
+ * that the stepping kernels and the result copies follow (no kernel reads a
+ * buffer a copy is still writing).  Page-locked host buffers make the copies
+ * asynchronous; pageable ones work.  Synchronises `stream`. */
+int pd_rollout_actions_host_packed(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const float* h_actions_xy, int32_t action_mode,
+    double max_distance_angstroms, int64_t dwell_us_scalar, int32_t n_steps,
+    int64_t image_duration_us, uint16_t* h_packed, void* stream);
+
 /* ---- the guarded float32 iteration (rollouts on the prior / simple rates).
  * pd_rollout_actions with one positive dwell time below 3000 s decides every
  * iteration of graphene.py:658-694 (hop or not, which neighbour) in float32
@@ -363,9 +381,8 @@ typedef struct pd_fast_audit {
   double waiting_time_error_over_bound;
   double choice_error_over_bound;
   /* the float32 unit-exponential draw against float64 over all 2^24 values
-   * of its 24-bit uniform (exhaustive), and the bound assumed for it */
-  double draw_error_abs_max;
-  double draw_error_bound;
+   * of its 24-bit uniform (exhaustive), over the bound assumed for it */
+  double draw_error_over_bound;
 } pd_fast_audit;
 int pd_fast_path_audit(const pd_lattice* lat, int32_t rate_fn, uint64_t seed,
                        int64_t n_samples, int64_t dwell_us,

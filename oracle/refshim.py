@@ -29,7 +29,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('PDUNE_REFERENCE_ROOT', '/root/reference')
+def _default_root() -> str:
+  # /root/reference in the build container; on the GPU box the plain copy of
+  # the reference's package that __graft_entry__.build() leaves under
+  # baseline/_ref (git-ignored, travels with gpurun).
+  if os.path.isdir('/root/reference/putting_dune'):
+    return '/root/reference'
+  here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  return os.path.join(here, 'baseline', '_ref')
+
+
+REFERENCE_ROOT = os.environ.get('PDUNE_REFERENCE_ROOT', _default_root())
 
 
 def reference_available() -> bool:

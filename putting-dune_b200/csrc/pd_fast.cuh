@@ -24,8 +24,9 @@
 // The reference's own float32 steps (cast of the rates, sequential sum,
 // reciprocal: 3e-7) are inside the same bound.  The unit-exponential draw
 // uses the top 24 bits u24 of the 53-bit uniform: 1 - u24 is exact,
-// lg2.approx is good to 2^-22.6 absolute (1.1e-7 after the ln 2), and the
-// dropped bits move the draw up by < 2^-24 / (1 - u).  pd_fast_path_audit
+// -ln 2 lg2.approx(1 - u24) is good to 3e-7 absolute (measured over all 2^24
+// values by pd_fast_path_audit), and the dropped bits move the draw up by
+// < 6.1e-8 / (1 - u) while 1 - u > 2^-12 (no upper bound is claimed beyond).  pd_fast_path_audit
 // (pd_step_fast.cu) measures all of these against the exact path.
 #pragma once
 
@@ -35,7 +36,8 @@ namespace pd {
 
 constexpr float kFastEps0 = 5e-5f;       // relative bound of the total rate
 constexpr float kFastEps1 = 4e-6f;       // ... per unit of the prior's exponent
-constexpr float kFastDrawAbs = 8e-7f;    // absolute bound of -log(1 - u24)
+constexpr float kFastDrawAbs = 6e-7f;    // absolute bound of -log(1 - u24)
+                                         // (+ 1e-6 relative, inside the slack)
 constexpr float kFastMaxDwellS = 3000.f; // below graphene.py:668's 3600 s cap
 
 enum : int { FAST_NO_HOP = 0, FAST_HOP = 1, FAST_UNSURE = 2 };
@@ -97,6 +99,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // and no table is touched; everything is evaluated in float64 and rounded
 // once.
 // ---------------------------------------------------------------------------
+// Scale of the beam offset that fast_event expects: bond units for the prior,
+// angstrom for the simple rate.
+template <int RATE>
+__device__ __forceinline__ float fast_offset_scale() {
+  return RATE == PD_RATE_PRIOR ? static_cast<float>(1.0 / kBond) : 1.0f;
+}
+
 struct FastGeo {
   float gx[3], gy[3];
 };
@@ -182,21 +191,34 @@ __device__ __forceinline__ FastSite fast_site(const Tables& tab, int si,
 template <int RATE, class Tables, class LoadRotation>
 __device__ __forceinline__ void fast_hop(const Tables& tab, int slot,
                                          LoadRotation rotation, FastSite* f,
-                                         float* bx, float* by) {
-  const float gx = slot == 0 ? f->geo.gx[0]
-                             : (slot == 1 ? f->geo.gx[1] : f->geo.gx[2]);
-  const float gy = slot == 0 ? f->geo.gy[0]
-                             : (slot == 1 ? f->geo.gy[1] : f->geo.gy[2]);
-  if (RATE == PD_RATE_PRIOR) {
-    // peak = 0.85 (ux, -uy) of the unit vector u towards the neighbour
-    *bx -= gx * (1.0f / 0.85f);
-    *by += gy * (1.0f / 0.85f);
-  } else {
-    *bx -= gx;
-    *by -= gy;
-  }
+                                         float* bx, float* by, float* ox,
+                                         float* oy) {
   const int to = slot == 0 ? f->nb[0] : (slot == 1 ? f->nb[1] : f->nb[2]);
   const int cls_old = f->cls;
+  // (*ox, *oy): the neighbour's offset in angstrom
+  if (cls_old < 2) {
+    const float gx = slot == 0 ? f->geo.gx[0]
+                               : (slot == 1 ? f->geo.gx[1] : f->geo.gx[2]);
+    const float gy = slot == 0 ? f->geo.gy[0]
+                               : (slot == 1 ? f->geo.gy[1] : f->geo.gy[2]);
+    if (RATE == PD_RATE_PRIOR) {
+      // bulk: a bond vector; peak = 0.85 (ux, -uy) of its unit vector u
+      *ox = gx * static_cast<float>(kBond / 0.85);
+      *oy = -gy * static_cast<float>(kBond / 0.85);
+    } else {
+      *ox = gx;
+      *oy = gy;
+    }
+  } else {
+    // sheet edge: the nearest sites need not be a bond away
+    const double2 cs = rotation();
+    const double2 b0 = tab.position(f->si), b1 = tab.position(to);
+    const double dx = b1.x - b0.x, dy = b1.y - b0.y;
+    *ox = static_cast<float>(dx * cs.x + dy * cs.y);
+    *oy = static_cast<float>(dy * cs.x - dx * cs.y);
+  }
+  *bx -= *ox * fast_offset_scale<RATE>();
+  *by -= *oy * fast_offset_scale<RATE>();
   f->si = to;
   f->cls = tab.neighbors_class(to, f->nb);
   if (cls_old < 2 && f->cls < 2) {
@@ -213,13 +235,6 @@ __device__ __forceinline__ void fast_hop(const Tables& tab, int slot,
     f->geo = fast_geo_any<RATE>(tab, to, f->nb[0], f->nb[1], f->nb[2], f->cls,
                                 cs.x, cs.y);
   }
-}
-
-// Scale of the beam offset that fast_event expects: bond units for the prior,
-// angstrom for the simple rate.
-template <int RATE>
-__device__ __forceinline__ float fast_offset_scale() {
-  return RATE == PD_RATE_PRIOR ? static_cast<float>(1.0 / kBond) : 1.0f;
 }
 
 // ---------------------------------------------------------------------------
@@ -283,7 +298,11 @@ __device__ __forceinline__ int fast_event(const FastGeo& g, float bx, float by,
   const float t_mid = draw * rc;
   const float slack = __fmaf_rn(t_mid, eps + 1e-6f, kFastDrawAbs * rc);
   *t_lo = t_mid - slack;
-  *t_hi = (t_mid + slack) + (6.0e-8f * rcp_approx(v)) * rc;
+  // the bits dropped from the uniform raise the draw by -log(1 - d / v),
+  // d < 2^-24: below 6.1e-8 / v while v > 2^-12, unbounded as v -> 2^-24
+  const float dropped =
+      v > 2.5e-4f ? 6.1e-8f * rcp_approx(v) : __int_as_float(0x7f800000);
+  *t_hi = (t_mid + slack) + dropped * rc;
   // A vanishing total rate (beam far away; float32 underflow of the prior is
   // routine) means a waiting time of hours whatever the
   // error, unless the draw is exactly zero.

@@ -585,6 +585,8 @@ struct StepArgs {
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]
   int64_t* elapsed_us_out;    // rollout [T][n]
+  uint16_t* packed_out;       // rollout [T][n]: Si site | re-centred << 15
+                              // (fast kernels, with actions_f32 as the input)
   // streamed host rollout (k_rollout_pre<.., STREAM>): the float32 actions
   // are still arriving (one copy-engine H2D copy into a staging pre-filled
   // with 0xFF) while the launch runs, and the CTAs of a few SMs write the

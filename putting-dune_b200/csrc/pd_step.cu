@@ -1592,8 +1592,7 @@ static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
 
 // pd_step_fast.cu: the guarded float32 kernels (prior / simple rates).
 template <int RATE>
-int launch_fast(const StepArgs& a, bool walk, bool staged, int grid,
-                cudaStream_t stream);
+int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream);
 
 // PD_FAST=0 keeps every iteration on the float64 chain (A/B timing; the
 // parity tests compare the two).
@@ -1628,16 +1627,15 @@ static int launch_step(const StepArgs& a_in, bool rollout,
     // in float32 with an error bound, exact replay of what it cannot settle.
     if (rollout && !a.stream_mode && fast_enabled() && a.dwell_us_scalar > 0 &&
         a.dwell_us_scalar < 3000LL * 1000000LL && !a.skip) {
-      // The tables are read through L1 (a hop touches one 16-byte row, 10 % of
-      // the iterations): staging them would cost more than it saves and take
-      // the shared memory the action stream's L1 lines need.
-      static const bool stage_fast = env_int("PD_FAST_STAGE", 0) != 0;
-      const bool st = staged && stage_fast;
       if (walk || !spec)
-        return launch_fast<RATE>(a, true, st, grid_for(a.st.n_envs, true),
-                                 stream);
-      return launch_fast<RATE>(a, false, st, grid, stream);
+        return launch_fast<RATE>(a, true, grid_for(a.st.n_envs, true), stream);
+      return launch_fast<RATE>(a, false, grid, stream);
     }
+  }
+  if (a.packed_out) {
+    set_error("the packed rollout format needs the prior / simple rates, one "
+              "positive dwell time below 3000 s and pd_set_fast_path(1)");
+    return PD_ERR_UNSUPPORTED;
   }
   if (a.stream_mode) {
     // streamed host rollout: the caller went through stream_plan
@@ -2570,6 +2568,132 @@ extern "C" int pd_rollout_actions_host_f32(
       PD_CUDA_OK(cudaMemcpyAsync(h_elapsed_us32 + off, d_elapsed_us32 + off,
                                  static_cast<size_t>(items) * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, pipe->d2h));
+  }
+  PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+  PD_CUDA_OK(cudaStreamSynchronize(s));
+  return PD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Packed host format: float32 actions in, one uint16 per env-step out (Si site
+// | re-centred << 15; the elapsed time of a step is dwell + image duration *
+// (1 + re-centred), simulator.py:131-169).  8 + 2 instead of 8 + 8 bytes per
+// env-step cross PCIe.  Copy-engine pipeline: the action stream goes in as a
+// few chunks of whole steps, the fast kernels (pd_step_fast.cu) run chunk c
+// while chunk c + 1 is on the wire and the results of chunk c - 1 leave; what
+// is left over at the end is the last (short) chunk's launch and its D2H copy.
+// ---------------------------------------------------------------------------
+extern "C" int pd_rollout_actions_host_packed(
+    const pd_lattice* lat, const pd_state* st, const pd_rate_config* rc,
+    const float* h_actions_xy, int32_t action_mode,
+    double max_distance_angstroms, int64_t dwell_us_scalar, int32_t n_steps,
+    int64_t image_duration_us, uint16_t* h_packed, void* stream) {
+  PD_REQUIRE(action_mode == PD_ACTION_DIRECT ||
+                 action_mode == PD_ACTION_RELATIVE_TO_SILICON,
+             "unknown action_mode");
+  int rcode = pd::validate_common(lat, st, rc);
+  if (rcode != PD_OK) return rcode;
+  PD_REQUIRE(rc != nullptr, "null rate config");
+  PD_REQUIRE(n_steps >= 0, "negative n_steps");
+  PD_REQUIRE(dwell_us_scalar >= 0 && image_duration_us >= 0, "negative time");
+  PD_REQUIRE(lat->n_sites <= 32768, "site ids do not fit 15 bits");
+  const int64_t n = st->n_envs;
+  if (n == 0 || n_steps == 0) return PD_OK;
+  PD_REQUIRE(h_actions_xy && h_packed, "null host buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pd::HostPipeline* pipe = nullptr;
+  rcode = pd::host_pipeline(&pipe);
+  if (rcode != PD_OK) return rcode;
+  const size_t items = static_cast<size_t>(n_steps) * n;
+  // a re-fill of the streamed form may still be using stagings 0 / 2
+  PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
+  pipe->clean_in = pipe->clean_out = 0;
+  if ((rcode = pd::own_staging(pipe, 0, items * 8)) != PD_OK) return rcode;
+  if ((rcode = pd::own_staging(pipe, 2, items * 4)) != PD_OK) return rcode;
+  float* d_act = static_cast<float*>(pipe->own[0]);
+  uint16_t* d_packed = static_cast<uint16_t*>(pipe->own[2]);
+  // Chunks in sixteenths of the steps; short last chunk (it is the one whose
+  // launch and D2H copy nothing hides).  PD_PACKED_SCHEDULE overrides.
+  static const std::vector<int> schedule = [] {
+    std::vector<int> w;
+    const char* v = getenv("PD_PACKED_SCHEDULE");
+    const char* p = v ? v : "5,5,4,2";
+    while (*p) {
+      w.push_back(atoi(p));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+    if (w.empty() || w.size() > 16) w.assign(1, 1);
+    return w;
+  }();
+  int total_w = 0;
+  for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
+  int n_chunks = static_cast<int>(schedule.size());
+  if (items * 8 < (1u << 20) || n_steps < 2 * n_chunks) n_chunks = 1;
+  int t0[17];
+  t0[0] = 0;
+  for (int c = 0, acc = 0; c < n_chunks; ++c) {
+    acc += schedule[c] > 0 ? schedule[c] : 1;
+    t0[c + 1] = n_chunks == 1
+                    ? n_steps
+                    : static_cast<int>(static_cast<int64_t>(n_steps) * acc /
+                                       total_w);
+  }
+  t0[n_chunks] = n_steps;
+  PD_CUDA_OK(cudaEventRecord(pipe->start, s));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
+  PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
+  auto drain = [&] {  // nothing may be in flight on the caller's buffers
+    cudaStreamSynchronize(pipe->h2d);
+    cudaStreamSynchronize(pipe->d2h);
+    cudaStreamSynchronize(s);
+  };
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n;
+    const size_t cnt = static_cast<size_t>(t0[c + 1] - t0[c]) * n;
+    if (cnt == 0) continue;
+    cudaError_t e = cudaMemcpyAsync(d_act + 2 * off, h_actions_xy + 2 * off,
+                                    cnt * 2 * sizeof(float),
+                                    cudaMemcpyHostToDevice, pipe->h2d);
+    if (e == cudaSuccess) e = cudaEventRecord(pipe->copied[c], pipe->h2d);
+    if (e != cudaSuccess) {
+      drain();
+      PD_CUDA_OK(e);
+    }
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const size_t off = static_cast<size_t>(t0[c]) * n;
+    const int steps = t0[c + 1] - t0[c];
+    if (steps == 0) continue;
+    StepArgs a{};
+    a.lat = *lat;
+    a.st = *st;
+    a.actions_f32 = reinterpret_cast<const float2*>(d_act) + off;
+    a.packed_out = d_packed + off;
+    a.dwell_us_scalar = dwell_us_scalar;
+    a.n_controls = 1;
+    a.n_steps = steps;
+    a.action_mode = action_mode;
+    a.max_distance = max_distance_angstroms;
+    a.image_duration_us = image_duration_us;
+    cudaError_t e = cudaStreamWaitEvent(s, pipe->copied[c], 0);
+    if (e == cudaSuccess) {
+      rcode = pd::dispatch_step(rc, a, true, s);
+      if (rcode != PD_OK) {
+        drain();
+        return rcode;
+      }
+      e = cudaEventRecord(pipe->stepped[c], s);
+    }
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_packed + off, d_packed + off,
+                          static_cast<size_t>(steps) * n * sizeof(uint16_t),
+                          cudaMemcpyDeviceToHost, pipe->d2h);
+    if (e != cudaSuccess) {
+      drain();
+      PD_CUDA_OK(e);
+    }
   }
   PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
   PD_CUDA_OK(cudaStreamSynchronize(s));

@@ -35,23 +35,86 @@ __device__ __noinline__ EnvRegs exact_control(const Tables tab,
   return r;
 }
 
-// What the observation of the Si in the FOV implies for the fast path:
-//   *inside    float32 says the Si is well inside the safe area
-//              (simulator.py:236-249), no float64 test needed;
-//   *clip_free the relative adapter's clip to [0, 1]
-//              (action_adapters.py:186-188) cannot engage for any action, so
-//              beam - Si = clip(action, -1, 1) * max_distance up to 1e-14 A.
-__device__ __forceinline__ void observe_f32(const Fov4& fov, const double2 psi,
-                                            float max_distance, bool* inside,
-                                            bool* clip_free) {
-  const float wx = static_cast<float>(fov.urx - fov.llx);
-  const float wy = static_cast<float>(fov.ury - fov.lly);
-  const float qx = __fdividef(static_cast<float>(psi.x - fov.llx), wx);
-  const float qy = __fdividef(static_cast<float>(psi.y - fov.lly), wy);
-  *inside = qx > 0.2501f && qx < 0.7499f && qy > 0.2501f && qy < 0.7499f;
-  const float rx = __fdividef(max_distance, wx) + 1e-4f;
-  const float ry = __fdividef(max_distance, wy) + 1e-4f;
-  *clip_free = qx > rx && qx < 1.0f - rx && qy > ry && qy < 1.0f - ry;
+// The Si as the microscope sees it, in float32: its normalised position q in
+// the FOV (graphene.py:623-638) and the reciprocal FOV extents.  Synchronised
+// with the float64 state when an env is loaded and whenever the float64 test
+// runs, advanced by the neighbour offset on a hop (1e-7 per hop; callers
+// re-synchronise every kObservedSyncHops hops, the decisions below keep 1e-4
+// of margin).  What it decides:
+//   inside()    the Si is well inside the safe area (simulator.py:236-249): no
+//               float64 test needed, no re-centre;
+//   clip_free() the relative adapter's clip to [0, 1]
+//               (action_adapters.py:186-188) cannot engage for any action, so
+//               beam - Si = clip(action, -1, 1) * max_distance up to 1e-14 A.
+constexpr int kObservedSyncHops = 128;
+
+struct Observed {
+  float qx, qy, iwx, iwy;
+  __device__ __forceinline__ void sync(const Fov4& fov, const double2 psi) {
+    iwx = __fdividef(1.0f, static_cast<float>(fov.urx - fov.llx));
+    iwy = __fdividef(1.0f, static_cast<float>(fov.ury - fov.lly));
+    qx = static_cast<float>(psi.x - fov.llx) * iwx;
+    qy = static_cast<float>(psi.y - fov.lly) * iwy;
+  }
+  // the Si moved by (ox, oy) angstrom
+  __device__ __forceinline__ void hop(float ox, float oy) {
+    qx = __fmaf_rn(ox, iwx, qx);
+    qy = __fmaf_rn(oy, iwy, qy);
+  }
+  __device__ __forceinline__ bool inside() const {
+    return qx > 0.2501f && qx < 0.7499f && qy > 0.2501f && qy < 0.7499f;
+  }
+  __device__ __forceinline__ bool clip_free(float max_distance) const {
+    const float rx = __fmaf_rn(max_distance, iwx, 1e-4f);
+    const float ry = __fmaf_rn(max_distance, iwy, 1e-4f);
+    return qx > rx && qx < 1.0f - rx && qy > ry && qy < 1.0f - ry;
+  }
+};
+
+// Host-format policy of the fast kernels.
+//   IO == 0  pd_rollout_actions: float64 actions [T][n][2] in, int32 Si site
+//            and int64 elapsed microseconds [T][n] out (either may be null);
+//   IO == 1  pd_rollout_actions_host_packed: float32 actions in, one uint16
+//            per env-step out: Si site | re-centred << 15 (the elapsed time of
+//            a step is dwell + image duration * (1 + re-centred),
+//            simulator.py:131-169).
+template <int IO>
+struct ActionStream {
+  const void* base;
+  int64_t n;
+  __device__ __forceinline__ ActionStream(const StepArgs& a)
+      : base(IO == 1 ? static_cast<const void*>(a.actions_f32)
+                     : static_cast<const void*>(a.controls_xy)),
+        n(a.st.n_envs) {}
+  __device__ __forceinline__ const void* at(int64_t step, int64_t env) const {
+    const int64_t i = step * n + env;
+    return IO == 1 ? static_cast<const void*>(
+                         static_cast<const float2*>(base) + i)
+                   : static_cast<const void*>(
+                         static_cast<const double2*>(base) + i);
+  }
+  __device__ __forceinline__ double2 load(int64_t step, int64_t env) const {
+    if (IO == 1) {
+      const float2 v = *static_cast<const float2*>(at(step, env));
+      return make_double2(static_cast<double>(v.x), static_cast<double>(v.y));
+    }
+    return *static_cast<const double2*>(at(step, env));
+  }
+};
+
+template <int IO>
+__device__ __forceinline__ void store_step(const StepArgs& a, int64_t step,
+                                           int64_t env, int si, bool recentred,
+                                           long long step_us) {
+  const int64_t i = step * a.st.n_envs + env;
+  if (IO == 1) {
+    a.packed_out[i] =
+        static_cast<uint16_t>(si | (recentred ? 0x8000 : 0));
+  } else {
+    if (a.si_idx_out) a.si_idx_out[i] = si;
+    if (a.elapsed_us_out)
+      a.elapsed_us_out[i] = step_us + (recentred ? a.image_duration_us : 0);
+  }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -69,17 +132,14 @@ constexpr int kActionsAhead = 8;  // steps of the action stream requested ahead
 // registers of env state: the lattice transform, the FOV and the float64 Si
 // position are re-read / re-derived in the few places that need them.
 // ---------------------------------------------------------------------------
-template <int RATE, bool STAGE>
+template <int RATE, int IO>
 __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     k_walk_fast(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
-  if constexpr (STAGE) {
-    tab = stage_tables(a.lat, smem);
-  } else {
-    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
-    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
-  }
+  // The tables are read through L1: a hop touches one 16-byte row, in one
+  // iteration of ten, and staging them would take the shared memory that the
+  // action stream's L1 lines need.
+  const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
+                         reinterpret_cast<const int4*>(a.lat.nbr)};
   const FastTimes tm = fast_times(a.dwell_us_scalar);
   const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const float md_f = static_cast<float>(a.max_distance);
@@ -91,7 +151,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   const long long step_us = dwell + a.image_duration_us;
   const int64_t n = a.st.n_envs;
   const int n_steps = a.n_steps;
-  const double2* ctl = reinterpret_cast<const double2*>(a.controls_xy);
+  const ActionStream<IO> ctl(a);
   const int lane = threadIdx.x & 31;
   const int64_t n_batches = (n + 31) / 32;
   const int64_t warps_total =
@@ -119,7 +179,8 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     float e_lo = 0.f, e_hi = 0.f, bx = 0.f, by = 0.f;
     bool check_area = true;  // simulator.py:156 can only change its answer
                              // after a hop (and is unknown at call start)
-    bool usable = false, inside = false, clip_free = false;
+    bool usable = false;
+    Observed obs{0.5f, 0.5f, 0.f, 0.f};
     auto rotation = [&]() {
       return reinterpret_cast<const double2*>(a.st.lattice)[2 * env + 1];
     };
@@ -134,7 +195,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         const float ay = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f);
         bx = ax * md_s;
         by = ay * md_s;
-        usable = clip_free;
+        usable = obs.clip_free(md_f);
       } else {
         // simulator.py:137 in float64, then the offset from the Si
         const Fov4 fov = load_fov4(a.st.fov, env);
@@ -147,18 +208,18 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       }
     };
     if (active) {
-      const double2 act = ctl[env];
-      if (n_steps > 1) act_next = ctl[n + env];
+      const double2 act = ctl.load(0, env);
+      if (n_steps > 1) act_next = ctl.load(1, env);
       // a step takes a few hundred cycles, DRAM a thousand: the action
       // stream is requested several steps ahead (L2 now, L1 two steps ahead
       // in the loop), the next batch's state a whole batch ahead
 #pragma unroll 1
       for (int k = 2; k < n_steps && k < 2 + kActionsAhead; ++k)
-        prefetch_l2(ctl + static_cast<int64_t>(k) * n + env);
+        prefetch_l2(ctl.at(k, env));
       if (env + warps_total * 32 < n) {
         prefetch_env(a, env + warps_total * 32);
-        prefetch_l1(ctl + env + warps_total * 32);
-        if (n_steps > 1) prefetch_l1(ctl + n + env + warps_total * 32);
+        prefetch_l1(ctl.at(0, env + warps_total * 32));
+        if (n_steps > 1) prefetch_l1(ctl.at(1, env + warps_total * 32));
       }
       prefetch_l1(a.st.fov_scale + env);
       const Lattice4 lat = load_lattice4(a.st.lattice, env);
@@ -167,8 +228,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       ctrl_count = a.st.ctrl_count[env];
       status = a.st.status[env];
       s = fast_site<RATE>(tab, a.st.si_idx[env], lat.c, lat.s);
-      observe_f32(fov, site_position(tab.position(s.si), lat), md_f, &inside,
-                  &clip_free);
+      obs.sync(fov, site_position(tab.position(s.si), lat));
       begin_control(act);
     }
 
@@ -183,7 +243,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
                                 &t_lo, &t_hi);
       }
       if (kind == FAST_HOP) {
-        fast_hop<RATE>(tab, slot, rotation, &s, &bx, &by);
+        float ox, oy;
+        fast_hop<RATE>(tab, slot, rotation, &s, &bx, &by, &ox, &oy);
+        obs.hop(ox, oy);
         transitions += 1;
         events += 1;
         ++it;
@@ -207,13 +269,15 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         r.log_n = 0;
         r.status = status;
         const int tr0 = r.transitions;
-        double2 pos =
-            ctl[static_cast<int64_t>(t) * n + env];  // this control, again
+        double2 pos = ctl.load(t, env);  // this control, again
         if (relative) pos = relative_to_silicon(fov, r.psi, pos, a.max_distance);
         const double2 beam = microscope_to_material(fov, pos.x, pos.y);
         r = exact_control<RATE>(tab, a.ra, a.st.seed, beam, dwell, r);
         hopped = r.transitions != tr0;
-        if (hopped || it > 0) s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
+        if (hopped || it > 0) {
+          s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
+          obs.sync(fov, r.psi);
+        }
         ctrl_count = r.ctrl_count;
         transitions = r.transitions;
         events = r.events;
@@ -223,35 +287,36 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         ctrl_count += 1;
       }
       // image, safe area (simulator.py:152-169)
-      long long el = step_us;
+      bool recentred = false;
       if (hopped || check_area) {
         check_area = false;
-        Fov4 fov = load_fov4(a.st.fov, env);
-        const double2 psi = site_position(tab.position(s.si),
-                                          load_lattice4(a.st.lattice, env));
-        if (hopped) observe_f32(fov, psi, md_f, &inside, &clip_free);
-        if (!inside && silicon_outside_safe_area(fov, psi)) {
-          fov = centred_fov(psi, a.st.fov_scale[env]);
-          store_fov4(a.st.fov, env, fov);
-          el += a.image_duration_us;
-          recentres += 1;
-          observe_f32(fov, psi, md_f, &inside, &clip_free);
+        // the float64 test (and a re-synchronised float32 view) only when
+        // float32 cannot rule the re-centre out, or is due for a refresh
+        const bool due = (transitions / kObservedSyncHops) !=
+                         ((transitions - static_cast<int>(it)) /
+                          kObservedSyncHops);
+        if (!obs.inside() || due) {
+          Fov4 fov = load_fov4(a.st.fov, env);
+          const double2 psi = site_position(tab.position(s.si),
+                                            load_lattice4(a.st.lattice, env));
+          if (silicon_outside_safe_area(fov, psi)) {
+            fov = centred_fov(psi, a.st.fov_scale[env]);
+            store_fov4(a.st.fov, env, fov);
+            recentred = true;
+            recentres += 1;
+          }
+          obs.sync(fov, psi);
         }
       }
-      if (a.si_idx_out)
-        a.si_idx_out[static_cast<int64_t>(t) * n + env] = s.si;
-      if (a.elapsed_us_out)
-        a.elapsed_us_out[static_cast<int64_t>(t) * n + env] = el;
+      store_step<IO>(a, t, env, s.si, recentred, step_us);
       ++t;
       if (t < n_steps) {
         const double2 act = act_next;
         if (t + 1 < n_steps)
-          act_next = ctl[static_cast<int64_t>(t + 1) * n + env];
-        if (t + 3 < n_steps)
-          prefetch_l1(ctl + static_cast<int64_t>(t + 3) * n + env);
+          act_next = ctl.load(t + 1, env);
+        if (t + 3 < n_steps) prefetch_l1(ctl.at(t + 3, env));
         if (t + 2 + kActionsAhead < n_steps)
-          prefetch_l2(ctl + static_cast<int64_t>(t + 2 + kActionsAhead) * n +
-                      env);
+          prefetch_l2(ctl.at(t + 2 + kActionsAhead, env));
         begin_control(act);
       } else {
         const long long total =
@@ -286,17 +351,14 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
 // then applies what the first other lane found: a hop (float32, certain) or
 // an iteration float32 cannot settle, whose control is replayed exactly.
 // ---------------------------------------------------------------------------
-template <int RATE, bool STAGE>
+template <int RATE, int IO>
 __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     k_rollout_fast(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  typename std::conditional<STAGE, SharedTables, GlobalTables>::type tab;
-  if constexpr (STAGE) {
-    tab = stage_tables(a.lat, smem);
-  } else {
-    tab.base = reinterpret_cast<const double2*>(a.lat.base_xy);
-    tab.nbr = reinterpret_cast<const int4*>(a.lat.nbr);
-  }
+  // The tables are read through L1: a hop touches one 16-byte row, in one
+  // iteration of ten, and staging them would take the shared memory that the
+  // action stream's L1 lines need.
+  const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
+                         reinterpret_cast<const int4*>(a.lat.nbr)};
   const FastTimes tm = fast_times(a.dwell_us_scalar);
   const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const float md_f = static_cast<float>(a.max_distance);
@@ -307,7 +369,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   const long long step_us = dwell + a.image_duration_us;
   const int64_t n = a.st.n_envs;
   const int n_steps = a.n_steps;
-  const double2* ctl = reinterpret_cast<const double2*>(a.controls_xy);
+  const ActionStream<IO> ctl(a);
   const int G = a.lane_stride;  // power of two, 2..32
   const int lane = threadIdx.x & 31;
   const int j = lane & (G - 1);
@@ -321,9 +383,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   for (int64_t e = gtid / G; e < n; e += n_groups) {
     // the whole action column of this env into L2, the first windows into L1
     for (int k = j; k < n_steps; k += G)
-      prefetch_l2(ctl + static_cast<int64_t>(k) * n + e);
-    if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
-    if (G + j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(G + j) * n + e);
+      prefetch_l2(ctl.at(k, e));
+    if (j < n_steps) prefetch_l1(ctl.at(j, e));
+    if (G + j < n_steps) prefetch_l1(ctl.at(G + j, e));
     // ---- state of the env, replicated in the G lanes of its group ----
     const Lattice4 lat = load_lattice4(a.st.lattice, e);
     Fov4 fov = load_fov4(a.st.fov, e);
@@ -333,7 +395,20 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     uint8_t status = a.st.status[e];
     int events = 0, transitions = 0, recentres = 0;
     FastSite s = fast_site<RATE>(tab, a.st.si_idx[e], lat.c, lat.s);
+    // float64 Si position: kept current in the direct mode (the beam offset
+    // needs it), derived on demand otherwise
     double2 psi = site_position(tab.position(s.si), lat);
+    bool psi_ok = true;
+    auto get_psi = [&]() {
+      if (!psi_ok) {
+        psi = site_position(tab.position(s.si), lat);
+        psi_ok = true;
+      }
+      return psi;
+    };
+    Observed obs;
+    obs.sync(fov, psi);
+    int hops_synced = 0;    // transitions at the last obs.sync
     int t = 0;              // current step
     uint32_t it = 0;        // next iteration of the current step's control
                             // = its hops so far
@@ -343,22 +418,26 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     bool first = true;       // first round: lane 0 only, un-re-centred FOV
     bool need_check = true;  // simulator.py:156 runs at t = 0 and after a hop
     bool stale = true;       // Si or FOV changed since the values below
-    bool pending_rec = false, inside = false, clip_free = false,
-         clip_free_n = false;
+    bool pending_rec = false, clip_free = false, clip_free_n = false;
     auto rotation = [&]() { return make_double2(lat.c, lat.s); };
 
     while (t < n_steps) {
       if (stale) {
-        observe_f32(fov, psi, md_f, &inside, &clip_free);
         // Will the step that ends the current control re-centre the FOV
         // (simulator.py:156-169)?  The steps after it see the new FOV.
-        pending_rec =
-            need_check && !inside && silicon_outside_safe_area(fov, psi);
+        pending_rec = false;
+        if (need_check && (!obs.inside() ||
+                           transitions - hops_synced >= kObservedSyncHops)) {
+          pending_rec = silicon_outside_safe_area(fov, get_psi());
+          obs.sync(fov, psi);
+          hops_synced = transitions;
+        }
+        clip_free = obs.clip_free(md_f);
         clip_free_n = clip_free;
         if (pending_rec) {
-          bool unused;
-          observe_f32(centred_fov(psi, scale), psi, md_f, &unused,
-                      &clip_free_n);
+          Observed next;
+          next.sync(centred_fov(psi, scale), psi);
+          clip_free_n = next.clip_free(md_f);
         }
         stale = false;
       }
@@ -370,7 +449,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       if (valid) {
         bool usable = true;
         if (!(j == 0 && cont)) {
-          const double2 c = ctl[static_cast<int64_t>(step) * n + e];
+          const double2 c = ctl.load(step, e);
           if (relative) {
             const float ax = fminf(fmaxf(static_cast<float>(c.x), -1.f), 1.f);
             const float ay = fminf(fmaxf(static_cast<float>(c.y), -1.f), 1.f);
@@ -378,12 +457,12 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
             by = ay * md_s;
             usable = j == 0 ? clip_free : clip_free_n;
           } else {
-            const Fov4 f = (j > 0 && pending_rec)
-                               ? centred_fov(psi, scale)
-                               : fov;
+            const double2 p = get_psi();
+            const Fov4 f =
+                (j > 0 && pending_rec) ? centred_fov(p, scale) : fov;
             const double2 beam = microscope_to_material(f, c.x, c.y);
-            bx = static_cast<float>(beam.x - psi.x) * off_s;
-            by = static_cast<float>(beam.y - psi.y) * off_s;
+            bx = static_cast<float>(beam.x - p.x) * off_s;
+            by = static_cast<float>(beam.y - p.y) * off_s;
           }
         }
         if (usable) {
@@ -395,7 +474,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         }
       }
       if (step + 2 * G < n_steps)
-        prefetch_l1(ctl + static_cast<int64_t>(step + 2 * G) * n + e);
+        prefetch_l1(ctl.at(step + 2 * G, e));
       const unsigned valids = (__ballot_sync(gmask, valid) & gmask) >> gbase;
       const unsigned quiet =
           (__ballot_sync(gmask, valid && kind == FAST_NO_HOP) & gmask) >> gbase;
@@ -404,15 +483,11 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       if (n_done > 0) {
         // the current control and the n_done - 1 after it end without a hop
         const bool rec = pending_rec;  // simulator.py:156-169
-        if (j < n_done) {
-          if (a.si_idx_out)
-            a.si_idx_out[static_cast<int64_t>(step) * n + e] = s.si;
-          if (a.elapsed_us_out)
-            a.elapsed_us_out[static_cast<int64_t>(step) * n + e] =
-                step_us + ((j == 0 && rec) ? a.image_duration_us : 0);
-        }
+        if (j < n_done) store_step<IO>(a, step, e, s.si, j == 0 && rec, step_us);
         if (rec) {
-          fov = centred_fov(psi, scale);
+          fov = centred_fov(get_psi(), scale);
+          obs.sync(fov, psi);
+          hops_synced = transitions;
           recentres += 1;
           pending_rec = false;
           clip_free = clip_free_n;
@@ -436,8 +511,10 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         bx0 = __shfl_sync(gmask, bx, src);
         by0 = __shfl_sync(gmask, by, src);
         if (it == 0) si0 = s.si;
-        fast_hop<RATE>(tab, slot_s, rotation, &s, &bx0, &by0);
-        psi = site_position(tab.position(s.si), lat);
+        float ox, oy;
+        fast_hop<RATE>(tab, slot_s, rotation, &s, &bx0, &by0, &ox, &oy);
+        obs.hop(ox, oy);
+        psi_ok = false;
         transitions += 1;
         events += 1;
         ++it;
@@ -449,7 +526,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       // ---- float32 cannot settle it: the control of step t, exactly ----
       EnvRegs r;
       r.si = it > 0 ? si0 : s.si;
-      r.psi = it > 0 ? site_position(tab.position(si0), lat) : psi;
+      r.psi = it > 0 ? site_position(tab.position(si0), lat) : get_psi();
       r.lat = lat;
       r.env_id = env_id;
       r.ctrl_count = ctrl_count;
@@ -459,7 +536,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       r.status = status;
       const int tr0 = r.transitions;
       {
-        const double2 c = ctl[static_cast<int64_t>(t) * n + e];
+        const double2 c = ctl.load(t, e);
         double2 pos = c;
         if (relative) pos = relative_to_silicon(fov, r.psi, c, a.max_distance);
         const double2 beam = microscope_to_material(fov, pos.x, pos.y);
@@ -468,23 +545,21 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       if (r.transitions != tr0 || it > 0) {
         s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
         psi = r.psi;
+        psi_ok = true;
       }
       if (r.transitions != tr0) need_check = true;
       ctrl_count = r.ctrl_count;
       transitions = r.transitions;
       events = r.events;
       status = r.status;
-      const bool rec = need_check && silicon_outside_safe_area(fov, psi);
-      if (j == 0) {
-        if (a.si_idx_out) a.si_idx_out[static_cast<int64_t>(t) * n + e] = s.si;
-        if (a.elapsed_us_out)
-          a.elapsed_us_out[static_cast<int64_t>(t) * n + e] =
-              step_us + (rec ? a.image_duration_us : 0);
-      }
+      const bool rec = need_check && silicon_outside_safe_area(fov, get_psi());
+      if (j == 0) store_step<IO>(a, t, e, s.si, rec, step_us);
       if (rec) {
         fov = centred_fov(psi, scale);
         recentres += 1;
       }
+      obs.sync(fov, psi);
+      hops_synced = transitions;
       need_check = false;
       stale = true;
       t += 1;
@@ -513,27 +588,19 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
 // Launch (called from launch_step, pd_step.cu).
 // ---------------------------------------------------------------------------
 template <int RATE>
-int launch_fast(const StepArgs& a, bool walk, bool staged, int grid,
-                cudaStream_t stream) {
-  const size_t smem =
-      staged ? static_cast<size_t>(a.lat.n_sites) *
-                   (sizeof(double2) + sizeof(ushort4))
-             : 0;
-  auto kern = walk ? (staged ? k_walk_fast<RATE, true> : k_walk_fast<RATE, false>)
-                   : (staged ? k_rollout_fast<RATE, true>
-                             : k_rollout_fast<RATE, false>);
-  if (staged)
-    PD_CUDA_OK(cudaFuncSetAttribute(
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(smem)));
-  kern<<<grid, kStepThreads, smem, stream>>>(a);
+int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream) {
+  const bool packed = a.packed_out != nullptr;
+  auto kern = walk ? (packed ? k_walk_fast<RATE, 1> : k_walk_fast<RATE, 0>)
+                   : (packed ? k_rollout_fast<RATE, 1>
+                             : k_rollout_fast<RATE, 0>);
+  kern<<<grid, kStepThreads, 0, stream>>>(a);
   PD_CUDA_OK(cudaGetLastError());
   return PD_OK;
 }
 
-template int launch_fast<PD_RATE_SIMPLE>(const StepArgs&, bool, bool, int,
+template int launch_fast<PD_RATE_SIMPLE>(const StepArgs&, bool, int,
                                          cudaStream_t);
-template int launch_fast<PD_RATE_PRIOR>(const StepArgs&, bool, bool, int,
+template int launch_fast<PD_RATE_PRIOR>(const StepArgs&, bool, int,
                                         cudaStream_t);
 
 // ---------------------------------------------------------------------------
@@ -680,17 +747,20 @@ __global__ void __launch_bounds__(256)
 }
 
 // All 2^24 values of the top-24-bit uniform: the float32 draw
-// -ln 2 * lg2.approx(1 - u24) against -log1p(-u24) in float64.
-__global__ void __launch_bounds__(256) k_draw_audit(unsigned int* max_err_bits) {
+// -ln 2 * lg2.approx(1 - u24) against -log1p(-u24) in float64, as a fraction
+// of what fast_event allows for it (kFastDrawAbs absolute + 1e-6 relative).
+__global__ void __launch_bounds__(256) k_draw_audit(unsigned int* max_ratio_bits) {
   float m = 0.f;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < (1u << 24);
        k += gridDim.x * blockDim.x) {
     const float v = 1.0f - static_cast<float>(k) * (1.0f / 16777216.0f);
     const float draw = -0.6931471805599453f * lg2_approx(v);
     const double exact = -log1p(-static_cast<double>(k) / 16777216.0);
-    m = fmaxf(m, static_cast<float>(fabs(static_cast<double>(draw) - exact)));
+    const double allowed = static_cast<double>(kFastDrawAbs) + 1e-6 * exact;
+    m = fmaxf(m, static_cast<float>(
+                     fabs(static_cast<double>(draw) - exact) / allowed));
   }
-  atomicMax(max_err_bits, __float_as_uint(m));
+  atomicMax(max_ratio_bits, __float_as_uint(m));
 }
 
 }  // namespace pd
@@ -739,7 +809,6 @@ extern "C" int pd_fast_path_audit(const pd_lattice* lat, int32_t rate_fn,
   out->total_rate_error_over_bound = f(h.tot_ratio);
   out->waiting_time_error_over_bound = f(h.t_ratio);
   out->choice_error_over_bound = f(h.choice_ratio);
-  out->draw_error_abs_max = f(h.draw_abs);
-  out->draw_error_bound = pd::kFastDrawAbs;
+  out->draw_error_over_bound = f(h.draw_abs);
   return PD_OK;
 }

@@ -181,10 +181,11 @@ class PdFastAudit(C.Structure):
               ('total_rate_error_over_bound', C.c_double),
               ('waiting_time_error_over_bound', C.c_double),
               ('choice_error_over_bound', C.c_double),
-              ('draw_error_abs_max', C.c_double),
-              ('draw_error_bound', C.c_double)]
+              ('draw_error_over_bound', C.c_double)]
 
 
+_SIGNATURES['pd_rollout_actions_host_packed'] = (
+    [_LP, _SP, _RP, _p, _i32, C.c_double, _i64, _i32, _i64, _p, _p], C.c_int)
 _SIGNATURES['pd_set_fast_path'] = ([C.c_int], C.c_int)
 _SIGNATURES['pd_fast_path_audit'] = (
     [_LP, _i32, C.c_uint64, _i64, _i64, C.c_double, C.POINTER(PdFastAudit),

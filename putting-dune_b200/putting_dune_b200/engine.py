@@ -444,6 +444,52 @@ class EnvBatch:
             None, _ptr(h_si), _ptr(h_el), _stream(self.device)))
     return h_si, h_el
 
+  def rollout_host_packed(self, actions_xy, dwell_us: int, rate: RateSpec,
+                          image_duration_us: int = 2000000,
+                          action_mode: int = nat.ACTION_DIRECT,
+                          max_distance_angstroms: float = 1.42,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`rollout_host` in the packed result format of
+    pd_rollout_actions_host_packed: float32 actions [T, E, 2] in, one uint16
+    per env-step out (Si site | re-centred << 15); `unpack_rollout` widens it
+    to the (si_idx, elapsed_us) pair of `rollout_host`.  Prior / simple rates
+    with one positive dwell time below 3000 s."""
+    act = torch.as_tensor(actions_xy)
+    if act.device.type != 'cpu':
+      raise ValueError('rollout_host_packed takes host buffers')
+    act = act.to(torch.float32)
+    if act.ndim != 3 or act.shape[1] != self.num_envs or act.shape[2] != 2:
+      raise ValueError(f'actions must be [T, E, 2], got {tuple(act.shape)}')
+    act = act.contiguous()
+    if not act.is_pinned():
+      act = act.pin_memory()
+    t, e = act.shape[0], self.num_envs
+    if out is None:
+      out = torch.empty((t, e), dtype=torch.uint16).pin_memory()
+    elif out.shape != (t, e) or out.dtype != torch.uint16:
+      raise ValueError('out does not match this call')
+    if t == 0:
+      return out
+    with torch.cuda.device(self.device):
+      nat.check(nat.lib.pd_rollout_actions_host_packed(
+          C.byref(self.lattice_tables.c), C.byref(self.c), C.byref(rate.c),
+          _ptr(act), int(action_mode), float(max_distance_angstroms),
+          int(dwell_us), t, int(image_duration_us), _ptr(out),
+          _stream(self.device)))
+    return out
+
+  @staticmethod
+  def unpack_rollout(packed: torch.Tensor, dwell_us: int,
+                     image_duration_us: int = 2000000):
+    """(si_idx int32, elapsed_us int64) of a packed rollout result:
+    elapsed = dwell + image duration * (1 + re-centred)
+    (simulator.py:131-169)."""
+    p = packed.numpy().astype(np.int32)
+    si = p & 0x7FFF
+    el = (int(dwell_us) + int(image_duration_us) * (1 + (p >> 15))).astype(
+        np.int64)
+    return torch.from_numpy(si), torch.from_numpy(el)
+
   # -- queries --------------------------------------------------------------
   def max_atoms_in_view(self) -> int:
     """Upper bound on atoms inside any current FOV (density 0.382 / A^2
