@@ -1,8 +1,8 @@
 """Host-buffer rollout (pd_rollout_actions_host_f32) at configs[1]: wall time
 per call and a digest of the results.
 
-  python profiles/prof_e2e.py                        # streamed launch
-  PD_HOST_STREAMED=0 python profiles/prof_e2e.py     # chunked copy-engine pipeline
+  python profiles/prof_e2e.py                        # chunked copy-engine pipeline
+  PD_HOST_STREAMED=1 python profiles/prof_e2e.py     # streamed launch (opt-in)
   PD_HOST_TRACE=1 REPS=4 python profiles/prof_e2e.py # timeline of each call
   OWNED=1 python profiles/prof_e2e.py                # library-owned stagings
   PD_HOST_COPY_SMS=8 python profiles/prof_e2e.py     # SMs given to the writers
@@ -66,14 +66,20 @@ torch.cuda.synchronize()
 digest.update(batch.si_idx.cpu().numpy().tobytes())
 digest.update(batch.sim_time_us.cpu().numpy().tobytes())
 times = []
+checksum = 0  # CHECKSUM=1: over the results of every timed call (stress test)
 for i in range(reps):
   t0 = time.perf_counter()
   call(i)
   times.append(time.perf_counter() - t0)
+  if os.environ.get('CHECKSUM') == '1':
+    checksum = (checksum * 1000003 + int(h_si.numpy().sum(dtype=np.int64)) +
+                3 * int(h_el.numpy().sum(dtype=np.int64))) % (1 << 61)
+if os.environ.get('CHECKSUM') == '1':
+  digest.update(str(checksum).encode())
 times = np.asarray(times) * 1e3
 print('streamed=%s owned=%s n=%d steps=%d: median %.4f ms  min %.4f ms  '
       '%.3e env-steps/s  digest %s' % (
-          os.environ.get('PD_HOST_STREAMED', '1'),
+          os.environ.get('PD_HOST_STREAMED', '0'),
           os.environ.get('OWNED', '0'), n, t_steps,
           np.median(times), times.min(), n * t_steps / np.median(times) * 1e3,
           digest.hexdigest()[:16]))

@@ -5,8 +5,8 @@ RelativeToSiliconActionAdapter, prior rates, dwell 1.5 s.
   python profiles/prof_walk.py [n_envs] [steps_per_launch] [rate] [reps]
 
 Prints env-steps/s (median of `reps` launches, L2 flushed between them).
-Knobs are read by the library from the environment: PD_PREPASS,
-PD_WALK_MIN_READY, PD_WALK_MAX_REPS.
+Knobs are read by the library from the environment: PD_FAST (0: float64
+kernels), PD_PREPASS, PD_LANE_STRIDE; OUTPUTS=1 writes the per-step results.
 """
 import ctypes as C
 import os
@@ -39,11 +39,20 @@ stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 P = lambda t: C.c_void_p(t.data_ptr())
 
 
+# OUTPUTS=1: per-step Si site (int32) and elapsed microseconds (int64) written
+# for every env-step, as bench.py times it
+d_si = d_el = None
+if os.environ.get('OUTPUTS') == '1':
+  d_si = torch.empty((steps, n), dtype=torch.int32, device=dev)
+  d_el = torch.empty((steps, n), dtype=torch.int64, device=dev)
+
+
 def launch(i):
   nat.check(nat.lib.pd_rollout_actions(
       C.byref(b.lattice_tables.c), C.byref(b.c), C.byref(rate.c),
       P(acts[i % 3]), nat.ACTION_RELATIVE_TO_SILICON, 1.42, 1500000, steps,
-      2000000, None, None, stream))
+      2000000, P(d_si) if d_si is not None else None,
+      P(d_el) if d_el is not None else None, stream))
 
 
 for i in range(3):
@@ -61,8 +70,7 @@ for i in range(reps):
   ms.append(s.elapsed_time(e))
 m = float(np.median(ms))
 ev = float(b.n_events.sum().item()) / float(b.ctrl_count.sum().item())
-print('n=%d steps=%d rate=%s prepass=%s min_ready=%s max_reps=%s: %.4f ms  '
+print('n=%d steps=%d rate=%s fast=%s outputs=%s: %.4f ms  '
       '%.3e env-steps/s  (%.2f iterations per control)' %
-      (n, steps, rate_name, os.environ.get('PD_PREPASS', '1'),
-       os.environ.get('PD_WALK_MIN_READY', '-'),
-       os.environ.get('PD_WALK_MAX_REPS', '-'), m, n * steps / (m / 1e3), ev))
+      (n, steps, rate_name, os.environ.get('PD_FAST', '1'),
+       os.environ.get('OUTPUTS', '0'), m, n * steps / (m / 1e3), ev))

@@ -448,9 +448,12 @@ __device__ __forceinline__ float2 ld_relaxed_f2(const float2* p) {
                : "memory");
   return v;
 }
+// `copy_done` is written by the copy engine behind the action copy: acquire at
+// system scope, so that the re-read of the element that follows it observes
+// everything the copy wrote before the flag.
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ double2 ld_relaxed_d2(const double2* p) {
@@ -461,11 +464,14 @@ __device__ __forceinline__ double2 ld_relaxed_d2(const double2* p) {
                : "memory");
   return v;
 }
+// An element has arrived only when NEITHER of its words holds the fill pattern
+// any more (a half-landed element must not be consumed); real data with that
+// pattern in one word is settled by `copy_done`.
 __device__ __forceinline__ bool action_missing(const double2 v) {
-  return __double_as_longlong(v.x) == -1LL && __double_as_longlong(v.y) == -1LL;
+  return __double_as_longlong(v.x) == -1LL || __double_as_longlong(v.y) == -1LL;
 }
 __device__ __forceinline__ bool action_missing(const float2 v) {
-  return __float_as_uint(v.x) == 0xFFFFFFFFu &&
+  return __float_as_uint(v.x) == 0xFFFFFFFFu ||
          __float_as_uint(v.y) == 0xFFFFFFFFu;
 }
 // A 16-byte unit of results is final when none of its elements (int32 words,
@@ -1632,9 +1638,10 @@ static int launch_step(const StepArgs& a_in, bool rollout,
       return launch_fast<RATE>(a, false, grid, stream);
     }
   }
-  if (a.packed_out) {
-    set_error("the packed rollout format needs the prior / simple rates, one "
-              "positive dwell time below 3000 s and pd_set_fast_path(1)");
+  if (a.packed_out || (a.actions_f32 && !a.stream_mode)) {
+    set_error("the float32 / packed rollout formats need the prior / simple "
+              "rates, one positive dwell time below 3000 s and "
+              "pd_set_fast_path(1)");
     return PD_ERR_UNSUPPORTED;
   }
   if (a.stream_mode) {
@@ -2146,8 +2153,14 @@ static int streamed_rollout(HostPipeline* pipe, const pd_lattice* lat,
   const int el_bytes = mode == 2 ? 8 : 4;
   int rcode = PD_OK;
   static const int copy_sms = [] {
-    const char* off = getenv("PD_HOST_STREAMED");
-    if (off && off[0] == '0') return 0;
+    // Opt-in (PD_HOST_STREAMED=1): the launch reads a staging that a
+    // copy-engine copy is still writing, which CUDA's memory model leaves
+    // undefined; it is correct on this hardware as long as the copy engine's
+    // writes land in units of >= 8 bytes (the checks below; tests/
+    // test_gpu_events.py stress test), not by specification.  The default is
+    // the chunked pipeline, where no kernel touches a buffer in flight.
+    const char* on = getenv("PD_HOST_STREAMED");
+    if (!on || on[0] != '1') return 0;
     const char* v = getenv("PD_HOST_COPY_SMS");
     const int c = v ? atoi(v) : 4;
     return c < 1 ? 1 : (c > 64 ? 64 : c);
@@ -2388,7 +2401,13 @@ extern "C" int pd_rollout_actions_host(
         max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
         h_si_idx ? d_si_idx + off : nullptr,
         h_elapsed_us ? d_elapsed_us + off : nullptr, stream);
-    if (rcode != PD_OK) return rcode;
+    if (rcode != PD_OK) {
+      // nothing may stay in flight on the caller's buffers
+      cudaStreamSynchronize(pipe->h2d);
+      cudaStreamSynchronize(pipe->d2h);
+      cudaStreamSynchronize(s);
+      return rcode;
+    }
     PD_CUDA_OK(cudaEventRecord(pipe->stepped[c], s));
     PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0));
     if (h_si_idx)
@@ -2504,15 +2523,32 @@ extern "C" int pd_rollout_actions_host_f32(
     if (rcode != PD_OK || handled) return rcode;
   }
 
+  // Prior / simple rates: the fast kernels read the float32 actions and write
+  // the int32 results themselves; other rate functions go through a widening
+  // and a narrowing pass around the float64 rollout.
+  const bool direct32 =
+      rc && (rc->rate_fn == PD_RATE_PRIOR || rc->rate_fn == PD_RATE_SIMPLE) &&
+      pd::fast_enabled() && dwell_us_scalar > 0 &&
+      dwell_us_scalar < 3000LL * 1000000LL;
   if (owned) {
     const size_t items = static_cast<size_t>(n_steps) * n;
     PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));  // a re-fill may be running
     pipe->clean_in = pipe->clean_out = 0;
-    if ((rcode = pd::own_staging(pipe, 1, items * 16)) != PD_OK) return rcode;
-    if ((rcode = pd::own_staging(pipe, 3, items * 8)) != PD_OK) return rcode;
-    d_controls_xy = static_cast<double*>(pipe->own[1]);
-    d_elapsed_us = static_cast<int64_t*>(pipe->own[3]);
+    if (!direct32) {
+      if ((rcode = pd::own_staging(pipe, 1, items * 16)) != PD_OK) return rcode;
+      if ((rcode = pd::own_staging(pipe, 3, items * 8)) != PD_OK) return rcode;
+      d_controls_xy = static_cast<double*>(pipe->own[1]);
+      d_elapsed_us = static_cast<int64_t*>(pipe->own[3]);
+    }
   }
+  // On an error nothing may stay in flight on the caller's buffers.
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(pipe->h2d);
+    cudaStreamSynchronize(pipe->d2h);
+    cudaStreamSynchronize(s);
+    pipe->clean_in = pipe->clean_out = 0;
+    return code;
+  };
   int total_w = 0;
   for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
   int n_chunks = static_cast<int>(schedule.size());
@@ -2543,20 +2579,38 @@ extern "C" int pd_rollout_actions_host_f32(
     const int steps = t0[c + 1] - t0[c];
     const int64_t items = static_cast<int64_t>(steps) * n;
     PD_CUDA_OK(cudaStreamWaitEvent(s, pipe->copied[c], 0));
-    pd::k_widen_actions<<<pd::convert_grid(items), 256, 0, s>>>(
-        reinterpret_cast<const float2*>(d_actions_f32) + off,
-        reinterpret_cast<double2*>(d_controls_xy) + off, items);
-    PD_CUDA_OK(cudaGetLastError());
-    rcode = pd_rollout_actions(
-        lat, st, rc, d_controls_xy + off * 2, action_mode,
-        max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
-        h_si_idx ? d_si_idx + off : nullptr,
-        h_elapsed_us32 ? d_elapsed_us + off : nullptr, stream);
-    if (rcode != PD_OK) return rcode;
-    if (h_elapsed_us32) {
-      pd::k_narrow_elapsed<<<pd::convert_grid(items), 256, 0, s>>>(
-          d_elapsed_us + off, d_elapsed_us32 + off, items);
-      PD_CUDA_OK(cudaGetLastError());
+    if (direct32) {
+      rcode = pd::validate_common(lat, st, rc);
+      if (rcode != PD_OK) return fail(rcode);
+      StepArgs a{};
+      a.lat = *lat;
+      a.st = *st;
+      a.actions_f32 = reinterpret_cast<const float2*>(d_actions_f32) + off;
+      a.si_idx_out = h_si_idx ? d_si_idx + off : nullptr;
+      a.elapsed32_out = h_elapsed_us32 ? d_elapsed_us32 + off : nullptr;
+      a.dwell_us_scalar = dwell_us_scalar;
+      a.n_controls = 1;
+      a.n_steps = steps;
+      a.action_mode = action_mode;
+      a.max_distance = max_distance_angstroms;
+      a.image_duration_us = image_duration_us;
+      rcode = pd::dispatch_step(rc, a, true, s);
+      if (rcode != PD_OK) return fail(rcode);
+    } else {
+      pd::k_widen_actions<<<pd::convert_grid(items), 256, 0, s>>>(
+          reinterpret_cast<const float2*>(d_actions_f32) + off,
+          reinterpret_cast<double2*>(d_controls_xy) + off, items);
+      rcode = pd_rollout_actions(
+          lat, st, rc, d_controls_xy + off * 2, action_mode,
+          max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
+          h_si_idx ? d_si_idx + off : nullptr,
+          h_elapsed_us32 ? d_elapsed_us + off : nullptr, stream);
+      if (rcode != PD_OK) return fail(rcode);
+      if (h_elapsed_us32)
+        pd::k_narrow_elapsed<<<pd::convert_grid(items), 256, 0, s>>>(
+            d_elapsed_us + off, d_elapsed_us32 + off, items);
+      if (cudaGetLastError() != cudaSuccess)
+        return fail(pd::check_cuda(cudaErrorLaunchFailure, "convert kernels"));
     }
     PD_CUDA_OK(cudaEventRecord(pipe->stepped[c], s));
     PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0));
@@ -2640,9 +2694,21 @@ extern "C" int pd_rollout_actions_host_packed(
                                        total_w);
   }
   t0[n_chunks] = n_steps;
-  PD_CUDA_OK(cudaEventRecord(pipe->start, s));
-  PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
-  PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
+  // (The stagings are the library's and the previous call has synchronised:
+  // the copies need not wait for anything queued on `s`.)
+  // PD_PACKED_TRACE=1: device-side timeline of the call on stderr
+  static const bool trace = getenv("PD_PACKED_TRACE") != nullptr;
+  cudaEvent_t tev[40];
+  int n_tev = 0;
+  const char* tev_name[40];
+  auto mark = [&](cudaStream_t q, const char* name) {
+    if (!trace || n_tev >= 40) return;
+    cudaEventCreate(&tev[n_tev]);
+    cudaEventRecord(tev[n_tev], q);
+    tev_name[n_tev++] = name;
+  };
+  const auto cpu_t0 = std::chrono::steady_clock::now();
+  mark(pipe->h2d, "h2d begin");
   auto drain = [&] {  // nothing may be in flight on the caller's buffers
     cudaStreamSynchronize(pipe->h2d);
     cudaStreamSynchronize(pipe->d2h);
@@ -2656,6 +2722,7 @@ extern "C" int pd_rollout_actions_host_packed(
                                     cnt * 2 * sizeof(float),
                                     cudaMemcpyHostToDevice, pipe->h2d);
     if (e == cudaSuccess) e = cudaEventRecord(pipe->copied[c], pipe->h2d);
+    mark(pipe->h2d, "h2d chunk done");
     if (e != cudaSuccess) {
       drain();
       PD_CUDA_OK(e);
@@ -2678,24 +2745,48 @@ extern "C" int pd_rollout_actions_host_packed(
     a.image_duration_us = image_duration_us;
     cudaError_t e = cudaStreamWaitEvent(s, pipe->copied[c], 0);
     if (e == cudaSuccess) {
+      mark(s, "kernel may start");
       rcode = pd::dispatch_step(rc, a, true, s);
       if (rcode != PD_OK) {
         drain();
         return rcode;
       }
-      e = cudaEventRecord(pipe->stepped[c], s);
+      mark(s, "kernel done");
+      // the last chunk's results leave on `s` itself (no stream hand-off
+      // on the path nothing hides), the others on the D2H stream
+      if (c + 1 < n_chunks) {
+        e = cudaEventRecord(pipe->stepped[c], s);
+        if (e == cudaSuccess)
+          e = cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0);
+      }
     }
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(h_packed + off, d_packed + off,
                           static_cast<size_t>(steps) * n * sizeof(uint16_t),
-                          cudaMemcpyDeviceToHost, pipe->d2h);
+                          cudaMemcpyDeviceToHost,
+                          c + 1 < n_chunks ? pipe->d2h : s);
+    mark(c + 1 < n_chunks ? pipe->d2h : s, "d2h chunk done");
     if (e != cudaSuccess) {
       drain();
       PD_CUDA_OK(e);
     }
   }
+  const auto cpu_t1 = std::chrono::steady_clock::now();
   PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
   PD_CUDA_OK(cudaStreamSynchronize(s));
+  if (trace) {
+    const auto cpu_t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "pd packed trace: enqueue %.1f us, call %.1f us |",
+            std::chrono::duration<double, std::micro>(cpu_t1 - cpu_t0).count(),
+            std::chrono::duration<double, std::micro>(cpu_t2 - cpu_t0).count());
+    for (int k = 0; k < n_tev; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tev[0], tev[k]);
+      fprintf(stderr, " %s %.1f;", tev_name[k], ms * 1e3);
+      if (k > 0) cudaEventDestroy(tev[k]);
+    }
+    if (n_tev > 0) cudaEventDestroy(tev[0]);
+    fprintf(stderr, "\n");
+  }
   return PD_OK;
 }

@@ -20,6 +20,9 @@
 #ifndef PD_STEP_MIN_BLOCKS
 #define PD_STEP_MIN_BLOCKS 4
 #endif
+#ifndef PD_FAST_MIN_BLOCKS  // resident CTAs per SM of the fast kernels
+#define PD_FAST_MIN_BLOCKS 4
+#endif
 
 namespace pd {
 
@@ -77,39 +80,52 @@ struct Observed {
 //   IO == 1  pd_rollout_actions_host_packed: float32 actions in, one uint16
 //            per env-step out: Si site | re-centred << 15 (the elapsed time of
 //            a step is dwell + image duration * (1 + re-centred),
-//            simulator.py:131-169).
+//            simulator.py:131-169);
+//   IO == 2  pd_rollout_actions_host_f32: float32 actions in, int32 Si site
+//            and int32 elapsed microseconds out.
 template <int IO>
 struct ActionStream {
   const void* base;
   int64_t n;
   __device__ __forceinline__ ActionStream(const StepArgs& a)
-      : base(IO == 1 ? static_cast<const void*>(a.actions_f32)
+      : base(IO != 0 ? static_cast<const void*>(a.actions_f32)
                      : static_cast<const void*>(a.controls_xy)),
         n(a.st.n_envs) {}
-  __device__ __forceinline__ const void* at(int64_t step, int64_t env) const {
-    const int64_t i = step * n + env;
-    return IO == 1 ? static_cast<const void*>(
+  // i: linear element index step * n + env
+  __device__ __forceinline__ const void* at(int64_t i) const {
+    return IO != 0 ? static_cast<const void*>(
                          static_cast<const float2*>(base) + i)
                    : static_cast<const void*>(
                          static_cast<const double2*>(base) + i);
   }
-  __device__ __forceinline__ double2 load(int64_t step, int64_t env) const {
-    if (IO == 1) {
-      const float2 v = *static_cast<const float2*>(at(step, env));
+  __device__ __forceinline__ double2 load(int64_t i) const {
+    if (IO != 0) {
+      const float2 v = *static_cast<const float2*>(at(i));
       return make_double2(static_cast<double>(v.x), static_cast<double>(v.y));
     }
-    return *static_cast<const double2*>(at(step, env));
+    return *static_cast<const double2*>(at(i));
+  }
+  __device__ __forceinline__ const void* at(int64_t step, int64_t env) const {
+    return at(step * n + env);
+  }
+  __device__ __forceinline__ double2 load(int64_t step, int64_t env) const {
+    return load(step * n + env);
   }
 };
 
+// i: linear element index step * n + env
 template <int IO>
-__device__ __forceinline__ void store_step(const StepArgs& a, int64_t step,
-                                           int64_t env, int si, bool recentred,
+__device__ __forceinline__ void store_step(const StepArgs& a, int64_t i,
+                                           int si, bool recentred,
                                            long long step_us) {
-  const int64_t i = step * a.st.n_envs + env;
   if (IO == 1) {
     a.packed_out[i] =
         static_cast<uint16_t>(si | (recentred ? 0x8000 : 0));
+  } else if (IO == 2) {
+    if (a.si_idx_out) a.si_idx_out[i] = si;
+    if (a.elapsed32_out)
+      a.elapsed32_out[i] = static_cast<int32_t>(
+          step_us + (recentred ? a.image_duration_us : 0));
   } else {
     if (a.si_idx_out) a.si_idx_out[i] = si;
     if (a.elapsed_us_out)
@@ -123,32 +139,118 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 constexpr int kActionsAhead = 8;  // steps of the action stream requested ahead
 
 // ---------------------------------------------------------------------------
+// Rare paths of the fast kernels, out of line so that the hot loops hold only
+// their own registers.  They read the launch arguments through the kernel's
+// (__grid_constant__) parameter.
+// ---------------------------------------------------------------------------
+struct ReplayResult {
+  FastSite s;
+  Observed obs;
+  uint32_t ctrl_count;
+  int transitions, events;
+  uint8_t status;
+  bool hopped;
+};
+
+// The control of step t of env `env`, which began with the Si at si0 and has
+// made `it` float32 hops so far, again and exactly (run_control).
+template <int RATE, int IO>
+__device__ __noinline__ void replay_control(const StepArgs& a, int64_t env,
+                                            int t, int si0, uint32_t it,
+                                            uint32_t ctrl_count,
+                                            int transitions, int events,
+                                            uint8_t status, const Fov4 fov,
+                                            ReplayResult* out) {
+  const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
+                         reinterpret_cast<const int4*>(a.lat.nbr)};
+  const ActionStream<IO> ctl(a);
+  const Lattice4 lat = load_lattice4(a.st.lattice, env);
+  EnvRegs r;
+  r.si = si0;
+  r.psi = site_position(tab.position(si0), lat);
+  r.lat = lat;
+  r.env_id = a.st.env_offset + static_cast<uint32_t>(env);
+  r.ctrl_count = ctrl_count;
+  r.transitions = transitions - static_cast<int>(it);
+  r.events = events - static_cast<int>(it);
+  r.log_n = 0;
+  r.status = status;
+  const int tr0 = r.transitions;
+  double2 pos = ctl.load(t, env);
+  if (a.action_mode == PD_ACTION_RELATIVE_TO_SILICON)
+    pos = relative_to_silicon(fov, r.psi, pos, a.max_distance);
+  const double2 beam = microscope_to_material(fov, pos.x, pos.y);
+  const LogSink log{0, nullptr, nullptr, nullptr};
+  run_control<RATE>(tab, a.ra, a.st.seed, beam, a.dwell_us_scalar, 0, 0, log,
+                    &r);
+  out->s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
+  out->obs.sync(fov, r.psi);
+  out->ctrl_count = r.ctrl_count;
+  out->transitions = r.transitions;
+  out->events = r.events;
+  out->status = r.status;
+  out->hopped = r.transitions != tr0;
+}
+
+// simulator.py:156-169 in float64 for the Si at site `si`: re-centres the FOV
+// (in memory) if the Si has left the safe area; returns whether it did and the
+// re-synchronised float32 view.
+__device__ __noinline__ bool exact_area_check(const StepArgs& a, int64_t env,
+                                              int si, Observed* obs) {
+  const double2 base =
+      __ldg(reinterpret_cast<const double2*>(a.lat.base_xy) + si);
+  Fov4 fov = load_fov4(a.st.fov, env);
+  const double2 psi = site_position(base, load_lattice4(a.st.lattice, env));
+  bool recentred = false;
+  if (silicon_outside_safe_area(fov, psi)) {
+    fov = centred_fov(psi, a.st.fov_scale[env]);
+    store_fov4(a.st.fov, env, fov);
+    recentred = true;
+  }
+  obs->sync(fov, psi);
+  return recentred;
+}
+
+// Beam offset from the Si (fast_event's units) of a control given in the
+// microscope frame (PD_ACTION_DIRECT; simulator.py:137 in float64).
+template <int RATE>
+__device__ __noinline__ float2 direct_offset(const StepArgs& a, int64_t env,
+                                             int si, const double2 act) {
+  const double2 base =
+      __ldg(reinterpret_cast<const double2*>(a.lat.base_xy) + si);
+  const Fov4 fov = load_fov4(a.st.fov, env);
+  const double2 psi = site_position(base, load_lattice4(a.st.lattice, env));
+  const double2 beam = microscope_to_material(fov, act.x, act.y);
+  const float k = fast_offset_scale<RATE>();
+  return make_float2(static_cast<float>(beam.x - psi.x) * k,
+                     static_cast<float>(beam.y - psi.y) * k);
+}
+
+// ---------------------------------------------------------------------------
 // k_walk_fast: large batches.  A lane owns one environment and walks it
 // through its n_steps controls, one iteration per trip of the loop; the 32
 // environments of a warp start together and the warp moves on when all of
 // them are done.  A trip is the float32 iteration for every lane, then one of
 // two short blocks: the hop (~10 % of the lanes) or the end of the control
-// and the start of the next (the others).  Between trips a lane holds ~30
+// and the start of the next (the others).  Between trips a lane holds ~35
 // registers of env state: the lattice transform, the FOV and the float64 Si
-// position are re-read / re-derived in the few places that need them.
+// position are re-read / re-derived in the (out-of-line) places that need
+// them.  REL: the relative adapter (action_adapters.py:163-188).
 // ---------------------------------------------------------------------------
-template <int RATE, int IO>
-__global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
-    k_walk_fast(const StepArgs a) {
+template <int RATE, int IO, bool REL>
+__global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
+    k_walk_fast(const __grid_constant__ StepArgs a) {
   // The tables are read through L1: a hop touches one 16-byte row, in one
   // iteration of ten, and staging them would take the shared memory that the
   // action stream's L1 lines need.
   const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
                          reinterpret_cast<const int4*>(a.lat.nbr)};
   const FastTimes tm = fast_times(a.dwell_us_scalar);
-  const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const float md_f = static_cast<float>(a.max_distance);
   // action -> beam offset in the units fast_event expects
   const float md_s = static_cast<float>(
       a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
-  const float off_s = fast_offset_scale<RATE>();
-  const long long dwell = a.dwell_us_scalar;
-  const long long step_us = dwell + a.image_duration_us;
+  const long long step_us = a.dwell_us_scalar + a.image_duration_us;
   const int64_t n = a.st.n_envs;
   const int n_steps = a.n_steps;
   const ActionStream<IO> ctl(a);
@@ -174,8 +276,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     uint8_t status = 0;
     double2 act_next = make_double2(0.0, 0.0);
     int t = 0;
-    uint32_t it = 0;  // iteration of the current control = its hops so far
-    int si0 = 0;      // Si site when the control began
+    int64_t row = env;  // t * n + env: this step's element of every [T][n] array
+    uint32_t it = 0;    // iteration of the current control = its hops so far
+    int si0 = 0;        // Si site when the control began
     float e_lo = 0.f, e_hi = 0.f, bx = 0.f, by = 0.f;
     bool check_area = true;  // simulator.py:156 can only change its answer
                              // after a hop (and is unknown at call start)
@@ -189,7 +292,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       it = 0;
       e_lo = e_hi = 0.f;
       si0 = s.si;
-      if (relative) {
+      if (REL) {
         // action_adapters.py:163-188 without the clip to the frame
         const float ax = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f);
         const float ay = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f);
@@ -197,29 +300,25 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         by = ay * md_s;
         usable = obs.clip_free(md_f);
       } else {
-        // simulator.py:137 in float64, then the offset from the Si
-        const Fov4 fov = load_fov4(a.st.fov, env);
-        const double2 psi = site_position(tab.position(s.si),
-                                          load_lattice4(a.st.lattice, env));
-        const double2 beam = microscope_to_material(fov, act.x, act.y);
-        bx = static_cast<float>(beam.x - psi.x) * off_s;
-        by = static_cast<float>(beam.y - psi.y) * off_s;
+        const float2 o = direct_offset<RATE>(a, env, s.si, act);
+        bx = o.x;
+        by = o.y;
         usable = true;
       }
     };
     if (active) {
-      const double2 act = ctl.load(0, env);
-      if (n_steps > 1) act_next = ctl.load(1, env);
+      const double2 act = ctl.load(row);
+      if (n_steps > 1) act_next = ctl.load(row + n);
       // a step takes a few hundred cycles, DRAM a thousand: the action
       // stream is requested several steps ahead (L2 now, L1 two steps ahead
       // in the loop), the next batch's state a whole batch ahead
 #pragma unroll 1
       for (int k = 2; k < n_steps && k < 2 + kActionsAhead; ++k)
-        prefetch_l2(ctl.at(k, env));
+        prefetch_l2(ctl.at(row + k * n));
       if (env + warps_total * 32 < n) {
         prefetch_env(a, env + warps_total * 32);
-        prefetch_l1(ctl.at(0, env + warps_total * 32));
-        if (n_steps > 1) prefetch_l1(ctl.at(1, env + warps_total * 32));
+        prefetch_l1(ctl.at(row + warps_total * 32));
+        if (n_steps > 1) prefetch_l1(ctl.at(row + n + warps_total * 32));
       }
       prefetch_l1(a.st.fov_scale + env);
       const Lattice4 lat = load_lattice4(a.st.lattice, env);
@@ -256,32 +355,18 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       bool hopped = it > 0;
       if (kind == FAST_UNSURE) {
         // replay it from its start with the exact code
-        const Lattice4 lat = load_lattice4(a.st.lattice, env);
-        const Fov4 fov = load_fov4(a.st.fov, env);
-        EnvRegs r;
-        r.si = si0;
-        r.psi = site_position(tab.position(si0), lat);
-        r.lat = lat;
-        r.env_id = env_id;
-        r.ctrl_count = ctrl_count;
-        r.transitions = transitions - static_cast<int>(it);
-        r.events = events - static_cast<int>(it);
-        r.log_n = 0;
-        r.status = status;
-        const int tr0 = r.transitions;
-        double2 pos = ctl.load(t, env);  // this control, again
-        if (relative) pos = relative_to_silicon(fov, r.psi, pos, a.max_distance);
-        const double2 beam = microscope_to_material(fov, pos.x, pos.y);
-        r = exact_control<RATE>(tab, a.ra, a.st.seed, beam, dwell, r);
-        hopped = r.transitions != tr0;
-        if (hopped || it > 0) {
-          s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
-          obs.sync(fov, r.psi);
+        ReplayResult rr;
+        replay_control<RATE, IO>(a, env, t, si0, it, ctrl_count, transitions,
+                                 events, status, load_fov4(a.st.fov, env), &rr);
+        if (rr.hopped || it > 0) {
+          s = rr.s;
+          obs = rr.obs;
         }
-        ctrl_count = r.ctrl_count;
-        transitions = r.transitions;
-        events = r.events;
-        status = r.status;
+        hopped = rr.hopped;
+        ctrl_count = rr.ctrl_count;
+        transitions = rr.transitions;
+        events = rr.events;
+        status = rr.status;
       } else {
         events += 1;
         ctrl_count += 1;
@@ -296,27 +381,19 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
                          ((transitions - static_cast<int>(it)) /
                           kObservedSyncHops);
         if (!obs.inside() || due) {
-          Fov4 fov = load_fov4(a.st.fov, env);
-          const double2 psi = site_position(tab.position(s.si),
-                                            load_lattice4(a.st.lattice, env));
-          if (silicon_outside_safe_area(fov, psi)) {
-            fov = centred_fov(psi, a.st.fov_scale[env]);
-            store_fov4(a.st.fov, env, fov);
-            recentred = true;
-            recentres += 1;
-          }
-          obs.sync(fov, psi);
+          recentred = exact_area_check(a, env, s.si, &obs);
+          recentres += recentred ? 1 : 0;
         }
       }
-      store_step<IO>(a, t, env, s.si, recentred, step_us);
+      store_step<IO>(a, row, s.si, recentred, step_us);
       ++t;
+      row += n;
       if (t < n_steps) {
         const double2 act = act_next;
-        if (t + 1 < n_steps)
-          act_next = ctl.load(t + 1, env);
-        if (t + 3 < n_steps) prefetch_l1(ctl.at(t + 3, env));
+        if (t + 1 < n_steps) act_next = ctl.load(row + n);
+        if (t + 3 < n_steps) prefetch_l1(ctl.at(row + 3 * n));
         if (t + 2 + kActionsAhead < n_steps)
-          prefetch_l2(ctl.at(t + 2 + kActionsAhead, env));
+          prefetch_l2(ctl.at(row + (2 + kActionsAhead) * n));
         begin_control(act);
       } else {
         const long long total =
@@ -381,9 +458,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   const int64_t n_groups = static_cast<int64_t>(gridDim.x) * blockDim.x / G;
 
   for (int64_t e = gtid / G; e < n; e += n_groups) {
-    // the whole action column of this env into L2, the first windows into L1
-    for (int k = j; k < n_steps; k += G)
-      prefetch_l2(ctl.at(k, e));
+    // the first windows of the env's action column into L1
+    // (requesting the env's whole action column into L2 here was measured:
+    // 3 % slower than the rolling L1 prefetch alone)
     if (j < n_steps) prefetch_l1(ctl.at(j, e));
     if (G + j < n_steps) prefetch_l1(ctl.at(G + j, e));
     // ---- state of the env, replicated in the G lanes of its group ----
@@ -483,7 +560,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       if (n_done > 0) {
         // the current control and the n_done - 1 after it end without a hop
         const bool rec = pending_rec;  // simulator.py:156-169
-        if (j < n_done) store_step<IO>(a, step, e, s.si, j == 0 && rec, step_us);
+        if (j < n_done)
+          store_step<IO>(a, static_cast<int64_t>(step) * n + e, s.si,
+                         j == 0 && rec, step_us);
         if (rec) {
           fov = centred_fov(get_psi(), scale);
           obs.sync(fov, psi);
@@ -553,7 +632,8 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
       events = r.events;
       status = r.status;
       const bool rec = need_check && silicon_outside_safe_area(fov, get_psi());
-      if (j == 0) store_step<IO>(a, t, e, s.si, rec, step_us);
+      if (j == 0)
+        store_step<IO>(a, static_cast<int64_t>(t) * n + e, s.si, rec, step_us);
       if (rec) {
         fov = centred_fov(psi, scale);
         recentres += 1;
@@ -589,10 +669,29 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
 // ---------------------------------------------------------------------------
 template <int RATE>
 int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream) {
-  const bool packed = a.packed_out != nullptr;
-  auto kern = walk ? (packed ? k_walk_fast<RATE, 1> : k_walk_fast<RATE, 0>)
-                   : (packed ? k_rollout_fast<RATE, 1>
-                             : k_rollout_fast<RATE, 0>);
+  const int io = a.packed_out ? 1 : (a.actions_f32 ? 2 : 0);
+  const bool rel = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
+  void (*kern)(const StepArgs) = nullptr;
+  if (walk) {
+    kern = io == 1   ? (rel ? k_walk_fast<RATE, 1, true>
+                            : k_walk_fast<RATE, 1, false>)
+           : io == 2 ? (rel ? k_walk_fast<RATE, 2, true>
+                            : k_walk_fast<RATE, 2, false>)
+                     : (rel ? k_walk_fast<RATE, 0, true>
+                            : k_walk_fast<RATE, 0, false>);
+  } else {
+    kern = io == 1   ? k_rollout_fast<RATE, 1>
+           : io == 2 ? k_rollout_fast<RATE, 2>
+                     : k_rollout_fast<RATE, 0>;
+  }
+  if (walk) {
+    // persistent warps, one batch of 32 envs at a time: a whole number of
+    // CTAs per SM
+    const int64_t want =
+        (a.st.n_envs + kStepThreads - 1) / kStepThreads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * PD_FAST_MIN_BLOCKS;
+    grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  }
   kern<<<grid, kStepThreads, 0, stream>>>(a);
   PD_CUDA_OK(cudaGetLastError());
   return PD_OK;

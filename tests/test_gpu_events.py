@@ -697,22 +697,44 @@ def test_envbatch_rollout_host(eng):
   assert h_si.shape == (64, n) and (h_el.numpy() >= 3500000).all()
 
 
-def test_rollout_host_streamed_equals_chunked():
-  """The two forms of pd_rollout_actions_host_f32 (PD_HOST_STREAMED=0 forces
-  the chunked copy-engine pipeline) return the same bytes; the environment
-  variable is read once per process, hence the subprocesses."""
+def _prof_e2e_digest(**env):
   import subprocess
   import sys
   script = os.path.join(os.path.dirname(__file__), '..', 'profiles',
                         'prof_e2e.py')
-  digests = []
-  for streamed in ('1', '0'):
-    env = dict(os.environ, PD_HOST_STREAMED=streamed, REPS='3')
-    out = subprocess.run([sys.executable, script], env=env, check=True,
-                         capture_output=True, text=True, timeout=300).stdout
-    assert 'streamed=' + streamed in out
-    digests.append(out.strip().rsplit('digest ', 1)[1])
-  assert digests[0] == digests[1]
+  out = subprocess.run([sys.executable, script],
+                       env=dict(os.environ, **env), check=True,
+                       capture_output=True, text=True, timeout=600).stdout
+  assert 'streamed=' + env.get('PD_HOST_STREAMED', '0') in out
+  return out.strip().rsplit('digest ', 1)[1]
+
+
+def test_rollout_host_streamed_equals_chunked():
+  """The two forms of pd_rollout_actions_host_f32 return the same bytes: the
+  chunked copy-engine pipeline (default; prior / simple rates run the fast
+  kernels on the float32 actions directly) and the opt-in streamed launch
+  (PD_HOST_STREAMED=1: k_rollout_pre follows the H2D copy element by
+  element), and so does the float64 code under the chunks (PD_FAST=0).  The
+  environment variables are read once per process, hence the subprocesses."""
+  digests = [_prof_e2e_digest(PD_HOST_STREAMED=s, PD_FAST=f, REPS='3')
+             for s, f in (('0', '1'), ('1', '1'), ('0', '0'))]
+  assert digests[0] == digests[1] == digests[2]
+
+
+@pytest.mark.parametrize('n,t_steps,reps', [(4096, 256, 4000),
+                                            (4112, 77, 3000),
+                                            (8208, 33, 3000)])
+def test_streamed_rollout_stress(n, t_steps, reps):
+  """The streamed launch reads its action staging while a copy-engine copy is
+  still writing it and recognises data by the absence of the 0xFF fill
+  pattern in either word of an element -- behaviour of this hardware, not of
+  the CUDA memory model (which is why the form is opt-in).  10^4 calls at
+  three sizes, two of them with rows that are not whole cache lines: a
+  checksum over the results of every call equals the chunked pipeline's."""
+  env = dict(N_ENVS=str(n), N_STEPS=str(t_steps), REPS=str(reps),
+             CHECKSUM='1')
+  assert (_prof_e2e_digest(PD_HOST_STREAMED='1', **env) ==
+          _prof_e2e_digest(PD_HOST_STREAMED='0', **env))
 
 
 GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
