@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
 // ---------------------------------------------------------------------------
 template <int RATE, int IO>
 __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
-    k_rollout_fast(const StepArgs a) {
+    k_rollout_fast(const __grid_constant__ StepArgs a) {
   // The tables are read through L1: a hop touches one 16-byte row, in one
   // iteration of ten, and staging them would take the shared memory that the
   // action stream's L1 lines need.
@@ -603,42 +603,29 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         continue;
       }
       // ---- float32 cannot settle it: the control of step t, exactly ----
-      EnvRegs r;
-      r.si = it > 0 ? si0 : s.si;
-      r.psi = it > 0 ? site_position(tab.position(si0), lat) : get_psi();
-      r.lat = lat;
-      r.env_id = env_id;
-      r.ctrl_count = ctrl_count;
-      r.transitions = transitions - static_cast<int>(it);
-      r.events = events - static_cast<int>(it);
-      r.log_n = 0;
-      r.status = status;
-      const int tr0 = r.transitions;
       {
-        const double2 c = ctl.load(t, e);
-        double2 pos = c;
-        if (relative) pos = relative_to_silicon(fov, r.psi, c, a.max_distance);
-        const double2 beam = microscope_to_material(fov, pos.x, pos.y);
-        r = exact_control<RATE>(tab, a.ra, a.st.seed, beam, dwell, r);
+        ReplayResult rr;
+        replay_control<RATE, IO>(a, e, t, it > 0 ? si0 : s.si, it, ctrl_count,
+                                 transitions, events, status, fov, &rr);
+        if (rr.hopped || it > 0) {
+          s = rr.s;
+          psi_ok = false;
+        }
+        if (rr.hopped) need_check = true;
+        ctrl_count = rr.ctrl_count;
+        transitions = rr.transitions;
+        events = rr.events;
+        status = rr.status;
       }
-      if (r.transitions != tr0 || it > 0) {
-        s = fast_site<RATE>(tab, r.si, lat.c, lat.s);
-        psi = r.psi;
-        psi_ok = true;
-      }
-      if (r.transitions != tr0) need_check = true;
-      ctrl_count = r.ctrl_count;
-      transitions = r.transitions;
-      events = r.events;
-      status = r.status;
-      const bool rec = need_check && silicon_outside_safe_area(fov, get_psi());
+      const double2 p_now = get_psi();
+      const bool rec = need_check && silicon_outside_safe_area(fov, p_now);
       if (j == 0)
         store_step<IO>(a, static_cast<int64_t>(t) * n + e, s.si, rec, step_us);
       if (rec) {
-        fov = centred_fov(psi, scale);
+        fov = centred_fov(p_now, scale);
         recentres += 1;
       }
-      obs.sync(fov, psi);
+      obs.sync(fov, p_now);
       hops_synced = transitions;
       need_check = false;
       stale = true;
