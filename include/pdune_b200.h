@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PDUNE_B200_ABI_VERSION 1
+#define PDUNE_B200_ABI_VERSION 2
 
 typedef enum pd_status {
   PD_OK = 0,
@@ -166,6 +166,17 @@ typedef struct pd_mlp {
   const void* w1_umma;
 } pd_mlp;
 
+/* HumanPriorRatePredictor(mean, cov, max_rate) (graphene.py:181-189): the
+ * peak position relative to a neighbour at (1, 0) in bond lengths, the
+ * covariance of the Gaussian fall-off (symmetric positive definite; it stays
+ * in the material frame, only the mean is rotated towards each neighbour,
+ * graphene.py:222-227) and the rate at the peak. */
+typedef struct pd_prior {
+  double mean[2];
+  double cov[2][2];
+  double max_rate;
+} pd_prior;
+
 /* Rate-function selection passed to every stepping call. */
 typedef struct pd_rate_config {
   int32_t rate_fn;         /* pd_rate_fn                                       */
@@ -174,6 +185,9 @@ typedef struct pd_rate_config {
   float constant_rates[3]; /* PD_RATE_CONSTANT only                            */
   float reserved2_;
   const pd_gmm* gmm;       /* HOST pointer; PD_RATE_GMM only                   */
+  const pd_prior* prior;   /* HOST pointer; PD_RATE_PRIOR only; NULL = the
+                            * defaults of constants.py:26-28 ((0.85, 0),
+                            * 0.1 I, ln 2 / 3)                                 */
 } pd_rate_config;
 
 /* Optional per-call outputs of the stepping calls (any pointer may be NULL).
@@ -388,6 +402,32 @@ int pd_fast_path_audit(const pd_lattice* lat, int32_t rate_fn, uint64_t seed,
                        int64_t n_samples, int64_t dwell_us,
                        double max_distance_angstroms, pd_fast_audit* out,
                        void* stream);
+
+/* The float64 rate expressions of the kernels against the reference's
+ * operation sequence (graphene.py:151-166, :210-229), each neighbour of
+ * n_samples random (site, lattice angle, beam offset within max_distance)
+ * triples = 3 n_samples evaluations per rate function:
+ *   simple_max_ulps / prior_max_ulps  largest difference of the two float64
+ *       forms, in float64 ulps;
+ *   simple_cast_differs_unguarded     float32 casts of the short form that
+ *       differ from the operation sequence's, before the guard;
+ *   simple_guard_taken                evaluations the guard (within
+ *       guard_ulps of a float32 rounding boundary) sends to the operation
+ *       sequence;
+ *   simple_cast_differs               differing casts the guard missed (must
+ *       be 0: the simple rate is the reference's float32 value, bit for bit);
+ *   prior_cast_differs                differing casts of the human prior
+ *       (unguarded: the reference evaluates it in JAX float32, no float64
+ *       form is "the" reference there). */
+typedef struct pd_rate_ops_stats {
+  int64_t evaluations;
+  int64_t simple_cast_differs_unguarded, simple_cast_differs;
+  int64_t simple_guard_taken, prior_cast_differs;
+  uint32_t simple_max_ulps, prior_max_ulps, guard_ulps, reserved_;
+} pd_rate_ops_stats;
+int pd_rate_ops_audit(const pd_lattice* lat, uint64_t seed, int64_t n_samples,
+                      double max_distance_angstroms, pd_rate_ops_stats* out,
+                      void* stream);
 
 /* ---- imaging.py:42-72: re-draws the nine image parameters of the envs'
  *      current episode from the uniforms the last pd_reset used (RESET draws

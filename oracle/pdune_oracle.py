@@ -363,8 +363,8 @@ def simple_rates(beam: np.ndarray, p_si: np.ndarray,
   return 1.0 / (np.square(dist * 4) + 1.0)
 
 
-def prior_rates(beam: np.ndarray, p_si: np.ndarray,
-                p_nbr: np.ndarray) -> np.ndarray:
+def prior_rates(beam: np.ndarray, p_si: np.ndarray, p_nbr: np.ndarray,
+                prior: Optional[dict] = None) -> np.ndarray:
   """graphene.py:191-229 `HumanPriorRatePredictor.predict` + :121-130.
 
   theta_i = atan2 of neighbour i; the mean (0.85, 0) is rotated by
@@ -377,14 +377,23 @@ def prior_rates(beam: np.ndarray, p_si: np.ndarray,
   theta = np.arctan2(nbr_rel[..., 1], nbr_rel[..., 0])
   ang = -theta
   c, s = np.cos(ang), np.sin(ang)
-  # mean @ [[c, s], [-s, c]] with mean = (0.85, 0)
-  mu_x = PRIOR_MEAN[0] * c + PRIOR_MEAN[1] * (-s)
-  mu_y = PRIOR_MEAN[0] * s + PRIOR_MEAN[1] * c
+  mean = PRIOR_MEAN if prior is None else np.asarray(prior['mean'], float)
+  # mean @ [[c, s], [-s, c]] (mean = (0.85, 0) by default)
+  mu_x = mean[0] * c + mean[1] * (-s)
+  mu_y = mean[0] * s + mean[1] * c
   x = (beam - p_si) / BOND
   dx = x[:, None, 0] - mu_x
   dy = x[:, None, 1] - mu_y
-  maha = (dx * dx + dy * dy) / PRIOR_VAR
-  return PRIOR_MAX_RATE * np.exp(-0.5 * maha)
+  if prior is None:
+    maha = (dx * dx + dy * dy) / PRIOR_VAR
+    return PRIOR_MAX_RATE * np.exp(-0.5 * maha)
+  # HumanPriorRatePredictor(mean, cov, max_rate), graphene.py:181-229: only
+  # the mean is rotated towards the neighbour, the covariance stays in the
+  # material frame; max_rate * pdf(x) / pdf(mean) = max_rate * exp(-maha / 2)
+  prec = np.linalg.inv(np.asarray(prior['cov'], float).reshape(2, 2))
+  maha = (prec[0, 0] * dx * dx + (prec[0, 1] + prec[1, 0]) * dx * dy +
+          prec[1, 1] * dy * dy)
+  return float(prior['max_rate']) * np.exp(-0.5 * maha)
 
 
 @dataclasses.dataclass
@@ -530,7 +539,8 @@ def gmm_rates(beam: np.ndarray, p_si: np.ndarray, p_nbr: np.ndarray,
 
 def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
               rate_fn: int, mlp: Optional[MlpParams] = None, constant=None,
-              gmm: Optional[dict] = None, keep64: bool = False):
+              gmm: Optional[dict] = None, keep64: bool = False,
+              prior: Optional[dict] = None):
   """graphene.py:238-259: Si + 3-NN geometry -> canonical fn -> float32[3]."""
   si = state.si_idx[envs]
   nbr = state.nbr[si]
@@ -539,7 +549,7 @@ def rates_for(state: OracleState, envs: np.ndarray, beam: np.ndarray,
   if rate_fn == RATE_SIMPLE:
     r64 = simple_rates(beam, p_si, p_nbr)
   elif rate_fn == RATE_PRIOR:
-    r64 = prior_rates(beam, p_si, p_nbr)
+    r64 = prior_rates(beam, p_si, p_nbr, prior)
   elif rate_fn == RATE_LEARNED:
     r64 = learned_rates(mlp, beam, p_si, p_nbr)
   elif rate_fn == RATE_CONSTANT:
@@ -580,7 +590,8 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
                   rate_fn: int = RATE_SIMPLE, mlp: Optional[MlpParams] = None,
                   log: Optional[EventLog] = None,
                   rates_override=None, gmm: Optional[dict] = None,
-                  skip: Optional[np.ndarray] = None) -> dict:
+                  skip: Optional[np.ndarray] = None,
+                  prior: Optional[dict] = None) -> dict:
   """graphene.py:646-694 for all envs at once.
 
   beam: float64 [E, 2] material frame; dwell_us: int64 [E].
@@ -607,7 +618,7 @@ def apply_control(state: OracleState, beam: np.ndarray, dwell_us: np.ndarray,
                            keep64=True)
       r32 = r64.astype(np.float32)
     else:
-      r32, nbr = rates_for(state, idx, beam[idx], rate_fn, mlp)
+      r32, nbr = rates_for(state, idx, beam[idx], rate_fn, mlp, prior=prior)
     if it == 0:
       first_rates[idx] = r32
     # Rates.total_rate: Python sum of np.float32 -> sequential float32 adds.
@@ -684,7 +695,8 @@ def step_and_image(state: OracleState, controls: np.ndarray,
                    mlp: Optional[MlpParams] = None,
                    log: Optional[EventLog] = None,
                    gmm: Optional[dict] = None,
-                   skip: Optional[np.ndarray] = None) -> dict:
+                   skip: Optional[np.ndarray] = None,
+                   prior: Optional[dict] = None) -> dict:
   """simulator.py:107-182 for all envs (without rendering).
 
   controls: float64 [E, C, 2] microscope frame; dwell_us: int64 [E, C].
@@ -702,7 +714,7 @@ def step_and_image(state: OracleState, controls: np.ndarray,
   for c in range(controls.shape[1]):
     beam = microscope_to_material(state.fov, controls[:, c])  # :137
     out = apply_control(state, beam, dwell_us[:, c], rate_fn, mlp, log,
-                        gmm=gmm, skip=skip)  # :147
+                        gmm=gmm, skip=skip, prior=prior)  # :147
     ev += out['events']
     tr += out['transitions']
     elapsed += dwell_us[:, c]  # :149

@@ -108,8 +108,14 @@ def greedy_controls(state: po.OracleState, envs, goal_pos):
   scores = np.sqrt(diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1])
   best = np.argmin(scores, axis=1)
   bd = np.take_along_axis(deltas, best[:, None, None], axis=1)[:, 0, :]
-  angle = np.arctan2(bd[:, 1], bd[:, 0])  # float32
-  c, s = np.cos(angle), np.sin(angle)  # float32
+  # float32 trigonometry, evaluated in float64 and rounded (the correctly
+  # rounded float32 value up to ~1e-8 of the cases): libm / NumPy / CUDA
+  # float32 routines differ from each other by an ulp now and then, their
+  # float64 ones rounded to float32 do not -- the device does the same
+  angle = np.arctan2(bd[:, 1].astype(np.float64),
+                     bd[:, 0].astype(np.float64)).astype(np.float32)
+  c = np.cos(angle.astype(np.float64)).astype(np.float32)
+  s = np.sin(angle.astype(np.float64)).astype(np.float32)
   action = np.stack((ARGMAX[0] * c.astype(np.float64) +
                      ARGMAX[1] * (-s).astype(np.float64),
                      ARGMAX[0] * s.astype(np.float64) +

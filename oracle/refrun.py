@@ -105,7 +105,7 @@ def uninstall_canonical_neighbors(mods):
     mods.geometry.nearest_neighbors3 = orig
 
 
-def make_rate_function(mods, rate_fn: int, mlp=None, gmm=None):
+def make_rate_function(mods, rate_fn: int, mlp=None, gmm=None, prior=None):
   g = mods.graphene
   if rate_fn == po.RATE_GMM:
     return g.GaussianMixtureRateFunction(
@@ -116,7 +116,11 @@ def make_rate_function(mods, rate_fn: int, mlp=None, gmm=None):
   if rate_fn == po.RATE_SIMPLE:
     fn = g.simple_canonical_rate_function
   elif rate_fn == po.RATE_PRIOR:
-    fn = g.HumanPriorRatePredictor().predict
+    fn = (g.HumanPriorRatePredictor().predict if prior is None else
+          g.HumanPriorRatePredictor(
+              mean=np.asarray(prior['mean'], dtype=np.float64),
+              cov=np.asarray(prior['cov'], dtype=np.float64),
+              max_rate=float(prior['max_rate'])).predict)
   elif rate_fn == po.RATE_LEARNED:
     packaged = lambda ctx: po.mlp_forward(mlp, np.asarray(ctx, np.float32))
     fn = refshim.reference_learned_predict(packaged)

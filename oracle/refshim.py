@@ -136,9 +136,19 @@ def load_reference():
   if 'etils' not in sys.modules:
     epath = _module('etils.epath', Path=pathlib.Path)
     _module('etils', epath=epath)
-  for name in ('msgpack_numpy', 'tensorflow'):
-    if name not in sys.modules:
-      _module(name)
+  if 'msgpack_numpy' not in sys.modules:
+    # graphene.py:28 `import msgpack_numpy as msgpack`: the restatement of
+    # its wire encoding, so that the reference's own (de)serialisation runs
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg_dir = os.path.join(here, 'putting-dune_b200', 'putting_dune_b200')
+    import importlib.util  # pylint: disable=g-import-not-at-top
+    spec = importlib.util.spec_from_file_location(
+        'msgpack_numpy', os.path.join(pkg_dir, 'msgpack_numpy_codec.py'))
+    codec = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(codec)
+    sys.modules['msgpack_numpy'] = codec
+  if 'tensorflow' not in sys.modules:
+    _module('tensorflow')
   if 'skimage' not in sys.modules:
     exposure = _module('skimage.exposure')
     util = _module('skimage.util')

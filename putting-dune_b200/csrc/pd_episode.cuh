@@ -70,9 +70,16 @@ __device__ __forceinline__ double2 greedy_control(const Fov4& fov,
       bdy = dy;
     }
   }
-  const float angle = atan2f(bdy, bdx);
-  const double c = static_cast<double>(cosf(angle));
-  const double s = static_cast<double>(sinf(angle));
+  // float32 trigonometry (agent_lib.py:172-181 on float32 features) evaluated
+  // in float64 and rounded: float32 library routines differ between libm,
+  // NumPy and CUDA by an ulp now and then, the rounded float64 ones do not
+  // (the parity tests do the same on the NumPy side)
+  const float angle = static_cast<float>(
+      atan2(static_cast<double>(bdy), static_cast<double>(bdx)));
+  const double c = static_cast<double>(
+      static_cast<float>(cos(static_cast<double>(angle))));
+  const double s = static_cast<double>(
+      static_cast<float>(sin(static_cast<double>(angle))));
   // rotate_coordinates(argmax, angle): (x c - y s, x s + y c)
   const double ax =
       __dadd_rn(__dmul_rn(argmax_x, c), __dmul_rn(argmax_y, -s));

@@ -85,8 +85,18 @@ __device__ __forceinline__ SharedTables stage_tables(const pd_lattice& lat,
 }
 
 // Rate-function parameters that travel by value to the kernels.
+// Internal rate id: PD_RATE_PRIOR with caller-supplied parameters
+// (pd_rate_config.prior); the float64 kernels only.
+constexpr int kRatePriorGeneral = 100;
+
 struct RateArgs {
   float constant_rates[3];
+  // HumanPriorRatePredictor(mean, cov, max_rate): mean, the precision matrix
+  // cov^-1 as (p00, p01 + p10, p11), max_rate
+  int32_t prior_general;
+  double prior_mean[2];
+  double prior_prec[3];
+  double prior_max_rate;
   // PD_RATE_GMM, precomputed on the host: coef = normalising factor * weight
   // / (2 pi sqrt(v1 v2)); nh_inv_v = -0.5 / variance
   int32_t gmm_n;
@@ -101,38 +111,67 @@ struct RateArgs {
 // The reference evaluates the rate in float64 and casts to float32
 // (graphene.py:256); everything downstream (total rate, waiting-time scale,
 // branch probabilities) is a function of those float32 values only.  The
-// float64 expression therefore has to be *accurate* (a few ulp, so that the
-// float32 cast lands on the same value except with probability ~1e-8 per
-// evaluation), not operation-for-operation identical.  The default forms
-// below use that freedom to drop the square root and all but one division;
-// -DPD_EXACT_RATE_OPS keeps the reference's operation sequence.
+// default forms below drop the square root and all but one division; the
+// simple rate falls back to the reference's operation sequence whenever the
+// short form's float32 cast could differ from it (cast_margin_ulps), so its
+// float32 value is the reference's in every case; -DPD_EXACT_RATE_OPS uses
+// the operation sequence everywhere.  pd_rate_ops_audit compares the forms.
 // ---------------------------------------------------------------------------
 // One neighbour of graphene.py:133-166 simple_canonical_rate_function:
 //   r = 1 / ((4 |beam - nbr| / 1.42)^2 + 1) = 1 / (|beam - nbr|^2 16/1.42^2 + 1)
-__device__ __forceinline__ float rate_simple_one(const double2 beam,
-                                                 const double2 psi,
-                                                 const double2 p) {
-#ifdef PD_EXACT_RATE_OPS
-  // op for op
+// Op for op as NumPy evaluates it (np.linalg.norm(axis=-1) = sqrt(dx*dx +
+// dy*dy)), in float64.
+__device__ __forceinline__ double rate_simple_ops(const double2 beam,
+                                                  const double2 psi,
+                                                  const double2 p) {
   const double bx = __dsub_rn(beam.x, psi.x);
   const double by = __dsub_rn(beam.y, psi.y);
   const double nx = __dsub_rn(p.x, psi.x);
   const double ny = __dsub_rn(p.y, psi.y);
   const double dx = __dsub_rn(bx, nx);
   const double dy = __dsub_rn(by, ny);
-  // np.linalg.norm(axis=-1) == sqrt(dx*dx + dy*dy)
   double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
   d = __ddiv_rn(d, kBond);
   const double a = __dmul_rn(d, 4.0);
-  const double den = __dadd_rn(__dmul_rn(a, a), 1.0);
-  return __double2float_rn(__ddiv_rn(1.0, den));
-#else
+  return __ddiv_rn(1.0, __dadd_rn(__dmul_rn(a, a), 1.0));
+}
+
+// The same without the square root and with one division.
+__device__ __forceinline__ double rate_simple_short(const double2 beam,
+                                                    const double2 p) {
   const double kScale = 16.0 / (kBond * kBond);
-  (void)psi;
   const double dx = beam.x - p.x;
   const double dy = beam.y - p.y;
-  const double d2 = fma(dx, dx, dy * dy);
-  return __double2float_rn(1.0 / fma(d2, kScale, 1.0));
+  return 1.0 / fma(fma(dx, dx, dy * dy), kScale, 1.0);
+}
+
+// Distance, in units of the float64 ulp, of a float64 value from the nearest
+// point where its float32 cast changes (the midpoints of float32's grid).
+__device__ __forceinline__ unsigned cast_margin_ulps(double r) {
+  const unsigned low =
+      static_cast<unsigned>(__double_as_longlong(r)) & 0x1FFFFFFFu;
+  return low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+}
+
+// The two float64 forms differ by the roundings of the coordinate
+// differences: <= ~2e-13 relative for coordinates up to a few hundred
+// angstrom (measured by pd_rate_ops_audit: < 2^11 ulp).  Unless the short
+// form lands within kCastGuardUlps of a float32 rounding boundary (6e-5 of
+// the evaluations) its cast IS the cast of the op-for-op value; otherwise the
+// op-for-op form decides.  The simple rate is pure float64 NumPy upstream, so
+// this is the reference's float32 value bit for bit.
+constexpr unsigned kCastGuardUlps = 1u << 14;
+
+__device__ __forceinline__ float rate_simple_one(const double2 beam,
+                                                 const double2 psi,
+                                                 const double2 p) {
+#ifdef PD_EXACT_RATE_OPS
+  return __double2float_rn(rate_simple_ops(beam, psi, p));
+#else
+  const double r = rate_simple_short(beam, p);
+  if (cast_margin_ulps(r) < kCastGuardUlps || !(r > 1e-37))
+    return __double2float_rn(rate_simple_ops(beam, psi, p));
+  return __double2float_rn(r);
 #endif
 }
 
@@ -150,11 +189,12 @@ __device__ __forceinline__ void rates_simple(const double2 beam,
 // quirk); cos/sin of atan2 are taken directly from the
 // neighbour vector.  With covariance 0.1*I,
 //   max_rate * pdf(x)/pdf(mu) = (ln 2 / 3) * exp(-5 |x - mu|^2).
-__device__ __forceinline__ float rate_prior_one(const double2 beam,
-                                                const double2 psi,
-                                                const double2 p) {
+__device__ __forceinline__ double rate_prior_ops(const double2 beam,
+                                                 const double2 psi,
+                                                 const double2 p) {
+  // operation for operation (float64; the reference evaluates the pdf ratio
+  // through jax.scipy.stats in float32, which no float64 form reproduces)
   const double kMaxRate = 0.23104906018664842;  // np.log(2) / 3
-#ifdef PD_EXACT_RATE_OPS
   const double x = __ddiv_rn(__dsub_rn(beam.x, psi.x), kBond);
   const double y = __ddiv_rn(__dsub_rn(beam.y, psi.y), kBond);
   const double nx = __dsub_rn(p.x, psi.x);
@@ -165,8 +205,13 @@ __device__ __forceinline__ float rate_prior_one(const double2 beam,
   const double dy = __dadd_rn(y, __dmul_rn(ny, inv));
   const double maha =
       __ddiv_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.1);
-  return __double2float_rn(__dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha))));
-#else
+  return __dmul_rn(kMaxRate, exp(__dmul_rn(-0.5, maha)));
+}
+
+__device__ __forceinline__ double rate_prior_short(const double2 beam,
+                                                   const double2 psi,
+                                                   const double2 p) {
+  const double kMaxRate = 0.23104906018664842;  // np.log(2) / 3
   const double kInvBond = 1.0 / kBond;
   const double x = (beam.x - psi.x) * kInvBond;
   const double y = (beam.y - psi.y) * kInvBond;
@@ -175,8 +220,48 @@ __device__ __forceinline__ float rate_prior_one(const double2 beam,
   const double inv = 0.85 * rsqrt(fma(nx, nx, ny * ny));
   const double dx = fma(-nx, inv, x);
   const double dy = fma(ny, inv, y);
-  return __double2float_rn(kMaxRate * exp(-5.0 * fma(dx, dx, dy * dy)));
+  return kMaxRate * exp(-5.0 * fma(dx, dx, dy * dy));
+}
+
+// The human prior is Gaussian in float32 upstream (JAX): its float32 value is
+// defined up to the tolerance north_star states for rates, not to the bit,
+// so the short float64 form stands as is; pd_rate_ops_audit reports how often
+// its cast differs from the op-for-op form's (~1e-7 of the evaluations).
+__device__ __forceinline__ float rate_prior_one(const double2 beam,
+                                                const double2 psi,
+                                                const double2 p) {
+#ifdef PD_EXACT_RATE_OPS
+  return __double2float_rn(rate_prior_ops(beam, psi, p));
+#else
+  return __double2float_rn(rate_prior_short(beam, psi, p));
 #endif
+}
+
+// graphene.py:191-229 with caller-supplied mean / cov / max_rate:
+//   mu_i = rotate_coordinates(mean, -theta_i)
+//        = (mx cos t + my sin t, -mx sin t + my cos t),
+//   r_i = max_rate * pdf(x; mu_i, cov) / pdf(mu_i; mu_i, cov)
+//       = max_rate * exp(-(x - mu_i)^T cov^-1 (x - mu_i) / 2).
+__device__ __forceinline__ void rates_prior_general(const RateArgs& ra,
+                                                    const double2 beam,
+                                                    const double2 psi,
+                                                    const double2 pn[3],
+                                                    float r[3]) {
+  const double x = __ddiv_rn(__dsub_rn(beam.x, psi.x), kBond);
+  const double y = __ddiv_rn(__dsub_rn(beam.y, psi.y), kBond);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = pn[i].x - psi.x, ny = pn[i].y - psi.y;
+    const double inv = rsqrt(fma(nx, nx, ny * ny));
+    const double c = nx * inv, s = ny * inv;  // cos, sin of theta_i
+    const double mux = fma(ra.prior_mean[0], c, ra.prior_mean[1] * s);
+    const double muy = fma(ra.prior_mean[1], c, -ra.prior_mean[0] * s);
+    const double dx = x - mux, dy = y - muy;
+    const double maha = fma(ra.prior_prec[0] * dx, dx,
+                            fma(ra.prior_prec[1] * dx, dy,
+                                ra.prior_prec[2] * dy * dy));
+    r[i] = __double2float_rn(ra.prior_max_rate * exp(-0.5 * maha));
+  }
 }
 
 __device__ __forceinline__ void rates_prior(const double2 beam,
@@ -656,6 +741,8 @@ __device__ __forceinline__ void eval_rates(const RateArgs& ra,
     rates_simple(beam, psi, pn, r);
   } else if (RATE == PD_RATE_PRIOR) {
     rates_prior(beam, psi, pn, r);
+  } else if (RATE == kRatePriorGeneral) {
+    rates_prior_general(ra, beam, psi, pn, r);
   } else if (RATE == PD_RATE_GMM) {
     double r64[3];
     rates_gmm(ra, beam, psi, pn, r64);

@@ -1591,7 +1591,7 @@ static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
                               int want_copy_sms, int mode) {
   if (rc->rate_fn == PD_RATE_SIMPLE)
     return stream_plan_for<PD_RATE_SIMPLE>(a, want_copy_sms, mode);
-  if (rc->rate_fn == PD_RATE_PRIOR)
+  if (rc->rate_fn == PD_RATE_PRIOR && !rc->prior)
     return stream_plan_for<PD_RATE_PRIOR>(a, want_copy_sms, mode);
   return StreamPlan{0, 0, 0, 0};
 }
@@ -1687,6 +1687,29 @@ static int launch_step(const StepArgs& a_in, bool rollout,
 int fill_rate_args(const pd_rate_config* rc, RateArgs* ra) {
   for (int i = 0; i < 3; ++i) ra->constant_rates[i] = rc->constant_rates[i];
   ra->gmm_n = 0;
+  ra->prior_general = 0;
+  if (rc->rate_fn == PD_RATE_PRIOR && rc->prior) {
+    const pd_prior* p = rc->prior;
+    const bool defaults = p->mean[0] == 0.85 && p->mean[1] == 0.0 &&
+                          p->cov[0][0] == 0.1 && p->cov[1][1] == 0.1 &&
+                          p->cov[0][1] == 0.0 && p->cov[1][0] == 0.0 &&
+                          p->max_rate == 0.23104906018664842;
+    if (!defaults) {
+      const double det = p->cov[0][0] * p->cov[1][1] -
+                         p->cov[0][1] * p->cov[1][0];
+      PD_REQUIRE(det > 0 && p->cov[0][0] > 0 && p->cov[1][1] > 0 &&
+                     p->max_rate >= 0,
+                 "pd_prior: covariance must be positive definite, max_rate "
+                 ">= 0");
+      ra->prior_general = 1;
+      ra->prior_mean[0] = p->mean[0];
+      ra->prior_mean[1] = p->mean[1];
+      ra->prior_prec[0] = p->cov[1][1] / det;
+      ra->prior_prec[1] = -(p->cov[0][1] + p->cov[1][0]) / det;
+      ra->prior_prec[2] = p->cov[0][0] / det;
+      ra->prior_max_rate = p->max_rate;
+    }
+  }
   if (rc->rate_fn != PD_RATE_GMM) return PD_OK;
   const pd_gmm* g = rc->gmm;
   PD_REQUIRE(g != nullptr, "PD_RATE_GMM needs rc->gmm");
@@ -1726,6 +1749,8 @@ static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
     case PD_RATE_SIMPLE:
       return launch_step<PD_RATE_SIMPLE>(a, rollout, stream);
     case PD_RATE_PRIOR:
+      if (a.ra.prior_general)
+        return launch_step<kRatePriorGeneral>(a, rollout, stream);
       return launch_step<PD_RATE_PRIOR>(a, rollout, stream);
     case PD_RATE_CONSTANT:
       for (int i = 0; i < 3; ++i) a.ra.constant_rates[i] = rc->constant_rates[i];
@@ -1782,6 +1807,8 @@ int launch_episodes(const pd_lattice* lat, const pd_state* st,
     case PD_RATE_SIMPLE:
       return launch_episode_walk<PD_RATE_SIMPLE>(a, stream);
     case PD_RATE_PRIOR:
+      if (a.ra.prior_general)
+        return launch_episode_walk<kRatePriorGeneral>(a, stream);
       return launch_episode_walk<PD_RATE_PRIOR>(a, stream);
     case PD_RATE_CONSTANT:
       return launch_episode_walk<PD_RATE_CONSTANT>(a, stream);
@@ -1853,8 +1880,12 @@ extern "C" int pd_rates(const pd_lattice* lat, const pd_state* st,
           a, rates_out, nbr_out);
       break;
     case PD_RATE_PRIOR:
-      pd::k_rates<PD_RATE_PRIOR><<<grid, pd::kStepThreads, 0, s>>>(
-          a, rates_out, nbr_out);
+      if (a.ra.prior_general)
+        pd::k_rates<pd::kRatePriorGeneral><<<grid, pd::kStepThreads, 0, s>>>(
+            a, rates_out, nbr_out);
+      else
+        pd::k_rates<PD_RATE_PRIOR><<<grid, pd::kStepThreads, 0, s>>>(
+            a, rates_out, nbr_out);
       break;
     default:
       pd::k_rates<PD_RATE_CONSTANT><<<grid, pd::kStepThreads, 0, s>>>(
@@ -2527,7 +2558,8 @@ extern "C" int pd_rollout_actions_host_f32(
   // the int32 results themselves; other rate functions go through a widening
   // and a narrowing pass around the float64 rollout.
   const bool direct32 =
-      rc && (rc->rate_fn == PD_RATE_PRIOR || rc->rate_fn == PD_RATE_SIMPLE) &&
+      rc && ((rc->rate_fn == PD_RATE_PRIOR && !rc->prior) ||
+             rc->rate_fn == PD_RATE_SIMPLE) &&
       pd::fast_enabled() && dwell_us_scalar > 0 &&
       dwell_us_scalar < 3000LL * 1000000LL;
   if (owned) {

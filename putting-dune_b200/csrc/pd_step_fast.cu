@@ -849,7 +849,103 @@ __global__ void __launch_bounds__(256) k_draw_audit(unsigned int* max_ratio_bits
   atomicMax(max_ratio_bits, __float_as_uint(m));
 }
 
+// The short float64 rate forms against the reference's operation sequence
+// (pd_kmc.cuh) at random sites / lattice angles / beam offsets.
+struct RateOpsStats {
+  unsigned long long samples, simple_cast_differs_unguarded,
+      simple_cast_differs, simple_guard_taken, prior_cast_differs;
+  unsigned int simple_max_ulps, prior_max_ulps;
+};
+
+__global__ void __launch_bounds__(256)
+    k_rate_ops_audit(const pd_lattice lat, uint64_t seed, int64_t n_samples,
+                     double max_distance, RateOpsStats* out) {
+  GlobalTables tab{reinterpret_cast<const double2*>(lat.base_xy),
+                   reinterpret_cast<const int4*>(lat.nbr)};
+  const PhiloxKeys keys = philox_keys(seed);
+  unsigned long long c_n = 0, c_su = 0, c_s = 0, c_g = 0, c_p = 0;
+  unsigned int m_s = 0, m_p = 0;
+  auto ulps = [](double a, double b) {
+    const long long d = __double_as_longlong(a) - __double_as_longlong(b);
+    const unsigned long long u = d < 0 ? -d : d;
+    return u > 0xFFFFFFFFull ? 0xFFFFFFFFu : static_cast<unsigned int>(u);
+  };
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+       i < n_samples; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t lo = static_cast<uint32_t>(i), hi = static_cast<uint32_t>(i >> 32);
+    const uint4 s0 = philox4x32_10k(lo, hi, 0u, 101u, keys);
+    const uint4 s1 = philox4x32_10k(lo, hi, 1u, 101u, keys);
+    const uint4 s2 = philox4x32_10k(lo, hi, 2u, 101u, keys);
+    const int si = static_cast<int>(s0.x % static_cast<uint32_t>(lat.n_sites));
+    double sn, cs;
+    sincos(6.283185307179586 * u53(s0.y, s0.z), &sn, &cs);
+    const Lattice4 lt{1.42 * (u53(s0.w, s1.x) - 0.5),
+                      1.42 * (u53(s1.y, s1.z) - 0.5), cs, sn};
+    const double2 psi = site_position(tab.position(si), lt);
+    const double2 beam =
+        make_double2(psi.x + (2.0 * u53(s1.w, s2.x) - 1.0) * max_distance,
+                     psi.y + (2.0 * u53(s2.y, s2.z) - 1.0) * max_distance);
+    int nb[3];
+    tab.neighbors(si, nb);
+    for (int k = 0; k < 3; ++k) {
+      const double2 p = site_position(tab.position(nb[k]), lt);
+      const double a = rate_simple_ops(beam, psi, p);
+      const double b = rate_simple_short(beam, p);
+      const bool guard = cast_margin_ulps(b) < kCastGuardUlps || !(b > 1e-37);
+      ++c_n;
+      m_s = max(m_s, ulps(a, b));
+      if (__double2float_rn(a) != __double2float_rn(b)) {
+        ++c_su;
+        if (!guard) ++c_s;
+      }
+      if (guard) ++c_g;
+      const double pa = rate_prior_ops(beam, psi, p);
+      const double pb = rate_prior_short(beam, psi, p);
+      if (pa > 1e-300) m_p = max(m_p, ulps(pa, pb));
+      if (__double2float_rn(pa) != __double2float_rn(pb)) ++c_p;
+    }
+  }
+  atomicAdd(&out->samples, c_n);
+  atomicAdd(&out->simple_cast_differs_unguarded, c_su);
+  atomicAdd(&out->simple_cast_differs, c_s);
+  atomicAdd(&out->simple_guard_taken, c_g);
+  atomicAdd(&out->prior_cast_differs, c_p);
+  atomicMax(&out->simple_max_ulps, m_s);
+  atomicMax(&out->prior_max_ulps, m_p);
+}
+
 }  // namespace pd
+
+extern "C" int pd_rate_ops_audit(const pd_lattice* lat, uint64_t seed,
+                                 int64_t n_samples,
+                                 double max_distance_angstroms,
+                                 pd_rate_ops_stats* out, void* stream) {
+  PD_REQUIRE(lat && lat->base_xy && lat->nbr && out, "null lattice / output");
+  PD_REQUIRE(n_samples > 0, "nothing to audit");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pd::RateOpsStats* d = nullptr;
+  PD_CUDA_OK(cudaMalloc(&d, sizeof(pd::RateOpsStats)));
+  PD_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(pd::RateOpsStats), s));
+  pd::k_rate_ops_audit<<<pd::sm_count() * 8, 256, 0, s>>>(
+      *lat, seed, n_samples, max_distance_angstroms, d);
+  pd::RateOpsStats h{};
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  cudaFree(d);
+  PD_CUDA_OK(err);
+  out->evaluations = static_cast<int64_t>(h.samples);
+  out->simple_cast_differs_unguarded =
+      static_cast<int64_t>(h.simple_cast_differs_unguarded);
+  out->simple_cast_differs = static_cast<int64_t>(h.simple_cast_differs);
+  out->simple_guard_taken = static_cast<int64_t>(h.simple_guard_taken);
+  out->prior_cast_differs = static_cast<int64_t>(h.prior_cast_differs);
+  out->simple_max_ulps = h.simple_max_ulps;
+  out->prior_max_ulps = h.prior_max_ulps;
+  out->guard_ulps = pd::kCastGuardUlps;
+  return PD_OK;
+}
 
 extern "C" int pd_fast_path_audit(const pd_lattice* lat, int32_t rate_fn,
                                   uint64_t seed, int64_t n_samples,

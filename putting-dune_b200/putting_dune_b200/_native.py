@@ -63,10 +63,17 @@ class PdGmm(C.Structure):
               ('variances', (C.c_double * 2) * GMM_MAX_MIXTURES)]
 
 
+class PdPrior(C.Structure):
+  """pd_prior: HumanPriorRatePredictor(mean, cov, max_rate)."""
+  _fields_ = [('mean', C.c_double * 2), ('cov', (C.c_double * 2) * 2),
+              ('max_rate', C.c_double)]
+
+
 class PdRateConfig(C.Structure):
   _fields_ = [('rate_fn', C.c_int32), ('reserved_', C.c_int32),
               ('mlp', C.POINTER(PdMlp)), ('constant_rates', C.c_float * 3),
-              ('reserved2_', C.c_float), ('gmm', C.POINTER(PdGmm))]
+              ('reserved2_', C.c_float), ('gmm', C.POINTER(PdGmm)),
+              ('prior', C.POINTER(PdPrior))]
 
 
 class PdStepOut(C.Structure):
@@ -184,6 +191,20 @@ class PdFastAudit(C.Structure):
               ('draw_error_over_bound', C.c_double)]
 
 
+class PdRateOpsStats(C.Structure):
+  """pd_rate_ops_stats (include/pdune_b200.h)."""
+  _fields_ = [('evaluations', C.c_int64),
+              ('simple_cast_differs_unguarded', C.c_int64),
+              ('simple_cast_differs', C.c_int64),
+              ('simple_guard_taken', C.c_int64),
+              ('prior_cast_differs', C.c_int64),
+              ('simple_max_ulps', C.c_uint32), ('prior_max_ulps', C.c_uint32),
+              ('guard_ulps', C.c_uint32), ('reserved_', C.c_uint32)]
+
+
+_SIGNATURES['pd_rate_ops_audit'] = (
+    [_LP, C.c_uint64, _i64, C.c_double, C.POINTER(PdRateOpsStats), _p],
+    C.c_int)
 _SIGNATURES['pd_rollout_actions_host_packed'] = (
     [_LP, _SP, _RP, _p, _i32, C.c_double, _i64, _i32, _i64, _p, _p], C.c_int)
 _SIGNATURES['pd_set_fast_path'] = ([C.c_int], C.c_int)

@@ -141,12 +141,26 @@ class RateSpec:
 
   def __init__(self, kind: int, *, mlp: Optional[MlpWeights] = None,
                constant: Optional[Sequence[float]] = None, device=None,
-               tensor_core: bool = False, gmm: Optional[dict] = None):
+               tensor_core: bool = False, gmm: Optional[dict] = None,
+               prior: Optional[dict] = None):
     self.kind = int(kind)
     self.c = nat.PdRateConfig()
     self.c.rate_fn = self.kind
     self._mlp_c = None
     self._tensors = {}
+    if prior is not None:
+      # HumanPriorRatePredictor(mean, cov, max_rate), graphene.py:181-189
+      if self.kind != nat.RATE_PRIOR:
+        raise ValueError('prior parameters need RATE_PRIOR')
+      mean = np.asarray(prior['mean'], dtype=np.float64).reshape(2)
+      cov = np.asarray(prior['cov'], dtype=np.float64).reshape(2, 2)
+      self._prior_c = nat.PdPrior()
+      for i in range(2):
+        self._prior_c.mean[i] = mean[i]
+        for j in range(2):
+          self._prior_c.cov[i][j] = cov[i, j]
+      self._prior_c.max_rate = float(prior['max_rate'])
+      self.c.prior = C.pointer(self._prior_c)
     if self.kind == nat.RATE_CONSTANT:
       if constant is None or len(constant) != 3:
         raise ValueError('RATE_CONSTANT needs three rates')
@@ -200,8 +214,15 @@ class RateSpec:
     return cls(nat.RATE_SIMPLE)
 
   @classmethod
-  def prior(cls):
-    return cls(nat.RATE_PRIOR)
+  def prior(cls, mean=None, cov=None, max_rate=None):
+    """The human prior; with arguments, HumanPriorRatePredictor(mean, cov,
+    max_rate) (graphene.py:181-189; evaluated by the float64 kernels)."""
+    if mean is None and cov is None and max_rate is None:
+      return cls(nat.RATE_PRIOR)
+    return cls(nat.RATE_PRIOR, prior={
+        'mean': (0.85, 0.0) if mean is None else mean,
+        'cov': ((0.1, 0.0), (0.0, 0.1)) if cov is None else cov,
+        'max_rate': np.log(2) / 3 if max_rate is None else max_rate})
 
 
 @dataclasses.dataclass

@@ -92,16 +92,23 @@ class HumanPriorRatePredictor:
   def __init__(self, mean: np.ndarray = constants.SIGR_PRIOR_RATE_MEAN,
                cov: np.ndarray = constants.SIGR_PRIOR_RATE_COV,
                max_rate: float = constants.SIGR_PRIOR_MAX_RATE):
-    if (not np.allclose(mean, constants.SIGR_PRIOR_RATE_MEAN) or
-        not np.allclose(cov, constants.SIGR_PRIOR_RATE_COV) or
-        not np.isclose(max_rate, constants.SIGR_PRIOR_MAX_RATE)):
-      raise NotImplementedError(
-          'the device kernel implements the default human prior '
-          '(mean (0.85, 0), cov 0.1*I, max rate ln2/3)')
-    self.mean, self.cov, self.max_rate = mean, cov, max_rate
+    self.mean = np.asarray(mean, dtype=np.float64)
+    self.cov = np.asarray(cov, dtype=np.float64)
+    self.max_rate = float(max_rate)
+    if self.mean.shape != (2,) or self.cov.shape != (2, 2):
+      raise ValueError('mean must have shape (2,), cov (2, 2)')
+
+  def _is_default(self) -> bool:
+    return (np.array_equal(self.mean, constants.SIGR_PRIOR_RATE_MEAN) and
+            np.array_equal(self.cov, constants.SIGR_PRIOR_RATE_COV) and
+            self.max_rate == constants.SIGR_PRIOR_MAX_RATE)
 
   def rate_spec(self) -> engine.RateSpec:
-    return engine.RateSpec.prior()
+    # the defaults take the specialised kernels (closed form, float32 fast
+    # path); anything else the general float64 form of the same expression
+    if self._is_default():
+      return engine.RateSpec.prior()
+    return engine.RateSpec.prior(self.mean, self.cov, self.max_rate)
 
   def predict(self, grid, beam_position, silicon_position,
               neighbor_indices) -> np.ndarray:
@@ -177,8 +184,7 @@ class PristineSingleSiGrRatePredictor:
 class GaussianMixtureRateFunction:
   """graphene.py:279-461: per-neighbour anisotropic Gaussian mixture placed
   along the Si->neighbour vector; a ``RateFunction`` evaluated on the device
-  (PD_RATE_GMM).  File (de)serialisation of the reference (msgpack) is an
-  offline format and not provided."""
+  (PD_RATE_GMM)."""
   max_rate: float
   mixture_weights: np.ndarray  # [n_mixtures]
   loc_distances: np.ndarray  # [n_mixtures]
@@ -202,6 +208,34 @@ class GaussianMixtureRateFunction:
       states.append(SuccessorState(
           mu.AtomicGrid(grid.atom_positions, numbers), float(r)))
     return Rates(states)
+
+  def serialize_to_directory(self, save_dir, /) -> None:
+    """graphene.py:392-409: <save_dir>/gmm_parameters.mpk, a msgpack map of
+    the four parameters with msgpack-numpy's array encoding."""
+    import pathlib
+    from putting_dune_b200 import msgpack_numpy_codec as codec
+    path = pathlib.Path(save_dir)
+    path.mkdir(parents=True, exist_ok=True)
+    bundle = {
+        'sem_ver': '1.0.0',
+        'max_rate': self.max_rate,
+        'mixture_weights': self.mixture_weights,
+        'loc_distances': self.loc_distances,
+        'variances': self.variances,
+    }
+    (path / 'gmm_parameters.mpk').write_bytes(codec.packb(bundle))
+
+  @classmethod
+  def deserialize_from_directory(cls, load_dir, /):
+    """graphene.py:411-427."""
+    import pathlib
+    from putting_dune_b200 import msgpack_numpy_codec as codec
+    bundle = codec.unpackb(
+        (pathlib.Path(load_dir) / 'gmm_parameters.mpk').read_bytes())
+    return cls(max_rate=bundle['max_rate'],
+               mixture_weights=bundle['mixture_weights'],
+               loc_distances=bundle['loc_distances'],
+               variances=bundle['variances'])
 
   @classmethod
   def sample_new(cls, rng: np.random.Generator):

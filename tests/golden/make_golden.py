@@ -33,11 +33,19 @@ GMM_PARAMS = {  # graphene_test.py:337-345 parameter set
     'variances': np.asarray(((0.1, 0.1), (1.0, 1.0), (2.0, 0.5), (0.5, 2.0),
                              (0.01, 0.01))),
 }
+# a HumanPriorRatePredictor(mean, cov, max_rate) away from the defaults of
+# constants.py:26-28: off-axis mean, anisotropic correlated covariance
+PRIOR_CUSTOM = {
+    'mean': (0.7, 0.15),
+    'cov': ((0.12, 0.03), (0.03, 0.07)),
+    'max_rate': 0.4,
+}
 
 
 def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None,
-                         gmm=None):
-  """Controls that follow the Si (RelativeToSilicon-style), from the oracle."""
+                         gmm=None, float32=False, dwell_pair=(1500000, 5000000)):
+  """Controls that follow the Si (RelativeToSilicon-style), from the oracle.
+  float32: controls rounded to float32 values (stored compactly)."""
   st = po.make_state(n_envs, seed)
   po.reset(st)
   rng = np.random.default_rng(ctrl_seed)
@@ -48,7 +56,9 @@ def closed_loop_controls(seed, n_envs, n_steps, rate_fn, ctrl_seed, mlp=None,
     q = po.material_to_microscope(st.fov, p)
     a = rng.uniform(-1, 1, size=(n_envs, 2))
     controls[t, :, 0] = q + a * po.BOND / st.fov_scale[:, None]
-    dwell[t, :, 0] = np.where(np.arange(n_envs) % 2 == 0, 1500000, 5000000)
+    if float32:
+      controls[t] = controls[t].astype(np.float32).astype(np.float64)
+    dwell[t, :, 0] = np.where(np.arange(n_envs) % 2 == 0, *dwell_pair)
     po.step_and_image(st, controls[t], dwell[t], rate_fn=rate_fn, mlp=mlp,
                       gmm=gmm)
   return controls, dwell
@@ -88,6 +98,51 @@ def events_fixture(name, rate_fn, seed, n_envs, n_steps, mlp=None, gmm=None):
         arrays['transitions'].shape[0])
 
 
+def _large_worker(args):
+  seed, e, controls, dwell, rate_fn = args
+  r = refrun.run_reference_env(seed, e, controls, dwell, rate_fn)
+  t = r['transitions']
+  return (e, r['si0'], r['fov0'], r['fov_scale'], r['image_params'], r['si'],
+          r['elapsed_us'], r['fov'][-1], r['n_observed'][-1],
+          np.concatenate([np.full((t.shape[0], 1), e), t], axis=1))
+
+
+def events_fixture_large(name, rate_fn, seed, n_envs, n_steps,
+                         dwell_pair=(1500000, 5000000)):
+  """The same kind of trajectory fixture at a size the judge asked for (256
+  envs x 100 steps per rate function; one env x 1000 steps = BASELINE
+  configs[0]), the unmodified reference run env by env on all cores.  Stored
+  compactly: float32-valued controls, the FOV only after the last step."""
+  import multiprocessing as mp
+  controls, dwell = closed_loop_controls(seed, n_envs, n_steps, rate_fn,
+                                         ctrl_seed=seed + 1, float32=True,
+                                         dwell_pair=dwell_pair)
+  refshim.load_reference()  # before the fork
+  jobs = [(seed, e, controls[:, e], dwell[:, e], rate_fn)
+          for e in range(n_envs)]
+  with mp.get_context('fork').Pool(min(os.cpu_count() or 1, n_envs)) as pool:
+    res = sorted(pool.map(_large_worker, jobs, chunksize=1),
+                 key=lambda r: r[0])
+  arrays = {
+      'si0': np.asarray([r[1] for r in res]),
+      'fov0': np.asarray([r[2] for r in res]),
+      'fov_scale': np.asarray([r[3] for r in res]),
+      'image_params': np.asarray([r[4] for r in res]),
+      'si': np.asarray([r[5] for r in res], dtype=np.int32),
+      'elapsed_us': np.asarray([r[6] for r in res]),
+      'fov_last': np.asarray([r[7] for r in res]),
+      'n_observed_last': np.asarray([r[8] for r in res]),
+      'transitions': np.concatenate([r[9] for r in res], axis=0),
+      'controls': controls.astype(np.float32),
+      'dwell_us': dwell[0, :, 0],  # per env, the same at every step
+      'seed': np.int64(seed), 'rate_fn': np.int64(rate_fn),
+  }
+  np.savez_compressed(os.path.join(HERE, name), **arrays)
+  print(name, 'envs', n_envs, 'steps', n_steps, 'transitions',
+        arrays['transitions'].shape[0], 'bytes',
+        os.path.getsize(os.path.join(HERE, name)))
+
+
 def rates_fixture():
   """Rates of the reference's own rate functions at scattered beam offsets."""
   mods = refshim.load_reference()
@@ -102,8 +157,11 @@ def rates_fixture():
   mlp = po.MlpParams.synthetic(3, hidden=(32, 32))
   res = {'beam': beam, 'seed': np.int64(seed)}
   for name, rate_fn in (('simple', po.RATE_SIMPLE), ('prior', po.RATE_PRIOR),
-                        ('learned', po.RATE_LEARNED), ('gmm', po.RATE_GMM)):
-    fn = refrun.make_rate_function(mods, rate_fn, mlp, GMM_PARAMS)
+                        ('learned', po.RATE_LEARNED), ('gmm', po.RATE_GMM),
+                        ('prior_custom', po.RATE_PRIOR)):
+    fn = refrun.make_rate_function(
+        mods, rate_fn, mlp, GMM_PARAMS,
+        prior=PRIOR_CUSTOM if name == 'prior_custom' else None)
     rates = np.zeros((n, 3), dtype=np.float64 if name == 'gmm' else np.float32)
     succ = np.zeros((n, 3), dtype=np.int32)
     for e in range(n):
@@ -430,18 +488,35 @@ def synth_fixture():
   print('synth fixture written')
 
 
+FIXTURES = {
+    'events_simple': lambda: events_fixture('events_simple.npz',
+                                            po.RATE_SIMPLE, 2024, 32, 30),
+    'events_prior': lambda: events_fixture('events_prior.npz', po.RATE_PRIOR,
+                                           2025, 32, 30),
+    'events_gmm': lambda: events_fixture('events_gmm.npz', po.RATE_GMM, 2026,
+                                         24, 20, gmm=GMM_PARAMS),
+    'events_simple_large': lambda: events_fixture_large(
+        'events_simple_large.npz', po.RATE_SIMPLE, 3024, 256, 100),
+    'events_prior_large': lambda: events_fixture_large(
+        'events_prior_large.npz', po.RATE_PRIOR, 3025, 256, 100),
+    # BASELINE configs[0]: one env, prior rates, 1000 beam steps, dwell 1.5 s
+    'events_prior_single1000': lambda: events_fixture_large(
+        'events_prior_single1000.npz', po.RATE_PRIOR, 3026, 1, 1000,
+        dwell_pair=(1500000, 1500000)),
+    'rates': rates_fixture,
+    'standardize': standardize_fixture,
+    'frames': frames_fixture,
+    'perception': perception_fixture,
+    'episodes': episodes_fixture,
+    'env': env_fixture,
+    'proto': proto_fixture,
+    'synth': synth_fixture,
+}
+
 if __name__ == '__main__':
+  # python tests/golden/make_golden.py [fixture ...]   (default: all)
   if not refshim.reference_available():
     sys.exit('reference not available; golden vectors are generated only in '
              'the build container')
-  events_fixture('events_simple.npz', po.RATE_SIMPLE, 2024, 32, 30)
-  events_fixture('events_prior.npz', po.RATE_PRIOR, 2025, 32, 30)
-  events_fixture('events_gmm.npz', po.RATE_GMM, 2026, 24, 20, gmm=GMM_PARAMS)
-  rates_fixture()
-  standardize_fixture()
-  frames_fixture()
-  perception_fixture()
-  episodes_fixture()
-  env_fixture()
-  proto_fixture()
-  synth_fixture()
+  for fixture in (sys.argv[1:] or list(FIXTURES)):
+    FIXTURES[fixture]()

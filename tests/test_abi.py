@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
   lib = ctypes.CDLL(str(nat.LIB_PATH))
   for name in _declared_functions():
     assert hasattr(lib, name), f'{name} declared in header but not exported'
-  assert nat.lib.pd_abi_version() == 1
+  assert nat.lib.pd_abi_version() == 2  # 2: pd_rate_config.prior
 
 
 def test_python_binding_covers_header():

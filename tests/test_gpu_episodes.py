@@ -45,12 +45,14 @@ def test_episodes_match_oracle_4096():
   b, s, goal_site, goal_xy = _run(n, seed, po.RATE_SIMPLE)
   np.testing.assert_array_equal(goal_site, want['goal_site'])
   np.testing.assert_allclose(goal_xy, want['goal_pos'], rtol=0, atol=1e-12)
-  # float32 trig in the controller can differ from NumPy's by an ulp, which
-  # moves a waiting time by ~1e-7 relative; episode outcomes only change when
-  # that crosses the end of a dwell (~1e-7 per event).
+  # The controller's float32 trigonometry is evaluated in float64 and rounded
+  # on both sides (pd_episode.cuh, pdune_oracle_episode.py), so the control
+  # positions agree to the bit except when a float64 result sits within
+  # ~2 ulp of a float32 rounding boundary (~1e-8 per evaluation, 1e-3 for the
+  # ~1e5 evaluations of this test): every episode must agree.
   same = (s['num_actions'] == want['num_actions']) & (
       s['reached_goal'].astype(bool) == want['reached'])
-  assert same.mean() >= 0.999, same.mean()
+  assert same.all(), (int((~same).sum()), 'episodes differ')
   ok = same & want['reached']
   np.testing.assert_allclose(s['env_seconds'][ok], want['env_seconds'][ok],
                              rtol=1e-6)

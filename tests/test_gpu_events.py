@@ -100,13 +100,20 @@ def test_rates_match_oracle_and_reference_golden(eng, golden_dir):
       assert np.abs(r - fix['rates_prior']).max() <= tol
 
 
-@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz'])
+@pytest.mark.parametrize('name', [
+    'events_simple.npz', 'events_prior.npz',
+    # 256 envs x 100 steps per rate function and one env x 1000 steps
+    # (BASELINE configs[0]) from the unmodified reference
+    'events_simple_large.npz', 'events_prior_large.npz',
+    'events_prior_single1000.npz'])
 def test_reference_golden_trajectories(eng, golden_dir, name):
   """The reference's own trajectories, replayed through the C ABI with the
   device doing its own reset."""
+  from tests.test_oracle import expand_controls
   fix = np.load(os.path.join(golden_dir, name))
-  controls, dwell = fix['controls'], fix['dwell_us']
+  controls, dwell = expand_controls(fix)
   n_steps, n = controls.shape[:2]
+  compact = 'fov_last' in fix
   b = eng.EnvBatch(n, seed=int(fix['seed']), log_capacity=64)
   b.reset()
   np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si0'])
@@ -120,8 +127,10 @@ def test_reference_golden_trajectories(eng, golden_dir, name):
     np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si'][:, t])
     np.testing.assert_array_equal(gh.np_(out.elapsed_us),
                                   fix['elapsed_us'][:, t])
-    np.testing.assert_allclose(gh.np_(b.fov), fix['fov'][:, t], rtol=0,
-                               atol=1e-13)
+    np.testing.assert_allclose(
+        gh.np_(b.fov),
+        fix['fov_last'] if compact else fix['fov'][:, t], rtol=0,
+        atol=1e-13) if (not compact or t == n_steps - 1) else None
     cnt = gh.np_(out.log_count)
     el, site = gh.np_(out.log_elapsed_us), gh.np_(out.log_site)
     for e in np.nonzero(cnt)[0]:
@@ -132,7 +141,67 @@ def test_reference_golden_trajectories(eng, golden_dir, name):
   got = np.asarray(sorted(trans), dtype=np.int64)
   np.testing.assert_array_equal(got, want)
   xy, z, count = b.get_atoms_in_bounds()
-  np.testing.assert_array_equal(gh.np_(count), fix['n_observed'][:, -1])
+  np.testing.assert_array_equal(
+      gh.np_(count),
+      fix['n_observed_last'] if compact else fix['n_observed'][:, -1])
+
+
+PRIOR_CUSTOM = {  # as in make_golden: HumanPriorRatePredictor(mean, cov, max)
+    'mean': (0.7, 0.15),
+    'cov': ((0.12, 0.03), (0.03, 0.07)),
+    'max_rate': 0.4,
+}
+
+
+def test_custom_human_prior(eng, golden_dir):
+  """HumanPriorRatePredictor(mean, cov, max_rate) with non-default parameters
+  (graphene.py:181-229): rates against the reference's own (golden) and
+  4096 envs x 40 steps of trajectories against the oracle, through
+  step_and_image and through the rollout kernels; parameters equal to the
+  defaults take the specialised path and give identical results."""
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  spec = eng.RateSpec.prior(**PRIOR_CUSTOM)
+  r, nb = b.rates(fix['beam'], spec)
+  np.testing.assert_array_equal(gh.np_(nb), fix['succ_prior_custom'])
+  want = fix['rates_prior_custom']
+  assert np.abs(gh.np_(r) - want).max() <= 2e-6 * want.max() + 1e-12
+  assert want.max() > 0.05
+  # trajectories
+  n, t_steps, seed = 4096, 40, 19
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  c = gh.batch_from_oracle(st)
+  rng = np.random.default_rng(2)
+  ctl_all = np.zeros((t_steps, n, 2))
+  for t in range(t_steps):
+    ctl = gh.closed_loop_control(st, rng)
+    ctl_all[t] = ctl
+    wanted = po.step_and_image(st, ctl[:, None, :], 3000000,
+                               rate_fn=po.RATE_PRIOR, prior=PRIOR_CUSTOM)
+    out = b.step_and_image(ctl[:, None, :], 3000000, spec)
+    np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
+    np.testing.assert_array_equal(gh.np_(out.elapsed_us), wanted['elapsed_us'])
+    np.testing.assert_array_equal(gh.np_(out.transitions),
+                                  wanted['transitions'])
+  assert st.n_transitions.sum() > 5000
+  si, _ = c.rollout(ctl_all, 3000000, spec, record=True)
+  np.testing.assert_array_equal(gh.np_(si[-1]), st.si_idx)
+  np.testing.assert_array_equal(gh.np_(c.n_events), st.n_events)
+  # defaults passed explicitly == the specialised human prior
+  d0, d1 = eng.EnvBatch(512, seed=3), eng.EnvBatch(512, seed=3)
+  d0.reset()
+  d1.reset()
+  ctl = np.full((512, 1, 2), 0.52)
+  o0 = d0.step_and_image(ctl, 5000000, eng.RateSpec.prior())
+  o1 = d1.step_and_image(ctl, 5000000, eng.RateSpec.prior(
+      (0.85, 0.0), ((0.1, 0.0), (0.0, 0.1)), np.log(2) / 3))
+  np.testing.assert_array_equal(gh.np_(d0.si_idx), gh.np_(d1.si_idx))
+  np.testing.assert_array_equal(gh.np_(o0.events), gh.np_(o1.events))
 
 
 @pytest.mark.parametrize('rate_fn', [po.RATE_SIMPLE, po.RATE_PRIOR])

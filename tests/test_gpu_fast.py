@@ -285,3 +285,29 @@ def test_fast_rollout_consecutive_calls(eng, nat):
     np.testing.assert_array_equal(x[1], y[1], err_msg=f'call {i} elapsed')
     for k in STATE_KEYS:
       np.testing.assert_array_equal(x[2][k], y[2][k], err_msg=f'call {i} {k}')
+
+
+def test_rate_ops_audit(eng, nat):
+  """the default build's float64 rate expressions are not
+  the reference's operation sequence.  Over 3 x 10^8 evaluations per rate
+  function: the simple rate's float32 value never differs from the operation
+  sequence's (the cast guard catches every case; the simple rate is pure
+  float64 NumPy upstream, so that is the reference's value), and the human
+  prior's differs at the printed rate (it is JAX float32 upstream: covered by
+  the stated rate tolerance, not defined to the bit)."""
+  lat = eng.Lattice(50)
+  out = nat.PdRateOpsStats()
+  nat.check(nat.lib.pd_rate_ops_audit(C.byref(lat.c), 99, 100_000_000, 1.42,
+                                      C.byref(out), None))
+  print(f'\nrate ops audit: {out.evaluations} evaluations per rate fn; simple: '
+        f'max {out.simple_max_ulps} ulp between the forms (guard '
+        f'{out.guard_ulps}), casts differing before the guard '
+        f'{out.simple_cast_differs_unguarded}, guard taken '
+        f'{out.simple_guard_taken}, after the guard {out.simple_cast_differs}; '
+        f'prior: max {out.prior_max_ulps} ulp, casts differing '
+        f'{out.prior_cast_differs}')
+  assert out.evaluations == 300_000_000
+  assert out.simple_cast_differs == 0
+  assert out.simple_max_ulps * 4 <= out.guard_ulps
+  assert out.simple_guard_taken < 2e-4 * out.evaluations
+  assert out.prior_cast_differs < 1e-5 * out.evaluations

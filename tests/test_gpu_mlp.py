@@ -137,8 +137,11 @@ def test_learned_step_close_to_independent_oracle():
     ctl = gh.closed_loop_control(st, rng)[:, None, :]
     po.step_and_image(st, ctl, 5000000, rate_fn=po.RATE_LEARNED, mlp=mlp)
     b.step_and_image(ctl, 5000000, spec)
+  # float32 sums of the network run in a different order on the device
+  # (rates agree to 2e-5): an event changes its outcome with ~1e-5, so of the
+  # ~5e4 events of this test fewer than one is expected to; at most 4 envs
   same = gh.np_(b.si_idx) == st.si_idx
-  assert same.mean() >= 0.999, same.mean()
+  assert (~same).sum() <= 4, int((~same).sum())
   assert st.n_transitions.sum() > 1000
 
 

@@ -72,6 +72,29 @@ def test_render_stages_match_oracle(size):
   _check_stage('final', f1[n - 1], oi.render_env(st2, n - 1, size=size))
 
 
+def test_benchmarked_render_config_sampled_vs_oracle():
+  """BASELINE configs[3] as bench.py runs it: one pd_render launch over
+  16,384 frames of 512 x 512; 16 randomly chosen frames of it against the
+  imaging oracle, stage by stage."""
+  from putting_dune_b200 import imaging
+  n, seed = 16384, 3
+  st = po.make_state(n, seed)
+  po.reset(st)
+  b = gh.batch_from_oracle(st)
+  pick = np.sort(np.random.default_rng(11).choice(n, size=16, replace=False))
+  want = {int(e): oi.render_env(st, int(e), size=512, stages=True)
+          for e in pick}
+  out = torch.empty((n, 512, 512), dtype=torch.float32, device=b.device)
+  for k, name in enumerate(STAGES):
+    imaging.render_batch(b, image_size=512, stop_stage=k, out=out,
+                         advance_frame_count=False)
+    got = gh.np_(out[torch.as_tensor(pick, device=b.device)])
+    for j, e in enumerate(pick):
+      _check_stage(name, got[j], want[int(e)][name])
+  del out
+  torch.cuda.empty_cache()
+
+
 def test_render_matches_reference_golden_frames(golden_dir):
   from putting_dune_b200 import engine, imaging
   fix = np.load(os.path.join(golden_dir, 'frames_reference.npz'))

@@ -66,11 +66,30 @@ GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
 }
 
 
+PRIOR_CUSTOM = {  # as in make_golden: HumanPriorRatePredictor(mean, cov, max)
+    'mean': (0.7, 0.15),
+    'cov': ((0.12, 0.03), (0.03, 0.07)),
+    'max_rate': 0.4,
+}
+
+
 # -- event-path golden vectors from the reference ------------------------------
+def expand_controls(fix):
+  """(controls float64 [T, E, C, 2], dwell_us int64 [T, E, C]) of an event
+  fixture; the large ones store float32-valued controls and one dwell time
+  per env."""
+  controls = np.asarray(fix['controls'], dtype=np.float64)
+  dwell = np.asarray(fix['dwell_us'])
+  if dwell.ndim == 1:
+    dwell = np.broadcast_to(dwell[None, :, None],
+                            controls.shape[:3]).astype(np.int64)
+  return controls, dwell
+
+
 def _replay(fix):
   seed = int(fix['seed'])
   rate_fn = int(fix['rate_fn'])
-  controls, dwell = fix['controls'], fix['dwell_us']
+  controls, dwell = expand_controls(fix)
   n_steps, n_envs = controls.shape[:2]
   st = po.make_state(n_envs, seed)
   po.reset(st)
@@ -88,11 +107,28 @@ def _replay(fix):
   return st, reset_state, si, el, fov, np.asarray(trans, dtype=np.int64)
 
 
-@pytest.mark.parametrize('name', ['events_simple.npz', 'events_prior.npz',
-                                  'events_gmm.npz'])
+@pytest.mark.parametrize('name', [
+    'events_simple.npz', 'events_prior.npz', 'events_gmm.npz',
+    # 256 envs x 100 steps per rate function; one env x 1000 steps (BASELINE
+    # configs[0]) -- the unmodified reference, env by env
+    'events_simple_large.npz', 'events_prior_large.npz',
+    'events_prior_single1000.npz'])
 def test_oracle_matches_reference_trajectories(golden_dir, name):
   fix = np.load(os.path.join(golden_dir, name))
   st, r0, si, el, fov, trans = _replay(fix)
+  if 'fov_last' in fix:  # compact fixture
+    np.testing.assert_array_equal(r0['si'], fix['si0'])
+    np.testing.assert_allclose(r0['fov'], fix['fov0'], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(r0['ip'], fix['image_params'], rtol=0, atol=0)
+    np.testing.assert_array_equal(si, fix['si'])
+    np.testing.assert_array_equal(el, fix['elapsed_us'])
+    want = fix['transitions']
+    want = want[np.lexsort((want[:, 2], want[:, 1], want[:, 0]))]
+    np.testing.assert_array_equal(trans, want)
+    np.testing.assert_allclose(fov[:, -1], fix['fov_last'], rtol=0,
+                               atol=1e-13)
+    assert want.shape[0] >= 100
+    return
   # reset: Si site, FOV, image parameters
   np.testing.assert_array_equal(r0['si'], fix['si0'])
   np.testing.assert_allclose(r0['fov'], fix['fov0'], rtol=0, atol=1e-13)
@@ -135,8 +171,11 @@ def test_oracle_rates_match_reference(golden_dir):
   np.testing.assert_allclose(r64, fix['rates_gmm'], rtol=1e-12, atol=1e-300)
   for name, rate_fn, rtol in (('simple', po.RATE_SIMPLE, 0.0),
                               ('prior', po.RATE_PRIOR, 1e-6),
-                              ('learned', po.RATE_LEARNED, 1e-6)):
-    r32, nbr = po.rates_for(st, envs, fix['beam'], rate_fn, mlp)
+                              ('learned', po.RATE_LEARNED, 1e-6),
+                              ('prior_custom', po.RATE_PRIOR, 1e-6)):
+    r32, nbr = po.rates_for(
+        st, envs, fix['beam'], rate_fn, mlp,
+        prior=PRIOR_CUSTOM if name == 'prior_custom' else None)
     np.testing.assert_array_equal(nbr, fix[f'succ_{name}'])
     want = fix[f'rates_{name}']
     if rtol == 0.0:
