@@ -381,6 +381,15 @@ int pd_rollout_actions_host_packed(
  * environment variable PD_FAST=0 sets the default to 0. */
 int pd_set_fast_path(int enabled);
 
+/* Process-wide kernel-selection options (A/B timing and the parity tests that
+ * compare the kernels with each other); each is initialised once from the
+ * environment variable of the same meaning.  value: 0 / 1.
+ *   "fast_path"     PD_FAST          guarded float32 iteration (above)
+ *   "prepass"       PD_PREPASS       float32 pre-pass of the float64 kernels
+ *   "rollout_spec"  PD_ROLLOUT_SPEC  look-ahead over idle lanes in small
+ *                                    float64 rollouts */
+int pd_set_option(const char* name, int value);
+
 /* Measures the float32 quantities of that iteration against the float64 ones
  * over n_samples random iterations (random site, lattice angle, beam offset
  * within max_distance of the Si, Philox draw, clock).  The *_over_bound

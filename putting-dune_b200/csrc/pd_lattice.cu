@@ -81,7 +81,17 @@ __global__ void __launch_bounds__(1024, 1)
     const int xk = 2 * ik + (jk & 1);
     long long best_d[3] = {LLONG_MAX, LLONG_MAX, LLONG_MAX};
     int best_m[3] = {-1, -1, -1};
-    for (int m = 0; m < s.n_sites; ++m) {
+    // Every site has three others within two bond lengths (4 d^2 <= 16) in
+    // its own and the two rows on either side, and three rows away start at
+    // 4 d^2 = 27: rows jk - 3 .. jk + 3 hold the three nearest (ids are row
+    // major, so that is one contiguous id range).
+    const int pair = s.cnt_even + s.cnt_odd;
+    const int j_lo = jk - 3 < 0 ? 0 : jk - 3;
+    const int j_hi = jk + 4 > s.n_rows ? s.n_rows : jk + 4;  // exclusive
+    const int m_lo = (j_lo / 2) * pair + (j_lo & 1) * s.cnt_even;
+    int m_hi = (j_hi / 2) * pair + (j_hi & 1) * s.cnt_even;
+    if (m_hi > s.n_sites) m_hi = s.n_sites;
+    for (int m = m_lo; m < m_hi; ++m) {
       if (m == k) continue;
       int im, jm;
       site_ij(s, m, &im, &jm);

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <chrono>
 #include <vector>
@@ -1501,16 +1502,26 @@ static int env_int(const char* name, int fallback) {
 
 // PD_PREPASS=0 sends every iteration through the float64 chain (A/B timing,
 // parity tests).
-static bool prepass_enabled() {
-  const char* v = getenv("PD_PREPASS");
-  return !v || v[0] != '0';
+// Process-wide options: read from the environment once, changed at run time
+// through pd_set_option (tests, A/B timing).
+static int& option_prepass() {
+  static int on = [] {
+    const char* v = getenv("PD_PREPASS");
+    return (!v || v[0] != '0') ? 1 : 0;
+  }();
+  return on;
 }
+static int& option_rollout_spec() {
+  static int on = [] {
+    const char* v = getenv("PD_ROLLOUT_SPEC");
+    return (!v || v[0] != '0') ? 1 : 0;
+  }();
+  return on;
+}
+static bool prepass_enabled() { return option_prepass() != 0; }
 
 // PD_ROLLOUT_SPEC=0 keeps the serial k_rollout (A/B timing, parity tests).
-static bool speculation_enabled() {
-  const char* v = getenv("PD_ROLLOUT_SPEC");
-  return !v || v[0] != '0';
-}
+static bool speculation_enabled() { return option_rollout_spec() != 0; }
 
 template <int RATE, bool STAGE, int STREAM = 0>
 static auto rollout_pre_kernel() -> void (*)(const StepArgs) {
@@ -1624,9 +1635,13 @@ static int launch_step(const StepArgs& a_in, bool rollout,
   a.lane_stride = plan.lane_stride;
   a.keys = philox_keys_host(a.st.seed);
   a.prepass = prepass_enabled() ? 1 : 0;
-  a.walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
-  a.walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
-  a.walk_controls_per_pass = env_int("PD_WALK_CONTROLS", 4);
+  // PD_* knobs are read once per process, not per launch
+  static const int walk_min_ready = env_int("PD_WALK_MIN_READY", 12);
+  static const int walk_max_reps = env_int("PD_WALK_MAX_REPS", 4);
+  static const int walk_controls = env_int("PD_WALK_CONTROLS", 4);
+  a.walk_min_ready = walk_min_ready;
+  a.walk_max_reps = walk_max_reps;
+  a.walk_controls_per_pass = walk_controls;
   if constexpr (kHasPrepass) {
     // Rollouts with one positive dwell time below the reference's waiting
     // time cap (graphene.py:668; pd_fast.cuh kFastMaxDwellS): every decision
@@ -1851,6 +1866,20 @@ extern "C" int pd_set_fast_path(int enabled) {
   const int before = pd::fast_flag();
   pd::fast_flag() = enabled ? 1 : 0;
   return before;
+}
+
+extern "C" int pd_set_option(const char* name, int value) {
+  PD_REQUIRE(name != nullptr, "null option name");
+  int* slot = nullptr;
+  if (!strcmp(name, "fast_path")) slot = &pd::fast_flag();
+  if (!strcmp(name, "prepass")) slot = &pd::option_prepass();
+  if (!strcmp(name, "rollout_spec")) slot = &pd::option_rollout_spec();
+  if (!slot) {
+    pd::set_error("pd_set_option: unknown option '%s'", name);
+    return PD_ERR_INVALID_ARGUMENT;
+  }
+  *slot = value ? 1 : 0;
+  return PD_OK;
 }
 
 extern "C" int pd_rates(const pd_lattice* lat, const pd_state* st,

@@ -208,6 +208,7 @@ _SIGNATURES['pd_rate_ops_audit'] = (
 _SIGNATURES['pd_rollout_actions_host_packed'] = (
     [_LP, _SP, _RP, _p, _i32, C.c_double, _i64, _i32, _i64, _p, _p], C.c_int)
 _SIGNATURES['pd_set_fast_path'] = ([C.c_int], C.c_int)
+_SIGNATURES['pd_set_option'] = ([C.c_char_p, C.c_int], C.c_int)
 _SIGNATURES['pd_fast_path_audit'] = (
     [_LP, _i32, C.c_uint64, _i64, _i64, C.c_double, C.POINTER(PdFastAudit),
      _p], C.c_int)

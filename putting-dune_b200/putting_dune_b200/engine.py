@@ -424,9 +424,21 @@ class EnvBatch:
       act = act.to(torch.float64)
     if act.ndim != 3 or act.shape[1] != self.num_envs or act.shape[2] != 2:
       raise ValueError(f'actions must be [T, E, 2], got {tuple(act.shape)}')
+    # int32 microseconds hold dwell + 2 image durations up to ~35 minutes;
+    # beyond that the float32 actions are widened (exactly) and the call takes
+    # the float64 / int64 entry point
+    if (act.dtype == torch.float32 and
+        int(dwell_us) + 2 * int(image_duration_us) >= 2 ** 31):
+      act = act.to(torch.float64)
     act = act.contiguous()
     if not act.is_pinned():
-      act = act.pin_memory()
+      # one page-locked input buffer per (shape, dtype), re-used across calls
+      key = (tuple(act.shape), act.dtype)
+      if getattr(self, '_pinned_in_key', None) != key:
+        self._pinned_in = torch.empty(act.shape, dtype=act.dtype).pin_memory()
+        self._pinned_in_key = key
+      self._pinned_in.copy_(act)
+      act = self._pinned_in
     t, e = act.shape[0], self.num_envs
     wide = act.dtype == torch.float64
     el_dtype = torch.int64 if wide else torch.int32

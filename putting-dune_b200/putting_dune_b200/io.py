@@ -62,9 +62,16 @@ class TrajectoryRecorder:
   Trajectory(...).to_proto() (microscope_utils.py:737-757, io.py:65-82).
 
     rec = TrajectoryRecorder(batch)
-    rec.record(controls_xy=None, dwell_us=0)     # after reset
-    batch.step_and_image(ctl, dwell, rate); rec.record(ctl, dwell)
+    rec.record(None, 0, elapsed_us=image_duration_us)     # after reset
+    out = batch.step_and_image(ctl, dwell, rate)
+    rec.record(ctl, dwell, elapsed_us=out.elapsed_us)
     rec.write('run.tfrecords')
+
+  ``elapsed_us`` is the observation's ``elapsed_time``: per step in the
+  reference (simulator.py:100-105,131-182: the image duration after reset,
+  dwell + image time(s) after a step), so it has to be passed -- the
+  ``StepResult.elapsed_us`` of the step, an int for all envs, or 'sim_time'
+  for the cumulative simulated clock of the batch.
   """
 
   def __init__(self, batch, voltage_kv: float = 60.0, current_na: float = 0.1,
@@ -77,6 +84,18 @@ class TrajectoryRecorder:
   def record(self, controls_xy=None, dwell_us=0, elapsed_us=None) -> None:
     b = self.batch
     n, dev = b.num_envs, b.device
+    if elapsed_us is None:
+      raise ValueError(
+          "elapsed_us is required: the step's StepResult.elapsed_us, the "
+          "image duration (int, microseconds) for the observation after "
+          "reset, or 'sim_time' for the batch's cumulative clock")
+    if isinstance(elapsed_us, str):
+      if elapsed_us != 'sim_time':
+        raise ValueError(f'unknown elapsed_us {elapsed_us!r}')
+      elapsed_us = None  # the encoder reads st.sim_time_us
+    elif isinstance(elapsed_us, (int, np.integer)):
+      elapsed_us = torch.full((n,), int(elapsed_us), dtype=torch.int64,
+                              device=dev)
     if controls_xy is None:
       ctl = torch.zeros((n, 0, 2), dtype=torch.float64, device=dev)
     else:

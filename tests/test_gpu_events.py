@@ -24,6 +24,15 @@ def eng():
   return engine
 
 
+@pytest.fixture(autouse=True)
+def _default_options():
+  """Kernel-selection options back to their defaults after every test."""
+  yield
+  from putting_dune_b200 import _native as nat
+  for name in (b'fast_path', b'prepass', b'rollout_spec'):
+    nat.lib.pd_set_option(name, 1)
+
+
 def site_classes(cols):
   """0 / 1: bulk site whose three nearest neighbours are the bonded ones at
   (-1/2, -r), (1, 0), (-1/2, r) bond lengths (r = sqrt(3)/2) / the negatives
@@ -495,9 +504,12 @@ def test_rollout_speculative_equals_serial(eng, n, monkeypatch):
     res = []
     # k_rollout_pre (float32 look-ahead), k_rollout_spec (float64
     # speculation), k_rollout (serial)
-    for flag, pre in (('1', '1'), ('1', '0'), ('0', '0')):
-      monkeypatch.setenv('PD_ROLLOUT_SPEC', flag)
-      monkeypatch.setenv('PD_PREPASS', pre)
+    for flag, pre in ((1, 1), (1, 0), (0, 0)):
+      # (the float64 kernels: the fast path would take the prior / simple
+      # rollouts otherwise)
+      nat.check(nat.lib.pd_set_option(b'fast_path', 0))
+      nat.check(nat.lib.pd_set_option(b'rollout_spec', flag))
+      nat.check(nat.lib.pd_set_option(b'prepass', pre))
       b = eng.EnvBatch(n, seed=seed)
       b.reset()
       # a FOV the Si is not centred in: the t = 0 safe-area check matters
@@ -533,8 +545,11 @@ def test_prepass_equals_exact(eng, monkeypatch):
   dwell3 = rng.integers(0, 4000000, size=(n, 3))
   beam_m = rng.uniform(-3, 3, size=(n, 1, 2))
   results = []
-  for flag in ('1', '0'):
-    monkeypatch.setenv('PD_PREPASS', flag)
+  for flag in (1, 0):
+    # k_walk's float32 pre-pass on / off (with the fast path off: it would
+    # take the rollouts otherwise)
+    nat.check(nat.lib.pd_set_option(b'fast_path', 0))
+    nat.check(nat.lib.pd_set_option(b'prepass', flag))
     out = []
     for rate_fn in (po.RATE_PRIOR, po.RATE_SIMPLE):
       spec = gh.rate_spec(rate_fn)

@@ -59,7 +59,7 @@ def test_device_encoder_matches_wire_codec(eng):
     po.step_and_image(st, ctl, dwell, rate_fn=po.RATE_SIMPLE)
     b.step_and_image(ctl, dwell, spec)
     np.testing.assert_array_equal(gh.np_(b.si_idx), st.si_idx)
-    rec.record(ctl, dwell)
+    rec.record(ctl, dwell, elapsed_us='sim_time')
     by, off, ln, atoms = rec._steps[-1]
     assert (off % 16 == 0).all()
     for e in range(n):
@@ -96,7 +96,7 @@ def test_encoder_overflow_and_empty_views(eng):
   st.fov[3] = [500.0, 500.0, 520.0, 520.0]
   st.fov[4] = [-80.0, -80.0, 80.0, 80.0]
   rec = pio.TrajectoryRecorder(b, max_atoms=b.lattice_tables.n_sites)
-  rec.record(np.full((n, 1, 2), 0.5), 1500000)
+  rec.record(np.full((n, 1, 2), 0.5), 1500000, elapsed_us='sim_time')
   by, off, ln, atoms = rec._steps[-1]
   assert atoms[3] == 0 and atoms[4] == b.lattice_tables.n_sites
   for e in (3, 4, 5):
@@ -105,7 +105,9 @@ def test_encoder_overflow_and_empty_views(eng):
     assert by[off[e]:off[e] + ln[e]].tobytes() == want
   small = pio.TrajectoryRecorder(b, max_atoms=64)
   with pytest.raises(RuntimeError, match='max_atoms'):
-    small.record(np.full((n, 1, 2), 0.5), 1500000)
+    small.record(np.full((n, 1, 2), 0.5), 1500000, elapsed_us='sim_time')
+  with pytest.raises(ValueError, match='elapsed_us is required'):
+    rec.record(np.full((n, 1, 2), 0.5), 1500000)
 
 
 @pytest.mark.parametrize('num_states,context_dim,time_range',

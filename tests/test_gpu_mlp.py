@@ -157,6 +157,10 @@ def test_apply_model_ensemble():
   got = gh.np_(pred.apply_model(x))
   want = po.apply_model(models, x)
   np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-7)
+  # and against the independent float64 network (tests/mlp_independent.py)
+  from tests import mlp_independent as mi
+  np.testing.assert_allclose(got, mi.apply_model(models, x), rtol=2e-5,
+                             atol=1e-7)
   one = gh.np_(pred.apply_model(x, model_index=1))
   np.testing.assert_allclose(one, po.apply_model(models[1:2], x), rtol=2e-5,
                              atol=1e-7)

@@ -529,3 +529,29 @@ def test_synthetic_data_oracle_network_mode():
   np.testing.assert_allclose(frac, want / total, atol=0.01)
   other = osy.generate_synthetic_data_network(n, 11, 1, net)
   assert not np.array_equal(other['position'], out['position'])
+
+
+def test_mlp_restatement_against_independent_float64():
+  """a9 / a10 (parity unpinned: Haiku and TF are absent): the oracle's float32
+  NumPy network against an independent float64 torch.nn.functional one."""
+  from tests import mlp_independent as mi
+  rng = np.random.default_rng(3)
+  for hidden in ((32, 32), (128, 128), (256, 256), (48, 128)):
+    models = []
+    for seed in (1, 2, 3):
+      m = po.MlpParams.synthetic(seed, hidden=hidden)
+      m.bn_mean = rng.normal(0, 0.3, 2).astype(np.float32)
+      m.bn_var = rng.uniform(0.5, 2.0, 2).astype(np.float32)
+      m.bn_scale = rng.uniform(0.5, 1.5, 2).astype(np.float32)
+      m.bn_offset = rng.normal(0, 0.2, 2).astype(np.float32)
+      m.b0 = rng.normal(0, 0.1, hidden[0]).astype(np.float32)
+      m.b1 = rng.normal(0, 0.1, hidden[1]).astype(np.float32)
+      m.b2 = rng.normal(0, 0.1, 4).astype(np.float32)
+      models.append(m)
+    x = rng.uniform(-2.0, 2.0, size=(500, 2)).astype(np.float32)
+    o = po.mlp_forward(models[0], x)
+    want = mi.forward(models[0], x)
+    assert np.abs(o - want).max() <= 3e-6 * np.abs(want).max()
+    r = po.apply_model(models, x)
+    want = mi.apply_model(models, x)
+    assert np.abs(r - want).max() <= 3e-6 * np.abs(want).max()
