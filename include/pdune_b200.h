@@ -387,7 +387,15 @@ int pd_set_fast_path(int enabled);
  *   "fast_path"     PD_FAST          guarded float32 iteration (above)
  *   "prepass"       PD_PREPASS       float32 pre-pass of the float64 kernels
  *   "rollout_spec"  PD_ROLLOUT_SPEC  look-ahead over idle lanes in small
- *                                    float64 rollouts */
+ *                                    float64 rollouts
+ *   "race_sampling" PD_SAMPLING_RACE (default 0) events by the race of
+ *                                    competing exponentials -- each neighbour
+ *                                    draws Exp(rate_i), the smallest wins --
+ *                                    instead of the reference's direct method
+ *                                    (graphene.py:658-694).  Equal in
+ *                                    distribution, not draw for draw: never
+ *                                    the parity path.  Scalar rate functions
+ *                                    only (not PD_RATE_LEARNED). */
 int pd_set_option(const char* name, int value);
 
 /* Measures the float32 quantities of that iteration against the float64 ones

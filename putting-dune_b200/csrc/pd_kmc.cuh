@@ -91,6 +91,7 @@ constexpr int kRatePriorGeneral = 100;
 
 struct RateArgs {
   float constant_rates[3];
+  int32_t race_sampling;  // 1: kmc_event_race instead of the direct method
   // HumanPriorRatePredictor(mean, cov, max_rate): mean, the precision matrix
   // cov^-1 as (p00, p01 + p10, p11), max_rate
   int32_t prior_general;
@@ -756,6 +757,41 @@ __device__ __forceinline__ void eval_rates(const RateArgs& ra,
   }
 }
 
+// One event by the race of competing exponentials (first-reaction method):
+// every neighbour draws its own waiting time Exp(rate_i), the smallest one
+// happens.  Equal in distribution to the direct method above (waiting time
+// Exp(total), neighbour i with probability rate_i / total) but not draw for
+// draw, so this is an opt-in sampling mode (pd_set_option "race_sampling"),
+// never the parity path.  The three uniforms are the 53-bit waiting-time
+// uniform of the direct method and the two 26-bit halves of its choice
+// uniform (+ half a step, so that none is 0).
+__device__ __forceinline__ bool kmc_event_race(const double r[3], double u_exp,
+                                               double u_choice,
+                                               long long dwell_us,
+                                               long long* elapsed_us,
+                                               int* slot) {
+  const double scaled = u_choice * 67108864.0;  // 2^26
+  const double hi = floor(scaled);
+  const double u[3] = {u_exp, (hi + 0.5) * (1.0 / 67108864.0),
+                       (scaled - hi) * (1.0 - 1.0 / 134217728.0) +
+                           1.0 / 268435456.0};
+  double t = kMaxTransitionSeconds * 4.0;
+  int best = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double ti = r[i] > 0.0 ? -log1p(-u[i]) / r[i]
+                                 : kMaxTransitionSeconds * 4.0;
+    if (ti < t) {
+      t = ti;
+      best = i;
+    }
+  }
+  *elapsed_us += seconds_to_us(fmin(t, kMaxTransitionSeconds));
+  if (*elapsed_us > dwell_us) return false;
+  *slot = best;
+  return true;
+}
+
 // Rates + one event of the direct method.  Float64-rate functions (GMM) keep
 // the total in float64 (see kmc_event_drawn64).
 template <int RATE>
@@ -770,11 +806,18 @@ __device__ __forceinline__ bool rate_event(const RateArgs& ra,
     double r64[3];
     rates_gmm(ra, beam, psi, pn, r64);
     *bad = false;
+    if (ra.race_sampling)
+      return kmc_event_race(r64, u_exp, u_choice, dwell_us, elapsed_us, slot);
     return kmc_event_drawn64(r64, -log1p(-u_exp), u_choice, dwell_us,
                              elapsed_us, slot);
   } else {
     float r[3];
     eval_rates<RATE>(ra, beam, psi, pn, r);
+    if (ra.race_sampling) {
+      *bad = !(r[0] >= 0.f) || !(r[1] >= 0.f) || !(r[2] >= 0.f);
+      const double r64[3] = {r[0], r[1], r[2]};
+      return kmc_event_race(r64, u_exp, u_choice, dwell_us, elapsed_us, slot);
+    }
     return kmc_event(r, u_exp, u_choice, dwell_us, elapsed_us, slot, bad);
   }
 }

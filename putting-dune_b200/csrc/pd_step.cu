@@ -1518,7 +1518,17 @@ static int& option_rollout_spec() {
   }();
   return on;
 }
-static bool prepass_enabled() { return option_prepass() != 0; }
+static int& option_race_sampling() {
+  static int on = [] {
+    const char* v = getenv("PD_SAMPLING_RACE");
+    return (v && v[0] == '1') ? 1 : 0;
+  }();
+  return on;
+}
+// (the float32 pre-pass and the fast kernels reason about the direct method)
+static bool prepass_enabled() {
+  return option_prepass() != 0 && option_race_sampling() == 0;
+}
 
 // PD_ROLLOUT_SPEC=0 keeps the serial k_rollout (A/B timing, parity tests).
 static bool speculation_enabled() { return option_rollout_spec() != 0; }
@@ -1620,7 +1630,10 @@ static int& fast_flag() {
   }();
   return on;
 }
-static bool fast_enabled() { return fast_flag() != 0; }
+static int& option_race_sampling();
+static bool fast_enabled() {
+  return fast_flag() != 0 && option_race_sampling() == 0;
+}
 
 template <int RATE>
 static int launch_step(const StepArgs& a_in, bool rollout,
@@ -1703,6 +1716,7 @@ int fill_rate_args(const pd_rate_config* rc, RateArgs* ra) {
   for (int i = 0; i < 3; ++i) ra->constant_rates[i] = rc->constant_rates[i];
   ra->gmm_n = 0;
   ra->prior_general = 0;
+  ra->race_sampling = option_race_sampling();
   if (rc->rate_fn == PD_RATE_PRIOR && rc->prior) {
     const pd_prior* p = rc->prior;
     const bool defaults = p->mean[0] == 0.85 && p->mean[1] == 0.0 &&
@@ -1874,6 +1888,7 @@ extern "C" int pd_set_option(const char* name, int value) {
   if (!strcmp(name, "fast_path")) slot = &pd::fast_flag();
   if (!strcmp(name, "prepass")) slot = &pd::option_prepass();
   if (!strcmp(name, "rollout_spec")) slot = &pd::option_rollout_spec();
+  if (!strcmp(name, "race_sampling")) slot = &pd::option_race_sampling();
   if (!slot) {
     pd::set_error("pd_set_option: unknown option '%s'", name);
     return PD_ERR_INVALID_ARGUMENT;

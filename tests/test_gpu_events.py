@@ -31,6 +31,7 @@ def _default_options():
   from putting_dune_b200 import _native as nat
   for name in (b'fast_path', b'prepass', b'rollout_spec'):
     nat.lib.pd_set_option(name, 1)
+  nat.lib.pd_set_option(b'race_sampling', 0)
 
 
 def site_classes(cols):
@@ -819,6 +820,45 @@ def test_streamed_rollout_stress(n, t_steps, reps):
              CHECKSUM='1')
   assert (_prof_e2e_digest(PD_HOST_STREAMED='1', **env) ==
           _prof_e2e_digest(PD_HOST_STREAMED='0', **env))
+
+
+def test_race_sampling_matches_direct_method_in_distribution(eng):
+  """pd_set_option('race_sampling', 1): events by competing exponentials
+  (every neighbour draws Exp(rate_i), the smallest wins) instead of the
+  reference's direct method.  Not draw for draw -- so never a parity path --
+  but equal in distribution: over 2^20 envs the counts of (no hop, hop to
+  neighbour 0 / 1 / 2) after one control, and the histogram of hops per
+  control, pass a chi-square test against the direct method's, for the
+  simple and the prior rates."""
+  from putting_dune_b200 import _native as nat
+  n = 1 << 20
+  rng = np.random.default_rng(3)
+  acts = rng.uniform(-1, 1, size=(1, n, 2))
+  for rate_fn, dwell in ((po.RATE_SIMPLE, 1500000), (po.RATE_PRIOR, 5000000)):
+    spec = gh.rate_spec(rate_fn)
+    hists = []
+    for race in (0, 1):
+      nat.check(nat.lib.pd_set_option(b'race_sampling', race))
+      b = eng.EnvBatch(n, seed=5 + race)  # independent draws
+      b.reset()
+      si0 = gh.np_(b.si_idx).copy()
+      nbr = gh.np_(b.lattice_tables.nbr)[:, :3]
+      b.rollout(acts, dwell, spec, action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+      hops = gh.np_(b.n_transitions)
+      si1 = gh.np_(b.si_idx)
+      one = hops == 1
+      slot = np.argmax(nbr[si0[one]] == si1[one][:, None], axis=1)
+      first = np.array([(hops == 0).sum()] +
+                       [(slot == k).sum() for k in range(3)] +
+                       [(hops >= 2).sum()], dtype=np.float64)
+      per = np.bincount(np.minimum(hops, 4), minlength=5).astype(np.float64)
+      hists.append((first, per))
+    nat.check(nat.lib.pd_set_option(b'race_sampling', 0))
+    for a, c in zip(hists[0], hists[1]):
+      # two-sample chi-square, 4 degrees of freedom: 0.999 quantile = 18.5
+      chi2 = (((a - c) ** 2) / np.maximum(a + c, 1.0)).sum()
+      assert chi2 < 18.5, (rate_fn, chi2, a, c)
+    assert hists[0][0][1:].sum() > 0.05 * n
 
 
 GMM_PARAMS = {  # graphene_test.py:337-345 parameter set (as in make_golden)
