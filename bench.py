@@ -697,6 +697,22 @@ def run_ours(args, cfg):
   h2d = h_ctl32[0].numel() * 4
   d2h = h_packed.numel() * 2
   link = measure_link(dev) if rank == 0 else None
+  if world > 1:
+    # every rank copies at once: what the ranks' shared host path (PCIe
+    # switches / root ports / DRAM) gives each of them, summed
+    barrier()
+    mine = measure_link(dev, mb=32)
+    tsum = torch.tensor([mine['h2d_gbs'], mine['d2h_gbs'],
+                         mine['both_gbs_per_direction']],
+                        dtype=torch.float64, device=dev)
+    dist.all_reduce(tsum)
+    if rank == 0:
+      link['all_ranks_at_once'] = {
+          'h2d_gbs_sum': float(tsum[0]), 'd2h_gbs_sum': float(tsum[1]),
+          'both_gbs_per_direction_sum': float(tsum[2]), 'ranks': world,
+          'note': 'the same three copies issued by every rank after a '
+                  'barrier; sums over ranks (ceiling of the shared host '
+                  'path for the e2e call)'}
 
   # -- roofline of the dominant kernel ----------------------------------------
   peak, peak_kind = measured_peak()
