@@ -70,7 +70,37 @@ for i in range(reps):
   ms.append(s.elapsed_time(e))
 m = float(np.median(ms))
 ev = float(b.n_events.sum().item()) / float(b.ctrl_count.sum().item())
-print('n=%d steps=%d rate=%s fast=%s outputs=%s: %.4f ms  '
+print('n=%d steps=%d rate=%s fast=%s plan=%s outputs=%s: %.4f ms  '
       '%.3e env-steps/s  (%.2f iterations per control)' %
       (n, steps, rate_name, os.environ.get('PD_FAST', '1'),
-       os.environ.get('OUTPUTS', '0'), m, n * steps / (m / 1e3), ev))
+       os.environ.get('PD_PLAN', '1'), os.environ.get('OUTPUTS', '0'), m, n * steps / (m / 1e3), ev))
+
+# PLAN_CLOCKS=1 (library built with -DPD_PLAN_CLOCKS): phase times of the last
+# k_rollout_plan launch, per CTA (globaltimer, ns)
+if os.environ.get('PLAN_CLOCKS') == '1':
+  buf = (C.c_ulonglong * (1024 * 8))()
+  nat.lib.pd_debug_plan_clocks(buf)
+  a = np.frombuffer(buf, dtype=np.uint64).reshape(1024, 8).astype(np.int64)
+  a = a[a[:, 0] > 0]
+  t00 = a[:, 0].min()
+  names = ['prologue', 'dense', 'queue', 'commit', 'fill', 'store']
+  cnt = a[:, 4]
+  a = a[:, [0, 1, 2, 3, 5, 6, 7]]
+  d = np.diff(a, axis=1) / 1e3
+  print('CTAs %d; start spread %.1f us; end (max) %.1f us' %
+        (len(a), (a[:, 0].max() - t00) / 1e3, (a[:, -1].max() - t00) / 1e3))
+  for i, nm in enumerate(names):
+    print('  %-10s mean %6.1f  p50 %6.1f  max %6.1f us' %
+          (nm, d[:, i].mean(), np.median(d[:, i]), d[:, i].max()))
+  ev = np.stack([(cnt >> sh) & 0xFFFF for sh in (0, 16, 32, 48)], axis=1)
+  print('  warp-walker events per launch: replays %d, area checks %d, serial '
+        'controls %d, busy masks %d' % tuple(ev.sum(axis=0)))
+  tail = (a[:, 5] - a[:, 3]) / 1e3
+  order = np.argsort(-tail)[:6]
+  for i in order:
+    print('    CTA %4d commit+fill %6.1f us: replays %d, area %d, serial %d, '
+          'masks %d' % ((i, tail[i]) + tuple(ev[i])))
+  quiet = ev.sum(axis=1) == 0
+  if quiet.any():
+    print('  CTAs without events: %d, commit+fill mean %.1f max %.1f us' %
+          (quiet.sum(), tail[quiet].mean(), tail[quiet].max()))

@@ -184,6 +184,33 @@ __device__ __forceinline__ FastSite fast_site(const Tables& tab, int si,
   return f;
 }
 
+// Offset (angstrom) of neighbour `slot` of a BULK site whose geometry is g.
+template <int RATE>
+__device__ __forceinline__ void bulk_offset(const FastGeo& g, int slot,
+                                            float* ox, float* oy) {
+  const float gx = slot == 0 ? g.gx[0] : (slot == 1 ? g.gx[1] : g.gx[2]);
+  const float gy = slot == 0 ? g.gy[0] : (slot == 1 ? g.gy[1] : g.gy[2]);
+  if (RATE == PD_RATE_PRIOR) {
+    // a bond vector; peak = 0.85 (ux, -uy) of its unit vector u
+    *ox = gx * static_cast<float>(kBond / 0.85);
+    *oy = -gy * static_cast<float>(kBond / 0.85);
+  } else {
+    *ox = gx;
+    *oy = gy;
+  }
+}
+
+// bulk -> bulk always changes the sublattice: g'[i] = -g[2 - i]
+__device__ __forceinline__ void flip_geo(FastGeo* g) {
+  const float x0 = -g->gx[2], y0 = -g->gy[2];
+  g->gx[2] = -g->gx[0];
+  g->gy[2] = -g->gy[0];
+  g->gx[1] = -g->gx[1];
+  g->gy[1] = -g->gy[1];
+  g->gx[0] = x0;
+  g->gy[0] = y0;
+}
+
 // The hop to neighbour `slot`: new site and geometry, and the beam offset
 // (the beam stays where its control put it; the Si moves by the neighbour
 // offset, which the geometry holds in float32).  c, s: the env's lattice
@@ -197,18 +224,7 @@ __device__ __forceinline__ void fast_hop(const Tables& tab, int slot,
   const int cls_old = f->cls;
   // (*ox, *oy): the neighbour's offset in angstrom
   if (cls_old < 2) {
-    const float gx = slot == 0 ? f->geo.gx[0]
-                               : (slot == 1 ? f->geo.gx[1] : f->geo.gx[2]);
-    const float gy = slot == 0 ? f->geo.gy[0]
-                               : (slot == 1 ? f->geo.gy[1] : f->geo.gy[2]);
-    if (RATE == PD_RATE_PRIOR) {
-      // bulk: a bond vector; peak = 0.85 (ux, -uy) of its unit vector u
-      *ox = gx * static_cast<float>(kBond / 0.85);
-      *oy = -gy * static_cast<float>(kBond / 0.85);
-    } else {
-      *ox = gx;
-      *oy = gy;
-    }
+    bulk_offset<RATE>(f->geo, slot, ox, oy);
   } else {
     // sheet edge: the nearest sites need not be a bond away
     const double2 cs = rotation();
@@ -222,14 +238,7 @@ __device__ __forceinline__ void fast_hop(const Tables& tab, int slot,
   f->si = to;
   f->cls = tab.neighbors_class(to, f->nb);
   if (cls_old < 2 && f->cls < 2) {
-    // bulk -> bulk always changes the sublattice: g'[i] = -g[2 - i]
-    const float x0 = -f->geo.gx[2], y0 = -f->geo.gy[2];
-    f->geo.gx[2] = -f->geo.gx[0];
-    f->geo.gy[2] = -f->geo.gy[0];
-    f->geo.gx[1] = -f->geo.gx[1];
-    f->geo.gy[1] = -f->geo.gy[1];
-    f->geo.gx[0] = x0;
-    f->geo.gy[0] = y0;
+    flip_geo(&f->geo);
   } else {
     const double2 cs = rotation();
     f->geo = fast_geo_any<RATE>(tab, to, f->nb[0], f->nb[1], f->nb[2], f->cls,

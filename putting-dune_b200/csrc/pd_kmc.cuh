@@ -663,6 +663,7 @@ struct StepArgs {
                               // k_rollout; small batches trade idle lanes for
                               // more warps and less intra-warp divergence)
   int32_t action_mode;        // pd_action_mode (rollouts)
+  int32_t plan_envs_per_cta;  // k_rollout_plan: envs a CTA owns (<= 16)
   int32_t prepass;            // 1: float32 pre-pass (certainly_no_hop) enabled
   int32_t walk_min_ready;     // k_walk: lanes with an exact iteration pending
   int32_t walk_max_reps;      //   that end the bookkeeping repeats / their cap

@@ -1525,6 +1525,15 @@ static int& option_race_sampling() {
   }();
   return on;
 }
+// k_rollout_plan (pd_step_fast.cu) instead of k_rollout_fast: opt-in, it is
+// the slower of the two on the benchmarked workload.
+static int& option_plan() {
+  static int on = [] {
+    const char* v = getenv("PD_PLAN");
+    return (v && v[0] == '1') ? 1 : 0;
+  }();
+  return on;
+}
 // (the float32 pre-pass and the fast kernels reason about the direct method)
 static bool prepass_enabled() {
   return option_prepass() != 0 && option_race_sampling() == 0;
@@ -1619,7 +1628,8 @@ static StreamPlan stream_plan(const pd_rate_config* rc, const StepArgs& a,
 
 // pd_step_fast.cu: the guarded float32 kernels (prior / simple rates).
 template <int RATE>
-int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream);
+int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream,
+                int plan_mode);
 
 // PD_FAST=0 keeps every iteration on the float64 chain (A/B timing; the
 // parity tests compare the two).
@@ -1662,8 +1672,9 @@ static int launch_step(const StepArgs& a_in, bool rollout,
     if (rollout && !a.stream_mode && fast_enabled() && a.dwell_us_scalar > 0 &&
         a.dwell_us_scalar < 3000LL * 1000000LL && !a.skip) {
       if (walk || !spec)
-        return launch_fast<RATE>(a, true, grid_for(a.st.n_envs, true), stream);
-      return launch_fast<RATE>(a, false, grid, stream);
+        return launch_fast<RATE>(a, true, grid_for(a.st.n_envs, true), stream,
+                                 0);
+      return launch_fast<RATE>(a, false, grid, stream, option_plan());
     }
   }
   if (a.packed_out || (a.actions_f32 && !a.stream_mode)) {
@@ -1889,6 +1900,7 @@ extern "C" int pd_set_option(const char* name, int value) {
   if (!strcmp(name, "prepass")) slot = &pd::option_prepass();
   if (!strcmp(name, "rollout_spec")) slot = &pd::option_rollout_spec();
   if (!strcmp(name, "race_sampling")) slot = &pd::option_race_sampling();
+  if (!strcmp(name, "plan")) slot = &pd::option_plan();
   if (!slot) {
     pd::set_error("pd_set_option: unknown option '%s'", name);
     return PD_ERR_INVALID_ARGUMENT;

@@ -652,12 +652,784 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
 }
 
 // ---------------------------------------------------------------------------
+// k_rollout_plan: small-batch rollouts under the relative adapter, with the
+// time dimension taken out of the dependent chain.
+//
+// Under the relative adapter the beam offset of a control is clip(action, -1,
+// 1) * max_distance whatever the state (while the adapter's clip to the frame
+// cannot engage), the Philox draws of a control depend on (env, control
+// counter, iteration) only, and the neighbour geometry of a bulk site depends
+// on the env's lattice angle and the site's class (0 / 1) only.  So what a
+// control does to an env on a bulk site -- how many hops, to which neighbour
+// slots -- is a function of (env, step, class) alone.  A CTA owns up to
+// kPlanEnvs envs and walks the call in chunks of kPlanChunk steps:
+//   plan    every (env, step) of the chunk at full density, all threads, no
+//           dependence between items: iteration 0 of the control for both
+//           classes with fast_event (one Philox call serves both); the ~11 %
+//           that do not end there go to a queue and are run to their end by
+//           the next free lane.  One uint16 per class in shared memory:
+//           hops | UNSURE << 3 | slots << 4;
+//   commit  one warp per env walks the plan: ballots give the non-quiet
+//           steps of a 32-step window for either class, the warp jumps from
+//           one to the next, follows the slots through the neighbour table,
+//           keeps the float32 view of the Si in the FOV, and hands everything
+//           the plan does not cover (UNSURE controls, sheet-edge sites, a clip
+//           that may engage, the safe-area test when float32 cannot rule a
+//           re-centre out) to the exact float64 code;
+//   store   all threads write the chunk's per-step results, env-contiguous.
+// Results are those of k_rollout_fast / the float64 kernels bit for bit
+// (tests/test_gpu_fast.py runs every case through all three).
+// ---------------------------------------------------------------------------
+constexpr int kPlanThreads = 512;
+constexpr int kPlanEnvs = kPlanThreads / 32;  // one warp per env in `commit`
+constexpr int kPlanChunk = 256;               // steps per chunk
+constexpr int kPlanMaxHops = 5;               // hops one plan entry describes
+constexpr int kPlanQueue = 2048;              // queued (env, step, class)
+constexpr uint32_t kPlanUnsure = 8u;
+
+// The control of (env_id, ctrl) for a Si on a bulk site with geometry g and
+// beam offset (bx, by), run to its end in float32.
+template <int RATE>
+__device__ __forceinline__ uint32_t plan_control(FastGeo g, float bx, float by,
+                                                 uint32_t env_id, uint32_t ctrl,
+                                                 const FastTimes& tm,
+                                                 const PhiloxKeys& keys) {
+  const float off_s = fast_offset_scale<RATE>();
+  float e_lo = 0.f, e_hi = 0.f;
+  uint32_t hops = 0, slots = 0;
+  for (uint32_t it = 0;; ++it) {
+    const uint4 w = philox4x32_10k(env_id, ctrl, it, PD_STREAM_KMC, keys);
+    int slot = 0;
+    float t_lo, t_hi;
+    const int kind = fast_event<RATE>(g, bx, by, w.x, w.z, e_lo, e_hi, tm,
+                                      &slot, &t_lo, &t_hi);
+    if (kind == FAST_NO_HOP) break;
+    if (kind == FAST_UNSURE || hops == kPlanMaxHops) return kPlanUnsure;
+    float ox, oy;
+    bulk_offset<RATE>(g, slot, &ox, &oy);
+    bx -= ox * off_s;
+    by -= oy * off_s;
+    flip_geo(&g);
+    slots |= static_cast<uint32_t>(slot) << (2 * hops);
+    ++hops;
+    fast_advance(&e_lo, &e_hi, t_lo, t_hi);
+  }
+  return hops | (slots << 4);
+}
+
+// Rare paths of `commit`, out of line.  A Si on a sheet-edge site (class 2:
+// its neighbour geometry is the site's own, pd_lattice.cu) is not covered by
+// the plan; its controls still run in float32:
+//   site_busy_mask  iteration 0 of the steps [t_first, t_first + len) for a
+//                   Si parked on `si`, one step per lane: bit j = step
+//                   t_first + j does not certainly end without a hop;
+//   serial_control  one control from its start, iteration by iteration
+//                   (what a lane of k_walk_fast does).
+template <int RATE, int IO, class Tables>
+__device__ __noinline__ unsigned site_busy_mask(const StepArgs& a,
+                                                const Tables tab,
+                                                const double2 cs, int64_t env,
+                                                int t_first, int len, int si,
+                                                uint32_t ctrl_first) {
+  const FastSite s = fast_site<RATE>(tab, si, cs.x, cs.y);
+  const int lane = threadIdx.x & 31;
+  bool busy = false;
+  if (lane < len) {
+    const FastTimes tm = fast_times(a.dwell_us_scalar);
+    const float md_s = static_cast<float>(
+        a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
+    const double2 act = ActionStream<IO>(a).load(t_first + lane, env);
+    const float bx = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+    const float by = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+    const uint4 w = philox4x32_10k(
+        a.st.env_offset + static_cast<uint32_t>(env),
+        ctrl_first + static_cast<uint32_t>(lane), 0u, PD_STREAM_KMC, a.keys);
+    int slot;
+    float t_lo, t_hi;
+    busy = fast_event<RATE>(s.geo, bx, by, w.x, w.z, 0.f, 0.f, tm, &slot, &t_lo,
+                            &t_hi) != FAST_NO_HOP;
+  }
+  return __ballot_sync(0xffffffffu, busy);
+}
+
+struct SerialResult {
+  int si, nb[3], cls;  // the Si after the control
+  float ox, oy;        // how far it moved, angstrom
+  int hops;
+  bool unsure;         // float32 could not settle an iteration: replay
+};
+
+template <int RATE, int IO, class Tables>
+__device__ __noinline__ void serial_control(const StepArgs& a, const Tables tab,
+                                            const double2 cs, int64_t env,
+                                            int t, int si, uint32_t ctrl,
+                                            SerialResult* out) {
+  auto rotation = [&]() { return cs; };
+  FastSite s = fast_site<RATE>(tab, si, cs.x, cs.y);
+  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const float md_s = static_cast<float>(
+      a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
+  const double2 act = ActionStream<IO>(a).load(t, env);
+  float bx = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+  float by = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+  const uint32_t env_id = a.st.env_offset + static_cast<uint32_t>(env);
+  float e_lo = 0.f, e_hi = 0.f, oxs = 0.f, oys = 0.f;
+  int hops = 0;
+  out->unsure = false;
+  for (uint32_t it = 0;; ++it) {
+    const uint4 w = philox4x32_10k(env_id, ctrl, it, PD_STREAM_KMC, a.keys);
+    int slot = 0;
+    float t_lo, t_hi;
+    const int kind = fast_event<RATE>(s.geo, bx, by, w.x, w.z, e_lo, e_hi, tm,
+                                      &slot, &t_lo, &t_hi);
+    if (kind == FAST_NO_HOP) break;
+    if (kind == FAST_UNSURE) {
+      out->unsure = true;
+      return;
+    }
+    float ox, oy;
+    fast_hop<RATE>(tab, slot, rotation, &s, &bx, &by, &ox, &oy);
+    oxs += ox;
+    oys += oy;
+    ++hops;
+    fast_advance(&e_lo, &e_hi, t_lo, t_hi);
+  }
+  out->si = s.si;
+  out->nb[0] = s.nb[0];
+  out->nb[1] = s.nb[1];
+  out->nb[2] = s.nb[2];
+  out->cls = s.cls;
+  out->ox = oxs;
+  out->oy = oys;
+  out->hops = hops;
+}
+
+// State of an env between the phases of a chunk (shared memory).
+struct WalkState {
+  int si;
+  float qx, qy, iwx, iwy;  // Observed
+  int events, transitions, recentres, hops_synced;
+  int fov_site;    // >= 0: the FOV in memory is stale, the current one is the
+                   // FOV centred on this site (simulator.py:161-165)
+  int pos;         // next step of the chunk to commit
+  int status;
+  int check_area;  // simulator.py:156 at the first step of the call
+};
+
+// FOV centred on `site` (what exact_area_check stores when it re-centres).
+__device__ __noinline__ void store_centred_fov(const StepArgs& a, int64_t env,
+                                               int site) {
+  const double2 base =
+      __ldg(reinterpret_cast<const double2*>(a.lat.base_xy) + site);
+  const double2 psi = site_position(base, load_lattice4(a.st.lattice, env));
+  store_fov4(a.st.fov, env, centred_fov(psi, a.st.fov_scale[env]));
+}
+
+__device__ __forceinline__ bool q_inside(float qx, float qy) {
+  return qx > 0.2501f && qx < 0.7499f && qy > 0.2501f && qy < 0.7499f;
+}
+// certainly outside the safe area (simulator.py:236-249): a re-centre
+__device__ __forceinline__ bool q_outside(float qx, float qy) {
+  return qx < 0.2499f || qx > 0.7501f || qy < 0.2499f || qy > 0.7501f;
+}
+__device__ __forceinline__ bool q_clip_free(float qx, float qy, float iwx,
+                                            float iwy, float max_distance) {
+  const float rx = __fmaf_rn(max_distance, iwx, 1e-4f);
+  const float ry = __fmaf_rn(max_distance, iwy, 1e-4f);
+  return qx > rx && qx < 1.0f - rx && qy > ry && qy < 1.0f - ry;
+}
+
+#ifdef PD_PLAN_CLOCKS
+// phase clocks of k_rollout_plan (profiles/prof_walk.py PLAN_CLOCKS=1)
+__device__ unsigned long long g_plan_clocks[1024 * 8];
+#define PLAN_CLOCK(i)                                              \
+  do {                                                             \
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {                   \
+      unsigned long long t_;                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));       \
+      g_plan_clocks[blockIdx.x * 8 + (i)] = t_;                    \
+    }                                                              \
+  } while (0)
+// event counts of the warp walker: 16 bits each of replays, area checks,
+// serial controls, busy masks
+#define PLAN_COUNT(shift)                                                   \
+  do {                                                                      \
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < 1024)                       \
+      atomicAdd(&g_plan_clocks[blockIdx.x * 8 + 4], 1ull << (shift));       \
+  } while (0)
+#else
+#define PLAN_CLOCK(i)
+#define PLAN_COUNT(shift)
+#endif
+
+constexpr uint32_t kOutMark = 1u << 30;  // tile entry: a step's result
+constexpr uint32_t kOutRec = 1u << 31;   //   ... which re-centred the FOV
+
+template <int RATE, int IO>
+__global__ void __launch_bounds__(kPlanThreads, 2)
+    k_rollout_plan(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) unsigned char plan_smem[];
+  // plan records (uint16 per class: hops | UNSURE << 3 | slots << 4, bits 14
+  // and 15 unused), overwritten step by step with the results
+  // (site | kOutMark | kOutRec)
+  __shared__ uint32_t tile[kPlanEnvs][kPlanChunk + 1];
+  __shared__ uint32_t queue[kPlanQueue];
+  __shared__ uint32_t s_mask[kPlanEnvs][2][kPlanChunk / 32];  // busy steps
+  __shared__ float s_geo[kPlanEnvs][6];  // class-0 geometry (fast_event)
+  __shared__ float s_off[kPlanEnvs][6];  // class-0 neighbour offsets, angstrom
+  __shared__ float s_iws[kPlanEnvs];     // 1 / fov_scale
+  __shared__ double2 s_rot[kPlanEnvs];   // lattice rotation (cos, sin)
+  __shared__ uint32_t s_ctrl0[kPlanEnvs];
+  __shared__ int s_si_start[kPlanEnvs];
+  __shared__ WalkState s_ws[kPlanEnvs];
+  __shared__ uint32_t q_count;
+  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const float md_f = static_cast<float>(a.max_distance);
+  const float md_s = static_cast<float>(
+      a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
+  const long long step_us = a.dwell_us_scalar + a.image_duration_us;
+  const int64_t n = a.st.n_envs;
+  const int n_steps = a.n_steps;
+  const ActionStream<IO> ctl(a);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int epc = a.plan_envs_per_cta;
+  const int64_t env0 = static_cast<int64_t>(blockIdx.x) * epc;
+  const int n_env = n - env0 < epc ? static_cast<int>(n - env0) : epc;
+  const uint32_t env_id0 = a.st.env_offset + static_cast<uint32_t>(env0);
+  PLAN_CLOCK(0);
+#ifdef PD_PLAN_CLOCKS
+  if (tid == 0 && blockIdx.x < 1024) g_plan_clocks[blockIdx.x * 8 + 4] = 0;
+#endif
+
+  // the neighbour table as 8-byte rows in shared memory (a planned hop is a
+  // dependent lookup) and the per-env constants
+  double2* s_base = reinterpret_cast<double2*>(plan_smem);
+  ushort4* s_nbr = reinterpret_cast<ushort4*>(s_base + a.lat.n_sites);
+  {
+    const double2* gbase = reinterpret_cast<const double2*>(a.lat.base_xy);
+    const int4* gnbr = reinterpret_cast<const int4*>(a.lat.nbr);
+    for (int k = tid; k < a.lat.n_sites; k += kPlanThreads) {
+      s_base[k] = __ldg(gbase + k);
+      const int4 v = __ldg(gnbr + k);
+      s_nbr[k] = make_ushort4(
+          static_cast<unsigned short>(v.x), static_cast<unsigned short>(v.y),
+          static_cast<unsigned short>(v.z),
+          static_cast<unsigned short>((v.w >> kSiteClassShift) & 3));
+    }
+  }
+  const SharedTables stab{s_base, s_nbr};
+  if (tid < n_env) {
+    const int64_t e = env0 + tid;
+    const Lattice4 lat = load_lattice4(a.st.lattice, e);
+    s_rot[tid] = make_double2(lat.c, lat.s);
+    FastGeo g;
+    fast_geo_bulk<RATE>(Lattice4{0.0, 0.0, lat.c, lat.s}, 0, &g);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s_geo[tid][i] = g.gx[i];
+      s_geo[tid][3 + i] = g.gy[i];
+      bulk_offset<RATE>(g, i, &s_off[tid][i], &s_off[tid][3 + i]);
+    }
+    s_iws[tid] = __fdividef(1.0f, static_cast<float>(a.st.fov_scale[e]));
+    s_ctrl0[tid] = a.st.ctrl_count[e];
+    WalkState ws;
+    ws.si = a.st.si_idx[e];
+    Observed obs;
+    obs.sync(load_fov4(a.st.fov, e),
+             site_position(
+                 __ldg(reinterpret_cast<const double2*>(a.lat.base_xy) + ws.si),
+                 lat));
+    ws.qx = obs.qx;
+    ws.qy = obs.qy;
+    ws.iwx = obs.iwx;
+    ws.iwy = obs.iwy;
+    ws.events = ws.transitions = ws.recentres = ws.hops_synced = 0;
+    ws.fov_site = -1;
+    ws.pos = 0;
+    ws.status = a.st.status[e];
+    ws.check_area = 1;
+    s_ws[tid] = ws;
+  }
+  __syncthreads();
+
+  for (int t0 = 0; t0 < n_steps; t0 += kPlanChunk) {
+    const int len_c = n_steps - t0 < kPlanChunk ? n_steps - t0 : kPlanChunk;
+    const int n_win = (len_c + 31) >> 5;
+    PLAN_CLOCK(1);
+    if (tid == 0) q_count = 0;
+    if (tid < kPlanEnvs * 2 * (kPlanChunk / 32))
+      (&s_mask[0][0][0])[tid] = 0u;
+    __syncthreads();
+    // ---- plan, dense pass: iteration 0 of every control, both classes ----
+    const int items = n_env * len_c;
+    for (int idx = tid; idx < items; idx += kPlanThreads) {
+      const int k = idx / n_env, el = idx - k * n_env;
+      const int t = t0 + k;
+      const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
+      const float bx =
+          fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+      const float by =
+          fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+      FastGeo g;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        g.gx[i] = s_geo[el][i];
+        g.gy[i] = s_geo[el][3 + i];
+      }
+      const uint4 w = philox4x32_10k(env_id0 + static_cast<uint32_t>(el),
+                                     s_ctrl0[el] + static_cast<uint32_t>(t), 0u,
+                                     PD_STREAM_KMC, a.keys);
+      int slot;
+      float t_lo, t_hi;
+      const bool busy0 = fast_event<RATE>(g, bx, by, w.x, w.z, 0.f, 0.f, tm,
+                                          &slot, &t_lo, &t_hi) != FAST_NO_HOP;
+      flip_geo(&g);
+      const bool busy1 = fast_event<RATE>(g, bx, by, w.x, w.z, 0.f, 0.f, tm,
+                                          &slot, &t_lo, &t_hi) != FAST_NO_HOP;
+      // (a queue entry that does not fit stays UNSURE: the exact code runs it)
+      tile[el][k] =
+          (busy0 ? kPlanUnsure : 0u) | (busy1 ? kPlanUnsure << 16 : 0u);
+      const int want = (busy0 ? 1 : 0) + (busy1 ? 1 : 0);
+      if (want) {
+        if (busy0) atomicOr(&s_mask[el][0][k >> 5], 1u << (k & 31));
+        if (busy1) atomicOr(&s_mask[el][1][k >> 5], 1u << (k & 31));
+        uint32_t q = atomicAdd(&q_count, static_cast<uint32_t>(want));
+        if (busy0 && q < kPlanQueue) queue[q] = static_cast<uint32_t>(idx) << 1;
+        q += busy0 ? 1u : 0u;
+        if (busy1 && q < kPlanQueue)
+          queue[q] = (static_cast<uint32_t>(idx) << 1) | 1u;
+      }
+    }
+    __syncthreads();
+    PLAN_CLOCK(2);
+    // ---- plan, queue pass: the controls that went on, to their end ----
+    {
+      const int n_q = q_count < kPlanQueue ? static_cast<int>(q_count)
+                                           : kPlanQueue;
+      for (int q = tid; q < n_q; q += kPlanThreads) {
+        const uint32_t entry = queue[q];
+        const int idx = static_cast<int>(entry >> 1), c = entry & 1u;
+        const int k = idx / n_env, el = idx - k * n_env;
+        const int t = t0 + k;
+        const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
+        const float bx =
+            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+        const float by =
+            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+        FastGeo g;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          g.gx[i] = s_geo[el][i];
+          g.gy[i] = s_geo[el][3 + i];
+        }
+        if (c) flip_geo(&g);
+        const uint32_t r16 = plan_control<RATE>(
+            g, bx, by, env_id0 + static_cast<uint32_t>(el),
+            s_ctrl0[el] + static_cast<uint32_t>(t), tm, a.keys);
+        reinterpret_cast<unsigned short*>(&tile[el][k])[c] =
+            static_cast<unsigned short>(r16);
+      }
+    }
+    __syncthreads();
+    PLAN_CLOCK(3);
+    // ---- commit: a warp per env.  Lane 0 follows the plan from one busy
+    // step to the next while the Si stays on bulk sites, re-centres included
+    // (the FOV itself is formed when something needs it); it stops where the
+    // plan ends: UNSURE, a sheet-edge site, a clip that may engage, a
+    // safe-area test float32 cannot settle.  The whole warp then takes the
+    // env through those steps (float32 look-ahead over the window on edge
+    // sites, the exact code where float32 cannot speak) and lane 0 goes on.
+    // ----
+    if (tid < n_env) {
+      s_si_start[tid] = s_ws[tid].si;
+      s_ws[tid].pos = 0;
+    }
+    __syncthreads();
+    if (warp < n_env) for (;;) {
+      if (lane == 0 && s_ws[warp].pos < len_c) {
+        WalkState ws = s_ws[warp];
+        int si = ws.si;
+        ushort4 row = s_nbr[si];
+        int cls = row.w;
+        float qx = ws.qx, qy = ws.qy;
+        int stop_at = len_c, hops = 0;
+        bool ok = cls < 2 && q_clip_free(qx, qy, ws.iwx, ws.iwy, md_f);
+        if (ws.check_area) {
+          if (q_inside(qx, qy)) ws.check_area = 0;
+          else ok = false;
+        }
+        if (!ok) stop_at = ws.pos;
+        int w = ws.pos >> 5;
+        unsigned from = ~0u << (ws.pos & 31);
+        while (ok) {
+          unsigned m = 0;
+          while (w < n_win) {
+            m = s_mask[warp][cls][w] & from;
+            if (m) break;
+            ++w;
+            from = ~0u;
+          }
+          if (!m) break;  // the chunk is done
+          const int b = __ffs(m) - 1;
+          const int k = w * 32 + b;
+          from = b == 31 ? 0u : (~0u << (b + 1));
+          const uint32_t r16 =
+              reinterpret_cast<const unsigned short*>(&tile[warp][k])[cls];
+          if (r16 & kPlanUnsure) {
+            stop_at = k;
+            break;
+          }
+          const int n_hops = static_cast<int>(r16 & 7u);
+          int si_t = si, cls_t = cls;
+          ushort4 row_t = row;
+          float qx_t = qx, qy_t = qy;
+          for (int h = 0; h < n_hops; ++h) {
+            const int slot = static_cast<int>((r16 >> (4 + 2 * h)) & 3u);
+            // class 1: g1[i] = -g0[2 - i]
+            const int j = cls_t == 0 ? slot : 2 - slot;
+            const float sg = cls_t == 0 ? 1.f : -1.f;
+            qx_t = __fmaf_rn(sg * s_off[warp][j], ws.iwx, qx_t);
+            qy_t = __fmaf_rn(sg * s_off[warp][3 + j], ws.iwy, qy_t);
+            si_t = slot == 0 ? row_t.x : (slot == 1 ? row_t.y : row_t.z);
+            row_t = s_nbr[si_t];
+            cls_t = row_t.w;
+            if (cls_t == 2) break;  // onto the sheet's edge: the plan's next
+                                    // iteration assumed a bulk site's geometry
+          }
+          const bool in = q_inside(qx_t, qy_t), out = q_outside(qx_t, qy_t);
+          const bool due = ws.transitions + hops + n_hops - ws.hops_synced >=
+                           kObservedSyncHops;
+          if (cls_t == 2 || (!in && !out) || (due && !out)) {
+            stop_at = k;
+            break;
+          }
+          si = si_t;
+          row = row_t;
+          cls = cls_t;
+          qx = qx_t;
+          qy = qy_t;
+          hops += n_hops;
+          if (out) {
+            // simulator.py:156-169: the FOV is centred on the Si again
+            qx = qy = 0.5f;
+            ws.iwx = ws.iwy = s_iws[warp];
+            ws.recentres += 1;
+            ws.fov_site = si;
+            ws.hops_synced = ws.transitions + hops;
+          }
+          tile[warp][k] =
+              static_cast<uint32_t>(si) | kOutMark | (out ? kOutRec : 0u);
+          if (!q_clip_free(qx, qy, ws.iwx, ws.iwy, md_f)) {
+            stop_at = k + 1;
+            break;
+          }
+        }
+        const int reached = stop_at < len_c ? stop_at : len_c;
+        ws.si = si;
+        ws.qx = qx;
+        ws.qy = qy;
+        ws.transitions += hops;
+        ws.events += (reached - ws.pos) + hops;
+        ws.pos = reached;
+        s_ws[warp] = ws;
+      }
+      __syncwarp();
+      if (s_ws[warp].pos >= len_c) break;
+      {
+        const int64_t e = env0 + warp;
+        WalkState ws = s_ws[warp];
+        const double2 cs = s_rot[warp];
+        __syncwarp();
+        if (ws.fov_site >= 0) {
+          store_centred_fov(a, e, ws.fov_site);
+          ws.fov_site = -1;
+        }
+        int si = ws.si;
+        int nb0, nb1, nb2, cls;
+        {
+          const ushort4 row = s_nbr[si];
+          nb0 = row.x;
+          nb1 = row.y;
+          nb2 = row.z;
+          cls = row.w;
+        }
+        Observed obs{ws.qx, ws.qy, ws.iwx, ws.iwy};
+        uint32_t ctrl_count =
+            s_ctrl0[warp] + static_cast<uint32_t>(t0 + ws.pos);
+        uint8_t status = static_cast<uint8_t>(ws.status);
+        int events = ws.events, transitions = ws.transitions,
+            recentres = ws.recentres, hops_synced = ws.hops_synced;
+        bool check_area = ws.check_area != 0;
+        int next = len_c;     // where the lane walker takes over again
+        bool handed = false;
+        for (int w0 = ws.pos & ~31; w0 < len_c && !handed; w0 += 32) {
+          const int len = len_c - w0 < 32 ? len_c - w0 : 32;
+          int pos = w0 < ws.pos ? ws.pos - w0 : 0;
+          const uint32_t rec =
+              lane >= pos && lane < len ? tile[warp][w0 + lane] : 0u;
+          bool edge_ok = false;  // m_e describes the Si's current (edge) site
+          unsigned m_e = 0;
+          while (pos < len) {
+            // the plan speaks for a Si on a bulk site, the look-ahead below
+            // for one on a sheet-edge site, both while the adapter's clip
+            // cannot engage; anything else goes step by step through the
+            // exact code
+            const bool clip_free = obs.clip_free(md_f);
+            const bool planned = cls < 2 && clip_free;
+            const bool edge = cls == 2 && clip_free;
+            if (planned && !check_area && w0 + pos > ws.pos) {
+              // back on the plan: the lane walker goes on from here
+              next = w0 + pos;
+              handed = true;
+              break;
+            }
+            if (edge && !edge_ok && !check_area) {
+              PLAN_COUNT(48);
+              m_e = site_busy_mask<RATE, IO>(
+                  a, stab, cs, e, t0 + w0, len, si,
+                  s_ctrl0[warp] + static_cast<uint32_t>(t0 + w0));
+              edge_ok = true;
+            }
+            int stop;
+            if (!clip_free || check_area || planned) {
+              stop = pos;
+            } else {
+              const unsigned m = m_e & (~0u << pos);
+              stop = m ? __ffs(m) - 1 : len;
+            }
+            // steps [pos, stop) end without a hop
+            events += stop - pos;
+            ctrl_count += static_cast<uint32_t>(stop - pos);
+            if (stop >= len) break;
+            bool hopped = false;
+            bool exact = !clip_free;
+            bool serial = edge;
+            if (planned) {
+              const uint32_t r32 = __shfl_sync(0xffffffffu, rec, stop);
+              const uint32_t r16 = (cls == 1 ? r32 >> 16 : r32) & 0xFFFFu;
+              exact = (r16 & kPlanUnsure) != 0u;
+              if (!exact) {
+                // follow the planned hops through the neighbour table
+                const int n_hops = static_cast<int>(r16 & 7u);
+                int si_t = si, n0 = nb0, n1 = nb1, n2 = nb2, cls_t = cls;
+                float qx = obs.qx, qy = obs.qy;
+                for (int h = 0; h < n_hops; ++h) {
+                  const int slot =
+                      static_cast<int>((r16 >> (4 + 2 * h)) & 3u);
+                  const int j = cls_t == 0 ? slot : 2 - slot;
+                  const float sg = cls_t == 0 ? 1.f : -1.f;
+                  qx = __fmaf_rn(sg * s_off[warp][j], obs.iwx, qx);
+                  qy = __fmaf_rn(sg * s_off[warp][3 + j], obs.iwy, qy);
+                  si_t = slot == 0 ? n0 : (slot == 1 ? n1 : n2);
+                  const ushort4 row = s_nbr[si_t];
+                  n0 = row.x;
+                  n1 = row.y;
+                  n2 = row.z;
+                  cls_t = row.w;
+                  if (cls_t == 2) {
+                    // onto the sheet's edge: the plan's next iteration
+                    // assumed a bulk site's geometry
+                    serial = true;
+                    break;
+                  }
+                }
+                if (!serial) {
+                  si = si_t;
+                  nb0 = n0;
+                  nb1 = n1;
+                  nb2 = n2;
+                  cls = cls_t;
+                  obs.qx = qx;
+                  obs.qy = qy;
+                  hopped = n_hops > 0;
+                  transitions += n_hops;
+                  events += n_hops + 1;
+                  ctrl_count += 1;
+                }
+              }
+            }
+            if (serial) {
+              SerialResult sr;
+              PLAN_COUNT(32);
+              serial_control<RATE, IO>(a, stab, cs, e, t0 + w0 + stop, si,
+                                       ctrl_count, &sr);
+              if (sr.unsure) {
+                exact = true;
+              } else {
+                hopped = sr.hops > 0;
+                if (hopped) {
+                  si = sr.si;
+                  nb0 = sr.nb[0];
+                  nb1 = sr.nb[1];
+                  nb2 = sr.nb[2];
+                  cls = sr.cls;
+                  obs.hop(sr.ox, sr.oy);
+                }
+                transitions += sr.hops;
+                events += sr.hops + 1;
+                ctrl_count += 1;
+              }
+            }
+            if (exact) {
+              ReplayResult rr;
+              PLAN_COUNT(0);
+              replay_control<RATE, IO>(a, e, t0 + w0 + stop, si, 0u,
+                                       ctrl_count, transitions, events, status,
+                                       load_fov4(a.st.fov, e), &rr);
+              hopped = rr.hopped;
+              if (hopped) {
+                si = rr.s.si;
+                nb0 = rr.s.nb[0];
+                nb1 = rr.s.nb[1];
+                nb2 = rr.s.nb[2];
+                cls = rr.s.cls;
+                obs = rr.obs;
+              }
+              ctrl_count = rr.ctrl_count;
+              transitions = rr.transitions;
+              events = rr.events;
+              status = rr.status;
+            }
+            if (hopped) edge_ok = false;
+            // image, safe area (simulator.py:152-169)
+            bool recentred = false;
+            if (hopped || check_area) {
+              check_area = false;
+              if (!obs.inside() ||
+                  transitions - hops_synced >= kObservedSyncHops) {
+                PLAN_COUNT(16);
+                recentred = exact_area_check(a, e, si, &obs);
+                recentres += recentred ? 1 : 0;
+                hops_synced = transitions;
+              }
+            }
+            if (lane == stop)
+              tile[warp][w0 + stop] = static_cast<uint32_t>(si) | kOutMark |
+                                      (recentred ? kOutRec : 0u);
+            pos = stop + 1;
+          }
+        }
+        if (lane == 0) {
+          ws.si = si;
+          ws.qx = obs.qx;
+          ws.qy = obs.qy;
+          ws.iwx = obs.iwx;
+          ws.iwy = obs.iwy;
+          ws.events = events;
+          ws.transitions = transitions;
+          ws.recentres = recentres;
+          ws.hops_synced = hops_synced;
+          ws.status = status;
+          ws.check_area = check_area ? 1 : 0;
+          ws.pos = next;
+          s_ws[warp] = ws;
+        }
+      }
+      __syncwarp();
+      if (s_ws[warp].pos >= len_c) break;
+    }
+    __syncthreads();
+    PLAN_CLOCK(5);
+    // ---- fill: every step's result = that of the last step before it that
+    // changed something ----
+    if (warp < n_env) {
+      uint32_t carry = static_cast<uint32_t>(s_si_start[warp]);
+      for (int w0 = 0; w0 < len_c; w0 += 32) {
+        const uint32_t v = w0 + lane < len_c ? tile[warp][w0 + lane] : 0u;
+        const unsigned marks = __ballot_sync(0xffffffffu, (v & kOutMark) != 0u);
+        const unsigned upto = marks & (0xffffffffu >> (31 - lane));
+        const int src = upto ? 31 - __clz(upto) : 0;
+        const uint32_t got = __shfl_sync(0xffffffffu, v, src);
+        const uint32_t out = upto ? ((got & (kOutMark - 1u)) |
+                                     (src == lane ? (v & kOutRec) : 0u))
+                                  : carry;
+        if (w0 + lane < len_c) tile[warp][w0 + lane] = out;
+        carry = __shfl_sync(0xffffffffu, out, 31) & (kOutMark - 1u);
+      }
+    }
+    __syncthreads();
+    PLAN_CLOCK(6);
+    // ---- store: the chunk's results, env-contiguous ----
+    for (int idx = tid; idx < items; idx += kPlanThreads) {
+      const int k = idx / n_env, el = idx - k * n_env;
+      const uint32_t v = tile[el][k];
+      store_step<IO>(a, static_cast<int64_t>(t0 + k) * n + env0 + el,
+                     static_cast<int>(v & (kOutMark - 1u)),
+                     (v & kOutRec) != 0u, step_us);
+    }
+    // (the next chunk's first barrier orders these reads before its writes)
+  }
+  PLAN_CLOCK(7);
+  if (tid < n_env) {
+    const int64_t e = env0 + tid;
+    const WalkState ws = s_ws[tid];
+    if (ws.fov_site >= 0) store_centred_fov(a, e, ws.fov_site);
+    const long long total =
+        static_cast<long long>(n_steps) * step_us +
+        static_cast<long long>(ws.recentres) * a.image_duration_us;
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + e),
+              static_cast<unsigned long long>(total));
+    a.st.si_idx[e] = ws.si;
+    a.st.ctrl_count[e] = s_ctrl0[tid] + static_cast<uint32_t>(n_steps);
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + e),
+              static_cast<unsigned long long>(ws.events));
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_transitions + e),
+              static_cast<unsigned long long>(ws.transitions));
+    a.st.status[e] = static_cast<uint8_t>(ws.status);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Launch (called from launch_step, pd_step.cu).
 // ---------------------------------------------------------------------------
+// k_rollout_plan keeps the lattice tables (float64 positions, ushort4
+// neighbour rows) in shared memory: 24 bytes per site, two CTAs per SM.
+constexpr int kPlanMaxSites = 3072;
+static size_t shared_tables_bytes_host(int n_sites) {
+  return static_cast<size_t>(n_sites) * (sizeof(double2) + sizeof(ushort4));
+}
+
+template <int RATE, int IO>
+static int launch_plan(const StepArgs& a_in, cudaStream_t stream) {
+  StepArgs a = a_in;
+  // two CTAs per SM, one wave when the batch allows it
+  const int64_t slots = 2LL * sm_count();
+  int64_t epc = (a.st.n_envs + slots - 1) / slots;
+  if (epc > kPlanEnvs) epc = kPlanEnvs;
+  if (epc < 1) epc = 1;
+  a.plan_envs_per_cta = static_cast<int32_t>(epc);
+  const int64_t grid = (a.st.n_envs + epc - 1) / epc;
+  const size_t smem = shared_tables_bytes_host(a.lat.n_sites);
+  auto kern = k_rollout_plan<RATE, IO>;
+  PD_CUDA_OK(cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      static_cast<int>(smem)));
+  kern<<<static_cast<unsigned>(grid), kPlanThreads, smem, stream>>>(a);
+  PD_CUDA_OK(cudaGetLastError());
+  return PD_OK;
+}
+
+#ifdef PD_PLAN_CLOCKS
+extern "C" int pd_debug_plan_clocks(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_plan_clocks, sizeof(g_plan_clocks)) ==
+                 cudaSuccess
+             ? 0
+             : 1;
+}
+#endif
+
+// plan_mode: 1 = k_rollout_plan where it applies (small batches, relative
+// adapter), 0 = k_rollout_fast.
 template <int RATE>
-int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream) {
+int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream,
+                int plan_mode) {
   const int io = a.packed_out ? 1 : (a.actions_f32 ? 2 : 0);
   const bool rel = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
+  if (!walk && rel && plan_mode && a.n_steps >= 8 &&
+      a.lat.n_sites <= kPlanMaxSites)
+    return io == 1   ? launch_plan<RATE, 1>(a, stream)
+           : io == 2 ? launch_plan<RATE, 2>(a, stream)
+                     : launch_plan<RATE, 0>(a, stream);
   void (*kern)(const StepArgs) = nullptr;
   if (walk) {
     kern = io == 1   ? (rel ? k_walk_fast<RATE, 1, true>
@@ -685,9 +1457,9 @@ int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream) {
 }
 
 template int launch_fast<PD_RATE_SIMPLE>(const StepArgs&, bool, int,
-                                         cudaStream_t);
+                                         cudaStream_t, int);
 template int launch_fast<PD_RATE_PRIOR>(const StepArgs&, bool, int,
-                                        cudaStream_t);
+                                        cudaStream_t, int);
 
 // ---------------------------------------------------------------------------
 // pd_fast_path_audit: how far the float32 quantities of fast_event are from

@@ -37,11 +37,19 @@ def nat():
   from putting_dune_b200 import _native
   yield _native
   _native.lib.pd_set_fast_path(1)
+  _native.lib.pd_set_option(b'plan', 0)
 
 
-def _rollout(eng, nat, fast, n, seed, ctl, dwell, spec, mode, shift_fov,
+def _select(nat, kernels):
+  """'plan': k_rollout_plan where it applies (opt-in); 'fast': k_rollout_fast /
+  k_walk_fast (the default); 'exact': the float64 kernels."""
+  nat.check(nat.lib.pd_set_option(b'fast_path', 0 if kernels == 'exact' else 1))
+  nat.check(nat.lib.pd_set_option(b'plan', 1 if kernels == 'plan' else 0))
+
+
+def _rollout(eng, nat, kernels, n, seed, ctl, dwell, spec, mode, shift_fov,
              env_offset=0):
-  nat.lib.pd_set_fast_path(1 if fast else 0)
+  _select(nat, kernels)
   b = eng.EnvBatch(n, seed=seed, env_offset=env_offset)
   b.reset()
   if shift_fov:
@@ -79,14 +87,16 @@ def test_fast_rollout_equals_float64_kernels(eng, nat, n):
   ]
   for rate_fn, dwell, ctl, mode, shift in cases:
     spec = gh.rate_spec(rate_fn)
-    si_a, el_a, st_a = _rollout(eng, nat, True, n, seed, ctl, dwell, spec,
+    si_b, el_b, st_b = _rollout(eng, nat, 'exact', n, seed, ctl, dwell, spec,
                                 mode, shift)
-    si_b, el_b, st_b = _rollout(eng, nat, False, n, seed, ctl, dwell, spec,
-                                mode, shift)
-    np.testing.assert_array_equal(si_a, si_b)
-    np.testing.assert_array_equal(el_a, el_b)
-    for k in STATE_KEYS:
-      np.testing.assert_array_equal(st_a[k], st_b[k], err_msg=k)
+    for kernels in ('plan', 'fast'):
+      si_a, el_a, st_a = _rollout(eng, nat, kernels, n, seed, ctl, dwell,
+                                  spec, mode, shift)
+      np.testing.assert_array_equal(si_a, si_b, err_msg=kernels)
+      np.testing.assert_array_equal(el_a, el_b, err_msg=kernels)
+      for k in STATE_KEYS:
+        np.testing.assert_array_equal(st_a[k], st_b[k],
+                                      err_msg=f'{kernels} {k}')
     if dwell > 1000:
       assert st_b['n_transitions'].sum() > 0
 
@@ -95,16 +105,19 @@ def test_fast_rollout_single_step_and_edge_sites(eng, nat):
   """One-step rollouts (the fast walk kernel without look-ahead) and a Si that
   starts on the sheet's edge, where the three nearest sites are not the three
   bonded ones (geometry class 2: tables instead of the bulk constants)."""
-  n, seed = 5000, 5
+  seed = 5
   rng = np.random.default_rng(3)
   cls = None
-  for t_steps, rate_fn in ((1, po.RATE_SIMPLE), (40, po.RATE_SIMPLE),
-                           (60, po.RATE_PRIOR)):
+  # (600 steps: three 256-step chunks of k_rollout_plan, the last one ragged)
+  for n, t_steps, rate_fn in ((5000, 1, po.RATE_SIMPLE),
+                              (5000, 40, po.RATE_SIMPLE),
+                              (5000, 60, po.RATE_PRIOR),
+                              (301, 600, po.RATE_PRIOR)):
     spec = gh.rate_spec(rate_fn)
     acts = rng.uniform(-1, 1, size=(t_steps, n, 2))
     res = []
-    for fast in (True, False):
-      nat.lib.pd_set_fast_path(1 if fast else 0)
+    for kernels in ('plan', 'fast', 'exact'):
+      _select(nat, kernels)
       b = eng.EnvBatch(n, seed=seed)
       b.reset()
       if cls is None:
@@ -112,7 +125,7 @@ def test_fast_rollout_single_step_and_edge_sites(eng, nat):
       edge = np.nonzero(cls == 2)[0]
       assert edge.size > 50
       # park every second env's Si on an edge site, FOV centred on it
-      sites = edge[np.arange(n // 2) % edge.size]
+      sites = edge[np.arange((n + 1) // 2) % edge.size]
       b.si_idx[::2] = torch.as_tensor(sites.astype(np.int32), device=b.device)
       xy = gh.np_(b.silicon_position())
       half = gh.np_(b.fov_scale)[:, None] / 2
@@ -123,25 +136,29 @@ def test_fast_rollout_single_step_and_edge_sites(eng, nat):
       sd = b.state_dict()
       res.append((gh.np_(si), gh.np_(el),
                   {k: gh.np_(sd[k]) for k in STATE_KEYS}))
-    np.testing.assert_array_equal(res[0][0], res[1][0])
-    np.testing.assert_array_equal(res[0][1], res[1][1])
-    for k in STATE_KEYS:
-      np.testing.assert_array_equal(res[0][2][k], res[1][2][k], err_msg=k)
-    assert res[1][2]['n_transitions'][::2].sum() > 100 * (t_steps > 1)
+    for other in res[:2]:
+      np.testing.assert_array_equal(other[0], res[2][0])
+      np.testing.assert_array_equal(other[1], res[2][1])
+      for k in STATE_KEYS:
+        np.testing.assert_array_equal(other[2][k], res[2][2][k], err_msg=k)
+    assert res[2][2]['n_transitions'][::2].sum() > 100 * (t_steps > 1)
 
 
+@pytest.mark.parametrize('kernels', ['fast', 'plan'])
 @pytest.mark.parametrize('rate_fn', [po.RATE_PRIOR, po.RATE_SIMPLE])
-def test_benchmarked_config_vs_oracle(eng, nat, rate_fn):
+def test_benchmarked_config_vs_oracle(eng, nat, rate_fn, kernels):
   """BASELINE configs[1] exactly as bench.py runs it -- 4096 envs x 256 beam
   steps, relative_random actions, dwell 1.5 s -- against the oracle's
   step_and_image for all 1,048,576 env-steps: Si site and elapsed
-  microseconds of every step, final FOV, clocks and counters."""
+  microseconds of every step, final FOV, clocks and counters.  'fast' is
+  the kernel bench.py times (k_rollout_fast), 'plan' the opt-in
+  k_rollout_plan."""
   n, t_steps, seed = 4096, 256, 0
   rng = np.random.default_rng(100)
   acts = rng.uniform(-1.0, 1.0, size=(t_steps, n, 2))
   st = po.make_state(n, seed)
   po.reset(st)
-  nat.lib.pd_set_fast_path(1)
+  _select(nat, kernels)
   b = gh.batch_from_oracle(st)
   si, el = b.rollout(acts, 1500000, gh.rate_spec(rate_fn), record=True,
                      action_mode=nat.ACTION_RELATIVE_TO_SILICON,
@@ -268,8 +285,8 @@ def test_fast_rollout_consecutive_calls(eng, nat):
       np.float64) for _ in range(4)]
   spec = gh.rate_spec(po.RATE_PRIOR)
   runs = []
-  for fast in (1, 0):
-    nat.lib.pd_set_fast_path(fast)
+  for kernels in ('plan', 'fast', 'exact'):
+    _select(nat, kernels)
     b = eng.EnvBatch(n, seed=0)
     b.reset()
     out = []
@@ -280,11 +297,13 @@ def test_fast_rollout_consecutive_calls(eng, nat):
       out.append((gh.np_(si), gh.np_(el),
                   {k: gh.np_(sd[k]).copy() for k in STATE_KEYS}))
     runs.append(out)
-  for i, (x, y) in enumerate(zip(*runs)):
-    np.testing.assert_array_equal(x[0], y[0], err_msg=f'call {i} si')
-    np.testing.assert_array_equal(x[1], y[1], err_msg=f'call {i} elapsed')
-    for k in STATE_KEYS:
-      np.testing.assert_array_equal(x[2][k], y[2][k], err_msg=f'call {i} {k}')
+  for run in runs[:2]:
+    for i, (x, y) in enumerate(zip(run, runs[2])):
+      np.testing.assert_array_equal(x[0], y[0], err_msg=f'call {i} si')
+      np.testing.assert_array_equal(x[1], y[1], err_msg=f'call {i} elapsed')
+      for k in STATE_KEYS:
+        np.testing.assert_array_equal(x[2][k], y[2][k],
+                                      err_msg=f'call {i} {k}')
 
 
 def test_rate_ops_audit(eng, nat):
