@@ -37,8 +37,17 @@ def _check_stage(name, got, want):
   elif name in ('uniform', 'exponential', 'gaussian'):
     assert (d > 2e-5).mean() <= 1e-3, (name, (d > 2e-5).mean(), d.max())
   else:
-    assert d.mean() <= 2e-3 and (d > 2e-2).mean() <= 1e-2, (
-        name, d.mean(), (d > 2e-2).mean())
+    # CLAHE itself agrees with the oracle on every pixel to 7e-8 when both
+    # quantise the same input (test_clahe_matches_oracle_on_the_device_input).
+    # Here the inputs are the float32 and the float64 chain: a pixel whose
+    # 14-bit level sits on a bin edge lands in the other histogram bin, which
+    # moves that tile's map by a few grey levels.  Measured over the frames
+    # of this file: mean <= 6e-6, <= 4e-3 of the pixels beyond 1e-4, <= 1.1e-3
+    # beyond 2e-3, none beyond 2e-2.
+    assert d.mean() <= 5e-5, (name, d.mean())
+    assert (d > 1e-4).mean() <= 1e-2, (name, (d > 1e-4).mean())
+    assert (d > 2e-3).mean() <= 3e-3, (name, (d > 2e-3).mean())
+    assert (d > 2e-2).mean() <= 1e-4, (name, (d > 2e-2).mean(), d.max())
     assert got.min() >= 0.0 and got.max() <= 1.0  # imaging_test.py:75-78
 
 
@@ -148,3 +157,30 @@ def test_simulator_facade_returns_image():
   ctl = mu.BeamControl(geometry.Point(0.5, 0.5), dt.timedelta(seconds=1.5))
   obs = sim.step_and_image(np.random.default_rng(0), [ctl], return_image=True)
   assert obs.image.shape == (512, 512) and obs.image.min() >= 0.0
+
+
+@pytest.mark.parametrize('size', [128, 512])
+def test_clahe_matches_oracle_on_the_device_input(size):
+  """CLAHE alone (imaging.py:264 exposure.equalize_adapthist): the oracle's
+  restatement applied to the device's own stage-6 frame (float32, read back)
+  against the device's final frame.  Both sides then quantise the same
+  numbers, so the 14-bit levels, tile histograms, clip redistribution, maps
+  and the bilinear blend have to agree pixel for pixel; what is left is the
+  rounding of the final value to float32 (measured: <= 7e-8 on every
+  pixel)."""
+  from putting_dune_b200 import imaging
+  n, seed = (6 if size == 128 else 3), 91
+  st = po.make_state(n, seed)
+  po.reset(st)
+  st.image_params[0, 3] = 120.0  # large Poisson rates
+  b = gh.batch_from_oracle(st)
+  src = gh.np_(imaging.render_batch(b, image_size=size, stop_stage=6,
+                                    advance_frame_count=False))
+  got = gh.np_(imaging.render_batch(b, image_size=size, stop_stage=7,
+                                    advance_frame_count=False))
+  for e in range(n):
+    want = oi.equalize_adapthist(src[e].astype(np.float64))
+    d = np.abs(got[e].astype(np.float64) - want)
+    print(f'size {size} env {e}: max {d.max():.3g} mean {d.mean():.3g} '
+          f'>1e-6 {(d > 1e-6).mean():.3g} >1e-4 {(d > 1e-4).mean():.3g}')
+    assert d.max() <= 2.5e-7, (e, d.max())
