@@ -388,6 +388,12 @@ int pd_set_fast_path(int enabled);
  *   "prepass"       PD_PREPASS       float32 pre-pass of the float64 kernels
  *   "rollout_spec"  PD_ROLLOUT_SPEC  look-ahead over idle lanes in small
  *                                    float64 rollouts
+ *   "plan"          PD_PLAN          (default 0) small-batch rollouts under the
+ *                                    relative adapter through k_rollout_plan
+ *                                    (per-CTA plan of every (env, step) in
+ *                                    shared memory) instead of k_rollout_fast;
+ *                                    same results, slower on the benchmarked
+ *                                    workload
  *   "race_sampling" PD_SAMPLING_RACE (default 0) events by the race of
  *                                    competing exponentials -- each neighbour
  *                                    draws Exp(rate_i), the smallest wins --
