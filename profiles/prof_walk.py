@@ -73,7 +73,7 @@ ev = float(b.n_events.sum().item()) / float(b.ctrl_count.sum().item())
 print('n=%d steps=%d rate=%s fast=%s plan=%s outputs=%s: %.4f ms  '
       '%.3e env-steps/s  (%.2f iterations per control)' %
       (n, steps, rate_name, os.environ.get('PD_FAST', '1'),
-       os.environ.get('PD_PLAN', '1'), os.environ.get('OUTPUTS', '0'), m, n * steps / (m / 1e3), ev))
+       os.environ.get('PD_PLAN', '0') + '/' + os.environ.get('PD_WALK_PLAN', '1'), os.environ.get('OUTPUTS', '0'), m, n * steps / (m / 1e3), ev))
 
 # PLAN_CLOCKS=1 (library built with -DPD_PLAN_CLOCKS): phase times of the last
 # k_rollout_plan launch, per CTA (globaltimer, ns)
@@ -104,3 +104,20 @@ if os.environ.get('PLAN_CLOCKS') == '1':
   if quiet.any():
     print('  CTAs without events: %d, commit+fill mean %.1f max %.1f us' %
           (quiet.sum(), tail[quiet].mean(), tail[quiet].max()))
+
+# WALK_CLOCKS=1 (library built with -DPD_PLAN_CLOCKS): phase times of the
+# first 1024 CTAs of the last k_walk_plan launch (globaltimer, ns)
+if os.environ.get('WALK_CLOCKS') == '1':
+  buf = (C.c_ulonglong * (1024 * 8))()
+  nat.lib.pd_debug_plan_clocks(buf)
+  a = np.frombuffer(buf, dtype=np.uint64).reshape(1024, 8).astype(np.int64)
+  a = a[a[:, 0] > 0][:, :7]
+  names = ['prologue', 'dense', 'queue', 'commit', 'store (+ later chunks)',
+           'epilogue']
+  d = np.diff(a, axis=1) / 1e3
+  print('CTAs %d; first CTA start to last of these ending %.1f us; CTA '
+        'lifetime mean %.1f us' % (len(a), (a[:, 6].max() - a[:, 0].min()) / 1e3,
+                                   (a[:, 6] - a[:, 0]).mean() / 1e3))
+  for i, nm in enumerate(names):
+    print('  %-24s mean %6.2f  p50 %6.2f  max %6.2f us' %
+          (nm, d[:, i].mean(), np.median(d[:, i]), d[:, i].max()))

@@ -261,11 +261,84 @@ struct FastTimes {
   float margin;   // microsecond rounding + float32 sums of the comparisons
 };
 
-__device__ __forceinline__ FastTimes fast_times(long long dwell_us) {
+__host__ __device__ __forceinline__ FastTimes fast_times(long long dwell_us) {
   FastTimes t;
   t.dwell_s = static_cast<float>(static_cast<double>(dwell_us) * 1e-6);
   t.margin = 1.5e-6f + 3e-7f * t.dwell_s;
   return t;
+}
+// The launch's FastTimes, computed once on the host (launch_fast) and read as
+// constant-bank operands: the kernels would otherwise re-derive them from the
+// dwell time wherever registers are short.
+__device__ __forceinline__ FastTimes fast_times(const StepArgs& a) {
+  FastTimes t;
+  t.dwell_s = a.fast_dwell_s;
+  t.margin = a.fast_margin;
+  return t;
+}
+
+// The pieces of an iteration (fast_event and fast_quiet are the same
+// arithmetic, instruction for instruction).
+struct FastRates {
+  float r0, r1, r2, sum, tot, eps;
+};
+
+template <int RATE>
+__device__ __forceinline__ FastRates fast_rates(const FastGeo& g, float bx,
+                                                float by) {
+  FastRates f;
+  const float dx0 = bx - g.gx[0], dy0 = by - g.gy[0];
+  const float dx1 = bx - g.gx[1], dy1 = by - g.gy[1];
+  const float dx2 = bx - g.gx[2], dy2 = by - g.gy[2];
+  const float a0 = __fmaf_rn(dx0, dx0, dy0 * dy0);
+  const float a1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
+  const float a2 = __fmaf_rn(dx2, dx2, dy2 * dy2);
+  if (RATE == PD_RATE_PRIOR) {
+    // exp(-5 a) = 2^(-5 log2(e) a); the factor ln 2 / 3 goes on the sum
+    const float kC = -7.213475204444817f;
+    f.r0 = ex2_approx(kC * a0);
+    f.r1 = ex2_approx(kC * a1);
+    f.r2 = ex2_approx(kC * a2);
+    f.eps = __fmaf_rn(5.0f * kFastEps1, fminf(a0, fminf(a1, a2)), kFastEps0);
+  } else {
+    const float kS = static_cast<float>(16.0 / (kBond * kBond));
+    f.r0 = rcp_approx(__fmaf_rn(a0, kS, 1.0f));
+    f.r1 = rcp_approx(__fmaf_rn(a1, kS, 1.0f));
+    f.r2 = rcp_approx(__fmaf_rn(a2, kS, 1.0f));
+    f.eps = kFastEps0;
+  }
+  f.sum = (f.r0 + f.r1) + f.r2;
+  f.tot = RATE == PD_RATE_PRIOR ? 0.23104906018664842f * f.sum : f.sum;
+  return f;
+}
+
+// -log(1 - u): u53 lies in [u24, u24 + 2^-24); v = 1 - u24
+__device__ __forceinline__ float fast_draw(uint32_t wx, float* v) {
+  *v = 1.0f - static_cast<float>(wx >> 8) * (1.0f / 16777216.0f);
+  return -0.6931471805599453f * lg2_approx(*v);
+}
+
+// Lower bound of the waiting time, and 1 / total.
+__device__ __forceinline__ float fast_wait_lo(const FastRates& f, float draw,
+                                              float* rc, float* t_mid,
+                                              float* slack) {
+  *rc = rcp_approx(f.tot);
+  *t_mid = draw * *rc;
+  *slack = __fmaf_rn(*t_mid, f.eps + 1e-6f, kFastDrawAbs * *rc);
+  return *t_mid - *slack;
+}
+
+// A vanishing total rate (beam far away; float32 underflow of the prior is
+// routine) means a waiting time of hours whatever the
+// error, unless the draw is exactly zero.
+__device__ __forceinline__ bool fast_no_rate(const FastRates& f) {
+  return !(f.tot > 1e-30f) && f.tot == f.tot;
+}
+
+__device__ __forceinline__ bool fast_certain_no(bool no_rate, uint32_t wx,
+                                                float e_lo, float t_lo,
+                                                const FastTimes& tm) {
+  return no_rate ? (wx >> 8) != 0u : (e_lo + t_lo) - tm.margin > tm.dwell_s;
 }
 
 template <int RATE>
@@ -274,60 +347,27 @@ __device__ __forceinline__ int fast_event(const FastGeo& g, float bx, float by,
                                           float e_hi, const FastTimes& tm,
                                           int* slot, float* t_lo,
                                           float* t_hi) {
-  float r0, r1, r2, eps;
-  {
-    const float dx0 = bx - g.gx[0], dy0 = by - g.gy[0];
-    const float dx1 = bx - g.gx[1], dy1 = by - g.gy[1];
-    const float dx2 = bx - g.gx[2], dy2 = by - g.gy[2];
-    const float a0 = __fmaf_rn(dx0, dx0, dy0 * dy0);
-    const float a1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
-    const float a2 = __fmaf_rn(dx2, dx2, dy2 * dy2);
-    if (RATE == PD_RATE_PRIOR) {
-      // exp(-5 a) = 2^(-5 log2(e) a); the factor ln 2 / 3 goes on the sum
-      const float kC = -7.213475204444817f;
-      r0 = ex2_approx(kC * a0);
-      r1 = ex2_approx(kC * a1);
-      r2 = ex2_approx(kC * a2);
-      eps = __fmaf_rn(5.0f * kFastEps1, fminf(a0, fminf(a1, a2)), kFastEps0);
-    } else {
-      const float kS = static_cast<float>(16.0 / (kBond * kBond));
-      r0 = rcp_approx(__fmaf_rn(a0, kS, 1.0f));
-      r1 = rcp_approx(__fmaf_rn(a1, kS, 1.0f));
-      r2 = rcp_approx(__fmaf_rn(a2, kS, 1.0f));
-      eps = kFastEps0;
-    }
-  }
-  const float sum = (r0 + r1) + r2;
-  const float tot =
-      RATE == PD_RATE_PRIOR ? 0.23104906018664842f * sum : sum;
-  // -log(1 - u): u53 lies in [u24, u24 + 2^-24)
-  const float v = 1.0f - static_cast<float>(wx >> 8) * (1.0f / 16777216.0f);
-  const float draw = -0.6931471805599453f * lg2_approx(v);
-  const float rc = rcp_approx(tot);
-  const float t_mid = draw * rc;
-  const float slack = __fmaf_rn(t_mid, eps + 1e-6f, kFastDrawAbs * rc);
-  *t_lo = t_mid - slack;
+  const FastRates f = fast_rates<RATE>(g, bx, by);
+  float v, rc, t_mid, slack;
+  const float draw = fast_draw(wx, &v);
+  *t_lo = fast_wait_lo(f, draw, &rc, &t_mid, &slack);
   // the bits dropped from the uniform raise the draw by -log(1 - d / v),
   // d < 2^-24: below 6.1e-8 / v while v > 2^-12, unbounded as v -> 2^-24
   const float dropped =
       v > 2.5e-4f ? 6.1e-8f * rcp_approx(v) : __int_as_float(0x7f800000);
   *t_hi = (t_mid + slack) + dropped * rc;
-  // A vanishing total rate (beam far away; float32 underflow of the prior is
-  // routine) means a waiting time of hours whatever the
-  // error, unless the draw is exactly zero.
-  const bool no_rate = !(tot > 1e-30f) && tot == tot;
-  const bool certain_no =
-      no_rate ? (wx >> 8) != 0u : (e_lo + *t_lo) - tm.margin > tm.dwell_s;
+  const bool no_rate = fast_no_rate(f);
+  const bool certain_no = fast_certain_no(no_rate, wx, e_lo, *t_lo, tm);
   const bool certain_hop =
       !no_rate && (e_hi + *t_hi) + 2.0f * tm.margin < tm.dwell_s;
   if (certain_no) return FAST_NO_HOP;
   if (!certain_hop) return FAST_UNSURE;
   // rng.choice(3, p = rates / total): thresholds r0 / tot and (r0 + r1) / tot
   // against u53(z, w), which lies in [uc, uc + 2^-24)
-  const float inv = rcp_approx(sum);
-  const float p0 = r0 * inv, p01 = (r0 + r1) * inv;
+  const float inv = rcp_approx(f.sum);
+  const float p0 = f.r0 * inv, p01 = (f.r0 + f.r1) * inv;
   const float uc = static_cast<float>(wz >> 8) * (1.0f / 16777216.0f);
-  const float eta = __fmaf_rn(3.0f, eps, 2e-6f);
+  const float eta = __fmaf_rn(3.0f, f.eps, 2e-6f);
   const bool le0 = p0 + eta < uc;             // c0 <= u for sure
   const bool gt0 = p0 - eta > uc + 6.0e-8f;   // c0 >  u for sure
   const bool le1 = p01 + eta < uc;
@@ -335,6 +375,31 @@ __device__ __forceinline__ int fast_event(const FastGeo& g, float bx, float by,
   if (!((le0 || gt0) && (le1 || gt1))) return FAST_UNSURE;
   *slot = (le0 ? 1 : 0) + (le1 ? 1 : 0);
   return FAST_HOP;
+}
+
+// Iteration 0 of a control (clock at zero) for a Si on a bulk site of either
+// class, when all that is asked is "does it certainly end the control without
+// a hop": fast_event(...) == FAST_NO_HOP for the geometry g0 and for its flip,
+// the draw shared (it depends on the Philox word only).
+template <int RATE>
+__device__ __forceinline__ void fast_quiet_both(const FastGeo& g0, float bx,
+                                                float by, uint32_t wx,
+                                                const FastTimes& tm,
+                                                bool* quiet0, bool* quiet1) {
+  float v, rc, t_mid, slack;
+  const float draw = fast_draw(wx, &v);
+  {
+    const FastRates f = fast_rates<RATE>(g0, bx, by);
+    const float t_lo = fast_wait_lo(f, draw, &rc, &t_mid, &slack);
+    *quiet0 = fast_certain_no(fast_no_rate(f), wx, 0.f, t_lo, tm);
+  }
+  {
+    FastGeo g1 = g0;
+    flip_geo(&g1);
+    const FastRates f = fast_rates<RATE>(g1, bx, by);
+    const float t_lo = fast_wait_lo(f, draw, &rc, &t_mid, &slack);
+    *quiet1 = fast_certain_no(fast_no_rate(f), wx, 0.f, t_lo, tm);
+  }
 }
 
 // Clock bounds after a hop (directed rounding; 1 us for the rounding of the

@@ -664,6 +664,11 @@ struct StepArgs {
                               // more warps and less intra-warp divergence)
   int32_t action_mode;        // pd_action_mode (rollouts)
   int32_t plan_envs_per_cta;  // k_rollout_plan: envs a CTA owns (<= 16)
+  // k_walk_plan -> k_walk_fast<LIST>: (env, first step still to do) of the
+  // envs that left the plan, and how many there are
+  int2* defer_list;
+  uint32_t* defer_count;
+  float fast_dwell_s, fast_margin;  // FastTimes of dwell_us_scalar (pd_fast.cuh)
   int32_t prepass;            // 1: float32 pre-pass (certainly_no_hop) enabled
   int32_t walk_min_ready;     // k_walk: lanes with an exact iteration pending
   int32_t walk_max_reps;      //   that end the bookkeeping repeats / their cap

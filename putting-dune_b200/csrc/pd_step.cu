@@ -1534,6 +1534,15 @@ static int& option_plan() {
   }();
   return on;
 }
+// k_walk_plan + k_walk_fast<LIST> instead of k_walk_fast alone for large
+// batches under the relative adapter.
+static int& option_walk_plan() {
+  static int on = [] {
+    const char* v = getenv("PD_WALK_PLAN");
+    return (!v || v[0] != '0') ? 1 : 0;
+  }();
+  return on;
+}
 // (the float32 pre-pass and the fast kernels reason about the direct method)
 static bool prepass_enabled() {
   return option_prepass() != 0 && option_race_sampling() == 0;
@@ -1671,10 +1680,12 @@ static int launch_step(const StepArgs& a_in, bool rollout,
     // in float32 with an error bound, exact replay of what it cannot settle.
     if (rollout && !a.stream_mode && fast_enabled() && a.dwell_us_scalar > 0 &&
         a.dwell_us_scalar < 3000LL * 1000000LL && !a.skip) {
+      const int plan_mode = (option_plan() ? 1 : 0) |
+                            (option_walk_plan() ? 2 : 0);
       if (walk || !spec)
         return launch_fast<RATE>(a, true, grid_for(a.st.n_envs, true), stream,
-                                 0);
-      return launch_fast<RATE>(a, false, grid, stream, option_plan());
+                                 plan_mode);
+      return launch_fast<RATE>(a, false, grid, stream, plan_mode);
     }
   }
   if (a.packed_out || (a.actions_f32 && !a.stream_mode)) {
@@ -1901,6 +1912,7 @@ extern "C" int pd_set_option(const char* name, int value) {
   if (!strcmp(name, "rollout_spec")) slot = &pd::option_rollout_spec();
   if (!strcmp(name, "race_sampling")) slot = &pd::option_race_sampling();
   if (!strcmp(name, "plan")) slot = &pd::option_plan();
+  if (!strcmp(name, "walk_plan")) slot = &pd::option_walk_plan();
   if (!slot) {
     pd::set_error("pd_set_option: unknown option '%s'", name);
     return PD_ERR_INVALID_ARGUMENT;
@@ -2142,6 +2154,23 @@ struct HostPipeline {
   size_t own_bytes[5] = {};
   int64_t clean_in = 0, clean_out = 0;
   cudaEvent_t done = nullptr, copied_all = nullptr, cleaned = nullptr;
+};
+
+// Leaves no copy in flight on the caller's buffers when a host-buffer call
+// returns early (an error code from PD_CUDA_OK or a failed launch): the
+// caller may free or reuse its host and device buffers as soon as the call
+// is back.  The streamed form's "ready" state of the stagings is dropped too.
+struct DrainOnError {
+  HostPipeline* p;
+  cudaStream_t s;
+  bool armed = true;
+  ~DrainOnError() {
+    if (!armed) return;
+    cudaStreamSynchronize(p->h2d);
+    cudaStreamSynchronize(p->d2h);
+    cudaStreamSynchronize(s);
+    p->clean_in = p->clean_out = 0;
+  }
 };
 
 // Makes sure the library-owned staging `k` holds `bytes` bytes.
@@ -2465,6 +2494,7 @@ extern "C" int pd_rollout_actions_host(
   if (n_chunks > n_steps) n_chunks = n_steps;
   if (n_chunks < 1) n_chunks = 1;
   // staging may still be read by earlier work queued on `s`
+  pd::DrainOnError guard{pipe, s};
   PD_CUDA_OK(cudaEventRecord(pipe->start, s));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->h2d, pipe->start, 0));
   PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->start, 0));
@@ -2488,13 +2518,7 @@ extern "C" int pd_rollout_actions_host(
         max_distance_angstroms, dwell_us_scalar, steps, image_duration_us,
         h_si_idx ? d_si_idx + off : nullptr,
         h_elapsed_us ? d_elapsed_us + off : nullptr, stream);
-    if (rcode != PD_OK) {
-      // nothing may stay in flight on the caller's buffers
-      cudaStreamSynchronize(pipe->h2d);
-      cudaStreamSynchronize(pipe->d2h);
-      cudaStreamSynchronize(s);
-      return rcode;
-    }
+    if (rcode != PD_OK) return rcode;  // (the guard drains the streams)
     PD_CUDA_OK(cudaEventRecord(pipe->stepped[c], s));
     PD_CUDA_OK(cudaStreamWaitEvent(pipe->d2h, pipe->stepped[c], 0));
     if (h_si_idx)
@@ -2508,6 +2532,7 @@ extern "C" int pd_rollout_actions_host(
   }
   PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
   PD_CUDA_OK(cudaStreamSynchronize(s));
+  guard.armed = false;
   return PD_OK;
 }
 
@@ -2629,14 +2654,10 @@ extern "C" int pd_rollout_actions_host_f32(
       d_elapsed_us = static_cast<int64_t*>(pipe->own[3]);
     }
   }
-  // On an error nothing may stay in flight on the caller's buffers.
-  auto fail = [&](int code) {
-    cudaStreamSynchronize(pipe->h2d);
-    cudaStreamSynchronize(pipe->d2h);
-    cudaStreamSynchronize(s);
-    pipe->clean_in = pipe->clean_out = 0;
-    return code;
-  };
+  // On an error nothing may stay in flight on the caller's buffers: the
+  // guard drains the three streams on every early return (PD_CUDA_OK too).
+  pd::DrainOnError guard{pipe, s};
+  auto fail = [&](int code) { return code; };
   int total_w = 0;
   for (int wgt : schedule) total_w += wgt > 0 ? wgt : 1;
   int n_chunks = static_cast<int>(schedule.size());
@@ -2713,6 +2734,7 @@ extern "C" int pd_rollout_actions_host_f32(
   }
   PD_CUDA_OK(cudaStreamSynchronize(pipe->d2h));
   PD_CUDA_OK(cudaStreamSynchronize(s));
+  guard.armed = false;
   return PD_OK;
 }
 

@@ -237,7 +237,9 @@ __device__ __noinline__ float2 direct_offset(const StepArgs& a, int64_t env,
 // position are re-read / re-derived in the (out-of-line) places that need
 // them.  REL: the relative adapter (action_adapters.py:163-188).
 // ---------------------------------------------------------------------------
-template <int RATE, int IO, bool REL>
+// LIST: the envs and their first steps come from a.defer_list (the envs that
+// k_walk_plan handed over); otherwise every env of the batch from step 0.
+template <int RATE, int IO, bool REL, bool LIST = false>
 __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
     k_walk_fast(const __grid_constant__ StepArgs a) {
   // The tables are read through L1: a hop touches one 16-byte row, in one
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
   // action stream's L1 lines need.
   const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
                          reinterpret_cast<const int4*>(a.lat.nbr)};
-  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const FastTimes tm = fast_times(a);
   const float md_f = static_cast<float>(a.max_distance);
   // action -> beam offset in the units fast_event expects
   const float md_s = static_cast<float>(
@@ -255,15 +257,22 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
   const int n_steps = a.n_steps;
   const ActionStream<IO> ctl(a);
   const int lane = threadIdx.x & 31;
-  const int64_t n_batches = (n + 31) / 32;
+  const int64_t n_items = LIST ? static_cast<int64_t>(*a.defer_count) : n;
+  const int64_t n_batches = (n_items + 31) / 32;
   const int64_t warps_total =
       static_cast<int64_t>(gridDim.x) * (kStepThreads / 32);
   const int64_t wid = static_cast<int64_t>(blockIdx.x) * (kStepThreads / 32) +
                       (threadIdx.x >> 5);
 
   for (int64_t b = wid; b < n_batches; b += warps_total) {
-    const int64_t env = b * 32 + lane;
-    bool active = env < n;
+    bool active = b * 32 + lane < n_items;
+    int t_first = 0;
+    int64_t env = b * 32 + lane;
+    if (LIST) {
+      const int2 item = active ? a.defer_list[b * 32 + lane] : make_int2(0, 0);
+      env = item.x;
+      t_first = item.y;
+    }
     // ---- the env's registers ----
     FastSite s;
     s.si = 0;
@@ -275,8 +284,9 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
     int events = 0, transitions = 0, recentres = 0;
     uint8_t status = 0;
     double2 act_next = make_double2(0.0, 0.0);
-    int t = 0;
-    int64_t row = env;  // t * n + env: this step's element of every [T][n] array
+    int t = t_first;
+    // t * n + env: this step's element of every [T][n] array
+    int64_t row = static_cast<int64_t>(t_first) * n + env;
     uint32_t it = 0;    // iteration of the current control = its hops so far
     int si0 = 0;        // Si site when the control began
     float e_lo = 0.f, e_hi = 0.f, bx = 0.f, by = 0.f;
@@ -308,14 +318,14 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
     };
     if (active) {
       const double2 act = ctl.load(row);
-      if (n_steps > 1) act_next = ctl.load(row + n);
+      if (t + 1 < n_steps) act_next = ctl.load(row + n);
       // a step takes a few hundred cycles, DRAM a thousand: the action
       // stream is requested several steps ahead (L2 now, L1 two steps ahead
       // in the loop), the next batch's state a whole batch ahead
 #pragma unroll 1
-      for (int k = 2; k < n_steps && k < 2 + kActionsAhead; ++k)
+      for (int k = 2; t + k < n_steps && k < 2 + kActionsAhead; ++k)
         prefetch_l2(ctl.at(row + k * n));
-      if (env + warps_total * 32 < n) {
+      if (!LIST && env + warps_total * 32 < n) {
         prefetch_env(a, env + warps_total * 32);
         prefetch_l1(ctl.at(row + warps_total * 32));
         if (n_steps > 1) prefetch_l1(ctl.at(row + n + warps_total * 32));
@@ -397,7 +407,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
         begin_control(act);
       } else {
         const long long total =
-            static_cast<long long>(n_steps) * step_us +
+            static_cast<long long>(n_steps - t_first) * step_us +
             static_cast<long long>(recentres) * a.image_duration_us;
         atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + env),
                   static_cast<unsigned long long>(total));
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   // action stream's L1 lines need.
   const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
                          reinterpret_cast<const int4*>(a.lat.nbr)};
-  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const FastTimes tm = fast_times(a);
   const bool relative = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
   const float md_f = static_cast<float>(a.max_distance);
   const float md_s = static_cast<float>(
@@ -735,7 +745,7 @@ __device__ __noinline__ unsigned site_busy_mask(const StepArgs& a,
   const int lane = threadIdx.x & 31;
   bool busy = false;
   if (lane < len) {
-    const FastTimes tm = fast_times(a.dwell_us_scalar);
+    const FastTimes tm = fast_times(a);
     const float md_s = static_cast<float>(
         a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
     const double2 act = ActionStream<IO>(a).load(t_first + lane, env);
@@ -766,7 +776,7 @@ __device__ __noinline__ void serial_control(const StepArgs& a, const Tables tab,
                                             SerialResult* out) {
   auto rotation = [&]() { return cs; };
   FastSite s = fast_site<RATE>(tab, si, cs.x, cs.y);
-  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const FastTimes tm = fast_times(a);
   const float md_s = static_cast<float>(
       a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
   const double2 act = ActionStream<IO>(a).load(t, env);
@@ -883,7 +893,7 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
   __shared__ int s_si_start[kPlanEnvs];
   __shared__ WalkState s_ws[kPlanEnvs];
   __shared__ uint32_t q_count;
-  const FastTimes tm = fast_times(a.dwell_us_scalar);
+  const FastTimes tm = fast_times(a);
   const float md_f = static_cast<float>(a.max_distance);
   const float md_s = static_cast<float>(
       a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
@@ -979,13 +989,9 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
       const uint4 w = philox4x32_10k(env_id0 + static_cast<uint32_t>(el),
                                      s_ctrl0[el] + static_cast<uint32_t>(t), 0u,
                                      PD_STREAM_KMC, a.keys);
-      int slot;
-      float t_lo, t_hi;
-      const bool busy0 = fast_event<RATE>(g, bx, by, w.x, w.z, 0.f, 0.f, tm,
-                                          &slot, &t_lo, &t_hi) != FAST_NO_HOP;
-      flip_geo(&g);
-      const bool busy1 = fast_event<RATE>(g, bx, by, w.x, w.z, 0.f, 0.f, tm,
-                                          &slot, &t_lo, &t_hi) != FAST_NO_HOP;
+      bool quiet0, quiet1;
+      fast_quiet_both<RATE>(g, bx, by, w.x, tm, &quiet0, &quiet1);
+      const bool busy0 = !quiet0, busy1 = !quiet1;
       // (a queue entry that does not fit stays UNSURE: the exact code runs it)
       tile[el][k] =
           (busy0 ? kPlanUnsure : 0u) | (busy1 ? kPlanUnsure << 16 : 0u);
@@ -1380,6 +1386,295 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
 }
 
 // ---------------------------------------------------------------------------
+// k_walk_plan: the same plan for large batches (n_envs >= a few waves of
+// lanes), where there are enough envs to give each its own lane and a launch
+// covers few steps.  A CTA of 256 threads owns 256 envs and works through the
+// call in chunks of 16 steps; thread = env in every phase, so the env's
+// geometry, counters and busy masks stay in registers:
+//   plan    for k in the chunk: action (coalesced over the envs), Philox,
+//           iteration 0 for both bulk classes -- uniform over the lanes, no
+//           bookkeeping between the evaluations -- one busy bit per class and
+//           step in a register; the controls that go on (~11 % per class) are
+//           queued and run to their end by the next free thread
+//           (plan_control), one uint16 per class in shared memory;
+//   commit  the thread jumps from one busy step of its env's current class to
+//           the next and follows the planned slots through the neighbour
+//           table; a certain re-centre is recorded as "FOV centred on site s";
+//   store   the thread writes its env's results step by step (coalesced over
+//           the envs).
+// An env whose next control the plan does not cover (UNSURE, a sheet-edge
+// site, a clip that may engage, a safe-area test within 1e-4 of its
+// threshold) is written back as it stands and handed, with the step it
+// stopped at, to k_walk_fast<LIST>, which runs such envs 32 to a warp: what
+// is a serial tail in k_rollout_plan is dense work here.
+// ---------------------------------------------------------------------------
+constexpr int kWalkPlanThreads = 256;
+constexpr int kWalkPlanChunk = 16;
+constexpr int kWalkPlanQueue = 2048;
+
+template <int RATE, int IO>
+__global__ void __launch_bounds__(kWalkPlanThreads, 4)
+    k_walk_plan(const __grid_constant__ StepArgs a) {
+  __shared__ uint32_t tile[kWalkPlanChunk][kWalkPlanThreads];
+  __shared__ uint32_t queue[kWalkPlanQueue];
+  __shared__ float s_geo[6][kWalkPlanThreads];
+  __shared__ uint32_t s_ctrl0[kWalkPlanThreads];
+  __shared__ uint32_t q_count;
+  const GlobalTables tab{reinterpret_cast<const double2*>(a.lat.base_xy),
+                         reinterpret_cast<const int4*>(a.lat.nbr)};
+  const FastTimes tm = fast_times(a);
+  const float md_f = static_cast<float>(a.max_distance);
+  const float md_s = static_cast<float>(
+      a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
+  const long long step_us = a.dwell_us_scalar + a.image_duration_us;
+  const int64_t n = a.st.n_envs;
+  const int n_steps = a.n_steps;
+  const ActionStream<IO> ctl(a);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t env0 = static_cast<int64_t>(blockIdx.x) * kWalkPlanThreads;
+  const int64_t env = env0 + tid;
+  const uint32_t env_id0 = a.st.env_offset + static_cast<uint32_t>(env0);
+  const bool mine = env < n;
+  PLAN_CLOCK(0);
+
+  // ---- the env of this thread ----
+  FastGeo g0;
+  float o0x[3], o0y[3];
+  uint32_t ctrl0 = 0;
+  int si = 0, cls = 2;
+  int4 row = make_int4(0, 0, 0, 0);
+  float qx = 0.5f, qy = 0.5f, iwx = 0.f, iwy = 0.f, iws = 0.f;
+  int hops = 0, recentres = 0, hops_synced = 0, fov_site = -1;
+  bool check_area = true;   // simulator.py:156 at the first step of the call
+  int stopped_at = -1;      // >= 0: handed over at this step of the call
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g0.gx[i] = g0.gy[i] = o0x[i] = o0y[i] = 0.f;
+  if (mine) {
+    const Lattice4 lat = load_lattice4(a.st.lattice, env);
+    fast_geo_bulk<RATE>(Lattice4{0.0, 0.0, lat.c, lat.s}, 0, &g0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) bulk_offset<RATE>(g0, i, &o0x[i], &o0y[i]);
+    ctrl0 = a.st.ctrl_count[env];
+    si = a.st.si_idx[env];
+    row = __ldg(tab.nbr + si);
+    cls = (row.w >> kSiteClassShift) & 3;
+    Observed obs;
+    obs.sync(load_fov4(a.st.fov, env), site_position(tab.position(si), lat));
+    qx = obs.qx;
+    qy = obs.qy;
+    iwx = obs.iwx;
+    iwy = obs.iwy;
+    iws = __fdividef(1.0f, static_cast<float>(a.st.fov_scale[env]));
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s_geo[i][tid] = g0.gx[i];
+    s_geo[3 + i][tid] = g0.gy[i];
+  }
+  s_ctrl0[tid] = ctrl0;
+  int steps_done = 0;  // steps of the call committed by this kernel
+  PLAN_CLOCK(1);
+
+  for (int t0 = 0; t0 < n_steps; t0 += kWalkPlanChunk) {
+    const int len_c =
+        n_steps - t0 < kWalkPlanChunk ? n_steps - t0 : kWalkPlanChunk;
+    __syncthreads();  // the previous chunk's tile and queue are done with
+    if (tid == 0) q_count = 0;
+    __syncthreads();
+    const bool live = mine && stopped_at < 0;
+    // ---- plan, dense pass ----
+    uint32_t busy = 0;  // bit k: class 0, bit 16 + k: class 1
+    if (live) {
+      int64_t at = static_cast<int64_t>(t0) * n + env;
+      uint32_t ctrl = ctrl0 + static_cast<uint32_t>(t0);
+      for (int k = 0; k < len_c; ++k, at += n, ++ctrl) {
+        const double2 act = ctl.load(at);
+        const float bx =
+            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+        const float by =
+            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+        const uint4 w = philox4x32_10k(env_id0 + static_cast<uint32_t>(tid),
+                                       ctrl, 0u, PD_STREAM_KMC, a.keys);
+        bool quiet0, quiet1;
+        fast_quiet_both<RATE>(g0, bx, by, w.x, tm, &quiet0, &quiet1);
+        busy |= (quiet0 ? 0u : 1u) << k | (quiet1 ? 0u : 1u) << (16 + k);
+      }
+    }
+    // queue the controls that go on: a warp scan of the counts, one
+    // shared-memory atomic per warp
+    {
+      const int cnt = __popc(busy);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t base = 0;
+      if (total > 0) {
+        if (lane == 31)
+          base = atomicAdd(&q_count, static_cast<uint32_t>(total));
+        base = __shfl_sync(0xffffffffu, base, 31);
+      }
+      uint32_t q = base + static_cast<uint32_t>(incl - cnt);
+      for (uint32_t bits = busy; bits; bits &= bits - 1u, ++q) {
+        const int bit = __ffs(bits) - 1;
+        const int k = bit & 15, c = bit >> 4;
+        if (q < kWalkPlanQueue)
+          queue[q] =
+              (static_cast<uint32_t>(k * kWalkPlanThreads + tid) << 1) | c;
+        else  // no room: the exact code runs it (the env is handed over)
+          reinterpret_cast<unsigned short*>(&tile[k][tid])[c] =
+              static_cast<unsigned short>(kPlanUnsure);
+      }
+    }
+    __syncthreads();
+    if (t0 == 0) PLAN_CLOCK(2);
+    // ---- plan, queue pass ----
+    {
+      const int n_q = q_count < kWalkPlanQueue ? static_cast<int>(q_count)
+                                               : kWalkPlanQueue;
+      for (int q = tid; q < n_q; q += kWalkPlanThreads) {
+        const uint32_t entry = queue[q];
+        const int c = entry & 1u;
+        const int k = static_cast<int>(entry >> 1) / kWalkPlanThreads;
+        const int el = static_cast<int>(entry >> 1) % kWalkPlanThreads;
+        const int t = t0 + k;
+        const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
+        const float bx =
+            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+        const float by =
+            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+        FastGeo g;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          g.gx[i] = s_geo[i][el];
+          g.gy[i] = s_geo[3 + i][el];
+        }
+        if (c) flip_geo(&g);
+        const uint32_t r16 = plan_control<RATE>(
+            g, bx, by, env_id0 + static_cast<uint32_t>(el),
+            s_ctrl0[el] + static_cast<uint32_t>(t), tm, a.keys);
+        reinterpret_cast<unsigned short*>(&tile[k][el])[c] =
+            static_cast<unsigned short>(r16);
+      }
+    }
+    __syncthreads();
+    if (t0 == 0) PLAN_CLOCK(3);
+    // ---- commit ----
+    int committed = 0;  // steps of this chunk committed
+    uint32_t changed = 0, recd = 0;  // bit k: step k moved the Si / re-centred
+    const int si_start = si;
+    if (live) {
+      committed = len_c;
+      bool ok = cls < 2 && q_clip_free(qx, qy, iwx, iwy, md_f);
+      if (check_area) {
+        if (q_inside(qx, qy)) check_area = false;
+        else ok = false;
+      }
+      if (!ok) committed = 0;
+      unsigned from = ~0u;
+      while (ok) {
+        const unsigned m = (cls == 0 ? busy : busy >> 16) & 0xFFFFu & from;
+        if (!m) break;  // the chunk is done
+        const int k = __ffs(m) - 1;
+        from = ~0u << (k + 1);
+        const uint32_t r16 =
+            reinterpret_cast<const unsigned short*>(&tile[k][tid])[cls];
+        if (r16 & kPlanUnsure) {
+          committed = k;
+          break;
+        }
+        const int n_hops = static_cast<int>(r16 & 7u);
+        int si_t = si, cls_t = cls;
+        int4 row_t = row;
+        float qx_t = qx, qy_t = qy;
+        for (int h = 0; h < n_hops; ++h) {
+          const int slot = static_cast<int>((r16 >> (4 + 2 * h)) & 3u);
+          // class 1: g1[i] = -g0[2 - i]
+          const int j = cls_t == 0 ? slot : 2 - slot;
+          const float sg = cls_t == 0 ? 1.f : -1.f;
+          const float ox = j == 0 ? o0x[0] : (j == 1 ? o0x[1] : o0x[2]);
+          const float oy = j == 0 ? o0y[0] : (j == 1 ? o0y[1] : o0y[2]);
+          qx_t = __fmaf_rn(sg * ox, iwx, qx_t);
+          qy_t = __fmaf_rn(sg * oy, iwy, qy_t);
+          si_t = slot == 0 ? row_t.x : (slot == 1 ? row_t.y : row_t.z);
+          row_t = __ldg(tab.nbr + si_t);
+          cls_t = (row_t.w >> kSiteClassShift) & 3;
+          if (cls_t == 2) break;  // onto the sheet's edge: the plan's next
+                                  // iteration assumed a bulk site's geometry
+        }
+        const bool in = q_inside(qx_t, qy_t), out = q_outside(qx_t, qy_t);
+        const bool due = hops + n_hops - hops_synced >= kObservedSyncHops;
+        if (cls_t == 2 || (!in && !out) || (due && !out)) {
+          committed = k;
+          break;
+        }
+        si = si_t;
+        row = row_t;
+        cls = cls_t;
+        qx = qx_t;
+        qy = qy_t;
+        hops += n_hops;
+        if (out) {
+          // simulator.py:156-169: the FOV is centred on the Si again
+          qx = qy = 0.5f;
+          iwx = iwy = iws;
+          recentres += 1;
+          fov_site = si;
+          hops_synced = hops;
+        }
+        tile[k][tid] = static_cast<uint32_t>(si);
+        changed |= 1u << k;
+        if (out) recd |= 1u << k;
+        if (!q_clip_free(qx, qy, iwx, iwy, md_f)) {
+          committed = k + 1;
+          break;
+        }
+      }
+      steps_done = t0 + committed;
+      if (committed < len_c) stopped_at = steps_done;
+    }
+    if (t0 == 0) PLAN_CLOCK(4);
+    // ---- store ----
+    {
+      int cur = si_start;
+      int64_t at = static_cast<int64_t>(t0) * n + env;
+      for (int k = 0; k < committed; ++k, at += n) {
+        if ((changed >> k) & 1u) cur = static_cast<int>(tile[k][tid]);
+        store_step<IO>(a, at, cur, ((recd >> k) & 1u) != 0u, step_us);
+      }
+    }
+  }
+  PLAN_CLOCK(5);
+  if (mine) {
+    // the env as it stands after steps_done steps
+    if (fov_site >= 0) store_centred_fov(a, env, fov_site);
+    if (steps_done > 0) {
+      const long long total =
+          static_cast<long long>(steps_done) * step_us +
+          static_cast<long long>(recentres) * a.image_duration_us;
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.sim_time_us + env),
+                static_cast<unsigned long long>(total));
+      a.st.si_idx[env] = si;
+      a.st.ctrl_count[env] = ctrl0 + static_cast<uint32_t>(steps_done);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + env),
+                static_cast<unsigned long long>(steps_done + hops));
+      if (hops > 0)
+        atomicAdd(
+            reinterpret_cast<unsigned long long*>(a.st.n_transitions + env),
+            static_cast<unsigned long long>(hops));
+    }
+    if (stopped_at >= 0) {
+      const uint32_t at = atomicAdd(a.defer_count, 1u);
+      a.defer_list[at] = make_int2(static_cast<int>(env), stopped_at);
+    }
+  }
+  PLAN_CLOCK(6);
+}
+
+// ---------------------------------------------------------------------------
 // Launch (called from launch_step, pd_step.cu).
 // ---------------------------------------------------------------------------
 // k_rollout_plan keeps the lattice tables (float64 positions, ushort4
@@ -1418,18 +1713,71 @@ extern "C" int pd_debug_plan_clocks(unsigned long long* out) {
 }
 #endif
 
-// plan_mode: 1 = k_rollout_plan where it applies (small batches, relative
-// adapter), 0 = k_rollout_fast.
+// Large batches under the relative adapter: k_walk_plan, then k_walk_fast over
+// the list of envs (and first steps) it handed over.
+template <int RATE, int IO>
+static int launch_walk_plan(const StepArgs& a_in, cudaStream_t stream) {
+  StepArgs a = a_in;
+  const int64_t n = a.st.n_envs;
+  // stream-ordered scratch from the device's default pool, which is told once
+  // to keep what it has been given (no trip to the driver per call)
+  static thread_local int pool_ready_for = -1;
+  int dev = 0;
+  PD_CUDA_OK(cudaGetDevice(&dev));
+  if (pool_ready_for != dev) {
+    cudaMemPool_t pool;
+    PD_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    PD_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
+                                       &keep));
+    pool_ready_for = dev;
+  }
+  void* scratch = nullptr;
+  const size_t bytes = 16 + static_cast<size_t>(n) * sizeof(int2);
+  PD_CUDA_OK(cudaMallocAsync(&scratch, bytes, stream));
+  a.defer_count = static_cast<uint32_t*>(scratch);
+  a.defer_list =
+      reinterpret_cast<int2*>(static_cast<unsigned char*>(scratch) + 16);
+  cudaError_t err = cudaMemsetAsync(scratch, 0, 16, stream);
+  if (err == cudaSuccess) {
+    const int64_t grid_p = (n + kWalkPlanThreads - 1) / kWalkPlanThreads;
+    k_walk_plan<RATE, IO>
+        <<<static_cast<unsigned>(grid_p), kWalkPlanThreads, 0, stream>>>(a);
+    // the list is short (the envs near the sheet's edge, a few per 10^4
+    // UNSURE controls): one CTA per SM is plenty, warps without work exit
+    k_walk_fast<RATE, IO, true, true>
+        <<<sm_count() * 2, kStepThreads, 0, stream>>>(a);
+    err = cudaGetLastError();
+  }
+  cudaFreeAsync(scratch, stream);
+  PD_CUDA_OK(err);
+  return PD_OK;
+}
+
+// plan_mode: bit 0 = k_rollout_plan where it applies (small batches, relative
+// adapter) instead of k_rollout_fast; bit 1 = k_walk_plan (large batches,
+// relative adapter, a few steps or more) instead of k_walk_fast.
 template <int RATE>
-int launch_fast(const StepArgs& a, bool walk, int grid, cudaStream_t stream,
+int launch_fast(const StepArgs& a_in, bool walk, int grid, cudaStream_t stream,
                 int plan_mode) {
+  StepArgs a = a_in;
+  {
+    const FastTimes tm = fast_times(static_cast<long long>(a.dwell_us_scalar));
+    a.fast_dwell_s = tm.dwell_s;
+    a.fast_margin = tm.margin;
+  }
   const int io = a.packed_out ? 1 : (a.actions_f32 ? 2 : 0);
   const bool rel = a.action_mode == PD_ACTION_RELATIVE_TO_SILICON;
-  if (!walk && rel && plan_mode && a.n_steps >= 8 &&
+  if (!walk && rel && (plan_mode & 1) && a.n_steps >= 8 &&
       a.lat.n_sites <= kPlanMaxSites)
     return io == 1   ? launch_plan<RATE, 1>(a, stream)
            : io == 2 ? launch_plan<RATE, 2>(a, stream)
                      : launch_plan<RATE, 0>(a, stream);
+  if (walk && rel && (plan_mode & 2) && a.n_steps >= 4 &&
+      a.st.n_envs >= 32768)
+    return io == 1   ? launch_walk_plan<RATE, 1>(a, stream)
+           : io == 2 ? launch_walk_plan<RATE, 2>(a, stream)
+                     : launch_walk_plan<RATE, 0>(a, stream);
   void (*kern)(const StepArgs) = nullptr;
   if (walk) {
     kern = io == 1   ? (rel ? k_walk_fast<RATE, 1, true>

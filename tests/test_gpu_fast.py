@@ -38,13 +38,17 @@ def nat():
   yield _native
   _native.lib.pd_set_fast_path(1)
   _native.lib.pd_set_option(b'plan', 0)
+  _native.lib.pd_set_option(b'walk_plan', 1)
 
 
 def _select(nat, kernels):
-  """'plan': k_rollout_plan where it applies (opt-in); 'fast': k_rollout_fast /
-  k_walk_fast (the default); 'exact': the float64 kernels."""
+  """'plan': k_rollout_plan (small batches) / k_walk_plan (large batches) where
+  they apply; 'fast': k_rollout_fast / k_walk_fast only; 'exact': the float64
+  kernels.  (The default is k_rollout_fast for small, k_walk_plan for large
+  batches.)"""
   nat.check(nat.lib.pd_set_option(b'fast_path', 0 if kernels == 'exact' else 1))
   nat.check(nat.lib.pd_set_option(b'plan', 1 if kernels == 'plan' else 0))
+  nat.check(nat.lib.pd_set_option(b'walk_plan', 1 if kernels == 'plan' else 0))
 
 
 def _rollout(eng, nat, kernels, n, seed, ctl, dwell, spec, mode, shift_fov,
