@@ -394,6 +394,12 @@ int pd_set_fast_path(int enabled);
  *                                    shared memory) instead of k_rollout_fast;
  *                                    same results, slower on the benchmarked
  *                                    workload
+ *   "walk_plan"     PD_WALK_PLAN     (default 1) large-batch rollouts under the
+ *                                    relative adapter (>= 3 waves of CTAs, >=
+ *                                    8 steps) through k_walk_plan, followed by
+ *                                    k_walk_fast over the envs it hands over,
+ *                                    instead of k_walk_fast alone; 2 = for
+ *                                    every large batch (parity tests)
  *   "race_sampling" PD_SAMPLING_RACE (default 0) events by the race of
  *                                    competing exponentials -- each neighbour
  *                                    draws Exp(rate_i), the smallest wins --

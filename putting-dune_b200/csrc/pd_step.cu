@@ -1539,7 +1539,7 @@ static int& option_plan() {
 static int& option_walk_plan() {
   static int on = [] {
     const char* v = getenv("PD_WALK_PLAN");
-    return (!v || v[0] != '0') ? 1 : 0;
+    return !v ? 1 : (v[0] == '2' ? 2 : (v[0] != '0' ? 1 : 0));
   }();
   return on;
 }
@@ -1681,7 +1681,8 @@ static int launch_step(const StepArgs& a_in, bool rollout,
     if (rollout && !a.stream_mode && fast_enabled() && a.dwell_us_scalar > 0 &&
         a.dwell_us_scalar < 3000LL * 1000000LL && !a.skip) {
       const int plan_mode = (option_plan() ? 1 : 0) |
-                            (option_walk_plan() ? 2 : 0);
+                            (option_walk_plan() ? 2 : 0) |
+                            (option_walk_plan() == 2 ? 4 : 0);
       if (walk || !spec)
         return launch_fast<RATE>(a, true, grid_for(a.st.n_envs, true), stream,
                                  plan_mode);
@@ -1917,7 +1918,7 @@ extern "C" int pd_set_option(const char* name, int value) {
     pd::set_error("pd_set_option: unknown option '%s'", name);
     return PD_ERR_INVALID_ARGUMENT;
   }
-  *slot = value ? 1 : 0;
+  *slot = slot == &pd::option_walk_plan() && value == 2 ? 2 : (value ? 1 : 0);
   return PD_OK;
 }
 

@@ -1412,8 +1412,12 @@ constexpr int kWalkPlanThreads = 256;
 constexpr int kWalkPlanChunk = 16;
 constexpr int kWalkPlanQueue = 2048;
 
+#ifndef PD_WALK_PLAN_BLOCKS  // resident CTAs per SM (registers: 65536 / 256 / this)
+#define PD_WALK_PLAN_BLOCKS 4
+#endif
+
 template <int RATE, int IO>
-__global__ void __launch_bounds__(kWalkPlanThreads, 4)
+__global__ void __launch_bounds__(kWalkPlanThreads, PD_WALK_PLAN_BLOCKS)
     k_walk_plan(const __grid_constant__ StepArgs a) {
   __shared__ uint32_t tile[kWalkPlanChunk][kWalkPlanThreads];
   __shared__ uint32_t queue[kWalkPlanQueue];
@@ -1756,7 +1760,8 @@ static int launch_walk_plan(const StepArgs& a_in, cudaStream_t stream) {
 
 // plan_mode: bit 0 = k_rollout_plan where it applies (small batches, relative
 // adapter) instead of k_rollout_fast; bit 1 = k_walk_plan (large batches,
-// relative adapter, a few steps or more) instead of k_walk_fast.
+// relative adapter, eight steps or more) instead of k_walk_fast; bit 2 =
+// k_walk_plan for every batch the walk kernels take.
 template <int RATE>
 int launch_fast(const StepArgs& a_in, bool walk, int grid, cudaStream_t stream,
                 int plan_mode) {
@@ -1773,8 +1778,15 @@ int launch_fast(const StepArgs& a_in, bool walk, int grid, cudaStream_t stream,
     return io == 1   ? launch_plan<RATE, 1>(a, stream)
            : io == 2 ? launch_plan<RATE, 2>(a, stream)
                      : launch_plan<RATE, 0>(a, stream);
-  if (walk && rel && (plan_mode & 2) && a.n_steps >= 4 &&
-      a.st.n_envs >= 32768)
+  // (measured: k_walk_plan pays from three waves of its CTAs and eight steps
+  // per launch on; below that the fixed cost of the second launch and the
+  // last, partly filled wave eat the gain)
+  // plan_mode bit 2: whatever the sizes (the parity tests)
+  if (walk && rel &&
+      ((plan_mode & 4) ||
+       ((plan_mode & 2) && a.n_steps >= 8 &&
+        a.st.n_envs >=
+            3LL * sm_count() * PD_WALK_PLAN_BLOCKS * kWalkPlanThreads)))
     return io == 1   ? launch_walk_plan<RATE, 1>(a, stream)
            : io == 2 ? launch_walk_plan<RATE, 2>(a, stream)
                      : launch_walk_plan<RATE, 0>(a, stream);

@@ -48,7 +48,8 @@ def _select(nat, kernels):
   batches.)"""
   nat.check(nat.lib.pd_set_option(b'fast_path', 0 if kernels == 'exact' else 1))
   nat.check(nat.lib.pd_set_option(b'plan', 1 if kernels == 'plan' else 0))
-  nat.check(nat.lib.pd_set_option(b'walk_plan', 1 if kernels == 'plan' else 0))
+  # (2: k_walk_plan whatever the batch size and the number of steps)
+  nat.check(nat.lib.pd_set_option(b'walk_plan', 2 if kernels == 'plan' else 0))
 
 
 def _rollout(eng, nat, kernels, n, seed, ctl, dwell, spec, mode, shift_fov,
@@ -116,7 +117,11 @@ def test_fast_rollout_single_step_and_edge_sites(eng, nat):
   for n, t_steps, rate_fn in ((5000, 1, po.RATE_SIMPLE),
                               (5000, 40, po.RATE_SIMPLE),
                               (5000, 60, po.RATE_PRIOR),
-                              (301, 600, po.RATE_PRIOR)):
+                              (301, 600, po.RATE_PRIOR),
+                              # k_walk_plan with half of the envs handed over
+                              # to k_walk_fast<LIST>; a ragged last CTA, two
+                              # chunks
+                              (200001, 21, po.RATE_PRIOR)):
     spec = gh.rate_spec(rate_fn)
     acts = rng.uniform(-1, 1, size=(t_steps, n, 2))
     res = []
