@@ -794,13 +794,42 @@ def run_ours(args, cfg):
     g8 = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n * 8 / (ms8 / 1e3) / 1e9
     at_scale['rollout8'] = {
         'workload': '1Mi envs x 8 steps per launch',
-        'kernel': 'pd::k_walk_fast',
+        'kernel': 'pd::k_walk_plan (+ pd::k_walk_fast<LIST> over the envs it '
+                  'hands over)',
         'value': big_n * 8 / (ms8 / 1e3), 'unit': UNIT, 'launch_ms': ms8,
         'achieved': g8, 'peak': peak, 'frac': g8 / peak,
-        'traffic': ncu_traffic('r02_k_walk_fast_1Mi_8step.ncu.json'),
-        'warp_instructions': ncu_value('r02_k_walk_fast_1Mi_8step.ncu.json',
+        'traffic': ncu_traffic('r02_k_walk_plan_1Mi_8step.ncu.json'),
+        'warp_instructions': ncu_value('r02_k_walk_plan_1Mi_8step.ncu.json',
                                        'smsp__inst_executed.sum')}
-    del big, acts8, b_si, b_el
+    del acts8, b_si, b_el
+    # ... and in 64-step rollouts (the per-launch costs -- env state in and
+    # out, the second launch -- spread over 64 steps)
+    acts64 = torch.as_tensor(synthetic_controls(big_n, 64, 29)).to(dev)
+    b_si = torch.empty((64, big_n), dtype=torch.int32, device=dev)
+    b_el = torch.empty((64, big_n), dtype=torch.int64, device=dev)
+    def big_launch64(i):
+      nat.check(nat.lib.pd_rollout_actions(
+          C.byref(big.lattice_tables.c), C.byref(big.c), C.byref(rate.c),
+          P(acts64), nat.ACTION_RELATIVE_TO_SILICON, 1.42, DWELL_US,
+          64, IMAGE_US, P(b_si), P(b_el), stream))
+    big_launch64(0)
+    torch.cuda.synchronize()
+    bev = [(torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(4)]
+    for i in range(4):
+      flush.zero_()
+      bev[i][0].record()
+      big_launch64(i)
+      bev[i][1].record()
+    torch.cuda.synchronize()
+    ms64 = sum(a.elapsed_time(b) for a, b in bev) / 4
+    g64 = ALGORITHMIC_BYTES_PER_ENV_STEP * big_n * 64 / (ms64 / 1e3) / 1e9
+    at_scale['rollout64'] = {
+        'workload': '1Mi envs x 64 steps per launch',
+        'kernel': 'pd::k_walk_plan (+ pd::k_walk_fast<LIST>)',
+        'value': big_n * 64 / (ms64 / 1e3), 'unit': UNIT, 'launch_ms': ms64,
+        'achieved': g64, 'peak': peak, 'frac': g64 / peak}
+    del big, acts64, b_si, b_el
 
   # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
   frames = None
@@ -873,15 +902,15 @@ def run_ours(args, cfg):
                     'd2h_bytes_per_step': h_si.numel() * 4 +
                                           h_el32.numel() * 4,
                     'api': 'pd_rollout_actions_host_f32 (int32 Si site + '
-                           'int32 elapsed us out; one k_rollout_pre<STREAM> '
-                           'launch that follows the H2D copy)'},
+                           'int32 elapsed us out; the same copy-engine '
+                           'pipeline of chunks)'},
                 'float64_io': {
                     'value': e2e_f64, 'unit': UNIT,
                     'h2d_bytes_per_step': h_ctl[0].numel() * 8,
                     'd2h_bytes_per_step': h_si.numel() * 4 + h_el.numel() * 8,
                     'api': 'pd_rollout_actions_host (float64 actions, int64 '
-                           'elapsed us; the same streamed launch, '
-                           'k_rollout_pre<STREAM = 2>)'}},
+                           'elapsed us; copy-engine pipeline of 4 MiB '
+                           'chunks)'}},
         'gpu_launches': args.steps,
         'value_outputs': 'Si site int32 + elapsed us int64 written for every '
                          'env-step inside the timed launch',

@@ -1440,6 +1440,13 @@ __global__ void __launch_bounds__(kWalkPlanThreads, PD_WALK_PLAN_BLOCKS)
   const uint32_t env_id0 = a.st.env_offset + static_cast<uint32_t>(env0);
   const bool mine = env < n;
   PLAN_CLOCK(0);
+  // the first chunk's actions are DRAM-cold: ask for their lines now, the
+  // prologue's loads and float64 arithmetic cover the wait
+  if (mine && (lane & (IO != 0 ? 15 : 7)) == 0) {
+    const int first = n_steps < kWalkPlanChunk ? n_steps : kWalkPlanChunk;
+    for (int k = 0; k < first; ++k)
+      prefetch_l2(ctl.at(static_cast<int64_t>(k) * n + env));
+  }
 
   // ---- the env of this thread ----
   FastGeo g0;
@@ -1567,6 +1574,10 @@ __global__ void __launch_bounds__(kWalkPlanThreads, PD_WALK_PLAN_BLOCKS)
     __syncthreads();
     if (t0 == 0) PLAN_CLOCK(3);
     // ---- commit ----
+    if (mine && stopped_at < 0 && (lane & (IO != 0 ? 15 : 7)) == 0)
+      for (int k = t0 + kWalkPlanChunk;
+           k < n_steps && k < t0 + 2 * kWalkPlanChunk; ++k)
+        prefetch_l2(ctl.at(static_cast<int64_t>(k) * n + env));
     int committed = 0;  // steps of this chunk committed
     uint32_t changed = 0, recd = 0;  // bit k: step k moved the Si / re-centred
     const int si_start = si;
