@@ -11,6 +11,7 @@ the decisions assume.
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -339,3 +340,37 @@ def test_rate_ops_audit(eng, nat):
   assert out.simple_max_ulps * 4 <= out.guard_ulps
   assert out.simple_guard_taken < 2e-4 * out.evaluations
   assert out.prior_cast_differs < 1e-5 * out.evaluations
+
+
+@pytest.mark.parametrize('name', ['events_simple_large.npz',
+                                  'events_prior_large.npz',
+                                  'events_prior_single1000.npz'])
+def test_fast_rollout_vs_reference_golden(eng, nat, golden_dir, name):
+  """The fast rollout kernels against the unmodified reference itself: the
+  reference's own trajectories (256 envs x 100 steps per rate function; one
+  env x 1000 steps = BASELINE configs[0]) replayed as ONE pd_rollout_actions
+  launch per dwell time (the fixtures hold two; a launch takes one, the envs
+  are independent, so each launch is compared on the envs that used its dwell
+  time).  Si site and elapsed microseconds of every step, final FOV."""
+  from tests.test_oracle import expand_controls
+  fix = np.load(os.path.join(golden_dir, name))
+  controls, dwell = expand_controls(fix)
+  n_steps, n = controls.shape[:2]
+  spec = gh.rate_spec(int(fix['rate_fn']))
+  nat.lib.pd_set_fast_path(1)
+  checked = 0
+  for d in np.unique(dwell):
+    mask = (dwell[:, :, 0] == d).all(axis=0)
+    b = eng.EnvBatch(n, seed=int(fix['seed']))
+    b.reset()
+    np.testing.assert_array_equal(gh.np_(b.si_idx), fix['si0'])
+    si, el = b.rollout(controls[:, :, 0, :], int(d), spec, record=True,
+                       action_mode=nat.ACTION_DIRECT)
+    si, el = gh.np_(si), gh.np_(el)
+    np.testing.assert_array_equal(si[:, mask], fix['si'][mask].T)
+    np.testing.assert_array_equal(el[:, mask], fix['elapsed_us'][mask].T)
+    if 'fov_last' in fix:
+      np.testing.assert_allclose(gh.np_(b.fov)[mask], fix['fov_last'][mask],
+                                 rtol=0, atol=1e-13)
+    checked += int(mask.sum())
+  assert checked == n
