@@ -374,3 +374,44 @@ def test_fast_rollout_vs_reference_golden(eng, nat, golden_dir, name):
                                  rtol=0, atol=1e-13)
     checked += int(mask.sum())
   assert checked == n
+
+
+def test_walk_plan_host_formats(eng, nat):
+  """k_walk_plan in the float32 / packed host formats (IO 1 and 2): a large
+  batch through pd_rollout_actions_host_packed and
+  pd_rollout_actions_host_f32 with k_walk_plan forced for every chunk,
+  against the device-resident rollout through k_walk_fast; every fifth FOV
+  moved off-centre (first-step area test, clip)."""
+  n, t_steps, dwell = 100000, 24, 1500000
+  rng = np.random.default_rng(8)
+  acts = rng.uniform(-1.1, 1.1, size=(t_steps, n, 2)).astype(np.float32)
+  spec = gh.rate_spec(po.RATE_PRIOR)
+
+  def batch():
+    b = eng.EnvBatch(n, seed=21)
+    b.reset()
+    b.fov[::5] += 4.1
+    return b
+
+  _select(nat, 'fast')
+  a = batch()
+  si, el = a.rollout(acts.astype(np.float64), dwell, spec, record=True,
+                     action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+  si, el = gh.np_(si), gh.np_(el)
+  want = {k: gh.np_(v) for k, v in a.state_dict().items() if k in STATE_KEYS}
+  _select(nat, 'plan')
+  b = batch()
+  packed = b.rollout_host_packed(acts, dwell, spec,
+                                 action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+  si_p, el_p = eng.EnvBatch.unpack_rollout(packed, dwell)
+  np.testing.assert_array_equal(si_p.numpy(), si)
+  np.testing.assert_array_equal(el_p.numpy(), el)
+  c = batch()
+  si_h, el_h = c.rollout_host(acts, dwell, spec,
+                              action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+  np.testing.assert_array_equal(si_h.numpy(), si)
+  np.testing.assert_array_equal(el_h.numpy().astype(np.int64), el)
+  for other in (b, c):
+    sd = other.state_dict()
+    for k in STATE_KEYS:
+      np.testing.assert_array_equal(gh.np_(sd[k]), want[k], err_msg=k)
