@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
     for (int i = 0; i < 3; ++i) s.geo.gx[i] = s.geo.gy[i] = 0.f;
     uint32_t env_id = 0, ctrl_count = 0;
     int events = 0, transitions = 0, recentres = 0;
-    uint8_t status = 0;
+    uint8_t status = 0, status_in = 0;
     double2 act_next = make_double2(0.0, 0.0);
     int t = t_first;
     // t * n + env: this step's element of every [T][n] array
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
       const Fov4 fov = load_fov4(a.st.fov, env);
       env_id = a.st.env_offset + static_cast<uint32_t>(env);
       ctrl_count = a.st.ctrl_count[env];
-      status = a.st.status[env];
+      status = status_in = a.st.status[env];
       s = fast_site<RATE>(tab, a.st.si_idx[env], lat.c, lat.s);
       obs.sync(fov, site_position(tab.position(s.si), lat));
       begin_control(act);
@@ -415,10 +415,13 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
         a.st.ctrl_count[env] = ctrl_count;
         atomicAdd(reinterpret_cast<unsigned long long*>(a.st.n_events + env),
                   static_cast<unsigned long long>(events));
-        atomicAdd(
-            reinterpret_cast<unsigned long long*>(a.st.n_transitions + env),
-            static_cast<unsigned long long>(transitions));
-        a.st.status[env] = status;
+        // (one-step launches: 9 envs in 10 do not hop, and the status byte
+        // changes for a handful of envs per 10^9 -- skip those lines)
+        if (transitions > 0)
+          atomicAdd(
+              reinterpret_cast<unsigned long long*>(a.st.n_transitions + env),
+              static_cast<unsigned long long>(transitions));
+        if (status != status_in) a.st.status[env] = status;
         active = false;
       }
     }
