@@ -669,6 +669,7 @@ struct StepArgs {
   int2* defer_list;
   uint32_t* defer_count;
   float fast_dwell_s, fast_margin;  // FastTimes of dwell_us_scalar (pd_fast.cuh)
+  int32_t fast_episode;       // k_walk<EPISODE>: guarded float32 iterations
   int32_t prepass;            // 1: float32 pre-pass (certainly_no_hop) enabled
   int32_t walk_min_ready;     // k_walk: lanes with an exact iteration pending
   int32_t walk_max_reps;      //   that end the bookkeeping repeats / their cap

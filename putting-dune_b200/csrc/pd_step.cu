@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "pd_episode.cuh"
+#include "pd_fast.cuh"
 
 #ifndef PD_STEP_MIN_BLOCKS
 #define PD_STEP_MIN_BLOCKS 4
@@ -1062,6 +1063,26 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
   double2 goal = make_double2(0.0, 0.0);
   long long env_time = 0;
   int actions = 0;
+  // episode mode on the prior / simple rates: the guarded float32 iteration
+  // of pd_fast.cuh.  A control runs in float32 (site, geometry and beam
+  // offset in `fs`, `bxf`, `byf`, its clock as the interval [e_lo, e_hi])
+  // until it ends or float32 cannot settle an iteration; then the control is
+  // taken again from its start (`si0` ...) by the exact code below.
+  constexpr bool kFastRates = RATE == PD_RATE_SIMPLE || RATE == PD_RATE_PRIOR;
+  const bool fast_on = EPISODE && kFastRates && a.fast_episode != 0 &&
+                       a.ep.dwell_us > 0 &&
+                       a.ep.dwell_us < 3000LL * 1000000LL && log.capacity == 0;
+  const FastTimes tm = fast_times(static_cast<long long>(a.ep.dwell_us));
+  FastSite fs;
+  fs.si = -1;
+  fs.cls = 2;
+  fs.nb[0] = fs.nb[1] = fs.nb[2] = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) fs.geo.gx[i] = fs.geo.gy[i] = 0.f;
+  float bxf = 0.f, byf = 0.f, e_lo = 0.f, e_hi = 0.f;
+  bool exact_ctl = true;
+  int si0 = 0, tr0 = 0, ev0 = 0;
+  double2 psi0 = make_double2(0.0, 0.0);
 
   while (true) {
     // Bookkeeping repeats until enough lanes hold an iteration that needs the
@@ -1123,6 +1144,18 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
                 dwell = a.ep.dwell_us;
                 elapsed = 0;
                 it = 0;
+                if constexpr (kFastRates) {
+                  exact_ctl = !fast_on;
+                  e_lo = e_hi = 0.f;
+                  si0 = r.si;
+                  psi0 = r.psi;
+                  tr0 = r.transitions;
+                  ev0 = r.events;
+                  const float k = fast_offset_scale<kFastRates ? RATE
+                                                               : PD_RATE_SIMPLE>();
+                  bxf = static_cast<float>(beam.x - r.psi.x) * k;
+                  byf = static_cast<float>(beam.y - r.psi.y) * k;
+                }
                 if (dwell > 0) {
                   ready = true;
                   checked = true;  // the greedy beam sits on a neighbour: hops
@@ -1333,6 +1366,7 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
             goal = reinterpret_cast<const double2*>(a.goal_xy)[env];
             env_time = a.ep.image_duration_us;  // eval_lib.py:121
             actions = 0;
+            fs.si = -1;  // (its geometry is the previous env's)
           }
           t = 0;
           c = 0;
@@ -1358,7 +1392,48 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     }
     if (!__any_sync(0xffffffffu, env >= 0)) break;
 
-    if (ready) {
+    bool settled_fast = false;
+    if constexpr (EPISODE && kFastRates) {
+      if (ready && !exact_ctl) {
+        // ---- one KMC iteration in float32 (pd_fast.cuh) ----
+        settled_fast = true;
+        if (fs.si != r.si) fs = fast_site<RATE>(tab, r.si, r.lat.c, r.lat.s);
+        const uint4 w = philox4x32_10k(r.env_id, r.ctrl_count, it,
+                                       PD_STREAM_KMC, a.keys);
+        int slot = 0;
+        float t_lo = 0.f, t_hi = 0.f;
+        const int kind = fast_event<RATE>(fs.geo, bxf, byf, w.x, w.z, e_lo,
+                                          e_hi, tm, &slot, &t_lo, &t_hi);
+        if (kind == FAST_NO_HOP) {
+          r.events += 1;
+          r.ctrl_count += 1;
+          ++c;
+          ready = false;
+        } else if (kind == FAST_HOP) {
+          float ox, oy;
+          auto rotation = [&]() { return make_double2(r.lat.c, r.lat.s); };
+          fast_hop<RATE>(tab, slot, rotation, &fs, &bxf, &byf, &ox, &oy);
+          r.si = fs.si;
+          r.psi = site_position(tab.position(r.si), r.lat);
+          r.transitions += 1;
+          r.events += 1;
+          ++it;
+          fast_advance(&e_lo, &e_hi, t_lo, t_hi);
+        } else {
+          // float32 cannot settle it: the control again, from its start, by
+          // the exact code (this trip)
+          r.si = si0;
+          r.psi = psi0;
+          r.transitions = tr0;
+          r.events = ev0;
+          it = 0;
+          elapsed = 0;
+          exact_ctl = true;
+          settled_fast = false;
+        }
+      }
+    }
+    if (ready && !settled_fast) {
       // ---- one KMC iteration (graphene.py:658-694) ----
       int nb[3];
       tab.neighbors(r.si, nb);
@@ -1817,6 +1892,8 @@ static int dispatch_step(const pd_rate_config* rc, StepArgs& a, bool rollout,
 template <int RATE>
 static int launch_episode_walk(const StepArgs& a_in, cudaStream_t stream) {
   StepArgs a = a_in;
+  a.keys = philox_keys_host(a.st.seed);
+  a.fast_episode = fast_enabled() ? 1 : 0;
   a.walk_min_ready = 33;  // episodes: two bookkeeping passes per trip
   a.walk_max_reps = 2;
   a.walk_controls_per_pass = 1 << 30;
