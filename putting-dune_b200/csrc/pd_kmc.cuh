@@ -674,6 +674,7 @@ struct StepArgs {
   int32_t walk_min_ready;     // k_walk: lanes with an exact iteration pending
   int32_t walk_max_reps;      //   that end the bookkeeping repeats / their cap
   int32_t walk_controls_per_pass;  // controls a lane may settle per pass
+  int32_t walk_lockstep;      // episodes: bookkeeping only between controls
   double max_distance;        // RelativeToSilicon adapter, angstroms
   pd_step_out out;
   int32_t* si_idx_out;        // rollout [T][n]

@@ -1091,6 +1091,14 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
     // controls are consumed here as well), or until nothing can change.
 #pragma unroll 1
     for (int rep = 0;; ++rep) {
+      // Episodes: the controller (float64 round trips, atan2 / cos / sin) is
+      // by far the longest block of a lane's cycle, so the lanes of a warp
+      // take it together: no bookkeeping while any lane is inside a control.
+      if constexpr (EPISODE) {
+        if (a.walk_lockstep != 0 &&
+            __any_sync(0xffffffffu, env >= 0 && ready))
+          break;
+      }
       // ---- next control / end of step / end of environment ----
       // A lane leaves this block with an iteration that needs the float64
       // chain pending (ready && checked) or without an env.  Controls whose
@@ -1894,6 +1902,8 @@ static int launch_episode_walk(const StepArgs& a_in, cudaStream_t stream) {
   StepArgs a = a_in;
   a.keys = philox_keys_host(a.st.seed);
   a.fast_episode = fast_enabled() ? 1 : 0;
+  static const int lockstep = env_int("PD_EPISODE_LOCKSTEP", 1);
+  a.walk_lockstep = lockstep;
   a.walk_min_ready = 33;  // episodes: two bookkeeping passes per trip
   a.walk_max_reps = 2;
   a.walk_controls_per_pass = 1 << 30;
