@@ -376,13 +376,15 @@ def test_fast_rollout_vs_reference_golden(eng, nat, golden_dir, name):
   assert checked == n
 
 
-def test_walk_plan_host_formats(eng, nat):
-  """k_walk_plan in the float32 / packed host formats (IO 1 and 2): a large
-  batch through pd_rollout_actions_host_packed and
-  pd_rollout_actions_host_f32 with k_walk_plan forced for every chunk,
-  against the device-resident rollout through k_walk_fast; every fifth FOV
-  moved off-centre (first-step area test, clip)."""
-  n, t_steps, dwell = 100000, 24, 1500000
+@pytest.mark.parametrize('n,t_steps', [(100000, 24), (4096, 96)])
+def test_plan_kernels_host_formats(eng, nat, n, t_steps):
+  """The plan kernels in the float32 / packed host formats (IO 1 and 2):
+  pd_rollout_actions_host_packed and pd_rollout_actions_host_f32 with
+  k_walk_plan (large batch) / k_rollout_plan (small batch) selected for every
+  chunk, against the device-resident rollout through k_walk_fast /
+  k_rollout_fast; every fifth FOV moved off-centre (first-step area test,
+  clip)."""
+  dwell = 1500000
   rng = np.random.default_rng(8)
   acts = rng.uniform(-1.1, 1.1, size=(t_steps, n, 2)).astype(np.float32)
   spec = gh.rate_spec(po.RATE_PRIOR)
