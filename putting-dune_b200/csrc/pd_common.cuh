@@ -83,6 +83,18 @@ __device__ __forceinline__ double draw_linear(uint64_t seed, uint32_t env,
 // graphene.py:545-557: (base + off) @ [[c, -s], [s, c]]
 //   x' = bx*c + by*s ; y' = by*c - bx*s  (each product rounded: no FMA).
 // ---------------------------------------------------------------------------
+// np.clip: a NaN stays a NaN (fmin / fmax would drop it), so that a NaN
+// action reaches the rate function and is flagged there as in the reference
+// (graphene.py:258).
+__device__ __forceinline__ double clip_nan(double x, double lo, double hi) {
+  const double c = fmin(fmax(x, lo), hi);
+  return x == x ? c : x;
+}
+__device__ __forceinline__ float clip_nanf(float x, float lo, float hi) {
+  const float c = fminf(fmaxf(x, lo), hi);
+  return x == x ? c : x;
+}
+
 struct Lattice4 {
   double ox, oy, c, s;
 };

@@ -33,11 +33,11 @@ __global__ void __launch_bounds__(kEnvThreads)
     double2 ctl;
     long long dwell = fixed_dwell_us;
     if (cfg.adapter == PD_ADAPTER_DIRECT) {
-      ctl = make_double2(fmin(fmax(a[0], 0.0), 1.0), fmin(fmax(a[1], 0.0), 1.0));
+      ctl = make_double2(clip_nan(a[0], 0.0, 1.0), clip_nan(a[1], 0.0, 1.0));
     } else if (cfg.adapter == PD_ADAPTER_DELTA) {
       double2 b = reinterpret_cast<double2*>(buf.beam_pos)[e];
-      b.x = fmin(fmax(__dadd_rn(b.x, a[0]), 0.0), 1.0);
-      b.y = fmin(fmax(__dadd_rn(b.y, a[1]), 0.0), 1.0);
+      b.x = clip_nan(__dadd_rn(b.x, a[0]), 0.0, 1.0);
+      b.y = clip_nan(__dadd_rn(b.y, a[1]), 0.0, 1.0);
       reinterpret_cast<double2*>(buf.beam_pos)[e] = b;
       ctl = b;
     } else {
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kEnvThreads)
         const double2 si_m = round_trip(fov, psi);
         ctl = observe(fov, make_double2(__dadd_rn(si_m.x, a[0]),
                                         __dadd_rn(si_m.y, a[1])));
-        ctl.x = fmin(fmax(ctl.x, 0.0), 1.0);
-        ctl.y = fmin(fmax(ctl.y, 0.0), 1.0);
+        ctl.x = clip_nan(ctl.x, 0.0, 1.0);
+        ctl.y = clip_nan(ctl.y, 0.0, 1.0);
       }
       if (cfg.action_dim == 3) {  // action_adapters.py:193-199
         const double frac = fmin(fmax(a[2], 0.0), 1.0);

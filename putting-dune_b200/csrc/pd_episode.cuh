@@ -34,13 +34,13 @@ __device__ __forceinline__ double2 relative_to_silicon(const Fov4& fov,
                                                        const double2 action,
                                                        double max_distance) {
   const double2 q = observe(fov, psi);
-  const double ax = fmin(fmax(action.x, -1.0), 1.0);
-  const double ay = fmin(fmax(action.y, -1.0), 1.0);
+  const double ax = clip_nan(action.x, -1.0, 1.0);
+  const double ay = clip_nan(action.y, -1.0, 1.0);
   const double rx = __ddiv_rn(max_distance, __dsub_rn(fov.urx, fov.llx));
   const double ry = __ddiv_rn(max_distance, __dsub_rn(fov.ury, fov.lly));
   return make_double2(
-      fmin(fmax(__dadd_rn(q.x, __dmul_rn(ax, rx)), 0.0), 1.0),
-      fmin(fmax(__dadd_rn(q.y, __dmul_rn(ay, ry)), 0.0), 1.0));
+      clip_nan(__dadd_rn(q.x, __dmul_rn(ax, rx)), 0.0, 1.0),
+      clip_nan(__dadd_rn(q.y, __dmul_rn(ay, ry)), 0.0, 1.0));
 }
 
 // Features -> GreedyAgent.step (float32) -> adapter: the control position in

@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(kStepThreads)
           q_stale = false;
         }
         // action_adapters.py:163-188
-        const double ax = fmin(fmax(ctl.x, -1.0), 1.0);
-        const double ay = fmin(fmax(ctl.y, -1.0), 1.0);
-        pos.x = fmin(fmax(__dadd_rn(q.x, __dmul_rn(ax, rx)), 0.0), 1.0);
-        pos.y = fmin(fmax(__dadd_rn(q.y, __dmul_rn(ay, ry)), 0.0), 1.0);
+        const double ax = clip_nan(ctl.x, -1.0, 1.0);
+        const double ay = clip_nan(ctl.y, -1.0, 1.0);
+        pos.x = clip_nan(__dadd_rn(q.x, __dmul_rn(ax, rx)), 0.0, 1.0);
+        pos.y = clip_nan(__dadd_rn(q.y, __dmul_rn(ay, ry)), 0.0, 1.0);
       }
       const double2 beam = microscope_to_material(fov, pos.x, pos.y);
       const int hops_before = r.transitions;
@@ -293,10 +293,10 @@ __global__ void __launch_bounds__(kStepThreads)
         const double2 c = ctl[static_cast<int64_t>(step) * n + e];
         double2 pos = c;
         if (relative) {
-          const double ax = fmin(fmax(c.x, -1.0), 1.0);
-          const double ay = fmin(fmax(c.y, -1.0), 1.0);
-          pos.x = fmin(fmax(__dadd_rn(q_n.x, __dmul_rn(ax, rx_n)), 0.0), 1.0);
-          pos.y = fmin(fmax(__dadd_rn(q_n.y, __dmul_rn(ay, ry_n)), 0.0), 1.0);
+          const double ax = clip_nan(c.x, -1.0, 1.0);
+          const double ay = clip_nan(c.y, -1.0, 1.0);
+          pos.x = clip_nan(__dadd_rn(q_n.x, __dmul_rn(ax, rx_n)), 0.0, 1.0);
+          pos.y = clip_nan(__dadd_rn(q_n.y, __dmul_rn(ay, ry_n)), 0.0, 1.0);
         }
         beam = microscope_to_material(fov_n, pos.x, pos.y);
       }
@@ -790,10 +790,10 @@ __global__ void __launch_bounds__(kStepThreads)
               py = static_cast<float>(c.y);
             }
             if (relative) {
-              px = fminf(fmaxf(px, -1.f), 1.f);
-              py = fminf(fmaxf(py, -1.f), 1.f);
-              px = fminf(fmaxf(qfx + px * __fdividef(md, wfx), 0.f), 1.f);
-              py = fminf(fmaxf(qfy + py * __fdividef(md, wfy), 0.f), 1.f);
+              px = clip_nanf(px, -1.f, 1.f);
+              py = clip_nanf(py, -1.f, 1.f);
+              px = clip_nanf(qfx + px * __fdividef(md, wfx), 0.f, 1.f);
+              py = clip_nanf(qfy + py * __fdividef(md, wfy), 0.f, 1.f);
             }
             bx = (px - qfx) * wfx;
             by = (py - qfy) * wfy;
@@ -888,10 +888,10 @@ __global__ void __launch_bounds__(kStepThreads)
             const double qy = shfl_double(gmask, val, gbase + 1);
             const double rx = shfl_double(gmask, val, gbase + 2);
             const double ry = shfl_double(gmask, val, gbase + 3);
-            const double ax = fmin(fmax(c.x, -1.0), 1.0);
-            const double ay = fmin(fmax(c.y, -1.0), 1.0);
-            pos.x = fmin(fmax(__dadd_rn(qx, __dmul_rn(ax, rx)), 0.0), 1.0);
-            pos.y = fmin(fmax(__dadd_rn(qy, __dmul_rn(ay, ry)), 0.0), 1.0);
+            const double ax = clip_nan(c.x, -1.0, 1.0);
+            const double ay = clip_nan(c.y, -1.0, 1.0);
+            pos.x = clip_nan(__dadd_rn(qx, __dmul_rn(ax, rx)), 0.0, 1.0);
+            pos.y = clip_nan(__dadd_rn(qy, __dmul_rn(ay, ry)), 0.0, 1.0);
           } else {
             pos = relative_to_silicon(fov, psi, c, a.max_distance);
           }
@@ -1308,10 +1308,10 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
                 if (rollout &&
                     a.action_mode == PD_ACTION_RELATIVE_TO_SILICON) {
                   const float md = static_cast<float>(a.max_distance);
-                  px = fminf(fmaxf(px, -1.f), 1.f);
-                  py = fminf(fmaxf(py, -1.f), 1.f);
-                  px = fminf(fmaxf(qfx + px * __fdividef(md, wx), 0.f), 1.f);
-                  py = fminf(fmaxf(qfy + py * __fdividef(md, wy), 0.f), 1.f);
+                  px = clip_nanf(px, -1.f, 1.f);
+                  py = clip_nanf(py, -1.f, 1.f);
+                  px = clip_nanf(qfx + px * __fdividef(md, wx), 0.f, 1.f);
+                  py = clip_nanf(qfy + py * __fdividef(md, wy), 0.f, 1.f);
                 }
                 bx = (px - qfx) * wx;
                 by = (py - qfy) * wy;

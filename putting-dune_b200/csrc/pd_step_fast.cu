@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
       si0 = s.si;
       if (REL) {
         // action_adapters.py:163-188 without the clip to the frame
-        const float ax = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f);
-        const float ay = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f);
+        const float ax = clip_nanf(static_cast<float>(act.x), -1.f, 1.f);
+        const float ay = clip_nanf(static_cast<float>(act.y), -1.f, 1.f);
         bx = ax * md_s;
         by = ay * md_s;
         usable = obs.clip_free(md_f);
@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(kStepThreads, PD_STEP_MIN_BLOCKS)
         if (!(j == 0 && cont)) {
           const double2 c = ctl.load(step, e);
           if (relative) {
-            const float ax = fminf(fmaxf(static_cast<float>(c.x), -1.f), 1.f);
-            const float ay = fminf(fmaxf(static_cast<float>(c.y), -1.f), 1.f);
+            const float ax = clip_nanf(static_cast<float>(c.x), -1.f, 1.f);
+            const float ay = clip_nanf(static_cast<float>(c.y), -1.f, 1.f);
             bx = ax * md_s;
             by = ay * md_s;
             usable = j == 0 ? clip_free : clip_free_n;
@@ -752,8 +752,8 @@ __device__ __noinline__ unsigned site_busy_mask(const StepArgs& a,
     const float md_s = static_cast<float>(
         a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
     const double2 act = ActionStream<IO>(a).load(t_first + lane, env);
-    const float bx = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
-    const float by = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+    const float bx = clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
+    const float by = clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
     const uint4 w = philox4x32_10k(
         a.st.env_offset + static_cast<uint32_t>(env),
         ctrl_first + static_cast<uint32_t>(lane), 0u, PD_STREAM_KMC, a.keys);
@@ -783,8 +783,8 @@ __device__ __noinline__ void serial_control(const StepArgs& a, const Tables tab,
   const float md_s = static_cast<float>(
       a.max_distance * (RATE == PD_RATE_PRIOR ? 1.0 / kBond : 1.0));
   const double2 act = ActionStream<IO>(a).load(t, env);
-  float bx = fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
-  float by = fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+  float bx = clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
+  float by = clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
   const uint32_t env_id = a.st.env_offset + static_cast<uint32_t>(env);
   float e_lo = 0.f, e_hi = 0.f, oxs = 0.f, oys = 0.f;
   int hops = 0;
@@ -980,9 +980,9 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
       const int t = t0 + k;
       const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
       const float bx =
-          fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+          clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
       const float by =
-          fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+          clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
       FastGeo g;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -1022,9 +1022,9 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
         const int t = t0 + k;
         const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
         const float bx =
-            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
         const float by =
-            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
         FastGeo g;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -1504,9 +1504,9 @@ __global__ void __launch_bounds__(kWalkPlanThreads, PD_WALK_PLAN_BLOCKS)
       for (int k = 0; k < len_c; ++k, at += n, ++ctrl) {
         const double2 act = ctl.load(at);
         const float bx =
-            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
         const float by =
-            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
         const uint4 w = philox4x32_10k(env_id0 + static_cast<uint32_t>(tid),
                                        ctrl, 0u, PD_STREAM_KMC, a.keys);
         bool quiet0, quiet1;
@@ -1557,9 +1557,9 @@ __global__ void __launch_bounds__(kWalkPlanThreads, PD_WALK_PLAN_BLOCKS)
         const int t = t0 + k;
         const double2 act = ctl.load(static_cast<int64_t>(t) * n + env0 + el);
         const float bx =
-            fminf(fmaxf(static_cast<float>(act.x), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.x), -1.f, 1.f) * md_s;
         const float by =
-            fminf(fmaxf(static_cast<float>(act.y), -1.f), 1.f) * md_s;
+            clip_nanf(static_cast<float>(act.y), -1.f, 1.f) * md_s;
         FastGeo g;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {

@@ -82,6 +82,14 @@ def test_fast_rollout_equals_float64_kernels(eng, nat, n):
   direct[1, 5:10] = 1e9
   direct[2, 10:15] = np.inf
   far = 0.5 + rng.uniform(-0.6, 0.6, size=(t_steps, n, 2))  # beam off the Si
+  # non-finite actions under the relative adapter: np.clip keeps a NaN, so the
+  # control is NaN and the rate function flags it (graphene.py:258); +-inf
+  # clip to +-1
+  acts_nan = acts.copy()
+  acts_nan[0, :3] = np.nan
+  acts_nan[min(3, t_steps - 1), 3:6, 0] = np.nan
+  acts_nan[1, 6:9] = np.inf
+  acts_nan[2, 9:12] = -np.inf
   cases = [
       (po.RATE_PRIOR, 1500000, acts, nat.ACTION_RELATIVE_TO_SILICON, True),
       (po.RATE_PRIOR, 1500000, acts, nat.ACTION_RELATIVE_TO_SILICON, False),
@@ -90,6 +98,8 @@ def test_fast_rollout_equals_float64_kernels(eng, nat, n):
       (po.RATE_PRIOR, 30000000, direct, nat.ACTION_DIRECT, False),
       (po.RATE_PRIOR, 1500000, far, nat.ACTION_DIRECT, False),
       (po.RATE_SIMPLE, 3, acts, nat.ACTION_RELATIVE_TO_SILICON, False),
+      (po.RATE_PRIOR, 1500000, acts_nan, nat.ACTION_RELATIVE_TO_SILICON,
+       False),
   ]
   for rate_fn, dwell, ctl, mode, shift in cases:
     spec = gh.rate_spec(rate_fn)
@@ -105,6 +115,10 @@ def test_fast_rollout_equals_float64_kernels(eng, nat, n):
                                       err_msg=f'{kernels} {k}')
     if dwell > 1000:
       assert st_b['n_transitions'].sum() > 0
+    if ctl is acts_nan:
+      # PD_ENV_BAD_RATE (1) on the envs that saw a NaN action, nowhere else
+      bad = (st_b['status'] & 1) != 0
+      assert bad[:6].all() and not bad[6:].any()
 
 
 def test_fast_rollout_single_step_and_edge_sites(eng, nat):
