@@ -1413,7 +1413,7 @@ __global__ void __launch_bounds__(kPlanThreads, 2)
 // ---------------------------------------------------------------------------
 constexpr int kWalkPlanThreads = 256;
 constexpr int kWalkPlanChunk = 16;
-constexpr int kWalkPlanQueue = 2048;
+constexpr int kWalkPlanQueue = 4096;  // (simple rate, 5 s: ~2300 per chunk)
 
 #ifndef PD_WALK_PLAN_BLOCKS  // resident CTAs per SM (registers: 65536 / 256 / this)
 #define PD_WALK_PLAN_BLOCKS 4
