@@ -668,6 +668,7 @@ struct StepArgs {
   // envs that left the plan, and how many there are
   int2* defer_list;
   uint32_t* defer_count;
+  uint32_t* list_hint;        // mapped host word: the list's length, or null
   float fast_dwell_s, fast_margin;  // FastTimes of dwell_us_scalar (pd_fast.cuh)
   int32_t fast_episode;       // k_walk<EPISODE>: guarded float32 iterations
   int32_t prepass;            // 1: float32 pre-pass (certainly_no_hop) enabled

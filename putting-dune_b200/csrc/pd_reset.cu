@@ -16,6 +16,8 @@
 
 namespace pd {
 
+void forget_plan_hint(const void* key);  // pd_step_fast.cu
+
 constexpr int kResetThreads = 128;
 
 // imaging.py:42-54 sample_image_parameters (mode 0) and :57-72
@@ -150,5 +152,6 @@ extern "C" int pd_reset(const pd_lattice* lat, const pd_state* st,
   pd::k_reset<<<grid, pd::kResetThreads, 0,
                 static_cast<cudaStream_t>(stream)>>>(*lat, *st, mask);
   PD_CUDA_OK(cudaGetLastError());
+  pd::forget_plan_hint(st->si_idx);  // pd_step_fast.cu: kernel choice hint
   return PD_OK;
 }

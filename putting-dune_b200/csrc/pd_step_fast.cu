@@ -14,6 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "pd_episode.cuh"
 #include "pd_fast.cuh"
 
@@ -258,6 +261,10 @@ __global__ void __launch_bounds__(kStepThreads, PD_FAST_MIN_BLOCKS)
   const ActionStream<IO> ctl(a);
   const int lane = threadIdx.x & 31;
   const int64_t n_items = LIST ? static_cast<int64_t>(*a.defer_count) : n;
+  // (the host reads the list's length before its next launch on this batch:
+  // a mapped host word, written once)
+  if (LIST && a.list_hint && blockIdx.x == 0 && threadIdx.x == 0)
+    *a.list_hint = static_cast<uint32_t>(n_items);
   const int64_t n_batches = (n_items + 31) / 32;
   const int64_t warps_total =
       static_cast<int64_t>(gridDim.x) * (kStepThreads / 32);
@@ -1731,12 +1738,78 @@ extern "C" int pd_debug_plan_clocks(unsigned long long* out) {
 }
 #endif
 
+// How many envs the last k_walk_plan launch on a batch handed over.  A batch
+// that has run for thousands of steps without a reset has 30-50 % of its Si
+// atoms on the sheet's edge sites (the boundary is sticky under the
+// relative_random workload), half of the batch goes through the list, and
+// k_walk_fast alone is the faster kernel (measured at 1 Mi envs: 0.32 against
+// 0.37 ms per 8 steps, 2.1 against 2.8 ms per 64; within an episode's length
+// of a reset it is 0.23 against 0.20 and 1.8 against 1.1).  So the list kernel
+// leaves the length of its list in a mapped host word, keyed by the batch's
+// si_idx array, and launch_fast reads it before the next launch: above
+// kListFraction of the batch it takes k_walk_fast, and tries the plan again
+// every kProbeEvery-th launch; pd_reset forgets the hint.
+struct PlanHint {
+  const void* key;
+  volatile uint32_t* count;  // cudaHostAlloc, mapped
+  uint32_t launches;
+};
+static std::mutex& plan_hint_mutex() {
+  static std::mutex m;
+  return m;
+}
+static std::vector<PlanHint>& plan_hints() {
+  static std::vector<PlanHint> v;
+  return v;
+}
+constexpr double kListFraction = 0.15;
+constexpr uint32_t kProbeEvery = 16;
+
+static PlanHint* plan_hint_for(const void* key, bool create) {
+  auto& v = plan_hints();
+  for (auto& h : v)
+    if (h.key == key) return &h;
+  if (!create) return nullptr;
+  if (v.size() >= 64) v.erase(v.begin());  // (the words are never freed)
+  void* word = nullptr;
+  if (cudaHostAlloc(&word, sizeof(uint32_t),
+                    cudaHostAllocMapped | cudaHostAllocPortable) !=
+      cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  *static_cast<volatile uint32_t*>(word) = 0u;
+  v.push_back(PlanHint{key, static_cast<volatile uint32_t*>(word), 0u});
+  return &v.back();
+}
+
+// pd_reset: the batch starts afresh.
+void forget_plan_hint(const void* key) {
+  std::lock_guard<std::mutex> lock(plan_hint_mutex());
+  if (PlanHint* h = plan_hint_for(key, false)) {
+    *h->count = 0u;
+    h->launches = 0u;
+  }
+}
+
 // Large batches under the relative adapter: k_walk_plan, then k_walk_fast over
 // the list of envs (and first steps) it handed over.
 template <int RATE, int IO>
 static int launch_walk_plan(const StepArgs& a_in, cudaStream_t stream) {
   StepArgs a = a_in;
   const int64_t n = a.st.n_envs;
+  a.list_hint = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(plan_hint_mutex());
+    if (PlanHint* h = plan_hint_for(a.st.si_idx, true)) {
+      void* dev_word = nullptr;
+      if (cudaHostGetDevicePointer(&dev_word, const_cast<uint32_t*>(h->count),
+                                   0) == cudaSuccess)
+        a.list_hint = static_cast<uint32_t*>(dev_word);
+      else
+        (void)cudaGetLastError();
+    }
+  }
   // stream-ordered scratch from the device's default pool, which is told once
   // to keep what it has been given (no trip to the driver per call)
   static thread_local int pool_ready_for = -1;
@@ -1761,10 +1834,11 @@ static int launch_walk_plan(const StepArgs& a_in, cudaStream_t stream) {
     const int64_t grid_p = (n + kWalkPlanThreads - 1) / kWalkPlanThreads;
     k_walk_plan<RATE, IO>
         <<<static_cast<unsigned>(grid_p), kWalkPlanThreads, 0, stream>>>(a);
-    // the list is short (the envs near the sheet's edge, a few per 10^4
-    // UNSURE controls): one CTA per SM is plenty, warps without work exit
+    // the list: a few envs per 10^4 in a fresh batch (UNSURE controls,
+    // ambiguous area tests), the envs in the sheet's edge region later on; a
+    // full wave, warps without work exit
     k_walk_fast<RATE, IO, true, true>
-        <<<sm_count() * 2, kStepThreads, 0, stream>>>(a);
+        <<<sm_count() * PD_FAST_MIN_BLOCKS, kStepThreads, 0, stream>>>(a);
     err = cudaGetLastError();
   }
   cudaFreeAsync(scratch, stream);
@@ -1795,12 +1869,22 @@ int launch_fast(const StepArgs& a_in, bool walk, int grid, cudaStream_t stream,
   // (measured: k_walk_plan pays from three waves of its CTAs and eight steps
   // per launch on; below that the fixed cost of the second launch and the
   // last, partly filled wave eat the gain)
-  // plan_mode bit 2: whatever the sizes (the parity tests)
-  if (walk && rel &&
-      ((plan_mode & 4) ||
-       ((plan_mode & 2) && a.n_steps >= 8 &&
-        a.st.n_envs >=
-            3LL * sm_count() * PD_WALK_PLAN_BLOCKS * kWalkPlanThreads)))
+  // plan_mode bit 2: whatever the sizes and the hint (the parity tests)
+  bool walk_plan = walk && rel && (plan_mode & 4);
+  if (walk && rel && !walk_plan && (plan_mode & 2) && a.n_steps >= 8 &&
+      a.st.n_envs >=
+          3LL * sm_count() * PD_WALK_PLAN_BLOCKS * kWalkPlanThreads) {
+    walk_plan = true;
+    std::lock_guard<std::mutex> lock(plan_hint_mutex());
+    if (PlanHint* h = plan_hint_for(a.st.si_idx, false)) {
+      h->launches += 1;
+      if (static_cast<double>(*h->count) >
+              kListFraction * static_cast<double>(a.st.n_envs) &&
+          h->launches % kProbeEvery != 0)
+        walk_plan = false;
+    }
+  }
+  if (walk_plan)
     return io == 1   ? launch_walk_plan<RATE, 1>(a, stream)
            : io == 2 ? launch_walk_plan<RATE, 2>(a, stream)
                      : launch_walk_plan<RATE, 0>(a, stream);
