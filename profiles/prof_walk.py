@@ -55,7 +55,8 @@ def launch(i):
       P(d_el) if d_el is not None else None, stream))
 
 
-for i in range(3):
+# (WARM=0 EACH=1: every launch since the reset, timed and printed)
+for i in range(int(os.environ.get('WARM', '3'))):
   launch(i)
 torch.cuda.synchronize()
 ms = []
@@ -68,6 +69,8 @@ for i in range(reps):
   e.record()
   torch.cuda.synchronize()
   ms.append(s.elapsed_time(e))
+if os.environ.get('EACH') == '1':
+  print('ms per launch:', ' '.join('%.4f' % v for v in ms))
 m = float(np.median(ms))
 ev = float(b.n_events.sum().item()) / float(b.ctrl_count.sum().item())
 print('n=%d steps=%d rate=%s fast=%s plan=%s outputs=%s: %.4f ms  '
