@@ -431,3 +431,48 @@ def test_plan_kernels_host_formats(eng, nat, n, t_steps):
     sd = other.state_dict()
     for k in STATE_KEYS:
       np.testing.assert_array_equal(gh.np_(sd[k]), want[k], err_msg=k)
+
+
+@pytest.mark.parametrize('kernels', ['fast', 'plan'])
+@pytest.mark.parametrize('rate_fn', [po.RATE_PRIOR, po.RATE_SIMPLE])
+def test_sheet_edge_sites_vs_oracle(eng, nat, rate_fn, kernels):
+  """Every Si parked on a sheet-edge site (the three nearest sites are not
+  the three bonded ones; where the Si atoms of a long rollout end up),
+  FOV centred on it, 48 relative_random steps against the oracle: Si site and
+  elapsed microseconds of every step, counters, final FOV."""
+  n, t_steps, seed = 2048, 48, 9
+  st = po.make_state(n, seed)
+  po.reset(st)
+  nbr = po.neighbor_table(50)
+  base = po.base_lattice(50)
+  d = np.linalg.norm(base[nbr] - base[:, None, :], axis=2)
+  edge = np.nonzero((d > po.BOND * 1.01).any(axis=1))[0]
+  assert 100 < edge.size < 200
+  st.si_idx[:] = edge[np.arange(n) % edge.size]
+  xy = po.site_positions(st, st.si_idx, np.arange(n))
+  half = st.fov_scale[:, None] / 2
+  st.fov[:] = np.concatenate([xy - half, xy + half], axis=1)
+  rng = np.random.default_rng(4)
+  acts = rng.uniform(-1.0, 1.0, size=(t_steps, n, 2))
+  _select(nat, kernels)
+  b = gh.batch_from_oracle(st)
+  si, el = b.rollout(acts, 1500000, gh.rate_spec(rate_fn), record=True,
+                     action_mode=nat.ACTION_RELATIVE_TO_SILICON,
+                     max_distance_angstroms=1.42)
+  si, el = gh.np_(si), gh.np_(el)
+  on_edge = 0
+  for t in range(t_steps):
+    ctl = oe.relative_to_silicon_controls(st, acts[t])[:, None, :]
+    want = po.step_and_image(st, ctl, 1500000, rate_fn=rate_fn)
+    np.testing.assert_array_equal(si[t], st.si_idx, err_msg=f'step {t}')
+    np.testing.assert_array_equal(el[t], want['elapsed_us'],
+                                  err_msg=f'step {t}')
+    on_edge += int(np.isin(st.si_idx, edge).sum())
+  np.testing.assert_array_equal(gh.np_(b.n_transitions), st.n_transitions)
+  np.testing.assert_array_equal(gh.np_(b.n_events), st.n_events)
+  np.testing.assert_allclose(gh.np_(b.fov), st.fov, rtol=0, atol=1e-13)
+  assert st.n_transitions.sum() > 5000
+  # (a good part of the env-steps stays on edge sites)
+  print(f'rate {rate_fn}: {on_edge / (n * t_steps):.2f} of the env-steps on '
+        f'edge sites, {int(st.n_transitions.sum())} transitions')
+  assert on_edge > 0.1 * n * t_steps
