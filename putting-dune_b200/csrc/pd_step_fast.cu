@@ -5,6 +5,15 @@
 // results are those of k_rollout / k_walk (pd_step.cu) bit for bit
 // (tests/test_gpu_fast.py) at ~1/4 of the instructions.
 //
+//   k_rollout_fast   small batches: 16 lanes per env look ahead over the steps
+//   k_walk_fast      large batches: a lane per env, one iteration per trip;
+//                    <LIST>: the envs (and first steps) k_walk_plan hands over
+//   k_walk_plan      large batches under the relative adapter: every (env,
+//                    step, bulk site class) evaluated densely first, then a
+//                    walk through tables (the default within an episode's
+//                    length of a reset, see launch_fast)
+//   k_rollout_plan   the same plan for small batches (opt-in: slower there)
+//
 //   graphene.py:646-694   PristineSingleDopedGraphene.apply_control
 //   simulator.py:107-182  PuttingDuneSimulator.step_and_image
 //   action_adapters.py:163-188 RelativeToSiliconActionAdapter.get_action
