@@ -1808,7 +1808,14 @@ static int launch_walk_plan(const StepArgs& a_in, cudaStream_t stream) {
   StepArgs a = a_in;
   const int64_t n = a.st.n_envs;
   a.list_hint = nullptr;
-  {
+  // (no page-locked allocation while the stream is being captured into a
+  // graph: the launch then goes without a hint)
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) {
+    (void)cudaGetLastError();
+    capturing = cudaStreamCaptureStatusNone;
+  }
+  if (capturing == cudaStreamCaptureStatusNone) {
     std::lock_guard<std::mutex> lock(plan_hint_mutex());
     if (PlanHint* h = plan_hint_for(a.st.si_idx, true)) {
       void* dev_word = nullptr;
