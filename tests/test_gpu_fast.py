@@ -476,3 +476,37 @@ def test_sheet_edge_sites_vs_oracle(eng, nat, rate_fn, kernels):
   print(f'rate {rate_fn}: {on_edge / (n * t_steps):.2f} of the env-steps on '
         f'edge sites, {int(st.n_transitions.sum())} transitions')
   assert on_edge > 0.1 * n * t_steps
+
+
+def test_large_batch_kernel_choice_across_regimes(eng, nat):
+  """The default large-batch path picks its kernel per batch (k_walk_plan
+  while few envs leave the plan, k_walk_fast once the Si atoms have gathered
+  on the sheet's edge, the plan again after a reset): 5120 steps, a reset,
+  480 more, launch by launch against k_walk_fast alone -- per-step results and
+  final state."""
+  n, t_steps, dwell = 460800, 8, 1500000
+  spec = gh.rate_spec(po.RATE_PRIOR)
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(3)
+  acts = [torch.rand((t_steps, n, 2), generator=gen, device='cuda',
+                     dtype=torch.float64) * 2 - 1 for _ in range(5)]
+  runs = []
+  for walk_plan in (1, 0):
+    nat.check(nat.lib.pd_set_option(b'fast_path', 1))
+    nat.check(nat.lib.pd_set_option(b'plan', 0))
+    nat.check(nat.lib.pd_set_option(b'walk_plan', walk_plan))
+    b = eng.EnvBatch(n, seed=12)
+    b.reset()
+    digest = torch.zeros((), dtype=torch.int64, device='cuda')
+    for i in range(700):
+      if i == 640:
+        b.reset()
+      si, el = b.rollout(acts[i % 5], dwell, spec, record=True,
+                         action_mode=nat.ACTION_RELATIVE_TO_SILICON)
+      digest = digest * 1000003 + (si.to(torch.int64) * 31 + el).sum()
+    sd = b.state_dict()
+    runs.append((int(digest.item()),
+                 {k: gh.np_(sd[k]) for k in STATE_KEYS}))
+  assert runs[0][0] == runs[1][0]
+  for k in STATE_KEYS:
+    np.testing.assert_array_equal(runs[0][1][k], runs[1][1][k], err_msg=k)
