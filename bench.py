@@ -847,7 +847,10 @@ def run_ours(args, cfg):
         'workload': '1Mi envs x 64 steps per launch',
         'kernel': 'pd::k_walk_plan (+ pd::k_walk_fast<LIST>)',
         'value': big_n * 64 / (ms64 / 1e3), 'unit': UNIT, 'launch_ms': ms64,
-        'achieved': g64, 'peak': peak, 'frac': g64 / peak}
+        'achieved': g64, 'peak': peak, 'frac': g64 / peak,
+        'traffic': ncu_traffic('r02_k_walk_plan_1Mi_64step.ncu.json'),
+        'warp_instructions': ncu_value('r02_k_walk_plan_1Mi_64step.ncu.json',
+                                       'smsp__inst_executed.sum')}
     del big, acts64, b_si, b_el
 
   # -- STEM frames/s (the second half of BASELINE.json's metric) ---------------
@@ -893,10 +896,11 @@ def run_ours(args, cfg):
     roofline['issue_slots'] = issue_slots(
         ncu_value(issue_src, 'smsp__inst_executed.sum') if issue_src else None,
         launch_s, sm_mhz)
-    if at_scale and at_scale.get('rollout8'):
-      r8 = at_scale['rollout8']
-      r8['issue_slots'] = issue_slots(r8.pop('warp_instructions'),
-                                      r8['launch_ms'] / 1e3, sm_mhz)
+    for key in ('rollout8', 'rollout64'):
+      if at_scale and at_scale.get(key):
+        r8 = at_scale[key]
+        r8['issue_slots'] = issue_slots(r8.pop('warp_instructions'),
+                                        r8['launch_ms'] / 1e3, sm_mhz)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup,
