@@ -483,8 +483,13 @@ def measure_mlp(pd, batch, dev, args):
   out = {}
   n = 65536
   rng = np.random.default_rng(0)
-  for hidden, tensor_core in (((128, 128), False), ((256, 256), False),
-                              ((128, 128), True), ((256, 256), True)):
+  # tensor_core: False = FP32 FMA (parity path), 1 = tcgen05 with bf16
+  # operands (2e-2 of the largest rate), 2 = tcgen05 with fp16 hi + lo
+  # operands, three MMAs per K step (3e-7: a parity path; hidden <= 128)
+  for hidden, tensor_core in (((64, 64), False), ((128, 128), False),
+                              ((256, 256), False), ((64, 64), 2),
+                              ((128, 128), 2), ((128, 128), True),
+                              ((256, 256), True)):
     mlp = po.MlpParams.synthetic(7, hidden=hidden)
     w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
     rate = pd.RateSpec(2, mlp=w, device=dev, tensor_core=tensor_core)
@@ -505,15 +510,21 @@ def measure_mlp(pd, batch, dev, args):
     ms = sum(a.elapsed_time(c) for a, c in evs) / len(evs)
     evals = (int(b.n_events.sum().item()) - ev0) / len(evs)
     flop = 2 * (2 * hidden[0] + hidden[0] * hidden[1] + 4 * hidden[1])
-    out[f'H{hidden[0]}' + ('_tcgen05_bf16' if tensor_core else '_fp32')] = {
+    tag = {0: '_fp32', 1: '_tcgen05_bf16', 2: '_tcgen05_f16x3'}[
+        int(tensor_core)]
+    out[f'H{hidden[0]}' + tag] = {
         'envs': n, 'launch_ms': ms, 'env_steps_per_s': n / (ms / 1e3),
         'rate_evals_per_step': evals / n, 'flop_per_eval': flop,
         'tflops': evals * flop / (ms / 1e3) / 1e12,
-        'kernel': ('pd::k_step_learned<TC> (tcgen05.mma kind::f16, BF16 '
-                   'operands, FP32 accumulate in TMEM; 512 threads)'
-                   if tensor_core else
-                   'pd::k_step_learned (FP32 FMA, queue-batched GEMM, '
-                   'cp.async double-buffered W1 chunks; 512 threads)')}
+        'parity_path': int(tensor_core) != 1,
+        'kernel': {
+            0: 'pd::k_step_learned (FP32 FMA, queue-batched GEMM, cp.async '
+               'double-buffered W1 chunks; 512 threads)',
+            1: 'pd::k_step_learned<TC> (tcgen05.mma kind::f16, BF16 '
+               'operands, FP32 accumulate in TMEM; 512 threads)',
+            2: 'pd::k_step_learned<TC> (tcgen05.mma kind::f16, FP16 hi + lo '
+               'operands, three MMAs per K step into one TMEM accumulator; '
+               'rates within 3e-7 of the FP32 path)'}[int(tensor_core)]}
   return out
 
 

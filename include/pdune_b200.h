@@ -160,7 +160,12 @@ typedef struct pd_mlp {
    * default (0) is the FP32 parity path.  w1_umma: device copy of W1
    * transposed to [H2][H1], bf16, in the canonical no-swizzle K-major UMMA
    * layout (see pd_mlp_umma_layout_bytes / DESIGN.md).  Needs H1 % 16 == 0,
-   * H2 % 16 == 0, 32 <= H2 <= 256, and H1*(128 + H2)*2 B of shared memory. */
+   * H2 % 16 == 0, 32 <= H2 <= 256, and H1*(128 + H2)*2 B of shared memory.
+   * tensor_core = 2: both operands as fp16 hi + fp16 lo, three MMAs per K
+   * step (hi hi + hi lo + lo hi) -- rates within 3e-7 of the FP32 path's, i.e.
+   * a parity path; w1_umma then holds the hi tile followed by the lo tile
+   * (fp16, same layout), and the shared memory doubles: hidden sizes up to
+   * 128. */
   int32_t tensor_core;
   int32_t reserved_;
   const void* w1_umma;

@@ -17,6 +17,7 @@
 // up with fresh environments, so every GEMM wave is full until the tail.
 //
 // FP32 FMA throughout (the parity path of BASELINE.json's north_star).
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <type_traits>
@@ -233,6 +234,15 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
 // network inputs every wave.  The epilogue reads the accumulator with
 // tcgen05.ld (thread = TMEM lane = env), applies bias + swish, contracts with
 // W2 in registers and finishes with softplus.
+//
+// pd_mlp.tensor_core == 2, the split form: both operands as fp16 hi + fp16 lo
+// (x = hi + lo to ~2^-22 relative) and three MMAs per K step into the same
+// accumulator, hi hi + hi lo + lo hi (the lo lo term is below 2^-22); the
+// activations use the accurate expf / division of the FP32 path.  The rates
+// then agree with the FP32 path to 3e-7 of the largest rate (bf16, one MMA:
+// 2e-3), i.e. inside the FP32 path's own tolerance against the oracle.  Twice
+// the operand tiles: H1 (128 + H2) 4 bytes of shared memory, which H = 128
+// fits and H = 256 does not.
 // ---------------------------------------------------------------------------
 struct TcShared {
   unsigned long long mbar;
@@ -263,15 +273,35 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
          | (static_cast<uint32_t>(m >> 4) << 24);   // M; K-major A and B
 }
 
+__device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4)                                  // D format F32; A, B = F16
+         | (static_cast<uint32_t>(n >> 3) << 17)    // N
+         | (static_cast<uint32_t>(m >> 4) << 24);   // M; K-major A and B
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
+// x = hi + lo in fp16: (a, b) -> the packed hi pair and the packed lo pair
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t* hi,
+                                            uint32_t* lo) {
+  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+  const __half al = __float2half_rn(a - __half2float(ah));
+  const __half bl = __float2half_rn(b - __half2float(bh));
+  *hi = static_cast<uint32_t>(__half_as_ushort(ah)) |
+        (static_cast<uint32_t>(__half_as_ushort(bh)) << 16);
+  *lo = static_cast<uint32_t>(__half_as_ushort(al)) |
+        (static_cast<uint32_t>(__half_as_ushort(bl)) << 16);
+}
+
 struct TcCtx {
-  unsigned char* a_tile;   // shared, [128][H1] bf16 canonical
-  uint32_t a_addr, b_addr; // shared-window addresses
+  unsigned char* a_tile;   // shared, [128][H1] bf16 / fp16 canonical
+                           // (split: the lo tile follows, a_bytes further on)
+  uint32_t a_addr, b_addr; // shared-window addresses (split: lo tiles follow)
+  uint32_t a_bytes, b_bytes;  // size of one A / B tile
   TcShared* ts;
   uint32_t phase;
 };
@@ -284,8 +314,11 @@ __device__ __forceinline__ void tc_setup(const MlpView& w, TcCtx& tc,
   tc.b_addr = smem_u32(b_tile);
   tc.ts = ts;
   tc.phase = 0;
-  // W1^T in UMMA layout: verbatim 16-byte copies
-  const int n16 = w.h1 * w.h2 * 2 / 16;
+  tc.a_bytes = static_cast<uint32_t>(kMlpBatch) * w.h1 * 2;
+  tc.b_bytes = static_cast<uint32_t>(w.h2) * w.h1 * 2;
+  // W1^T in UMMA layout (split: hi tile, then lo tile): verbatim 16-byte
+  // copies
+  const int n16 = w.h1 * w.h2 * 2 / 16 * (w.tensor_core == 2 ? 2 : 1);
   const uint4* src = reinterpret_cast<const uint4*>(w.w1_umma);
   uint4* dst = reinterpret_cast<uint4*>(b_tile);
   for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -327,6 +360,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kblocks = w.h1 >> 3;          // 16-byte blocks along K
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
+  const bool split = w.tensor_core == 2;
   // ---- h1 = swish(x_hat W0 + b0) as bf16, canonical K-major ----
   // A warp writes 8 rows x 4 k-blocks (512 contiguous bytes) per trip; with
   // kblocks / 4 dividing the warp count a thread keeps its 8 columns of W0 /
@@ -354,16 +388,30 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
       const float x0 = xr.x * sh.bn_a[0] + sh.bn_b[0];
       const float x1 = xr.y * sh.bn_a[1] + sh.bn_b[1];
       float h[8];
+      unsigned char* cell_p =
+          tc.a_tile + static_cast<size_t>(g) * sbo + kb * 128 + m8 * 16;
+      if (split) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
-      uint4 v;
-      v.x = pack_bf16x2(h[0], h[1]);
-      v.y = pack_bf16x2(h[2], h[3]);
-      v.z = pack_bf16x2(h[4], h[5]);
-      v.w = pack_bf16x2(h[6], h[7]);
-      *reinterpret_cast<uint4*>(tc.a_tile + static_cast<size_t>(g) * sbo +
-                                kb * 128 + m8 * 16) = v;
+        for (int j = 0; j < 8; ++j)
+          h[j] = swishf(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+        uint4 vh, vl;
+        split_f16x2(h[0], h[1], &vh.x, &vl.x);
+        split_f16x2(h[2], h[3], &vh.y, &vl.y);
+        split_f16x2(h[4], h[5], &vh.z, &vl.z);
+        split_f16x2(h[6], h[7], &vh.w, &vl.w);
+        *reinterpret_cast<uint4*>(cell_p) = vh;
+        *reinterpret_cast<uint4*>(cell_p + tc.a_bytes) = vl;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+        uint4 v;
+        v.x = pack_bf16x2(h[0], h[1]);
+        v.y = pack_bf16x2(h[2], h[3]);
+        v.z = pack_bf16x2(h[4], h[5]);
+        v.w = pack_bf16x2(h[6], h[7]);
+        *reinterpret_cast<uint4*>(cell_p) = v;
+      }
     }
   }
   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -373,11 +421,11 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   const uint32_t tmem = tc.ts->tmem_base;
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t idesc = umma_idesc_bf16(kMlpBatch, w.h2);
-    for (int kk = 0; kk < (w.h1 >> 4); ++kk) {
-      const uint64_t da = umma_desc(tc.a_addr + kk * 256, 128u, sbo);
-      const uint64_t db = umma_desc(tc.b_addr + kk * 256, 128u, sbo);
-      const uint32_t accumulate = kk > 0 ? 1u : 0u;
+    const uint32_t idesc = split ? umma_idesc_f16(kMlpBatch, w.h2)
+                                 : umma_idesc_bf16(kMlpBatch, w.h2);
+    auto mma = [&](uint32_t a_addr, uint32_t b_addr, uint32_t accumulate) {
+      const uint64_t da = umma_desc(a_addr, 128u, sbo);
+      const uint64_t db = umma_desc(b_addr, 128u, sbo);
       asm volatile(
           "{\n\t"
           ".reg .pred p;\n\t"
@@ -385,6 +433,14 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
           "}\n" ::"r"(tmem),
           "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+    };
+    for (int kk = 0; kk < (w.h1 >> 4); ++kk) {
+      const uint32_t a_hi = tc.a_addr + kk * 256, b_hi = tc.b_addr + kk * 256;
+      mma(a_hi, b_hi, kk > 0 ? 1u : 0u);
+      if (split) {  // + hi lo + lo hi
+        mma(a_hi, b_hi + tc.b_bytes, 1u);
+        mma(a_hi + tc.a_bytes, b_hi, 1u);
+      }
     }
     // arrives on the mbarrier when every MMA above has completed
     asm volatile(
@@ -438,7 +494,8 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = c0 + j;
-          const float hh = swish_fast(__uint_as_float(r[j]) + sh.b1[col]);
+          const float z = __uint_as_float(r[j]) + sh.b1[col];
+          const float hh = split ? swishf(z) : swish_fast(z);
           const float4 w2v = *reinterpret_cast<const float4*>(sh.w2[col]);
           o[0] = fmaf(hh, w2v.x, o[0]);
           o[1] = fmaf(hh, w2v.y, o[1]);
@@ -464,11 +521,12 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
 }
 
 // Shared-memory carve-up of the tensor-core kernels (dynamic, 1 KB aligned).
-__host__ __device__ inline size_t tc_a_bytes(int h1) {
-  return static_cast<size_t>(kMlpBatch) * h1 * 2;
+// (tiles = 2 in the split form: hi and lo)
+__host__ __device__ inline size_t tc_a_bytes(int h1, int tiles = 1) {
+  return static_cast<size_t>(kMlpBatch) * h1 * 2 * tiles;
 }
-__host__ __device__ inline size_t tc_b_bytes(int h1, int h2) {
-  return static_cast<size_t>(h2) * h1 * 2;
+__host__ __device__ inline size_t tc_b_bytes(int h1, int h2, int tiles = 1) {
+  return static_cast<size_t>(h2) * h1 * 2 * tiles;
 }
 
 // predict()'s frame canonicalisation for one env (float64 like the
@@ -547,12 +605,13 @@ __device__ __forceinline__ void tc_carve(const MlpView& w,
       (reinterpret_cast<uintptr_t>(smem_raw + used) + 15) & ~uintptr_t(15));
   unsigned char* a_tile = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(ts + 1) + 127) & ~uintptr_t(127));
-  tc_setup(w, tc, a_tile, a_tile + tc_a_bytes(w.h1), ts);
+  tc_setup(w, tc, a_tile,
+           a_tile + tc_a_bytes(w.h1, w.tensor_core == 2 ? 2 : 1), ts);
 }
 
-static size_t tc_smem_bytes(size_t used, int h1, int h2) {
-  return used + sizeof(TcShared) + 16 + 128 + tc_a_bytes(h1) +
-         tc_b_bytes(h1, h2);
+static size_t tc_smem_bytes(size_t used, int h1, int h2, int tiles) {
+  return used + sizeof(TcShared) + 16 + 128 + tc_a_bytes(h1, tiles) +
+         tc_b_bytes(h1, h2, tiles);
 }
 
 template <int NPT, bool TC>
@@ -859,6 +918,13 @@ static int mlp_view(const pd_mlp* mlp, MlpView* v) {
     PD_REQUIRE(mlp->w1_umma != nullptr, "tensor_core needs w1_umma");
     PD_REQUIRE(mlp->hidden2 % 32 == 0, "tensor_core needs hidden2 % 32 == 0");
     PD_REQUIRE(mlp->hidden1 % 32 == 0, "tensor_core needs hidden1 % 32 == 0");
+    PD_REQUIRE(mlp->tensor_core == 1 || mlp->tensor_core == 2,
+               "tensor_core: 0 (FP32), 1 (bf16) or 2 (fp16 hi + lo)");
+    PD_REQUIRE(mlp->tensor_core == 1 ||
+                   tc_smem_bytes(sizeof(MlpStepSharedT<true>), mlp->hidden1,
+                                 mlp->hidden2, 2) <= 227 * 1024,
+               "tensor_core = 2 keeps two tiles per operand in shared memory: "
+               "hidden sizes up to 128");
   }
   *v = MlpView{mlp->context_dim, mlp->hidden1, mlp->hidden2, mlp->batchnorm,
                mlp->bn_scale, mlp->bn_offset, mlp->bn_mean, mlp->bn_var,
@@ -892,7 +958,8 @@ int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (v.tensor_core) {
     const int smem = static_cast<int>(
-        tc_smem_bytes(sizeof(MlpStepSharedT<true>), v.h1, v.h2));
+        tc_smem_bytes(sizeof(MlpStepSharedT<true>), v.h1, v.h2,
+                      v.tensor_core == 2 ? 2 : 1));
     auto kern = k_step_learned<2, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -921,7 +988,8 @@ int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   if (v.tensor_core) {
     const int smem =
-        static_cast<int>(tc_smem_bytes(sizeof(MlpSmall), v.h1, v.h2));
+        static_cast<int>(tc_smem_bytes(sizeof(MlpSmall), v.h1, v.h2,
+                                       v.tensor_core == 2 ? 2 : 1));
     auto kern = k_rates_learned<2, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

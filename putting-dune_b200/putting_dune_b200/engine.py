@@ -125,13 +125,28 @@ def umma_k_major_bf16(mat: np.ndarray) -> np.ndarray:
   core matrices; consecutive core matrices along K are 128 B apart (LBO) and
   each group of 8 rows owns K/8 of them (SBO = K/8 * 128 B).  Returned as the
   flat uint16 array to copy into shared memory verbatim."""
-  rows, k = mat.shape
+  return _umma_k_major(to_bf16_bits(mat))
+
+
+def _umma_k_major(bits: np.ndarray) -> np.ndarray:
+  rows, k = bits.shape
   if rows % 8 or k % 8:
     raise ValueError('rows and K must be multiples of 8')
-  bits = to_bf16_bits(mat).reshape(rows // 8, 8, k // 8, 8)
+  bits = bits.reshape(rows // 8, 8, k // 8, 8)
   # (row group, row in group, k block, k in block) ->
   # (row group, k block, row in group, k in block)
   return np.ascontiguousarray(bits.transpose(0, 2, 1, 3)).reshape(-1)
+
+
+def umma_k_major_f16_split(mat: np.ndarray) -> np.ndarray:
+  """[rows, K] float32 -> fp16 hi tile followed by fp16 lo tile (mat = hi + lo
+  to ~2^-22 relative), each in the layout of `umma_k_major_bf16`: the operand
+  of pd_mlp.tensor_core = 2."""
+  mat = np.asarray(mat, dtype=np.float32)
+  hi = mat.astype(np.float16)
+  lo = (mat - hi.astype(np.float32)).astype(np.float16)
+  return np.concatenate([_umma_k_major(hi.view(np.uint16)),
+                         _umma_k_major(lo.view(np.uint16))])
 
 
 class RateSpec:
@@ -197,15 +212,20 @@ class RateSpec:
             np.ascontiguousarray(getattr(mlp, name), dtype=np.float32),
             device=device)
       umma_ptr = None
-      if tensor_core:
+      # tensor_core: False / 0 = FP32 FMA (the parity path); True / 1 = tcgen05
+      # with bf16 operands (2e-2 of the largest rate); 2 = tcgen05 with fp16
+      # hi + lo operands, three MMAs per K step (3e-7; hidden sizes <= 128)
+      tc_mode = int(tensor_core)
+      if tc_mode:
+        w1t = np.asarray(mlp.w1, dtype=np.float32).T
         self._tensors['w1_umma'] = torch.as_tensor(
-            umma_k_major_bf16(np.asarray(mlp.w1, dtype=np.float32).T),
-            device=device)
+            umma_k_major_f16_split(w1t) if tc_mode == 2
+            else umma_k_major_bf16(w1t), device=device)
         umma_ptr = self._tensors['w1_umma'].data_ptr()
       self._mlp_c = nat.PdMlp(d, h1, h2, int(mlp.batchnorm),
                               *[self._tensors[n].data_ptr()
                                 for n in MlpWeights.NAMES],
-                              int(bool(tensor_core)), 0, umma_ptr)
+                              tc_mode, 0, umma_ptr)
       self.c.mlp = C.pointer(self._mlp_c)
       self.mlp = mlp
 

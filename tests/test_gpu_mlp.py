@@ -229,3 +229,64 @@ def test_tensor_core_step_statistics():
     assert (gh.np_(out.elapsed_us) >= 3500000).all()
     tr.append(float(gh.np_(b.n_transitions).mean()))
   assert tr[0] > 0.5 and abs(tr[1] - tr[0]) <= 0.03 * tr[0], tr
+
+
+@pytest.mark.parametrize('hidden', [(128, 128), (64, 64), (32, 32),
+                                    (64, 128)])
+def test_tensor_core_split_is_a_parity_path(hidden):
+  """pd_mlp.tensor_core = 2: tcgen05 with both operands as fp16 hi + fp16 lo
+  and three MMAs per K step.  The rates must meet the FP32 path's own bar --
+  2e-5 of the largest rate against the float64 oracle -- and agree with the
+  FP32 path to 2e-6; a step through it must leave almost every env where the
+  FP32 path leaves it."""
+  from putting_dune_b200 import engine
+  n, seed = 3000, 6
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(4, hidden=hidden)
+  rng = np.random.default_rng(1)
+  mlp.b1 = rng.normal(0, 0.2, hidden[1]).astype(np.float32)
+  mlp.b2 = rng.normal(0, 0.3, 4).astype(np.float32)
+  beam = po.site_positions(st, st.si_idx, np.arange(n)) + rng.uniform(
+      -2.0, 2.0, size=(n, 2))
+  b = gh.batch_from_oracle(st)
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  fp32 = engine.RateSpec(po.RATE_LEARNED, mlp=w)
+  split = engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=2)
+  r32, nb32 = b.rates(beam, fp32)
+  rsp, nbsp = b.rates(beam, split)
+  np.testing.assert_array_equal(gh.np_(nb32), gh.np_(nbsp))
+  r32, rsp = gh.np_(r32), gh.np_(rsp)
+  scale = np.abs(r32).max()
+  err = np.abs(rsp - r32).max() / scale
+  print(f'hidden {hidden}: split vs FP32 path {err:.2e} of the largest rate')
+  assert err <= 2e-6, err
+  want, nbr = po.rates_for(st, np.arange(n), beam, po.RATE_LEARNED, mlp)
+  np.testing.assert_array_equal(gh.np_(nbsp), nbr)
+  assert np.abs(rsp - want).max() <= _tol(want)
+  rsp2, _ = b.rates(beam, split)
+  np.testing.assert_array_equal(gh.np_(rsp2), rsp)
+  # a few steps: trajectories differ from the FP32 path's only where a rate
+  # difference of 1e-6 flips a draw
+  ctl = 0.5 + rng.uniform(-0.05, 0.05, size=(n, 1, 2))
+  sites = []
+  for spec in (fp32, split):
+    bb = gh.batch_from_oracle(st)
+    for _ in range(6):
+      bb.step_and_image(ctl, 1500000, spec)
+    sites.append(gh.np_(bb.si_idx))
+  assert (sites[0] != sites[1]).sum() <= 3
+
+
+def test_tensor_core_split_needs_its_tiles_to_fit():
+  from putting_dune_b200 import engine
+  from putting_dune_b200 import _native as nat
+  mlp = po.MlpParams.synthetic(4, hidden=(256, 256))
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  b = engine.EnvBatch(64, seed=0)
+  b.reset()
+  with pytest.raises(nat.NativeError, match='hidden sizes up to 128'):
+    b.rates(np.zeros((64, 2)),
+            engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=2))
