@@ -485,11 +485,12 @@ def measure_mlp(pd, batch, dev, args):
   rng = np.random.default_rng(0)
   # tensor_core: False = FP32 FMA (parity path), 1 = tcgen05 with bf16
   # operands (2e-2 of the largest rate), 2 = tcgen05 with fp16 hi + lo
-  # operands, three MMAs per K step (3e-7: a parity path; hidden <= 128)
+  # operands, three MMAs per K step (3e-7 .. 6e-7: a parity path; at H = 256
+  # the W1 tiles are streamed from L2, K in two halves per wave)
   for hidden, tensor_core in (((64, 64), False), ((128, 128), False),
                               ((256, 256), False), ((64, 64), 2),
-                              ((128, 128), 2), ((128, 128), True),
-                              ((256, 256), True)):
+                              ((128, 128), 2), ((256, 256), 2),
+                              ((128, 128), True), ((256, 256), True)):
     mlp = po.MlpParams.synthetic(7, hidden=hidden)
     w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
     rate = pd.RateSpec(2, mlp=w, device=dev, tensor_core=tensor_core)

@@ -54,6 +54,9 @@ struct MlpView {
   const float *w0, *b0, *w1, *b1, *w2, *b2;
   int tensor_core;
   const void* w1_umma;
+  int tc_k_phases;  // tensor path: K handled in this many parts per wave (1 =
+                    // W1 resident in shared memory; 2 = its tiles streamed
+                    // from L2, half of K at a time)
 };
 
 __device__ __forceinline__ float swishf(float z) {
@@ -238,11 +241,14 @@ __device__ __forceinline__ void mlp_wave(const MlpView& w, MlpShared& sh) {
 // pd_mlp.tensor_core == 2, the split form: both operands as fp16 hi + fp16 lo
 // (x = hi + lo to ~2^-22 relative) and three MMAs per K step into the same
 // accumulator, hi hi + hi lo + lo hi (the lo lo term is below 2^-22); the
-// activations use the accurate expf / division of the FP32 path.  The rates
-// then agree with the FP32 path to 3e-7 of the largest rate (bf16, one MMA:
-// 2e-3), i.e. inside the FP32 path's own tolerance against the oracle.  Twice
+// activations keep the SFU forms (ex2 / rcp, ~2^-21 relative).  The rates
+// then agree with the FP32 path to ~1e-6 of the largest rate (bf16, one MMA:
+// 2e-3), i.e. inside the FP32 path's own tolerance against the oracle (2e-5).  Twice
 // the operand tiles: H1 (128 + H2) 4 bytes of shared memory, which H = 128
-// fits and H = 256 does not.
+// fits and H = 256 does not: there a wave takes K in two halves, copying the
+// W1 tiles of a half from global memory (L2: 256 KB per wave and CTA, ~1.5 TB/s
+// over the device) and regenerating h1 for it, with the MMAs of the second
+// half accumulating onto the first.
 // ---------------------------------------------------------------------------
 struct TcShared {
   unsigned long long mbar;
@@ -304,6 +310,7 @@ struct TcCtx {
   uint32_t a_bytes, b_bytes;  // size of one A / B tile
   TcShared* ts;
   uint32_t phase;
+  int b_part;  // streamed W1: the part of K whose tiles are in shared memory
 };
 
 __device__ __forceinline__ void tc_setup(const MlpView& w, TcCtx& tc,
@@ -314,11 +321,14 @@ __device__ __forceinline__ void tc_setup(const MlpView& w, TcCtx& tc,
   tc.b_addr = smem_u32(b_tile);
   tc.ts = ts;
   tc.phase = 0;
-  tc.a_bytes = static_cast<uint32_t>(kMlpBatch) * w.h1 * 2;
-  tc.b_bytes = static_cast<uint32_t>(w.h2) * w.h1 * 2;
+  tc.b_part = -1;
+  tc.a_bytes = static_cast<uint32_t>(kMlpBatch) * w.h1 * 2 / w.tc_k_phases;
+  tc.b_bytes = static_cast<uint32_t>(w.h2) * w.h1 * 2 / w.tc_k_phases;
   // W1^T in UMMA layout (split: hi tile, then lo tile): verbatim 16-byte
-  // copies
-  const int n16 = w.h1 * w.h2 * 2 / 16 * (w.tensor_core == 2 ? 2 : 1);
+  // copies (when it is streamed, mlp_wave_tc copies it part by part)
+  const int n16 = w.tc_k_phases > 1
+                      ? 0
+                      : w.h1 * w.h2 * 2 / 16 * (w.tensor_core == 2 ? 2 : 1);
   const uint4* src = reinterpret_cast<const uint4*>(w.w1_umma);
   uint4* dst = reinterpret_cast<uint4*>(b_tile);
   for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -358,116 +368,142 @@ __device__ __forceinline__ void tc_teardown(const MlpView& w, TcCtx& tc) {
 __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
                                             TcCtx& tc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int kblocks = w.h1 >> 3;          // 16-byte blocks along K
+  const int kblocks_all = w.h1 >> 3;      // 16-byte blocks along K
+  const int kblocks = kblocks_all / w.tc_k_phases;  // ... of one part of K
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
   const bool split = w.tensor_core == 2;
-  // ---- h1 = swish(x_hat W0 + b0) as bf16, canonical K-major ----
-  // A warp writes 8 rows x 4 k-blocks (512 contiguous bytes) per trip; with
-  // kblocks / 4 dividing the warp count a thread keeps its 8 columns of W0 /
-  // b0 in registers for the whole wave.
-  {
-    const int m8 = lane & 7, kb_lo = lane >> 3;
-    const int wcols = kblocks >> 2;  // warp columns
-    const int n_cells = 16 * wcols;
-    int cur_wc = -1;
-    float w0a[8], w0b[8], b0v[8];
-    for (int cell = warp; cell < n_cells; cell += kMlpThreads / 32) {
-      const int wc = cell % wcols, g = cell / wcols;
-      const int kb = wc * 4 + kb_lo;
-      if (wc != cur_wc) {
-        cur_wc = wc;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          w0a[j] = sh.w0[0][kb * 8 + j];
-          w0b[j] = sh.w0[1][kb * 8 + j];
-          b0v[j] = sh.b0[kb * 8 + j];
+  const uint32_t tmem = tc.ts->tmem_base;
+  // (streamed W1: a wave starts with the part of K the previous wave ended
+  // with, whose tiles are still there -- one copy per wave instead of two)
+  const int first_part = tc.b_part >= 0 ? tc.b_part : 0;
+  for (int pi = 0; pi < w.tc_k_phases; ++pi) {
+    const int ph = (first_part + pi) % w.tc_k_phases;
+    if (w.tc_k_phases > 1 && tc.b_part != ph) {
+      // ---- this part's W1 tiles (hi, then lo), from global memory: per
+      // 8-row group the part's k blocks are contiguous ----
+      const int per_group = kblocks * 8;  // 16-byte units
+      const int n_units = (w.h2 >> 3) * per_group;
+      for (int t = 0; t < (split ? 2 : 1); ++t) {
+        const uint4* src = reinterpret_cast<const uint4*>(w.w1_umma) +
+                           static_cast<size_t>(t) * w.h1 * w.h2 * 2 / 16;
+        uint4* dst = reinterpret_cast<uint4*>(
+            tc.a_tile + (split ? 2 : 1) * tc.a_bytes + t * tc.b_bytes);
+        for (int i = tid; i < n_units; i += kMlpThreads) {
+          const int g = i / per_group, j = i - g * per_group;
+          dst[i] = __ldg(src + (g * kblocks_all + ph * kblocks) * 8 + j);
         }
       }
-      const int m = g * 8 + m8;
-      const float2 xr = *reinterpret_cast<const float2*>(sh.xs[m]);
-      const float x0 = xr.x * sh.bn_a[0] + sh.bn_b[0];
-      const float x1 = xr.y * sh.bn_a[1] + sh.bn_b[1];
-      float h[8];
-      unsigned char* cell_p =
-          tc.a_tile + static_cast<size_t>(g) * sbo + kb * 128 + m8 * 16;
-      if (split) {
+      tc.b_part = ph;
+    }
+    // ---- h1 = swish(x_hat W0 + b0) as bf16 / fp16, canonical K-major ----
+    // A warp writes 8 rows x 4 k-blocks (512 contiguous bytes) per trip; with
+    // kblocks / 4 dividing the warp count a thread keeps its 8 columns of W0 /
+    // b0 in registers for the whole wave.
+    {
+      const int m8 = lane & 7, kb_lo = lane >> 3;
+      const int wcols = kblocks >> 2;  // warp columns
+      const int n_cells = 16 * wcols;
+      int cur_wc = -1;
+      float w0a[8], w0b[8], b0v[8];
+      for (int cell = warp; cell < n_cells; cell += kMlpThreads / 32) {
+        const int wc = cell % wcols, g = cell / wcols;
+        const int kb = wc * 4 + kb_lo;           // within this part of K
+        const int kcol = (ph * kblocks + kb) * 8;  // column of W0 / b0
+        if (wc != cur_wc) {
+          cur_wc = wc;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          h[j] = swishf(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
-        uint4 vh, vl;
-        split_f16x2(h[0], h[1], &vh.x, &vl.x);
-        split_f16x2(h[2], h[3], &vh.y, &vl.y);
-        split_f16x2(h[4], h[5], &vh.z, &vl.z);
-        split_f16x2(h[6], h[7], &vh.w, &vl.w);
-        *reinterpret_cast<uint4*>(cell_p) = vh;
-        *reinterpret_cast<uint4*>(cell_p + tc.a_bytes) = vl;
-      } else {
+          for (int j = 0; j < 8; ++j) {
+            w0a[j] = sh.w0[0][kcol + j];
+            w0b[j] = sh.w0[1][kcol + j];
+            b0v[j] = sh.b0[kcol + j];
+          }
+        }
+        const int m = g * 8 + m8;
+        const float2 xr = *reinterpret_cast<const float2*>(sh.xs[m]);
+        const float x0 = xr.x * sh.bn_a[0] + sh.bn_b[0];
+        const float x1 = xr.y * sh.bn_a[1] + sh.bn_b[1];
+        float h[8];
+        unsigned char* cell_p =
+            tc.a_tile + static_cast<size_t>(g) * sbo + kb * 128 + m8 * 16;
+        if (split) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
-        uint4 v;
-        v.x = pack_bf16x2(h[0], h[1]);
-        v.y = pack_bf16x2(h[2], h[3]);
-        v.z = pack_bf16x2(h[4], h[5]);
-        v.w = pack_bf16x2(h[6], h[7]);
-        *reinterpret_cast<uint4*>(cell_p) = v;
+          for (int j = 0; j < 8; ++j)
+            h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+          uint4 vh, vl;
+          split_f16x2(h[0], h[1], &vh.x, &vl.x);
+          split_f16x2(h[2], h[3], &vh.y, &vl.y);
+          split_f16x2(h[4], h[5], &vh.z, &vl.z);
+          split_f16x2(h[6], h[7], &vh.w, &vl.w);
+          *reinterpret_cast<uint4*>(cell_p) = vh;
+          *reinterpret_cast<uint4*>(cell_p + tc.a_bytes) = vl;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+          uint4 v;
+          v.x = pack_bf16x2(h[0], h[1]);
+          v.y = pack_bf16x2(h[2], h[3]);
+          v.z = pack_bf16x2(h[4], h[5]);
+          v.w = pack_bf16x2(h[6], h[7]);
+          *reinterpret_cast<uint4*>(cell_p) = v;
+        }
       }
     }
-  }
-  // generic-proxy writes -> visible to the tensor core (async proxy)
-  asm volatile("fence.proxy.async.shared::cta;");
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  const uint32_t tmem = tc.ts->tmem_base;
-  if (tid == 0) {
+    // generic-proxy writes -> visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t idesc = split ? umma_idesc_f16(kMlpBatch, w.h2)
+                                   : umma_idesc_bf16(kMlpBatch, w.h2);
+      auto mma = [&](uint32_t a_addr, uint32_t b_addr, uint32_t accumulate) {
+        const uint64_t da = umma_desc(a_addr, 128u, sbo);
+        const uint64_t db = umma_desc(b_addr, 128u, sbo);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+      };
+      for (int kk = 0; kk < (kblocks >> 1); ++kk) {
+        const uint32_t a_hi = tc.a_addr + kk * 256;
+        const uint32_t b_hi = tc.b_addr + kk * 256;
+        mma(a_hi, b_hi, (pi > 0 || kk > 0) ? 1u : 0u);
+        if (split) {  // + hi lo + lo hi
+          mma(a_hi, b_hi + tc.b_bytes, 1u);
+          mma(a_hi + tc.a_bytes, b_hi, 1u);
+        }
+      }
+      // arrives on the mbarrier when every MMA above has completed
+      asm volatile(
+          "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster."
+          "b64 [%0];" ::"r"(smem_u32(&tc.ts->mbar)));
+    }
+    // ---- wait for the MMAs (the accumulator; the tiles are free again) ----
+    {
+      const uint32_t bar = smem_u32(&tc.ts->mbar);
+      uint32_t done = 0;
+      // try_wait suspends for a hardware-defined interval; the spin bound
+      // turns a lost completion into a trap instead of a hung GPU.
+      for (int spin = 0; !done && spin < (1 << 24); ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(tc.phase)
+            : "memory");
+      }
+      if (!done) __trap();
+      tc.phase ^= 1u;
+    }
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t idesc = split ? umma_idesc_f16(kMlpBatch, w.h2)
-                                 : umma_idesc_bf16(kMlpBatch, w.h2);
-    auto mma = [&](uint32_t a_addr, uint32_t b_addr, uint32_t accumulate) {
-      const uint64_t da = umma_desc(a_addr, 128u, sbo);
-      const uint64_t db = umma_desc(b_addr, 128u, sbo);
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "setp.ne.b32 p, %4, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-          "}\n" ::"r"(tmem),
-          "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
-    };
-    for (int kk = 0; kk < (w.h1 >> 4); ++kk) {
-      const uint32_t a_hi = tc.a_addr + kk * 256, b_hi = tc.b_addr + kk * 256;
-      mma(a_hi, b_hi, kk > 0 ? 1u : 0u);
-      if (split) {  // + hi lo + lo hi
-        mma(a_hi, b_hi + tc.b_bytes, 1u);
-        mma(a_hi + tc.a_bytes, b_hi, 1u);
-      }
-    }
-    // arrives on the mbarrier when every MMA above has completed
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 "
-        "[%0];" ::"r"(smem_u32(&tc.ts->mbar)));
   }
-  // ---- wait for the accumulator ----
-  {
-    const uint32_t bar = smem_u32(&tc.ts->mbar);
-    uint32_t done = 0;
-    // try_wait suspends for a hardware-defined interval; the spin bound turns
-    // a lost completion into a trap instead of a hung GPU.
-    for (int spin = 0; !done && spin < (1 << 24); ++spin) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred P1;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, P1;\n\t"
-          "}\n"
-          : "=r"(done)
-          : "r"(bar), "r"(tc.phase)
-          : "memory");
-    }
-    if (!done) __trap();
-    tc.phase ^= 1u;
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;");
   // ---- epilogue: thread = TMEM lane = env row; up to four column slices ----
   const int n_slices = (w.h2 >> 4) < 4 ? (w.h2 >> 4) : 4;
   {
@@ -495,7 +531,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
         for (int j = 0; j < 16; ++j) {
           const int col = c0 + j;
           const float z = __uint_as_float(r[j]) + sh.b1[col];
-          const float hh = split ? swishf(z) : swish_fast(z);
+          const float hh = swish_fast(z);
           const float4 w2v = *reinterpret_cast<const float4*>(sh.w2[col]);
           o[0] = fmaf(hh, w2v.x, o[0]);
           o[1] = fmaf(hh, w2v.y, o[1]);
@@ -606,12 +642,16 @@ __device__ __forceinline__ void tc_carve(const MlpView& w,
   unsigned char* a_tile = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(ts + 1) + 127) & ~uintptr_t(127));
   tc_setup(w, tc, a_tile,
-           a_tile + tc_a_bytes(w.h1, w.tensor_core == 2 ? 2 : 1), ts);
+           a_tile + tc_a_bytes(w.h1 / w.tc_k_phases,
+                               w.tensor_core == 2 ? 2 : 1),
+           ts);
 }
 
-static size_t tc_smem_bytes(size_t used, int h1, int h2, int tiles) {
-  return used + sizeof(TcShared) + 16 + 128 + tc_a_bytes(h1, tiles) +
-         tc_b_bytes(h1, h2, tiles);
+static size_t tc_smem_bytes(size_t used, int h1, int h2, int tiles,
+                            int k_phases) {
+  return used + sizeof(TcShared) + 16 + 128 +
+         tc_a_bytes(h1 / k_phases, tiles) +
+         tc_b_bytes(h1 / k_phases, h2, tiles);
 }
 
 template <int NPT, bool TC>
@@ -920,16 +960,27 @@ static int mlp_view(const pd_mlp* mlp, MlpView* v) {
     PD_REQUIRE(mlp->hidden1 % 32 == 0, "tensor_core needs hidden1 % 32 == 0");
     PD_REQUIRE(mlp->tensor_core == 1 || mlp->tensor_core == 2,
                "tensor_core: 0 (FP32), 1 (bf16) or 2 (fp16 hi + lo)");
-    PD_REQUIRE(mlp->tensor_core == 1 ||
-                   tc_smem_bytes(sizeof(MlpStepSharedT<true>), mlp->hidden1,
-                                 mlp->hidden2, 2) <= 227 * 1024,
-               "tensor_core = 2 keeps two tiles per operand in shared memory: "
-               "hidden sizes up to 128");
+  }
+  // W1's tiles stay in shared memory when they fit beside the h1 tiles;
+  // otherwise a wave takes K in two halves and streams them (split form at
+  // H = 256)
+  int k_phases = 1;
+  if (mlp->tensor_core) {
+    const int tiles = mlp->tensor_core == 2 ? 2 : 1;
+    const size_t cap = 227 * 1024;
+    if (tc_smem_bytes(sizeof(MlpStepSharedT<true>), mlp->hidden1, mlp->hidden2,
+                      tiles, 1) > cap) {
+      k_phases = 2;
+      PD_REQUIRE(mlp->hidden1 % 64 == 0 &&
+                     tc_smem_bytes(sizeof(MlpStepSharedT<true>), mlp->hidden1,
+                                   mlp->hidden2, tiles, 2) <= cap,
+                 "tensor_core: the operand tiles do not fit in shared memory");
+    }
   }
   *v = MlpView{mlp->context_dim, mlp->hidden1, mlp->hidden2, mlp->batchnorm,
                mlp->bn_scale, mlp->bn_offset, mlp->bn_mean, mlp->bn_var,
                mlp->w0, mlp->b0, mlp->w1, mlp->b1, mlp->w2, mlp->b2,
-               mlp->tensor_core, mlp->w1_umma};
+               mlp->tensor_core, mlp->w1_umma, k_phases};
   return PD_OK;
 }
 
@@ -959,7 +1010,7 @@ int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   if (v.tensor_core) {
     const int smem = static_cast<int>(
         tc_smem_bytes(sizeof(MlpStepSharedT<true>), v.h1, v.h2,
-                      v.tensor_core == 2 ? 2 : 1));
+                      v.tensor_core == 2 ? 2 : 1, v.tc_k_phases));
     auto kern = k_step_learned<2, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -989,7 +1040,8 @@ int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
   if (v.tensor_core) {
     const int smem =
         static_cast<int>(tc_smem_bytes(sizeof(MlpSmall), v.h1, v.h2,
-                                       v.tensor_core == 2 ? 2 : 1));
+                                       v.tensor_core == 2 ? 2 : 1,
+                                       v.tc_k_phases));
     auto kern = k_rates_learned<2, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
