@@ -6,7 +6,10 @@ Reference: putting_dune/rate_learning/learn_rates.py --
 
 Weights come from the reference's Haiku parameter/state trees
 (``engine.MlpWeights.from_haiku``) or any flat set of arrays; the forward pass
-runs in the CUDA library (FP32 FMA GEMM, ``csrc/pd_mlp.cu``).
+runs in the CUDA library (``csrc/pd_mlp.cu``): on the tensor cores with fp16
+hi + lo operands (``tensor_core=2``: rates within 1e-6 of the FP32 kernel's,
+inside its tolerance against the reference arithmetic) where the layer sizes
+allow it, else as an FP32 FMA GEMM.
 """
 
 from __future__ import annotations
@@ -26,18 +29,32 @@ class LearnedTransitionRatePredictor:
   plus ``apply_model`` over an ensemble."""
 
   def __init__(self, models: Sequence[engine.MlpWeights] | engine.MlpWeights,
-               device=None):
+               device=None, tensor_core='auto'):
+    """tensor_core: 'auto' (the split-precision tcgen05 kernel when the hidden
+    sizes are multiples of 32 up to 256, else FP32), 0 (FP32 FMA), 2 (split
+    precision, a parity path) or 1 (bf16 operands: 2e-2, throughput only)."""
     if isinstance(models, engine.MlpWeights):
       models = [models]
     self.models = list(models)
     self.num_models = len(self.models)
     self._device = device
+    self._tensor_core = tensor_core
     self._specs = None
+
+  @staticmethod
+  def _tensor_mode(mlp: engine.MlpWeights, requested) -> int:
+    if requested != 'auto':
+      return int(requested)
+    h1, h2 = np.asarray(mlp.w1).shape
+    ok = (h1 % 32 == 0 and h1 <= 256 and h2 in (32, 64, 128, 256) and
+          (h1 * (128 + h2) * 4 <= 190 * 1024 or h1 % 64 == 0))
+    return 2 if ok else 0
 
   def _build(self):
     if self._specs is None:
-      self._specs = [engine.RateSpec(nat.RATE_LEARNED, mlp=m,
-                                     device=self._device)
+      self._specs = [engine.RateSpec(
+          nat.RATE_LEARNED, mlp=m, device=self._device,
+          tensor_core=self._tensor_mode(m, self._tensor_core))
                      for m in self.models]
     return self._specs
 
