@@ -1,4 +1,5 @@
-"""Driver for ncu: learned-rate step, 65536 envs, H=256."""
+"""Driver for ncu: learned-rate step, 65536 envs.
+python profiles/prof_mlp.py [H] [fp32 | tc (bf16) | split (fp16 hi + lo)]"""
 import os
 import sys
 
@@ -13,7 +14,7 @@ import putting_dune_b200 as pd
 from oracle import pdune_oracle as po
 
 h = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-tc = len(sys.argv) > 2 and sys.argv[2] == 'tc'
+tc = {'tc': 1, 'split': 2}.get(sys.argv[2] if len(sys.argv) > 2 else '', 0)
 n = 65536
 mlp = po.MlpParams.synthetic(7, hidden=(h, h))
 w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})

@@ -390,7 +390,12 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
             tc.a_tile + (split ? 2 : 1) * tc.a_bytes + t * tc.b_bytes);
         for (int i = tid; i < n_units; i += kMlpThreads) {
           const int g = i / per_group, j = i - g * per_group;
-          dst[i] = __ldg(src + (g * kblocks_all + ph * kblocks) * 8 + j);
+          // (cp.async: the copy lands while this thread generates h1 below)
+          asm volatile(
+              "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                  smem_u32(dst + i)),
+              "l"(src + (g * kblocks_all + ph * kblocks) * 8 + j)
+              : "memory");
         }
       }
       tc.b_part = ph;
@@ -449,6 +454,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
         }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // generic-proxy writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
