@@ -16,7 +16,7 @@ from oracle import pdune_oracle as po
 from putting_dune_b200 import _native as nat
 
 h = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-tc = len(sys.argv) > 2 and sys.argv[2] == 'tc'
+tc = {'tc': 1, 'split': 2}.get(sys.argv[2] if len(sys.argv) > 2 else '', 0)
 n = 65536
 mlp = po.MlpParams.synthetic(7, hidden=(h, h))
 w = pd.MlpWeights(**{k: getattr(mlp, k) for k in pd.MlpWeights.NAMES})
@@ -36,7 +36,7 @@ e.record()
 torch.cuda.synchronize()
 nat.lib.pd_debug_mlp_phases(buf)
 t = np.array(list(buf), dtype=np.float64)
-print('H', h, 'tc' if tc else 'fp32', 'ms', s.elapsed_time(e))
+print('H', h, {0: 'fp32', 1: 'tc bf16', 2: 'tc split'}[tc], 'ms', s.elapsed_time(e))
 for i, name in enumerate(['build items (f64 canonicalise)', 'network wave',
                           'events + finalise', 'compaction']):
   print('%-32s %5.1f%%  %.0f cycles/CTA' % (name, 100 * t[i] / t[:4].sum(),
