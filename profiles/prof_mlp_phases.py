@@ -41,3 +41,11 @@ for i, name in enumerate(['build items (f64 canonicalise)', 'network wave',
                           'events + finalise', 'compaction']):
   print('%-32s %5.1f%%  %.0f cycles/CTA' % (name, 100 * t[i] / t[:4].sum(),
                                             t[i] / 148))
+if tc:
+  w_tot = t[8:12].sum()
+  for i, name in zip(range(8, 12), ['operands (h1 split, W1 copy)',
+                                    'MMA issue + wait',
+                                    'epilogue (tcgen05.ld, bias, swish, W2)',
+                                    'head reduction + softplus']):
+    print('  wave: %-38s %5.1f%%  %.0f cycles/CTA' %
+          (name, 100 * t[i] / max(w_tot, 1), t[i] / 148))

@@ -39,8 +39,20 @@ __device__ unsigned long long g_mlp_phase[16];
       ph_t0 = now_;                                             \
     }                                                           \
   } while (0)
+// ... and inside the tensor-core wave (slots 8..11: operand generation, MMA
+// issue + wait, epilogue, head reduction)
+#define PD_MLP_SUB(i)                                           \
+  do {                                                          \
+    if (threadIdx.x == 0) {                                     \
+      const long long now_ = clock64();                         \
+      atomicAdd(&g_mlp_phase[i],                                \
+                static_cast<unsigned long long>(now_ - sub_t0)); \
+      sub_t0 = now_;                                            \
+    }                                                           \
+  } while (0)
 #else
 #define PD_MLP_PHASE(i) do { } while (0)
+#define PD_MLP_SUB(i) do { } while (0)
 #endif
 
 constexpr int kMlpThreads = 512;
@@ -66,7 +78,12 @@ __device__ __forceinline__ float swishf(float z) {
 // Tensor-core path only: operands are rounded to bf16 anyway, so the
 // activations use the SFU approximations (ex2 / rcp, ~2^-21 relative).
 __device__ __forceinline__ float swish_fast(float z) {
-  return __fdividef(z, 1.0f + __expf(-z));
+  // z / (1 + 2^(-z log2 e)): five instructions (the library forms of __expf /
+  // __fdividef carry range fix-ups worth another six)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return z * r;
 }
 
 __device__ __forceinline__ float softplusf(float z) {
@@ -373,6 +390,9 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
   const bool split = w.tensor_core == 2;
   const uint32_t tmem = tc.ts->tmem_base;
+#ifdef PD_MLP_PHASE_CLOCKS
+  long long sub_t0 = clock64();
+#endif
   // (streamed W1: a wave starts with the part of K the previous wave ended
   // with, whose tiles are still there -- one copy per wave instead of two)
   const int first_part = tc.b_part >= 0 ? tc.b_part : 0;
@@ -388,8 +408,11 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
                            static_cast<size_t>(t) * w.h1 * w.h2 * 2 / 16;
         uint4* dst = reinterpret_cast<uint4*>(
             tc.a_tile + (split ? 2 : 1) * tc.a_bytes + t * tc.b_bytes);
+        const int pg_shift = 31 - __clz(per_group);
+        const bool pg_pow2 = (per_group & (per_group - 1)) == 0;
         for (int i = tid; i < n_units; i += kMlpThreads) {
-          const int g = i / per_group, j = i - g * per_group;
+          const int g = pg_pow2 ? i >> pg_shift : i / per_group;
+          const int j = i - g * per_group;
           // (cp.async: the copy lands while this thread generates h1 below)
           asm volatile(
               "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
@@ -410,8 +433,11 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
       const int n_cells = 16 * wcols;
       int cur_wc = -1;
       float w0a[8], w0b[8], b0v[8];
+      const int wc_shift = 31 - __clz(wcols);
+      const bool wc_pow2 = (wcols & (wcols - 1)) == 0;
       for (int cell = warp; cell < n_cells; cell += kMlpThreads / 32) {
-        const int wc = cell % wcols, g = cell / wcols;
+        const int g = wc_pow2 ? cell >> wc_shift : cell / wcols;
+        const int wc = cell - g * wcols;
         const int kb = wc * 4 + kb_lo;           // within this part of K
         const int kcol = (ph * kblocks + kb) * 8;  // column of W0 / b0
         if (wc != cur_wc) {
@@ -459,6 +485,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
     asm volatile("fence.proxy.async.shared::cta;");
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    PD_MLP_SUB(8);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t idesc = split ? umma_idesc_f16(kMlpBatch, w.h2)
@@ -509,6 +536,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
       tc.phase ^= 1u;
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
+    PD_MLP_SUB(9);
   }
   // ---- epilogue: thread = TMEM lane = env row; up to four column slices ----
   const int n_slices = (w.h2 >> 4) < 4 ? (w.h2 >> 4) : 4;
@@ -551,6 +579,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+  PD_MLP_SUB(10);
   if (tid < kMlpBatch) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -560,6 +589,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
     }
   }
   __syncthreads();
+  PD_MLP_SUB(11);
 }
 
 // Shared-memory carve-up of the tensor-core kernels (dynamic, 1 KB aligned).
