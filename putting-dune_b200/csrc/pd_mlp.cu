@@ -580,13 +580,13 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   PD_MLP_SUB(10);
-  if (tid < kMlpBatch) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float acc = sh.b2[q];
-      for (int sl = 0; sl < n_slices; ++sl) acc += tc.ts->partial[sl][tid][q];
-      sh.out[tid][q] = softplusf(acc);
-    }
+  // (one head per thread: 128 envs x 4 heads = the CTA's 512 threads)
+  static_assert(kMlpBatch * 4 == kMlpThreads, "one head per thread");
+  {
+    const int m = tid >> 2, q = tid & 3;
+    float acc = sh.b2[q];
+    for (int sl = 0; sl < n_slices; ++sl) acc += tc.ts->partial[sl][m][q];
+    sh.out[m][q] = softplusf(acc);
   }
   __syncthreads();
   PD_MLP_SUB(11);
