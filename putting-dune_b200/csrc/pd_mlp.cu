@@ -609,29 +609,18 @@ struct Canonical {
   int head[3];
 };
 
-__device__ __forceinline__ Canonical canonicalise(const double2 beam,
-                                                  const double2 psi,
-                                                  const double2 pn[3]) {
+// The reference's own formulation (atan2 / sincos / fmod), kept for geometries
+// where the shortcut below cannot order the neighbours safely.
+__device__ __noinline__ Canonical canonicalise_by_angles(
+    const double bx, const double by, const double nx0, const double ny0,
+    const double nx1, const double ny1, const double nx2, const double ny2,
+    const int k) {
   const double kTwoPi = 6.283185307179586;
-  double nx[3], ny[3], ang[3];
-  // beam in bond lengths, neighbours in angstroms (learn_rates.py:952-955:
-  // the reference's unit mix, SURVEY appendix B.2).
-  const double bx = (beam.x - psi.x) / kBond, by = (beam.y - psi.y) / kBond;
-  int k = 0;
-  double best = 0.0;
+  const double nx[3] = {nx0, nx1, nx2}, ny[3] = {ny0, ny1, ny2};
+  double ang[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    nx[i] = pn[i].x - psi.x;
-    ny[i] = pn[i].y - psi.y;
-    const double dx = nx[i] - bx, dy = ny[i] - by;
-    const double dist = sqrt(dx * dx + dy * dy);
-    if (i == 0 || dist < best) {
-      best = dist;
-      k = i;
-    }
-    ang[i] = atan2(ny[i], nx[i]);
-  }
-  const double rot = -ang[k];
+  for (int i = 0; i < 3; ++i) ang[i] = atan2(ny[i], nx[i]);
+  const double rot = -(k == 0 ? ang[0] : (k == 1 ? ang[1] : ang[2]));
   double s, c;
   sincos(rot, &s, &c);
   Canonical out;
@@ -654,6 +643,60 @@ __device__ __forceinline__ Canonical canonicalise(const double2 beam,
       rank += (pos[j] < pos[i]) || (pos[j] == pos[i] && j < i);
     out.head[i] = rank;
   }
+  return out;
+}
+
+// The rotation by -atan2(n_k) is the unit vector of n_k itself, and the
+// argsort of the rotated angles only asks on which side of n_k the other two
+// neighbours lie; on a honeycomb lattice they sit near +-120 degrees, so two
+// cross products decide it.  cos/sin taken this way differ from
+// sincos(atan2(.)) by an ulp or two of float64, i.e. the float32 network
+// input is the same number except on a rounding tie (~1e-8 of the inputs);
+// when the two neighbours are not clearly on opposite sides the angle form
+// above runs instead.
+__device__ __forceinline__ Canonical canonicalise(const double2 beam,
+                                                  const double2 psi,
+                                                  const double2 pn[3]) {
+  double nx[3], ny[3];
+  // beam in bond lengths, neighbours in angstroms (learn_rates.py:952-955:
+  // the reference's unit mix, SURVEY appendix B.2).
+  const double bx = (beam.x - psi.x) / kBond, by = (beam.y - psi.y) / kBond;
+  int k = 0;
+  double best = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    nx[i] = pn[i].x - psi.x;
+    ny[i] = pn[i].y - psi.y;
+    const double dx = nx[i] - bx, dy = ny[i] - by;
+    const double dist = sqrt(dx * dx + dy * dy);
+    if (i == 0 || dist < best) {
+      best = dist;
+      k = i;
+    }
+  }
+  const double kx = k == 0 ? nx[0] : (k == 1 ? nx[1] : nx[2]);
+  const double ky = k == 0 ? ny[0] : (k == 1 ? ny[1] : ny[2]);
+  // the other two, in index order
+  const double px = k == 0 ? nx[1] : nx[0], py = k == 0 ? ny[1] : ny[0];
+  const double qx = k == 2 ? nx[1] : nx[2], qy = k == 2 ? ny[1] : ny[2];
+  const double len2 = kx * kx + ky * ky;
+  const double cp = kx * py - ky * px, cq = kx * qy - ky * qx;
+  // sin(120 deg) |n|^2 = 0.87 len2 on the undistorted lattice
+  const double margin = 0.05 * len2;
+  const bool p_first = cp > margin && cq < -margin;
+  const bool q_first = cq > margin && cp < -margin;
+  if (!(p_first || q_first) || !(len2 > 0.0))
+    return canonicalise_by_angles(bx, by, nx[0], ny[0], nx[1], ny[1], nx[2],
+                                  ny[2], k);
+  const double inv = 1.0 / sqrt(len2);
+  const double c = kx * inv, s = -ky * inv;
+  Canonical out;
+  out.x0 = static_cast<float>(bx * c - by * s);
+  out.x1 = static_cast<float>(bx * s + by * c);
+  const int hp = p_first ? 1 : 2, hq = p_first ? 2 : 1;
+  out.head[0] = k == 0 ? 0 : hp;                   // p is index 0 unless k == 0
+  out.head[1] = k == 1 ? 0 : (k == 0 ? hp : hq);   // index 1: p if k==0, q if k==2
+  out.head[2] = k == 2 ? 0 : hq;                   // q is index 2 unless k == 2
   return out;
 }
 

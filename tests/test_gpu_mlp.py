@@ -47,6 +47,33 @@ def test_learned_rates_match_oracle(hidden):
   assert np.abs(gh.np_(r) - want).max() <= _tol(want)
 
 
+def test_learned_rates_match_oracle_on_every_site():
+  """The frame canonicalisation takes a cross-product shortcut where the two
+  far neighbours lie clearly on opposite sides of the nearest one and the
+  reference's atan2 / argsort form elsewhere (sheet-edge sites, whose three
+  nearest atoms are not at 120 degrees): every site of the sheet, several
+  beams each, against the oracle's atan2 form."""
+  st0 = po.make_state(1, 0)
+  n_sites = st0.nbr.shape[0]
+  reps = 6
+  n = n_sites * reps
+  st = po.make_state(n, 21)
+  po.reset(st)
+  st.si_idx[:] = np.tile(np.arange(n_sites), reps)
+  mlp = po.MlpParams.synthetic(4, hidden=(64, 64))
+  rng = np.random.default_rng(8)
+  mlp.b2 = rng.normal(0, 0.3, 4).astype(np.float32)
+  beam = po.site_positions(st, st.si_idx, np.arange(n)) + rng.uniform(
+      -3.0, 3.0, size=(n, 2))
+  # beams almost on a neighbour and almost on the Si atom itself
+  beam[::7] = po.site_positions(st, st.si_idx, np.arange(n))[::7] + 1e-9
+  b = gh.batch_from_oracle(st)
+  r, nb = b.rates(beam, gh.rate_spec(po.RATE_LEARNED, mlp))
+  want, nbr = po.rates_for(st, np.arange(n), beam, po.RATE_LEARNED, mlp)
+  np.testing.assert_array_equal(gh.np_(nb), nbr)
+  assert np.abs(gh.np_(r) - want).max() <= _tol(want)
+
+
 def test_learned_rates_match_reference_predict(golden_dir):
   """rates_reference.npz: the reference's own predict() body around the
   NumPy network."""
