@@ -49,3 +49,8 @@ if tc:
                                     'head reduction + softplus']):
     print('  wave: %-38s %5.1f%%  %.0f cycles/CTA' %
           (name, 100 * t[i] / max(w_tot, 1), t[i] / 148))
+e_tot = t[12:16].sum()
+for i, name in zip(range(12, 16), ['rates + ctrl_count + Philox', 'kmc_event',
+                                   'hop bookkeeping', 'finalise']):
+  print('  events (warp 0): %-28s %5.1f%%  %.0f cycles/CTA' %
+        (name, 100 * t[i] / max(e_tot, 1), t[i] / 148))

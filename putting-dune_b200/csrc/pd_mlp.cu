@@ -50,9 +50,21 @@ __device__ unsigned long long g_mlp_phase[16];
       sub_t0 = now_;                                            \
     }                                                           \
   } while (0)
+// ... and inside the event phase (slots 12..15: rates + Philox, event draw,
+// hop bookkeeping, finalise), on warp 0's own timeline
+#define PD_MLP_EV(i)                                            \
+  do {                                                          \
+    if (threadIdx.x == 0) {                                     \
+      const long long now_ = clock64();                         \
+      atomicAdd(&g_mlp_phase[i],                                \
+                static_cast<unsigned long long>(now_ - ev_t0)); \
+      ev_t0 = now_;                                             \
+    }                                                           \
+  } while (0)
 #else
 #define PD_MLP_PHASE(i) do { } while (0)
 #define PD_MLP_SUB(i) do { } while (0)
+#define PD_MLP_EV(i) do { } while (0)
 #endif
 
 constexpr int kMlpThreads = 512;
@@ -707,6 +719,11 @@ struct MlpStepSharedT {
   uint32_t q_it[kMlpBatch];
   long long q_elapsed[kMlpBatch], q_total[kMlpBatch];
   int q_ev[kMlpBatch], q_tr[kMlpBatch], q_logn[kMlpBatch];
+  uint32_t q_cc[kMlpBatch];
+  // Philox key of each item's next event (written by the owner) and the two
+  // variates drawn from it by a helper thread while the owner canonicalises
+  double k_draw[kMlpBatch], k_choice[kMlpBatch];
+  uint32_t k_env[kMlpBatch], k_seq[kMlpBatch], k_it[kMlpBatch];
   int warp_cnt[kMlpThreads / 32];
   int q_count;
 };
@@ -769,7 +786,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     if (n_act == 0) break;
     // ---- build items (threads 0..n_act-1 own one item each) ----
     int env = 0, ctl = 0, si = 0, ev = 0, tr = 0, logn = 0;
-    uint32_t it = 0;
+    uint32_t it = 0, cc = 0;  // cc: the env's control counter at launch
     long long elapsed = 0, total = 0, dwell = 0;
     int nb[3] = {0, 0, 0};
     double2 pn[3];
@@ -785,10 +802,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         env = sh.q_env[tid]; ctl = sh.q_ctl[tid]; si = sh.q_si[tid];
         it = sh.q_it[tid]; elapsed = sh.q_elapsed[tid];
         total = sh.q_total[tid]; ev = sh.q_ev[tid]; tr = sh.q_tr[tid];
-        logn = sh.q_logn[tid];
+        logn = sh.q_logn[tid]; cc = sh.q_cc[tid];
       } else {
         env = static_cast<int>(cursor + (tid - n_pending));
         si = a.st.si_idx[env];
+        cc = a.st.ctrl_count[env];
       }
       skipped = a.skip && a.skip[env];
       lt = load_lattice4(a.st.lattice, env);
@@ -811,6 +829,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         elapsed = 0;
         it = 0;
       }
+    }
+    // The event's random variates depend on (env, control, iteration) only:
+    // threads 128..255 draw them (Philox + the float64 log) while the owners
+    // run the geometry below.
+    if (tid < kMlpBatch) {
+      sh.k_it[tid] = need_eval ? it : 0xFFFFFFFFu;
+      sh.k_env[tid] = static_cast<uint32_t>(env);
+      sh.k_seq[tid] = cc + static_cast<uint32_t>(ctl);
+    }
+    __syncthreads();
+    if (tid >= kMlpBatch && tid < 2 * kMlpBatch) {
+      const int m = tid - kMlpBatch;
+      const uint32_t k_it = sh.k_it[m];
+      if (k_it != 0xFFFFFFFFu) {
+        const uint4 pw = philox4x32_10(a.st.env_offset + sh.k_env[m],
+                                       sh.k_seq[m], k_it, PD_STREAM_KMC,
+                                       a.st.seed);
+        sh.k_draw[m] = -log1p(-u53(pw.x, pw.y));
+        sh.k_choice[m] = u53(pw.z, pw.w);
+      }
+    }
+    if (own && !skipped) {
       psi = site_position(__ldg(base + si), lt);
       if (need_eval) {
         const double2 c2 = reinterpret_cast<const double2*>(
@@ -841,19 +881,32 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     PD_MLP_PHASE(1);
     // ---- events ----
     bool survive = false;
+#ifdef PD_MLP_PHASE_CLOCKS
+    long long ev_t0 = clock64();
+#endif
     if (own) {
+      // the env's counters, asked for now so that they are here when an env
+      // finalises below (loads issued after the first store there would
+      // queue up behind one another: the pointers may alias)
+      long long st_time = 0;
+      int st_events = 0, st_transitions = 0;
+      double st_scale = 0.0;
+      if (!skipped) {
+        st_time = a.st.sim_time_us[env];
+        st_events = a.st.n_events[env];
+        st_transitions = a.st.n_transitions[env];
+        st_scale = a.st.fov_scale[env];
+      }
       if (need_eval) {
         float r[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] = sh.m.out[tid][can.head[i]];
-        const uint32_t seq = a.st.ctrl_count[env] + static_cast<uint32_t>(ctl);
-        const uint4 pw = philox4x32_10(
-            a.st.env_offset + static_cast<uint32_t>(env), seq, it,
-            PD_STREAM_KMC, a.st.seed);
+        PD_MLP_EV(12);
         int slot = 0;
         bool bad = false;
-        const bool hit = kmc_event(r, u53(pw.x, pw.y), u53(pw.z, pw.w), dwell,
-                                   &elapsed, &slot, &bad);
+        const bool hit = kmc_event_drawn(r, sh.k_draw[tid], sh.k_choice[tid],
+                                         dwell, &elapsed, &slot, &bad);
+        PD_MLP_EV(13);
         if (bad) a.st.status[env] |= PD_ENV_BAD_RATE;
         ++ev;
         ++it;
@@ -881,22 +934,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         }
         survive = ctl < a.n_controls;
       }
+      PD_MLP_EV(14);
       if (!survive && !skipped) {
         // ---- finalise the env: simulator.py:152-169 ----
         uint8_t recentred = 0;
         if (!a.material_frame) {
           total += a.image_duration_us;
           if (silicon_outside_safe_area(fov, psi)) {
-            store_fov4(a.st.fov, env, centred_fov(psi, a.st.fov_scale[env]));
+            store_fov4(a.st.fov, env, centred_fov(psi, st_scale));
             total += a.image_duration_us;
             recentred = 1;
           }
-          a.st.sim_time_us[env] += total;
+          a.st.sim_time_us[env] = st_time + total;
         }
         a.st.si_idx[env] = si;
-        a.st.ctrl_count[env] += static_cast<uint32_t>(a.n_controls);
-        a.st.n_events[env] += ev;
-        a.st.n_transitions[env] += tr;
+        a.st.ctrl_count[env] = cc + static_cast<uint32_t>(a.n_controls);
+        a.st.n_events[env] = st_events + ev;
+        a.st.n_transitions[env] = st_transitions + tr;
         if (a.out.elapsed_us) a.out.elapsed_us[env] = total;
         if (a.out.transitions) a.out.transitions[env] = tr;
         if (a.out.events) a.out.events[env] = ev;
@@ -904,6 +958,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
         if (a.out.si_xy) reinterpret_cast<double2*>(a.out.si_xy)[env] = psi;
         if (a.out.log_count) a.out.log_count[env] = logn;
       }
+      PD_MLP_EV(15);
     }
     // ---- ordered compaction of the survivors into the queue ----
     const unsigned bal = __ballot_sync(0xffffffffu, survive);
@@ -919,6 +974,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
       sh.q_env[pos] = env; sh.q_ctl[pos] = ctl; sh.q_si[pos] = si;
       sh.q_it[pos] = it; sh.q_elapsed[pos] = elapsed; sh.q_total[pos] = total;
       sh.q_ev[pos] = ev; sh.q_tr[pos] = tr; sh.q_logn[pos] = logn;
+      sh.q_cc[pos] = cc;
     }
     cursor += n_fresh;
     __syncthreads();
