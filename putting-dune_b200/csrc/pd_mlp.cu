@@ -965,10 +965,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
     __syncthreads();
     PD_MLP_PHASE(2);
-    int offset = 0;
-    for (int w2 = 0; w2 < warp; ++w2) offset += sh.warp_cnt[w2];
-    int total_surv = 0;
-    for (int w2 = 0; w2 < kMlpThreads / 32; ++w2) total_surv += sh.warp_cnt[w2];
+    // only the owners' warps (the first kMlpBatch / 32) hold survivors
+    int offset = 0, total_surv = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kMlpBatch / 32; ++w2) {
+      const int c = sh.warp_cnt[w2];
+      offset += w2 < warp ? c : 0;
+      total_surv += c;
+    }
+    // every thread read q_count at the top of the loop, barriers ago
+    if (tid == 0) sh.q_count = total_surv;
     if (survive) {
       const int pos = offset + __popc(bal & ((1u << lane) - 1u));
       sh.q_env[pos] = env; sh.q_ctl[pos] = ctl; sh.q_si[pos] = si;
@@ -977,8 +983,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
       sh.q_cc[pos] = cc;
     }
     cursor += n_fresh;
-    __syncthreads();
-    if (tid == 0) sh.q_count = total_surv;
     __syncthreads();
     PD_MLP_PHASE(3);
   }
