@@ -320,16 +320,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// x = hi + lo in fp16: (a, b) -> the packed hi pair and the packed lo pair
+// x = hi + lo in fp16: (a, b) -> the packed hi pair and the packed lo pair.
+// Packed conversions (F2FP on the ALU pipe): the scalar cvt.rn.f16.f32 is an
+// F2F on the same quarter-rate unit as the wave's ex2 / rcp.
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t* hi,
                                             uint32_t* lo) {
-  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-  const __half al = __float2half_rn(a - __half2float(ah));
-  const __half bl = __float2half_rn(b - __half2float(bh));
-  *hi = static_cast<uint32_t>(__half_as_ushort(ah)) |
-        (static_cast<uint32_t>(__half_as_ushort(bh)) << 16);
-  *lo = static_cast<uint32_t>(__half_as_ushort(al)) |
-        (static_cast<uint32_t>(__half_as_ushort(bl)) << 16);
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));  // a: low
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  uint32_t l;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - back.y),
+      "f"(a - back.x));
+  *hi = h;
+  *lo = l;
 }
 
 struct TcCtx {
