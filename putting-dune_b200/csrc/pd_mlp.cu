@@ -87,15 +87,26 @@ __device__ __forceinline__ float swishf(float z) {
   return z / (1.0f + expf(-z));
 }
 
-// Tensor-core path only: operands are rounded to bf16 anyway, so the
-// activations use the SFU approximations (ex2 / rcp, ~2^-21 relative).
-__device__ __forceinline__ float swish_fast(float z) {
-  // z / (1 + 2^(-z log2 e)): five instructions (the library forms of __expf /
-  // __fdividef carry range fix-ups worth another six)
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return z * r;
+// Tensor-core paths only: the activations use the SFU approximations (ex2 /
+// rcp, ~2^-21 relative) as z / (1 + 2^(-z log2 e)); the library forms of
+// __expf / __fdividef carry range fix-ups worth another six instructions.
+// Two at a time with one reciprocal: 1/a = b / (a b), 1/b = a / (a b).  The
+// wave is bound by the MUFU unit (ex2 + rcp per activation, a quarter-rate
+// pipe); this trades one MUFU per pair for three multiplies.  The exponent is
+// capped at 60 so that the product stays finite: below z = -41.6 the result
+// is z 2^-60 instead of z 2^(z log2 e), both zero at float32 resolution of
+// anything they are added to.
+__device__ __forceinline__ void swish_fast2(float z0, float z1, float* s0,
+                                            float* s1) {
+  float e0, e1, r;
+  asm("ex2.approx.ftz.f32 %0, %1;"
+      : "=f"(e0) : "f"(fminf(z0 * -1.4426950408889634f, 60.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;"
+      : "=f"(e1) : "f"(fminf(z1 * -1.4426950408889634f, 60.f)));
+  const float a = 1.0f + e0, b = 1.0f + e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a * b));
+  *s0 = z0 * (r * b);
+  *s1 = z1 * (r * a);
 }
 
 __device__ __forceinline__ float softplusf(float z) {
@@ -473,8 +484,10 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
             tc.a_tile + static_cast<size_t>(g) * sbo + kb * 128 + m8 * 16;
         if (split) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+          for (int j = 0; j < 8; j += 2)
+            swish_fast2(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])),
+                        fmaf(x1, w0b[j + 1], fmaf(x0, w0a[j + 1], b0v[j + 1])),
+                        &h[j], &h[j + 1]);
           uint4 vh, vl;
           split_f16x2(h[0], h[1], &vh.x, &vl.x);
           split_f16x2(h[2], h[3], &vh.y, &vl.y);
@@ -484,8 +497,10 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
           *reinterpret_cast<uint4*>(cell_p + tc.a_bytes) = vl;
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            h[j] = swish_fast(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])));
+          for (int j = 0; j < 8; j += 2)
+            swish_fast2(fmaf(x1, w0b[j], fmaf(x0, w0a[j], b0v[j])),
+                        fmaf(x1, w0b[j + 1], fmaf(x0, w0a[j + 1], b0v[j + 1])),
+                        &h[j], &h[j + 1]);
           uint4 v;
           v.x = pack_bf16x2(h[0], h[1]);
           v.y = pack_bf16x2(h[2], h[3]);
@@ -577,15 +592,21 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; j += 2) {
           const int col = c0 + j;
-          const float z = __uint_as_float(r[j]) + sh.b1[col];
-          const float hh = swish_fast(z);
-          const float4 w2v = *reinterpret_cast<const float4*>(sh.w2[col]);
-          o[0] = fmaf(hh, w2v.x, o[0]);
-          o[1] = fmaf(hh, w2v.y, o[1]);
-          o[2] = fmaf(hh, w2v.z, o[2]);
-          o[3] = fmaf(hh, w2v.w, o[3]);
+          float hh[2];
+          swish_fast2(__uint_as_float(r[j]) + sh.b1[col],
+                      __uint_as_float(r[j + 1]) + sh.b1[col + 1], &hh[0],
+                      &hh[1]);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const float4 w2v =
+                *reinterpret_cast<const float4*>(sh.w2[col + t]);
+            o[0] = fmaf(hh[t], w2v.x, o[0]);
+            o[1] = fmaf(hh[t], w2v.y, o[1]);
+            o[2] = fmaf(hh[t], w2v.z, o[2]);
+            o[3] = fmaf(hh[t], w2v.w, o[3]);
+          }
         }
       }
 #pragma unroll
