@@ -469,6 +469,10 @@ __device__ __forceinline__ double2 ld_relaxed_d2(const double2* p) {
 // An element has arrived only when NEITHER of its words holds the fill pattern
 // any more (a half-landed element must not be consumed); real data with that
 // pattern in one word is settled by `copy_done`.
+// Bound on the polls of the streamed rollout (~15 s of 100 ns sleeps; the
+// writers sleep 300 ns and use a quarter of it): beyond it the launch traps.
+constexpr unsigned kStreamPollBound = 1u << 27;
+
 __device__ __forceinline__ bool action_missing(const double2 v) {
   return __double_as_longlong(v.x) == -1LL || __double_as_longlong(v.y) == -1LL;
 }
@@ -570,7 +574,11 @@ __device__ __forceinline__ void stream_write(const StreamCopyArgs& a,
       for (int k = 0; k < kInFlight; ++k)
         if (base + k * kStepThreads + threadIdx.x < lim) pending |= 1u << k;
       const unsigned mine = pending;
-      for (;;) {
+      for (unsigned polls = 0u;; ++polls) {
+        // (results come from the stepping CTAs of this launch: if none can
+        // become resident -- an SM limit at or below copy_sms -- this ends
+        // the launch with an error instead of spinning for ever)
+        if (polls > kStreamPollBound / 4u) __trap();
 #pragma unroll
         for (int k = 0; k < kInFlight; ++k)
           if (pending >> k & 1u) {
@@ -620,7 +628,10 @@ __global__ void __launch_bounds__(kStepThreads)
         r = k < static_cast<uint32_t>(a.copy_sms) ? 2u : 3u;
         atomicExch(role_p, r);
       } else {
-        while (r == 1u) r = *reinterpret_cast<volatile uint32_t*>(role_p);
+        for (unsigned polls = 0u; r == 1u; ++polls) {
+          if (polls > kStreamPollBound) __trap();
+          r = *reinterpret_cast<volatile uint32_t*>(role_p);
+        }
       }
       s_slot[1] = r == 2u ? atomicAdd(a.sm_ctl + kCtlCopyIdx, 1u) : ~0u;
     }
@@ -691,6 +702,7 @@ __global__ void __launch_bounds__(kStepThreads)
 #pragma unroll
     for (int i = 0; i < 3; ++i) geo.cx[i] = geo.cy[i] = 0.f;
     float qfx = 0.f, qfy = 0.f, wfx = 1.f, wfy = 1.f;
+    unsigned stalled = 0u;  // STREAM: consecutive polls without an action
 
     if constexpr (STREAM == 0) {
       if (j < n_steps) prefetch_l1(ctl + static_cast<int64_t>(j) * n + e);
@@ -764,9 +776,13 @@ __global__ void __launch_bounds__(kStepThreads)
         valid = valid && ((keep >> j) & 1u);
         if (!(vm & keep & 1u)) {
           // not even the current step is there: the copy front is behind us
+          // (bounded: a copy that never arrives ends the launch with an
+          // error the host sees, not with a hung device)
+          if (++stalled > kStreamPollBound) __trap();
           __nanosleep(100);
           continue;
         }
+        stalled = 0u;
       }
       bool certain = false;
       uint4 w = make_uint4(0u, 0u, 0u, 0u);  // Philox words of this lane's
