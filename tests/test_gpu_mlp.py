@@ -91,6 +91,24 @@ def test_learned_rates_match_reference_predict(golden_dir):
       fix['rates_learned'])
 
 
+def test_tensor_core_split_matches_reference_predict(golden_dir):
+  """The same golden through the tcgen05 fp16 hi + lo path (what
+  LearnedTransitionRatePredictor(tensor_core='auto') selects for 32 x 32)."""
+  from putting_dune_b200 import engine
+  fix = np.load(os.path.join(golden_dir, 'rates_reference.npz'))
+  n = fix['beam'].shape[0]
+  st = po.make_state(n, int(fix['seed']))
+  po.reset(st)
+  w = engine.MlpWeights(**{k: fix[f'mlp_{k}'] for k in
+                           engine.MlpWeights.NAMES})
+  b = gh.batch_from_oracle(st)
+  r, nb = b.rates(fix['beam'], engine.RateSpec(po.RATE_LEARNED, mlp=w,
+                                               tensor_core=2))
+  np.testing.assert_array_equal(gh.np_(nb), fix['succ_learned'])
+  assert np.abs(gh.np_(r) - fix['rates_learned']).max() <= _tol(
+      fix['rates_learned'])
+
+
 def test_learned_step_event_machinery_is_exact():
   """With the oracle fed the device's own rates, the learned-rate step must
   reproduce sites, counters and the transition log bit-exactly."""
