@@ -190,6 +190,44 @@ def test_learned_step_close_to_independent_oracle():
   assert st.n_transitions.sum() > 1000
 
 
+@pytest.mark.parametrize('tensor_core', [0, 2])
+def test_learned_step_at_the_benchmarked_config(tensor_core):
+  """BASELINE configs[2] as bench.py's measure_mlp runs it: 65,536 envs, one
+  control of 1.5 s per step, beams near the frame centre, the 64 x 64 network
+  with the seeded synthetic weights -- three steps through the FP32 kernel
+  and through the tcgen05 fp16 hi + lo kernel against the oracle's float64
+  network.  A rate rounding difference (<= 2e-5 of the largest rate) changes
+  an event's outcome with ~1e-5, so of the ~8e5 events a handful of envs may
+  end elsewhere; every other env must agree in site, event count and clock."""
+  from putting_dune_b200 import engine
+  n, seed = 65536, 11
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(7, hidden=(64, 64))
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  spec = engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=tensor_core)
+  b = gh.batch_from_oracle(st)
+  rng = np.random.default_rng(0)
+  want_elapsed = np.zeros(n, dtype=np.int64)
+  got_elapsed = np.zeros(n, dtype=np.int64)
+  for _ in range(3):
+    ctl = 0.5 + rng.uniform(-1.0, 1.0, size=(n, 1, 2)) * (1.42 / 22.5)
+    o = po.step_and_image(st, ctl, 1500000, rate_fn=po.RATE_LEARNED, mlp=mlp)
+    out = b.step_and_image(ctl, 1500000, spec)
+    want_elapsed += o['elapsed_us']
+    got_elapsed += gh.np_(out.elapsed_us)
+  same = gh.np_(b.si_idx) == st.si_idx
+  n_diff = int((~same).sum())
+  print(f'tensor_core {tensor_core}: {n_diff} of {n} envs end elsewhere, '
+        f'{int(st.n_events.sum())} events')
+  assert n_diff <= 12, n_diff
+  np.testing.assert_array_equal(gh.np_(b.n_events)[same], st.n_events[same])
+  np.testing.assert_array_equal(got_elapsed[same], want_elapsed[same])
+  assert st.n_events.sum() > 5e5 and st.n_transitions.sum() > 1e4
+  assert not (gh.np_(b.status) & 1).any()
+
+
 def test_apply_model_ensemble():
   from putting_dune_b200 import engine
   from putting_dune_b200.rate_learning import learn_rates
