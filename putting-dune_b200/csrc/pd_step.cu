@@ -466,13 +466,13 @@ __device__ __forceinline__ double2 ld_relaxed_d2(const double2* p) {
                : "memory");
   return v;
 }
-// An element has arrived only when NEITHER of its words holds the fill pattern
-// any more (a half-landed element must not be consumed); real data with that
-// pattern in one word is settled by `copy_done`.
 // Bound on the polls of the streamed rollout (~15 s of 100 ns sleeps; the
 // writers sleep 300 ns and use a quarter of it): beyond it the launch traps.
 constexpr unsigned kStreamPollBound = 1u << 27;
 
+// An element has arrived only when NEITHER of its words holds the fill pattern
+// any more (a half-landed element must not be consumed); real data with that
+// pattern in one word is settled by `copy_done`.
 __device__ __forceinline__ bool action_missing(const double2 v) {
   return __double_as_longlong(v.x) == -1LL || __double_as_longlong(v.y) == -1LL;
 }
