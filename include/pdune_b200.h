@@ -405,6 +405,14 @@ int pd_set_fast_path(int enabled);
  *                                    k_walk_fast over the envs it hands over,
  *                                    instead of k_walk_fast alone; 2 = for
  *                                    every large batch (parity tests)
+ *   "mlp_slim"      PD_MLP_SLIM      (default 1) learned-rate step on the
+ *                                    tensor cores with 256 threads and two
+ *                                    CTAs per SM where two sets of operand
+ *                                    tiles fit in shared memory (H <= 64 in
+ *                                    the fp16 hi + lo form), so that one
+ *                                    CTA's item build / event phases run under
+ *                                    the other's wave; 0 = 512 threads, one
+ *                                    CTA per SM for every shape; same results
  *   "race_sampling" PD_SAMPLING_RACE (default 0) events by the race of
  *                                    competing exponentials -- each neighbour
  *                                    draws Exp(rate_i), the smallest wins --

@@ -19,6 +19,7 @@
 // FP32 FMA throughout (the parity path of BASELINE.json's north_star).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -411,6 +412,8 @@ __device__ __forceinline__ void tc_teardown(const MlpView& w, TcCtx& tc) {
 __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
                                             TcCtx& tc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // 512 threads (one CTA per SM) or 256 (two: see learned_step)
+  const int n_threads = blockDim.x, n_warps = n_threads >> 5;
   const int kblocks_all = w.h1 >> 3;      // 16-byte blocks along K
   const int kblocks = kblocks_all / w.tc_k_phases;  // ... of one part of K
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
@@ -436,7 +439,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
             tc.a_tile + (split ? 2 : 1) * tc.a_bytes + t * tc.b_bytes);
         const int pg_shift = 31 - __clz(per_group);
         const bool pg_pow2 = (per_group & (per_group - 1)) == 0;
-        for (int i = tid; i < n_units; i += kMlpThreads) {
+        for (int i = tid; i < n_units; i += n_threads) {
           const int g = pg_pow2 ? i >> pg_shift : i / per_group;
           const int j = i - g * per_group;
           // (cp.async: the copy lands while this thread generates h1 below)
@@ -461,7 +464,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
       float w0a[8], w0b[8], b0v[8];
       const int wc_shift = 31 - __clz(wcols);
       const bool wc_pow2 = (wcols & (wcols - 1)) == 0;
-      for (int cell = warp; cell < n_cells; cell += kMlpThreads / 32) {
+      for (int cell = warp; cell < n_cells; cell += n_warps) {
         const int g = wc_pow2 ? cell >> wc_shift : cell / wcols;
         const int wc = cell - g * wcols;
         const int kb = wc * 4 + kb_lo;           // within this part of K
@@ -568,12 +571,14 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
     asm volatile("tcgen05.fence::after_thread_sync;");
     PD_MLP_SUB(9);
   }
-  // ---- epilogue: thread = TMEM lane = env row; up to four column slices ----
+  // ---- epilogue: thread = TMEM lane = env row; up to four column slices,
+  // dealt to the groups of four warps (the slices, and with them the order of
+  // the float32 sums, are the same for 256 and 512 threads) ----
   const int n_slices = (w.h2 >> 4) < 4 ? (w.h2 >> 4) : 4;
   {
-    const int quarter = warp & 3, slice = warp >> 2;
+    const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    if (slice < n_slices) {
+    for (int slice = warp >> 2; slice < n_slices; slice += n_warps >> 2) {
       const int per = w.h2 / n_slices;
       const int c_lo = slice * per, c_hi = c_lo + per;
       float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -616,10 +621,9 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   PD_MLP_SUB(10);
-  // (one head per thread: 128 envs x 4 heads = the CTA's 512 threads)
-  static_assert(kMlpBatch * 4 == kMlpThreads, "one head per thread");
-  {
-    const int m = tid >> 2, q = tid & 3;
+  // (128 envs x 4 heads over the CTA's threads: one or two per thread)
+  for (int i = tid; i < kMlpBatch * 4; i += n_threads) {
+    const int m = i >> 2, q = i & 3;
     float acc = sh.b2[q];
     for (int sl = 0; sl < n_slices; ++sl) acc += tc.ts->partial[sl][m][q];
     sh.out[m][q] = softplusf(acc);
@@ -774,9 +778,16 @@ static size_t tc_smem_bytes(size_t used, int h1, int h2, int tiles,
          tc_b_bytes(h1 / k_phases, h2, tiles);
 }
 
-template <int NPT, bool TC>
-__global__ void __launch_bounds__(kMlpThreads, 1)
+// SLIM (tensor path, operand tiles <= ~100 KB): 256 threads and two CTAs per
+// SM, so that one CTA's float64 item build / event phases (four warps,
+// latency-bound) run under the other's wave.
+constexpr int kMlpSlimThreads = 256;
+template <int NPT, bool TC, bool SLIM = false>
+__global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
+                                  SLIM ? 2 : 1)
     k_step_learned(const StepArgs a, const MlpView w) {
+  static_assert(!SLIM || TC, "the slim form is a tensor-path form");
+  static_assert(kMlpSlimThreads >= 2 * kMlpBatch, "owners + variate helpers");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Shared = MlpStepSharedT<TC>;
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -1101,6 +1112,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
   }
 }
 
+// PD_MLP_SLIM=0 keeps the one-CTA-per-SM form of the tensor step for every
+// shape.  Default: two CTAs per SM where two sets of resident tiles fit.
+// (Streaming W1 to make two CTAs fit at H = 128 was measured: 0.225 ms
+// against 0.215 ms with one CTA and resident tiles.)
+int& option_mlp_slim() {
+  static int v = [] {
+    const char* e = getenv("PD_MLP_SLIM");
+    return e && e[0] == '0' ? 0 : 1;
+  }();
+  return v;
+}
+
 static int mlp_view(const pd_mlp* mlp, MlpView* v) {
   PD_REQUIRE(mlp != nullptr, "null pd_mlp");
   PD_REQUIRE(mlp->context_dim == 2,
@@ -1174,6 +1197,20 @@ int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
     const int smem = static_cast<int>(
         tc_smem_bytes(sizeof(MlpStepSharedT<true>), v.h1, v.h2,
                       v.tensor_core == 2 ? 2 : 1, v.tc_k_phases));
+    // two CTAs per SM when two sets of tiles fit (1 KB per CTA is reserved)
+    if (option_mlp_slim() && 2 * (smem + 1024) <= 228 * 1024) {
+      auto kern = k_step_learned<2, true, true>;
+      PD_CUDA_OK(cudaFuncSetAttribute(
+          kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      PD_CUDA_OK(cudaFuncSetAttribute(
+          kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+          cudaSharedmemCarveoutMaxShared));
+      const int grid2 = static_cast<int>(
+          tiles < 2 * sm_count() ? tiles : 2 * sm_count());
+      kern<<<grid2, kMlpSlimThreads, smem, stream>>>(a, v);
+      PD_CUDA_OK(cudaGetLastError());
+      return PD_OK;
+    }
     auto kern = k_step_learned<2, true>;
     PD_CUDA_OK(cudaFuncSetAttribute(
         kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

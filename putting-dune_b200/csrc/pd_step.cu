@@ -1992,6 +1992,7 @@ int validate_common(const pd_lattice* lat, const pd_state* st,
 }
 
 // Implemented in pd_mlp.cu.
+int& option_mlp_slim();
 int learned_step(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
                  const StepArgs& a, bool rollout, cudaStream_t stream);
 int learned_rates(const pd_lattice* lat, const pd_state* st, const pd_mlp* mlp,
@@ -2017,6 +2018,7 @@ extern "C" int pd_set_option(const char* name, int value) {
   if (!strcmp(name, "race_sampling")) slot = &pd::option_race_sampling();
   if (!strcmp(name, "plan")) slot = &pd::option_plan();
   if (!strcmp(name, "walk_plan")) slot = &pd::option_walk_plan();
+  if (!strcmp(name, "mlp_slim")) slot = &pd::option_mlp_slim();
   if (!slot) {
     pd::set_error("pd_set_option: unknown option '%s'", name);
     return PD_ERR_INVALID_ARGUMENT;

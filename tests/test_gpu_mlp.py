@@ -228,6 +228,47 @@ def test_learned_step_at_the_benchmarked_config(tensor_core):
   assert not (gh.np_(b.status) & 1).any()
 
 
+@pytest.mark.parametrize('tensor_core,hidden', [(2, (64, 64)), (2, (32, 64)),
+                                                (1, (128, 128))])
+def test_two_ctas_per_sm_form_is_the_same_computation(tensor_core, hidden):
+  """pd_set_option("mlp_slim"): 256 threads, two CTAs per SM (default where
+  two sets of tiles fit) against 512 threads, one CTA per SM -- identical
+  sites, counters, clocks and transition logs."""
+  from putting_dune_b200 import _native as nat
+  from putting_dune_b200 import engine
+  n, seed = 40000, 14
+  st = po.make_state(n, seed)
+  po.reset(st)
+  mlp = po.MlpParams.synthetic(3, hidden=hidden)
+  w = engine.MlpWeights(**{k: getattr(mlp, k) for k in
+                           engine.MlpWeights.NAMES})
+  spec = engine.RateSpec(po.RATE_LEARNED, mlp=w, tensor_core=tensor_core)
+  rng = np.random.default_rng(4)
+  ctl = [0.5 + rng.uniform(-1.0, 1.0, size=(n, 2, 2)) * (1.42 / 22.5)
+         for _ in range(3)]
+  dwell = rng.integers(0, 3000000, size=(n, 2))
+  dwell[::11, 1] = 0
+  res = []
+  try:
+    for slim in (1, 0):
+      assert nat.lib.pd_set_option(b'mlp_slim', slim) == 0
+      b = gh.batch_from_oracle(st, log_capacity=64)
+      outs = [b.step_and_image(c, dwell, spec) for c in ctl]
+      res.append([gh.np_(b.si_idx), gh.np_(b.n_events),
+                  gh.np_(b.n_transitions), gh.np_(b.sim_time_us),
+                  gh.np_(b.fov), gh.np_(b.status)] +
+                 [gh.np_(o.elapsed_us) for o in outs] +
+                 [gh.np_(outs[-1].log_count)] +
+                 [np.where(np.arange(64)[None, :] <
+                           gh.np_(outs[-1].log_count)[:, None], gh.np_(v), -1)
+                  for v in (outs[-1].log_site, outs[-1].log_elapsed_us)])
+  finally:
+    nat.lib.pd_set_option(b'mlp_slim', 1)
+  for x, y in zip(*res):
+    np.testing.assert_array_equal(x, y)
+  assert res[0][2].sum() > 1e5
+
+
 def test_apply_model_ensemble():
   from putting_dune_b200 import engine
   from putting_dune_b200.rate_learning import learn_rates
