@@ -522,10 +522,12 @@ def measure_mlp(pd, batch, dev, args):
             0: 'pd::k_step_learned (FP32 FMA, queue-batched GEMM, cp.async '
                'double-buffered W1 chunks; 512 threads)',
             1: 'pd::k_step_learned<TC> (tcgen05.mma kind::f16, BF16 '
-               'operands, FP32 accumulate in TMEM; 512 threads)',
+               'operands, FP32 accumulate in TMEM; two CTAs of 256 threads per '
+               'SM where two sets of tiles fit, else one of 512)',
             2: 'pd::k_step_learned<TC> (tcgen05.mma kind::f16, FP16 hi + lo '
                'operands, three MMAs per K step into one TMEM accumulator; '
-               'rates within 3e-7 of the FP32 path)'}[int(tensor_core)]}
+               'rates within 3e-7 of the FP32 path; two CTAs of 256 threads per SM '
+               'at H <= 64, else one of 512)'}[int(tensor_core)]}
   return out
 
 
