@@ -409,11 +409,12 @@ __device__ __forceinline__ void tc_teardown(const MlpView& w, TcCtx& tc) {
   }
 }
 
+template <int THREADS>
 __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
                                             TcCtx& tc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 512 threads (one CTA per SM) or 256 (two: see learned_step)
-  const int n_threads = blockDim.x, n_warps = n_threads >> 5;
+  constexpr int n_threads = THREADS, n_warps = THREADS >> 5;
   const int kblocks_all = w.h1 >> 3;      // 16-byte blocks along K
   const int kblocks = kblocks_all / w.tc_k_phases;  // ... of one part of K
   const uint32_t sbo = static_cast<uint32_t>(kblocks) * 128u;
@@ -578,7 +579,7 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
   {
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
-    for (int slice = warp >> 2; slice < n_slices; slice += n_warps >> 2) {
+    auto run_slice = [&](const int slice) {
       const int per = w.h2 / n_slices;
       const int c_lo = slice * per, c_hi = c_lo + per;
       float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -616,6 +617,12 @@ __device__ __forceinline__ void mlp_wave_tc(const MlpView& w, MlpSmall& sh,
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) tc.ts->partial[slice][m][q] = o[q];
+    };
+    if constexpr (n_warps >= 16) {
+      if ((warp >> 2) < n_slices) run_slice(warp >> 2);
+    } else {
+      for (int slice = warp >> 2; slice < n_slices; slice += n_warps >> 2)
+        run_slice(slice);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -909,7 +916,7 @@ __global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
     PD_MLP_PHASE(0);
     // ---- network for the whole batch ----
     if constexpr (TC) {
-      mlp_wave_tc(w, sh.m, tc);
+      mlp_wave_tc<SLIM ? kMlpSlimThreads : kMlpThreads>(w, sh.m, tc);
     } else {
       mlp_wave<NPT>(w, sh.m);
     }
@@ -1065,7 +1072,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
     }
     __syncthreads();
     if constexpr (TC) {
-      mlp_wave_tc(w, sh, tc);
+      mlp_wave_tc<kMlpThreads>(w, sh, tc);
     } else {
       mlp_wave<NPT>(w, sh);
     }
