@@ -54,3 +54,8 @@ for i, name in zip(range(12, 16), ['rates + ctrl_count + Philox', 'kmc_event',
                                    'hop bookkeeping', 'finalise']):
   print('  events (warp 0): %-28s %5.1f%%  %.0f cycles/CTA' %
         (name, 100 * t[i] / max(e_tot, 1), t[i] / 148))
+b_tot = t[4:8].sum()
+for i, name in zip(range(4, 8), ['state loads + dwell loop', 'key barrier',
+                                 'site / neighbour positions', 'canonicalise']):
+  print('  build (warp 0): %-28s %5.1f%%  %.0f cycles/CTA' %
+        (name, 100 * t[i] / max(b_tot, 1), t[i] / 148))

@@ -62,7 +62,19 @@ __device__ unsigned long long g_mlp_phase[16];
       ev_t0 = now_;                                             \
     }                                                           \
   } while (0)
+// ... and inside the item build (slots 4..7: state loads + dwell loop, key
+// hand-over barrier, positions of the Si and its neighbours, canonicalise)
+#define PD_MLP_BLD(i)                                            \
+  do {                                                           \
+    if (threadIdx.x == 0) {                                      \
+      const long long now_ = clock64();                          \
+      atomicAdd(&g_mlp_phase[i],                                 \
+                static_cast<unsigned long long>(now_ - bld_t0)); \
+      bld_t0 = now_;                                             \
+    }                                                            \
+  } while (0)
 #else
+#define PD_MLP_BLD(i) do { } while (0)
 #define PD_MLP_PHASE(i) do { } while (0)
 #define PD_MLP_SUB(i) do { } while (0)
 #define PD_MLP_EV(i) do { } while (0)
@@ -708,17 +720,34 @@ __device__ __forceinline__ Canonical canonicalise(const double2 beam,
   // beam in bond lengths, neighbours in angstroms (learn_rates.py:952-955:
   // the reference's unit mix).
   const double bx = (beam.x - psi.x) / kBond, by = (beam.y - psi.y) / kBond;
+  // nearest neighbour of the beam: first index of the smallest distance.
+  // Squared distances order like their roots unless two of them are within
+  // rounding of each other (the roots could then round to the same number,
+  // which the strict comparison resolves by index): the roots decide there.
   int k = 0;
-  double best = 0.0;
+  double best = 0.0, d2[3];
+  bool close_call = false;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     nx[i] = pn[i].x - psi.x;
     ny[i] = pn[i].y - psi.y;
     const double dx = nx[i] - bx, dy = ny[i] - by;
-    const double dist = sqrt(dx * dx + dy * dy);
-    if (i == 0 || dist < best) {
-      best = dist;
+    d2[i] = dx * dx + dy * dy;
+    if (i > 0) close_call |= fabs(d2[i] - best) <= 1e-15 * best;
+    if (i == 0 || d2[i] < best) {
+      best = d2[i];
       k = i;
+    }
+  }
+  if (close_call) {
+    k = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double dist = sqrt(d2[i]);
+      if (i == 0 || dist < best) {
+        best = dist;
+        k = i;
+      }
     }
   }
   const double kx = k == 0 ? nx[0] : (k == 1 ? nx[1] : nx[2]);
@@ -827,6 +856,9 @@ __global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
     const int n_act = n_pending + n_fresh;
     if (n_act == 0) break;
     // ---- build items (threads 0..n_act-1 own one item each) ----
+#ifdef PD_MLP_PHASE_CLOCKS
+    long long bld_t0 = clock64();
+#endif
     int env = 0, ctl = 0, si = 0, ev = 0, tr = 0, logn = 0;
     uint32_t it = 0, cc = 0;  // cc: the env's control counter at launch
     long long elapsed = 0, total = 0, dwell = 0;
@@ -875,13 +907,17 @@ __global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
     // The event's random variates depend on (env, control, iteration) only:
     // threads 128..255 draw them (Philox + the float64 log) while the owners
     // run the geometry below.
+    PD_MLP_BLD(4);
+    // (named barrier 1: the four owner warps arrive and go on, the four
+    // helper warps wait for them; the other warps take no part)
     if (tid < kMlpBatch) {
       sh.k_it[tid] = need_eval ? it : 0xFFFFFFFFu;
       sh.k_env[tid] = static_cast<uint32_t>(env);
       sh.k_seq[tid] = cc + static_cast<uint32_t>(ctl);
-    }
-    __syncthreads();
-    if (tid >= kMlpBatch && tid < 2 * kMlpBatch) {
+      __threadfence_block();
+      asm volatile("bar.arrive 1, %0;" ::"n"(2 * kMlpBatch) : "memory");
+    } else if (tid < 2 * kMlpBatch) {
+      asm volatile("bar.sync 1, %0;" ::"n"(2 * kMlpBatch) : "memory");
       const int m = tid - kMlpBatch;
       const uint32_t k_it = sh.k_it[m];
       if (k_it != 0xFFFFFFFFu) {
@@ -892,6 +928,7 @@ __global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
         sh.k_choice[m] = u53(pw.z, pw.w);
       }
     }
+    PD_MLP_BLD(5);
     if (own && !skipped) {
       psi = site_position(__ldg(base + si), lt);
       if (need_eval) {
@@ -905,7 +942,9 @@ __global__ void __launch_bounds__(SLIM ? kMlpSlimThreads : kMlpThreads,
 #pragma unroll
         for (int i = 0; i < 3; ++i)
           pn[i] = site_position(__ldg(base + nb[i]), lt);
+        PD_MLP_BLD(6);
         can = canonicalise(beam, psi, pn);
+        PD_MLP_BLD(7);
       }
     }
     if (tid < kMlpBatch) {
